@@ -1,0 +1,216 @@
+"""Audio feature ops with the reference's names and signatures (audio_processing.py:9-184),
+computed by the fused sm_100a front-end kernels.
+
+Tensors are torch CUDA tensors instead of TF graph tensors; shapes, argument meaning and the
+millisecond -> sample conversion (``int(round(ms / 1e3 * sr))``, audio_processing.py:27-28) are
+the reference's.  ``fused_features`` is the one-launch path the models use; the individual
+functions exist for drop-in use (masking.py, audio_feat_preprocessing.py) and run the same
+kernel with different outputs enabled.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+
+NFFT = 512
+_tables = {}
+
+
+def ms_to_samples(ms, sample_rate):
+    return int(round(ms / 1e3 * sample_rate))
+
+
+def _device_tables(device, frame_len, hop=None):
+    key = (str(device), frame_len, hop)
+    tab = _tables.get(key)
+    if tab is None:
+        k = np.arange(frame_len, dtype=np.float64)
+        window = 0.5 - 0.5 * np.cos(2.0 * np.pi * k / frame_len)           # periodic Hann (tf.signal.hann_window)
+        m = np.arange(NFFT, dtype=np.float64)
+        tw = np.stack([np.cos(2.0 * np.pi * m / NFFT), -np.sin(2.0 * np.pi * m / NFFT)], axis=1)
+        tab = {'window': torch.tensor(window, dtype=torch.float32, device=device),
+               'twiddle': torch.tensor(tw, dtype=torch.float32, device=device).contiguous()}
+        if hop is not None:
+            # tf.contrib.signal.inverse_stft_window_fn(hop) for a Hann forward window
+            overlaps = -(-frame_len // hop)
+            denom = np.concatenate([window ** 2, np.zeros(overlaps * hop - frame_len)])
+            denom = np.tile(denom.reshape(overlaps, hop).sum(0, keepdims=True), (overlaps, 1)).reshape(-1)
+            tab['inv_window'] = torch.tensor(window / denom[:frame_len], dtype=torch.float32, device=device)
+        _tables[key] = tab
+    return tab
+
+
+def linear_to_mel_weight_matrix(num_mel_bins=80, num_spec_bins=257, sample_rate=16000,
+                                lower_edge_hertz=125.0, upper_edge_hertz=7600.0):
+    """tf.signal.linear_to_mel_weight_matrix: HTK mel scale, triangles linear in mel, DC row zero.
+    Host-side table construction in float64 (the projection itself runs in the kernel)."""
+    def hz_to_mel(f):
+        return 1127.0 * np.log1p(np.asarray(f, dtype=np.float64) / 700.0)
+    nyquist = sample_rate / 2.0
+    lin = np.linspace(0.0, nyquist, num_spec_bins)[1:]
+    spec_mel = hz_to_mel(lin)[:, None]
+    edges = np.linspace(hz_to_mel(lower_edge_hertz), hz_to_mel(upper_edge_hertz), num_mel_bins + 2)
+    lower, center, upper = edges[:-2][None], edges[1:-1][None], edges[2:][None]
+    w = np.maximum(0.0, np.minimum((spec_mel - lower) / (center - lower), (upper - spec_mel) / (upper - center)))
+    return np.concatenate([np.zeros((1, num_mel_bins)), w], axis=0)
+
+
+def _f32(t, device):
+    if t is None:
+        return None
+    if not torch.is_tensor(t):
+        t = torch.as_tensor(np.asarray(t))
+    return t.to(device=device, dtype=torch.float32).contiguous()
+
+
+def fused_features(sources, frame_len, hop, T=None, F=257, mean=None, std=None, mask=None, video=None,
+                   power=1.0, log=True, want_stft=False, stft_masked=False, want_spec=True, want_feat=False,
+                   xh_out=None, ldx=0, mel=None, mel_eps=1e-6, hole_count=None, xh_video_only=False):
+    """One launch of the fused front end.  Returns dict(stft, spec, feat, logmel) (missing = None).
+
+    sources [B,N] f32 CUDA; mask [B,T,F]; video [B,T,V]; xh_out optional preallocated
+    time-major fp16 [T*B, ldx] network-input buffer; mel = (matrix [257,n_mel] CUDA f32)."""
+    if not sources.is_cuda:
+        raise _lib.AvsiError('fused_features needs CUDA tensors (no CPU fallback)')
+    lib = _lib.load()
+    dev = sources.device
+    sources = _f32(sources, dev)
+    B, N = sources.shape
+    if T is None:
+        T = -(-N // hop)
+    tab = _device_tables(dev, frame_len)
+    mean, std, mask, video = _f32(mean, dev), _f32(std, dev), _f32(mask, dev), _f32(video, dev)
+    V = 0 if video is None else video.shape[2]
+    out = {'stft': None, 'spec': None, 'feat': None, 'logmel': None}
+    if want_stft:
+        out['stft'] = torch.empty(B, T, F, 2, dtype=torch.float32, device=dev)
+    if want_spec:
+        out['spec'] = torch.empty(B, T, F, dtype=torch.float32, device=dev)
+    if want_feat:
+        out['feat'] = torch.empty(B, T, F + V, dtype=torch.float32, device=dev)
+    n_mel = 0
+    if mel is not None:
+        n_mel = mel.shape[1]
+        out['logmel'] = torch.empty(B, T, n_mel, dtype=torch.float32, device=dev)
+    a = _lib.FrontendArgs()
+    a.wav, a.B, a.N = sources.data_ptr(), B, N
+    a.frame_len, a.hop, a.nfft, a.T, a.F = frame_len, hop, NFFT, T, F
+    a.window, a.twiddle = tab['window'].data_ptr(), tab['twiddle'].data_ptr()
+    a.mean = mean.data_ptr() if mean is not None else None
+    a.stdev = std.data_ptr() if std is not None else None
+    a.mask = mask.data_ptr() if mask is not None else None
+    a.video = video.data_ptr() if video is not None else None
+    a.V = V
+    a.power, a.log_flag, a.stft_masked = float(power), int(bool(log)), int(bool(stft_masked))
+    a.stft_out = out['stft'].data_ptr() if want_stft else None
+    a.spec_out = out['spec'].data_ptr() if want_spec else None
+    a.feat_out = out['feat'].data_ptr() if want_feat else None
+    a.xh_out = xh_out.data_ptr() if xh_out is not None else None
+    a.ldx = int(ldx)
+    a.logmel_out = out['logmel'].data_ptr() if mel is not None else None
+    a.mel_w = mel.data_ptr() if mel is not None else None
+    a.n_mel, a.mel_eps = n_mel, float(mel_eps)
+    a.hole_count = hole_count.data_ptr() if hole_count is not None else None
+    a.xh_video_only = int(bool(xh_video_only))
+    _lib.check(lib.avsi_frontend_fwd(a, _lib.stream_ptr()), 'avsi_frontend_fwd')
+    if want_stft:
+        out['stft'] = torch.view_as_complex(out['stft'])
+    return out
+
+
+def _sliced(x, out_shape):
+    if all(int(s) == 0 for s in out_shape):
+        return x
+    return x[:out_shape[0], :out_shape[1], :out_shape[2]]
+
+
+def get_stft(sources, sample_rate=16000, window_size=25, step_size=10, n_fft=512, out_shape=[0, 0, 0]):
+    """Compute STFT (audio_processing.py:25-42) -> complex64 [B, T, 257] (sliced to out_shape)."""
+    if n_fft != NFFT:
+        raise _lib.AvsiError('only n_fft = 512 is supported (the reference never uses another)')
+    frame_len, hop = ms_to_samples(window_size, sample_rate), ms_to_samples(step_size, sample_rate)
+    res = fused_features(sources, frame_len, hop, log=False, want_stft=True, want_spec=False)
+    return _sliced(res['stft'], out_shape)
+
+
+def get_spectrogram(stfts, power=1, log=False, out_shape=[0, 0, 0]):
+    """audio_processing.py:45-56 on an already computed STFT tensor (element-wise, torch)."""
+    spec = torch.abs(stfts)
+    if power != 1:
+        spec = spec ** power
+    if log:
+        spec = torch.log(spec + 1e-6)
+    return _sliced(spec, out_shape)
+
+
+def get_log_mel_spectrogram(spectrograms, sample_rate=16000, num_spec_bins=257, num_mel_bins=80,
+                            lower_edge_freq=125, upper_edge_freq=7600, eps=1e-6, out_shape=[0, 0, 0]):
+    """audio_processing.py:59-72 on a spectrogram tensor (out_shape is ignored there too)."""
+    if upper_edge_freq is None:
+        upper_edge_freq = sample_rate / 2
+    m = linear_to_mel_weight_matrix(num_mel_bins, num_spec_bins, sample_rate, lower_edge_freq, upper_edge_freq)
+    m = torch.tensor(m, dtype=spectrograms.dtype, device=spectrograms.device)
+    return torch.log(torch.tensordot(spectrograms, m, dims=1) + eps)
+
+
+def log_mel_features(sources, sample_rate=16000, window_size=25, step_size=10, num_mel_bins=80,
+                     lower_edge_freq=125, upper_edge_freq=7600, eps=1e-6):
+    """Fused `fbanks` path of audio_feat_preprocessing.py:49-50 / models_asr.py:31-37:
+    power-2 spectrogram -> mel projection -> log, one kernel."""
+    frame_len, hop = ms_to_samples(window_size, sample_rate), ms_to_samples(step_size, sample_rate)
+    m = linear_to_mel_weight_matrix(num_mel_bins, 257, sample_rate, lower_edge_freq, upper_edge_freq)
+    mel = torch.tensor(m, dtype=torch.float32, device=sources.device).contiguous()
+    res = fused_features(sources, frame_len, hop, power=2.0, log=False, want_spec=False, mel=mel, mel_eps=eps)
+    return res['logmel']
+
+
+def reconstruct_from(mag, phase_src, mask=None, mean=None, std=None, num_samples=48000, sample_rate=16000,
+                     window_size=24, step_size=12):
+    """Fused inverse path (audio_processing.py:145-164 + models.py:185-187): mag (or normalised
+    prediction when mean/std given) x unit phase of ``phase_src`` (x mask) -> iSTFT -> [B, num_samples]."""
+    lib = _lib.load()
+    dev = mag.device
+    frame_len, hop = ms_to_samples(window_size, sample_rate), ms_to_samples(step_size, sample_rate)
+    tab = _device_tables(dev, frame_len, hop)
+    mag = _f32(mag, dev)
+    B, T, F = mag.shape
+    ph = torch.view_as_real(phase_src.to(torch.complex64).contiguous()).contiguous()
+    mask, mean, std = _f32(mask, dev), _f32(mean, dev), _f32(std, dev)
+    out_len = num_samples if num_samples > 0 else (T - 1) * hop + frame_len
+    out = torch.empty(B, out_len, dtype=torch.float32, device=dev)
+    a = _lib.IstftArgs()
+    a.mag, a.phase_src = mag.data_ptr(), ph.data_ptr()
+    a.mask = mask.data_ptr() if mask is not None else None
+    a.mean = mean.data_ptr() if mean is not None else None
+    a.stdev = std.data_ptr() if std is not None else None
+    a.inv_window, a.twiddle = tab['inv_window'].data_ptr(), tab['twiddle'].data_ptr()
+    a.B, a.T, a.F, a.frame_len, a.hop, a.nfft, a.num_samples = B, T, F, frame_len, hop, NFFT, int(num_samples)
+    a.out = out.data_ptr()
+    _lib.check(lib.avsi_istft_fwd(a, _lib.stream_ptr()), 'avsi_istft_fwd')
+    return out
+
+
+def reconstruct_sources(stfts, num_samples=0, sample_rate=16000, window_size=16, step_size=8):
+    """Compute inverse STFT (audio_processing.py:145-157)."""
+    return reconstruct_from(torch.abs(stfts), stfts, num_samples=num_samples, sample_rate=sample_rate,
+                            window_size=window_size, step_size=step_size)
+
+
+def get_sources(mag_spectrograms, rec_ang_spectrograms, num_samples=48000, sample_rate=16000, window_size=24,
+                step_size=12):
+    """Get waveform from magnitude and phase of STFT (audio_processing.py:160-164)."""
+    unit = torch.polar(torch.ones_like(rec_ang_spectrograms), rec_ang_spectrograms)
+    return reconstruct_from(mag_spectrograms, unit, num_samples=num_samples, sample_rate=sample_rate,
+                            window_size=window_size, step_size=step_size)
+
+
+def downsampling(samples, sample_rate, downsample_rate):
+    """audio_processing.py:9-16 (host-side scipy FFT resampling, offline data preparation)."""
+    from scipy import signal
+    secs = len(samples) / float(sample_rate)
+    num_samples = int(downsample_rate * secs)
+    if sample_rate != downsample_rate:
+        return signal.resample(samples, num_samples)
+    return samples

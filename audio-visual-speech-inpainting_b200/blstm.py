@@ -1,0 +1,195 @@
+"""Stacked-BLSTM engine: weights, workspaces and the forward / backward / update schedule.
+
+Host-side orchestration of the sm_100a kernels for the network of models.py:89-125
+(CudnnLSTM(num_layers, num_units, bidirectional, linear_input) + linear head(s)) and its
+gradient.  torch is used for device memory, streams and (in parallel.py) NCCL only; every
+arithmetic op is a kernel from libavsi_b200.so.  No autograd: the backward schedule is explicit.
+
+Per layer l (time-major rows r = t*B + b, fp16 activations, fp32 accumulate):
+  forward   G_l = X_l . Wih_l^T                  tcgen05 GEMM  [T*B,Kp] x [2048,Kp]^T -> f16
+            (Y_l, C_l, G_l<-gates) = recur(G_l)  cluster-persistent LSTM kernel
+  head      logits = Y_last . Whead^T + b        tcgen05 GEMM -> f32
+  backward  G_l <- dgates = bptt(G_l, C_l, dY_l) cluster-persistent BPTT kernel
+            dWih_l += G_l^T . X_l ; dWhh_l += G_l^T . Y_l(shifted)   tcgen05 GEMM (MN-major, split-K)
+            dY_{l-1} = G_l . Wih_l               tcgen05 GEMM -> f16
+Gradients are computed on loss-scaled fp16 activations gradients and unscaled inside Adam.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from .layout import GATES, HP, ParamLayout
+
+NG = 2 * GATES * HP     # 2048 gate columns (both directions)
+NY = 2 * HP             # 512 output columns (both directions)
+
+
+def _p(t):
+    return _lib.ptr(t)
+
+
+def gemm(A, lda, B, ldb, C, ldc, bias, M, N, K, trans, out_mode, split_k=1):
+    lib = _lib.load()
+    _lib.check(lib.avsi_gemm_f16(A, lda, B, ldb, C, ldc, bias, M, N, K, trans, out_mode, split_k, _lib.stream_ptr()),
+               'avsi_gemm_f16')
+
+
+def pick_split_k(m_rows, n_cols, k, target_ctas=296):
+    tiles = -(-m_rows // 128) * -(-n_cols // 128)
+    kb = -(-k // 64)
+    return int(max(1, min(-(-target_ctas // tiles), 32, kb)))
+
+
+class BLSTMEngine(object):
+    def __init__(self, in_dim, hidden=250, n_layers=3, out_dim=257, n_classes=0, device='cuda'):
+        if not torch.cuda.is_available():
+            raise _lib.AvsiError('BLSTMEngine needs a CUDA device (there is no CPU fallback)')
+        _lib.load()
+        self.layout = ParamLayout(in_dim, hidden, n_layers, out_dim, n_classes)
+        self.device = torch.device(device)
+        L = self.layout
+        n = L.n_params_padded
+        self.theta = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.grad = torch.zeros(n + 8, dtype=torch.float32, device=self.device)   # + loss scalars tail
+        self.adam_m = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.adam_v = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.step_count = 0
+        # fp16 operand copies
+        self.half = {}
+        for l in range(L.n_layers):
+            kp = L.layer_k(l)
+            self.half['wih%d' % l] = torch.zeros(NG, kp, dtype=torch.float16, device=self.device)
+            self.half['wihT%d' % l] = torch.zeros(kp, NG, dtype=torch.float16, device=self.device)
+            self.half['whh%d' % l] = torch.zeros(NG, HP, dtype=torch.float16, device=self.device)
+            self.half['whhT%d' % l] = torch.zeros(HP, NG, dtype=torch.float16, device=self.device)
+        self.half['head'] = torch.zeros(L.nop, NY, dtype=torch.float16, device=self.device)
+        self.half['headT'] = torch.zeros(NY, L.nop, dtype=torch.float16, device=self.device)
+        self._ws = {}
+
+    # ---- parameters ---------------------------------------------------------------------------
+    def view(self, buf, name):
+        off, shp = self.layout.index[name]
+        return buf[off:off + int(np.prod(shp))].view(*shp)
+
+    def load_canonical(self, params):
+        flat = self.layout.pack(params, np.float32)
+        self.theta.copy_(torch.from_numpy(flat))
+        self.refresh_half()
+
+    def export_canonical(self):
+        return self.layout.unpack(self.theta.detach().cpu().numpy())
+
+    def export_canonical_grads(self, unscale=1.0):
+        g = self.grad[:self.layout.n_params_padded].detach().cpu().numpy().astype(np.float64) * unscale
+        return self.layout.unpack(g)
+
+    def refresh_half(self):
+        lib = _lib.load()
+        st = _lib.stream_ptr()
+        L = self.layout
+        for l in range(L.n_layers):
+            kp = L.layer_k(l)
+            _lib.check(lib.avsi_cast_weights(_p(self.view(self.theta, 'wih%d' % l)), NG, kp, _p(self.half['wih%d' % l]),
+                                             _p(self.half['wihT%d' % l]), st), 'avsi_cast_weights')
+            _lib.check(lib.avsi_cast_weights(_p(self.view(self.theta, 'whh%d' % l)), NG, HP, _p(self.half['whh%d' % l]),
+                                             _p(self.half['whhT%d' % l]), st), 'avsi_cast_weights')
+        _lib.check(lib.avsi_cast_weights(_p(self.view(self.theta, 'head_w')), L.nop, NY, _p(self.half['head']),
+                                         _p(self.half['headT']), st), 'avsi_cast_weights')
+
+    # ---- workspaces ---------------------------------------------------------------------------
+    def workspace(self, T, B, training=True):
+        key = (T, B, training)
+        ws = self._ws.get(key)
+        if ws is not None:
+            return ws
+        L = self.layout
+        M = T * B
+        dev = self.device
+        ws = {'T': T, 'B': B, 'M': M}
+        ws['x0'] = torch.zeros(M, L.k0p, dtype=torch.float16, device=dev)
+        ws['G'] = [torch.empty(M, NG, dtype=torch.float16, device=dev) for _ in range(L.n_layers if training else 1)]
+        ws['Y'] = [torch.empty(M, NY, dtype=torch.float16, device=dev) for _ in range(L.n_layers)]
+        ws['C'] = [torch.empty(M, NY, dtype=torch.float32, device=dev) for _ in range(L.n_layers if training else 1)]
+        ws['logits'] = torch.zeros(M, L.nop, dtype=torch.float32, device=dev)
+        if training:
+            ws['dlogits'] = torch.zeros(M, L.nop, dtype=torch.float16, device=dev)
+            ws['dY'] = [torch.empty(M, NY, dtype=torch.float16, device=dev) for _ in range(2)]
+            nbytes = int(_lib.load().avsi_lstm_bwd_scratch_bytes(B))
+            ws['scratch'] = torch.empty(max(nbytes, 16) // 4, dtype=torch.float32, device=dev)
+        self._ws = {key: ws} if len(self._ws) > 4 else dict(self._ws, **{key: ws})
+        return ws
+
+    # ---- forward ------------------------------------------------------------------------------
+    def forward(self, ws):
+        """ws['x0'] (time-major fp16 network input) -> ws['logits'] [T*B, nop] fp32."""
+        lib = _lib.load()
+        L = self.layout
+        T, B, M = ws['T'], ws['B'], ws['M']
+        training = len(ws['G']) == L.n_layers
+        x, ldx = ws['x0'], L.k0p
+        for l in range(L.n_layers):
+            G = ws['G'][l if training else 0]
+            C = ws['C'][l if training else 0]
+            kp = L.layer_k(l)
+            gemm(_p(x), ldx, _p(self.half['wih%d' % l]), kp, _p(G), NG, None, M, NG, kp, 0, 0)
+            _lib.check(lib.avsi_lstm_fwd(_p(G), _p(self.half['whh%d' % l]), _p(self.view(self.theta, 'b%d' % l)),
+                                         _p(ws['Y'][l]), _p(C), T, B, _lib.stream_ptr()), 'avsi_lstm_fwd')
+            x, ldx = ws['Y'][l], NY
+        gemm(_p(x), NY, _p(self.half['head']), NY, _p(ws['logits']), L.nop, _p(self.view(self.theta, 'head_b')),
+             M, L.n_out, NY, 0, 1)
+        return ws['logits']
+
+    # ---- backward -----------------------------------------------------------------------------
+    def backward(self, ws, zero_grad=True):
+        """ws['dlogits'] (scaled dL/dlogits, fp16) -> self.grad (scaled, padded flat fp32)."""
+        lib = _lib.load()
+        L = self.layout
+        T, B, M = ws['T'], ws['B'], ws['M']
+        st = _lib.stream_ptr
+        if zero_grad:
+            self.grad.zero_()
+        g = self.grad
+        dl = ws['dlogits']
+        ylast = ws['Y'][L.n_layers - 1]
+        # head: dW = dlogits^T . Y ; db = colsum(dlogits) ; dY = dlogits . Whead
+        gemm(_p(dl), L.nop, _p(ylast), NY, _p(self.view(g, 'head_w')), NY, None, L.n_out, NY, M, 1, 2,
+             pick_split_k(L.n_out, NY, M))
+        _lib.check(lib.avsi_colsum_f16(_p(dl), L.nop, M, 0, L.n_out, _p(self.view(g, 'head_b')), st()), 'avsi_colsum_f16')
+        dY = ws['dY'][0]
+        gemm(_p(dl), L.nop, _p(self.half['headT']), L.nop, _p(dY), NY, None, M, NY, L.nop, 0, 0)
+        cur = 0
+        for l in range(L.n_layers - 1, -1, -1):
+            G, C, Y = ws['G'][l], ws['C'][l], ws['Y'][l]
+            kp = L.layer_k(l)
+            _lib.check(lib.avsi_lstm_bwd(_p(G), _p(self.half['whhT%d' % l]), _p(C), _p(ws['dY'][cur]),
+                                         _p(self.view(g, 'b%d' % l)), _p(ws['scratch']), T, B, st()), 'avsi_lstm_bwd')
+            x, ldx = (ws['x0'], L.k0p) if l == 0 else (ws['Y'][l - 1], NY)
+            # dWih = dG^T . X
+            gemm(_p(G), NG, _p(x), ldx, _p(self.view(g, 'wih%d' % l)), kp, None, NG, kp, M, 1, 2,
+                 pick_split_k(NG, kp, M))
+            # dWhh[dir] = dG[dir]^T . h_prev  (fw: h_{t-1}, bw: h_{t+1})
+            if T > 1:
+                Kr = (T - 1) * B
+                gw = self.view(g, 'whh%d' % l)
+                sk = pick_split_k(GATES * HP, HP, Kr, 148)
+                a_fw = G.data_ptr() + B * NG * 2
+                b_fw = Y.data_ptr()
+                gemm(a_fw, NG, b_fw, NY, _p(gw), HP, None, GATES * HP, HP, Kr, 1, 2, sk)
+                a_bw = G.data_ptr() + GATES * HP * 2
+                b_bw = Y.data_ptr() + (B * NY + HP) * 2
+                gemm(a_bw, NG, b_bw, NY, gw.data_ptr() + GATES * HP * HP * 4, HP, None, GATES * HP, HP, Kr, 1, 2, sk)
+            if l > 0:
+                nxt = 1 - cur
+                gemm(_p(G), NG, _p(self.half['wihT%d' % l]), NG, _p(ws['dY'][nxt]), NY, None, M, NY, NG, 0, 0)
+                cur = nxt
+        return g
+
+    # ---- update -------------------------------------------------------------------------------
+    def adam_step(self, lr=1e-3, grad_unscale=1.0, unscale_dev=None, l2=0.0, b1=0.9, b2=0.999, eps=1e-8):
+        lib = _lib.load()
+        self.step_count += 1
+        n = self.layout.n_params_padded
+        _lib.check(lib.avsi_adam_tf(_p(self.theta), _p(self.grad), _p(self.adam_m), _p(self.adam_v), n, lr, b1, b2, eps,
+                                    self.step_count, grad_unscale, _p(unscale_dev), l2, _lib.stream_ptr()),
+                   'avsi_adam_tf')
+        self.refresh_half()

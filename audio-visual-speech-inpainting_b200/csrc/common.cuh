@@ -1,0 +1,92 @@
+// Shared helpers for the avsi_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <atomic>
+
+#include "../../include/avsi_b200.h"
+
+namespace avsi {
+
+extern thread_local char g_last_error[512];
+extern std::atomic<long long> g_launch_count;
+
+inline int set_error(int code, const char* fmt, const char* a = "", const char* b = "") {
+  snprintf(g_last_error, sizeof(g_last_error), fmt, a, b);
+  return code;
+}
+
+#define AVSI_REQUIRE(cond, msg)                                                     \
+  do {                                                                              \
+    if (!(cond)) return avsi::set_error(AVSI_ERR_INVALID, "%s: requirement failed: %s", __func__, msg); \
+  } while (0)
+
+#define AVSI_CUDA(call)                                                             \
+  do {                                                                              \
+    cudaError_t e_ = (call);                                                        \
+    if (e_ != cudaSuccess)                                                          \
+      return avsi::set_error(AVSI_ERR_CUDA, "%s: CUDA error: %s", __func__, cudaGetErrorString(e_)); \
+  } while (0)
+
+#define AVSI_LAUNCH_CHECK()                                                         \
+  do {                                                                              \
+    avsi::g_launch_count.fetch_add(1, std::memory_order_relaxed);                   \
+    cudaError_t e_ = cudaGetLastError();                                            \
+    if (e_ != cudaSuccess)                                                          \
+      return avsi::set_error(AVSI_ERR_CUDA, "%s: launch failed: %s", __func__, cudaGetErrorString(e_)); \
+  } while (0)
+
+inline int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+__device__ __forceinline__ float sigmoidf_fast(float x) {
+  // sigma(x) = 0.5 * tanh(0.5 x) + 0.5  (one MUFU.TANH)
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+  return fmaf(0.5f, t, 0.5f);
+}
+__device__ __forceinline__ float tanhf_fast(float x) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x));
+  return t;
+}
+// accurate versions (expf based, ~1e-7 rel) used where the 2e-3 budget is tight
+__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanhf_acc(float x) {
+  float e = __expf(-2.0f * fabsf(x));
+  float t = (1.0f - e) / (1.0f + e);
+  return copysignf(t, x);
+}
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack_half2(uint32_t u) {
+  __half2 h = *reinterpret_cast<__half2*>(&u);
+  return __half22float2(h);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace avsi

@@ -1,0 +1,171 @@
+// CTC negative log-likelihood + gradient on the GPU.
+//
+// Replaces tf.nn.ctc_loss (a CPU-only op in TF1, forcing a device->host->device hop every
+// training step) as called at models.py:1950-1953 / models_asr.py:146-148: unnormalised
+// time-major logits, blank = C-1, ctc_merge_repeated=True, frames t >= seq_len ignored.
+// One 128-thread CTA per utterance: log-softmax rows -> alpha (forward in t) -> beta and the
+// gradient softmax - posterior (backward in t), all in fp32 log space.  alpha and the
+// log-softmax live in an L2-resident workspace; the recursion state sits in shared memory.
+#include "common.cuh"
+
+namespace avsi {
+
+constexpr int CTC_THREADS = 128;
+constexpr int CTC_MAX_S = 1024;   // 2*Lmax+1 limit (shared-memory state)
+constexpr int CTC_MAX_C = 128;
+#define CTC_NEG (-1e30f)
+
+__device__ __forceinline__ float lse2(float a, float b) {
+  float m = fmaxf(a, b);
+  if (m <= CTC_NEG) return CTC_NEG;
+  return m + log1pf(__expf(fminf(a, b) - m));
+}
+
+__global__ void __launch_bounds__(CTC_THREADS)
+ctc_kernel(const float* __restrict__ logits, int ldl, int col0, int C, const int32_t* __restrict__ labels, int Lmax,
+           const int32_t* __restrict__ lab_len, const int32_t* __restrict__ seq_len, int B, int T, float grad_scale,
+           const float* __restrict__ grad_scale_dev, float* __restrict__ nll, uint16_t* __restrict__ dlogits,
+           int ldd, int dcol0, float* __restrict__ ws_logp, float* __restrict__ ws_alpha) {
+  __shared__ int ext[CTC_MAX_S];
+  __shared__ unsigned char skip[CTC_MAX_S];
+  __shared__ float st[2][CTC_MAX_S];
+  __shared__ float ab[CTC_MAX_S];
+  __shared__ float ll_sh;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int blank = C - 1;
+  const int L = min(max(lab_len[b], 0), Lmax);
+  const int Tb = min(max(seq_len[b], 0), T);
+  const int S = 2 * L + 1;
+  const int Smax = 2 * Lmax + 1;
+  const float scale = grad_scale * (grad_scale_dev ? *grad_scale_dev : 1.f);
+  float* logp = ws_logp + (long long)b * T * C;
+  float* alpha = ws_alpha + (long long)b * T * Smax;
+
+  for (int s = tid; s < S; s += CTC_THREADS) ext[s] = (s & 1) ? labels[b * Lmax + (s >> 1)] : blank;
+  __syncthreads();
+  for (int s = tid; s < S; s += CTC_THREADS) skip[s] = (s >= 2 && ext[s] != blank && ext[s] != ext[s - 2]) ? 1 : 0;
+
+  // ---- log-softmax, one warp per frame ---------------------------------------------------
+  for (int t = warp; t < Tb; t += CTC_THREADS / 32) {
+    const float* row = logits + ((long long)t * B + b) * ldl + col0;
+    float mx = CTC_NEG;
+    for (int c = lane; c < C; c += 32) mx = fmaxf(mx, row[c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int c = lane; c < C; c += 32) sum += expf(row[c] - mx);
+    sum = warp_sum(sum);
+    const float lz = mx + logf(sum);
+    for (int c = lane; c < C; c += 32) logp[t * C + c] = row[c] - lz;
+  }
+  // frames beyond the sequence get zero gradient
+  if (dlogits)
+    for (int i = tid; i < (T - Tb) * C; i += CTC_THREADS) {
+      const int t = Tb + i / C, c = i % C;
+      dlogits[((long long)t * B + b) * ldd + dcol0 + c] = 0;
+    }
+  __syncthreads();
+  if (Tb == 0) {
+    if (tid == 0) nll[b] = (L == 0) ? 0.f : INFINITY;
+    return;
+  }
+
+  // ---- alpha -------------------------------------------------------------------------------
+  for (int s = tid; s < S; s += CTC_THREADS) {
+    float a = CTC_NEG;
+    if (s == 0) a = logp[blank];
+    else if (s == 1) a = logp[ext[1]];
+    st[0][s] = a;
+    alpha[s] = a;
+  }
+  __syncthreads();
+  for (int t = 1; t < Tb; ++t) {
+    const float* prev = st[(t - 1) & 1];
+    float* cur = st[t & 1];
+    for (int s = tid; s < S; s += CTC_THREADS) {
+      float a = prev[s];
+      if (s >= 1) a = lse2(a, prev[s - 1]);
+      if (skip[s]) a = lse2(a, prev[s - 2]);
+      a = (a <= CTC_NEG) ? CTC_NEG : a + logp[t * C + ext[s]];
+      cur[s] = a;
+      alpha[(long long)t * Smax + s] = a;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const float* last = st[(Tb - 1) & 1];
+    ll_sh = (S == 1) ? last[0] : lse2(last[S - 1], last[S - 2]);
+  }
+  __syncthreads();
+  const float ll = ll_sh;
+  const bool feasible = ll > CTC_NEG;
+  if (tid == 0) nll[b] = feasible ? -ll : INFINITY;
+  if (!dlogits) return;
+
+  // ---- beta + gradient -------------------------------------------------------------------
+  for (int t = Tb - 1; t >= 0; --t) {
+    float* cur = st[t & 1];
+    const float* nxt = st[(t + 1) & 1];
+    for (int s = tid; s < S; s += CTC_THREADS) {
+      float bt;
+      if (t == Tb - 1) {
+        bt = (s == S - 1 || s == S - 2) ? 0.f : CTC_NEG;
+      } else {
+        bt = nxt[s];
+        if (s + 1 < S) bt = lse2(bt, nxt[s + 1]);
+        if (s + 2 < S && skip[s + 2]) bt = lse2(bt, nxt[s + 2]);
+      }
+      bt = (bt <= CTC_NEG) ? CTC_NEG : bt + logp[t * C + ext[s]];
+      cur[s] = bt;
+      ab[s] = alpha[(long long)t * Smax + s] + bt;
+    }
+    __syncthreads();
+    // class posterior: thread c sums the positions that carry class c
+    for (int c = tid; c < C; c += CTC_THREADS) {
+      float mx = CTC_NEG;
+      for (int s = (c == blank) ? 0 : 1; s < S; s += 2)
+        if (ext[s] == c) mx = fmaxf(mx, ab[s]);
+      float grad;
+      const float lp = logp[t * C + c];
+      if (!feasible) {
+        grad = 0.f;
+      } else if (mx <= -1e29f) {
+        grad = expf(lp);
+      } else {
+        float sum = 0.f;
+        for (int s = (c == blank) ? 0 : 1; s < S; s += 2)
+          if (ext[s] == c) sum += expf(ab[s] - mx);
+        // alpha*beta counts y_t(c) twice -> subtract lp once
+        grad = expf(lp) - expf(mx + logf(sum) - lp - ll);
+      }
+      dlogits[((long long)t * B + b) * ldd + dcol0 + c] = __half_as_ushort(__float2half_rn(scale * grad));
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace avsi
+
+extern "C" int64_t avsi_ctc_workspace_bytes(int B, int T, int Lmax) {
+  if (B <= 0 || T <= 0 || Lmax < 0) return 0;
+  return (int64_t)B * T * (avsi::CTC_MAX_C + (2LL * Lmax + 1)) * (int64_t)sizeof(float);
+}
+
+extern "C" int avsi_ctc_loss(const float* logits, int ldl, int col0, int C, const int32_t* labels, int Lmax,
+                             const int32_t* lab_len, const int32_t* seq_len, int B, int T, float grad_scale,
+                             const float* grad_scale_dev, float* nll, uint16_t* dlogits, int ldd, int dcol0,
+                             void* workspace, void* stream) {
+  using namespace avsi;
+  AVSI_REQUIRE(logits && labels && lab_len && seq_len && nll && workspace, "null pointer");
+  AVSI_REQUIRE(B > 0 && T > 0 && C > 1 && C <= CTC_MAX_C, "sizes");
+  AVSI_REQUIRE(Lmax >= 1 && 2 * Lmax + 1 <= CTC_MAX_S, "Lmax");
+  AVSI_REQUIRE(ldl >= col0 + C, "ldl");
+  AVSI_REQUIRE(!dlogits || ldd >= dcol0 + C, "ldd");
+  float* ws_logp = reinterpret_cast<float*>(workspace);
+  float* ws_alpha = ws_logp + (long long)B * T * CTC_MAX_C;
+  ctc_kernel<<<B, CTC_THREADS, 0, (cudaStream_t)stream>>>(logits, ldl, col0, C, labels, Lmax, lab_len, seq_len, B, T,
+                                                         grad_scale, grad_scale_dev, nll, dlogits, ldd, dcol0,
+                                                         ws_logp, ws_alpha);
+  AVSI_LAUNCH_CHECK();
+  return AVSI_OK;
+}

@@ -1,0 +1,259 @@
+// Fused spectrogram front end: frame -> Hann window -> rFFT-512 -> |.|^p -> log -> normalise
+// -> mask -> (concat video) -> fp32 / time-major fp16 outputs, one kernel, frames never in HBM.
+//
+// Replaces get_stft / get_spectrogram / get_log_mel_spectrogram (audio_processing.py:25-72),
+// the normalise + mask + concat of models.py:30-45 and the complex mask of masking.py:42.
+//
+// Mapping: 16 threads per frame, 16 frames per 256-thread CTA, persistent grid-stride loop
+// over groups of 16 consecutive global frame indices g = b*T + t.  The 512-point real FFT is
+// a 256-point complex FFT of z[n] = x[2n] + i x[2n+1] done as a four-step 16x16 FFT: every
+// thread runs two 16-point FFTs in registers with ONE shared-memory exchange in between,
+// then a second exchange for the real-FFT split (needs Z[k] and Z[256-k]).
+// Global loads are 8-byte, 128 B contiguous per frame per instruction (the 50 % frame
+// overlap is served by L1/L2, not HBM); stores are 64 B contiguous per frame per instruction.
+#include "common.cuh"
+
+namespace avsi {
+
+struct cpx {
+  float x, y;
+};
+__device__ __forceinline__ cpx cadd(cpx a, cpx b) { return {a.x + b.x, a.y + b.y}; }
+__device__ __forceinline__ cpx csub(cpx a, cpx b) { return {a.x - b.x, a.y - b.y}; }
+__device__ __forceinline__ cpx cmul(cpx a, cpx b) {
+  return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x};
+}
+// multiply by -i (forward FFT quarter turn) / +i (inverse)
+template <bool INV>
+__device__ __forceinline__ cpx rot90(cpx a) {
+  return INV ? cpx{-a.y, a.x} : cpx{a.y, -a.x};
+}
+
+template <bool INV>
+__device__ __forceinline__ void fft4(cpx& a, cpx& b, cpx& c, cpx& d) {
+  // in: x0..x3, out: X0..X3 (natural order)
+  cpx s0 = cadd(a, c), s1 = csub(a, c), s2 = cadd(b, d), s3 = rot90<INV>(csub(b, d));
+  a = cadd(s0, s2);
+  c = csub(s0, s2);
+  b = cadd(s1, s3);
+  d = csub(s1, s3);
+}
+
+// 16-point FFT, in place, natural order in and out.  16 = 4 x 4:
+// X[k1 + 4 k2] = sum_n2 W16^(n2 k1) [ sum_n1 x[4 n1 + n2] W4^(n1 k1) ] W4^(n2 k2)
+template <bool INV>
+__device__ __forceinline__ void fft16(cpx (&v)[16]) {
+  const float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, r2 = 0.70710678118654752f;
+#pragma unroll
+  for (int n2 = 0; n2 < 4; ++n2) fft4<INV>(v[n2], v[4 + n2], v[8 + n2], v[12 + n2]);
+  // v[4*k1 + n2] now holds A[k1][n2]; twiddle by W16^(n2*k1)  (conjugated for inverse)
+  const float sg = INV ? 1.f : -1.f;
+  const cpx w1 = {c1, sg * s1}, w2 = {r2, sg * r2}, w3 = {s1, sg * c1};
+  const cpx w6 = {-r2, sg * r2}, w9 = {-c1, sg * (-s1)};
+  v[4 * 1 + 1] = cmul(v[4 * 1 + 1], w1);
+  v[4 * 1 + 2] = cmul(v[4 * 1 + 2], w2);
+  v[4 * 1 + 3] = cmul(v[4 * 1 + 3], w3);
+  v[4 * 2 + 1] = cmul(v[4 * 2 + 1], w2);
+  v[4 * 2 + 2] = rot90<INV>(v[4 * 2 + 2]);  // W16^4 = -i
+  v[4 * 2 + 3] = cmul(v[4 * 2 + 3], w6);
+  v[4 * 3 + 1] = cmul(v[4 * 3 + 1], w3);
+  v[4 * 3 + 2] = cmul(v[4 * 3 + 2], w6);
+  v[4 * 3 + 3] = cmul(v[4 * 3 + 3], w9);
+#pragma unroll
+  for (int k1 = 0; k1 < 4; ++k1) fft4<INV>(v[4 * k1 + 0], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3]);
+  // v[4*k1 + k2] = X[k1 + 4*k2] -> reorder to natural order
+  cpx t[16];
+#pragma unroll
+  for (int k1 = 0; k1 < 4; ++k1)
+#pragma unroll
+    for (int k2 = 0; k2 < 4; ++k2) t[k1 + 4 * k2] = v[4 * k1 + k2];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = t[i];
+}
+
+constexpr int FE_THREADS = 256;
+constexpr int FE_FRAMES = 16;          // frames per CTA iteration
+constexpr int FE_XROW = 17;            // padded row (complex) of the 16x16 exchange
+constexpr int FE_XCH = 16 * FE_XROW;   // 272 complex per frame
+
+struct FrontendSmem {
+  float2 tw[512];                       // exp(-2 pi i m / 512)
+  float win[512];                       // window, zero beyond frame_len
+  float2 xch[FE_FRAMES][FE_XCH];        // per-frame exchange / Z buffer
+  float pw[FE_FRAMES][260];             // per-frame power spectrum (mel path only)
+};
+
+__global__ void __launch_bounds__(FE_THREADS) frontend_kernel(avsi_frontend_args p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FrontendSmem& sm = *reinterpret_cast<FrontendSmem*>(smem_raw);
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 512; i += FE_THREADS) {
+    sm.tw[i] = reinterpret_cast<const float2*>(p.twiddle)[i];
+    sm.win[i] = (i < p.frame_len) ? p.window[i] : 0.f;
+  }
+  __syncthreads();
+
+  const int fl = tid >> 4;   // local frame
+  const int q = tid & 15;    // lane within the frame
+  const long long total = (long long)p.B * p.T;
+  const int I = p.F + (p.video ? p.V : 0);
+  const bool want_mel = p.logmel_out != nullptr;
+  float holes = 0.f;
+
+  for (long long g0 = (long long)blockIdx.x * FE_FRAMES; g0 < total; g0 += (long long)gridDim.x * FE_FRAMES) {
+    const long long g = g0 + fl;
+    const bool live = g < total;
+    const int b = live ? (int)(g / p.T) : 0;
+    const int t = live ? (int)(g - (long long)b * p.T) : 0;
+
+    // ---- load + window: thread q holds z[16 n1 + q], n1 = 0..15 -------------------------
+    cpx v[16];
+    {
+      const long long base = (long long)b * p.N + (long long)t * p.hop;   // sample index of frame start
+      const float* src = p.wav + base;
+      const int avail = live ? (int)min((long long)p.frame_len, (long long)p.N - (long long)t * p.hop) : 0;
+      const bool vec_ok = ((base & 1LL) == 0);
+#pragma unroll
+      for (int n1 = 0; n1 < 16; ++n1) {
+        const int i0 = 32 * n1 + 2 * q;
+        float x0 = 0.f, x1 = 0.f;
+        if (i0 + 1 < avail) {
+          if (vec_ok) {
+            float2 xx = __ldg(reinterpret_cast<const float2*>(src + i0));
+            x0 = xx.x;
+            x1 = xx.y;
+          } else {
+            x0 = __ldg(src + i0);
+            x1 = __ldg(src + i0 + 1);
+          }
+        } else if (i0 < avail) {
+          x0 = __ldg(src + i0);
+        }
+        v[n1].x = x0 * sm.win[i0];
+        v[n1].y = x1 * sm.win[i0 + 1];
+      }
+    }
+    // ---- step 1: FFT16 over n1, twiddle W256^(q*k1), exchange ---------------------------
+    fft16<false>(v);
+    float2* xc = sm.xch[fl];
+#pragma unroll
+    for (int k1 = 0; k1 < 16; ++k1) {
+      float2 w = sm.tw[(2 * q * k1) & 511];
+      cpx r = cmul(v[k1], cpx{w.x, w.y});
+      xc[k1 * FE_XROW + q] = make_float2(r.x, r.y);
+    }
+    __syncwarp();
+    // ---- step 2: thread q = k1 reads A[k1][n2], FFT16 over n2 -> Z[k1 + 16 k2] ----------
+#pragma unroll
+    for (int n2 = 0; n2 < 16; ++n2) {
+      float2 a = xc[q * FE_XROW + n2];
+      v[n2] = cpx{a.x, a.y};
+    }
+    fft16<false>(v);
+    __syncwarp();
+#pragma unroll
+    for (int k2 = 0; k2 < 16; ++k2) xc[q + 16 * k2] = make_float2(v[k2].x, v[k2].y);   // natural order Z[k]
+    __syncwarp();
+
+    // ---- real-FFT split + epilogue: thread q handles bins k = q + 16 m (and 256 for q == 0) -
+    const long long row_bt = g;                                   // (b*T + t)
+    const long long row_tb = (long long)t * p.B + b;              // time-major row
+    const int nb = (q == 0) ? 17 : 16;
+    for (int m = 0; m < nb; ++m) {
+      const int k = (m < 16) ? (q + 16 * m) : 256;
+      float2 zk = xc[k & 255];
+      float2 zn = xc[(256 - k) & 255];
+      // E = (Z[k] + conj Z[N-k]) / 2 ; O = -i (Z[k] - conj Z[N-k]) / 2 ; X = E + W512^k O
+      cpx e = {0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y)};
+      cpx d = {0.5f * (zk.x - zn.x), 0.5f * (zk.y + zn.y)};
+      cpx o = {d.y, -d.x};
+      float2 w = sm.tw[k];   // k <= 256
+      cpx X = cadd(e, cmul(o, cpx{w.x, w.y}));
+      if (k >= p.F && !(want_mel && k < 257)) continue;
+      float mval = 1.f;
+      if (live && p.mask && k < p.F) {
+        mval = __ldg(p.mask + row_bt * p.F + k);
+        holes += 1.f - mval;
+      }
+      if (live && p.stft_out && k < p.F) {
+        float sc = p.stft_masked ? mval : 1.f;
+        reinterpret_cast<float2*>(p.stft_out)[row_bt * p.F + k] = make_float2(X.x * sc, X.y * sc);
+      }
+      float s = X.x * X.x + X.y * X.y;
+      float mag;
+      if (p.power == 2.f) mag = s;
+      else {
+        mag = sqrtf(s);
+        if (p.power != 1.f) mag = powf(mag, p.power);
+      }
+      if (want_mel) sm.pw[fl][k] = mag;
+      if (!live || k >= p.F) continue;
+      float val = p.log_flag ? logf(mag + 1e-6f) : mag;
+      if (p.mean) val = (val - __ldg(p.mean + k)) / __ldg(p.stdev + k);
+      if (p.spec_out) p.spec_out[row_bt * p.F + k] = val;
+      const float mv = val * mval;
+      if (p.feat_out) p.feat_out[row_bt * I + k] = mv;
+      if (p.xh_out && !p.xh_video_only) p.xh_out[row_tb * p.ldx + k] = __half_as_ushort(__float2half_rn(mv));
+    }
+    // ---- video columns and zero padding ---------------------------------------------------
+    if (live && p.video) {
+      const float* vs = p.video + row_bt * p.V;
+      for (int c = q; c < p.V; c += 16) {
+        float x = __ldg(vs + c);
+        if (p.feat_out) p.feat_out[row_bt * I + p.F + c] = x;
+        if (p.xh_out) p.xh_out[row_tb * p.ldx + (p.xh_video_only ? 0 : p.F) + c] = __half_as_ushort(__float2half_rn(x));
+      }
+    }
+    if (live && p.xh_out)
+      for (int c = (p.xh_video_only ? p.V : I) + q; c < p.ldx; c += 16) p.xh_out[row_tb * p.ldx + c] = 0;
+    // ---- log-mel ------------------------------------------------------------------------------
+    if (want_mel) {
+      __syncwarp();
+      if (live) {
+        for (int mb = q; mb < p.n_mel; mb += 16) {
+          float acc = 0.f;
+          for (int k = 0; k < 257; ++k) {
+            float w = __ldg(p.mel_w + k * p.n_mel + mb);
+            acc = fmaf(sm.pw[fl][k], w, acc);
+          }
+          p.logmel_out[row_bt * p.n_mel + mb] = logf(acc + p.mel_eps);
+        }
+      }
+    }
+    __syncwarp();
+  }
+  if (p.hole_count) {
+    holes = warp_sum(holes);
+    if ((tid & 31) == 0 && holes != 0.f) atomicAdd(p.hole_count, holes);
+  }
+}
+
+}  // namespace avsi
+
+extern "C" int avsi_frontend_fwd(const avsi_frontend_args* a, void* stream) {
+  using namespace avsi;
+  AVSI_REQUIRE(a != nullptr, "args");
+  AVSI_REQUIRE(a->nfft == 512, "nfft must be 512");
+  AVSI_REQUIRE(a->frame_len > 0 && a->frame_len <= 512, "frame_len in (0,512]");
+  AVSI_REQUIRE(a->hop > 0, "hop > 0");
+  AVSI_REQUIRE(a->F > 0 && a->F <= 257, "F in (0,257]");
+  AVSI_REQUIRE(a->B > 0 && a->T > 0 && a->N > 0, "B,T,N > 0");
+  AVSI_REQUIRE(a->wav && a->window && a->twiddle, "wav/window/twiddle");
+  AVSI_REQUIRE((a->mean == nullptr) == (a->stdev == nullptr), "mean and std together");
+  AVSI_REQUIRE(!a->logmel_out || (a->mel_w && a->n_mel > 0), "mel weights");
+  AVSI_REQUIRE(!a->xh_out || a->ldx >= (a->xh_video_only ? 0 : a->F) + (a->video ? a->V : 0), "ldx too small");
+  AVSI_REQUIRE(!a->xh_video_only || a->video, "xh_video_only needs video");
+  const long long total = (long long)a->B * a->T;
+  const long long groups = (total + FE_FRAMES - 1) / FE_FRAMES;
+  const int smem = (int)sizeof(FrontendSmem);
+  static bool attr_done = false;
+  if (!attr_done) {
+    AVSI_CUDA(cudaFuncSetAttribute(frontend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_done = true;
+  }
+  long long grid = (long long)num_sms() * 4;
+  if (grid > groups) grid = groups;
+  frontend_kernel<<<(unsigned)grid, FE_THREADS, smem, (cudaStream_t)stream>>>(*a);
+  AVSI_LAUNCH_CHECK();
+  return AVSI_OK;
+}

@@ -1,0 +1,469 @@
+// fp16 x fp16 -> fp32 GEMM on the 5th-gen tensor cores (tcgen05.mma kind::f16, cta_group::1).
+//
+// Replaces the cuBLAS/cuDNN contractions behind CudnnLSTM's input projections
+// (models.py:95-104), the tf.matmul heads (models.py:117-123, 1902-1912) and their gradients.
+//
+// Structure (one 128 x BN output tile per CTA, 2 CTAs co-resident per SM so one CTA's
+// epilogue overlaps the other's main loop):
+//   warp 0      TMA producer: cp.async.bulk.tensor.2d (SWIZZLE_128B) into a STAGES-deep ring
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer, tcgen05.commit -> mbarriers
+//   warps 2..5  epilogue: tcgen05.ld (32 lanes x 32 columns) -> registers -> global
+// Operand layouts:
+//   trans == 0  A [M,K], B [N,K] row-major  -> K-major smem tiles   (box 64(k) x rows)
+//   trans == 1  A [K,M], B [K,N] row-major  -> MN-major smem tiles  (boxes 64(mn) x 64(k))
+// Shared-memory matrix descriptors follow the canonical SWIZZLE_128B layouts
+// (K-major: SBO = 1024 B; MN-major: SBO = 1024 B, LBO = 8192 B), version = 1 (sm_100).
+#include <cuda.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+
+namespace avsi {
+
+constexpr int GEMM_BM = 128;
+constexpr int GEMM_BK = 64;
+constexpr int GEMM_THREADS = 192;
+
+struct GemmParams {
+  void* C;
+  const float* bias;
+  int ldc, M, N, K;
+  int trans, out_mode, split_k;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// tcgen05.commit: arrives on the mbarrier once all previously issued MMAs have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// [0,14) addr>>4, [16,30) LBO>>4, [32,46) SBO>>4, [46,48) version=1, [61,64) layout (2 = SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 = 1 @4, a/b_format F16 = 0 @7/@10,
+// a_major @15, b_major @16 (1 = MN-major), N>>3 @17, M>>4 @24.
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+
+template <int BN, int STAGES>
+struct GemmSmem {
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;   // 16 KB
+  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;    // barriers + alignment slack
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS)
+gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
+  using S = GemmSmem<BN, STAGES>;
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + S::BAR_OFFSET;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * STAGES);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 1);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_dyn + (tmem_slot - smem_u32(smem_dyn)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const int m_blk = blockIdx.x / n_tiles;
+  const int n_blk = blockIdx.x % n_tiles;
+  const int kb_total = (p.K + GEMM_BK - 1) / GEMM_BK;
+  const int chunk = (kb_total + p.split_k - 1) / p.split_k;
+  const int kb0 = blockIdx.y * chunk;
+  const int kb1 = min(kb_total, kb0 + chunk);
+  const int nkb = kb1 - kb0;
+  if (nkb <= 0) return;   // uniform for the whole CTA
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(empty_bar(s), ph ^ 1);
+        const uint32_t sa = smem_base + s * S::STAGE_BYTES;
+        const uint32_t sb = sa + S::A_BYTES;
+        mbar_expect_tx(full_bar(s), S::STAGE_BYTES);
+        const int k0 = (kb0 + i) * GEMM_BK;
+        if (p.trans == 0) {
+          tma_load_2d(sa, &tmA, full_bar(s), k0, m_blk * GEMM_BM);
+          tma_load_2d(sb, &tmB, full_bar(s), k0, n_blk * BN);
+        } else {
+#pragma unroll
+          for (int a = 0; a < GEMM_BM / 64; ++a) tma_load_2d(sa + a * 8192, &tmA, full_bar(s), m_blk * GEMM_BM + 64 * a, k0);
+#pragma unroll
+          for (int b = 0; b < BN / 64; ++b) tma_load_2d(sb + b * 8192, &tmB, full_bar(s), n_blk * BN + 64 * b, k0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(GEMM_BM, BN, p.trans, p.trans);
+      const uint32_t lbo = p.trans ? 8192u : 0u;
+      const uint32_t kstep = p.trans ? 2048u : 32u;   // bytes per UMMA_K = 16 advance
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t sa = smem_base + s * S::STAGE_BYTES;
+        const uint32_t sb = sa + S::A_BYTES;
+#pragma unroll
+        for (int k = 0; k < GEMM_BK / 16; ++k) {
+          const uint64_t da = make_smem_desc(sa + k * kstep, lbo, 1024u);
+          const uint64_t db = make_smem_desc(sb + k * kstep, lbo, 1024u);
+          umma_f16(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(empty_bar(s));               // frees the smem slot when these MMAs retire
+      }
+      umma_commit(tmem_full_bar);                // accumulator complete
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..5)
+    const int quarter = warp & 3;                // TMEM lane quarter this warp may access
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int row = m_blk * GEMM_BM + quarter * 32 + lane;
+    const bool row_ok = row < p.M;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32), r);
+      tmem_ld_wait();
+      const int n0 = n_blk * BN + c * 32;
+      if (!row_ok || n0 >= p.N) continue;
+      const bool full = (n0 + 32 <= p.N);
+      if (p.out_mode == 0) {
+        uint16_t* dst = reinterpret_cast<uint16_t*>(p.C) + (long long)row * p.ldc + n0;
+        if (full && (p.ldc % 8 == 0)) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 v;
+            v.x = pack_half2(__uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1]));
+            v.y = pack_half2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]));
+            v.z = pack_half2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]));
+            v.w = pack_half2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
+            reinterpret_cast<uint4*>(dst)[j] = v;
+          }
+        } else {
+          for (int j = 0; j < 32; ++j)
+            if (n0 + j < p.N) dst[j] = __half_as_ushort(__float2half_rn(__uint_as_float(r[j])));
+        }
+      } else if (p.out_mode == 1) {
+        float* dst = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + n0;
+        if (full && (p.ldc % 4 == 0)) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 v;
+            v.x = __uint_as_float(r[4 * j + 0]);
+            v.y = __uint_as_float(r[4 * j + 1]);
+            v.z = __uint_as_float(r[4 * j + 2]);
+            v.w = __uint_as_float(r[4 * j + 3]);
+            if (p.bias) {
+              v.x += __ldg(p.bias + n0 + 4 * j + 0);
+              v.y += __ldg(p.bias + n0 + 4 * j + 1);
+              v.z += __ldg(p.bias + n0 + 4 * j + 2);
+              v.w += __ldg(p.bias + n0 + 4 * j + 3);
+            }
+            reinterpret_cast<float4*>(dst)[j] = v;
+          }
+        } else {
+          for (int j = 0; j < 32; ++j)
+            if (n0 + j < p.N) dst[j] = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + n0 + j) : 0.f);
+        }
+      } else {
+        float* dst = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + n0;
+        for (int j = 0; j < 32; ++j)
+          if (n0 + j < p.N) atomicAdd(dst + j, __uint_as_float(r[j]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// ---------------------------------------------------------------- debug / validation GEMM (CUDA cores)
+// Same contract as the tensor-core kernel; selected only by AVSI_GEMM_DEBUG_SIMT=1 to bisect
+// failures.  Never used silently.
+__global__ void __launch_bounds__(256)
+gemm_simt_kernel(const uint16_t* __restrict__ A, int lda, const uint16_t* __restrict__ B, int ldb, GemmParams p) {
+  __shared__ float sa[16][17], sb[16][17];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int row = blockIdx.y * 16 + ty, col = blockIdx.x * 16 + tx;
+  float acc = 0.f;
+  for (int k0 = 0; k0 < p.K; k0 += 16) {
+    // sa[ty][tx] = A(row, k0+tx) ; sb[ty][tx] = B(col_of_ty.., k0+tx)
+    int ar = blockIdx.y * 16 + ty, ak = k0 + tx;
+    int bn = blockIdx.x * 16 + ty, bk = k0 + tx;
+    float av = 0.f, bv = 0.f;
+    if (ar < p.M && ak < p.K)
+      av = __half2float(__ushort_as_half(p.trans ? A[(long long)ak * lda + ar] : A[(long long)ar * lda + ak]));
+    if (bn < p.N && bk < p.K)
+      bv = __half2float(__ushort_as_half(p.trans ? B[(long long)bk * ldb + bn] : B[(long long)bn * ldb + bk]));
+    sa[ty][tx] = av;
+    sb[ty][tx] = bv;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc = fmaf(sa[ty][k], sb[tx][k], acc);
+    __syncthreads();
+  }
+  if (row < p.M && col < p.N) {
+    if (p.out_mode == 0)
+      reinterpret_cast<uint16_t*>(p.C)[(long long)row * p.ldc + col] = __half_as_ushort(__float2half_rn(acc));
+    else if (p.out_mode == 1)
+      reinterpret_cast<float*>(p.C)[(long long)row * p.ldc + col] = acc + (p.bias ? p.bias[col] : 0.f);
+    else
+      atomicAdd(reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + col, acc);
+  }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+struct TmapKey {
+  const void* ptr;
+  uint64_t d0, d1, ld;
+  uint32_t b0, b1;
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && ld == o.ld && b0 == o.b0 && b1 == o.b1;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = std::hash<const void*>()(k.ptr);
+    h = h * 1000003u ^ std::hash<uint64_t>()(k.d0 * 31 + k.d1);
+    h = h * 1000003u ^ std::hash<uint64_t>()(k.ld * 131 + k.b0 * 7 + k.b1);
+    return h;
+  }
+};
+
+// 2-D fp16 tensor map: dims {d0 (contiguous), d1}, row pitch ld elements, box {b0, b1}, 128B swizzle.
+static int get_tmap(const void* ptr, uint64_t d0, uint64_t d1, uint64_t ld, uint32_t b0, uint32_t b1, CUtensorMap* out) {
+  static std::mutex mu;
+  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  TmapKey key{ptr, d0, d1, ld, b0, b1};
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *out = it->second;
+    return AVSI_OK;
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return set_error(AVSI_ERR_CUDA, "%s: cuTensorMapEncodeTiled entry point unavailable%s", "get_tmap");
+  cuuint64_t dims[2] = {d0, d1};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {b0, b1};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[64];
+    snprintf(buf, sizeof(buf), "%d", (int)r);
+    return set_error(AVSI_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed, CUresult %s", "get_tmap", buf);
+  }
+  if (cache.size() > 4096) cache.clear();
+  cache[key] = m;
+  *out = m;
+  return AVSI_OK;
+}
+
+template <int BN, int STAGES>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+  using S = GemmSmem<BN, STAGES>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    AVSI_CUDA(cudaFuncSetAttribute(gemm_f16_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    attr_done = true;
+  }
+  dim3 grid(((p.M + GEMM_BM - 1) / GEMM_BM) * ((p.N + BN - 1) / BN), p.split_k);
+  gemm_f16_kernel<BN, STAGES><<<grid, GEMM_THREADS, S::TOTAL, st>>>(ta, tb, p);
+  AVSI_LAUNCH_CHECK();
+  return AVSI_OK;
+}
+
+}  // namespace avsi
+
+extern "C" int avsi_gemm_f16(const uint16_t* A, int lda, const uint16_t* B, int ldb, void* C, int ldc,
+                             const float* bias, int M, int N, int K, int trans, int out_mode, int split_k,
+                             void* stream) {
+  using namespace avsi;
+  AVSI_REQUIRE(A && B && C, "null pointer");
+  AVSI_REQUIRE(M > 0 && N > 0 && K > 0, "M,N,K > 0");
+  AVSI_REQUIRE(trans == 0 || trans == 1, "trans");
+  AVSI_REQUIRE(out_mode >= 0 && out_mode <= 2, "out_mode");
+  AVSI_REQUIRE(split_k >= 1 && (split_k == 1 || out_mode == 2), "split_k > 1 needs out_mode 2");
+  AVSI_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "lda/ldb multiples of 8");
+  AVSI_REQUIRE(((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0), "A/B 16-byte aligned");
+  AVSI_REQUIRE(ldc >= N, "ldc >= N");
+  GemmParams p{C, bias, ldc, M, N, K, trans, out_mode, split_k};
+  cudaStream_t st = (cudaStream_t)stream;
+
+  static int debug_simt = -1;
+  if (debug_simt < 0) {
+    const char* e = getenv("AVSI_GEMM_DEBUG_SIMT");
+    debug_simt = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (debug_simt) {
+    GemmParams q = p;
+    q.split_k = 1;
+    dim3 grid((N + 15) / 16, (M + 15) / 16);
+    gemm_simt_kernel<<<grid, 256, 0, st>>>(A, lda, B, ldb, q);
+    AVSI_LAUNCH_CHECK();
+    return AVSI_OK;
+  }
+
+  // tile width: wide tiles for wide outputs, narrow ones so that small-N problems still fill the chip
+  // tile width: 128 (3 stages, 2 CTAs/SM) by default; 256 (4 stages, 1 CTA/SM) for long-K problems
+  // where the main loop dominates; 64 for narrow outputs.  AVSI_GEMM_BN overrides (tuning only).
+  static int bn_env = -1;
+  if (bn_env < 0) {
+    const char* e = getenv("AVSI_GEMM_BN");
+    bn_env = e ? atoi(e) : 0;
+  }
+  int bn = 128;
+  if (N > 128 && K >= 4096) bn = 256;
+  if (N <= 64) bn = 64;
+  if (bn_env == 64 || bn_env == 128 || bn_env == 256) bn = bn_env;
+  CUtensorMap ta, tb;
+  int rc;
+  if (trans == 0) {
+    rc = get_tmap(A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, GEMM_BK, GEMM_BM, &ta);
+    if (rc) return rc;
+    rc = get_tmap(B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, GEMM_BK, (uint32_t)bn, &tb);
+    if (rc) return rc;
+  } else {
+    rc = get_tmap(A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, GEMM_BK, &ta);
+    if (rc) return rc;
+    rc = get_tmap(B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, GEMM_BK, &tb);
+    if (rc) return rc;
+  }
+  if (bn == 256) return launch_gemm<256, 4>(ta, tb, p, st);
+  if (bn == 128) return launch_gemm<128, 3>(ta, tb, p, st);
+  return launch_gemm<64, 4>(ta, tb, p, st);
+}

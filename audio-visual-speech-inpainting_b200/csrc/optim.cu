@@ -1,0 +1,95 @@
+// Optimiser update (TF1 AdamOptimizer semantics) and fp32 -> fp16 weight copies.
+//
+// avsi_adam_tf replaces the per-variable ApplyAdam kernels behind
+// tf.train.AdamOptimizer(...).minimize (models.py:168,178): ONE launch over the flat
+// parameter buffer.  epsilon is added to the uncorrected sqrt(v) ("epsilon hat").
+#include "common.cuh"
+
+namespace avsi {
+
+__global__ void __launch_bounds__(256)
+adam_tf_kernel(float* __restrict__ theta, const float* __restrict__ g, float* __restrict__ m,
+               float* __restrict__ v, long long n, float lr_t, float b1, float b2, float eps,
+               float unscale, const float* __restrict__ unscale_dev, float l2) {
+  const float us = unscale * (unscale_dev ? *unscale_dev : 1.f);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float th = theta[i];
+    float gi = fmaf(g[i], us, l2 * th);
+    float mi = b1 * m[i] + (1.f - b1) * gi;
+    float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    theta[i] = th - lr_t * mi / (sqrtf(vi) + eps);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+cast_weights_kernel(const float* __restrict__ w, int R, int C, uint16_t* __restrict__ w16,
+                    uint16_t* __restrict__ w16t) {
+  // 32x32 tile transpose through shared memory; also writes the straight copy
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int r = r0 + ty + 8 * i, c = c0 + tx;
+    float x = (r < R && c < C) ? w[(long long)r * C + c] : 0.f;
+    tile[ty + 8 * i][tx] = x;
+    if (w16 && r < R && c < C) w16[(long long)r * C + c] = __half_as_ushort(__float2half_rn(x));
+  }
+  if (!w16t) return;
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int c = c0 + ty + 8 * i, r = r0 + tx;
+    if (r < R && c < C) w16t[(long long)c * R + r] = __half_as_ushort(__float2half_rn(tile[tx][ty + 8 * i]));
+  }
+}
+
+__global__ void mtl_scales_kernel(const float* __restrict__ hole_count, int B, float ctc_w, float* __restrict__ out) {
+  // out[0] = S  (scale of the L1 dlogits), out[1] = S * (w/B) * holes (scale of the CTC dlogits),
+  // out[2] = 1 / (S * holes)  (optimiser unscale), out[3] = holes
+  float holes = fmaxf(*hole_count, 1.f);
+  float rel = ctc_w / (float)B * holes;         // CTC gradient relative to the +-1 L1 gradient
+  float S = 1.f;
+  while (rel * S > 64.f) S *= 0.5f;             // keep fp16 dlogits far from 65504
+  out[0] = S;
+  out[1] = S * rel;
+  out[2] = 1.f / (S * holes);
+  out[3] = holes;
+}
+
+}  // namespace avsi
+
+extern "C" int avsi_adam_tf(float* theta, const float* g, float* m, float* v, int64_t n, float lr, float b1,
+                            float b2, float eps, int step, float grad_unscale, const float* grad_unscale_dev,
+                            float l2, void* stream) {
+  using namespace avsi;
+  AVSI_REQUIRE(theta && g && m && v, "null pointer");
+  AVSI_REQUIRE(n > 0 && step >= 1, "n > 0, step >= 1");
+  // lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t), evaluated in double on the host
+  double lr_t = (double)lr * sqrt(1.0 - pow((double)b2, (double)step)) / (1.0 - pow((double)b1, (double)step));
+  int blocks = (int)min((long long)(n + 255) / 256, (long long)num_sms() * 8);
+  adam_tf_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(theta, g, m, v, (long long)n, (float)lr_t, b1, b2, eps,
+                                                          grad_unscale, grad_unscale_dev, l2);
+  AVSI_LAUNCH_CHECK();
+  return AVSI_OK;
+}
+
+extern "C" int avsi_cast_weights(const float* w, int R, int C, uint16_t* w16, uint16_t* w16t, void* stream) {
+  using namespace avsi;
+  AVSI_REQUIRE(w && (w16 || w16t), "null pointer");
+  AVSI_REQUIRE(R > 0 && C > 0, "sizes");
+  dim3 grid((C + 31) / 32, (R + 31) / 32);
+  cast_weights_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, R, C, w16, w16t);
+  AVSI_LAUNCH_CHECK();
+  return AVSI_OK;
+}
+
+extern "C" int avsi_mtl_scales(const float* hole_count, int B, float ctc_weight, float* out, void* stream) {
+  using namespace avsi;
+  AVSI_REQUIRE(hole_count && out && B > 0, "args");
+  mtl_scales_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(hole_count, B, ctc_weight, out);
+  AVSI_LAUNCH_CHECK();
+  return AVSI_OK;
+}

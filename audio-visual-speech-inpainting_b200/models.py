@@ -1,0 +1,407 @@
+"""Speech-inpainting BLSTM models with the reference's class names, constructor signatures and
+attribute names (models.py:11-237 StackedBLSTMModel = A-SI / V-SI / AV-SI; models.py:1741-2047
+StackedBLSTMSSNNCTCLossModel = the runnable multi-task model).
+
+The reference builds a TF graph once from placeholders and feeds it every step; here the model
+object is built once from the config and fed every step with ``feed(...)`` (same names as the
+reference's placeholders, training_ctc.py:67-77).  Attributes (``inference``, ``prediction``,
+``loss``, ``loss_hole``, ``enhanced_sources`` ...) evaluate lazily on the fed batch and are
+cached until the next ``feed``; ``train_op()`` runs forward + backward + optimiser update.
+All arithmetic runs in the sm_100a kernels of libavsi_b200.so; there is no autograd and no
+CPU fallback.
+"""
+import sys
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import audio_processing as ap
+from .blstm import BLSTMEngine, NY
+from .layout import init_canonical
+
+_p = _lib.ptr
+
+
+class StackedBLSTMModel(object):
+    """
+    Speech inpainting BLSTM model
+    Input: log-compressed linear spectrogram of corrupted audio (+ landmark motion vectors).
+    Model: stacked BLSTM.  Output: log-compressed linear spectrogram of restored audio.
+    Loss: L1 (target_spectrogram - reconstructed_spectrogram)       [models.py:11-18]
+    """
+    MTL = False
+
+    def __init__(self, sequence_lengths, target_sources, masks, audio_feat_mean, audio_feat_std, dropout_rate,
+                 config, audio_features=None, video_features=None, input='a', is_training=True, device='cuda',
+                 process_group=None):
+        if audio_features is not None:
+            raise NotImplementedError('precomputed audio_features (two-step model) are out of scope')
+        if input not in ('a', 'v', 'av'):
+            raise ValueError("input must be 'a', 'v' or 'av'")
+        self.config = config
+        self.audio_feat_dim = config['audio_feat_dim']
+        self.video_feat_dim = config.get('video_feat_dim', 136)
+        self.audio_len = config['audio_len']
+        self.input_type = input
+        self.net_dim = config['net_dim']
+        if len(set(self.net_dim)) != 1:
+            # the reference passes net_dim[0] to every layer (models.py:96-97)
+            raise ValueError('net_dim must be uniform (the reference uses net_dim[0] for all layers)')
+        self.num_layers = len(self.net_dim)
+        self.optimizer_choice = config.get('optimizer_type', 'adam')
+        self.starter_learning_rate = config.get('starter_learning_rate', 1e-3)
+        self.updating_step = config.get('lr_updating_steps', 10000)
+        self.learning_decay = config.get('lr_decay', 1.0)
+        self.regularization = config.get('l2', 0.0)
+        self.is_training = is_training
+        self.batch_size = config.get('batch_size', 1)
+        self.device = torch.device(device)
+        self.process_group = process_group
+        self.var_scope = ''
+        self.frame_len = ap.ms_to_samples(24, 16000)      # models.py:31 window_size=24, step_size=12
+        self.hop = ap.ms_to_samples(12, 16000)
+        in_dim = {'a': self.audio_feat_dim, 'v': self.video_feat_dim,
+                  'av': self.audio_feat_dim + self.video_feat_dim}[input]
+        self.num_classes = config['num_asr_labels'] if self.MTL else 0
+        self.engine = BLSTMEngine(in_dim, self.net_dim[0], self.num_layers, self.audio_feat_dim, self.num_classes,
+                                  device=self.device)
+        self.engine.load_canonical(init_canonical(self.engine.layout, seed=config.get('seed', 0)))
+        self.global_step = 0
+        self._sums = torch.zeros(8, dtype=torch.float64, device=self.device)
+        self._cache = {}
+        self._fed = {}
+        self.feed(sequence_lengths=sequence_lengths, target_sources=target_sources, masks=masks,
+                  audio_features_mean=audio_feat_mean, audio_features_std=audio_feat_std,
+                  dropout_rate=dropout_rate, video_features=video_features)
+
+    # ---- feed contract (training_ctc.py:67-77, 264-275) -------------------------------------------
+    def _to_dev(self, x, dtype):
+        if x is None:
+            return None
+        if not torch.is_tensor(x):
+            x = torch.as_tensor(np.asarray(x))
+        return x.to(device=self.device, dtype=dtype, non_blocking=True).contiguous()
+
+    def feed(self, **kw):
+        """Set the tensors of the next batch; unknown names raise.  None values are ignored."""
+        f32 = ('target_sources', 'masks', 'audio_features_mean', 'audio_features_std', 'video_features')
+        i32 = ('sequence_lengths', 'labels_lengths', 'labels')
+        for k, v in kw.items():
+            if v is None:
+                continue
+            if k in f32:
+                self._fed[k] = self._to_dev(v, torch.float32)
+            elif k in i32:
+                self._fed[k] = self._to_dev(v, torch.int32)
+            elif k == 'dropout_rate':
+                if float(v) != 0.0:
+                    raise NotImplementedError('dropout_rate != 0 is not supported (0.0 in every shipped config)')
+                self._fed[k] = 0.0
+            else:
+                raise KeyError('unknown feed name %r' % k)
+        self._cache = {}
+        return self
+
+    def _need(self, *names):
+        for n in names:
+            if n not in self._fed:
+                raise _lib.AvsiError('tensor %r has not been fed' % n)
+        return [self._fed[n] for n in names]
+
+    # ---- front end (models.py:30-45) -----------------------------------------------------------------
+    def _front(self, want_stft=False):
+        key = 'front_stft' if want_stft else 'front'
+        if key in self._cache:
+            return self._cache[key]
+        wav, masks, mean, std, seq = self._need('target_sources', 'masks', 'audio_features_mean',
+                                                'audio_features_std', 'sequence_lengths')
+        B = wav.shape[0]
+        T = masks.shape[1]                   # = max(sequence_lengths) in the reference's feed
+        video = self._fed.get('video_features') if self.input_type in ('v', 'av') else None
+        if self.input_type != 'a' and video is None:
+            raise _lib.AvsiError("video_features must be fed for input='%s'" % self.input_type)
+        ws = self.engine.workspace(T, B, self.is_training)
+        hole = None
+        if self.MTL:
+            hole = self._cache.setdefault('hole', torch.zeros(1, dtype=torch.float32, device=self.device))
+            hole.zero_()
+        res = ap.fused_features(wav, self.frame_len, self.hop, T=T, F=self.audio_feat_dim, mean=mean, std=std,
+                                mask=masks, video=video, power=1.0, log=True, want_stft=want_stft, want_spec=True,
+                                xh_out=ws['x0'], ldx=self.engine.layout.k0p, hole_count=hole,
+                                xh_video_only=(self.input_type == 'v'))
+        out = {'ws': ws, 'B': B, 'T': T, 'target_spec_norm': res['spec'], 'target_stft': res['stft'], 'hole': hole}
+        self._cache[key] = out
+        if want_stft:
+            self._cache['front'] = out
+        return out
+
+    @property
+    def target_spec_norm(self):
+        return self._front()['target_spec_norm']
+
+    @property
+    def target_stft(self):
+        return self._front(want_stft=True)['target_stft']
+
+    @property
+    def net_inputs(self):
+        """fp32 [B,T,I] view of the network input (the kernels consume the fp16 time-major copy)."""
+        fr = self._front()
+        L = self.engine.layout
+        x = fr['ws']['x0'].view(fr['T'], fr['B'], L.k0p)[:, :, :L.in_dim]
+        return x.permute(1, 0, 2).float()
+
+    # ---- network (models.py:89-125) ----------------------------------------------------------------
+    def _logits(self):
+        if 'logits' not in self._cache:
+            fr = self._front()
+            self._cache['logits'] = self.engine.forward(fr['ws'])
+        return self._cache['logits']
+
+    def _bt(self, lo, n):
+        fr = self._front()
+        lg = self._logits().view(fr['T'], fr['B'], -1)[:, :, lo:lo + n]
+        return lg.permute(1, 0, 2).contiguous()
+
+    @property
+    def inference(self):
+        return self._bt(0, self.audio_feat_dim)
+
+    # ---- loss (models.py:127-159) --------------------------------------------------------------------
+    def _loss_pass(self, want_grad):
+        key = 'loss_grad' if want_grad else 'loss'
+        if key in self._cache:
+            return self._cache[key]
+        if 'loss_grad' in self._cache:
+            return self._cache['loss_grad']
+        lib = _lib.load()
+        fr = self._front()
+        ws, B, T = fr['ws'], fr['B'], fr['T']
+        F = self.audio_feat_dim
+        logits = self._logits()
+        masks, seq = self._need('masks', 'sequence_lengths')
+        L = self.engine.layout
+        self._sums.zero_()
+        pred = torch.empty(B, T, F, dtype=torch.float32, device=self.device)
+        out = {'prediction': pred}
+        scales = None
+        if self.MTL:
+            scales = torch.empty(4, dtype=torch.float32, device=self.device)
+            hole = fr['hole']
+            world = 1
+            if self.process_group is not None:
+                import torch.distributed as dist
+                dist.all_reduce(hole, group=self.process_group)
+                world = dist.get_world_size(self.process_group)
+            _lib.check(lib.avsi_mtl_scales(_p(hole), B * world, float(self.ctc_loss_weight), _p(scales),
+                                           _lib.stream_ptr()), 'avsi_mtl_scales')
+        dl = ws['dlogits'] if (want_grad and 'dlogits' in ws) else None
+        _lib.check(lib.avsi_masked_l1(_p(logits), L.nop, _p(fr['target_spec_norm']), _p(masks), _p(seq), B, T, F,
+                                      1 if self.MTL else 0, 1.0, _p(scales) if self.MTL else None, _p(self._sums),
+                                      _p(pred), _p(dl), L.nop, _lib.stream_ptr()), 'avsi_masked_l1')
+        if self.MTL:
+            labels, lab_len = self._need('labels', 'labels_lengths')
+            Lmax = labels.shape[1]
+            nbytes = int(lib.avsi_ctc_workspace_bytes(B, T, Lmax))
+            wsc = ws.get('ctc_ws')
+            if wsc is None or wsc.numel() * 4 < nbytes:
+                wsc = ws['ctc_ws'] = torch.empty(nbytes // 4 + 4, dtype=torch.float32, device=self.device)
+            nll = torch.empty(B, dtype=torch.float32, device=self.device)
+            scale_ptr = (scales.data_ptr() + 4) if dl is not None else None
+            _lib.check(lib.avsi_ctc_loss(_p(logits), L.nop, F, self.num_classes, _p(labels), Lmax, _p(lab_len),
+                                         _p(seq), B, T, 1.0, scale_ptr, _p(nll), _p(dl), L.nop, F, _p(wsc),
+                                         _lib.stream_ptr()), 'avsi_ctc_loss')
+            out['ctc_nll'] = nll
+            out['scales'] = scales
+        out['sums'] = self._sums
+        self._cache[key] = out
+        return out
+
+    @property
+    def prediction(self):
+        return self._loss_pass(False)['prediction']
+
+    def _sum(self, i):
+        return self._loss_pass(False)['sums'][i]
+
+    @property
+    def loss_hole(self):
+        return (self._sum(0) / self._sum(1)).float()
+
+    @property
+    def loss_valid(self):
+        return (self._sum(2) / self._sum(3)).float()
+
+    @property
+    def loss_func(self):
+        return (self._sum(4) / self._sum(5)).float()                     # models.py:151
+
+    @property
+    def reg_loss(self):
+        if not self.regularization:
+            return torch.zeros((), device=self.device)
+        n = self.engine.layout.n_params_padded
+        return 0.5 * (self.engine.theta[:n] ** 2).sum()                  # models.py:153-154 (padding is zero)
+
+    @property
+    def loss(self):
+        return self.loss_func + self.regularization * self.reg_loss      # models.py:158
+
+    @property
+    def learning_rate(self):
+        # exponential_decay(staircase=True); Adam is given the constant starter rate (models.py:165-168)
+        return self.starter_learning_rate * self.learning_decay ** (self.global_step // self.updating_step)
+
+    # ---- training step (models.py:161-179) ---------------------------------------------------------------
+    def _grad_unscale(self, out, world):
+        """(host factor, device factor) turning the scaled gradient sum into d loss / d theta."""
+        fr = self._front()
+        return 1.0 / (fr['B'] * world * fr['T'] * self.audio_feat_dim), None
+
+    def compute_gradients(self):
+        """forward + loss + backward; leaves the (scaled) gradient in engine.grad."""
+        if not self.is_training:
+            raise _lib.AvsiError('model was built with is_training=False')
+        out = self._loss_pass(True)
+        self.engine.backward(self._front()['ws'])
+        return out
+
+    def train_op(self):
+        if self.optimizer_choice != 'adam':
+            print('Optimizer must be adam in this build (sgd / momentum not implemented). Closing...')
+            sys.exit(1)
+        out = self.compute_gradients()
+        world = 1
+        if self.process_group is not None:
+            import torch.distributed as dist
+            world = dist.get_world_size(self.process_group)
+            n = self.engine.layout.n_params_padded
+            self.engine.grad[n:n + 6].copy_(out['sums'][:6].float())      # loss scalars ride along
+            dist.all_reduce(self.engine.grad, group=self.process_group)
+        host, dev = self._grad_unscale(out, world)
+        self.engine.adam_step(lr=self.starter_learning_rate, grad_unscale=host, unscale_dev=dev,
+                              l2=self.regularization)
+        self.global_step += 1
+
+    def canonical_gradients(self):
+        """d loss / d variable in the reference's canonical layout (float64 numpy), for parity tests."""
+        out = self.compute_gradients()
+        host, dev = self._grad_unscale(out, 1)
+        if dev is not None:
+            host = host * float(dev.item())
+        return self.engine.export_canonical_grads(host)
+
+    # ---- waveform reconstruction (models.py:181-197) -----------------------------------------------------
+    def _enhanced(self, oracle_phase):
+        mean, std, masks = self._need('audio_features_mean', 'audio_features_std', 'masks')
+        return ap.reconstruct_from(self.prediction, self.target_stft, mask=None if oracle_phase else masks,
+                                   mean=mean, std=std, num_samples=self.audio_len)
+
+    @property
+    def enhanced_sources(self):
+        return self._enhanced(False)
+
+    @property
+    def enhanced_sources_oracle_phase(self):
+        return self._enhanced(True)
+
+    # ---- variables / checkpoints --------------------------------------------------------------
+    def build_graph(self, var_scope=''):
+        self.var_scope = var_scope
+
+    def _scoped(self, name):
+        return (self.var_scope + '/' + name) if self.var_scope else name
+
+    @property
+    def train_vars(self):
+        return {self._scoped(k): v for k, v in self.engine.export_canonical().items()}
+
+    @property
+    def all_vars(self):
+        v = self.train_vars
+        v[self._scoped('Variable')] = np.asarray(self.global_step, np.int32)
+        return v
+
+    def assign_vars(self, variables):
+        """Load canonical variables (names with or without the scope prefix)."""
+        want = self.engine.layout.canonical_shapes()
+        got = {}
+        for k in want:
+            for cand in (self._scoped(k), k):
+                if cand in variables:
+                    got[k] = np.asarray(variables[cand])
+                    break
+        self.engine.load_canonical(got)
+        gs = variables.get(self._scoped('Variable'), variables.get('Variable'))
+        if gs is not None:
+            self.global_step = int(gs)
+        self._cache = {}
+
+
+class StackedBLSTMSSNNCTCLossModel(StackedBLSTMModel):
+    """Multi-task model: inpainting head + phone-recognition head with CTC loss
+    (models.py:1741-2047).  The speaker-embedding MLP of that class is dead w.r.t. the loss in
+    the reference and is not built."""
+    MTL = True
+
+    def __init__(self, sequence_lengths, labels_lengths, target_sources, masks, labels, audio_feat_mean,
+                 audio_feat_std, dropout_rate, config, audio_features=None, video_features=None, input='a',
+                 apply_mask=False, is_training=True, device='cuda', process_group=None):
+        self.ctc_loss_weight = config.get('ctc_loss', 1)
+        super(StackedBLSTMSSNNCTCLossModel, self).__init__(
+            sequence_lengths, target_sources, masks, audio_feat_mean, audio_feat_std, dropout_rate, config,
+            audio_features=audio_features, video_features=video_features, input=input, is_training=is_training,
+            device=device, process_group=process_group)
+        self.feed(labels_lengths=labels_lengths, labels=labels)
+
+    @property
+    def inference(self):
+        return self._bt(0, self.audio_feat_dim), self._bt(self.audio_feat_dim, self.num_classes)
+
+    @property
+    def ctc_loss(self):
+        return self._loss_pass(False)['ctc_nll'].mean()                   # models.py:1950-1953
+
+    @property
+    def loss_func(self):
+        return self.loss_hole + self.ctc_loss_weight * self.ctc_loss      # models.py:1955
+
+    def _grad_unscale(self, out, world):
+        return 1.0, out['scales'][2:3]
+
+    @property
+    def decoding(self):
+        """Best-path (greedy) CTC decoding; the reference's beam search (width 20, models.py:1627) is a
+        monitoring op kept off the training hot loop."""
+        fr = self._front()
+        logits = self._logits().view(fr['T'], fr['B'], -1)[:, :, self.audio_feat_dim:self.audio_feat_dim + self.num_classes]
+        best = logits.argmax(dim=2).t().cpu().numpy()
+        seq = self._fed['sequence_lengths'].cpu().numpy()
+        blank = self.num_classes - 1
+        outs = []
+        for b in range(best.shape[0]):
+            prev, seqo = -1, []
+            for k in best[b, :int(seq[b])]:
+                if k != prev and k != blank:
+                    seqo.append(int(k))
+                prev = k
+            outs.append(seqo)
+        width = max([len(o) for o in outs] + [1])
+        dense = -np.ones((len(outs), width), np.int32)
+        for b, o in enumerate(outs):
+            dense[b, :len(o)] = o
+        return dense
+
+
+# In the reference, StackedBLSTMCTCLossModel.inference is broken (models.py:1565-1566 uses an undefined
+# attribute); its intended semantics are those of the SSNN-CTC class without the embedding.
+StackedBLSTMCTCLossModel = StackedBLSTMSSNNCTCLossModel
+
+MODEL_REGISTRY = {
+    'a-blstm': (StackedBLSTMModel, 'a'), 'v-blstm': (StackedBLSTMModel, 'v'), 'av-blstm': (StackedBLSTMModel, 'av'),
+    'a-blstm-ctc': (StackedBLSTMCTCLossModel, 'a'), 'v-blstm-ctc': (StackedBLSTMCTCLossModel, 'v'),
+    'av-blstm-ctc': (StackedBLSTMCTCLossModel, 'av'),
+    'a-blstm-ssnn-ctc': (StackedBLSTMSSNNCTCLossModel, 'a'), 'v-blstm-ssnn-ctc': (StackedBLSTMSSNNCTCLossModel, 'v'),
+    'av-blstm-ssnn-ctc': (StackedBLSTMSSNNCTCLossModel, 'av'),
+}

@@ -1,0 +1,192 @@
+/*
+ * avsi_b200.h -- C ABI of the B200-native audio-visual speech-inpainting hot path.
+ *
+ * Drop-in boundary.  The reference
+ * (dr-pato/audio-visual-speech-inpainting, paths below are relative to
+ * av_speech_inpainting/) has no FFI of its own: its hot path is reached through
+ * Python functions / classes whose arithmetic is delegated to TensorFlow library
+ * kernels.  Each entry point here replaces one such group of TF call sites and is
+ * bound from Python with ctypes (audio-visual-speech-inpainting_b200/_lib.py); the
+ * Python shims keep the reference's names and signatures.
+ *
+ * Conventions
+ *   - every pointer is CALLER-OWNED DEVICE memory (row-major), no allocation inside;
+ *   - every call enqueues work on `stream` (a cudaStream_t passed as void*) and
+ *     returns immediately; 0 = ok, negative = error (avsi_last_error() has the text);
+ *   - fp16 tensors are IEEE binary16 (`uint16_t` storage); "time-major" means row
+ *     index r = t * B + b;
+ *   - thread-safe per stream; no global state except lazily cached TMA descriptors.
+ */
+#ifndef AVSI_B200_H_
+#define AVSI_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AVSI_OK 0
+#define AVSI_ERR_INVALID (-1)
+#define AVSI_ERR_CUDA (-2)
+#define AVSI_ERR_UNSUPPORTED (-3)
+
+/* Text of the last error raised on the calling thread ("" if none). */
+const char* avsi_last_error(void);
+/* Library version / build info string (arch, build flags). */
+const char* avsi_version(void);
+/* Number of kernel launches issued by this library since load (all threads). */
+int64_t avsi_launch_count(void);
+/* sizeof() of the argument structs below, for FFI bindings to self-check their mirrors. */
+int avsi_sizeof_frontend_args(void);
+int avsi_sizeof_istft_args(void);
+
+/* ------------------------------------------------------------------------------------
+ * Spectrogram front end.  Replaces, in ONE kernel:
+ *   get_stft            audio_processing.py:25-42  (tf.contrib.signal.stft: frame, Hann, rFFT-512)
+ *   get_spectrogram     audio_processing.py:45-56  (abs, **power, log(x + 1e-6))
+ *   get_log_mel_spectrogram audio_processing.py:59-72 (mel projection + log)
+ *   normalise + mask    models.py:30-35            ((spec - mean) / std, * masks)
+ *   mask on complex STFT masking.py:42, models.py:186
+ *   concat + transpose  models.py:45,102           (audio ++ video, time-major)
+ * Frames never touch HBM.  nfft must be 512 and frame_len <= 512.
+ *
+ *   wav        [B,N] f32            window [frame_len] f32 (periodic Hann, host-made)
+ *   twiddle    [512] complex64      exp(-2*pi*i*m/512), host-made from float64
+ *   T, F       frames / bins to emit (the reference's out_shape slice; F <= 257)
+ *   mean,std   [F] f32 or NULL      (NULL: no normalisation)
+ *   mask       [B,T,F] f32 or NULL  (1 = reliable, 0 = hole)
+ *   video      [B,T,V] f32 or NULL
+ * Outputs (each may be NULL = not produced):
+ *   stft_out   [B,T,F] complex64    STFT (multiplied by mask if stft_masked != 0)
+ *   spec_out   [B,T,F] f32          |X|^power, log'd if log_flag, normalised if mean/std
+ *                                   (= target_spec_norm for power=1, log_flag=1)
+ *   feat_out   [B,T,F+V] f32        spec_out * mask  ++ video         (= net_inputs)
+ *   xh_out     [T*B, ldx] f16       same as feat_out, time-major, zero padded to ldx
+ *   logmel_out [B,T,n_mel] f32      log(|X|^power . mel_w + mel_eps); mel_w [257,n_mel] f32
+ */
+typedef struct {
+  const float* wav; int B; int N;
+  int frame_len; int hop; int nfft; int T; int F;
+  const float* window; const float* twiddle;
+  const float* mean; const float* stdev; const float* mask;
+  const float* video; int V;
+  float power; int log_flag; int stft_masked;
+  float* stft_out; float* spec_out; float* feat_out;
+  uint16_t* xh_out; int ldx;
+  float* logmel_out; const float* mel_w; int n_mel; float mel_eps;
+  float* hole_count;   /* optional [1] f32 device accumulator: += sum(1 - mask) (caller zeroes) */
+  int xh_video_only;   /* input='v' (models.py:42-43): xh_out holds only the video columns, from column 0 */
+} avsi_frontend_args;
+int avsi_frontend_fwd(const avsi_frontend_args* args, void* stream);
+
+/* Waveform reconstruction (next row 8f.1): get_sources / reconstruct_sources
+ * audio_processing.py:145-164, enhanced_sources models.py:181-197.
+ *   mag [B,T,F] f32 (or pred with denorm: mag = exp(pred*std+mean) when mean != NULL)
+ *   phase_src [B,T,F] complex64 (angle taken inside; multiplied by mask first if mask != NULL)
+ *   inv_window [frame_len] f32 (inverse_stft_window_fn), out [B,num_samples] f32.  */
+typedef struct {
+  const float* mag; const float* phase_src; const float* mask;
+  const float* mean; const float* stdev;
+  const float* inv_window; const float* twiddle;
+  int B; int T; int F; int frame_len; int hop; int nfft; int num_samples;
+  float* out;
+} avsi_istft_args;
+int avsi_istft_fwd(const avsi_istft_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Landmark stream -> network video features.  Replaces inc_fps /
+ * sync_audio_visual_features (av_sync.py:7-40), get_motion_vector
+ * (face_landmarks.py:30-39) and the z-normalisation of tfrecord_utils.py:104-107.
+ *   landmarks [B,L,D] f32 (already start-padded to L frames), vmean/vstd [B,D] f32
+ *   out [B,T,D] f32: lerp to T frames (clamped), first difference (row 0 = 0), z-norm. */
+int avsi_video_features(const float* landmarks, const float* vmean, const float* vstd,
+                        int B, int L, int D, int T, float* out, void* stream);
+
+/* Dense mask from intervals: get_intrusions_mask tail, dataset_generator.py:43-46.
+ *   intervals [B,K,2] i32 (onset, length; length 0 = unused) -> mask [B,T,F] f32 of {0,1}. */
+int avsi_expand_mask(const int32_t* intervals, int B, int K, int T, int F, float* mask, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Tensor-core GEMM (tcgen05.mma kind::f16, fp16 operands, fp32 accumulate in TMEM,
+ * operands staged by TMA).  Replaces the cuBLAS / cuDNN contractions behind
+ * CudnnLSTM input projections (models.py:95-104), tf.matmul heads (models.py:117-123,
+ * 1902-1912) and their gradients.
+ *   C[M,N] (+)= A . B^T      trans == 0: A [M,K] (lda), B [N,K] (ldb), both K-contiguous
+ *   C[M,N] (+)= A^T . B      trans == 1: A [K,M] (lda), B [K,N] (ldb), both MN-contiguous
+ *   out_mode 0: C f16 = acc ; 1: C f32 = acc + bias[N] (bias may be NULL) ; 2: C f32 += acc (atomic)
+ *   split_k > 1 only with out_mode 2.  lda/ldb multiples of 8 elements; A,B 16-byte aligned. */
+int avsi_gemm_f16(const uint16_t* A, int lda, const uint16_t* B, int ldb, void* C, int ldc,
+                  const float* bias, int M, int N, int K, int trans, int out_mode, int split_k,
+                  void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Persistent bidirectional LSTM recurrence.  Replaces cudnnRNNForwardTraining /
+ * BackwardData of tf.contrib.cudnn_rnn.CudnnLSTM (models.py:95-104) and the
+ * CudnnCompatibleLSTMCell while-loop (models.py:106-115).  Both directions of one
+ * layer run in one launch; W_hh stays register-resident across all T steps in a
+ * thread-block cluster of 8 CTAs.  HP = 256 (H padded), gate columns are laid out
+ * [dir][unit][i,g,f,o] (column = dir*1024 + unit*4 + gate).
+ *   gates [T*B, 2048] f16   in: x.W_ih^T pre-activations ; out: activated gates (in place)
+ *   whh   [2,1024,256] f16  recurrent weights, [dir][gate column][h_in]
+ *   bias  [2048] f32
+ *   y     [T*B, 512] f16    out: h_t, columns dir*256 + unit
+ *   cst   [T*B, 512] f32    out: c_t (stash for BPTT)
+ * Backward: dy [T*B,512] f16 (scaled dL/dy), whhT [256,2048] f16 (whh^T) -> gates becomes dgates
+ * (in place), dbias[2048] f32 += column sums, scratch >= avsi_lstm_bwd_scratch_bytes(B). */
+int avsi_lstm_fwd(uint16_t* gates, const uint16_t* whh, const float* bias, uint16_t* y, float* cst,
+                  int T, int B, void* stream);
+int64_t avsi_lstm_bwd_scratch_bytes(int B);
+int avsi_lstm_bwd(uint16_t* gates, const uint16_t* whhT, const float* cst, const uint16_t* dy,
+                  float* dbias, void* scratch, int T, int B, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Masked-L1 loss + gradient.  Replaces prediction / loss of models.py:127-159 (SI, mode 0)
+ * and models.py:1920-1963 (MTL, mode 1) and their autodiff mirror.
+ *   logits [T*B, ldl] f32 time-major (head GEMM output), target/mask [B,T,F] f32, seq_len [B] i32
+ *   sums[8] f64 += { sum|d|(1-m), sum(1-m), sum|d|m, sum m, sum|d|, count, 0, 0 }
+ *   prediction [B,T,F] f32 (optional)
+ *   dlogits [T*B, ldd] f16 (optional): grad_scale * dL/dlogits of the UNnormalised sums, i.e.
+ *     mode 0: sign(pred - target) * seqmask            (caller folds 1/(B*T*F) into grad_scale)
+ *     mode 1: sign(pred - target) * (1-m) * seqmask    (caller folds 1/sum(1-m)) */
+int avsi_masked_l1(const float* logits, int ldl, const float* target, const float* mask,
+                   const int32_t* seq_len, int B, int T, int F, int mode, float grad_scale,
+                   const float* grad_scale_dev, double* sums, float* prediction, uint16_t* dlogits,
+                   int ldd, void* stream);
+/* grad_scale_dev (here and below): optional device scalar multiplied into grad_scale, so that
+ * data-dependent normalisers (sum(1-m) of the MTL loss) never need a host round trip. */
+
+/* MTL gradient scales from the hole count: out[0] = S (L1 dlogits scale, a power of two),
+ * out[1] = S*(ctc_weight/B)*holes (CTC dlogits scale), out[2] = 1/(S*holes) (optimiser unscale),
+ * out[3] = holes.  loss = loss_hole + ctc_weight * mean_b(nll_b)  (models.py:1955). */
+int avsi_mtl_scales(const float* hole_count, int B, float ctc_weight, float* out, void* stream);
+
+/* Column sums: out[n] += sum_r X[r, col0 + n] (f16 in, f32 out) -- bias gradients. */
+int avsi_colsum_f16(const uint16_t* X, int ldx, int rows, int col0, int ncols, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * CTC loss + gradient.  Replaces tf.nn.ctc_loss (CPU-only op in TF1) as called at
+ * models.py:1950-1953: unnormalised logits, blank = C-1, merge_repeated.
+ *   logits [T*B, ldl] f32 time-major, classes at columns col0 .. col0+C-1
+ *   labels [B,Lmax] i32, lab_len/seq_len [B] i32
+ *   nll [B] f32 ; dlogits [T*B, ldd] f16 at columns dcol0.. : grad_scale * d nll_b / d logits
+ *   workspace >= avsi_ctc_workspace_bytes(B,T,Lmax) */
+int64_t avsi_ctc_workspace_bytes(int B, int T, int Lmax);
+int avsi_ctc_loss(const float* logits, int ldl, int col0, int C, const int32_t* labels, int Lmax,
+                  const int32_t* lab_len, const int32_t* seq_len, int B, int T, float grad_scale,
+                  const float* grad_scale_dev, float* nll, uint16_t* dlogits, int ldd, int dcol0,
+                  void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Optimiser.  Replaces tf.train.AdamOptimizer ApplyAdam (models.py:168,178), TF epsilon-hat form.
+ *   g is multiplied by grad_unscale first; l2 adds l2 * theta to the gradient (models.py:153-158). */
+int avsi_adam_tf(float* theta, const float* g, float* m, float* v, int64_t n, float lr, float b1,
+                 float b2, float eps, int step, float grad_unscale, const float* grad_unscale_dev,
+                 float l2, void* stream);
+/* fp32 -> fp16 copies of a weight matrix W [R,C]: w16 [R,C] and (optional) w16t [C,R]. */
+int avsi_cast_weights(const float* w, int R, int C, uint16_t* w16, uint16_t* w16t, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVSI_B200_H_ */
