@@ -113,3 +113,66 @@ def stream_ptr():
 
 def launch_count():
     return int(load().avsi_launch_count())
+
+
+# ---- optional per-kernel CUDA-event timing (bench.py); zero cost when disabled -----------------
+_prof = None
+
+
+class _Span(object):
+    __slots__ = ('name', 'bytes', 'flops', 'start', 'stop')
+
+    def __init__(self, name, nbytes, flops):
+        self.name, self.bytes, self.flops = name, nbytes, flops
+
+    def __enter__(self):
+        import torch
+        self.start = torch.cuda.Event(enable_timing=True)
+        self.stop = torch.cuda.Event(enable_timing=True)
+        self.start.record()
+        return self
+
+    def __exit__(self, *exc):
+        self.stop.record()
+        _prof.append(self)
+        return False
+
+
+class _NullSpan(object):
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NULL = _NullSpan()
+
+
+def span(name, nbytes=0, flops=0):
+    """``with span('lstm_fwd'):`` brackets kernel launches with CUDA events on the current stream
+    while profiling is enabled (profile_start / profile_stop)."""
+    if _prof is None:
+        return _NULL
+    return _Span(name, nbytes, flops)
+
+
+def profile_start():
+    global _prof
+    _prof = []
+
+
+def profile_stop():
+    """Returns {name: dict(ms, launches, bytes, flops)} summed over the recorded spans."""
+    global _prof
+    import torch
+    torch.cuda.synchronize()
+    spans, _prof = _prof, None
+    out = {}
+    for s in spans or []:
+        d = out.setdefault(s.name, {'ms': 0.0, 'launches': 0, 'bytes': 0, 'flops': 0})
+        d['ms'] += s.start.elapsed_time(s.stop)
+        d['launches'] += 1
+        d['bytes'] += s.bytes
+        d['flops'] += s.flops
+    return out

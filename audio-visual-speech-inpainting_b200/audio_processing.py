@@ -114,7 +114,13 @@ def fused_features(sources, frame_len, hop, T=None, F=257, mean=None, std=None, 
     a.n_mel, a.mel_eps = n_mel, float(mel_eps)
     a.hole_count = hole_count.data_ptr() if hole_count is not None else None
     a.xh_video_only = int(bool(xh_video_only))
-    _lib.check(lib.avsi_frontend_fwd(a, _lib.stream_ptr()), 'avsi_frontend_fwd')
+    # algorithmic bytes of this launch: every requested input / output once
+    nbytes = 4 * B * N + (4 * B * T * F if mask is not None else 0) + 4 * B * T * V
+    nbytes += (8 * B * T * F if want_stft else 0) + (4 * B * T * F if want_spec else 0)
+    nbytes += (4 * B * T * (F + V) if want_feat else 0) + (2 * B * T * int(ldx) if xh_out is not None else 0)
+    nbytes += 4 * B * T * n_mel
+    with _lib.span('frontend', nbytes=nbytes):
+        _lib.check(lib.avsi_frontend_fwd(a, _lib.stream_ptr()), 'avsi_frontend_fwd')
     if want_stft:
         out['stft'] = torch.view_as_complex(out['stft'])
     return out

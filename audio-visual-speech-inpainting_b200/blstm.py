@@ -28,10 +28,11 @@ def _p(t):
     return _lib.ptr(t)
 
 
-def gemm(A, lda, B, ldb, C, ldc, bias, M, N, K, trans, out_mode, split_k=1):
+def gemm(A, lda, B, ldb, C, ldc, bias, M, N, K, trans, out_mode, split_k=1, tag='gemm'):
     lib = _lib.load()
-    _lib.check(lib.avsi_gemm_f16(A, lda, B, ldb, C, ldc, bias, M, N, K, trans, out_mode, split_k, _lib.stream_ptr()),
-               'avsi_gemm_f16')
+    with _lib.span(tag, flops=2 * M * N * K):
+        _lib.check(lib.avsi_gemm_f16(A, lda, B, ldb, C, ldc, bias, M, N, K, trans, out_mode, split_k,
+                                     _lib.stream_ptr()), 'avsi_gemm_f16')
 
 
 def pick_split_k(m_rows, n_cols, k, target_ctas=296):
@@ -131,12 +132,13 @@ class BLSTMEngine(object):
             G = ws['G'][l if training else 0]
             C = ws['C'][l if training else 0]
             kp = L.layer_k(l)
-            gemm(_p(x), ldx, _p(self.half['wih%d' % l]), kp, _p(G), NG, None, M, NG, kp, 0, 0)
-            _lib.check(lib.avsi_lstm_fwd(_p(G), _p(self.half['whh%d' % l]), _p(self.view(self.theta, 'b%d' % l)),
-                                         _p(ws['Y'][l]), _p(C), T, B, _lib.stream_ptr()), 'avsi_lstm_fwd')
+            gemm(_p(x), ldx, _p(self.half['wih%d' % l]), kp, _p(G), NG, None, M, NG, kp, 0, 0, tag='gemm_proj_fwd')
+            with _lib.span('lstm_fwd', flops=2 * M * NG * HP):
+                _lib.check(lib.avsi_lstm_fwd(_p(G), _p(self.half['whh%d' % l]), _p(self.view(self.theta, 'b%d' % l)),
+                                             _p(ws['Y'][l]), _p(C), T, B, _lib.stream_ptr()), 'avsi_lstm_fwd')
             x, ldx = ws['Y'][l], NY
         gemm(_p(x), NY, _p(self.half['head']), NY, _p(ws['logits']), L.nop, _p(self.view(self.theta, 'head_b')),
-             M, L.n_out, NY, 0, 1)
+             M, L.n_out, NY, 0, 1, tag='gemm_head_fwd')
         return ws['logits']
 
     # ---- backward -----------------------------------------------------------------------------
@@ -153,20 +155,21 @@ class BLSTMEngine(object):
         ylast = ws['Y'][L.n_layers - 1]
         # head: dW = dlogits^T . Y ; db = colsum(dlogits) ; dY = dlogits . Whead
         gemm(_p(dl), L.nop, _p(ylast), NY, _p(self.view(g, 'head_w')), NY, None, L.n_out, NY, M, 1, 2,
-             pick_split_k(L.n_out, NY, M))
+             pick_split_k(L.n_out, NY, M), tag='gemm_dw')
         _lib.check(lib.avsi_colsum_f16(_p(dl), L.nop, M, 0, L.n_out, _p(self.view(g, 'head_b')), st()), 'avsi_colsum_f16')
         dY = ws['dY'][0]
-        gemm(_p(dl), L.nop, _p(self.half['headT']), L.nop, _p(dY), NY, None, M, NY, L.nop, 0, 0)
+        gemm(_p(dl), L.nop, _p(self.half['headT']), L.nop, _p(dY), NY, None, M, NY, L.nop, 0, 0, tag='gemm_dx')
         cur = 0
         for l in range(L.n_layers - 1, -1, -1):
             G, C, Y = ws['G'][l], ws['C'][l], ws['Y'][l]
             kp = L.layer_k(l)
-            _lib.check(lib.avsi_lstm_bwd(_p(G), _p(self.half['whhT%d' % l]), _p(C), _p(ws['dY'][cur]),
-                                         _p(self.view(g, 'b%d' % l)), _p(ws['scratch']), T, B, st()), 'avsi_lstm_bwd')
+            with _lib.span('lstm_bwd', flops=2 * M * NG * HP):
+                _lib.check(lib.avsi_lstm_bwd(_p(G), _p(self.half['whhT%d' % l]), _p(C), _p(ws['dY'][cur]),
+                                             _p(self.view(g, 'b%d' % l)), _p(ws['scratch']), T, B, st()), 'avsi_lstm_bwd')
             x, ldx = (ws['x0'], L.k0p) if l == 0 else (ws['Y'][l - 1], NY)
             # dWih = dG^T . X
             gemm(_p(G), NG, _p(x), ldx, _p(self.view(g, 'wih%d' % l)), kp, None, NG, kp, M, 1, 2,
-                 pick_split_k(NG, kp, M))
+                 pick_split_k(NG, kp, M), tag='gemm_dw')
             # dWhh[dir] = dG[dir]^T . h_prev  (fw: h_{t-1}, bw: h_{t+1})
             if T > 1:
                 Kr = (T - 1) * B
@@ -174,13 +177,15 @@ class BLSTMEngine(object):
                 sk = pick_split_k(GATES * HP, HP, Kr, 148)
                 a_fw = G.data_ptr() + B * NG * 2
                 b_fw = Y.data_ptr()
-                gemm(a_fw, NG, b_fw, NY, _p(gw), HP, None, GATES * HP, HP, Kr, 1, 2, sk)
+                gemm(a_fw, NG, b_fw, NY, _p(gw), HP, None, GATES * HP, HP, Kr, 1, 2, sk, tag='gemm_dw')
                 a_bw = G.data_ptr() + GATES * HP * 2
                 b_bw = Y.data_ptr() + (B * NY + HP) * 2
-                gemm(a_bw, NG, b_bw, NY, gw.data_ptr() + GATES * HP * HP * 4, HP, None, GATES * HP, HP, Kr, 1, 2, sk)
+                gemm(a_bw, NG, b_bw, NY, gw.data_ptr() + GATES * HP * HP * 4, HP, None, GATES * HP, HP, Kr, 1, 2, sk,
+                     tag='gemm_dw')
             if l > 0:
                 nxt = 1 - cur
-                gemm(_p(G), NG, _p(self.half['wihT%d' % l]), NG, _p(ws['dY'][nxt]), NY, None, M, NY, NG, 0, 0)
+                gemm(_p(G), NG, _p(self.half['wihT%d' % l]), NG, _p(ws['dY'][nxt]), NY, None, M, NY, NG, 0, 0,
+                     tag='gemm_dx')
                 cur = nxt
         return g
 
@@ -189,7 +194,8 @@ class BLSTMEngine(object):
         lib = _lib.load()
         self.step_count += 1
         n = self.layout.n_params_padded
-        _lib.check(lib.avsi_adam_tf(_p(self.theta), _p(self.grad), _p(self.adam_m), _p(self.adam_v), n, lr, b1, b2, eps,
-                                    self.step_count, grad_unscale, _p(unscale_dev), l2, _lib.stream_ptr()),
-                   'avsi_adam_tf')
-        self.refresh_half()
+        with _lib.span('adam'):
+            _lib.check(lib.avsi_adam_tf(_p(self.theta), _p(self.grad), _p(self.adam_m), _p(self.adam_v), n, lr, b1, b2,
+                                        eps, self.step_count, grad_unscale, _p(unscale_dev), l2, _lib.stream_ptr()),
+                       'avsi_adam_tf')
+            self.refresh_half()

@@ -197,9 +197,10 @@ class StackedBLSTMModel(object):
             _lib.check(lib.avsi_mtl_scales(_p(hole), B * world, float(self.ctc_loss_weight), _p(scales),
                                            _lib.stream_ptr()), 'avsi_mtl_scales')
         dl = ws['dlogits'] if (want_grad and 'dlogits' in ws) else None
-        _lib.check(lib.avsi_masked_l1(_p(logits), L.nop, _p(fr['target_spec_norm']), _p(masks), _p(seq), B, T, F,
-                                      1 if self.MTL else 0, 1.0, _p(scales) if self.MTL else None, _p(self._sums),
-                                      _p(pred), _p(dl), L.nop, _lib.stream_ptr()), 'avsi_masked_l1')
+        with _lib.span('masked_l1'):
+            _lib.check(lib.avsi_masked_l1(_p(logits), L.nop, _p(fr['target_spec_norm']), _p(masks), _p(seq), B, T, F,
+                                          1 if self.MTL else 0, 1.0, _p(scales) if self.MTL else None, _p(self._sums),
+                                          _p(pred), _p(dl), L.nop, _lib.stream_ptr()), 'avsi_masked_l1')
         if self.MTL:
             labels, lab_len = self._need('labels', 'labels_lengths')
             Lmax = labels.shape[1]
@@ -209,9 +210,10 @@ class StackedBLSTMModel(object):
                 wsc = ws['ctc_ws'] = torch.empty(nbytes // 4 + 4, dtype=torch.float32, device=self.device)
             nll = torch.empty(B, dtype=torch.float32, device=self.device)
             scale_ptr = (scales.data_ptr() + 4) if dl is not None else None
-            _lib.check(lib.avsi_ctc_loss(_p(logits), L.nop, F, self.num_classes, _p(labels), Lmax, _p(lab_len),
-                                         _p(seq), B, T, 1.0, scale_ptr, _p(nll), _p(dl), L.nop, F, _p(wsc),
-                                         _lib.stream_ptr()), 'avsi_ctc_loss')
+            with _lib.span('ctc'):
+                _lib.check(lib.avsi_ctc_loss(_p(logits), L.nop, F, self.num_classes, _p(labels), Lmax, _p(lab_len),
+                                             _p(seq), B, T, 1.0, scale_ptr, _p(nll), _p(dl), L.nop, F, _p(wsc),
+                                             _lib.stream_ptr()), 'avsi_ctc_loss')
             out['ctc_nll'] = nll
             out['scales'] = scales
         out['sums'] = self._sums

@@ -1,0 +1,272 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: AV-SI training utterances/s (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W              (N > 1: launched under torchrun)
+    python bench.py --impl reference ...                       (CPU arm: the oracle port on host cores)
+
+A step = one pass of the hot path over one synthetic GRID-shaped batch (3 s, 16 kHz, 75 landmark
+frames): landmark upsampling + motion vectors -> fused STFT front end -> 3-layer BLSTM forward ->
+masked-L1 -> BPTT -> (NCCL gradient all-reduce) -> TF-form Adam.  `value` times it with inputs
+resident in HBM; `e2e` times the same step through the public model API from pinned HOST buffers
+(H2D of wav / mask / landmarks and D2H of the loss inside the timed region).  Prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'AV-SI training utterances/sec'
+UNIT = 'utterances/s'
+CPU_SAMPLE_B = 8
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=8)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=int(os.environ.get('AVSI_BENCH_BATCH', 512)), help='utterances per GPU per step')
+    ap.add_argument('--audio-len', type=int, default=48000)
+    ap.add_argument('--model', default='av-blstm')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {'hbm_gbs': p.get('hbm_gbs', 6650.0), 'bf16_tflops': p.get('bf16_tflops', 1590.0),
+                'bf16_tflops_sustained': p.get('bf16_tflops_sustained', 1400.0), 'source': 'measured'}
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0, 'source': 'fallback'}
+
+
+class ClockSampler(object):
+    """nvidia-smi clock / throttle-reason samples during the timed region (B200_PROFILING.md recipe)."""
+    FIELDS = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+              'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.FIELDS,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(nm)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(smax) if smax else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def cpu_baseline(args, steps=1, warmup=0):
+    """The oracle port (kind = "port") timed on the host cores on a bounded sample of the workload."""
+    import numpy as np
+    from avsi_b200 import synth
+    from oracle import cpu_port
+    from oracle import video as ovideo
+    B = CPU_SAMPLE_B
+    b = synth.make_batch(B, audio_len=args.audio_len, seed=0)
+    b['video'] = np.stack([ovideo.video_features(b['landmarks'][i].astype(np.float64), b['T'], b['vmean'][i], b['vstd'][i])
+                           for i in range(B)]).astype(np.float32)
+    ups, cores, dt = cpu_port.time_train_steps(b, steps=steps, warmup=warmup)
+    return {'value': ups, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+            'sample': '%d step(s) of a %d-utterance AV-SI train step (fwd+bwd+Adam, fp32 torch-CPU port of the '
+                      'reference TF graph; TF 1.x itself is not installable here), %.2f s/step' % (steps, B, dt)}, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cb, dt = cpu_baseline(args, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    line = {'impl': 'reference', 'metric': METRIC, 'value': cb['value'], 'unit': UNIT, 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'AV-SI train step (configs[1]): 3 s 16 kHz utterances, 75-frame landmarks, '
+                                   '3x BLSTM-250, L1, Adam', 'batch_per_step': CPU_SAMPLE_B},
+            'cpu_baseline': cb,
+            'e2e': {'value': cb['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line))
+
+
+def main():
+    args = parse_args()
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if rank == 0:
+        __graft_entry__.build()
+    torch.cuda.set_device(local_rank)
+    pg = None
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        dist.barrier()
+        pg = dist.group.WORLD
+    from avsi_b200 import _lib, av_sync, models, synth
+    dev = torch.device('cuda', local_rank)
+    B = args.batch
+    host = synth.make_batch(B, audio_len=args.audio_len, seed=rank)      # rank-offset data, identical weights
+    T = host['T']
+    cfg = synth.default_config(args.model, batch_size=B * world, audio_len=args.audio_len)
+    pin = {k: torch.from_numpy(np.ascontiguousarray(host[k])).pin_memory()
+           for k in ('wav', 'mask', 'landmarks', 'vmean', 'vstd', 'seq_len', 'mean', 'std')}
+    res = {k: v.to(dev) for k, v in pin.items()}
+
+    def video_of(src):
+        with _lib.span('video_features'):
+            return av_sync.video_pipeline(src['landmarks'], T, src['vmean'], src['vstd'], device=dev)
+
+    model = models.StackedBLSTMModel(res['seq_len'], res['wav'], res['mask'], res['mean'], res['std'], 0.0, cfg,
+                                     video_features=video_of(res), input='av', is_training=True, device=dev,
+                                     process_group=pg)
+
+    def step_resident():
+        model.feed(sequence_lengths=res['seq_len'], target_sources=res['wav'], masks=res['mask'],
+                   video_features=video_of(res))
+        model.train_op()
+
+    def step_e2e():
+        d = {k: pin[k].to(dev, non_blocking=True) for k in ('wav', 'mask', 'landmarks', 'vmean', 'vstd', 'seq_len')}
+        model.feed(sequence_lengths=d['seq_len'], target_sources=d['wav'], masks=d['mask'], video_features=video_of(d))
+        model.train_op()
+        n = model.engine.layout.n_params_padded
+        return float(model.engine.grad[n + 4].item()) if pg is not None else float(model._loss_pass(True)['sums'][4].item())
+
+    def timed(fn, steps, profile=False):
+        torch.cuda.synchronize()
+        if pg is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = _lib.launch_count()
+        if profile:
+            _lib.profile_start()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        prof = _lib.profile_stop() if profile else None
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if pg is not None:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), _lib.launch_count() - n0, prof
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.15)
+    ms, launches, prof = timed(step_resident, args.steps, profile=True)
+    clocks = sampler.stop() if rank == 0 else None
+    step_e2e()
+    ms_e2e, _, _ = timed(step_e2e, args.steps)
+
+    if rank != 0:
+        if pg is not None:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    utt = B * world * args.steps
+    value = utt / (ms * 1e-3)
+    h2d = sum(pin[k].numel() * pin[k].element_size() for k in ('wav', 'mask', 'landmarks', 'vmean', 'vstd', 'seq_len'))
+    kernels = {}
+    tot = sum(v['ms'] for v in prof.values()) or 1.0
+    for name, v in sorted(prof.items(), key=lambda kv: -kv[1]['ms']):
+        kernels[name] = {'ms_per_step': v['ms'] / args.steps, 'share': v['ms'] / tot, 'launches_per_step': v['launches'] / args.steps}
+
+    def roof(name):
+        v = prof.get(name)
+        if not v or v['ms'] <= 0:
+            return None
+        sec = v['ms'] * 1e-3
+        if v['bytes']:
+            a = v['bytes'] / sec / 1e9
+            return {'kernel': name, 'bound': 'hbm', 'achieved': a, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
+                    'frac': a / pk['hbm_gbs'], 'traffic': None, 'peak_source': pk['source'],
+                    'algorithmic_bytes_per_launch': v['bytes'] / v['launches']}
+        a = v['flops'] / sec / 1e12
+        return {'kernel': name, 'bound': 'tensor', 'achieved': a, 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
+                'frac': a / pk['bf16_tflops_sustained'], 'traffic': None, 'peak_source': pk['source'] + ' (sustained)',
+                'algorithmic_flops_per_launch': v['flops'] / v['launches']}
+
+    dominant = next(iter(kernels)) if kernels else None
+    line = {
+        'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+        'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f16', 'data': 'synthetic',
+        'config': {'workload': 'AV-SI train step (configs[1]): 3 s 16 kHz utterances + 75-frame landmark streams, '
+                               'masked log-spectrogram ++ upsampled motion vectors, 3x BLSTM-250, L1 loss, TF-form Adam',
+                   'model': args.model, 'batch_per_gpu': B, 'global_batch': B * world, 'frames': T,
+                   'parallelism': 'dp%d' % world, 'arithmetic': 'fp16 operands, fp32 accumulate / state',
+                   'l2_policy': 'inputs larger than L2 (wav+mask %.0f MB per step, activations %.1f GB)'
+                                % ((pin['wav'].numel() + pin['mask'].numel()) * 4 / 1e6, T * B * (3 * 2048 * 2 + 3 * 512 * 6) / 1e9)},
+        'e2e': {'value': utt / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 8},
+        'gpu_launches': launches,
+        'clocks': clocks,
+        'roofline': roof(dominant) if dominant else None,
+        'roofline_frontend': roof('frontend'),
+        'roofline_gemm_proj': roof('gemm_proj_fwd'),
+        'kernels': kernels,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        line['cpu_baseline'], _ = cpu_baseline(args, steps=3, warmup=0)
+    elif world == 1:
+        line['cpu_baseline'] = None
+    print(json.dumps(line))
+    if pg is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

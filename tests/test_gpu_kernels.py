@@ -1,0 +1,436 @@
+"""Kernel-level parity tests (B200): every C-ABI kernel against the CPU oracle / float64 numpy."""
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device('cuda:0')
+
+
+def sync():
+    torch.cuda.synchronize()
+
+
+# ------------------------------------------------------------------------------------------ GEMM
+GEMM_CASES = [
+    # M, N, K, trans, out_mode, split_k, ldc_pad
+    (128, 128, 64, 0, 1, 1, 0),
+    (256, 128, 128, 0, 0, 1, 0),
+    (300, 257, 512, 0, 1, 1, 63),
+    (1000, 2048, 448, 0, 0, 1, 0),
+    (777, 512, 2048, 0, 0, 1, 0),
+    (640, 512, 320, 0, 0, 1, 0),
+    (130, 34, 512, 0, 1, 1, 6),
+    (128, 128, 64, 1, 2, 1, 0),
+    (2048, 448, 1000, 1, 2, 1, 0),
+    (2048, 512, 4100, 1, 2, 3, 0),
+    (1024, 256, 996, 1, 2, 4, 0),
+    (291, 512, 1000, 1, 2, 2, 0),
+    (512, 2048, 8192, 0, 2, 2, 0),
+]
+
+
+@pytest.mark.parametrize('M,N,K,trans,out_mode,split_k,ldc_pad', GEMM_CASES)
+def test_gemm_f16(M, N, K, trans, out_mode, split_k, ldc_pad):
+    from avsi_b200 import blstm
+    rng = np.random.default_rng(M * 7 + N * 3 + K + trans)
+    d = dev()
+    ka = (K + 7) // 8 * 8
+    if trans == 0:
+        A = rng.standard_normal((M, ka)).astype(np.float16)
+        Bm = rng.standard_normal((N, ka)).astype(np.float16)
+        A[:, K:] = 7.0          # beyond K must be ignored (TMA box clipping by tensor extent)
+        Bm[:, K:] = 7.0
+        ref = A[:, :K].astype(np.float64) @ Bm[:, :K].astype(np.float64).T
+        lda = ldb = ka
+    else:
+        ma, na = (M + 7) // 8 * 8, (N + 7) // 8 * 8
+        A = rng.standard_normal((K, ma)).astype(np.float16)
+        Bm = rng.standard_normal((K, na)).astype(np.float16)
+        ref = A[:, :M].astype(np.float64).T @ Bm[:, :N].astype(np.float64)
+        lda, ldb = ma, na
+    At, Bt = torch.from_numpy(A).to(d), torch.from_numpy(Bm).to(d)
+    ldc = N + ldc_pad
+    bias = None
+    if out_mode == 0:
+        ldc = (ldc + 7) // 8 * 8
+        C = torch.full((M, ldc), -3.0, dtype=torch.float16, device=d)
+    else:
+        C = torch.full((M, ldc), 0.5 if out_mode == 2 else -3.0, dtype=torch.float32, device=d)
+        if out_mode == 1:
+            bias = torch.from_numpy(rng.standard_normal(N).astype(np.float32)).to(d)
+    blstm.gemm(At.data_ptr(), lda, Bt.data_ptr(), ldb, C.data_ptr(), ldc, None if bias is None else bias.data_ptr(),
+               M, N, K, trans, out_mode, split_k)
+    sync()
+    got = C.cpu().numpy().astype(np.float64)
+    if out_mode == 1:
+        ref = ref + bias.cpu().numpy().astype(np.float64)
+    if out_mode == 2:
+        ref = ref + 0.5
+    err = np.abs(got[:, :N] - ref)
+    tol = 2e-3 if out_mode == 0 else 2e-5
+    r = rel_l2(got[:, :N], ref)
+    if r >= tol:
+        bad = np.argwhere(err > 10 * tol * np.abs(ref).max())
+        rows, cols = np.unique(bad[:, 0]), np.unique(bad[:, 1])
+        pytest.fail('gemm rel-L2 %.3e (tol %.1e); %d bad elems; bad rows %s.. cols %s..; got[0,:4]=%s ref[0,:4]=%s'
+                    % (r, tol, len(bad), rows[:12], cols[:12], got[0, :4], ref[0, :4]))
+    # untouched padding columns keep their fill value
+    if ldc > N:
+        fill = 0.5 if out_mode == 2 else -3.0
+        assert np.all(got[:, N:] == fill)
+
+
+# ------------------------------------------------------------------------------------------ front end
+def _frontend_case(B, N, T=None, F=257, with_video=True, frame_ms=24, hop_ms=12, seed=0):
+    from avsi_b200 import audio_processing as ap
+    from oracle import stft as ostft
+    rng = np.random.default_rng(seed)
+    d = dev()
+    frame_len, hop = ap.ms_to_samples(frame_ms, 16000), ap.ms_to_samples(hop_ms, 16000)
+    Tfull = -(-N // hop)
+    T = Tfull if T is None else T
+    wav = np.round(np.clip(rng.normal(0, 3500, (B, N)), -32767, 32767)).astype(np.float32)
+    mask = np.ones((B, T, F), np.float32)
+    for b in range(B):
+        o = int(rng.integers(0, max(1, T - 5)))
+        mask[b, o:o + int(rng.integers(1, 6))] = 0
+    mean = rng.normal(6.0, 0.5, F).astype(np.float32)
+    std = rng.uniform(1.5, 2.5, F).astype(np.float32)
+    V = 136
+    video = rng.standard_normal((B, T, V)).astype(np.float32) if with_video else None
+    ldx = (F + (V if with_video else 0) + 63) // 64 * 64
+    xh = torch.full((T * B, ldx), 9.0, dtype=torch.float16, device=d)
+    hole = torch.zeros(1, dtype=torch.float32, device=d)
+    res = ap.fused_features(torch.from_numpy(wav).to(d), frame_len, hop, T=T, F=F, mean=mean, std=std, mask=mask,
+                            video=video, want_stft=True, want_spec=True, want_feat=True, xh_out=xh, ldx=ldx,
+                            hole_count=hole)
+    sync()
+    st = ostft.get_stft(wav.astype(np.float64), window_size=frame_ms, step_size=hop_ms, out_shape=(B, T, F))
+    lin = np.abs(st)
+    tsn = (np.log(lin + 1e-6) - mean.astype(np.float64)) / std.astype(np.float64)
+    got_st = res['stft'].cpu().numpy()
+    assert got_st.shape == (B, T, F)
+    # tolerance (BASELINE.json north_star): fp32 spectra within 1e-5 relative (relative L2)
+    assert rel_l2(np.stack([got_st.real, got_st.imag]), np.stack([st.real, st.imag])) < 1e-5
+    spec = res['spec'].cpu().numpy()
+    assert rel_l2(np.exp(spec * std + mean), lin + 1e-6) < 1e-5          # linear magnitude
+    assert rel_l2(spec, tsn) < 1e-5                                      # normalised log spectrum
+    feat = res['feat'].cpu().numpy()
+    assert np.array_equal(feat[:, :, :F], spec * mask)                   # mask application is exact
+    assert np.all(feat[:, :, :F][mask == 0] == 0)
+    if with_video:
+        assert np.array_equal(feat[:, :, F:], video)
+    x = xh.cpu().numpy().reshape(T, B, ldx).transpose(1, 0, 2)
+    I = feat.shape[2]
+    assert np.array_equal(x[:, :, :I], feat.astype(np.float16))
+    assert np.all(x[:, :, I:] == 0)
+    assert float(hole.item()) == float((1 - mask).sum())
+    return res
+
+
+def test_frontend_grid_shape():
+    _frontend_case(4, 48000)
+
+
+def test_frontend_ragged_and_sliced():
+    _frontend_case(3, 4801, with_video=False, seed=1)          # odd length: unaligned rows, partial last frame
+    _frontend_case(2, 16000, T=70, F=200, seed=2)              # out_shape slice in T and F
+    _frontend_case(1, 100, with_video=False, seed=3)           # shorter than one frame
+    _frontend_case(5, 9600, frame_ms=25, hop_ms=10, seed=4)    # the 400/160 framing of audio_feat_preprocessing
+
+
+def test_frontend_long_utterance():
+    _frontend_case(2, 320000, seed=5)                          # 20 s -> T = 1667 (BASELINE config 5)
+
+
+def test_frontend_power2_logmel_and_plain_stft():
+    from avsi_b200 import audio_processing as ap
+    from oracle import stft as ostft
+    rng = np.random.default_rng(7)
+    d = dev()
+    wav = np.round(rng.normal(0, 3000, (3, 16000))).astype(np.float32)
+    w = torch.from_numpy(wav).to(d)
+    lm = ap.log_mel_features(w, window_size=25, step_size=10).cpu().numpy()
+    st = ostft.get_stft(wav.astype(np.float64), window_size=25, step_size=10)
+    ref = ostft.get_log_mel_spectrogram(ostft.get_spectrogram(st, power=2))
+    assert lm.shape == ref.shape == (3, 100, 80)
+    assert rel_l2(np.exp(lm), np.exp(ref)) < 1e-5
+    s2 = ap.get_stft(w, window_size=25, step_size=10).cpu().numpy()
+    assert rel_l2(np.stack([s2.real, s2.imag]), np.stack([st.real, st.imag])) < 1e-5
+    sp = ap.get_spectrogram(ap.get_stft(w, window_size=24, step_size=12), log=True).cpu().numpy()
+    ref_sp = ostft.get_spectrogram(ostft.get_stft(wav.astype(np.float64), window_size=24, step_size=12), log=True)
+    assert rel_l2(np.exp(sp), np.exp(ref_sp)) < 1e-5
+
+
+def test_mask_app_chain_matches_docs_fixtures(golden_dir):
+    """masking.py:41-45,93-95 on the GPU: STFT -> x mask -> iSTFT -> int16 == shipped masked.wav +-1 LSB."""
+    from avsi_b200 import audio_processing as ap
+    fx = np.load(os.path.join(golden_dir, 'docs_fixtures.npz'))
+    d = dev()
+    for key in ('800ms_ex1', '800ms_ex2', '1600ms_ex1', '1600ms_ex2'):
+        target, masked = fx[key + '_target'], fx[key + '_masked']
+        a, b = fx[key + '_range']
+        mask = torch.ones(1, 250, 257, device=d)
+        mask[:, a:b] = 0
+        wav = torch.from_numpy(target.astype(np.float32))[None].to(d)
+        stft = ap.get_stft(wav, window_size=24, step_size=12, n_fft=512, out_shape=[1, 250, 257])
+        mstft = stft * mask
+        rec = ap.reconstruct_from(torch.abs(mstft), stft, num_samples=48000)      # oracle phase = angle(target)
+        out = rec[0].cpu().numpy().astype(np.int16)
+        err = np.abs(out.astype(int) - masked.astype(int))
+        assert err.max() <= 1, (key, err.max())
+        rec2 = ap.get_sources(torch.abs(mstft), torch.angle(stft), num_samples=48000)
+        assert np.abs(rec2[0].cpu().numpy().astype(np.int16).astype(int) - masked.astype(int)).max() <= 1
+
+
+def test_istft_roundtrip_and_denorm():
+    from avsi_b200 import audio_processing as ap
+    from oracle import stft as ostft
+    rng = np.random.default_rng(11)
+    d = dev()
+    wav = np.round(rng.normal(0, 3000, (2, 9600))).astype(np.float32)
+    w = torch.from_numpy(wav).to(d)
+    st = ap.get_stft(w, window_size=24, step_size=12)
+    mean = np.full(257, 6.0, np.float32)
+    std = np.full(257, 2.0, np.float32)
+    pred = (torch.log(torch.abs(st) + 1e-6) - 6.0) / 2.0
+    rec = ap.reconstruct_from(pred, st, mean=mean, std=std, num_samples=9600).cpu().numpy()
+    assert np.abs(rec[:, 192:9408] - wav[:, 192:9408]).max() < 0.05
+    ref = ostft.reconstruct_sources(st.cpu().numpy().astype(np.complex128), 0, window_size=24, step_size=12)
+    full = ap.reconstruct_sources(st, num_samples=0, window_size=24, step_size=12).cpu().numpy()
+    assert full.shape == ref.shape and rel_l2(full, ref) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------ video / mask
+def test_video_features_match_oracle():
+    from avsi_b200 import av_sync
+    from oracle import video as ovideo
+    rng = np.random.default_rng(3)
+    for (B, L, T) in ((3, 75, 250), (2, 75, 1667), (1, 75, 25), (2, 500, 1667)):
+        lm = np.round(rng.uniform(50, 300, (B, L, 136)) + np.cumsum(rng.normal(0, 1, (B, L, 136)), 1)).astype(np.float32)
+        vmean = rng.normal(0, 0.1, (B, 136)).astype(np.float32)
+        vstd = rng.uniform(0.2, 0.5, (B, 136)).astype(np.float32)
+        got = av_sync.video_pipeline(lm, T, vmean, vstd).cpu().numpy()
+        ref = np.stack([ovideo.video_features(lm[b].astype(np.float64), T, vmean[b].astype(np.float64),
+                                              vstd[b].astype(np.float64), tot_frames=L, min_frames=1) for b in range(B)])
+        assert got.shape == ref.shape
+        assert np.abs(got - ref.astype(np.float32)).max() <= 1e-5 * np.abs(ref).max()
+        assert np.all(got[:, 0] == (-vmean / vstd).astype(np.float32))
+
+
+def test_expand_mask_bit_exact(golden_dir):
+    import json
+    from avsi_b200 import dataset_generator as dg
+    cases = json.load(open(os.path.join(golden_dir, 'maskgen_cases.json')))
+    gold = np.load(os.path.join(golden_dir, 'maskgen.npz'))
+    ivs, cols = [], []
+    last = None
+    for c in cases:
+        key = (c['seed'], c['n_max'], c['mean'], c['std'])
+        if key != last:
+            random.seed(c['seed'])
+            last = key
+        iv, cov, n = dg.draw_intrusions(250, c['mean'], c['std'], c['n_max'])
+        ivs.append(iv)
+        cols.append(np.unpackbits(gold[c['key']])[:250])
+    mask = dg.expand_masks(ivs, 250, 257).cpu().numpy()
+    assert mask.shape == (len(cases), 250, 257)
+    assert np.array_equal(mask[:, :, 0].astype(np.uint8), np.stack(cols))
+    assert np.all(mask == mask[:, :, :1])
+    random.seed(30)
+    m1, cov, n = dg.get_intrusions_mask(257, 250, 0.27, 0.1, 1)
+    assert np.array_equal(m1[:, 0].astype(np.uint8), cols[0]) and m1.dtype == np.float64
+
+
+# ------------------------------------------------------------------------------------------ losses / optimiser
+@pytest.mark.parametrize('mode', [0, 1])
+def test_masked_l1(mode):
+    from avsi_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(mode)
+    d = dev()
+    B, T, F, ldl = 5, 37, 257, 320
+    logits = rng.standard_normal((T * B, ldl)).astype(np.float32)
+    target = rng.standard_normal((B, T, F)).astype(np.float32)
+    mask = np.ones((B, T, F), np.float32)
+    mask[:, 10:20] = 0
+    mask[2, 30:] = 0
+    seq = np.array([37, 30, 37, 12, 1], np.int32)
+    tl, tt, tm, ts = (torch.from_numpy(x).to(d) for x in (logits, target, mask, seq))
+    sums = torch.zeros(8, dtype=torch.float64, device=d)
+    pred = torch.empty(B, T, F, device=d)
+    dl = torch.zeros(T * B, ldl, dtype=torch.float16, device=d)
+    _lib.check(lib.avsi_masked_l1(_lib.ptr(tl), ldl, _lib.ptr(tt), _lib.ptr(tm), _lib.ptr(ts), B, T, F, mode, 4.0, None,
+                                  _lib.ptr(sums), _lib.ptr(pred), _lib.ptr(dl), ldl, _lib.stream_ptr()), 'l1')
+    sync()
+    x = torch.tensor(logits.reshape(T, B, ldl)[:, :, :F].transpose(1, 0, 2).astype(np.float64), requires_grad=True)
+    tg, mk = torch.tensor(target.astype(np.float64)), torch.tensor(mask.astype(np.float64))
+    sm = (torch.arange(T)[None] < torch.tensor(seq.astype(np.int64))[:, None]).double()[:, :, None]
+    p = (x if mode == 0 else tg * mk + x * (1 - mk)) * sm
+    ad = (tg - p).abs()
+    ref = [(ad * (1 - mk)).sum(), (1 - mk).sum(), (ad * mk).sum(), mk.sum(), ad.sum(), float(B * T * F)]
+    (ad.sum() if mode == 0 else (ad * (1 - mk)).sum()).backward()
+    got = sums.cpu().numpy()
+    for i in range(6):
+        assert abs(got[i] - float(ref[i])) <= 1e-6 * max(1.0, abs(float(ref[i]))), i
+    assert np.allclose(pred.cpu().numpy(), p.detach().numpy(), atol=1e-6)
+    g = dl.cpu().numpy().astype(np.float64).reshape(T, B, ldl)[:, :, :F].transpose(1, 0, 2)
+    assert np.array_equal(g, 4.0 * x.grad.numpy())
+    assert np.all(dl.cpu().numpy()[:, F:] == 0)
+
+
+def test_ctc_matches_oracle():
+    from avsi_b200 import _lib
+    from oracle import ctc as octc
+    lib = _lib.load()
+    rng = np.random.default_rng(2)
+    d = dev()
+    for (T, B, C, Lmax) in ((30, 4, 34, 50), (250, 6, 34, 50), (12, 3, 5, 4)):
+        ldl, col0 = 320, 257
+        if C == 5:
+            ldl, col0 = 16, 3
+        logits = (rng.standard_normal((T * B, ldl)) * 2).astype(np.float32)
+        lab_len = rng.integers(1, min(Lmax, max(2, T // 3)) + 1, B).astype(np.int32)
+        labels = np.zeros((B, Lmax), np.int32)
+        for b in range(B):
+            labels[b, :lab_len[b]] = rng.integers(0, C - 1, lab_len[b])
+        if lab_len[0] >= 2:
+            labels[0, 1] = labels[0, 0]
+        seq = np.full(B, T, np.int32)
+        seq[1] = max(int(2 * lab_len[1] + 1), T - 5)
+        tl, tlab, tll, tsl = (torch.from_numpy(x).to(d) for x in (logits, labels, lab_len, seq))
+        nll = torch.empty(B, device=d)
+        dl = torch.full((T * B, ldl), 5.0, dtype=torch.float16, device=d)
+        ws = torch.empty(int(lib.avsi_ctc_workspace_bytes(B, T, Lmax)) // 4 + 4, device=d)
+        _lib.check(lib.avsi_ctc_loss(_lib.ptr(tl), ldl, col0, C, _lib.ptr(tlab), Lmax, _lib.ptr(tll), _lib.ptr(tsl), B, T,
+                                     8.0, None, _lib.ptr(nll), _lib.ptr(dl), ldl, col0, _lib.ptr(ws), _lib.stream_ptr()),
+                   'ctc')
+        sync()
+        lg = logits.reshape(T, B, ldl)[:, :, col0:col0 + C].astype(np.float64)
+        rn, rg = octc.ctc_alpha_beta(lg, labels, lab_len, seq)
+        assert np.allclose(nll.cpu().numpy(), rn, rtol=2e-5, atol=1e-4), (nll.cpu().numpy(), rn)
+        g = dl.cpu().numpy().astype(np.float64).reshape(T, B, ldl)
+        assert np.abs(g[:, :, col0:col0 + C] / 8.0 - rg).max() < 2e-3          # fp16 storage of values in [-1, 1]
+        assert rel_l2(g[:, :, col0:col0 + C] / 8.0, rg) < 1e-3
+        assert np.all(g[:, :, :col0] == 5.0) and np.all(g[:, :, col0 + C:] == 5.0)
+
+
+def test_adam_tf_and_cast():
+    from avsi_b200 import _lib
+    from oracle import adam as oadam
+    lib = _lib.load()
+    rng = np.random.default_rng(4)
+    d = dev()
+    n = 100003
+    th, g = rng.standard_normal(n).astype(np.float32), (rng.standard_normal(n) * 64).astype(np.float32)
+    m, v = np.zeros(n, np.float32), np.zeros(n, np.float32)
+    tth, tg, tm, tv = (torch.from_numpy(x.copy()).to(d) for x in (th, g, m, v))
+    us = torch.tensor([0.25], device=d)
+    rth, rm, rv = th.astype(np.float64), m.astype(np.float64), v.astype(np.float64)
+    for step in (1, 2, 3):
+        _lib.check(lib.avsi_adam_tf(_lib.ptr(tth), _lib.ptr(tg), _lib.ptr(tm), _lib.ptr(tv), n, 1e-3, 0.9, 0.999, 1e-8,
+                                    step, 1.0 / 16, _lib.ptr(us), 0.0, _lib.stream_ptr()), 'adam')
+        rth, rm, rv = oadam.adam_tf_step(rth, g.astype(np.float64) / 64.0, rm, rv, step)
+    sync()
+    assert np.abs(tth.cpu().numpy() - rth).max() < 1e-6
+    assert rel_l2(tm.cpu().numpy(), rm) < 1e-6 and rel_l2(tv.cpu().numpy(), rv) < 1e-6
+    W = torch.from_numpy(rng.standard_normal((291, 77)).astype(np.float32)).to(d)
+    w16, w16t = torch.empty(291, 77, dtype=torch.float16, device=d), torch.empty(77, 291, dtype=torch.float16, device=d)
+    _lib.check(lib.avsi_cast_weights(_lib.ptr(W), 291, 77, _lib.ptr(w16), _lib.ptr(w16t), _lib.stream_ptr()), 'cast')
+    sync()
+    assert torch.equal(w16, W.half()) and torch.equal(w16t, W.half().t())
+
+
+def test_colsum():
+    from avsi_b200 import _lib
+    lib = _lib.load()
+    d = dev()
+    X = torch.randn(1000, 320, device=d).half()
+    out = torch.ones(291, device=d)
+    _lib.check(lib.avsi_colsum_f16(_lib.ptr(X), 320, 1000, 3, 291, _lib.ptr(out), _lib.stream_ptr()), 'colsum')
+    sync()
+    ref = X[:, 3:294].double().sum(0).cpu().numpy() + 1.0
+    assert np.abs(out.cpu().numpy() - ref).max() < 1e-3
+
+
+# ------------------------------------------------------------------------------------------ LSTM recurrence
+def _lstm_reference(P, Whh, bias, R):
+    """float64 torch recurrence in the kernel's layout.  P [T,B,2,256,4] pre-activations (leaf),
+    Whh [2,1024,256], bias [2,256,4], R [T,B,2,256] = dL/dY.  Returns Y, C, gates, dP, dbias."""
+    T, B = P.shape[:2]
+    Pt = torch.tensor(P, dtype=torch.float64, requires_grad=True)
+    bt = torch.tensor(bias, dtype=torch.float64, requires_grad=True)
+    W = torch.tensor(Whh, dtype=torch.float64).view(2, 256, 4, 256)
+    Ys, Cs, Gs = [[None] * T for _ in range(2)], [[None] * T for _ in range(2)], [[None] * T for _ in range(2)]
+    for d in range(2):
+        h = torch.zeros(B, 256, dtype=torch.float64)
+        c = torch.zeros(B, 256, dtype=torch.float64)
+        for t in (range(T) if d == 0 else range(T - 1, -1, -1)):
+            z = Pt[t, :, d] + torch.einsum('bk,uqk->buq', h, W[d]) + bt[d]
+            i, g, f, o = torch.sigmoid(z[..., 0]), torch.tanh(z[..., 1]), torch.sigmoid(z[..., 2]), torch.sigmoid(z[..., 3])
+            c = f * c + i * g
+            h = o * torch.tanh(c)
+            # the kernel feeds h back as fp16
+            h = h + (h.detach().half().double() - h.detach())
+            Ys[d][t], Cs[d][t], Gs[d][t] = h, c, torch.stack([i, g, f, o], -1)
+    Y = torch.stack([torch.stack(Ys[0]), torch.stack(Ys[1])], 2)          # [T,B,2,256]
+    (Y * torch.tensor(R, dtype=torch.float64)).sum().backward()
+    C = torch.stack([torch.stack(Cs[0]), torch.stack(Cs[1])], 2)
+    G = torch.stack([torch.stack(Gs[0]), torch.stack(Gs[1])], 2)
+    return Y.detach().numpy(), C.detach().numpy(), G.detach().numpy(), Pt.grad.numpy(), bt.grad.numpy()
+
+
+@pytest.mark.parametrize('T,B', [(6, 16), (9, 5), (40, 37), (12, 130)])
+def test_lstm_recurrence_fwd_bwd(T, B):
+    from avsi_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(T * 100 + B)
+    d = dev()
+    H = 250
+    P = (rng.standard_normal((T, B, 2, 256, 4)) * 1.5).astype(np.float16)
+    Whh = np.zeros((2, 1024, 256), np.float16)
+    Whh.reshape(2, 256, 4, 256)[:, :H, :, :H] = (rng.uniform(-1, 1, (2, H, 4, H)) * 0.12).astype(np.float16)
+    bias = np.zeros((2, 256, 4), np.float32)
+    bias[:, :H] = rng.standard_normal((2, H, 4)) * 0.1
+    P[:, :, :, H:] = 0
+    R = rng.standard_normal((T, B, 2, 256)).astype(np.float16)
+    R[..., H:] = 0
+    gates = torch.from_numpy(P.reshape(T * B, 2048).copy()).to(d)
+    whh = torch.from_numpy(Whh.reshape(2048, 256)).to(d)
+    whhT = whh.t().contiguous()
+    tb = torch.from_numpy(bias.reshape(2048)).to(d)
+    y = torch.full((T * B, 512), 3.0, dtype=torch.float16, device=d)
+    cst = torch.full((T * B, 512), 3.0, dtype=torch.float32, device=d)
+    _lib.check(lib.avsi_lstm_fwd(_lib.ptr(gates), _lib.ptr(whh), _lib.ptr(tb), _lib.ptr(y), _lib.ptr(cst), T, B,
+                                 _lib.stream_ptr()), 'lstm_fwd')
+    sync()
+    Yr, Cr, Gr, dPr, dbr = _lstm_reference(P.astype(np.float64), Whh.astype(np.float64), bias.astype(np.float64),
+                                           R.astype(np.float64))
+    Yg = y.cpu().numpy().astype(np.float64).reshape(T, B, 2, 256)
+    Cg = cst.cpu().numpy().astype(np.float64).reshape(T, B, 2, 256)
+    Gg = gates.cpu().numpy().astype(np.float64).reshape(T, B, 2, 256, 4)
+    msg = 'fwd T=%d B=%d: relY %.2e relC %.2e relG %.2e' % (T, B, rel_l2(Yg, Yr), rel_l2(Cg, Cr), rel_l2(Gg, Gr))
+    assert rel_l2(Yg, Yr) < 1e-3 and rel_l2(Cg, Cr) < 1e-3 and rel_l2(Gg, Gr) < 1e-3, msg
+    assert np.all(Yg[..., H:] == 0) and np.all(Cg[..., H:] == 0)       # padded units stay exactly zero
+    # backward
+    dy = torch.from_numpy(R.reshape(T * B, 512)).to(d)
+    dbias = torch.zeros(2048, device=d)
+    scratch = torch.empty(int(lib.avsi_lstm_bwd_scratch_bytes(B)) // 4 + 4, device=d)
+    _lib.check(lib.avsi_lstm_bwd(_lib.ptr(gates), _lib.ptr(whhT), _lib.ptr(cst), _lib.ptr(dy), _lib.ptr(dbias),
+                                 _lib.ptr(scratch), T, B, _lib.stream_ptr()), 'lstm_bwd')
+    sync()
+    dG = gates.cpu().numpy().astype(np.float64).reshape(T, B, 2, 256, 4)
+    dbg = dbias.cpu().numpy().astype(np.float64).reshape(2, 256, 4)
+    msg = 'bwd T=%d B=%d: rel dG %.2e rel db %.2e' % (T, B, rel_l2(dG, dPr), rel_l2(dbg, dbr))
+    assert rel_l2(dG, dPr) < 2e-3 and rel_l2(dbg, dbr) < 2e-3, msg
+    assert np.all(dG[:, :, :, H:] == 0)

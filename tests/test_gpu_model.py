@@ -1,0 +1,158 @@
+"""Model-level parity (B200): front end -> stacked BLSTM -> loss -> BPTT -> Adam against the float64
+oracle on identical synthetic inputs and weights.  Tolerances are BASELINE.json's: spectra 1e-5
+relative, BLSTM outputs and gradients 2e-3 relative L2."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL = 2e-3
+
+
+def _oracle_inputs(batch, input_type):
+    from oracle import stft as ostft
+    from oracle import video as ovideo
+    B, T = batch['wav'].shape[0], batch['T']
+    vid = np.stack([ovideo.video_features(batch['landmarks'][b].astype(np.float64), T, batch['vmean'][b].astype(np.float64),
+                                          batch['vstd'][b].astype(np.float64)) for b in range(B)])
+    _, tsn, audio = ostft.frontend(batch['wav'].astype(np.float64), batch['mask'].astype(np.float64),
+                                   batch['mean'].astype(np.float64), batch['std'].astype(np.float64), None)
+    net_in = {'a': audio, 'v': vid, 'av': np.concatenate([audio, vid], 2)}[input_type]
+    return tsn, net_in
+
+
+def _build(model_name, B, audio_len, seed, seq_len=None, bias_scale=0.05, **cfg_kw):
+    from avsi_b200 import av_sync, models, synth
+    from avsi_b200.layout import init_canonical
+    batch = synth.make_batch(B, audio_len=audio_len, seed=seed)
+    if seq_len is not None:
+        batch['seq_len'] = np.asarray(seq_len, np.int32)
+    cfg = synth.default_config(model_name, batch_size=B, audio_len=audio_len, **cfg_kw)
+    cls, inp = models.MODEL_REGISTRY[model_name]
+    video = av_sync.video_pipeline(batch['landmarks'], batch['T'], batch['vmean'], batch['vstd'])
+    if cls.MTL:
+        model = cls(batch['seq_len'], batch['lab_len'], batch['wav'], batch['mask'], batch['labels'], batch['mean'],
+                    batch['std'], 0.0, cfg, video_features=video, input=inp)
+    else:
+        model = cls(batch['seq_len'], batch['wav'], batch['mask'], batch['mean'], batch['std'], 0.0, cfg,
+                    video_features=video, input=inp)
+    canon = init_canonical(model.engine.layout, seed=seed + 1, bias_scale=bias_scale)
+    model.assign_vars(canon)
+    return model, batch, canon, inp
+
+
+def _check_grads(grads, ograds, what):
+    ga = np.concatenate([grads[k].ravel() for k in sorted(ograds)])
+    gb = np.concatenate([ograds[k].ravel() for k in sorted(ograds)])
+    worst = max((rel_l2(grads[k], ograds[k]), k) for k in ograds if np.linalg.norm(ograds[k]) > 0)
+    assert rel_l2(ga, gb) < TOL, '%s: grad rel-L2 %.3e, worst %s' % (what, rel_l2(ga, gb), worst)
+    assert worst[0] < 2 * TOL, '%s: worst per-variable grad rel-L2 %.3e at %s' % (what, worst[0], worst[1])
+
+
+@pytest.mark.parametrize('model_name,B,audio_len', [('av-blstm', 3, 9600), ('a-blstm', 5, 4800), ('v-blstm', 2, 4800),
+                                                    ('av-blstm', 20, 2400)])
+def test_si_forward_loss_gradients(model_name, B, audio_len):
+    from oracle import blstm as oblstm
+    T = -(-audio_len // 192)
+    seq = np.full(B, T)
+    seq[-1] = T - 3
+    model, batch, canon, inp = _build(model_name, B, audio_len, seed=B, seq_len=seq)
+    tsn, net_in = _oracle_inputs(batch, inp)
+    outs, ograds = oblstm.loss_and_grads('si', dict(net_in=net_in, target=tsn, mask=batch['mask'], seq_len=batch['seq_len']),
+                                         canon, 3)
+    assert rel_l2(model.target_spec_norm.cpu().numpy(), tsn) < 1e-5
+    assert rel_l2(model.net_inputs.cpu().numpy(), net_in) < 1e-3            # fp16 copy of the network input
+    assert rel_l2(model.inference.cpu().numpy(), outs['inference']) < TOL
+    assert rel_l2(model.prediction.cpu().numpy(), outs['prediction']) < TOL
+    for name in ('loss', 'loss_func', 'loss_hole', 'loss_valid'):
+        assert abs(float(getattr(model, name)) - float(outs[name])) < TOL * abs(float(outs[name])), name
+    _check_grads(model.canonical_gradients(), ograds, model_name)
+
+
+def test_si_full_length_utterance():
+    """GRID shape: 3 s, T = 250 -- error growth over the 250-step chain stays inside the budget."""
+    from oracle import blstm as oblstm
+    model, batch, canon, inp = _build('av-blstm', 2, 48000, seed=9)
+    tsn, net_in = _oracle_inputs(batch, inp)
+    outs, ograds = oblstm.loss_and_grads('si', dict(net_in=net_in, target=tsn, mask=batch['mask'], seq_len=batch['seq_len']),
+                                         canon, 3)
+    assert rel_l2(model.prediction.cpu().numpy(), outs['prediction']) < TOL
+    _check_grads(model.canonical_gradients(), ograds, 'av-blstm T=250')
+
+
+@pytest.mark.parametrize('model_name', ['av-blstm-ssnn-ctc', 'a-blstm-ctc'])
+def test_mtl_forward_loss_gradients(model_name):
+    from oracle import blstm as oblstm
+    B, audio_len = 4, 19200          # T = 100 >= 2 * 24 + 1 label states
+    model, batch, canon, inp = _build(model_name, B, audio_len, seed=21, ctc_loss=0.05)
+    tsn, net_in = _oracle_inputs(batch, inp)
+    outs, ograds = oblstm.loss_and_grads(
+        'mtl', dict(net_in=net_in, target=tsn, mask=batch['mask'], seq_len=batch['seq_len'], labels=batch['labels'],
+                    lab_len=batch['lab_len']), canon, 3, ctc_weight=0.05)
+    ipt, asr = model.inference
+    assert rel_l2(ipt.cpu().numpy(), outs['inference']) < TOL
+    assert rel_l2(asr.cpu().numpy(), outs['logits_asr']) < TOL
+    assert rel_l2(model.prediction.cpu().numpy(), outs['prediction']) < TOL
+    assert abs(float(model.loss_hole) - float(outs['loss_hole'])) < TOL * float(outs['loss_hole'])
+    assert abs(float(model.ctc_loss) - float(outs['ctc_loss'])) < TOL * float(outs['ctc_loss'])
+    assert abs(float(model.loss) - float(outs['loss'])) < TOL * float(outs['loss'])
+    _check_grads(model.canonical_gradients(), ograds, model_name)
+    dec = model.decoding
+    assert dec.shape[0] == B and dec.max() < 33
+
+
+def test_train_step_matches_oracle_adam_and_learns():
+    from oracle import adam as oadam
+    from oracle import blstm as oblstm
+    model, batch, canon, inp = _build('av-blstm', 4, 4800, seed=5)
+    tsn, net_in = _oracle_inputs(batch, inp)
+    inputs = dict(net_in=net_in, target=tsn, mask=batch['mask'], seq_len=batch['seq_len'])
+    outs, ograds = oblstm.loss_and_grads('si', inputs, canon, 3)
+    l0 = float(model.loss)
+    model.train_op()
+    new = model.engine.export_canonical()
+    # TF Adam, first step: every touched weight moves by ~lr * sign(g)
+    upd_ref, upd_got = [], []
+    for k in sorted(canon):
+        th, _, _ = oadam.adam_tf_step(canon[k], ograds[k], np.zeros_like(canon[k]), np.zeros_like(canon[k]), 1)
+        big = np.abs(ograds[k]) > 1e-6 * np.abs(ograds[k]).max()         # sign of tiny gradients is noise
+        upd_ref.append((th - canon[k])[big])
+        upd_got.append((new[k] - canon[k])[big])
+    ur, ug = np.concatenate(upd_ref), np.concatenate(upd_got)
+    assert rel_l2(ug, ur) < 0.02
+    assert model.global_step == 1
+    losses = [l0]
+    for _ in range(15):
+        model.feed()                 # same batch: invalidate caches
+        model.train_op()
+    model.feed()
+    losses.append(float(model.loss))
+    assert np.isfinite(losses[-1]) and losses[-1] < 0.9 * losses[0], losses
+    # padded parameters never move
+    pad = torch.from_numpy(1.0 - model.engine.layout.pad_mask()).to(model.device)
+    assert float((model.engine.theta.abs() * pad).max()) == 0.0
+
+
+def test_variables_roundtrip_and_inference_mode():
+    from avsi_b200 import av_sync, models, synth
+    model, batch, canon, inp = _build('av-blstm', 2, 4800, seed=7)
+    model.build_graph('av-blstm')
+    tv = model.train_vars
+    assert set(tv) == set('av-blstm/' + k for k in canon)
+    assert tv['av-blstm/logits/weights'].shape == (500, 257)
+    for k in canon:
+        assert np.allclose(tv['av-blstm/' + k], canon[k].astype(np.float32), atol=0)
+    cfg = synth.default_config('av-blstm', batch_size=2, audio_len=4800)
+    video = av_sync.video_pipeline(batch['landmarks'], batch['T'], batch['vmean'], batch['vstd'])
+    m2 = models.StackedBLSTMModel(batch['seq_len'], batch['wav'], batch['mask'], batch['mean'], batch['std'], 0.0, cfg,
+                                  video_features=video, input='av', is_training=False)
+    m2.build_graph('av-blstm')
+    m2.assign_vars(model.all_vars)
+    assert torch.equal(m2.prediction, model.prediction)
+    enh = m2.enhanced_sources
+    assert enh.shape == (2, 4800) and torch.isfinite(enh).all()
+    with pytest.raises(Exception):
+        m2.train_op()
