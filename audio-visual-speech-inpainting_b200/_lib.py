@@ -6,7 +6,7 @@ only the allocator / stream provider here.
 """
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libavsi_b200.so')
@@ -65,7 +65,7 @@ SIGNATURES = {
     'avsi_ctc_workspace_bytes': (c_int64, [c_int, c_int, c_int]),
     'avsi_ctc_loss': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int,
                               c_float, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
-    'avsi_adam_tf': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float,
+    'avsi_adam_tf': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double, c_double, c_double,
                              c_int, c_float, c_void_p, c_float, c_void_p]),
     'avsi_cast_weights': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
 }

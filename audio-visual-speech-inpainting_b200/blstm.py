@@ -117,7 +117,9 @@ class BLSTMEngine(object):
             ws['dY'] = [torch.empty(M, NY, dtype=torch.float16, device=dev) for _ in range(2)]
             nbytes = int(_lib.load().avsi_lstm_bwd_scratch_bytes(B))
             ws['scratch'] = torch.empty(max(nbytes, 16) // 4, dtype=torch.float32, device=dev)
-        self._ws = {key: ws} if len(self._ws) > 4 else dict(self._ws, **{key: ws})
+        if len(self._ws) > 4:
+            self._ws = {}
+        self._ws[key] = ws
         return ws
 
     # ---- forward ------------------------------------------------------------------------------

@@ -9,14 +9,14 @@ namespace avsi {
 
 __global__ void __launch_bounds__(256)
 adam_tf_kernel(float* __restrict__ theta, const float* __restrict__ g, float* __restrict__ m,
-               float* __restrict__ v, long long n, float lr_t, float b1, float b2, float eps,
+               float* __restrict__ v, long long n, float lr_t, float b1, float omb1, float b2, float omb2, float eps,
                float unscale, const float* __restrict__ unscale_dev, float l2) {
   const float us = unscale * (unscale_dev ? *unscale_dev : 1.f);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float th = theta[i];
     float gi = fmaf(g[i], us, l2 * th);
-    float mi = b1 * m[i] + (1.f - b1) * gi;
-    float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    float mi = b1 * m[i] + omb1 * gi;
+    float vi = b2 * v[i] + omb2 * gi * gi;
     m[i] = mi;
     v[i] = vi;
     theta[i] = th - lr_t * mi / (sqrtf(vi) + eps);
@@ -61,16 +61,17 @@ __global__ void mtl_scales_kernel(const float* __restrict__ hole_count, int B, f
 
 }  // namespace avsi
 
-extern "C" int avsi_adam_tf(float* theta, const float* g, float* m, float* v, int64_t n, float lr, float b1,
-                            float b2, float eps, int step, float grad_unscale, const float* grad_unscale_dev,
+extern "C" int avsi_adam_tf(float* theta, const float* g, float* m, float* v, int64_t n, double lr, double b1,
+                            double b2, double eps, int step, float grad_unscale, const float* grad_unscale_dev,
                             float l2, void* stream) {
   using namespace avsi;
   AVSI_REQUIRE(theta && g && m && v, "null pointer");
   AVSI_REQUIRE(n > 0 && step >= 1, "n > 0, step >= 1");
   // lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t), evaluated in double on the host
-  double lr_t = (double)lr * sqrt(1.0 - pow((double)b2, (double)step)) / (1.0 - pow((double)b1, (double)step));
+  double lr_t = lr * sqrt(1.0 - pow(b2, (double)step)) / (1.0 - pow(b1, (double)step));
   int blocks = (int)min((long long)(n + 255) / 256, (long long)num_sms() * 8);
-  adam_tf_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(theta, g, m, v, (long long)n, (float)lr_t, b1, b2, eps,
+  adam_tf_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(theta, g, m, v, (long long)n, (float)lr_t, (float)b1, (float)(1.0 - b1),
+                                                          (float)b2, (float)(1.0 - b2), (float)eps,
                                                           grad_unscale, grad_unscale_dev, l2);
   AVSI_LAUNCH_CHECK();
   return AVSI_OK;

@@ -180,8 +180,8 @@ int avsi_ctc_loss(const float* logits, int ldl, int col0, int C, const int32_t* 
 /* ------------------------------------------------------------------------------------
  * Optimiser.  Replaces tf.train.AdamOptimizer ApplyAdam (models.py:168,178), TF epsilon-hat form.
  *   g is multiplied by grad_unscale first; l2 adds l2 * theta to the gradient (models.py:153-158). */
-int avsi_adam_tf(float* theta, const float* g, float* m, float* v, int64_t n, float lr, float b1,
-                 float b2, float eps, int step, float grad_unscale, const float* grad_unscale_dev,
+int avsi_adam_tf(float* theta, const float* g, float* m, float* v, int64_t n, double lr, double b1,
+                 double b2, double eps, int step, float grad_unscale, const float* grad_unscale_dev,
                  float l2, void* stream);
 /* fp32 -> fp16 copies of a weight matrix W [R,C]: w16 [R,C] and (optional) w16t [C,R]. */
 int avsi_cast_weights(const float* w, int R, int C, uint16_t* w16, uint16_t* w16t, void* stream);
