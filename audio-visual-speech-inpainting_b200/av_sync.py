@@ -28,10 +28,13 @@ def video_pipeline(landmarks, target_len, vmean, vstd, device='cuda'):
     """landmarks [B,L,D] (padded), vmean/vstd [B,D] or [D] -> z-normed motion vectors [B,T,D] f32 CUDA.
     tfrecord_utils.py:90-107 order: upsample -> first difference -> normalise."""
     lib = _lib.load()
-    lm = torch.as_tensor(np.asarray(landmarks), dtype=torch.float32).to(device).contiguous()
+    def dev32(x):
+        if not torch.is_tensor(x):
+            x = torch.as_tensor(np.asarray(x))
+        return x.to(device=device, dtype=torch.float32)
+    lm = dev32(landmarks).contiguous()
     B, L, D = lm.shape
-    vm = torch.as_tensor(np.asarray(vmean), dtype=torch.float32).to(device)
-    vs = torch.as_tensor(np.asarray(vstd), dtype=torch.float32).to(device)
+    vm, vs = dev32(vmean), dev32(vstd)
     vm = vm.expand(B, D).contiguous() if vm.dim() == 1 else vm.contiguous()
     vs = vs.expand(B, D).contiguous() if vs.dim() == 1 else vs.contiguous()
     out = torch.empty(B, target_len, D, dtype=torch.float32, device=device)

@@ -1,0 +1,52 @@
+#!/usr/bin/env python
+"""Micro-benchmark of the recurrence kernels alone: us per time step vs batch size (CUDA events).
+usage: python profiles/bench_lstm.py [T] [B1,B2,...]"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from avsi_b200 import _lib
+
+lib = _lib.load()
+d = torch.device('cuda:0')
+T = int(sys.argv[1]) if len(sys.argv) > 1 else 250
+BS = [int(x) for x in (sys.argv[2] if len(sys.argv) > 2 else '16,64,112,128,224,448,512,896').split(',')]
+for B in BS:
+    g0 = torch.randn(T * B, 2048, device=d).half()
+    gates = g0.clone()
+    whh = (torch.randn(2048, 256, device=d) * 0.05).half()
+    whhT = whh.t().contiguous()
+    bias = torch.zeros(2048, device=d)
+    y = torch.empty(T * B, 512, dtype=torch.float16, device=d)
+    cst = torch.empty(T * B, 512, device=d)
+    dy = torch.randn(T * B, 512, device=d).half()
+    dbias = torch.zeros(2048, device=d)
+    scratch = torch.empty(16, device=d)
+
+    def fwd():
+        _lib.check(lib.avsi_lstm_fwd(_lib.ptr(gates), _lib.ptr(whh), _lib.ptr(bias), _lib.ptr(y), _lib.ptr(cst), T, B,
+                                     _lib.stream_ptr()))
+
+    def bwd():
+        _lib.check(lib.avsi_lstm_bwd(_lib.ptr(gates), _lib.ptr(whhT), _lib.ptr(cst), _lib.ptr(dy), _lib.ptr(dbias),
+                                     _lib.ptr(scratch), T, B, _lib.stream_ptr()))
+
+    res = {'fwd': 0.0, 'bwd': 0.0}
+    reps = 3
+    for it in range(reps + 2):
+        gates.copy_(g0)
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record()
+        fwd()
+        e[1].record()
+        bwd()
+        e[2].record()
+        torch.cuda.synchronize()
+        if it >= 2:
+            res['fwd'] += e[0].elapsed_time(e[1]) / reps
+            res['bwd'] += e[1].elapsed_time(e[2]) / reps
+    print('B=%4d T=%d  fwd %.3f ms (%.2f us/step)  bwd %.3f ms (%.2f us/step)  -> %.0f utt/s for one layer fwd+bwd'
+          % (B, T, res['fwd'], 1e3 * res['fwd'] / T, res['bwd'], 1e3 * res['bwd'] / T,
+             B / ((res['fwd'] + res['bwd']) * 1e-3)))

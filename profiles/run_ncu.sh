@@ -1,0 +1,14 @@
+#!/bin/bash
+# Profiling recipe (B200_PROFILING.md): plain run first, then the launch list, then --set full
+# captures of the top kernels.  Run under gpurun on ONE GPU; outputs land in gpurun_out/.
+# usage: bash profiles/run_ncu.sh <tag> [batch]
+TAG=${1:-r01}
+BATCH=${2:-128}
+CMD="python bench.py --steps 2 --warmup 3 --batch $BATCH --no-cpu-baseline"
+mkdir -p gpurun_out
+$CMD > gpurun_out/ncu_plain_$TAG.json 2> gpurun_out/ncu_plain_$TAG.err || { echo "plain run failed"; tail -5 gpurun_out/ncu_plain_$TAG.err; exit 1; }
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > /dev/null 2>&1
+for K in lstm_fwd_kernel lstm_bwd_kernel frontend_kernel gemm_f16_kernel; do
+  ncu --set full --clock-control none --import-source on -k regex:$K -s 4 -c 1 -f -o gpurun_out/prof_${K}_$TAG $CMD > /dev/null 2>&1
+done
+ls -la gpurun_out/
