@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, 'csrc')
 LIB_PATH = os.path.join(HERE, 'libavsi_b200.so')
 BUILD_DIR = os.path.join(HERE, 'csrc', 'build')
 
-SOURCES = ['capi.cu', 'frontend.cu', 'istft.cu', 'video.cu', 'gemm_sm100.cu', 'lstm.cu', 'loss.cu', 'ctc.cu', 'optim.cu']
+SOURCES = ['capi.cu', 'frontend.cu', 'istft.cu', 'video.cu', 'gemm_sm100.cu', 'lstm.cu', 'lstm_tc.cu', 'loss.cu', 'ctc.cu', 'optim.cu']
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-std=c++17', '-O3', '-lineinfo',
               '-Xcompiler', '-fPIC']
@@ -44,7 +44,7 @@ def sources():
 def build_library(force=False, verbose=False):
     """Compile every .cu under csrc/ and link libavsi_b200.so.  Returns the library path."""
     srcs = sources()
-    headers = [os.path.join(CSRC, 'common.cuh'), os.path.join(os.path.dirname(HERE), 'include', 'avsi_b200.h')]
+    headers = [os.path.join(CSRC, 'common.cuh'), os.path.join(CSRC, 'sm100_ptx.cuh'), os.path.join(os.path.dirname(HERE), 'include', 'avsi_b200.h')]
     stamp = os.path.join(BUILD_DIR, 'stamp.txt')
     dig = _digest(srcs + headers)
     if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp) and open(stamp).read() == dig:

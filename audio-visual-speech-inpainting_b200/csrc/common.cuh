@@ -61,6 +61,20 @@ __device__ __forceinline__ float tanhf_fast(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(x));
   return t;
 }
+// fast activations for the recurrence: ex2.approx + rcp.approx (2 MUFU, ~2 ulp each), no IEEE fix-up code
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_fast2(float x) { return rcp_approx(1.0f + ex2_approx(-1.4426950408889634f * x)); }
+// tanh(x) = 2 sigmoid(2x) - 1, saturates cleanly for |x| large
+__device__ __forceinline__ float tanh_fast2(float x) { return fmaf(2.0f, rcp_approx(1.0f + ex2_approx(-2.8853900817779268f * x)), -1.0f); }
 // accurate versions (expf based, ~1e-7 rel) used where the 2e-3 budget is tight
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + __expf(-x)); }
 __device__ __forceinline__ float tanhf_acc(float x) {

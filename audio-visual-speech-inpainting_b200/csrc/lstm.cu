@@ -27,6 +27,7 @@
 // st.async / mbarrier mechanism (reduce-scatter in DSMEM), the owner sums the 8 slots.
 // Bias gradients accumulate in registers over t.
 #include "common.cuh"
+#include "sm100_ptx.cuh"
 
 namespace avsi {
 
@@ -37,9 +38,6 @@ constexpr int LS_THREADS = 256;
 constexpr int LS_HSTRIDE = LS_HP + 8;     // halves per smem row of h (528 B, conflict-free ldmatrix)
 constexpr int LS_DSTRIDE = 128 + 8;       // halves per smem row of dgates
 
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 __device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& a0, uint32_t& a1, uint32_t& a2, uint32_t& a3) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3)
@@ -52,45 +50,9 @@ __device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem_addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void st_async_v2(uint32_t raddr, uint32_t a, uint32_t b, uint32_t rmbar) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];"
-               ::"r"(raddr), "r"(a), "r"(b), "r"(rmbar) : "memory");
-}
-__device__ __forceinline__ void st_async_v4(uint32_t raddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t rmbar) {
-  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
-               ::"r"(raddr), "r"(a), "r"(b), "r"(c), "r"(d), "r"(rmbar) : "memory");
-}
-__device__ __forceinline__ void ls_mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void ls_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void ls_mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "LS_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra LS_DONE;\n"
-      "bra LS_WAIT;\n"
-      "LS_DONE:\n"
-      "}\n" ::"r"(bar),
-      "r"(parity)
-      : "memory");
-}
-
 // fast, accurate-enough activations: ex2.approx + rcp.approx (2 MUFU each), ~2 ulp
-__device__ __forceinline__ float fsigmoid(float x) { return __frcp_rn(1.0f + __expf(-x)); }
-__device__ __forceinline__ float ftanh(float x) {
-  // tanh(x) = 1 - 2 / (exp(2x) + 1); saturates cleanly for |x| large
-  return 1.0f - 2.0f * __frcp_rn(__expf(2.0f * x) + 1.0f);
-}
+__device__ __forceinline__ float fsigmoid(float x) { return sigmoid_fast2(x); }
+__device__ __forceinline__ float ftanh(float x) { return tanh_fast2(x); }
 
 template <int BT>
 struct LstmFwdSmem {
@@ -116,11 +78,11 @@ lstm_fwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whh, 
   const uint32_t hbuf_s = (uint32_t)__cvta_generic_to_shared(&sm.hbuf[0][0]);
   const uint32_t mbar_s = (uint32_t)__cvta_generic_to_shared(&sm.mbar[0]);
   if (tid == 0) {
-    ls_mbar_init(mbar_s, 1);
-    ls_mbar_init(mbar_s + 8, 1);
+    mbar_init(mbar_s, 1);
+    mbar_init(mbar_s + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    if (T > 1) ls_mbar_expect_tx(mbar_s, PHASE_BYTES);          // h_0 lands in buffer 0
-    if (T > 2) ls_mbar_expect_tx(mbar_s + 8, PHASE_BYTES);      // h_1 lands in buffer 1
+    if (T > 1) mbar_expect_tx(mbar_s, PHASE_BYTES);          // h_0 lands in buffer 0
+    if (T > 2) mbar_expect_tx(mbar_s + 8, PHASE_BYTES);      // h_1 lands in buffer 1
   }
 
   // W_hh fragments: mma column c of n-tile nt <-> unit (c/2), gate (c%2) + 2 nt
@@ -172,8 +134,8 @@ lstm_fwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whh, 
 
     if (s > 0) {
       const int pb = (s - 1) & 1;
-      ls_mbar_wait(mbar_s + 8 * pb, ((s - 1) >> 1) & 1);          // all of h_{s-1} has landed here
-      if (tid == 0 && s + 1 < T - 1) ls_mbar_expect_tx(mbar_s + 8 * pb, PHASE_BYTES);   // re-arm for h_{s+1}
+      mbar_wait(mbar_s + 8 * pb, ((s - 1) >> 1) & 1);          // all of h_{s-1} has landed here
+      if (tid == 0 && s + 1 < T - 1) mbar_expect_tx(mbar_s + 8 * pb, PHASE_BYTES);   // re-arm for h_{s+1}
       const uint32_t hb = hbuf_s + (uint32_t)(pb * BT * LS_HSTRIDE) * 2u;
 #pragma unroll
       for (int kt = 0; kt < 16; ++kt) {
@@ -253,11 +215,11 @@ lstm_bwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whhT,
   const uint32_t pb_s = (uint32_t)__cvta_generic_to_shared(&sm.pbuf[0][0][0]);
   const uint32_t mbar_s = (uint32_t)__cvta_generic_to_shared(&sm.mbar[0]);
   if (tid == 0) {
-    ls_mbar_init(mbar_s, 1);
-    ls_mbar_init(mbar_s + 8, 1);
+    mbar_init(mbar_s, 1);
+    mbar_init(mbar_s + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    if (T > 1) ls_mbar_expect_tx(mbar_s, PHASE_BYTES);
-    if (T > 2) ls_mbar_expect_tx(mbar_s + 8, PHASE_BYTES);
+    if (T > 1) mbar_expect_tx(mbar_s, PHASE_BYTES);
+    if (T > 2) mbar_expect_tx(mbar_s + 8, PHASE_BYTES);
   }
 
   // W_hh^T fragments for partial dh[BT, 256] = dgates[BT, own 128 cols] . W_hh[own cols, 256]:
@@ -309,8 +271,8 @@ lstm_bwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whhT,
     for (int mt = 0; mt < MT; ++mt) dhr[mt][0] = dhr[mt][1] = 0.f;
     if (s > 0) {
       const int pb = (s - 1) & 1;
-      ls_mbar_wait(mbar_s + 8 * pb, ((s - 1) >> 1) & 1);          // the 8 partial slots of step s-1 are here
-      if (tid == 0 && s + 1 < T - 1) ls_mbar_expect_tx(mbar_s + 8 * pb, PHASE_BYTES);
+      mbar_wait(mbar_s + 8 * pb, ((s - 1) >> 1) & 1);          // the 8 partial slots of step s-1 are here
+      if (tid == 0 && s + 1 < T - 1) mbar_expect_tx(mbar_s + 8 * pb, PHASE_BYTES);
       const uint16_t* slots = &sm.pbuf[pb][0][0];
 #pragma unroll
       for (int src = 0; src < LS_CL; ++src)
@@ -470,6 +432,22 @@ static int launch_bwd(uint16_t* gates, const uint16_t* whhT, const float* cst, c
   return AVSI_OK;
 }
 
+int launch_lstm_fwd_tc(uint16_t* gates, const uint16_t* whh, const float* bias, uint16_t* y, float* cst, int T, int B,
+                       cudaStream_t st);   // lstm_tc.cu
+
+// which forward kernel: tcgen05 (128-row tiles) once the batch no longer fits 16-row mma.sync tiles
+// in one wave of clusters.  AVSI_LSTM_FWD=mma|tc overrides (A/B measurements only).
+static bool use_tc_fwd(int B) {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("AVSI_LSTM_FWD");
+    mode = (e && !strcmp(e, "mma")) ? 1 : ((e && !strcmp(e, "tc")) ? 2 : 0);
+  }
+  if (mode == 1) return false;
+  if (mode == 2) return true;
+  return pick_bt(B) > 16;
+}
+
 }  // namespace avsi
 
 extern "C" int avsi_lstm_fwd(uint16_t* gates, const uint16_t* whh, const float* bias, uint16_t* y, float* cst,
@@ -479,6 +457,7 @@ extern "C" int avsi_lstm_fwd(uint16_t* gates, const uint16_t* whh, const float* 
   AVSI_REQUIRE(T > 0 && B > 0, "T,B > 0");
   const int bt = pick_bt(B);
   cudaStream_t st = (cudaStream_t)stream;
+  if (use_tc_fwd(B)) return launch_lstm_fwd_tc(gates, whh, bias, y, cst, T, B, st);
   if (bt == 16) return launch_fwd<16>(gates, whh, bias, y, cst, T, B, st);
   if (bt == 32) return launch_fwd<32>(gates, whh, bias, y, cst, T, B, st);
   return launch_fwd<64>(gates, whh, bias, y, cst, T, B, st);

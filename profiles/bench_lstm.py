@@ -50,3 +50,15 @@ for B in BS:
     print('B=%4d T=%d  fwd %.3f ms (%.2f us/step)  bwd %.3f ms (%.2f us/step)  -> %.0f utt/s for one layer fwd+bwd'
           % (B, T, res['fwd'], 1e3 * res['fwd'] / T, res['bwd'], 1e3 * res['bwd'] / T,
              B / ((res['fwd'] + res['bwd']) * 1e-3)))
+
+if os.environ.get('AVSI_TC_TIMING'):
+    import ctypes
+    buf = (ctypes.c_ulonglong * 16)()
+    torch.cuda.synchronize()
+    fwd()
+    torch.cuda.synchronize()
+    lib.avsi_debug_lstm_tc_timing.argtypes = [ctypes.c_void_p]
+    lib.avsi_debug_lstm_tc_timing(buf)
+    names = ['prefetch', 'wait_h', 'mma_issue', 'wait_mma', 'tmem_ld', 'cell', 'stage+bar', 'copy+stores']
+    for o, who in ((0, 'thread 0'), (8, 'thread 511')):
+        print(who, '  '.join('%s %.0f' % (n, buf[o + i] / T) for i, n in enumerate(names)), ' total %.0f cyc/step' % (sum(buf[o:o + 8]) / T))

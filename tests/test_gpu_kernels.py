@@ -390,7 +390,7 @@ def _lstm_reference(P, Whh, bias, R):
     return Y.detach().numpy(), C.detach().numpy(), G.detach().numpy(), Pt.grad.numpy(), bt.grad.numpy()
 
 
-@pytest.mark.parametrize('T,B', [(6, 16), (9, 5), (40, 37), (12, 130)])
+@pytest.mark.parametrize('T,B', [(6, 16), (9, 5), (40, 37), (12, 130), (7, 300), (2, 128), (1, 200)])
 def test_lstm_recurrence_fwd_bwd(T, B):
     from avsi_b200 import _lib
     lib = _lib.load()
