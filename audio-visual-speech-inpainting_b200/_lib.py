@@ -54,7 +54,7 @@ SIGNATURES = {
     'avsi_video_features': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'avsi_expand_mask': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'avsi_gemm_f16': (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p,
-                              c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+                              c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'avsi_lstm_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     'avsi_lstm_bwd_scratch_bytes': (c_int64, [c_int]),
     'avsi_lstm_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),

@@ -28,11 +28,30 @@ def _p(t):
     return _lib.ptr(t)
 
 
-def gemm(A, lda, B, ldb, C, ldc, bias, M, N, K, trans, out_mode, split_k=1, tag='gemm'):
+A_IL, C_IL = 1, 2     # avsi_gemm_f16 layout bits: A operand / f16 output stored interleaved (include/avsi_b200.h)
+
+
+def gemm(A, lda, B, ldb, C, ldc, bias, M, N, K, trans, out_mode, split_k=1, tag='gemm', layout=0):
     lib = _lib.load()
     with _lib.span(tag, flops=2 * M * N * K):
-        _lib.check(lib.avsi_gemm_f16(A, lda, B, ldb, C, ldc, bias, M, N, K, trans, out_mode, split_k,
+        _lib.check(lib.avsi_gemm_f16(A, lda, B, ldb, C, ldc, bias, M, N, K, trans, out_mode, split_k, layout,
                                      _lib.stream_ptr()), 'avsi_gemm_f16')
+
+
+def to_il(x, chunk=8):
+    """Row-major [R, C] tensor -> interleaved [ceil32(R)/32, C/chunk, 32, chunk] copy (test / debug helper)."""
+    R, C = x.shape
+    Rp = -(-R // 32) * 32
+    xp = torch.zeros(Rp, C, dtype=x.dtype, device=x.device)
+    xp[:R] = x
+    return xp.view(Rp // 32, 32, C // chunk, chunk).permute(0, 2, 1, 3).contiguous().view(Rp, C)
+
+
+def from_il(x, R, chunk=8):
+    """Inverse of to_il: interleaved storage (any shape with ceil32(R)*C elements) -> row-major [R, C]."""
+    Rp = -(-R // 32) * 32
+    C = x.numel() // Rp
+    return x.view(Rp // 32, C // chunk, 32, chunk).permute(0, 2, 1, 3).contiguous().view(Rp, C)[:R]
 
 
 def pick_split_k(m_rows, n_cols, k, target_ctas=296):
@@ -108,9 +127,14 @@ class BLSTMEngine(object):
         dev = self.device
         ws = {'T': T, 'B': B, 'M': M}
         ws['x0'] = torch.zeros(M, L.k0p, dtype=torch.float16, device=dev)
-        ws['G'] = [torch.empty(M, NG, dtype=torch.float16, device=dev) for _ in range(L.n_layers if training else 1)]
-        ws['Y'] = [torch.empty(M, NY, dtype=torch.float16, device=dev) for _ in range(L.n_layers)]
-        ws['C'] = [torch.empty(M, NY, dtype=torch.float32, device=dev) for _ in range(L.n_layers if training else 1)]
+        Mp = -(-M // 32) * 32
+        # gate tensors and cell-state stash are INTERLEAVED (rows padded to 32, padding stays zero)
+        ws['G'] = [torch.zeros(Mp, NG, dtype=torch.float16, device=dev) for _ in range(L.n_layers if training else 1)]
+        # layer outputs sit between B leading and B trailing zero rows: h_{t-1} / h_{t+1} of the dW_hh
+        # contractions are then plain row-shifted views (h_{-1} = h_T = 0)
+        ws['Ybuf'] = [torch.zeros(M + 2 * B, NY, dtype=torch.float16, device=dev) for _ in range(L.n_layers)]
+        ws['Y'] = [yb[B:B + M] for yb in ws['Ybuf']]
+        ws['C'] = [torch.zeros(Mp, NY, dtype=torch.float32, device=dev) for _ in range(L.n_layers if training else 1)]
         ws['logits'] = torch.zeros(M, L.nop, dtype=torch.float32, device=dev)
         if training:
             ws['dlogits'] = torch.zeros(M, L.nop, dtype=torch.float16, device=dev)
@@ -134,7 +158,8 @@ class BLSTMEngine(object):
             G = ws['G'][l if training else 0]
             C = ws['C'][l if training else 0]
             kp = L.layer_k(l)
-            gemm(_p(x), ldx, _p(self.half['wih%d' % l]), kp, _p(G), NG, None, M, NG, kp, 0, 0, tag='gemm_proj_fwd')
+            gemm(_p(x), ldx, _p(self.half['wih%d' % l]), kp, _p(G), NG, None, M, NG, kp, 0, 0, tag='gemm_proj_fwd',
+                 layout=C_IL)
             with _lib.span('lstm_fwd', flops=2 * M * NG * HP):
                 _lib.check(lib.avsi_lstm_fwd(_p(G), _p(self.half['whh%d' % l]), _p(self.view(self.theta, 'b%d' % l)),
                                              _p(ws['Y'][l]), _p(C), T, B, _lib.stream_ptr()), 'avsi_lstm_fwd')
@@ -171,23 +196,22 @@ class BLSTMEngine(object):
             x, ldx = (ws['x0'], L.k0p) if l == 0 else (ws['Y'][l - 1], NY)
             # dWih = dG^T . X
             gemm(_p(G), NG, _p(x), ldx, _p(self.view(g, 'wih%d' % l)), kp, None, NG, kp, M, 1, 2,
-                 pick_split_k(NG, kp, M), tag='gemm_dw')
-            # dWhh[dir] = dG[dir]^T . h_prev  (fw: h_{t-1}, bw: h_{t+1})
+                 pick_split_k(NG, kp, M), tag='gemm_dw', layout=A_IL)
+            # dWhh[dir] = dG[dir]^T . h_prev  (fw: h_{t-1}, bw: h_{t+1}): row-shifted views of the zero-framed Y
             if T > 1:
-                Kr = (T - 1) * B
                 gw = self.view(g, 'whh%d' % l)
-                sk = pick_split_k(GATES * HP, HP, Kr, 148)
-                a_fw = G.data_ptr() + B * NG * 2
-                b_fw = Y.data_ptr()
-                gemm(a_fw, NG, b_fw, NY, _p(gw), HP, None, GATES * HP, HP, Kr, 1, 2, sk, tag='gemm_dw')
-                a_bw = G.data_ptr() + GATES * HP * 2
-                b_bw = Y.data_ptr() + (B * NY + HP) * 2
-                gemm(a_bw, NG, b_bw, NY, gw.data_ptr() + GATES * HP * HP * 4, HP, None, GATES * HP, HP, Kr, 1, 2, sk,
-                     tag='gemm_dw')
+                sk = pick_split_k(GATES * HP, HP, M, 148)
+                yb = ws['Ybuf'][l].data_ptr()
+                gemm(G.data_ptr(), NG, yb, NY, _p(gw), HP, None, GATES * HP, HP, M, 1, 2, sk, tag='gemm_dw',
+                     layout=A_IL)
+                a_bw = G.data_ptr() + (GATES * HP // 8) * 512            # IL column offset: 512 B per 8-column chunk
+                b_bw = yb + (2 * B * NY + HP) * 2
+                gemm(a_bw, NG, b_bw, NY, gw.data_ptr() + GATES * HP * HP * 4, HP, None, GATES * HP, HP, M, 1, 2, sk,
+                     tag='gemm_dw', layout=A_IL)
             if l > 0:
                 nxt = 1 - cur
                 gemm(_p(G), NG, _p(self.half['wihT%d' % l]), NG, _p(ws['dY'][nxt]), NY, None, M, NY, NG, 0, 0,
-                     tag='gemm_dx')
+                     tag='gemm_dx', layout=A_IL)
                 cur = nxt
         return g
 

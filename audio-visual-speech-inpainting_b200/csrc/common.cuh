@@ -92,6 +92,18 @@ __device__ __forceinline__ float2 unpack_half2(uint32_t u) {
   return __half22float2(h);
 }
 
+// Interleaved ("IL") activation layout: a [R x C] matrix stored as [R/32][C/chunk][32 rows][chunk] with
+// 16-byte chunks (8 halves / 4 floats).  A warp whose lanes own 32 consecutive rows reads or writes one
+// 512-byte contiguous run per 16-byte column chunk (4 cache lines per instruction instead of 32), and a
+// [rows x 8 cols] sub-block is exactly the SWIZZLE_NONE core-matrix layout tcgen05 descriptors address.
+// R is padded to a multiple of 32 by the allocator; C must be a multiple of the chunk.
+__host__ __device__ __forceinline__ long long il16(long long r, int c, int C) {
+  return (((r >> 5) * (long long)(C >> 3) + (c >> 3)) << 8) + ((r & 31) << 3) + (c & 7);
+}
+__host__ __device__ __forceinline__ long long il32(long long r, int c, int C) {
+  return (((r >> 5) * (long long)(C >> 2) + (c >> 2)) << 7) + ((r & 31) << 2) + (c & 3);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -11,6 +11,11 @@
 // Operand layouts:
 //   trans == 0  A [M,K], B [N,K] row-major  -> K-major smem tiles   (box 64(k) x rows)
 //   trans == 1  A [K,M], B [K,N] row-major  -> MN-major smem tiles  (boxes 64(mn) x 64(k))
+//   layout & 1  A is stored INTERLEAVED (common.cuh il16: [rows/32][cols/8][32][8]); one 3-D TMA box per
+//               stage lands it as SWIZZLE_NONE core matrices: K-major [k-chunk][128 rows][16 B] (trans 0,
+//               LBO 2048 / SBO 128) or MN-major [m-chunk][64 k-rows][16 B] (trans 1, LBO 128 / SBO 1024)
+//   layout & 2  the f16 output (out_mode 0) is written interleaved: a warp's 32 rows x 8 columns are one
+//               contiguous 512-byte store
 // Shared-memory matrix descriptors follow the canonical SWIZZLE_128B layouts
 // (K-major: SBO = 1024 B; MN-major: SBO = 1024 B, LBO = 8192 B), version = 1 (sm_100).
 #include <cuda.h>
@@ -32,6 +37,7 @@ struct GemmParams {
   const float* bias;
   int ldc, M, N, K;
   int trans, out_mode, split_k;
+  int a_il, c_il;
 };
 
 template <int BN, int STAGES>
@@ -98,11 +104,15 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         mbar_expect_tx(full_bar(s), S::STAGE_BYTES);
         const int k0 = (kb0 + i) * GEMM_BK;
         if (p.trans == 0) {
-          tma_load_2d(sa, &tmA, full_bar(s), k0, m_blk * GEMM_BM);
+          if (p.a_il) tma_load_3d(sa, &tmA, full_bar(s), 0, m_blk * (GEMM_BM / 32), k0 >> 3);
+          else tma_load_2d(sa, &tmA, full_bar(s), k0, m_blk * GEMM_BM);
           tma_load_2d(sb, &tmB, full_bar(s), k0, n_blk * BN);
         } else {
+          if (p.a_il) tma_load_3d(sa, &tmA, full_bar(s), 0, k0 >> 5, m_blk * (GEMM_BM / 8));
+          else {
 #pragma unroll
-          for (int a = 0; a < GEMM_BM / 64; ++a) tma_load_2d(sa + a * 8192, &tmA, full_bar(s), m_blk * GEMM_BM + 64 * a, k0);
+            for (int a = 0; a < GEMM_BM / 64; ++a) tma_load_2d(sa + a * 8192, &tmA, full_bar(s), m_blk * GEMM_BM + 64 * a, k0);
+          }
 #pragma unroll
           for (int b = 0; b < BN / 64; ++b) tma_load_2d(sb + b * 8192, &tmB, full_bar(s), n_blk * BN + 64 * b, k0);
         }
@@ -114,6 +124,9 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const uint32_t idesc = make_idesc(GEMM_BM, BN, p.trans, p.trans);
       const uint32_t lbo = p.trans ? 8192u : 0u;
       const uint32_t kstep = p.trans ? 2048u : 32u;   // bytes per UMMA_K = 16 advance
+      // interleaved A: SWIZZLE_NONE core matrices (see header comment)
+      const uint32_t a_lbo = p.trans ? 128u : 2048u, a_sbo = p.trans ? 1024u : 128u;
+      const uint32_t a_kstep = p.trans ? 256u : 4096u;
       for (int i = 0; i < nkb; ++i) {
         const int s = i % STAGES;
         const uint32_t ph = (i / STAGES) & 1;
@@ -123,7 +136,8 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const uint32_t sb = sa + S::A_BYTES;
 #pragma unroll
         for (int k = 0; k < GEMM_BK / 16; ++k) {
-          const uint64_t da = make_smem_desc(sa + k * kstep, lbo, 1024u);
+          const uint64_t da = p.a_il ? make_smem_desc(sa + k * a_kstep, a_lbo, a_sbo, 0u)
+                                     : make_smem_desc(sa + k * kstep, lbo, 1024u);
           const uint64_t db = make_smem_desc(sb + k * kstep, lbo, 1024u);
           umma_f16(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
         }
@@ -146,7 +160,18 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int n0 = n_blk * BN + c * 32;
       if (!row_ok || n0 >= p.N) continue;
       const bool full = (n0 + 32 <= p.N);
-      if (p.out_mode == 0) {
+      if (p.out_mode == 0 && p.c_il) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (n0 + 8 * j >= p.N) break;
+          uint4 v;
+          v.x = pack_half2(__uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1]));
+          v.y = pack_half2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]));
+          v.z = pack_half2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]));
+          v.w = pack_half2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
+          *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.C) + il16(row, n0 + 8 * j, p.ldc)) = v;
+        }
+      } else if (p.out_mode == 0) {
         uint16_t* dst = reinterpret_cast<uint16_t*>(p.C) + (long long)row * p.ldc + n0;
         if (full && (p.ldc % 8 == 0)) {
 #pragma unroll
@@ -302,6 +327,40 @@ static int get_tmap(const void* ptr, uint64_t d0, uint64_t d1, uint64_t ld, uint
   return AVSI_OK;
 }
 
+// 3-D tensor map over an interleaved fp16 matrix [rows x ld]: dims {256 (one 32-row x 8-col block, contiguous),
+// row blocks, column chunks}; box {256, brb, bcc}; no swizzle.  Rows / columns beyond the extents read as zero.
+static int get_tmap_il(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t brb, uint32_t bcc,
+                       CUtensorMap* out) {
+  static std::mutex mu;
+  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  TmapKey key{ptr, rows, cols, ld, brb, bcc};
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *out = it->second;
+    return AVSI_OK;
+  }
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return set_error(AVSI_ERR_CUDA, "%s: cuTensorMapEncodeTiled entry point unavailable%s", "get_tmap_il");
+  cuuint64_t dims[3] = {256, (rows + 31) / 32, (cols + 7) / 8};
+  cuuint64_t strides[2] = {(ld / 8) * 512, 512};
+  cuuint32_t box[3] = {256, brb, bcc};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[64];
+    snprintf(buf, sizeof(buf), "%d", (int)r);
+    return set_error(AVSI_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed, CUresult %s", "get_tmap_il", buf);
+  }
+  if (cache.size() > 4096) cache.clear();
+  cache[key] = m;
+  *out = m;
+  return AVSI_OK;
+}
+
 template <int BN, int STAGES>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
   using S = GemmSmem<BN, STAGES>;
@@ -320,7 +379,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
 
 extern "C" int avsi_gemm_f16(const uint16_t* A, int lda, const uint16_t* B, int ldb, void* C, int ldc,
                              const float* bias, int M, int N, int K, int trans, int out_mode, int split_k,
-                             void* stream) {
+                             int layout, void* stream) {
   using namespace avsi;
   AVSI_REQUIRE(A && B && C, "null pointer");
   AVSI_REQUIRE(M > 0 && N > 0 && K > 0, "M,N,K > 0");
@@ -330,7 +389,9 @@ extern "C" int avsi_gemm_f16(const uint16_t* A, int lda, const uint16_t* B, int 
   AVSI_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "lda/ldb multiples of 8");
   AVSI_REQUIRE(((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0), "A/B 16-byte aligned");
   AVSI_REQUIRE(ldc >= N, "ldc >= N");
-  GemmParams p{C, bias, ldc, M, N, K, trans, out_mode, split_k};
+  AVSI_REQUIRE(layout >= 0 && layout <= 3, "layout");
+  AVSI_REQUIRE(!(layout & 2) || (out_mode == 0 && ldc % 8 == 0), "interleaved output needs out_mode 0 and ldc % 8 == 0");
+  GemmParams p{C, bias, ldc, M, N, K, trans, out_mode, split_k, layout & 1, (layout >> 1) & 1};
   cudaStream_t st = (cudaStream_t)stream;
 
   static int debug_simt = -1;
@@ -338,7 +399,7 @@ extern "C" int avsi_gemm_f16(const uint16_t* A, int lda, const uint16_t* B, int 
     const char* e = getenv("AVSI_GEMM_DEBUG_SIMT");
     debug_simt = (e && e[0] == '1') ? 1 : 0;
   }
-  if (debug_simt) {
+  if (debug_simt && layout == 0) {
     GemmParams q = p;
     q.split_k = 1;
     dim3 grid((N + 15) / 16, (M + 15) / 16);
@@ -362,12 +423,14 @@ extern "C" int avsi_gemm_f16(const uint16_t* A, int lda, const uint16_t* B, int 
   CUtensorMap ta, tb;
   int rc;
   if (trans == 0) {
-    rc = get_tmap(A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, GEMM_BK, GEMM_BM, &ta);
+    rc = (layout & 1) ? get_tmap_il(A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, GEMM_BM / 32, GEMM_BK / 8, &ta)
+                      : get_tmap(A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, GEMM_BK, GEMM_BM, &ta);
     if (rc) return rc;
     rc = get_tmap(B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, GEMM_BK, (uint32_t)bn, &tb);
     if (rc) return rc;
   } else {
-    rc = get_tmap(A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, GEMM_BK, &ta);
+    rc = (layout & 1) ? get_tmap_il(A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, GEMM_BK / 32, GEMM_BM / 8, &ta)
+                      : get_tmap(A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, GEMM_BK, &ta);
     if (rc) return rc;
     rc = get_tmap(B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, GEMM_BK, &tb);
     if (rc) return rc;

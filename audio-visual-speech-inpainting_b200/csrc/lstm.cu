@@ -21,6 +21,7 @@
 // x.W_ih pre-activations of the step are prefetched before the wait.  Gate columns are laid
 // out [dir][unit][i,g,f,o]: a thread's four gates are one 8-byte load and the activated gates
 // overwrite the pre-activations in place (stash for BPTT); BPTT overwrites them with dgates.
+// The gate tensor and the cell-state stash are stored INTERLEAVED (common.cuh il16 / il32).
 //
 // BPTT: CTA j multiplies ITS 128 dgate columns with its W_hh^T slice (K-split, registers);
 // warp w's partial dh[BT, 32] belongs to CTA w and is pushed there as fp16 through the same
@@ -122,7 +123,7 @@ lstm_fwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whh, 
         const int row = b0 + mt * 16 + g + rh * 8;
         pre[mt][rh] = make_uint2(0u, 0u);
         if (row < B)
-          pre[mt][rh] = *reinterpret_cast<const uint2*>(gates + ((long long)t * B + row) * (2 * LS_G) + dir * LS_G + u * 4);
+          pre[mt][rh] = *reinterpret_cast<const uint2*>(gates + il16((long long)t * B + row, dir * LS_G + u * 4, 2 * LS_G));
       }
     float acc[MT][2][4];
 #pragma unroll
@@ -179,9 +180,9 @@ lstm_fwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whh, 
         }
         if (row < B) {
           const long long r = (long long)t * B + row;
-          *reinterpret_cast<uint2*>(gates + r * (2 * LS_G) + dir * LS_G + u * 4) =
+          *reinterpret_cast<uint2*>(gates + il16(r, dir * LS_G + u * 4, 2 * LS_G)) =
               make_uint2(pack_half2(gi, gg), pack_half2(gf, go));
-          cst[r * (2 * LS_HP) + dir * LS_HP + u] = c;
+          cst[il32(r, dir * LS_HP + u, 2 * LS_HP)] = c;
           if (uu == 0) *reinterpret_cast<uint2*>(y + r * (2 * LS_HP) + dir * LS_HP + u_base) = make_uint2(lo, hi);
         }
       }
@@ -260,10 +261,10 @@ lstm_bwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whhT,
         cprev[mt][rh] = 0.f;
         if (row < B) {
           const long long r = (long long)t * B + row;
-          gt[mt][rh] = *reinterpret_cast<const uint2*>(gates + r * (2 * LS_G) + dir * LS_G + u * 4);
+          gt[mt][rh] = *reinterpret_cast<const uint2*>(gates + il16(r, dir * LS_G + u * 4, 2 * LS_G));
           dyv[mt][rh] = __half2float(__ushort_as_half(dy[r * (2 * LS_HP) + dir * LS_HP + u]));
-          if (has_prev) cprev[mt][rh] = cst[((long long)tp * B + row) * (2 * LS_HP) + dir * LS_HP + u];
-          if (s == 0) c_cur[mt][rh] = cst[r * (2 * LS_HP) + dir * LS_HP + u];
+          if (has_prev) cprev[mt][rh] = cst[il32((long long)tp * B + row, dir * LS_HP + u, 2 * LS_HP)];
+          if (s == 0) c_cur[mt][rh] = cst[il32(r, dir * LS_HP + u, 2 * LS_HP)];
         }
       }
     float dhr[MT][2];
@@ -302,7 +303,7 @@ lstm_bwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whhT,
         const uint2 pk = make_uint2(pack_half2(d_i, d_g), pack_half2(d_f, d_o));
         *reinterpret_cast<uint2*>(dgb + rl * LS_DSTRIDE + ul * 4) = pk;
         if (b0 + rl < B) {
-          *reinterpret_cast<uint2*>(gates + ((long long)t * B + b0 + rl) * (2 * LS_G) + dir * LS_G + u * 4) = pk;
+          *reinterpret_cast<uint2*>(gates + il16((long long)t * B + b0 + rl, dir * LS_G + u * 4, 2 * LS_G)) = pk;
           db[0] += d_i;
           db[1] += d_g;
           db[2] += d_f;
@@ -432,20 +433,22 @@ static int launch_bwd(uint16_t* gates, const uint16_t* whhT, const float* cst, c
   return AVSI_OK;
 }
 
-int launch_lstm_fwd_tc(uint16_t* gates, const uint16_t* whh, const float* bias, uint16_t* y, float* cst, int T, int B,
-                       cudaStream_t st);   // lstm_tc.cu
+int launch_lstm4_fwd(uint16_t* gates, const uint16_t* whh, const float* bias, uint16_t* y, float* cst, int T, int B,
+                     cudaStream_t st);     // lstm4.cu
 
 // which forward kernel: tcgen05 (128-row tiles) once the batch no longer fits 16-row mma.sync tiles
 // in one wave of clusters.  AVSI_LSTM_FWD=mma|tc overrides (A/B measurements only).
-static bool use_tc_fwd(int B) {
+// returns 0 = mma.sync register-resident kernel (small batches: 16-row tiles, shortest step), 2 = tcgen05 4-CTA
+// kernel (lstm4.cu).  AVSI_LSTM_FWD=mma|l4 overrides (A/B measurements only).
+static int fwd_kernel_choice(int B) {
   static int mode = -1;
   if (mode < 0) {
     const char* e = getenv("AVSI_LSTM_FWD");
-    mode = (e && !strcmp(e, "mma")) ? 1 : ((e && !strcmp(e, "tc")) ? 2 : 0);
+    mode = (e && !strcmp(e, "mma")) ? 1 : ((e && !strcmp(e, "l4")) ? 3 : 0);
   }
-  if (mode == 1) return false;
-  if (mode == 2) return true;
-  return pick_bt(B) > 16;
+  if (mode == 1) return 0;
+  if (mode == 3) return 2;
+  return pick_bt(B) > 16 ? 2 : 0;
 }
 
 }  // namespace avsi
@@ -457,7 +460,8 @@ extern "C" int avsi_lstm_fwd(uint16_t* gates, const uint16_t* whh, const float* 
   AVSI_REQUIRE(T > 0 && B > 0, "T,B > 0");
   const int bt = pick_bt(B);
   cudaStream_t st = (cudaStream_t)stream;
-  if (use_tc_fwd(B)) return launch_lstm_fwd_tc(gates, whh, bias, y, cst, T, B, st);
+  const int kc = fwd_kernel_choice(B);
+  if (kc == 2) return launch_lstm4_fwd(gates, whh, bias, y, cst, T, B, st);
   if (bt == 16) return launch_fwd<16>(gates, whh, bias, y, cst, T, B, st);
   if (bt == 32) return launch_fwd<32>(gates, whh, bias, y, cst, T, B, st);
   return launch_fwd<64>(gates, whh, bias, y, cst, T, B, st);

@@ -1,0 +1,326 @@
+// Persistent bidirectional LSTM recurrence on tcgen05, cluster of 4 CTAs per (direction, 128-row
+// batch tile).  Forward kernel.
+//
+// Same contract as lstm.cu (avsi_lstm_fwd).  Decomposition: CTA j of the cluster owns hidden units
+// [64j, 64j+64) with all four gates = 256 gate columns.  Its W_hh slice [256 gate columns x 256]
+// (128 KB fp16) is RESIDENT IN SHARED MEMORY for the whole sequence, the recurrent product
+// h_{t-1} . W_hh^T is ONE tcgen05.mma chain per step (M = 128 batch rows, N = 256, K = 256,
+// accumulator in 256 TMEM columns), the cell update runs on 16 warps straight out of TMEM.
+//
+// Why 4 CTAs: the per-step all-gather of h_t through distributed shared memory is the scarce
+// resource (measured ~22 B/clk per SM for bulk DSMEM copies, profiles/README.md).  With 8 CTAs per
+// 128 rows every SM ships 56 KB per step and uses 1/8 of its tensor/MUFU throughput; with 4 CTAs
+// it ships 48 KB for twice the work, and 33 clusters (132 SMs) are co-resident instead of 15 (120).
+//
+// Per step, per CTA:
+//   control thread   wait hfull (48 KB of peers' h_{t-1} landed in the A tile) -> 16 tcgen05.mma ->
+//                    tcgen05.commit -> `done` (local) and, multicast, `afree` of all 4 CTAs ->
+//                    wait `staged` (the 16 compute warps wrote h_t) -> 3 bulk DSMEM copies of the
+//                    CTA's own 16 KB K-slice of the A tile into the peers' A tiles (complete_tx on
+//                    their hfull).
+//   compute warps    prefetch x.W_ih pre-activations -> wait `done` -> tcgen05.ld (32 columns = 8 units
+//                    x 4 gates per pass, 2 passes) -> gates / cell update (c_t in fp32 registers) ->
+//                    stores (activated gates, c_t, h_t) -> wait `afree` (every CTA's MMA of this step has
+//                    retired: the A tiles may be overwritten, and the peers have fully received the
+//                    previous push) -> write own h_t chunk into the LOCAL A tile -> arrive `staged`.
+// The A tile is K-major SWIZZLE_NONE: [k-chunk of 8 units][row][16 B], so a CTA's slice is one
+// contiguous 16 KB block and a warp's stores are 512 contiguous bytes (conflict free).
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace avsi {
+
+constexpr int L4_BT = 128;            // batch rows per cluster (UMMA M)
+constexpr int L4_CL = 4;              // CTAs per cluster
+constexpr int L4_NC = 256;            // gate columns per CTA (UMMA N) = 64 units x 4 gates
+constexpr int L4_HP = 256;            // padded hidden size (UMMA K total)
+constexpr int L4_G = 1024;            // gate columns per direction
+constexpr int L4_CWARPS = 16;         // compute warps
+constexpr int L4_THREADS = (L4_CWARPS + 1) * 32;
+constexpr uint32_t L4_W_BYTES = L4_NC * L4_HP * 2;      // 131072
+constexpr uint32_t L4_A_BYTES = L4_BT * L4_HP * 2;      // 65536
+constexpr uint32_t L4_SLICE_BYTES = L4_BT * 64 * 2;     // 16384: one CTA's K-slice (64 units) of the A tile
+constexpr uint32_t L4_W_LBO = 4096, L4_W_SBO = 128;     // W: [k-chunk][gate column][16 B]
+constexpr uint32_t L4_A_LBO = 2048, L4_A_SBO = 128;     // A: [k-chunk][row][16 B]
+
+struct Lstm4Smem {
+  unsigned char w[L4_W_BYTES];
+  unsigned char a[L4_A_BYTES];
+  float bias[L4_NC];
+  unsigned long long hfull;           // tx barrier: peers' h slices have landed
+  unsigned long long done;            // local MMA chain retired
+  unsigned long long afree[2];        // all 4 CTAs' MMA chains of the step retired (multicast commit), by step parity
+  unsigned long long staged;          // the 16 compute warps have written h_t into the local A tile
+  uint32_t tmem_slot;
+};
+
+__device__ __forceinline__ void mbar_arrive_local(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
+
+__device__ __forceinline__ void st_global_v8(void* p, uint4 a, uint4 b) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
+               "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
+
+// ACT = 0: tanh.approx.f32 (1 MUFU per activation, 2^-11 relative -- the precision h_t is stored in)
+// ACT = 1: ex2.approx + rcp.approx (2 MUFU, ~2 ulp)
+template <int ACT>
+__device__ __forceinline__ float act_sigmoid(float x) {
+  if (ACT == 0) return fmaf(0.5f, tanhf_fast(0.5f * x), 0.5f);
+  return sigmoid_fast2(x);
+}
+template <int ACT>
+__device__ __forceinline__ float act_tanh(float x) {
+  if (ACT == 0) return tanhf_fast(x);
+  return tanh_fast2(x);
+}
+
+// phase timers (cycles summed over steps) of CTA 0: control thread [0,8), compute thread 0 [8,16); debug only
+__device__ unsigned long long g_l4_timing[16];
+#define L4_TICK(i)                                         \
+  do {                                                     \
+    if (timing) {                                          \
+      const long long now_ = clock64();                    \
+      tacc[i] += (unsigned long long)(now_ - tprev);       \
+      tprev = now_;                                        \
+    }                                                      \
+  } while (0)
+
+template <int ACT>
+__global__ void __cluster_dims__(L4_CL, 1, 1) __launch_bounds__(L4_THREADS, 1)
+lstm4_fwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whh, const float* __restrict__ bias,
+                 uint16_t* __restrict__ y, float* __restrict__ cst, int T, int B) {
+  extern __shared__ unsigned char l4_smem_raw[];
+  const uint32_t raw_s = smem_u32(l4_smem_raw);
+  const uint32_t base_s = (raw_s + 127u) & ~127u;
+  Lstm4Smem& sm = *reinterpret_cast<Lstm4Smem*>(l4_smem_raw + (base_s - raw_s));
+
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int cid = blockIdx.x / L4_CL, j = blockIdx.x % L4_CL;
+  const int dir = cid & 1, b0 = (cid >> 1) * L4_BT;
+
+  const uint32_t w_s = smem_u32(&sm.w[0]);
+  const uint32_t a_s = smem_u32(&sm.a[0]);
+  const uint32_t hfull_s = smem_u32(&sm.hfull);
+  const uint32_t done_s = smem_u32(&sm.done);
+  const uint32_t afree_s = smem_u32(&sm.afree[0]);
+  const uint32_t staged_s = smem_u32(&sm.staged);
+  constexpr uint32_t PUSH_BYTES = (L4_CL - 1) * L4_SLICE_BYTES;
+
+  if (tid == 0) {
+    mbar_init(hfull_s, 1);
+    mbar_init(done_s, 1);
+    mbar_init(afree_s, L4_CL);
+    mbar_init(afree_s + 8, L4_CL);
+    mbar_init(staged_s, L4_CWARPS);
+    fence_barrier_init();
+    if (T > 1) mbar_expect_tx(hfull_s, PUSH_BYTES);          // push round 0 (h_0)
+  }
+  if (w == L4_CWARPS) tmem_alloc(smem_u32(&sm.tmem_slot), 256);
+  // W_hh slice -> smem: element (gate column n, k) at  (k/8)*4096 + n*16 + (k%8)*2
+  for (int idx = tid; idx < L4_NC * 32; idx += L4_THREADS) {
+    const int n = idx & (L4_NC - 1), c = idx >> 8;
+    const uint4 v = *reinterpret_cast<const uint4*>(whh + ((long long)(dir * L4_G + j * L4_NC + n)) * L4_HP + c * 8);
+    *reinterpret_cast<uint4*>(&sm.w[(uint32_t)c * L4_W_LBO + (uint32_t)n * 16u]) = v;
+  }
+  if (tid < L4_NC) sm.bias[tid] = bias[dir * L4_G + j * L4_NC + tid];
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&sm.tmem_slot);
+  cluster_sync_all();                               // every CTA's barriers are initialised and armed
+  const bool timing = (blockIdx.x == 0) && (tid == 0 || tid == L4_CWARPS * 32);
+  unsigned long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tprev = clock64();
+
+  if (w == L4_CWARPS) {
+    // ===================================================================== control warp
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(L4_BT, L4_NC, 0, 0);
+      const uint32_t my_slice = a_s + (uint32_t)j * L4_SLICE_BYTES;
+      uint32_t dst_a[L4_CL], dst_bar[L4_CL];
+#pragma unroll
+      for (int d = 0; d < L4_CL; ++d) {
+        dst_a[d] = map_to_cta(my_slice, (uint32_t)d);
+        dst_bar[d] = map_to_cta(hfull_s, (uint32_t)d);
+      }
+      for (int s = 0; s < T; ++s) {
+        if (s > 0) {
+          mbar_wait(hfull_s, (uint32_t)((s - 1) & 1));                 // peers' h_{s-1}
+          L4_TICK(0);
+          if (s + 1 < T) mbar_expect_tx(hfull_s, PUSH_BYTES);          // re-arm for push round s
+          tc_fence_after();
+#pragma unroll
+          for (int ks = 0; ks < 16; ++ks) {
+            const uint64_t da = make_smem_desc(a_s + (uint32_t)ks * 2u * L4_A_LBO, L4_A_LBO, L4_A_SBO, 0u);
+            const uint64_t db = make_smem_desc(w_s + (uint32_t)ks * 2u * L4_W_LBO, L4_W_LBO, L4_W_SBO, 0u);
+            umma_f16(tmem_base, da, db, idesc, ks > 0 ? 1u : 0u);
+          }
+          umma_commit(done_s);
+          umma_commit_mc(afree_s + 8u * ((s - 1) & 1), (uint16_t)0xF);
+          L4_TICK(1);
+        }
+        if (s + 1 < T) {
+          mbar_wait(staged_s, (uint32_t)(s & 1));                      // own h_s is in the local A tile
+          L4_TICK(2);
+#pragma unroll
+          for (int d = 0; d < L4_CL; ++d)
+            if (d != j) bulk_copy_to_cta(dst_a[d], my_slice, L4_SLICE_BYTES, dst_bar[d]);
+          L4_TICK(3);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================================================================== compute warps
+    const int q = w & 3, cg = w >> 2;               // TMEM lane quarter / column group of this warp
+    const int r = q * 32 + lane;                    // batch row inside the tile (= TMEM lane)
+    const int row = b0 + r;
+    const bool row_ok = row < B;
+    float c_state[2][8];
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) c_state[p][i] = 0.f;
+
+    for (int s = 0; s < T; ++s) {
+      const int t = dir ? (T - 1 - s) : s;
+      const long long grow = (long long)t * B + row;
+      // ---- prefetch the pre-activations of both passes (2 x 8 units x 4 gates x 2 B = 128 B) --------------
+      uint4 pre[2][4];
+#pragma unroll
+      for (int p = 0; p < 2; ++p)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pre[p][i] = make_uint4(0u, 0u, 0u, 0u);
+      if (row_ok) {
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+          const int col0 = dir * L4_G + (j * 64 + cg * 16 + p * 8) * 4;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            pre[p][i] = *reinterpret_cast<const uint4*>(gates + il16(grow, col0 + 8 * i, 2 * L4_G));
+        }
+      }
+      L4_TICK(0);
+      if (s > 0) {
+        mbar_wait(done_s, (uint32_t)((s - 1) & 1));
+        tc_fence_after();
+      }
+      L4_TICK(1);
+      uint4 hv[2];
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        const int ul0 = cg * 16 + p * 8;            // first local unit of this pass (a warp owns 16 contiguous units)
+        uint32_t acc[32];
+        if (s > 0) {
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ul0 * 4), acc);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc[i] = 0u;
+        }
+        uint4 gout[4];
+        float cout[8], hout[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 bq = *reinterpret_cast<const float4*>(&sm.bias[(ul0 + i) * 4]);
+          const uint4 pv = pre[p][i >> 1];
+          const float2 ig = unpack_half2((i & 1) ? pv.z : pv.x), fo = unpack_half2((i & 1) ? pv.w : pv.y);
+          const float gi = act_sigmoid<ACT>(__uint_as_float(acc[4 * i + 0]) + ig.x + bq.x);
+          const float gg = act_tanh<ACT>(__uint_as_float(acc[4 * i + 1]) + ig.y + bq.y);
+          const float gf = act_sigmoid<ACT>(__uint_as_float(acc[4 * i + 2]) + fo.x + bq.z);
+          const float go = act_sigmoid<ACT>(__uint_as_float(acc[4 * i + 3]) + fo.y + bq.w);
+          const float cc = fmaf(gf, c_state[p][i], gi * gg);
+          c_state[p][i] = cc;
+          cout[i] = cc;
+          hout[i] = go * act_tanh<ACT>(cc);
+          const uint32_t g0 = pack_half2(gi, gg), g1 = pack_half2(gf, go);
+          if (i & 1) {
+            gout[i >> 1].z = g0;
+            gout[i >> 1].w = g1;
+          } else {
+            gout[i >> 1].x = g0;
+            gout[i >> 1].y = g1;
+          }
+        }
+        hv[p] = make_uint4(pack_half2(hout[0], hout[1]), pack_half2(hout[2], hout[3]),
+                           pack_half2(hout[4], hout[5]), pack_half2(hout[6], hout[7]));
+        if (row_ok) {
+          const int ug0 = j * 64 + ul0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<uint4*>(gates + il16(grow, dir * L4_G + ug0 * 4 + 8 * i, 2 * L4_G)) = gout[i];
+          *reinterpret_cast<float4*>(cst + il32(grow, dir * L4_HP + ug0, 2 * L4_HP)) =
+              make_float4(cout[0], cout[1], cout[2], cout[3]);
+          *reinterpret_cast<float4*>(cst + il32(grow, dir * L4_HP + ug0 + 4, 2 * L4_HP)) =
+              make_float4(cout[4], cout[5], cout[6], cout[7]);
+        }
+      }
+      if (row_ok)                                    // h_t of the warp's 16 units: one 32-byte store per row
+        st_global_v8(y + grow * (2 * L4_HP) + dir * L4_HP + j * 64 + cg * 16, hv[0], hv[1]);
+      L4_TICK(2);
+      if (s + 1 < T) {
+        // every CTA's MMA chain of this step has retired: A tiles are free, previous pushes were consumed
+        if (s > 0) mbar_wait(afree_s + 8u * ((s - 1) & 1), (uint32_t)(((s - 1) >> 1) & 1));
+        L4_TICK(3);
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+          const uint32_t kc = (uint32_t)(j * 8 + cg * 2 + p);
+          *reinterpret_cast<uint4*>(&sm.a[kc * L4_A_LBO + (uint32_t)r * 16u]) = hv[p];
+        }
+        fence_proxy_async();                         // generic-proxy writes -> visible to UMMA / bulk copies
+        tc_fence_before();                           // our tcgen05.ld's precede the next MMA chain
+        __syncwarp();
+        if (lane == 0) mbar_arrive_local(staged_s);
+        L4_TICK(4);
+      }
+    }
+  }
+  if (timing) {
+    const int o = (tid == 0) ? 8 : 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g_l4_timing[o + i] = tacc[i];
+  }
+  tc_fence_before();
+  cluster_sync_all();                                // no CTA exits while peers may still address its smem
+  if (w == L4_CWARPS) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+int launch_lstm4_fwd(uint16_t* gates, const uint16_t* whh, const float* bias, uint16_t* y, float* cst, int T, int B,
+                     cudaStream_t st) {
+  static int act_mode = -1;
+  if (act_mode < 0) {
+    const char* e = getenv("AVSI_LSTM_ACT");
+    act_mode = (e && !strcmp(e, "exact")) ? 1 : 0;
+  }
+  const int smem = (int)sizeof(Lstm4Smem) + 128;
+  static bool attr_done = false;
+  if (!attr_done) {
+    AVSI_CUDA(cudaFuncSetAttribute(lstm4_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    AVSI_CUDA(cudaFuncSetAttribute(lstm4_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_done = true;
+  }
+  const int grid = 2 * ((B + L4_BT - 1) / L4_BT) * L4_CL;
+  if (act_mode == 1)
+    lstm4_fwd_kernel<1><<<grid, L4_THREADS, smem, st>>>(gates, whh, bias, y, cst, T, B);
+  else
+    lstm4_fwd_kernel<0><<<grid, L4_THREADS, smem, st>>>(gates, whh, bias, y, cst, T, B);
+  AVSI_LAUNCH_CHECK();
+  return AVSI_OK;
+}
+
+}  // namespace avsi
+
+// debug: cycles per phase summed over the steps of the last lstm4 forward launch (control thread [0,8), compute thread 0 [8,16))
+extern "C" int avsi_debug_lstm4_timing(unsigned long long* out16) {
+  return cudaMemcpyFromSymbol(out16, avsi::g_l4_timing, sizeof(unsigned long long) * 16) == cudaSuccess ? 0 : -2;
+}

@@ -115,10 +115,13 @@ int avsi_expand_mask(const int32_t* intervals, int B, int K, int T, int F, float
  *   C[M,N] (+)= A . B^T      trans == 0: A [M,K] (lda), B [N,K] (ldb), both K-contiguous
  *   C[M,N] (+)= A^T . B      trans == 1: A [K,M] (lda), B [K,N] (ldb), both MN-contiguous
  *   out_mode 0: C f16 = acc ; 1: C f32 = acc + bias[N] (bias may be NULL) ; 2: C f32 += acc (atomic)
- *   split_k > 1 only with out_mode 2.  lda/ldb multiples of 8 elements; A,B 16-byte aligned. */
+ *   split_k > 1 only with out_mode 2.  lda/ldb multiples of 8 elements; A,B 16-byte aligned.
+ *   layout bit 0: A is stored interleaved ("IL": [rows/32][lda/8][32][8] halves, rows padded to 32 with
+ *   zeros) instead of row-major; layout bit 1: the f16 output C (out_mode 0) is written interleaved with
+ *   row length ldc.  IL is the layout of the gate tensors G / dG shared with the recurrence kernels. */
 int avsi_gemm_f16(const uint16_t* A, int lda, const uint16_t* B, int ldb, void* C, int ldc,
                   const float* bias, int M, int N, int K, int trans, int out_mode, int split_k,
-                  void* stream);
+                  int layout, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Persistent bidirectional LSTM recurrence.  Replaces cudnnRNNForwardTraining /

@@ -14,13 +14,13 @@ d = torch.device('cuda:0')
 T = int(sys.argv[1]) if len(sys.argv) > 1 else 250
 BS = [int(x) for x in (sys.argv[2] if len(sys.argv) > 2 else '16,64,112,128,224,448,512,896').split(',')]
 for B in BS:
-    g0 = torch.randn(T * B, 2048, device=d).half()
+    g0 = torch.randn(-(-T * B // 32) * 32, 2048, device=d).half()
     gates = g0.clone()
     whh = (torch.randn(2048, 256, device=d) * 0.05).half()
     whhT = whh.t().contiguous()
     bias = torch.zeros(2048, device=d)
     y = torch.empty(T * B, 512, dtype=torch.float16, device=d)
-    cst = torch.empty(T * B, 512, device=d)
+    cst = torch.empty(-(-T * B // 32) * 32, 512, device=d)
     dy = torch.randn(T * B, 512, device=d).half()
     dbias = torch.zeros(2048, device=d)
     scratch = torch.empty(16, device=d)
@@ -51,14 +51,17 @@ for B in BS:
           % (B, T, res['fwd'], 1e3 * res['fwd'] / T, res['bwd'], 1e3 * res['bwd'] / T,
              B / ((res['fwd'] + res['bwd']) * 1e-3)))
 
-if os.environ.get('AVSI_TC_TIMING'):
+if os.environ.get('AVSI_L4_TIMING'):
     import ctypes
     buf = (ctypes.c_ulonglong * 16)()
     torch.cuda.synchronize()
+    gates.copy_(g0)
     fwd()
     torch.cuda.synchronize()
-    lib.avsi_debug_lstm_tc_timing.argtypes = [ctypes.c_void_p]
-    lib.avsi_debug_lstm_tc_timing(buf)
-    names = ['prefetch', 'wait_h', 'mma_issue', 'wait_mma', 'tmem_ld', 'cell', 'stage+bar', 'copy+stores']
-    for o, who in ((0, 'thread 0'), (8, 'thread 511')):
-        print(who, '  '.join('%s %.0f' % (n, buf[o + i] / T) for i, n in enumerate(names)), ' total %.0f cyc/step' % (sum(buf[o:o + 8]) / T))
+    lib.avsi_debug_lstm4_timing.argtypes = [ctypes.c_void_p]
+    lib.avsi_debug_lstm4_timing(buf)
+    for o, who, names in ((0, 'control', ['wait_hfull', 'mma_issue', 'wait_staged', 'push_issue']),
+                          (8, 'compute0', ['prefetch', 'wait_done', 'ld+cell+stores', 'wait_afree', 'stage'])):
+        print(who, '  '.join('%s %.0f' % (n, buf[o + i] / T) for i, n in enumerate(names)),
+              ' total %.0f cyc/step' % (sum(buf[o:o + 8]) / T))
+

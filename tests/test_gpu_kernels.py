@@ -90,6 +90,52 @@ def test_gemm_f16(M, N, K, trans, out_mode, split_k, ldc_pad):
         assert np.all(got[:, N:] == fill)
 
 
+GEMM_IL_CASES = [
+    # M, N, K, trans, out_mode, split_k, layout   (layout bit 0: A interleaved, bit 1: f16 output interleaved)
+    (1000, 2048, 448, 0, 0, 1, 2),        # projection: row-major X -> interleaved G
+    (300, 512, 2048, 0, 0, 1, 1),         # dX: interleaved dG (K-major) -> row-major dY
+    (777, 512, 2048, 0, 0, 1, 3),
+    (2048, 400, 1000, 1, 2, 3, 1),        # dW: interleaved dG (MN-major) x row-major X, split-K
+    (1024, 256, 2100, 1, 2, 1, 1),
+]
+
+
+@pytest.mark.parametrize('M,N,K,trans,out_mode,split_k,layout', GEMM_IL_CASES)
+def test_gemm_f16_interleaved(M, N, K, trans, out_mode, split_k, layout):
+    """Same contraction as test_gemm_f16 with the A operand / the f16 output in the interleaved layout the
+    recurrence kernels share with the GEMMs (column-offset views included)."""
+    from avsi_b200 import blstm
+    rng = np.random.default_rng(M + N * 5 + K * 11 + layout)
+    d = dev()
+    if trans == 0:
+        A = rng.standard_normal((M, K)).astype(np.float16)
+        Bm = rng.standard_normal((N, K)).astype(np.float16)
+        ref = A.astype(np.float64) @ Bm.astype(np.float64).T
+        lda = ldb = K
+    else:
+        A = rng.standard_normal((K, M)).astype(np.float16)
+        Bm = rng.standard_normal((K, N)).astype(np.float16)
+        ref = A.astype(np.float64).T @ Bm.astype(np.float64)
+        lda, ldb = M, N
+    At, Bt = torch.from_numpy(A).to(d), torch.from_numpy(Bm).to(d)
+    if layout & 1:
+        At = blstm.to_il(At)
+    if out_mode == 0:
+        rows = -(-M // 32) * 32 if layout & 2 else M
+        C = torch.zeros((rows, N), dtype=torch.float16, device=d)
+    else:
+        C = torch.full((M, N), 0.5, dtype=torch.float32, device=d)
+    blstm.gemm(At.data_ptr(), lda, Bt.data_ptr(), ldb, C.data_ptr(), N, None, M, N, K, trans, out_mode, split_k,
+               layout=layout)
+    sync()
+    if out_mode == 0 and layout & 2:
+        C = blstm.from_il(C, M)
+    got = C.cpu().numpy().astype(np.float64)
+    if out_mode == 2:
+        ref = ref + 0.5
+    assert rel_l2(got, ref) < (2e-3 if out_mode == 0 else 2e-5), rel_l2(got, ref)
+
+
 # ------------------------------------------------------------------------------------------ front end
 def _frontend_case(B, N, T=None, F=257, with_video=True, frame_ms=24, hop_ms=12, seed=0):
     from avsi_b200 import audio_processing as ap
@@ -405,20 +451,21 @@ def test_lstm_recurrence_fwd_bwd(T, B):
     P[:, :, :, H:] = 0
     R = rng.standard_normal((T, B, 2, 256)).astype(np.float16)
     R[..., H:] = 0
-    gates = torch.from_numpy(P.reshape(T * B, 2048).copy()).to(d)
+    from avsi_b200 import blstm
+    gates = blstm.to_il(torch.from_numpy(P.reshape(T * B, 2048).copy()).to(d))      # interleaved gate tensor
     whh = torch.from_numpy(Whh.reshape(2048, 256)).to(d)
     whhT = whh.t().contiguous()
     tb = torch.from_numpy(bias.reshape(2048)).to(d)
     y = torch.full((T * B, 512), 3.0, dtype=torch.float16, device=d)
-    cst = torch.full((T * B, 512), 3.0, dtype=torch.float32, device=d)
+    cst = torch.zeros((-(-T * B // 32) * 32, 512), dtype=torch.float32, device=d)                # interleaved (4-float chunks)
     _lib.check(lib.avsi_lstm_fwd(_lib.ptr(gates), _lib.ptr(whh), _lib.ptr(tb), _lib.ptr(y), _lib.ptr(cst), T, B,
                                  _lib.stream_ptr()), 'lstm_fwd')
     sync()
     Yr, Cr, Gr, dPr, dbr = _lstm_reference(P.astype(np.float64), Whh.astype(np.float64), bias.astype(np.float64),
                                            R.astype(np.float64))
     Yg = y.cpu().numpy().astype(np.float64).reshape(T, B, 2, 256)
-    Cg = cst.cpu().numpy().astype(np.float64).reshape(T, B, 2, 256)
-    Gg = gates.cpu().numpy().astype(np.float64).reshape(T, B, 2, 256, 4)
+    Cg = blstm.from_il(cst, T * B, chunk=4).cpu().numpy().astype(np.float64).reshape(T, B, 2, 256)
+    Gg = blstm.from_il(gates, T * B).cpu().numpy().astype(np.float64).reshape(T, B, 2, 256, 4)
     msg = 'fwd T=%d B=%d: relY %.2e relC %.2e relG %.2e' % (T, B, rel_l2(Yg, Yr), rel_l2(Cg, Cr), rel_l2(Gg, Gr))
     assert rel_l2(Yg, Yr) < 1e-3 and rel_l2(Cg, Cr) < 1e-3 and rel_l2(Gg, Gr) < 1e-3, msg
     assert np.all(Yg[..., H:] == 0) and np.all(Cg[..., H:] == 0)       # padded units stay exactly zero
@@ -429,7 +476,7 @@ def test_lstm_recurrence_fwd_bwd(T, B):
     _lib.check(lib.avsi_lstm_bwd(_lib.ptr(gates), _lib.ptr(whhT), _lib.ptr(cst), _lib.ptr(dy), _lib.ptr(dbias),
                                  _lib.ptr(scratch), T, B, _lib.stream_ptr()), 'lstm_bwd')
     sync()
-    dG = gates.cpu().numpy().astype(np.float64).reshape(T, B, 2, 256, 4)
+    dG = blstm.from_il(gates, T * B).cpu().numpy().astype(np.float64).reshape(T, B, 2, 256, 4)
     dbg = dbias.cpu().numpy().astype(np.float64).reshape(2, 256, 4)
     msg = 'bwd T=%d B=%d: rel dG %.2e rel db %.2e' % (T, B, rel_l2(dG, dPr), rel_l2(dbg, dbr))
     assert rel_l2(dG, dPr) < 2e-3 and rel_l2(dbg, dbr) < 2e-3, msg
