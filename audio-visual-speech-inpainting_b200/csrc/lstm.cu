@@ -433,6 +433,8 @@ static int launch_bwd(uint16_t* gates, const uint16_t* whhT, const float* cst, c
   return AVSI_OK;
 }
 
+int launch_lstm4_bwd(uint16_t* gates, const uint16_t* whhT, const float* cst, const uint16_t* dy, float* dbias, int T,
+                     int B, cudaStream_t st);   // lstm4_bwd.cu
 int launch_lstm4_fwd(uint16_t* gates, const uint16_t* whh, const float* bias, uint16_t* y, float* cst, int T, int B,
                      cudaStream_t st);     // lstm4.cu
 
@@ -480,6 +482,12 @@ extern "C" int avsi_lstm_bwd(uint16_t* gates, const uint16_t* whhT, const float*
   AVSI_REQUIRE(T > 0 && B > 0, "T,B > 0");
   const int bt = pick_bt(B);
   cudaStream_t st = (cudaStream_t)stream;
+  static int bmode = -1;               // AVSI_LSTM_BWD=mma|l4 overrides (A/B measurements only)
+  if (bmode < 0) {
+    const char* e = getenv("AVSI_LSTM_BWD");
+    bmode = (e && !strcmp(e, "mma")) ? 1 : ((e && !strcmp(e, "l4")) ? 2 : 0);
+  }
+  if (bmode == 2 || (bmode == 0 && bt > 16)) return launch_lstm4_bwd(gates, whhT, cst, dy, dbias, T, B, st);
   if (bt == 16) return launch_bwd<16>(gates, whhT, cst, dy, dbias, T, B, st);
   if (bt == 32) return launch_bwd<32>(gates, whhT, cst, dy, dbias, T, B, st);
   return launch_bwd<64>(gates, whhT, cst, dy, dbias, T, B, st);

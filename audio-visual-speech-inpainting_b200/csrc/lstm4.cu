@@ -54,18 +54,6 @@ struct Lstm4Smem {
   uint32_t tmem_slot;
 };
 
-__device__ __forceinline__ void mbar_arrive_local(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"(mask) : "memory");
-}
-
-__device__ __forceinline__ void st_global_v8(void* p, uint4 a, uint4 b) {
-  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w),
-               "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
-}
 
 // ACT = 0: tanh.approx.f32 (1 MUFU per activation, 2^-11 relative -- the precision h_t is stored in)
 // ACT = 1: ex2.approx + rcp.approx (2 MUFU, ~2 ulp)

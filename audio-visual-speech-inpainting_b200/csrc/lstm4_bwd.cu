@@ -1,0 +1,381 @@
+// BPTT of the bidirectional LSTM recurrence on tcgen05, cluster of 4 CTAs per (direction, 128-row
+// batch tile).  Same contract as the mma.sync kernel in lstm.cu (avsi_lstm_bwd): the activated gates
+// stashed by the forward kernel are overwritten in place with the pre-activation gradients dG.
+//
+// CTA j owns hidden units [64j, 64j+64) = 256 gate columns.  Per step (reverse chain order):
+//   dh      = dy_t + sum of the 4 CTAs' partial  dG_{t+1} . W_hh  restricted to the own 64 units
+//             (own partial straight from TMEM in fp32, 3 peers' partials as fp16 from shared-memory slots)
+//   dG_t    = cell backward (c_t, dc carried in fp32 registers)            -> global (interleaved) and
+//             the A operand tile in shared memory (K-major, K = own gate columns)
+//   partial = dG_t[128 x 256 own gate cols] . W_hh^T slice [256 gate cols x 256 h_in]   (tcgen05, TMEM)
+//             issued as two K-halves so that the second half of the cell math overlaps the first MMA chain
+//   reduce-scatter: the partial columns of owner c go to CTA c as fp16 with ONE 16 KB bulk DSMEM copy each.
+// The bias gradient (column sums of dG over rows and time) costs nothing extra: it is a second, tiny MMA
+// chain  dG^T(view of the same A tile, MN-major) . ones  accumulating in 32 spare TMEM columns over all steps.
+//
+// Shared memory: W_hh^T slice 128 KB (resident for the whole sequence) + 48 KB A-half / push staging (aliased:
+// the A tile is dead once its MMA chain retired) + 48 KB partial slots = 224 KB.
+// Hand-shakes (all mbarriers, no cluster barrier in the loop):
+//   slotfull   tx barrier, peers' partials of the previous step have landed
+//   delivered  3 remote arrives: every peer has RECEIVED my last push -> staging / A tile may be overwritten
+//   consumed   3 remote arrives: every peer has READ its slots       -> I may push again
+//   stagedA[h] 8 warps wrote K-half h of the A tile ; freeA / done : tcgen05.commit of the two MMA chains
+//   extracted  8 warps converted the peers' partial columns into the staging area
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace avsi {
+
+constexpr int B4_BT = 128;
+constexpr int B4_CL = 4;
+constexpr int B4_HP = 256;
+constexpr int B4_G = 1024;
+constexpr int B4_CWARPS = 8;
+constexpr int B4_THREADS = (B4_CWARPS + 1) * 32;
+constexpr uint32_t B4_W_BYTES = 256 * 256 * 2;
+constexpr uint32_t B4_SLICE = B4_BT * 64 * 2;          // 16384: partial of one owner (64 units), fp16
+constexpr uint32_t B4_AH_BYTES = 3 * B4_SLICE;          // A-half (first 32 KB) aliased with the 3 staging slices
+
+struct Lstm4BwdSmem {
+  unsigned char wt[B4_W_BYTES];      // [k-chunk position 0..31][h_in n 0..255][16 B]
+  unsigned char ah[B4_AH_BYTES];     // A-half [16 k-chunks][128 rows][16 B]  |  staging [3 owners][8 unit chunks][128 rows][16 B]
+  unsigned char slots[3 * B4_SLICE]; // [3 sources][8 unit chunks][128 rows][16 B]
+  unsigned char ones[128];           // 8 x 8 halves of 1.0 (B operand of the bias MMA, strides 0)
+  unsigned long long slotfull, delivered, consumed, stagedA[2], freeA, done, extracted, slotread;
+  uint32_t tmem_slot;
+};
+
+__device__ __forceinline__ void b4_cell(uint4 g4[4], const float cprev[8], uint4 dyv, const float dhrec[8],
+                                        float (&c_cur)[8], float (&dc_state)[8], uint4 (&pk)[4]) {
+  const uint32_t dyw[4] = {dyv.x, dyv.y, dyv.z, dyv.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const uint4 gv = g4[i >> 1];
+    const float2 ig = unpack_half2((i & 1) ? gv.z : gv.x), fo = unpack_half2((i & 1) ? gv.w : gv.y);
+    const float gi = ig.x, gg = ig.y, gf = fo.x, go = fo.y;
+    const float2 dy2 = unpack_half2(dyw[i >> 1]);
+    const float dh = ((i & 1) ? dy2.y : dy2.x) + dhrec[i];
+    const float tc = tanhf_fast(c_cur[i]);
+    const float d_o = dh * tc * go * (1.f - go);
+    const float dc = dc_state[i] + dh * go * (1.f - tc * tc);
+    const float d_i = dc * gg * gi * (1.f - gi);
+    const float d_g = dc * gi * (1.f - gg * gg);
+    const float d_f = dc * cprev[i] * gf * (1.f - gf);
+    dc_state[i] = dc * gf;
+    c_cur[i] = cprev[i];
+    const uint32_t p0 = pack_half2(d_i, d_g), p1 = pack_half2(d_f, d_o);
+    if (i & 1) {
+      pk[i >> 1].z = p0;
+      pk[i >> 1].w = p1;
+    } else {
+      pk[i >> 1].x = p0;
+      pk[i >> 1].y = p1;
+    }
+  }
+}
+
+__global__ void __cluster_dims__(B4_CL, 1, 1) __launch_bounds__(B4_THREADS, 1)
+lstm4_bwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whhT, const float* __restrict__ cst,
+                 const uint16_t* __restrict__ dy, float* __restrict__ dbias, int T, int B) {
+  extern __shared__ unsigned char b4_smem_raw[];
+  const uint32_t raw_s = smem_u32(b4_smem_raw);
+  const uint32_t base_s = (raw_s + 127u) & ~127u;
+  Lstm4BwdSmem& sm = *reinterpret_cast<Lstm4BwdSmem*>(b4_smem_raw + (base_s - raw_s));
+
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int cid = blockIdx.x / B4_CL, j = blockIdx.x % B4_CL;
+  const int dir = cid & 1, b0 = (cid >> 1) * B4_BT;
+
+  const uint32_t wt_s = smem_u32(&sm.wt[0]), ah_s = smem_u32(&sm.ah[0]), slots_s = smem_u32(&sm.slots[0]);
+  const uint32_t ones_s = smem_u32(&sm.ones[0]);
+  const uint32_t slotfull_s = smem_u32(&sm.slotfull), delivered_s = smem_u32(&sm.delivered);
+  const uint32_t consumed_s = smem_u32(&sm.consumed), stagedA_s = smem_u32(&sm.stagedA[0]);
+  const uint32_t freeA_s = smem_u32(&sm.freeA), done_s = smem_u32(&sm.done);
+  const uint32_t extracted_s = smem_u32(&sm.extracted), slotread_s = smem_u32(&sm.slotread);
+  constexpr uint32_t PUSH_BYTES = 3 * B4_SLICE;
+
+  if (tid == 0) {
+    mbar_init(slotfull_s, 1);
+    mbar_init(delivered_s, 3);
+    mbar_init(consumed_s, 3);
+    mbar_init(stagedA_s, B4_CWARPS);
+    mbar_init(stagedA_s + 8, B4_CWARPS);
+    mbar_init(freeA_s, 1);
+    mbar_init(done_s, 1);
+    mbar_init(extracted_s, B4_CWARPS);
+    mbar_init(slotread_s, B4_CWARPS);
+    fence_barrier_init();
+    if (T > 1) mbar_expect_tx(slotfull_s, PUSH_BYTES);
+  }
+  if (w == B4_CWARPS) tmem_alloc(smem_u32(&sm.tmem_slot), 512);
+  // W_hh^T slice -> smem.  K position kpos = [half h][cg][pp][i] <-> gate-column chunk 32j + 16cg + 8h + 4pp + i
+  // (the order in which the compute warps fill the two A-halves).
+  for (int idx = tid; idx < 256 * 32; idx += B4_THREADS) {
+    const int n = idx & 255, kpos = idx >> 8;
+    const int h = kpos >> 4, cgk = (kpos >> 3) & 1, pp = (kpos >> 2) & 1, i = kpos & 3;
+    const int gc = 32 * j + 16 * cgk + 8 * h + 4 * pp + i;
+    const uint4 v = *reinterpret_cast<const uint4*>(whhT + (long long)n * (2 * B4_G) + dir * B4_G + gc * 8);
+    *reinterpret_cast<uint4*>(&sm.wt[(uint32_t)kpos * 4096u + (uint32_t)n * 16u]) = v;
+  }
+  if (tid < 8) *reinterpret_cast<uint4*>(&sm.ones[tid * 16]) = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&sm.tmem_slot);
+  cluster_sync_all();
+
+  if (w == B4_CWARPS) {
+    // ===================================================================== control warp
+    if (lane == 0) {
+      const uint32_t idesc_main = make_idesc(B4_BT, 256, 0, 0);
+      const uint32_t idesc_bias = make_idesc(128, 16, 1, 0);          // A = MN-major view of the A-half (dG^T)
+      uint32_t peer_slot[3], peer_full[3], peer_delivered[3], peer_consumed[3];
+#pragma unroll
+      for (int cp = 0; cp < 3; ++cp) {
+        const int c = cp + (cp >= j ? 1 : 0);                          // owner CTA of staging slice cp
+        const int src = (j < c) ? j : j - 1;                           // my slot index at CTA c
+        peer_slot[cp] = map_to_cta(slots_s + (uint32_t)src * B4_SLICE, (uint32_t)c);
+        peer_full[cp] = map_to_cta(slotfull_s, (uint32_t)c);
+        peer_delivered[cp] = map_to_cta(delivered_s, (uint32_t)c);
+        peer_consumed[cp] = map_to_cta(consumed_s, (uint32_t)c);
+      }
+      for (int s = 0; s < T; ++s) {
+        if (s > 0) {
+          mbar_wait(slotfull_s, (uint32_t)((s - 1) & 1));              // peers' partials of step s-1 are here
+          if (s + 1 < T) mbar_expect_tx(slotfull_s, PUSH_BYTES);
+#pragma unroll
+          for (int cp = 0; cp < 3; ++cp) mbar_arrive_remote(peer_delivered[cp]);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          mbar_wait(stagedA_s + 8u * h, (uint32_t)(s & 1));
+          tc_fence_after();
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            umma_f16(tmem_base, make_smem_desc(ah_s + (uint32_t)ks * 4096u, 2048u, 128u, 0u),
+                     make_smem_desc(wt_s + (uint32_t)(16 * h + 2 * ks) * 4096u, 4096u, 128u, 0u), idesc_main,
+                     (h > 0 || ks > 0) ? 1u : 0u);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            umma_f16(tmem_base + 256u + 16u * h, make_smem_desc(ah_s + (uint32_t)ks * 256u, 128u, 2048u, 0u),
+                     make_smem_desc(ones_s, 0u, 0u, 0u), idesc_bias, (s > 0 || ks > 0) ? 1u : 0u);
+          umma_commit(h == 0 ? freeA_s : done_s);
+        }
+        if (s > 0) {
+          mbar_wait(slotread_s, (uint32_t)((s - 1) & 1));              // my warps have read their slots
+#pragma unroll
+          for (int cp = 0; cp < 3; ++cp) mbar_arrive_remote(peer_consumed[cp]);
+        }
+        if (s + 1 < T) {
+          mbar_wait(extracted_s, (uint32_t)(s & 1));
+          if (s > 0) mbar_wait(consumed_s, (uint32_t)((s - 1) & 1));   // peers' slots are free again
+#pragma unroll
+          for (int cp = 0; cp < 3; ++cp)
+            bulk_copy_to_cta(peer_slot[cp], ah_s + (uint32_t)cp * B4_SLICE, B4_SLICE, peer_full[cp]);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================================================================== compute warps
+    const int q = w & 3, cg = w >> 2;               // TMEM lane quarter / unit group (32 contiguous units)
+    const int r = q * 32 + lane;
+    const int row = b0 + r;
+    const bool row_ok = row < B;
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    float c_cur[4][8], dc_state[4][8];
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) c_cur[p][i] = dc_state[p][i] = 0.f;
+
+    for (int s = 0; s < T; ++s) {
+      const int t = dir ? s : (T - 1 - s);          // reverse of the forward chain order
+      const int tp = dir ? (t + 1) : (t - 1);       // chain predecessor
+      const bool has_prev = (s + 1 < T);
+      const long long grow = (long long)t * B + row, gprev = (long long)tp * B + row;
+      if (s == 0 && row_ok) {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const int ug0 = 64 * j + 32 * cg + 8 * p;
+          const float4 a = *reinterpret_cast<const float4*>(cst + il32(grow, dir * B4_HP + ug0, 2 * B4_HP));
+          const float4 b = *reinterpret_cast<const float4*>(cst + il32(grow, dir * B4_HP + ug0 + 4, 2 * B4_HP));
+          c_cur[p][0] = a.x; c_cur[p][1] = a.y; c_cur[p][2] = a.z; c_cur[p][3] = a.w;
+          c_cur[p][4] = b.x; c_cur[p][5] = b.y; c_cur[p][6] = b.z; c_cur[p][7] = b.w;
+        }
+      }
+      // inputs of pass 0 are requested before waiting for the peers' partials
+      uint4 g4[4], dyv;
+      float cprev[8];
+      auto load_pass = [&](int p, uint4 (&G4)[4], float (&CP)[8], uint4& DY) {
+        const int ug0 = 64 * j + 32 * cg + 8 * p;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) G4[i] = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) CP[i] = 0.f;
+        DY = make_uint4(0u, 0u, 0u, 0u);
+        if (row_ok) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            G4[i] = *reinterpret_cast<const uint4*>(gates + il16(grow, dir * B4_G + ug0 * 4 + 8 * i, 2 * B4_G));
+          DY = *reinterpret_cast<const uint4*>(dy + grow * (2 * B4_HP) + dir * B4_HP + ug0);
+          if (has_prev) {
+            const float4 a = *reinterpret_cast<const float4*>(cst + il32(gprev, dir * B4_HP + ug0, 2 * B4_HP));
+            const float4 b = *reinterpret_cast<const float4*>(cst + il32(gprev, dir * B4_HP + ug0 + 4, 2 * B4_HP));
+            CP[0] = a.x; CP[1] = a.y; CP[2] = a.z; CP[3] = a.w;
+            CP[4] = b.x; CP[5] = b.y; CP[6] = b.z; CP[7] = b.w;
+          }
+        }
+      };
+      load_pass(0, g4, cprev, dyv);
+      // own partial of the units of passes 2 and 3: read now, the first MMA chain of this step (issued once every
+      // warp has finished pass 1) overwrites the accumulator
+      uint32_t own23[16];
+      if (s > 0) {
+        mbar_wait(slotfull_s, (uint32_t)((s - 1) & 1));
+        tc_fence_after();
+        uint32_t o0[8], o1[8];
+        tmem_ld8(trow + (uint32_t)(64 * j + 32 * cg + 16), o0);
+        tmem_ld8(trow + (uint32_t)(64 * j + 32 * cg + 24), o1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          own23[i] = o0[i];
+          own23[8 + i] = o1[i];
+        }
+      }
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const int h = p >> 1, pp = p & 1;
+        const int ul0 = 32 * cg + 8 * p;            // first local unit of the pass
+        // next pass' inputs
+        uint4 g4n[4], dyn;
+        float cpn[8];
+        if (p < 3) load_pass(p + 1, g4n, cpn, dyn);
+        // recurrent gradient of these 8 units: own partial (TMEM, fp32) + 3 peers (slots, fp16)
+        float dhrec[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dhrec[i] = 0.f;
+        if (s > 0) {
+          if (p < 2) {
+            uint32_t own[8];
+            tmem_ld8(trow + (uint32_t)(64 * j + ul0), own);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dhrec[i] = __uint_as_float(own[i]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dhrec[i] = __uint_as_float(own23[(p - 2) * 8 + i]);
+          }
+#pragma unroll
+          for (int src = 0; src < 3; ++src) {
+            const uint4 v = *reinterpret_cast<const uint4*>(&sm.slots[(uint32_t)src * B4_SLICE + (uint32_t)(ul0 >> 3) * 2048u +
+                                                                      (uint32_t)r * 16u]);
+            const float2 a = unpack_half2(v.x), b = unpack_half2(v.y), c = unpack_half2(v.z), d = unpack_half2(v.w);
+            dhrec[0] += a.x; dhrec[1] += a.y; dhrec[2] += b.x; dhrec[3] += b.y;
+            dhrec[4] += c.x; dhrec[5] += c.y; dhrec[6] += d.x; dhrec[7] += d.y;
+          }
+          if (p == 3) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_local(slotread_s);
+          }
+        }
+        uint4 pk[4];
+        b4_cell(g4, cprev, dyv, dhrec, c_cur[p], dc_state[p], pk);
+        if (row_ok) {
+          const int ug0 = 64 * j + ul0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<uint4*>(gates + il16(grow, dir * B4_G + ug0 * 4 + 8 * i, 2 * B4_G)) = pk[i];
+        }
+        // A-half: the previous chain that read it must have retired, and (first write of the step) the peers
+        // must have received the staging slices that alias it
+        if (pp == 0) {
+          if (h == 0) {
+            if (s > 0) mbar_wait(delivered_s, (uint32_t)((s - 1) & 1));
+          } else {
+            mbar_wait(freeA_s, (uint32_t)(s & 1));
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          *reinterpret_cast<uint4*>(&sm.ah[(uint32_t)(cg * 8 + pp * 4 + i) * 2048u + (uint32_t)r * 16u]) = pk[i];
+        if (pp == 1) {
+          fence_proxy_async();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_local(stagedA_s + 8u * h);
+        }
+        if (p < 3) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) g4[i] = g4n[i];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) cprev[i] = cpn[i];
+          dyv = dyn;
+        }
+      }
+      // ---- the partial of this step: other owners' columns -> fp16 staging -> (control thread) DSMEM push ----
+      mbar_wait(done_s, (uint32_t)(s & 1));
+      tc_fence_after();
+      if (has_prev) {
+#pragma unroll
+        for (int cp = 0; cp < 3; ++cp) {
+          const int c = cp + (cp >= j ? 1 : 0);
+          uint32_t acc[32];
+          tmem_ld32(trow + (uint32_t)(64 * c + 32 * cg), acc);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            uint4 v;
+            v.x = pack_half2(__uint_as_float(acc[8 * k + 0]), __uint_as_float(acc[8 * k + 1]));
+            v.y = pack_half2(__uint_as_float(acc[8 * k + 2]), __uint_as_float(acc[8 * k + 3]));
+            v.z = pack_half2(__uint_as_float(acc[8 * k + 4]), __uint_as_float(acc[8 * k + 5]));
+            v.w = pack_half2(__uint_as_float(acc[8 * k + 6]), __uint_as_float(acc[8 * k + 7]));
+            *reinterpret_cast<uint4*>(&sm.ah[(uint32_t)cp * B4_SLICE + (uint32_t)(4 * cg + k) * 2048u + (uint32_t)r * 16u]) = v;
+          }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_local(extracted_s);
+      }
+    }
+    // ---- bias gradient: TMEM lane m of half h = sum over rows and steps of local gate column m ----------------------
+    if (cg == 0) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t v[8];
+        tmem_ld8(trow + 256u + 16u * h, v);
+        tmem_ld_wait();
+        const int m = q * 32 + lane, kc = m >> 3, e = m & 7;
+        const int cgk = kc >> 3, pp = (kc >> 2) & 1, i = kc & 3;
+        const int col = (64 * j + 32 * cgk + 16 * h + 8 * pp) * 4 + 8 * i + e;
+        atomicAdd(dbias + dir * B4_G + col, __uint_as_float(v[0]));
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (w == B4_CWARPS) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int launch_lstm4_bwd(uint16_t* gates, const uint16_t* whhT, const float* cst, const uint16_t* dy, float* dbias, int T,
+                     int B, cudaStream_t st) {
+  const int smem = (int)sizeof(Lstm4BwdSmem) + 128;
+  static bool attr_done = false;
+  if (!attr_done) {
+    AVSI_CUDA(cudaFuncSetAttribute(lstm4_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_done = true;
+  }
+  const int grid = 2 * ((B + B4_BT - 1) / B4_BT) * B4_CL;
+  lstm4_bwd_kernel<<<grid, B4_THREADS, smem, st>>>(gates, whhT, cst, dy, dbias, T, B);
+  AVSI_LAUNCH_CHECK();
+  return AVSI_OK;
+}
+
+}  // namespace avsi
