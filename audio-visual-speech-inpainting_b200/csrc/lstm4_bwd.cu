@@ -13,14 +13,17 @@
 // The bias gradient (column sums of dG over rows and time) costs nothing extra: it is a second, tiny MMA
 // chain  dG^T(view of the same A tile, MN-major) . ones  accumulating in 32 spare TMEM columns over all steps.
 //
+// Per-row state that must survive a step (c_t and the running dc of the 64 own units) is parked in 128 spare
+// TMEM columns (tcgen05.st / tcgen05.ld), which keeps 16 compute warps under 96 registers.
+//
 // Shared memory: W_hh^T slice 128 KB (resident for the whole sequence) + 48 KB A-half / push staging (aliased:
 // the A tile is dead once its MMA chain retired) + 48 KB partial slots = 224 KB.
 // Hand-shakes (all mbarriers, no cluster barrier in the loop):
 //   slotfull   tx barrier, peers' partials of the previous step have landed
 //   delivered  3 remote arrives: every peer has RECEIVED my last push -> staging / A tile may be overwritten
 //   consumed   3 remote arrives: every peer has READ its slots       -> I may push again
-//   stagedA[h] 8 warps wrote K-half h of the A tile ; freeA / done : tcgen05.commit of the two MMA chains
-//   extracted  8 warps converted the peers' partial columns into the staging area
+//   stagedA[h] 16 warps wrote K-half h of the A tile ; freeA / done : tcgen05.commit of the two MMA chains
+//   extracted  16 warps converted the peers' partial columns into the staging area
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 
@@ -30,11 +33,13 @@ constexpr int B4_BT = 128;
 constexpr int B4_CL = 4;
 constexpr int B4_HP = 256;
 constexpr int B4_G = 1024;
-constexpr int B4_CWARPS = 8;
+constexpr int B4_CWARPS = 16;
 constexpr int B4_THREADS = (B4_CWARPS + 1) * 32;
 constexpr uint32_t B4_W_BYTES = 256 * 256 * 2;
 constexpr uint32_t B4_SLICE = B4_BT * 64 * 2;          // 16384: partial of one owner (64 units), fp16
 constexpr uint32_t B4_AH_BYTES = 3 * B4_SLICE;          // A-half (first 32 KB) aliased with the 3 staging slices
+// TMEM columns: [0,256) partial dh accumulator, [256,288) bias-gradient accumulators, [288,352) c_t, [352,416) dc
+constexpr uint32_t B4_TM_BIAS = 256, B4_TM_C = 288, B4_TM_DC = 352;
 
 struct Lstm4BwdSmem {
   unsigned char wt[B4_W_BYTES];      // [k-chunk position 0..31][h_in n 0..255][16 B]
@@ -45,34 +50,16 @@ struct Lstm4BwdSmem {
   uint32_t tmem_slot;
 };
 
-__device__ __forceinline__ void b4_cell(uint4 g4[4], const float cprev[8], uint4 dyv, const float dhrec[8],
-                                        float (&c_cur)[8], float (&dc_state)[8], uint4 (&pk)[4]) {
-  const uint32_t dyw[4] = {dyv.x, dyv.y, dyv.z, dyv.w};
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const uint4 gv = g4[i >> 1];
-    const float2 ig = unpack_half2((i & 1) ? gv.z : gv.x), fo = unpack_half2((i & 1) ? gv.w : gv.y);
-    const float gi = ig.x, gg = ig.y, gf = fo.x, go = fo.y;
-    const float2 dy2 = unpack_half2(dyw[i >> 1]);
-    const float dh = ((i & 1) ? dy2.y : dy2.x) + dhrec[i];
-    const float tc = tanhf_fast(c_cur[i]);
-    const float d_o = dh * tc * go * (1.f - go);
-    const float dc = dc_state[i] + dh * go * (1.f - tc * tc);
-    const float d_i = dc * gg * gi * (1.f - gi);
-    const float d_g = dc * gi * (1.f - gg * gg);
-    const float d_f = dc * cprev[i] * gf * (1.f - gf);
-    dc_state[i] = dc * gf;
-    c_cur[i] = cprev[i];
-    const uint32_t p0 = pack_half2(d_i, d_g), p1 = pack_half2(d_f, d_o);
-    if (i & 1) {
-      pk[i >> 1].z = p0;
-      pk[i >> 1].w = p1;
-    } else {
-      pk[i >> 1].x = p0;
-      pk[i >> 1].y = p1;
-    }
-  }
-}
+// phase timers (cycles summed over steps) of CTA 0: control thread [0,12), compute thread 0 [12,24); debug only
+__device__ unsigned long long g_b4_timing[24];
+#define B4_TICK(i)                                         \
+  do {                                                     \
+    if (timing) {                                          \
+      const long long now_ = clock64();                    \
+      tacc[i] += (unsigned long long)(now_ - tprev);       \
+      tprev = now_;                                        \
+    }                                                      \
+  } while (0)
 
 __global__ void __cluster_dims__(B4_CL, 1, 1) __launch_bounds__(B4_THREADS, 1)
 lstm4_bwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whhT, const float* __restrict__ cst,
@@ -108,12 +95,12 @@ lstm4_bwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whhT
     if (T > 1) mbar_expect_tx(slotfull_s, PUSH_BYTES);
   }
   if (w == B4_CWARPS) tmem_alloc(smem_u32(&sm.tmem_slot), 512);
-  // W_hh^T slice -> smem.  K position kpos = [half h][cg][pp][i] <-> gate-column chunk 32j + 16cg + 8h + 4pp + i
+  // W_hh^T slice -> smem.  K position kpos = [half h][cg][i] <-> gate-column chunk 32j + 8cg + 4h + i
   // (the order in which the compute warps fill the two A-halves).
   for (int idx = tid; idx < 256 * 32; idx += B4_THREADS) {
     const int n = idx & 255, kpos = idx >> 8;
-    const int h = kpos >> 4, cgk = (kpos >> 3) & 1, pp = (kpos >> 2) & 1, i = kpos & 3;
-    const int gc = 32 * j + 16 * cgk + 8 * h + 4 * pp + i;
+    const int h = kpos >> 4, cgk = (kpos >> 2) & 3, i = kpos & 3;
+    const int gc = 32 * j + 8 * cgk + 4 * h + i;
     const uint4 v = *reinterpret_cast<const uint4*>(whhT + (long long)n * (2 * B4_G) + dir * B4_G + gc * 8);
     *reinterpret_cast<uint4*>(&sm.wt[(uint32_t)kpos * 4096u + (uint32_t)n * 16u]) = v;
   }
@@ -124,6 +111,9 @@ lstm4_bwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whhT
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&sm.tmem_slot);
   cluster_sync_all();
+  const bool timing = (blockIdx.x == 0) && (tid == 0 || tid == B4_CWARPS * 32);
+  unsigned long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long tprev = clock64();
 
   if (w == B4_CWARPS) {
     // ===================================================================== control warp
@@ -145,11 +135,13 @@ lstm4_bwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whhT
           mbar_wait(slotfull_s, (uint32_t)((s - 1) & 1));              // peers' partials of step s-1 are here
           if (s + 1 < T) mbar_expect_tx(slotfull_s, PUSH_BYTES);
 #pragma unroll
-          for (int cp = 0; cp < 3; ++cp) mbar_arrive_remote(peer_delivered[cp]);
+          for (int cp = 0; cp < 3; ++cp) mbar_arrive_remote_relaxed(peer_delivered[cp]);
         }
+        B4_TICK(0);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           mbar_wait(stagedA_s + 8u * h, (uint32_t)(s & 1));
+          B4_TICK(1 + 2 * h);
           tc_fence_after();
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)
@@ -158,58 +150,51 @@ lstm4_bwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whhT
                      (h > 0 || ks > 0) ? 1u : 0u);
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)
-            umma_f16(tmem_base + 256u + 16u * h, make_smem_desc(ah_s + (uint32_t)ks * 256u, 128u, 2048u, 0u),
+            umma_f16(tmem_base + B4_TM_BIAS + 16u * h, make_smem_desc(ah_s + (uint32_t)ks * 256u, 128u, 2048u, 0u),
                      make_smem_desc(ones_s, 0u, 0u, 0u), idesc_bias, (s > 0 || ks > 0) ? 1u : 0u);
-          umma_commit(h == 0 ? freeA_s : done_s);
-        }
-        if (s > 0) {
-          mbar_wait(slotread_s, (uint32_t)((s - 1) & 1));              // my warps have read their slots
+          umma_commit(h == 0 ? freeA_s : done_s);                      // both chains read the A-half
+          B4_TICK(2 + 2 * h);
+          if (h == 0 && s > 0) {
+            // my warps read their slots at the start of the second half: tell the senders as early as possible
+            // (every CTA's push waits for the peers' `consumed`; sending it after the own push would deadlock)
+            mbar_wait(slotread_s, (uint32_t)((s - 1) & 1));
 #pragma unroll
-          for (int cp = 0; cp < 3; ++cp) mbar_arrive_remote(peer_consumed[cp]);
+            for (int cp = 0; cp < 3; ++cp) mbar_arrive_remote_relaxed(peer_consumed[cp]);
+            B4_TICK(5);
+          }
         }
         if (s + 1 < T) {
           mbar_wait(extracted_s, (uint32_t)(s & 1));
+          B4_TICK(6);
           if (s > 0) mbar_wait(consumed_s, (uint32_t)((s - 1) & 1));   // peers' slots are free again
+          B4_TICK(7);
 #pragma unroll
           for (int cp = 0; cp < 3; ++cp)
             bulk_copy_to_cta(peer_slot[cp], ah_s + (uint32_t)cp * B4_SLICE, B4_SLICE, peer_full[cp]);
+          B4_TICK(8);
         }
       }
+    }
+    if (timing) {
+#pragma unroll
+      for (int i = 0; i < 12; ++i) g_b4_timing[i] = tacc[i];
     }
     __syncwarp();
   } else {
     // ===================================================================== compute warps
-    const int q = w & 3, cg = w >> 2;               // TMEM lane quarter / unit group (32 contiguous units)
+    const int q = w & 3, cg = w >> 2;               // TMEM lane quarter / unit group (16 contiguous units)
     const int r = q * 32 + lane;
     const int row = b0 + r;
     const bool row_ok = row < B;
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    float c_cur[4][8], dc_state[4][8];
-#pragma unroll
-    for (int p = 0; p < 4; ++p)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) c_cur[p][i] = dc_state[p][i] = 0.f;
 
     for (int s = 0; s < T; ++s) {
       const int t = dir ? s : (T - 1 - s);          // reverse of the forward chain order
       const int tp = dir ? (t + 1) : (t - 1);       // chain predecessor
       const bool has_prev = (s + 1 < T);
       const long long grow = (long long)t * B + row, gprev = (long long)tp * B + row;
-      if (s == 0 && row_ok) {
-#pragma unroll
-        for (int p = 0; p < 4; ++p) {
-          const int ug0 = 64 * j + 32 * cg + 8 * p;
-          const float4 a = *reinterpret_cast<const float4*>(cst + il32(grow, dir * B4_HP + ug0, 2 * B4_HP));
-          const float4 b = *reinterpret_cast<const float4*>(cst + il32(grow, dir * B4_HP + ug0 + 4, 2 * B4_HP));
-          c_cur[p][0] = a.x; c_cur[p][1] = a.y; c_cur[p][2] = a.z; c_cur[p][3] = a.w;
-          c_cur[p][4] = b.x; c_cur[p][5] = b.y; c_cur[p][6] = b.z; c_cur[p][7] = b.w;
-        }
-      }
-      // inputs of pass 0 are requested before waiting for the peers' partials
-      uint4 g4[4], dyv;
-      float cprev[8];
-      auto load_pass = [&](int p, uint4 (&G4)[4], float (&CP)[8], uint4& DY) {
-        const int ug0 = 64 * j + 32 * cg + 8 * p;
+      auto load_inputs = [&](int h, uint4 (&G4)[4], float (&CP)[8], uint4& DY) {
+        const int ug0 = 64 * j + 16 * cg + 8 * h;
 #pragma unroll
         for (int i = 0; i < 4; ++i) G4[i] = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
@@ -228,45 +213,58 @@ lstm4_bwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whhT
           }
         }
       };
-      load_pass(0, g4, cprev, dyv);
-      // own partial of the units of passes 2 and 3: read now, the first MMA chain of this step (issued once every
-      // warp has finished pass 1) overwrites the accumulator
-      uint32_t own23[16];
+      // the inputs of the first half do not depend on the peers: request them before waiting; the lines of the
+      // NEXT step are pulled into L2 now so that its loads are L2 hits
+      uint4 g4[4], dyv;
+      float cprev[8];
+      load_inputs(0, g4, cprev, dyv);
+      if (row_ok && has_prev) {
+        const int tn = dir ? (t + 1) : (t - 1), tnp = dir ? (t + 2) : (t - 2);
+        const long long gn = (long long)tn * B + row, gnp = (long long)tnp * B + row;
+        const int ug = 64 * j + 16 * cg;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) prefetch_l2(gates + il16(gn, dir * B4_G + ug * 4 + 8 * i, 2 * B4_G));
+        prefetch_l2(dy + gn * (2 * B4_HP) + dir * B4_HP + ug);
+        if (s + 2 < T) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) prefetch_l2(cst + il32(gnp, dir * B4_HP + ug + 4 * i, 2 * B4_HP));
+        }
+      }
+      uint32_t own1[8];                             // own partial of the second half's units (read before the MMA chain overwrites it)
       if (s > 0) {
         mbar_wait(slotfull_s, (uint32_t)((s - 1) & 1));
         tc_fence_after();
-        uint32_t o0[8], o1[8];
-        tmem_ld8(trow + (uint32_t)(64 * j + 32 * cg + 16), o0);
-        tmem_ld8(trow + (uint32_t)(64 * j + 32 * cg + 24), o1);
+        tmem_ld8(trow + (uint32_t)(64 * j + 16 * cg + 8), own1);
         tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          own23[i] = o0[i];
-          own23[8 + i] = o1[i];
-        }
       }
+      B4_TICK(0);
 #pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        const int h = p >> 1, pp = p & 1;
-        const int ul0 = 32 * cg + 8 * p;            // first local unit of the pass
-        // next pass' inputs
-        uint4 g4n[4], dyn;
-        float cpn[8];
-        if (p < 3) load_pass(p + 1, g4n, cpn, dyn);
-        // recurrent gradient of these 8 units: own partial (TMEM, fp32) + 3 peers (slots, fp16)
-        float dhrec[8];
+      for (int h = 0; h < 2; ++h) {
+        const int ul0 = 16 * cg + 8 * h;            // first local unit of the pass
+        const int ug0 = 64 * j + ul0;
+        // ---- inputs ------------------------------------------------------------------------------------------
+        float c_cur[8], dc_st[8], dhrec[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) dhrec[i] = 0.f;
+        for (int i = 0; i < 8; ++i) c_cur[i] = dc_st[i] = dhrec[i] = 0.f;
+        if (row_ok) {
+          if (s == 0) {
+            const float4 a = *reinterpret_cast<const float4*>(cst + il32(grow, dir * B4_HP + ug0, 2 * B4_HP));
+            const float4 b = *reinterpret_cast<const float4*>(cst + il32(grow, dir * B4_HP + ug0 + 4, 2 * B4_HP));
+            c_cur[0] = a.x; c_cur[1] = a.y; c_cur[2] = a.z; c_cur[3] = a.w;
+            c_cur[4] = b.x; c_cur[5] = b.y; c_cur[6] = b.z; c_cur[7] = b.w;
+          }
+        }
         if (s > 0) {
-          if (p < 2) {
-            uint32_t own[8];
-            tmem_ld8(trow + (uint32_t)(64 * j + ul0), own);
-            tmem_ld_wait();
+          uint32_t cc[8], dd[8], own[8];
+          tmem_ld8(trow + B4_TM_C + (uint32_t)ul0, cc);
+          tmem_ld8(trow + B4_TM_DC + (uint32_t)ul0, dd);
+          if (h == 0) tmem_ld8(trow + (uint32_t)ug0, own);
+          tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 8; ++i) dhrec[i] = __uint_as_float(own[i]);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) dhrec[i] = __uint_as_float(own23[(p - 2) * 8 + i]);
+          for (int i = 0; i < 8; ++i) {
+            c_cur[i] = __uint_as_float(cc[i]);
+            dc_st[i] = __uint_as_float(dd[i]);
+            dhrec[i] = __uint_as_float(h == 0 ? own[i] : own1[i]);
           }
 #pragma unroll
           for (int src = 0; src < 3; ++src) {
@@ -276,82 +274,109 @@ lstm4_bwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whhT
             dhrec[0] += a.x; dhrec[1] += a.y; dhrec[2] += b.x; dhrec[3] += b.y;
             dhrec[4] += c.x; dhrec[5] += c.y; dhrec[6] += d.x; dhrec[7] += d.y;
           }
-          if (p == 3) {
-            tc_fence_before();
+          if (h == 1) {
             __syncwarp();
             if (lane == 0) mbar_arrive_local(slotread_s);
           }
         }
+        // ---- cell backward -------------------------------------------------------------------------------------
         uint4 pk[4];
-        b4_cell(g4, cprev, dyv, dhrec, c_cur[p], dc_state[p], pk);
+        uint32_t cnew[8], dnew[8];
+        const uint32_t dyw[4] = {dyv.x, dyv.y, dyv.z, dyv.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint4 gv = g4[i >> 1];
+          const float2 ig = unpack_half2((i & 1) ? gv.z : gv.x), fo = unpack_half2((i & 1) ? gv.w : gv.y);
+          const float gi = ig.x, gg = ig.y, gf = fo.x, go = fo.y;
+          const float2 dy2 = unpack_half2(dyw[i >> 1]);
+          const float dh = ((i & 1) ? dy2.y : dy2.x) + dhrec[i];
+          const float tc = tanhf_fast(c_cur[i]);
+          const float d_o = dh * tc * go * (1.f - go);
+          const float dc = dc_st[i] + dh * go * (1.f - tc * tc);
+          const float d_i = dc * gg * gi * (1.f - gi);
+          const float d_g = dc * gi * (1.f - gg * gg);
+          const float d_f = dc * cprev[i] * gf * (1.f - gf);
+          dnew[i] = __float_as_uint(dc * gf);
+          cnew[i] = __float_as_uint(cprev[i]);
+          const uint32_t p0 = pack_half2(d_i, d_g), p1 = pack_half2(d_f, d_o);
+          if (i & 1) {
+            pk[i >> 1].z = p0;
+            pk[i >> 1].w = p1;
+          } else {
+            pk[i >> 1].x = p0;
+            pk[i >> 1].y = p1;
+          }
+        }
+        if (h == 0) load_inputs(1, g4, cprev, dyv);   // second half's inputs: in flight during the A-half hand-over
+        if (has_prev) {                               // park c_{t_prev} and dc for the next step
+          tmem_st8(trow + B4_TM_C + (uint32_t)ul0, cnew);
+          tmem_st8(trow + B4_TM_DC + (uint32_t)ul0, dnew);
+        }
         if (row_ok) {
-          const int ug0 = 64 * j + ul0;
 #pragma unroll
           for (int i = 0; i < 4; ++i)
             *reinterpret_cast<uint4*>(gates + il16(grow, dir * B4_G + ug0 * 4 + 8 * i, 2 * B4_G)) = pk[i];
         }
-        // A-half: the previous chain that read it must have retired, and (first write of the step) the peers
-        // must have received the staging slices that alias it
-        if (pp == 0) {
-          if (h == 0) {
-            if (s > 0) mbar_wait(delivered_s, (uint32_t)((s - 1) & 1));
-          } else {
-            mbar_wait(freeA_s, (uint32_t)(s & 1));
-          }
+        B4_TICK(1 + 2 * h);
+        // A-half: the chain that read it must have retired and (first half) the peers must have received the
+        // staging slices that alias it
+        if (h == 0) {
+          if (s > 0) mbar_wait(delivered_s, (uint32_t)((s - 1) & 1));
+        } else {
+          mbar_wait(freeA_s, (uint32_t)(s & 1));
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          *reinterpret_cast<uint4*>(&sm.ah[(uint32_t)(cg * 8 + pp * 4 + i) * 2048u + (uint32_t)r * 16u]) = pk[i];
-        if (pp == 1) {
-          fence_proxy_async();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_local(stagedA_s + 8u * h);
-        }
-        if (p < 3) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) g4[i] = g4n[i];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) cprev[i] = cpn[i];
-          dyv = dyn;
-        }
+          *reinterpret_cast<uint4*>(&sm.ah[(uint32_t)(cg * 4 + i) * 2048u + (uint32_t)r * 16u]) = pk[i];
+        if (has_prev) tmem_st_wait();
+        fence_proxy_async();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_local(stagedA_s + 8u * h);
+        B4_TICK(2 + 2 * h);
       }
       // ---- the partial of this step: other owners' columns -> fp16 staging -> (control thread) DSMEM push ----
       mbar_wait(done_s, (uint32_t)(s & 1));
       tc_fence_after();
+      B4_TICK(7);
       if (has_prev) {
 #pragma unroll
         for (int cp = 0; cp < 3; ++cp) {
           const int c = cp + (cp >= j ? 1 : 0);
-          uint32_t acc[32];
-          tmem_ld32(trow + (uint32_t)(64 * c + 32 * cg), acc);
+          uint32_t acc[16];
+          tmem_ld16(trow + (uint32_t)(64 * c + 16 * cg), acc);
           tmem_ld_wait();
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
+          for (int k = 0; k < 2; ++k) {
             uint4 v;
             v.x = pack_half2(__uint_as_float(acc[8 * k + 0]), __uint_as_float(acc[8 * k + 1]));
             v.y = pack_half2(__uint_as_float(acc[8 * k + 2]), __uint_as_float(acc[8 * k + 3]));
             v.z = pack_half2(__uint_as_float(acc[8 * k + 4]), __uint_as_float(acc[8 * k + 5]));
             v.w = pack_half2(__uint_as_float(acc[8 * k + 6]), __uint_as_float(acc[8 * k + 7]));
-            *reinterpret_cast<uint4*>(&sm.ah[(uint32_t)cp * B4_SLICE + (uint32_t)(4 * cg + k) * 2048u + (uint32_t)r * 16u]) = v;
+            *reinterpret_cast<uint4*>(&sm.ah[(uint32_t)cp * B4_SLICE + (uint32_t)(2 * cg + k) * 2048u + (uint32_t)r * 16u]) = v;
           }
         }
         fence_proxy_async();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_local(extracted_s);
+        B4_TICK(8);
       }
+    }
+    if (timing) {
+#pragma unroll
+      for (int i = 0; i < 12; ++i) g_b4_timing[12 + i] = tacc[i];
     }
     // ---- bias gradient: TMEM lane m of half h = sum over rows and steps of local gate column m ----------------------
     if (cg == 0) {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         uint32_t v[8];
-        tmem_ld8(trow + 256u + 16u * h, v);
+        tmem_ld8(trow + B4_TM_BIAS + 16u * h, v);
         tmem_ld_wait();
         const int m = q * 32 + lane, kc = m >> 3, e = m & 7;
-        const int cgk = kc >> 3, pp = (kc >> 2) & 1, i = kc & 3;
-        const int col = (64 * j + 32 * cgk + 16 * h + 8 * pp) * 4 + 8 * i + e;
+        const int cgk = kc >> 2, i = kc & 3;
+        const int col = (64 * j + 16 * cgk + 8 * h) * 4 + 8 * i + e;
         atomicAdd(dbias + dir * B4_G + col, __uint_as_float(v[0]));
       }
     }
@@ -379,3 +404,8 @@ int launch_lstm4_bwd(uint16_t* gates, const uint16_t* whhT, const float* cst, co
 }
 
 }  // namespace avsi
+
+// debug: cycles per phase summed over the steps of the last lstm4 backward launch (control [0,12), compute thread 0 [12,24))
+extern "C" int avsi_debug_lstm4_bwd_timing(unsigned long long* out24) {
+  return cudaMemcpyFromSymbol(out24, avsi::g_b4_timing, sizeof(unsigned long long) * 24) == cudaSuccess ? 0 : -2;
+}

@@ -65,3 +65,20 @@ if os.environ.get('AVSI_L4_TIMING'):
         print(who, '  '.join('%s %.0f' % (n, buf[o + i] / T) for i, n in enumerate(names)),
               ' total %.0f cyc/step' % (sum(buf[o:o + 8]) / T))
 
+
+if os.environ.get('AVSI_B4_TIMING'):
+    import ctypes
+    buf = (ctypes.c_ulonglong * 24)()
+    torch.cuda.synchronize()
+    gates.copy_(g0)
+    fwd()
+    bwd()
+    torch.cuda.synchronize()
+    lib.avsi_debug_lstm4_bwd_timing.argtypes = [ctypes.c_void_p]
+    lib.avsi_debug_lstm4_bwd_timing(buf)
+    for o, who, names in ((0, 'control', ['wait_slotfull', 'wait_stagedA0', 'mma0', 'wait_stagedA1', 'mma1', 'send_consumed',
+                                          'wait_extracted', 'wait_consumed', 'push']),
+                          (12, 'compute0', ['wait_slotfull+own', 'pass0', 'wait+write A0', 'pass1', 'wait+write A1', '-', '-',
+                                            'wait_done', 'extract'])):
+        print(who, '  '.join('%s %.0f' % (n, buf[o + i] / T) for i, n in enumerate(names)),
+              ' total %.0f cyc/step' % (sum(buf[o:o + 12]) / T))
