@@ -32,7 +32,7 @@ def parse_args():
     ap.add_argument('--steps', type=int, default=8)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--batch', type=int, default=int(os.environ.get('AVSI_BENCH_BATCH', 512)), help='utterances per GPU per step')
+    ap.add_argument('--batch', type=int, default=int(os.environ.get('AVSI_BENCH_BATCH', 2048)), help='utterances per GPU per step')
     ap.add_argument('--audio-len', type=int, default=48000)
     ap.add_argument('--model', default='av-blstm')
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -174,12 +174,58 @@ def main():
                    video_features=video_of(res))
         model.train_op()
 
+    # ---- end-to-end step: every step's inputs come from pinned HOST buffers (H2D inside the timed region) and
+    # every step's loss is read back to the host.  The copy of step k+1 runs on a side stream while step k
+    # computes (two device staging sets), and the loss of step k is fetched one step late (pinned, non-blocking),
+    # so that neither transfer stalls the kernels.
+    E2E_KEYS = ('wav', 'mask', 'landmarks', 'vmean', 'vstd', 'seq_len')
+    copy_stream = torch.cuda.Stream(device=dev)
+    stage = [{k: torch.empty_like(res[k]) for k in E2E_KEYS} for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    freed = [torch.cuda.Event() for _ in range(2)]
+    loss_pin = torch.zeros(2, dtype=torch.float64).pin_memory()
+    loss_evt = [torch.cuda.Event() for _ in range(2)]
+    e2e_state = {'i': 0, 'losses': []}
+
+    def e2e_prefetch(i):
+        sl = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(freed[sl])                 # the step that last used this staging set is done
+            for k in E2E_KEYS:
+                stage[sl][k].copy_(pin[k], non_blocking=True)
+            ready[sl].record(copy_stream)
+
+    def e2e_reset():
+        torch.cuda.synchronize()
+        e2e_state['i'] = 0
+        for sl in range(2):
+            freed[sl].record(torch.cuda.current_stream())
+        e2e_prefetch(0)
+
     def step_e2e():
-        d = {k: pin[k].to(dev, non_blocking=True) for k in ('wav', 'mask', 'landmarks', 'vmean', 'vstd', 'seq_len')}
+        i = e2e_state['i']
+        sl = i % 2
+        cur = torch.cuda.current_stream()
+        e2e_prefetch(i + 1)                                   # next step's H2D overlaps this step's kernels
+        cur.wait_event(ready[sl])
+        d = stage[sl]
         model.feed(sequence_lengths=d['seq_len'], target_sources=d['wav'], masks=d['mask'], video_features=video_of(d))
         model.train_op()
+        freed[sl].record(cur)
         n = model.engine.layout.n_params_padded
-        return float(model.engine.grad[n + 4].item()) if pg is not None else float(model._loss_pass(True)['sums'][4].item())
+        src = model.engine.grad[n + 4:n + 5].double() if pg is not None else model._loss_pass(True)['sums'][4:5]
+        if i > 0:                                             # read the previous step's loss (already on the host)
+            loss_evt[1 - sl].synchronize()
+            e2e_state['losses'].append(float(loss_pin[1 - sl]))
+        loss_pin[sl:sl + 1].copy_(src, non_blocking=True)
+        loss_evt[sl].record(cur)
+        e2e_state['i'] = i + 1
+
+    def e2e_drain():
+        i = e2e_state['i']
+        if i > 0:
+            loss_evt[(i - 1) % 2].synchronize()
+            e2e_state['losses'].append(float(loss_pin[(i - 1) % 2]))
 
     def timed(fn, steps, profile=False):
         torch.cuda.synchronize()
@@ -209,8 +255,19 @@ def main():
         time.sleep(0.15)
     ms, launches, prof = timed(step_resident, args.steps, profile=True)
     clocks = sampler.stop() if rank == 0 else None
-    step_e2e()
-    ms_e2e, _, _ = timed(step_e2e, args.steps)
+    e2e_reset()
+    for _ in range(2):
+        step_e2e()
+    e2e_drain()
+    e2e_reset()                                               # the first H2D of the timed run is inside the region's lead-in
+
+    def e2e_run():
+        step_e2e()
+        if e2e_state['i'] == args.steps:
+            e2e_drain()
+    ms_e2e, _, _ = timed(e2e_run, args.steps)
+    torch.cuda.current_stream().wait_stream(copy_stream)
+    torch.cuda.synchronize()
 
     if rank != 0:
         if pg is not None:
