@@ -228,6 +228,162 @@ __global__ void __launch_bounds__(FE_THREADS) frontend_kernel(avsi_frontend_args
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Training hot path (models.py:30-45 exactly: |STFT| -> log -> normalise -> mask -> concat video, fp32 loss
+// target + fp16 time-major network input), specialised so that the memory system stays busy:
+//   * the samples of the NEXT group of 16 frames are fetched with cp.async (LDGSTS, zero-filled past the end of
+//     the utterance) into a second shared-memory buffer while the current group is transformed: no registers,
+//     no scoreboard stall at the head of the iteration;
+//   * the mask row of a frame is requested before its FFT and consumed after it;
+//   * zero-padded FFT inputs (samples 384..511) are compile-time zeros, the first radix-16 pass is pruned;
+//   * sqrt / log are single MUFU ops (sqrt.approx, lg2.approx: <= 2 ulp, the 1e-5 budget is on relative L2).
+struct FrontendTrainSmem {
+  float2 tw[512];
+  float2 win2[192];                     // window as (w[2n], w[2n+1]) pairs
+  float2 nrm[260];                      // (1/std, -mean/std) per bin
+  float2 xch[FE_FRAMES][FE_XCH];
+  float2 wavb[2][FE_FRAMES][192];       // sample pairs of the frame, double buffered
+};
+
+__device__ __forceinline__ void cp_async8_zfill(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <bool HAS_VIDEO>
+__global__ void __launch_bounds__(FE_THREADS, 2) frontend_train_kernel(avsi_frontend_args p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FrontendTrainSmem& sm = *reinterpret_cast<FrontendTrainSmem*>(smem_raw);
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 512; i += FE_THREADS) sm.tw[i] = reinterpret_cast<const float2*>(p.twiddle)[i];
+  for (int i = tid; i < 192; i += FE_THREADS) sm.win2[i] = make_float2(p.window[2 * i], p.window[2 * i + 1]);
+  for (int i = tid; i < 257; i += FE_THREADS) {
+    const float is = 1.0f / p.stdev[i];
+    sm.nrm[i] = make_float2(is, -p.mean[i] * is);
+  }
+  __syncthreads();
+
+  const int fl = tid >> 4, q = tid & 15;
+  const long long total = (long long)p.B * p.T;
+  const long long stride = (long long)gridDim.x * FE_FRAMES;
+  float holes = 0.f;
+
+  auto issue = [&](long long g0, int buf) {
+    const long long g = g0 + fl;
+    const bool live = g < total;
+    const int b = live ? (int)(g / p.T) : 0;
+    const int t = live ? (int)(g - (long long)b * p.T) : 0;
+    const long long base = (long long)b * p.N + (long long)t * p.hop;
+    const int avail = live ? (int)min((long long)384, (long long)p.N - (long long)t * p.hop) : 0;
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&sm.wavb[buf][fl][0]);
+#pragma unroll
+    for (int n1 = 0; n1 < 12; ++n1) {
+      const int i0 = 32 * n1 + 2 * q;
+      const int nb = max(0, min(8, (avail - i0) * 4));
+      cp_async8_zfill(dst + (uint32_t)(16 * n1 + q) * 8u, p.wav + (nb > 0 ? base + i0 : 0), nb);
+    }
+    cp_async_commit();
+  };
+
+  long long g0 = (long long)blockIdx.x * FE_FRAMES;
+  int buf = 0;
+  if (g0 < total) issue(g0, 0);
+  for (; g0 < total; g0 += stride, buf ^= 1) {
+    if (g0 + stride < total) {
+      issue(g0 + stride, buf ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    const long long g = g0 + fl;
+    const bool live = g < total;
+    const int b = live ? (int)(g / p.T) : 0;
+    const int t = live ? (int)(g - (long long)b * p.T) : 0;
+    const long long row_bt = g, row_tb = (long long)t * p.B + b;
+    // mask row of this frame: requested now, used after the transform
+    float mv[17];
+    if (live) {
+      const float* mrow = p.mask + row_bt * 257;
+#pragma unroll
+      for (int m = 0; m < 16; ++m) mv[m] = __ldg(mrow + q + 16 * m);
+      mv[16] = (q == 0) ? __ldg(mrow + 256) : 1.f;
+    } else {
+#pragma unroll
+      for (int m = 0; m < 17; ++m) mv[m] = 1.f;
+    }
+    // ---- window; samples 384..511 are zero ----------------------------------------------------------------
+    cpx v[16];
+#pragma unroll
+    for (int n1 = 0; n1 < 12; ++n1) {
+      const float2 x = sm.wavb[buf][fl][16 * n1 + q];
+      const float2 w = sm.win2[16 * n1 + q];
+      v[n1].x = x.x * w.x;
+      v[n1].y = x.y * w.y;
+    }
+#pragma unroll
+    for (int n1 = 12; n1 < 16; ++n1) v[n1] = cpx{0.f, 0.f};
+    fft16<false>(v);
+    float2* xc = sm.xch[fl];
+#pragma unroll
+    for (int k1 = 0; k1 < 16; ++k1) {
+      const float2 w = sm.tw[(2 * q * k1) & 511];
+      const cpx r = cmul(v[k1], cpx{w.x, w.y});
+      xc[k1 * FE_XROW + q] = make_float2(r.x, r.y);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int n2 = 0; n2 < 16; ++n2) {
+      const float2 a = xc[q * FE_XROW + n2];
+      v[n2] = cpx{a.x, a.y};
+    }
+    fft16<false>(v);
+    __syncwarp();
+#pragma unroll
+    for (int k2 = 0; k2 < 16; ++k2) xc[q + 16 * k2] = make_float2(v[k2].x, v[k2].y);
+    __syncwarp();
+    // ---- real-FFT split + |.| + log + normalise + mask ------------------------------------------------------------
+    float* srow = p.spec_out + row_bt * 257;
+    uint16_t* xrow = p.xh_out + row_tb * p.ldx;
+#pragma unroll
+    for (int m = 0; m < 17; ++m) {
+      if (m == 16 && q != 0) break;
+      const int k = (m < 16) ? (q + 16 * m) : 256;
+      const float2 zk = xc[k & 255], zn = xc[(256 - k) & 255];
+      const cpx e = {0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y)};
+      const cpx d = {0.5f * (zk.x - zn.x), 0.5f * (zk.y + zn.y)};
+      const cpx o = {d.y, -d.x};
+      const float2 w = sm.tw[k];
+      const cpx X = cadd(e, cmul(o, cpx{w.x, w.y}));
+      float mag, lg;
+      asm("sqrt.approx.f32 %0, %1;" : "=f"(mag) : "f"(X.x * X.x + X.y * X.y));
+      asm("lg2.approx.f32 %0, %1;" : "=f"(lg) : "f"(mag + 1e-6f));
+      const float2 nr = sm.nrm[k];
+      const float val = fmaf(lg * 0.69314718055994531f, nr.x, nr.y);
+      if (live) {
+        srow[k] = val;
+        xrow[k] = __half_as_ushort(__float2half_rn(val * mv[m]));
+        holes += 1.f - mv[m];
+      }
+    }
+    if (live) {
+      if (HAS_VIDEO) {
+        const float* vs = p.video + row_bt * p.V;
+        for (int c = q; c < p.V; c += 16) xrow[257 + c] = __half_as_ushort(__float2half_rn(__ldg(vs + c)));
+      }
+      for (int c = 257 + (HAS_VIDEO ? p.V : 0) + q; c < p.ldx; c += 16) xrow[c] = 0;
+    }
+    __syncwarp();
+  }
+  if (p.hole_count) {
+    holes = warp_sum(holes);
+    if ((tid & 31) == 0 && holes != 0.f) atomicAdd(p.hole_count, holes);
+  }
+}
+
 }  // namespace avsi
 
 extern "C" int avsi_frontend_fwd(const avsi_frontend_args* a, void* stream) {
@@ -250,6 +406,28 @@ extern "C" int avsi_frontend_fwd(const avsi_frontend_args* a, void* stream) {
   if (!attr_done) {
     AVSI_CUDA(cudaFuncSetAttribute(frontend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_done = true;
+  }
+  // training hot path: spec + fp16 time-major network input only, log-magnitude, GRID framing
+  const bool train_path = a->frame_len == 384 && a->hop == 192 && a->F == 257 && a->power == 1.f && a->log_flag &&
+                          a->mean && a->mask && a->spec_out && a->xh_out && !a->stft_out && !a->feat_out &&
+                          !a->logmel_out && !a->xh_video_only && (a->N % 2 == 0) &&
+                          ((uintptr_t)a->wav % 8 == 0);
+  if (train_path) {
+    const int tsm = (int)sizeof(FrontendTrainSmem);
+    static bool tattr = false;
+    if (!tattr) {
+      AVSI_CUDA(cudaFuncSetAttribute(frontend_train_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tsm));
+      AVSI_CUDA(cudaFuncSetAttribute(frontend_train_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tsm));
+      tattr = true;
+    }
+    long long tg = (long long)num_sms() * 2;
+    if (tg > groups) tg = groups;
+    if (a->video)
+      frontend_train_kernel<true><<<(unsigned)tg, FE_THREADS, tsm, (cudaStream_t)stream>>>(*a);
+    else
+      frontend_train_kernel<false><<<(unsigned)tg, FE_THREADS, tsm, (cudaStream_t)stream>>>(*a);
+    AVSI_LAUNCH_CHECK();
+    return AVSI_OK;
   }
   long long grid = (long long)num_sms() * 4;
   if (grid > groups) grid = groups;
