@@ -117,7 +117,11 @@ def fused_features(sources, frame_len, hop, T=None, F=257, mean=None, std=None, 
     # algorithmic bytes of this launch: every requested input / output once
     nbytes = 4 * B * N + (4 * B * T * F if mask is not None else 0) + 4 * B * T * V
     nbytes += (8 * B * T * F if want_stft else 0) + (4 * B * T * F if want_spec else 0)
-    nbytes += (4 * B * T * (F + V) if want_feat else 0) + (2 * B * T * int(ldx) if xh_out is not None else 0)
+    # net_inputs counts as the reference's fp32 [B,T,I] tensor (4*T*I per utterance) even though the kernel
+    # writes the fp16 time-major copy: the actual traffic (2*ldx per row) is lower and is reported separately
+    I_cols = (0 if xh_video_only else F) + V
+    nbytes += (4 * B * T * (F + V) if want_feat else 0)
+    nbytes += (4 * B * T * I_cols if (xh_out is not None and not want_feat) else 0)
     nbytes += 4 * B * T * n_mel
     with _lib.span('frontend', nbytes=nbytes):
         _lib.check(lib.avsi_frontend_fwd(a, _lib.stream_ptr()), 'avsi_frontend_fwd')

@@ -160,7 +160,9 @@ class BLSTMEngine(object):
             kp = L.layer_k(l)
             gemm(_p(x), ldx, _p(self.half['wih%d' % l]), kp, _p(G), NG, None, M, NG, kp, 0, 0, tag='gemm_proj_fwd',
                  layout=C_IL)
-            with _lib.span('lstm_fwd', flops=2 * M * NG * HP):
+            # HBM-bound at large batch: per row the kernel reads G (4096 B), writes the activated gates (4096 B),
+            # c_t (2048 B) and h_t (1024 B); the recurrent product adds 2*M*2048*256 flops
+            with _lib.span('lstm_fwd', nbytes=M * (2 * NG * 2 + NY * 4 + NY * 2), flops=2 * M * NG * HP):
                 _lib.check(lib.avsi_lstm_fwd(_p(G), _p(self.half['whh%d' % l]), _p(self.view(self.theta, 'b%d' % l)),
                                              _p(ws['Y'][l]), _p(C), T, B, _lib.stream_ptr()), 'avsi_lstm_fwd')
             x, ldx = ws['Y'][l], NY
@@ -190,7 +192,8 @@ class BLSTMEngine(object):
         for l in range(L.n_layers - 1, -1, -1):
             G, C, Y = ws['G'][l], ws['C'][l], ws['Y'][l]
             kp = L.layer_k(l)
-            with _lib.span('lstm_bwd', flops=2 * M * NG * HP):
+            # per row: reads gates (4096 B), c (2048 B), dy (1024 B), writes dG (4096 B)
+            with _lib.span('lstm_bwd', nbytes=M * (2 * NG * 2 + NY * 4 + NY * 2), flops=2 * M * NG * HP):
                 _lib.check(lib.avsi_lstm_bwd(_p(G), _p(self.half['whhT%d' % l]), _p(C), _p(ws['dY'][cur]),
                                              _p(self.view(g, 'b%d' % l)), _p(ws['scratch']), T, B, st()), 'avsi_lstm_bwd')
             x, ldx = (ws['x0'], L.k0p) if l == 0 else (ws['Y'][l - 1], NY)

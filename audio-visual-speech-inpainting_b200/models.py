@@ -277,10 +277,12 @@ class StackedBLSTMModel(object):
         world = 1
         if self.process_group is not None:
             import torch.distributed as dist
+            from . import parallel
             world = dist.get_world_size(self.process_group)
-            n = self.engine.layout.n_params_padded
-            self.engine.grad[n:n + 6].copy_(out['sums'][:6].float())      # loss scalars ride along
-            dist.all_reduce(self.engine.grad, group=self.process_group)
+            # ONE all-reduce per step: flat fp32 gradient with the loss scalars riding in its tail
+            parallel.pack_loss_tail(self.engine.grad, self.engine.layout.n_params_padded, out['sums'])
+            with _lib.span('grad_allreduce', nbytes=self.engine.grad.numel() * 4):
+                parallel.all_reduce_flat(self.engine.grad, self.process_group)
         host, dev = self._grad_unscale(out, world)
         self.engine.adam_step(lr=self.starter_learning_rate, grad_unscale=host, unscale_dev=dev,
                               l2=self.regularization)

@@ -148,6 +148,9 @@ def main():
     torch.cuda.set_device(local_rank)
     pg = None
     if world > 1:
+        # NCCL prints its version banner to STDOUT at NCCL_DEBUG=VERSION/WARN; stdout carries the one JSON line
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', 'WARN'):
+            os.environ.pop('NCCL_DEBUG')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
         dist.barrier()
         pg = dist.group.WORLD
@@ -289,9 +292,12 @@ def main():
         sec = v['ms'] * 1e-3
         if v['bytes']:
             a = v['bytes'] / sec / 1e9
-            return {'kernel': name, 'bound': 'hbm', 'achieved': a, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
-                    'frac': a / pk['hbm_gbs'], 'traffic': None, 'peak_source': pk['source'],
-                    'algorithmic_bytes_per_launch': v['bytes'] / v['launches']}
+            r = {'kernel': name, 'bound': 'hbm', 'achieved': a, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
+                 'frac': a / pk['hbm_gbs'], 'traffic': None, 'peak_source': pk['source'],
+                 'algorithmic_bytes_per_launch': v['bytes'] / v['launches']}
+            if v['flops']:
+                r['tensor_tflops'] = v['flops'] / sec / 1e12
+            return r
         a = v['flops'] / sec / 1e12
         return {'kernel': name, 'bound': 'tensor', 'achieved': a, 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s',
                 'frac': a / pk['bf16_tflops_sustained'], 'traffic': None, 'peak_source': pk['source'] + ' (sustained)',
