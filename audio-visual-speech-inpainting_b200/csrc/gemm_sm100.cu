@@ -49,6 +49,64 @@ struct GemmSmem {
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;    // barriers + alignment slack
 };
 
+// one warp-lane's 32 consecutive accumulator columns [n0, n0+32) of output row `row`
+__device__ __forceinline__ void epilogue_store(const GemmParams& p, int row, int n0, bool full, const uint32_t (&r)[32]) {
+  if (p.out_mode == 0 && p.c_il) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (n0 + 8 * j >= p.N) break;
+      uint4 v;
+      v.x = pack_half2(__uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1]));
+      v.y = pack_half2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]));
+      v.z = pack_half2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]));
+      v.w = pack_half2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
+      *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.C) + il16(row, n0 + 8 * j, p.ldc)) = v;
+    }
+  } else if (p.out_mode == 0) {
+    uint16_t* dst = reinterpret_cast<uint16_t*>(p.C) + (long long)row * p.ldc + n0;
+    if (full && (p.ldc % 8 == 0)) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 v;
+        v.x = pack_half2(__uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1]));
+        v.y = pack_half2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]));
+        v.z = pack_half2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]));
+        v.w = pack_half2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
+        reinterpret_cast<uint4*>(dst)[j] = v;
+      }
+    } else {
+      for (int j = 0; j < 32; ++j)
+        if (n0 + j < p.N) dst[j] = __half_as_ushort(__float2half_rn(__uint_as_float(r[j])));
+    }
+  } else if (p.out_mode == 1) {
+    float* dst = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + n0;
+    if (full && (p.ldc % 4 == 0)) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 v;
+        v.x = __uint_as_float(r[4 * j + 0]);
+        v.y = __uint_as_float(r[4 * j + 1]);
+        v.z = __uint_as_float(r[4 * j + 2]);
+        v.w = __uint_as_float(r[4 * j + 3]);
+        if (p.bias) {
+          v.x += __ldg(p.bias + n0 + 4 * j + 0);
+          v.y += __ldg(p.bias + n0 + 4 * j + 1);
+          v.z += __ldg(p.bias + n0 + 4 * j + 2);
+          v.w += __ldg(p.bias + n0 + 4 * j + 3);
+        }
+        reinterpret_cast<float4*>(dst)[j] = v;
+      }
+    } else {
+      for (int j = 0; j < 32; ++j)
+        if (n0 + j < p.N) dst[j] = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + n0 + j) : 0.f);
+    }
+  } else {
+    float* dst = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + n0;
+    for (int j = 0; j < 32; ++j)
+      if (n0 + j < p.N) atomicAdd(dst + j, __uint_as_float(r[j]));
+  }
+}
+
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(GEMM_THREADS)
 gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
@@ -160,60 +218,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int n0 = n_blk * BN + c * 32;
       if (!row_ok || n0 >= p.N) continue;
       const bool full = (n0 + 32 <= p.N);
-      if (p.out_mode == 0 && p.c_il) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (n0 + 8 * j >= p.N) break;
-          uint4 v;
-          v.x = pack_half2(__uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1]));
-          v.y = pack_half2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]));
-          v.z = pack_half2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]));
-          v.w = pack_half2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
-          *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.C) + il16(row, n0 + 8 * j, p.ldc)) = v;
-        }
-      } else if (p.out_mode == 0) {
-        uint16_t* dst = reinterpret_cast<uint16_t*>(p.C) + (long long)row * p.ldc + n0;
-        if (full && (p.ldc % 8 == 0)) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 v;
-            v.x = pack_half2(__uint_as_float(r[8 * j + 0]), __uint_as_float(r[8 * j + 1]));
-            v.y = pack_half2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3]));
-            v.z = pack_half2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5]));
-            v.w = pack_half2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7]));
-            reinterpret_cast<uint4*>(dst)[j] = v;
-          }
-        } else {
-          for (int j = 0; j < 32; ++j)
-            if (n0 + j < p.N) dst[j] = __half_as_ushort(__float2half_rn(__uint_as_float(r[j])));
-        }
-      } else if (p.out_mode == 1) {
-        float* dst = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + n0;
-        if (full && (p.ldc % 4 == 0)) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 v;
-            v.x = __uint_as_float(r[4 * j + 0]);
-            v.y = __uint_as_float(r[4 * j + 1]);
-            v.z = __uint_as_float(r[4 * j + 2]);
-            v.w = __uint_as_float(r[4 * j + 3]);
-            if (p.bias) {
-              v.x += __ldg(p.bias + n0 + 4 * j + 0);
-              v.y += __ldg(p.bias + n0 + 4 * j + 1);
-              v.z += __ldg(p.bias + n0 + 4 * j + 2);
-              v.w += __ldg(p.bias + n0 + 4 * j + 3);
-            }
-            reinterpret_cast<float4*>(dst)[j] = v;
-          }
-        } else {
-          for (int j = 0; j < 32; ++j)
-            if (n0 + j < p.N) dst[j] = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + n0 + j) : 0.f);
-        }
-      } else {
-        float* dst = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + n0;
-        for (int j = 0; j < 32; ++j)
-          if (n0 + j < p.N) atomicAdd(dst + j, __uint_as_float(r[j]));
-      }
+      epilogue_store(p, row, n0, full, r);
     }
   }
   tc_fence_before();
@@ -221,6 +226,181 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// ---------------------------------------------------------------- persistent CTA-pair kernel
+// The one-tile-per-CTA kernel above re-reads its operands from L2 at 128 B per tensor-core clock; the L2 delivers
+// ~42 B/clk per SM (measured LTS cap, B300_MICROARCH.md), which is why it saturates near 0.8 PFLOP/s whatever the
+// pipeline depth (profiles/README.md).  This kernel halves the operand traffic per flop twice over:
+//   * cta_group::2: two CTAs of a cluster form one 256 x BN tile; each stages its own 128 rows of A and HALF of the
+//     B tile, the tensor cores of both SMs read both halves (tcgen05.mma.cta_group::2 issued by the leader);
+//   * BN = 256 columns per tile.
+// and it is persistent (one cluster per SM pair walks the tile list), with the accumulator double buffered in TMEM so
+// the epilogue of tile i (tcgen05.ld -> registers -> global, 4 warps per CTA) overlaps the main loop of tile i+1.
+//   warp 0  TMA producer (both CTAs; completion is signalled on the LEADER's `full` barrier)
+//   warp 1  leader CTA only: tcgen05.mma issue; tcgen05.commit multicast frees the smem slot in BOTH CTAs
+//   warps 2..5  epilogue of the CTA's own 128 accumulator rows
+constexpr int G2_THREADS = 192;
+
+template <int BN>
+struct Gemm2Smem {
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;          // 16 KB: this CTA's 128 rows
+  static constexpr int B_BYTES = (BN / 2) * GEMM_BK * 2;         // this CTA's half of the B tile
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 6 : 8;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 512 + 1024;
+};
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
+gemm_f16_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
+  using S = Gemm2Smem<BN>;
+  constexpr int STAGES = S::STAGES;
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + S::BAR_OFFSET;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };                       // used in the leader CTA
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };           // per CTA
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };       // per CTA
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };  // used in the leader CTA
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_dyn + (tmem_slot - smem_u32(smem_dyn)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();                 // 0 = leader
+  const int n_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
+
+  const int m_tiles = (p.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const int kb_total = (p.K + GEMM_BK - 1) / GEMM_BK;
+  const int chunk = (kb_total + p.split_k - 1) / p.split_k;
+  const int n_work = m_tiles * n_tiles * p.split_k;        // work item = (k split, m tile, n tile), n fastest
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 2);                            // one arrive.expect_tx per CTA of the pair
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 8);                          // 4 epilogue warps x 2 CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2sm(tmem_slot, 2 * BN);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int it = 0;
+      for (int w = cluster_id; w < n_work; w += n_clusters) {
+        const int n_blk = w % n_tiles, m_blk = (w / n_tiles) % m_tiles, ks = w / (n_tiles * m_tiles);
+        const int kb0 = ks * chunk, kb1 = min(kb_total, kb0 + chunk);
+        const int m0 = m_blk * 2 * GEMM_BM + (int)rank * GEMM_BM;       // this CTA's A rows
+        const int n0 = n_blk * BN + (int)rank * (BN / 2);                // this CTA's B rows
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1);
+          const uint32_t sa = smem_base + s * S::STAGE_BYTES;
+          const uint32_t sb = sa + S::A_BYTES;
+          const uint32_t lead_full = map_to_cta(full_bar(s), 0);
+          mbar_expect_tx_cluster(lead_full, S::STAGE_BYTES);
+          const int k0 = kb * GEMM_BK;
+          if (p.trans == 0) {
+            if (p.a_il) tma_load_3d_2sm(sa, &tmA, lead_full, 0, m0 / 32, k0 >> 3);
+            else tma_load_2d_2sm(sa, &tmA, lead_full, k0, m0);
+            tma_load_2d_2sm(sb, &tmB, lead_full, k0, n0);
+          } else {
+            if (p.a_il) tma_load_3d_2sm(sa, &tmA, lead_full, 0, k0 >> 5, m0 / 8);
+            else {
+#pragma unroll
+              for (int a = 0; a < GEMM_BM / 64; ++a) tma_load_2d_2sm(sa + a * 8192, &tmA, lead_full, m0 + 64 * a, k0);
+            }
+#pragma unroll
+            for (int b = 0; b < BN / 128; ++b) tma_load_2d_2sm(sb + b * 8192, &tmB, lead_full, n0 + 64 * b, k0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA)
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = make_idesc(2 * GEMM_BM, BN, p.trans, p.trans);
+      const uint32_t lbo = p.trans ? 8192u : 0u;
+      const uint32_t kstep = p.trans ? 2048u : 32u;
+      const uint32_t a_lbo = p.trans ? 128u : 2048u, a_sbo = p.trans ? 1024u : 128u;
+      const uint32_t a_kstep = p.trans ? 256u : 4096u;
+      int it = 0, tile = 0;
+      for (int w = cluster_id; w < n_work; w += n_clusters, ++tile) {
+        const int ks = w / (n_tiles * m_tiles);
+        const int kb0 = ks * chunk, kb1 = min(kb_total, kb0 + chunk);
+        const int acc = tile & 1;
+        mbar_wait(tempty_bar(acc), ((tile >> 1) & 1) ^ 1);               // both CTAs' epilogues drained this buffer
+        tc_fence_after();
+        const uint32_t td = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t sa = smem_base + s * S::STAGE_BYTES;
+          const uint32_t sb = sa + S::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            const uint64_t da = p.a_il ? make_smem_desc(sa + k * a_kstep, a_lbo, a_sbo, 0u)
+                                       : make_smem_desc(sa + k * kstep, lbo, 1024u);
+            const uint64_t db = make_smem_desc(sb + k * kstep, lbo, 1024u);
+            umma_f16_2sm(td, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_2sm(empty_bar(s), (uint16_t)3);                    // frees the slot in both CTAs
+        }
+        umma_commit_2sm(tfull_bar(acc), (uint16_t)3);                    // accumulator complete (both CTAs)
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..5, both CTAs)
+    const int quarter = warp & 3;
+    const uint32_t lead_tempty0 = map_to_cta(tempty_bar(0), 0);
+    int tile = 0;
+    for (int w = cluster_id; w < n_work; w += n_clusters, ++tile) {
+      const int n_blk = w % n_tiles, m_blk = (w / n_tiles) % m_tiles, ks = w / (n_tiles * m_tiles);
+      const int kb0 = ks * chunk, kb1 = min(kb_total, kb0 + chunk);
+      const int acc = tile & 1;
+      mbar_wait(tfull_bar(acc), (tile >> 1) & 1);
+      tc_fence_after();
+      const int row = m_blk * 2 * GEMM_BM + (int)rank * GEMM_BM + quarter * 32 + lane;
+      const bool row_ok = row < p.M && kb1 > kb0;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
+        tmem_ld_wait();
+        const int n0 = n_blk * BN + c * 32;
+        if (!row_ok || n0 >= p.N) continue;
+        epilogue_store(p, row, n0, n0 + 32 <= p.N, r);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(lead_tempty0 + 8u * acc);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 2 * BN);
   }
 }
 
@@ -375,6 +555,23 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   return AVSI_OK;
 }
 
+template <int BN>
+static int launch_gemm_2sm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+  using S = Gemm2Smem<BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    AVSI_CUDA(cudaFuncSetAttribute(gemm_f16_2sm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    attr_done = true;
+  }
+  const int m_tiles = (p.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM), n_tiles = (p.N + BN - 1) / BN;
+  const long long n_work = (long long)m_tiles * n_tiles * p.split_k;
+  long long clusters = num_sms() / 2;
+  if (clusters > n_work) clusters = n_work;
+  gemm_f16_2sm_kernel<BN><<<(unsigned)(2 * clusters), G2_THREADS, S::TOTAL, st>>>(ta, tb, p);
+  AVSI_LAUNCH_CHECK();
+  return AVSI_OK;
+}
+
 }  // namespace avsi
 
 extern "C" int avsi_gemm_f16(const uint16_t* A, int lda, const uint16_t* B, int ldb, void* C, int ldc,
@@ -415,6 +612,47 @@ extern "C" int avsi_gemm_f16(const uint16_t* A, int lda, const uint16_t* B, int 
   if (bn_env < 0) {
     const char* e = getenv("AVSI_GEMM_BN");
     bn_env = e ? atoi(e) : 0;
+  }
+  // large problems: persistent CTA-pair kernel (256 x 256 tiles, cta_group::2).  AVSI_GEMM_2SM=0 disables it.
+  static int use_2sm = -1;
+  if (use_2sm < 0) {
+    const char* e = getenv("AVSI_GEMM_2SM");
+    use_2sm = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (use_2sm && N >= 256 && ((N + 255) / 256) * 256 * 3 <= N * 4 && (long long)M * N * K >= (1LL << 29)) {
+    // split-K only as far as needed to give every SM pair a work item
+    const int m_t = (M + 255) / 256, n_t = (N + 255) / 256, kbt = (K + GEMM_BK - 1) / GEMM_BK;
+    if (out_mode == 2) {
+      // split K so that the work items fill whole waves of SM pairs (80 items on 74 pairs would take two waves)
+      const int pairs = num_sms() / 2, tiles = m_t * n_t;
+      int best = 1;
+      double best_eff = 0.0;
+      for (int sk = 1; sk <= kbt && sk * tiles <= 4 * pairs; ++sk) {
+        const int work = sk * tiles, waves = (work + pairs - 1) / pairs;
+        const double eff = (double)work / ((double)waves * pairs);
+        if (eff > best_eff + 1e-9) {
+          best_eff = eff;
+          best = sk;
+        }
+      }
+      p.split_k = best;
+    }
+    CUtensorMap ta2, tb2;
+    int rc2;
+    if (trans == 0) {
+      rc2 = (layout & 1) ? get_tmap_il(A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, GEMM_BM / 32, GEMM_BK / 8, &ta2)
+                         : get_tmap(A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, GEMM_BK, GEMM_BM, &ta2);
+      if (rc2) return rc2;
+      rc2 = get_tmap(B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, GEMM_BK, 128, &tb2);
+      if (rc2) return rc2;
+    } else {
+      rc2 = (layout & 1) ? get_tmap_il(A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, GEMM_BK / 32, GEMM_BM / 8, &ta2)
+                         : get_tmap(A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, GEMM_BK, &ta2);
+      if (rc2) return rc2;
+      rc2 = get_tmap(B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, GEMM_BK, &tb2);
+      if (rc2) return rc2;
+    }
+    return launch_gemm_2sm<256>(ta2, tb2, p, st);
   }
   int bn = 128;
   if (N > 128 && K >= 4096) bn = 256;
