@@ -4,27 +4,29 @@
 // Same contract as lstm.cu (avsi_lstm_fwd).  Decomposition: CTA j of the cluster owns hidden units
 // [64j, 64j+64) with all four gates = 256 gate columns.  Its W_hh slice [256 gate columns x 256]
 // (128 KB fp16) is RESIDENT IN SHARED MEMORY for the whole sequence, the recurrent product
-// h_{t-1} . W_hh^T is ONE tcgen05.mma chain per step (M = 128 batch rows, N = 256, K = 256,
-// accumulator in 256 TMEM columns), the cell update runs on 16 warps straight out of TMEM.
+// h_{t-1} . W_hh^T runs on tcgen05.mma (M = 128 batch rows, N = 256, K = 256, accumulator DOUBLE
+// BUFFERED in 2 x 256 TMEM columns), the cell update runs on 16 warps straight out of TMEM.
 //
 // Why 4 CTAs: the per-step all-gather of h_t through distributed shared memory is the scarce
-// resource (measured ~22 B/clk per SM for bulk DSMEM copies, profiles/README.md).  With 8 CTAs per
+// resource (measured 12..22 B/clk per SM for bulk DSMEM copies, profiles/README.md).  With 8 CTAs per
 // 128 rows every SM ships 56 KB per step and uses 1/8 of its tensor/MUFU throughput; with 4 CTAs
 // it ships 48 KB for twice the work, and 33 clusters (132 SMs) are co-resident instead of 15 (120).
 //
-// Per step, per CTA:
-//   control thread   wait hfull (48 KB of peers' h_{t-1} landed in the A tile) -> 16 tcgen05.mma ->
-//                    tcgen05.commit -> `done` (local) and, multicast, `afree` of all 4 CTAs ->
-//                    wait `staged` (the 16 compute warps wrote h_t) -> 3 bulk DSMEM copies of the
-//                    CTA's own 16 KB K-slice of the A tile into the peers' A tiles (complete_tx on
-//                    their hfull).
-//   compute warps    prefetch x.W_ih pre-activations -> wait `done` -> tcgen05.ld (32 columns = 8 units
-//                    x 4 gates per pass, 2 passes) -> gates / cell update (c_t in fp32 registers) ->
-//                    stores (activated gates, c_t, h_t) -> wait `afree` (every CTA's MMA of this step has
-//                    retired: the A tiles may be overwritten, and the peers have fully received the
-//                    previous push) -> write own h_t chunk into the LOCAL A tile -> arrive `staged`.
-// The A tile is K-major SWIZZLE_NONE: [k-chunk of 8 units][row][16 B], so a CTA's slice is one
-// contiguous 16 KB block and a warp's stores are 512 contiguous bytes (conflict free).
+// The step is software-pipelined in two halves of the hidden units (pass p = units 16cg + 8p .. +8 of each
+// warp's 16 units; K is ordered [pass][source CTA][warp] so that a CTA's half is one contiguous 8 KB
+// block of the A tile):
+//   compute warps    prefetch x.W_ih pre-activations -> wait `done` (this step's MMA chain retired) ->
+//                    pass 0: tcgen05.ld 32 columns, gates / cell update (c_t in fp32 registers), stores,
+//                    wait `afree` (every CTA's chain retired: the peers have consumed the previous push),
+//                    write the h_t chunk into the LOCAL A tile, arrive staged[0] -> pass 1 likewise.
+//   control thread   staged[0] -> 3 bulk DSMEM copies of the 8 KB half into the peers' A tiles (complete_tx
+//                    on their hfull[0]); staged[1] -> second half; hfull[0] -> first K-half of the NEXT
+//                    step's chain (8 tcgen05.mma into the other accumulator buffer, overlapping the second
+//                    half's transfer); hfull[1] -> second K-half; tcgen05.commit -> `done` (local) and,
+//                    multicast, `afree` of all 4 CTAs.
+// The A tile is K-major SWIZZLE_NONE: [k-chunk of 8 units][row][16 B]; a warp's stores are 512 contiguous
+// bytes (conflict free).  Gate pre-activations / activated gates and the c_t stash are INTERLEAVED in
+// global memory (common.cuh il16 / il32): every warp access is a run of 512 contiguous bytes.
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 
@@ -39,7 +41,7 @@ constexpr int L4_CWARPS = 16;         // compute warps
 constexpr int L4_THREADS = (L4_CWARPS + 1) * 32;
 constexpr uint32_t L4_W_BYTES = L4_NC * L4_HP * 2;      // 131072
 constexpr uint32_t L4_A_BYTES = L4_BT * L4_HP * 2;      // 65536
-constexpr uint32_t L4_SLICE_BYTES = L4_BT * 64 * 2;     // 16384: one CTA's K-slice (64 units) of the A tile
+constexpr uint32_t L4_HALF_BYTES = L4_BT * 32 * 2;      // 8192: one CTA's half (32 units) of the A tile
 constexpr uint32_t L4_W_LBO = 4096, L4_W_SBO = 128;     // W: [k-chunk][gate column][16 B]
 constexpr uint32_t L4_A_LBO = 2048, L4_A_SBO = 128;     // A: [k-chunk][row][16 B]
 
@@ -47,13 +49,12 @@ struct Lstm4Smem {
   unsigned char w[L4_W_BYTES];
   unsigned char a[L4_A_BYTES];
   float bias[L4_NC];
-  unsigned long long hfull;           // tx barrier: peers' h slices have landed
+  unsigned long long hfull[2];        // tx barriers: peers' halves of h have landed
   unsigned long long done;            // local MMA chain retired
-  unsigned long long afree[2];        // all 4 CTAs' MMA chains of the step retired (multicast commit), by step parity
-  unsigned long long staged;          // the 16 compute warps have written h_t into the local A tile
+  unsigned long long afree[2];        // all 4 CTAs' chains of the step retired (multicast commit), by step parity
+  unsigned long long staged[2];       // the 16 compute warps have written half p of h_t into the local A tile
   uint32_t tmem_slot;
 };
-
 
 // ACT = 0: tanh.approx.f32 (1 MUFU per activation, 2^-11 relative -- the precision h_t is stored in)
 // ACT = 1: ex2.approx + rcp.approx (2 MUFU, ~2 ulp)
@@ -94,27 +95,34 @@ lstm4_fwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whh,
 
   const uint32_t w_s = smem_u32(&sm.w[0]);
   const uint32_t a_s = smem_u32(&sm.a[0]);
-  const uint32_t hfull_s = smem_u32(&sm.hfull);
+  const uint32_t hfull_s = smem_u32(&sm.hfull[0]);
   const uint32_t done_s = smem_u32(&sm.done);
   const uint32_t afree_s = smem_u32(&sm.afree[0]);
-  const uint32_t staged_s = smem_u32(&sm.staged);
-  constexpr uint32_t PUSH_BYTES = (L4_CL - 1) * L4_SLICE_BYTES;
+  const uint32_t staged_s = smem_u32(&sm.staged[0]);
+  constexpr uint32_t PUSH_BYTES = (L4_CL - 1) * L4_HALF_BYTES;
 
   if (tid == 0) {
     mbar_init(hfull_s, 1);
+    mbar_init(hfull_s + 8, 1);
     mbar_init(done_s, 1);
     mbar_init(afree_s, L4_CL);
     mbar_init(afree_s + 8, L4_CL);
     mbar_init(staged_s, L4_CWARPS);
+    mbar_init(staged_s + 8, L4_CWARPS);
     fence_barrier_init();
-    if (T > 1) mbar_expect_tx(hfull_s, PUSH_BYTES);          // push round 0 (h_0)
+    if (T > 1) {                                              // push round 0 (h_0)
+      mbar_expect_tx(hfull_s, PUSH_BYTES);
+      mbar_expect_tx(hfull_s + 8, PUSH_BYTES);
+    }
   }
-  if (w == L4_CWARPS) tmem_alloc(smem_u32(&sm.tmem_slot), 256);
-  // W_hh slice -> smem: element (gate column n, k) at  (k/8)*4096 + n*16 + (k%8)*2
+  if (w == L4_CWARPS) tmem_alloc(smem_u32(&sm.tmem_slot), 512);
+  // W_hh slice -> smem.  K position kpos = [pass p][source CTA j'][warp cg] <-> unit chunk 8j' + 2cg + p;
+  // element (gate column n, kpos, e) at kpos*4096 + n*16 + e*2
   for (int idx = tid; idx < L4_NC * 32; idx += L4_THREADS) {
-    const int n = idx & (L4_NC - 1), c = idx >> 8;
+    const int n = idx & (L4_NC - 1), kpos = idx >> 8;
+    const int c = 8 * ((kpos >> 2) & 3) + 2 * (kpos & 3) + (kpos >> 4);
     const uint4 v = *reinterpret_cast<const uint4*>(whh + ((long long)(dir * L4_G + j * L4_NC + n)) * L4_HP + c * 8);
-    *reinterpret_cast<uint4*>(&sm.w[(uint32_t)c * L4_W_LBO + (uint32_t)n * 16u]) = v;
+    *reinterpret_cast<uint4*>(&sm.w[(uint32_t)kpos * L4_W_LBO + (uint32_t)n * 16u]) = v;
   }
   if (tid < L4_NC) sm.bias[tid] = bias[dir * L4_G + j * L4_NC + tid];
   fence_proxy_async();
@@ -131,38 +139,46 @@ lstm4_fwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whh,
     // ===================================================================== control warp
     if (lane == 0) {
       const uint32_t idesc = make_idesc(L4_BT, L4_NC, 0, 0);
-      const uint32_t my_slice = a_s + (uint32_t)j * L4_SLICE_BYTES;
       uint32_t dst_a[L4_CL], dst_bar[L4_CL];
 #pragma unroll
       for (int d = 0; d < L4_CL; ++d) {
-        dst_a[d] = map_to_cta(my_slice, (uint32_t)d);
+        dst_a[d] = map_to_cta(a_s, (uint32_t)d);
         dst_bar[d] = map_to_cta(hfull_s, (uint32_t)d);
       }
-      for (int s = 0; s < T; ++s) {
-        if (s > 0) {
-          mbar_wait(hfull_s, (uint32_t)((s - 1) & 1));                 // peers' h_{s-1}
-          L4_TICK(0);
-          if (s + 1 < T) mbar_expect_tx(hfull_s, PUSH_BYTES);          // re-arm for push round s
-          tc_fence_after();
+      for (int s = 0; s + 1 < T; ++s) {
+        // ---- ship h_s, one half at a time, as soon as the warps have staged it -------------------------------
 #pragma unroll
-          for (int ks = 0; ks < 16; ++ks) {
-            const uint64_t da = make_smem_desc(a_s + (uint32_t)ks * 2u * L4_A_LBO, L4_A_LBO, L4_A_SBO, 0u);
-            const uint64_t db = make_smem_desc(w_s + (uint32_t)ks * 2u * L4_W_LBO, L4_W_LBO, L4_W_SBO, 0u);
-            umma_f16(tmem_base, da, db, idesc, ks > 0 ? 1u : 0u);
-          }
-          umma_commit(done_s);
-          umma_commit_mc(afree_s + 8u * ((s - 1) & 1), (uint16_t)0xF);
-          L4_TICK(1);
-        }
-        if (s + 1 < T) {
-          mbar_wait(staged_s, (uint32_t)(s & 1));                      // own h_s is in the local A tile
-          L4_TICK(2);
+        for (int p = 0; p < 2; ++p) {
+          mbar_wait(staged_s + 8u * p, (uint32_t)(s & 1));
+          L4_TICK(p);
+          const uint32_t off = (uint32_t)(16 * p + 4 * j) * L4_A_LBO;
 #pragma unroll
           for (int d = 0; d < L4_CL; ++d)
-            if (d != j) bulk_copy_to_cta(dst_a[d], my_slice, L4_SLICE_BYTES, dst_bar[d]);
-          L4_TICK(3);
+            if (d != j) bulk_copy_to_cta(dst_a[d] + off, a_s + off, L4_HALF_BYTES, dst_bar[d] + 8u * p);
         }
+        // ---- the chain of step s+1, K-half by K-half as the peers' halves land ---------------------------------------
+        const uint32_t td = tmem_base + (uint32_t)(((s + 1) & 1) * L4_NC);
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+          mbar_wait(hfull_s + 8u * p, (uint32_t)(s & 1));
+          if (s + 2 < T) mbar_expect_tx(hfull_s + 8u * p, PUSH_BYTES);    // re-arm for round s+1
+          L4_TICK(2 + 2 * p);
+          tc_fence_after();
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint32_t kc = (uint32_t)(16 * p + 2 * ks);
+            umma_f16(td, make_smem_desc(a_s + kc * L4_A_LBO, L4_A_LBO, L4_A_SBO, 0u),
+                     make_smem_desc(w_s + kc * L4_W_LBO, L4_W_LBO, L4_W_SBO, 0u), idesc, (p > 0 || ks > 0) ? 1u : 0u);
+          }
+          L4_TICK(3 + 2 * p);
+        }
+        umma_commit(done_s);
+        umma_commit_mc(afree_s + 8u * (s & 1), (uint16_t)0xF);
       }
+    }
+    if (timing) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) g_l4_timing[i] = tacc[i];
     }
     __syncwarp();
   } else {
@@ -201,13 +217,14 @@ lstm4_fwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whh,
         tc_fence_after();
       }
       L4_TICK(1);
+      const uint32_t td = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((s & 1) * L4_NC);
       uint4 hv[2];
 #pragma unroll
       for (int p = 0; p < 2; ++p) {
         const int ul0 = cg * 16 + p * 8;            // first local unit of this pass (a warp owns 16 contiguous units)
         uint32_t acc[32];
         if (s > 0) {
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ul0 * 4), acc);
+          tmem_ld32(td + (uint32_t)(ul0 * 4), acc);
           tmem_ld_wait();
         } else {
 #pragma unroll
@@ -239,6 +256,16 @@ lstm4_fwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whh,
         }
         hv[p] = make_uint4(pack_half2(hout[0], hout[1]), pack_half2(hout[2], hout[3]),
                            pack_half2(hout[4], hout[5]), pack_half2(hout[6], hout[7]));
+        if (s + 1 < T) {
+          // every CTA's chain of this step has retired: the A tiles are free and the peers have consumed the
+          // previous push (whose source is the block overwritten here)
+          if (p == 0 && s > 0) mbar_wait(afree_s + 8u * ((s - 1) & 1), (uint32_t)(((s - 1) >> 1) & 1));
+          *reinterpret_cast<uint4*>(&sm.a[(uint32_t)(16 * p + 4 * j + cg) * L4_A_LBO + (uint32_t)r * 16u]) = hv[p];
+          fence_proxy_async();                       // generic-proxy writes -> visible to UMMA / bulk copies
+          if (p == 1) tc_fence_before();             // our tcgen05.ld's precede the chain that reuses this buffer
+          __syncwarp();
+          if (lane == 0) mbar_arrive_local(staged_s + 8u * p);
+        }
         if (row_ok) {
           const int ug0 = j * 64 + ul0;
 #pragma unroll
@@ -249,37 +276,22 @@ lstm4_fwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whh,
           *reinterpret_cast<float4*>(cst + il32(grow, dir * L4_HP + ug0 + 4, 2 * L4_HP)) =
               make_float4(cout[4], cout[5], cout[6], cout[7]);
         }
+        L4_TICK(2 + p);
       }
       if (row_ok)                                    // h_t of the warp's 16 units: one 32-byte store per row
         st_global_v8(y + grow * (2 * L4_HP) + dir * L4_HP + j * 64 + cg * 16, hv[0], hv[1]);
-      L4_TICK(2);
-      if (s + 1 < T) {
-        // every CTA's MMA chain of this step has retired: A tiles are free, previous pushes were consumed
-        if (s > 0) mbar_wait(afree_s + 8u * ((s - 1) & 1), (uint32_t)(((s - 1) >> 1) & 1));
-        L4_TICK(3);
-#pragma unroll
-        for (int p = 0; p < 2; ++p) {
-          const uint32_t kc = (uint32_t)(j * 8 + cg * 2 + p);
-          *reinterpret_cast<uint4*>(&sm.a[kc * L4_A_LBO + (uint32_t)r * 16u]) = hv[p];
-        }
-        fence_proxy_async();                         // generic-proxy writes -> visible to UMMA / bulk copies
-        tc_fence_before();                           // our tcgen05.ld's precede the next MMA chain
-        __syncwarp();
-        if (lane == 0) mbar_arrive_local(staged_s);
-        L4_TICK(4);
-      }
+      L4_TICK(4);
     }
-  }
-  if (timing) {
-    const int o = (tid == 0) ? 8 : 0;
+    if (timing) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) g_l4_timing[o + i] = tacc[i];
+      for (int i = 0; i < 8; ++i) g_l4_timing[8 + i] = tacc[i];
+    }
   }
   tc_fence_before();
   cluster_sync_all();                                // no CTA exits while peers may still address its smem
   if (w == L4_CWARPS) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 

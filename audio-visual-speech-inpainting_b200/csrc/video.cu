@@ -2,42 +2,69 @@
 //
 // avsi_video_features replaces inc_fps / sync_audio_visual_features (av_sync.py:7-40),
 // get_motion_vector(delta=1) (face_landmarks.py:30-39) and the z-normalisation of
-// tfrecord_utils.py:104-107.  The interpolation abscissa is computed in float64 exactly as
-// np.linspace(0, L*(1-1/T), T) does (start + i*step), so floor() picks the reference's frames.
+// tfrecord_utils.py:104-107.
 // avsi_expand_mask replaces the tail of get_intrusions_mask (dataset_generator.py:43-46).
 #include "common.cuh"
 
 namespace avsi {
 
-__device__ __forceinline__ double lerp_frame(const float* lm, int L, int D, int d, double y) {
-  y = fmin(y, (double)(L - 1));
-  int i0 = (int)floor(y);
-  if (i0 > L - 1) i0 = L - 1;
-  int i1 = min(i0 + 1, L - 1);
-  double w = y - (double)i0;
-  return (double)lm[(long long)i0 * D + d] * (1.0 - w) + (double)lm[(long long)i1 * D + d] * w;
+// Interpolation abscissa of output frame t: np.linspace(0, L*(1-1/T), T)[t] = t*L/T, an exact rational, so the
+// source frame floor(t*L/T) and the weight (t*L mod T)/T are computed in integers (no fp64, no rounding at the
+// frame boundaries); clamped to the last frame like inc_fps.  lerp = a + w*(b - a): for integer pixel
+// coordinates a and b - a are exact, and the motion vector is formed as (a1 - a0) + (w1*d1 - w0*d0).
+struct LerpPos {
+  int i0, i1;
+  float w;
+};
+__device__ __forceinline__ LerpPos lerp_pos(int t, int L, int T) {
+  const long long num = (long long)t * L;
+  int i0 = (int)(num / T);
+  float w = (float)(num - (long long)i0 * T) / (float)T;
+  if (i0 >= L - 1) {
+    i0 = L - 1;
+    w = 0.f;
+  }
+  return {i0, min(i0 + 1, L - 1), w};
 }
 
-__global__ void video_features_kernel(const float* __restrict__ lm, const float* __restrict__ vmean,
-                                      const float* __restrict__ vstd, int B, int L, int D, int T,
-                                      float* __restrict__ out) {
-  const long long n = (long long)B * T * D;
-  const double stop = (double)L * (1.0 - 1.0 / (double)T);
-  const double step = (T > 1) ? stop / (double)(T - 1) : 0.0;
+template <int VEC>
+__global__ void __launch_bounds__(256)
+video_features_kernel(const float* __restrict__ lm, const float* __restrict__ vmean, const float* __restrict__ vstd,
+                      int B, int L, int D, int T, float* __restrict__ out) {
+  const int dv = D / VEC;                            // vectors per frame
+  const long long n = (long long)B * T * dv;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
        idx += (long long)gridDim.x * blockDim.x) {
-    const int d = (int)(idx % D);
-    const int t = (int)((idx / D) % T);
-    const int b = (int)(idx / ((long long)D * T));
-    const float* src = lm + (long long)b * L * D;
-    double mv = 0.0;
+    const int bt = (int)(idx / dv);
+    const int d = (int)(idx - (long long)bt * dv) * VEC;
+    const int b = bt / T, t = bt - b * T;
+    const float* src = lm + (long long)b * L * D + d;
+    float mv[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) mv[k] = 0.f;
     if (t > 0) {
-      // np.linspace: y_i = start + i*step, last point forced to `stop`
-      double y1 = (t == T - 1) ? stop : (double)t * step;
-      double y0 = (double)(t - 1) * step;
-      mv = lerp_frame(src, L, D, d, y1) - lerp_frame(src, L, D, d, y0);
+      const LerpPos p1 = lerp_pos(t, L, T), p0 = lerp_pos(t - 1, L, T);
+      float a1[VEC], b1[VEC], a0[VEC], b0[VEC];
+      if (VEC == 4) {
+        *reinterpret_cast<float4*>(a1) = __ldg(reinterpret_cast<const float4*>(src + (long long)p1.i0 * D));
+        *reinterpret_cast<float4*>(b1) = __ldg(reinterpret_cast<const float4*>(src + (long long)p1.i1 * D));
+        *reinterpret_cast<float4*>(a0) = __ldg(reinterpret_cast<const float4*>(src + (long long)p0.i0 * D));
+        *reinterpret_cast<float4*>(b0) = __ldg(reinterpret_cast<const float4*>(src + (long long)p0.i1 * D));
+      } else {
+        a1[0] = __ldg(src + (long long)p1.i0 * D);
+        b1[0] = __ldg(src + (long long)p1.i1 * D);
+        a0[0] = __ldg(src + (long long)p0.i0 * D);
+        b0[0] = __ldg(src + (long long)p0.i1 * D);
+      }
+#pragma unroll
+      for (int k = 0; k < VEC; ++k)
+        mv[k] = (a1[k] - a0[k]) + (p1.w * (b1[k] - a1[k]) - p0.w * (b0[k] - a0[k]));
     }
-    out[idx] = (float)((mv - (double)vmean[b * D + d]) / (double)vstd[b * D + d]);
+    float o[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) o[k] = (mv[k] - __ldg(vmean + b * D + d + k)) / __ldg(vstd + b * D + d + k);
+    if (VEC == 4) *reinterpret_cast<float4*>(out + (long long)bt * D + d) = *reinterpret_cast<float4*>(o);
+    else out[(long long)bt * D + d] = o[0];
   }
 }
 
@@ -64,9 +91,13 @@ extern "C" int avsi_video_features(const float* landmarks, const float* vmean, c
   using namespace avsi;
   AVSI_REQUIRE(landmarks && vmean && vstd && out, "null pointer");
   AVSI_REQUIRE(B > 0 && L > 0 && D > 0 && T > 0, "sizes");
-  long long n = (long long)B * T * D;
-  int blocks = (int)min((n + 255) / 256, (long long)num_sms() * 8);
-  video_features_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(landmarks, vmean, vstd, B, L, D, T, out);
+  const bool vec = (D % 4 == 0) && ((uintptr_t)landmarks % 16 == 0) && ((uintptr_t)out % 16 == 0);
+  long long n = (long long)B * T * (vec ? D / 4 : D);
+  int blocks = (int)min((n + 255) / 256, (long long)num_sms() * 16);
+  if (vec)
+    video_features_kernel<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(landmarks, vmean, vstd, B, L, D, T, out);
+  else
+    video_features_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(landmarks, vmean, vstd, B, L, D, T, out);
   AVSI_LAUNCH_CHECK();
   return AVSI_OK;
 }

@@ -60,8 +60,8 @@ if os.environ.get('AVSI_L4_TIMING'):
     torch.cuda.synchronize()
     lib.avsi_debug_lstm4_timing.argtypes = [ctypes.c_void_p]
     lib.avsi_debug_lstm4_timing(buf)
-    for o, who, names in ((0, 'control', ['wait_hfull', 'mma_issue', 'wait_staged', 'push_issue']),
-                          (8, 'compute0', ['prefetch', 'wait_done', 'ld+cell+stores', 'wait_afree', 'stage'])):
+    for o, who, names in ((0, 'control', ['wait_staged0', 'wait_staged1(+push0)', 'wait_hfull0(+push1)', 'mma0', 'wait_hfull1', 'mma1']),
+                          (8, 'compute0', ['prefetch', 'wait_done', 'pass0', 'pass1', 'ystore'])):
         print(who, '  '.join('%s %.0f' % (n, buf[o + i] / T) for i, n in enumerate(names)),
               ' total %.0f cyc/step' % (sum(buf[o:o + 8]) / T))
 
