@@ -239,6 +239,7 @@ __global__ void __launch_bounds__(FE_THREADS) frontend_kernel(avsi_frontend_args
 //   * sqrt / log are single MUFU ops (sqrt.approx, lg2.approx: <= 2 ulp, the 1e-5 budget is on relative L2).
 struct FrontendTrainSmem {
   float2 tw[512];
+  float2 tw1[16][16];                   // step-1 twiddles W256^(q k1) as [k1][q]: conflict-free (tw[(2 q k1) & 511] is not)
   float2 win2[192];                     // window as (w[2n], w[2n+1]) pairs
   float2 nrm[260];                      // (1/std, -mean/std) per bin
   float2 xch[FE_FRAMES][FE_XCH];
@@ -260,6 +261,7 @@ __global__ void __launch_bounds__(FE_THREADS, 2) frontend_train_kernel(avsi_fron
   FrontendTrainSmem& sm = *reinterpret_cast<FrontendTrainSmem*>(smem_raw);
   const int tid = threadIdx.x;
   for (int i = tid; i < 512; i += FE_THREADS) sm.tw[i] = reinterpret_cast<const float2*>(p.twiddle)[i];
+  sm.tw1[tid >> 4][tid & 15] = reinterpret_cast<const float2*>(p.twiddle)[(2 * (tid & 15) * (tid >> 4)) & 511];
   for (int i = tid; i < 192; i += FE_THREADS) sm.win2[i] = make_float2(p.window[2 * i], p.window[2 * i + 1]);
   for (int i = tid; i < 257; i += FE_THREADS) {
     const float is = 1.0f / p.stdev[i];
@@ -330,7 +332,7 @@ __global__ void __launch_bounds__(FE_THREADS, 2) frontend_train_kernel(avsi_fron
     float2* xc = sm.xch[fl];
 #pragma unroll
     for (int k1 = 0; k1 < 16; ++k1) {
-      const float2 w = sm.tw[(2 * q * k1) & 511];
+      const float2 w = sm.tw1[k1][q];
       const cpx r = cmul(v[k1], cpx{w.x, w.y});
       xc[k1 * FE_XROW + q] = make_float2(r.x, r.y);
     }

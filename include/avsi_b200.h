@@ -107,6 +107,13 @@ int avsi_video_features(const float* landmarks, const float* vmean, const float*
  *   intervals [B,K,2] i32 (onset, length; length 0 = unused) -> mask [B,T,F] f32 of {0,1}. */
 int avsi_expand_mask(const int32_t* intervals, int B, int K, int T, int F, float* mask, void* stream);
 
+/* Feature statistics (hot-path row a15): the float64 accumulation of compute_mean_std_features
+ * (audio_feat_preprocessing.py:76-115).  x [rows, ldx] f32 features; mask [rows, ldm] f32 or NULL
+ * (feat * mask, frame count += mask[:, 0], :87-92,104-107).  sum/sumsq [F] f64 and count [1] f64 are
+ * ACCUMULATED (caller zeroes them once and calls this per batch). */
+int avsi_feature_stats(const float* x, int ldx, const float* mask, int ldm, int64_t rows, int F, double* sum,
+                       double* sumsq, double* count, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Tensor-core GEMM (tcgen05.mma kind::f16, fp16 operands, fp32 accumulate in TMEM,
  * operands staged by TMA).  Replaces the cuBLAS / cuDNN contractions behind

@@ -481,3 +481,52 @@ def test_lstm_recurrence_fwd_bwd(T, B):
     msg = 'bwd T=%d B=%d: rel dG %.2e rel db %.2e' % (T, B, rel_l2(dG, dPr), rel_l2(dbg, dbr))
     assert rel_l2(dG, dPr) < 2e-3 and rel_l2(dbg, dbr) < 2e-3, msg
     assert np.all(dG[:, :, :, H:] == 0)
+
+
+# ------------------------------------------------------------------------------------------ feature statistics (a15)
+@pytest.mark.parametrize('ftype,apply_mask', [('spec', False), ('spec', True), ('fbanks', False)])
+def test_compute_mean_std_features_matches_oracle(tmp_path, ftype, apply_mask):
+    """compute_mean_std_features (audio_feat_preprocessing.py:23-129) on a small folder of wav files vs the float64
+    oracle of the same loop: mean / std within 1e-5 relative, frame count exact."""
+    from scipy.io import wavfile
+    from avsi_b200 import audio_feat_preprocessing as afp
+    from oracle import feat_stats as ofs
+    rng = np.random.default_rng(11)
+    feats, masks = [], []
+    lens = [4800, 4800, 7000, 4800, 3000]
+    for i, n in enumerate(lens):
+        d = tmp_path / ('s%02d' % i)
+        d.mkdir()
+        x = np.round(np.clip(rng.normal(0, 3000, n), -32767, 32767)).astype(np.int16)
+        wavfile.write(str(d / 'target.wav'), 16000, x)
+        f = ofs.features_of(x.astype(np.float64), ftype)
+        feats.append(f)
+        if apply_mask:
+            Tm = len(f) - 1                       # masks are one frame shorter in the reference's data (discard last frame)
+            m = np.ones((Tm, 257), np.float64)
+            o = int(rng.integers(0, Tm - 4))
+            m[o:o + 3] = 0
+            np.save(str(d / 'mask.npy'), m)
+            masks.append(m)
+    mean, std = afp.compute_mean_std_features(str(tmp_path), 'target', 'stats', type=ftype, apply_mask=apply_mask,
+                                              save_feat=True, batch_size=2)
+    rm, rs, n = ofs.mean_std(feats, masks if apply_mask else None)
+    assert rel_l2(mean, rm) < 1e-5 and rel_l2(std, rs) < 1e-5
+    assert np.allclose(np.load(str(tmp_path / 'stats_mean.npy')), mean)
+    assert np.load(str(tmp_path / 's00' / 'target.npy')).shape[1] == (257 if ftype == 'spec' else 80)
+
+
+def test_feature_stats_counts_and_large():
+    from avsi_b200 import audio_feat_preprocessing as afp
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((3, 250, 257)).astype(np.float32)
+    m = (rng.uniform(size=(3, 250, 1)) > 0.3).astype(np.float32).repeat(257, 2)
+    st = afp.FeatureStats(257)
+    st.update(torch.from_numpy(x).to(dev()), torch.from_numpy(m).to(dev()))
+    st.update(torch.from_numpy(x[:1]).to(dev()))
+    mean, std, n = st.finalize()
+    xs = np.concatenate([(x * m).reshape(-1, 257), x[0]], 0).astype(np.float64)
+    cnt = int(m[:, :, 0].sum()) + 250
+    assert n == cnt
+    assert np.allclose(mean, xs.sum(0) / cnt, rtol=1e-12, atol=1e-14)
+    assert np.allclose(std, np.sqrt((xs ** 2).sum(0) / cnt - (xs.sum(0) / cnt) ** 2), rtol=1e-10)
