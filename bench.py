@@ -285,7 +285,21 @@ def main():
     for name, v in sorted(prof.items(), key=lambda kv: -kv[1]['ms']):
         kernels[name] = {'ms_per_step': v['ms'] / args.steps, 'share': v['ms'] / tot, 'launches_per_step': v['launches'] / args.steps}
 
+    traffic = {}
+    try:
+        tj = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')))
+        if tj['workload'] == {'batch': B, 'audio_len': args.audio_len}:
+            traffic = tj
+    except Exception:
+        traffic = {}
+
     def roof(name):
+        r = roof_(name)
+        if r is not None:
+            r['traffic'] = traffic.get(name)
+        return r
+
+    def roof_(name):
         v = prof.get(name)
         if not v or v['ms'] <= 0:
             return None
