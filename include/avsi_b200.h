@@ -134,14 +134,15 @@ int avsi_gemm_f16(const uint16_t* A, int lda, const uint16_t* B, int ldb, void* 
  * Persistent bidirectional LSTM recurrence.  Replaces cudnnRNNForwardTraining /
  * BackwardData of tf.contrib.cudnn_rnn.CudnnLSTM (models.py:95-104) and the
  * CudnnCompatibleLSTMCell while-loop (models.py:106-115).  Both directions of one
- * layer run in one launch; W_hh stays register-resident across all T steps in a
- * thread-block cluster of 8 CTAs.  HP = 256 (H padded), gate columns are laid out
- * [dir][unit][i,g,f,o] (column = dir*1024 + unit*4 + gate).
- *   gates [T*B, 2048] f16   in: x.W_ih^T pre-activations ; out: activated gates (in place)
+ * layer run in one launch; W_hh stays on chip across all T steps (shared memory of a 4-CTA
+ * thread-block cluster feeding tcgen05.mma, or registers of an 8-CTA cluster for small batches).
+ * HP = 256 (H padded), gate columns are laid out [dir][unit][i,g,f,o] (column = dir*1024 + unit*4 + gate).
+ *   gates [T*B, 2048] f16   INTERLEAVED storage ([rows/32][2048/8][32][8], rows padded to 32 with zeros):
+ *                           in: x.W_ih^T pre-activations (avsi_gemm_f16 layout bit 1) ; out: activated gates (in place)
  *   whh   [2,1024,256] f16  recurrent weights, [dir][gate column][h_in]
  *   bias  [2048] f32
- *   y     [T*B, 512] f16    out: h_t, columns dir*256 + unit
- *   cst   [T*B, 512] f32    out: c_t (stash for BPTT)
+ *   y     [T*B, 512] f16    out: h_t, row-major, columns dir*256 + unit
+ *   cst   [T*B, 512] f32    out: c_t (stash for BPTT), INTERLEAVED with 4-float chunks ([rows/32][512/4][32][4])
  * Backward: dy [T*B,512] f16 (scaled dL/dy), whhT [256,2048] f16 (whh^T) -> gates becomes dgates
  * (in place), dbias[2048] f32 += column sums, scratch >= avsi_lstm_bwd_scratch_bytes(B). */
 int avsi_lstm_fwd(uint16_t* gates, const uint16_t* whh, const float* bias, uint16_t* y, float* cst,
