@@ -19,7 +19,8 @@
 // Shared memory: W_hh^T slice 128 KB (resident for the whole sequence) + 48 KB A-half / push staging (aliased:
 // the A tile is dead once its MMA chain retired) + 48 KB partial slots = 224 KB.
 // Hand-shakes (all mbarriers, no cluster barrier in the loop):
-//   slotfull   tx barrier, peers' partials of the previous step have landed
+//   slotfull[p] tx barriers, peers' partials of the previous step for the units of pass p have landed (the push is
+//              split so that the second half's transfer overlaps the first cell-backward pass)
 //   delivered  3 remote arrives: every peer has RECEIVED my last push -> staging / A tile may be overwritten
 //   consumed   3 remote arrives: every peer has READ its slots       -> I may push again
 //   stagedA[h] 16 warps wrote K-half h of the A tile ; freeA / done : tcgen05.commit of the two MMA chains
@@ -43,10 +44,10 @@ constexpr uint32_t B4_TM_BIAS = 256, B4_TM_C = 288, B4_TM_DC = 352;
 
 struct Lstm4BwdSmem {
   unsigned char wt[B4_W_BYTES];      // [k-chunk position 0..31][h_in n 0..255][16 B]
-  unsigned char ah[B4_AH_BYTES];     // A-half [16 k-chunks][128 rows][16 B]  |  staging [3 owners][8 unit chunks][128 rows][16 B]
-  unsigned char slots[3 * B4_SLICE]; // [3 sources][8 unit chunks][128 rows][16 B]
+  unsigned char ah[B4_AH_BYTES];     // A-half [16 k-chunks][128 rows][16 B]  |  staging [2 passes][3 owners][4 warps][128 rows][16 B]
+  unsigned char slots[3 * B4_SLICE]; // [2 passes][3 sources][4 warps][128 rows][16 B]
   unsigned char ones[128];           // 8 x 8 halves of 1.0 (B operand of the bias MMA, strides 0)
-  unsigned long long slotfull, delivered, consumed, stagedA[2], freeA, done, extracted, slotread;
+  unsigned long long slotfull[2], delivered, consumed, stagedA[2], freeA, done, extracted[2], slotread;
   uint32_t tmem_slot;
 };
 
@@ -75,14 +76,16 @@ lstm4_bwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whhT
 
   const uint32_t wt_s = smem_u32(&sm.wt[0]), ah_s = smem_u32(&sm.ah[0]), slots_s = smem_u32(&sm.slots[0]);
   const uint32_t ones_s = smem_u32(&sm.ones[0]);
-  const uint32_t slotfull_s = smem_u32(&sm.slotfull), delivered_s = smem_u32(&sm.delivered);
+  const uint32_t slotfull_s = smem_u32(&sm.slotfull[0]), delivered_s = smem_u32(&sm.delivered);
   const uint32_t consumed_s = smem_u32(&sm.consumed), stagedA_s = smem_u32(&sm.stagedA[0]);
   const uint32_t freeA_s = smem_u32(&sm.freeA), done_s = smem_u32(&sm.done);
-  const uint32_t extracted_s = smem_u32(&sm.extracted), slotread_s = smem_u32(&sm.slotread);
-  constexpr uint32_t PUSH_BYTES = 3 * B4_SLICE;
+  const uint32_t extracted_s = smem_u32(&sm.extracted[0]), slotread_s = smem_u32(&sm.slotread);
+  constexpr uint32_t B4_HALF = B4_SLICE / 2;            // 8192: one owner's partial for the units of one pass
+  constexpr uint32_t PUSH_BYTES = 3 * B4_HALF;          // per pass
 
   if (tid == 0) {
     mbar_init(slotfull_s, 1);
+    mbar_init(slotfull_s + 8, 1);
     mbar_init(delivered_s, 3);
     mbar_init(consumed_s, 3);
     mbar_init(stagedA_s, B4_CWARPS);
@@ -90,9 +93,13 @@ lstm4_bwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whhT
     mbar_init(freeA_s, 1);
     mbar_init(done_s, 1);
     mbar_init(extracted_s, B4_CWARPS);
+    mbar_init(extracted_s + 8, B4_CWARPS);
     mbar_init(slotread_s, B4_CWARPS);
     fence_barrier_init();
-    if (T > 1) mbar_expect_tx(slotfull_s, PUSH_BYTES);
+    if (T > 1) {
+      mbar_expect_tx(slotfull_s, PUSH_BYTES);
+      mbar_expect_tx(slotfull_s + 8, PUSH_BYTES);
+    }
   }
   if (w == B4_CWARPS) tmem_alloc(smem_u32(&sm.tmem_slot), 512);
   // W_hh^T slice -> smem.  K position kpos = [half h][cg][i] <-> gate-column chunk 32j + 8cg + 4h + i
@@ -125,15 +132,18 @@ lstm4_bwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whhT
       for (int cp = 0; cp < 3; ++cp) {
         const int c = cp + (cp >= j ? 1 : 0);                          // owner CTA of staging slice cp
         const int src = (j < c) ? j : j - 1;                           // my slot index at CTA c
-        peer_slot[cp] = map_to_cta(slots_s + (uint32_t)src * B4_SLICE, (uint32_t)c);
+        peer_slot[cp] = map_to_cta(slots_s + (uint32_t)src * B4_HALF, (uint32_t)c);
         peer_full[cp] = map_to_cta(slotfull_s, (uint32_t)c);
         peer_delivered[cp] = map_to_cta(delivered_s, (uint32_t)c);
         peer_consumed[cp] = map_to_cta(consumed_s, (uint32_t)c);
       }
       for (int s = 0; s < T; ++s) {
         if (s > 0) {
-          mbar_wait(slotfull_s, (uint32_t)((s - 1) & 1));              // peers' partials of step s-1 are here
-          if (s + 1 < T) mbar_expect_tx(slotfull_s, PUSH_BYTES);
+#pragma unroll
+          for (int ph = 0; ph < 2; ++ph) {                             // peers' partials of step s-1 (both halves) are here
+            mbar_wait(slotfull_s + 8u * ph, (uint32_t)((s - 1) & 1));
+            if (s + 1 < T) mbar_expect_tx(slotfull_s + 8u * ph, PUSH_BYTES);
+          }
 #pragma unroll
           for (int cp = 0; cp < 3; ++cp) mbar_arrive_remote_relaxed(peer_delivered[cp]);
         }
@@ -164,14 +174,18 @@ lstm4_bwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whhT
           }
         }
         if (s + 1 < T) {
-          mbar_wait(extracted_s, (uint32_t)(s & 1));
-          B4_TICK(6);
-          if (s > 0) mbar_wait(consumed_s, (uint32_t)((s - 1) & 1));   // peers' slots are free again
-          B4_TICK(7);
 #pragma unroll
-          for (int cp = 0; cp < 3; ++cp)
-            bulk_copy_to_cta(peer_slot[cp], ah_s + (uint32_t)cp * B4_SLICE, B4_SLICE, peer_full[cp]);
-          B4_TICK(8);
+          for (int ph = 0; ph < 2; ++ph) {
+            mbar_wait(extracted_s + 8u * ph, (uint32_t)(s & 1));
+            B4_TICK(6);
+            if (ph == 0 && s > 0) mbar_wait(consumed_s, (uint32_t)((s - 1) & 1));   // peers' slots are free again
+            B4_TICK(7);
+#pragma unroll
+            for (int cp = 0; cp < 3; ++cp)
+              bulk_copy_to_cta(peer_slot[cp] + (uint32_t)ph * PUSH_BYTES, ah_s + (uint32_t)ph * PUSH_BYTES + (uint32_t)cp * B4_HALF,
+                               B4_HALF, peer_full[cp] + 8u * ph);
+            B4_TICK(8);
+          }
         }
       }
     }
@@ -218,18 +232,18 @@ lstm4_bwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whhT
       uint4 g4[4], dyv;
       float cprev[8];
       load_inputs(0, g4, cprev, dyv);
-      if (row_ok && has_prev) {
+      if (row_ok && has_prev && (lane & 7) == 0) {     // one lane per 128-byte line of the interleaved runs
         const int tn = dir ? (t + 1) : (t - 1), tnp = dir ? (t + 2) : (t - 2);
         const long long gn = (long long)tn * B + row, gnp = (long long)tnp * B + row;
         const int ug = 64 * j + 16 * cg;
 #pragma unroll
         for (int i = 0; i < 8; ++i) prefetch_l2(gates + il16(gn, dir * B4_G + ug * 4 + 8 * i, 2 * B4_G));
-        prefetch_l2(dy + gn * (2 * B4_HP) + dir * B4_HP + ug);
         if (s + 2 < T) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) prefetch_l2(cst + il32(gnp, dir * B4_HP + ug + 4 * i, 2 * B4_HP));
         }
       }
+      B4_TICK(9);
       uint32_t own1[8];                             // own partial of the second half's units (read before the MMA chain overwrites it)
       if (s > 0) {
         mbar_wait(slotfull_s, (uint32_t)((s - 1) & 1));
@@ -260,6 +274,7 @@ lstm4_bwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whhT
           tmem_ld8(trow + B4_TM_DC + (uint32_t)ul0, dd);
           if (h == 0) tmem_ld8(trow + (uint32_t)ug0, own);
           tmem_ld_wait();
+          if (h == 1) mbar_wait(slotfull_s + 8u, (uint32_t)((s - 1) & 1));      // second half of the peers' partials
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             c_cur[i] = __uint_as_float(cc[i]);
@@ -268,8 +283,8 @@ lstm4_bwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whhT
           }
 #pragma unroll
           for (int src = 0; src < 3; ++src) {
-            const uint4 v = *reinterpret_cast<const uint4*>(&sm.slots[(uint32_t)src * B4_SLICE + (uint32_t)(ul0 >> 3) * 2048u +
-                                                                      (uint32_t)r * 16u]);
+            const uint4 v = *reinterpret_cast<const uint4*>(&sm.slots[(uint32_t)h * PUSH_BYTES + (uint32_t)src * B4_HALF +
+                                                                      (uint32_t)cg * 2048u + (uint32_t)r * 16u]);
             const float2 a = unpack_half2(v.x), b = unpack_half2(v.y), c = unpack_half2(v.z), d = unpack_half2(v.w);
             dhrec[0] += a.x; dhrec[1] += a.y; dhrec[2] += b.x; dhrec[3] += b.y;
             dhrec[4] += c.x; dhrec[5] += c.y; dhrec[6] += d.x; dhrec[7] += d.y;
@@ -340,26 +355,28 @@ lstm4_bwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whhT
       tc_fence_after();
       B4_TICK(7);
       if (has_prev) {
+        // first the columns the receivers need for their first pass, shipped while the second half is converted
 #pragma unroll
-        for (int cp = 0; cp < 3; ++cp) {
-          const int c = cp + (cp >= j ? 1 : 0);
-          uint32_t acc[16];
-          tmem_ld16(trow + (uint32_t)(64 * c + 16 * cg), acc);
-          tmem_ld_wait();
+        for (int ph = 0; ph < 2; ++ph) {
 #pragma unroll
-          for (int k = 0; k < 2; ++k) {
+          for (int cp = 0; cp < 3; ++cp) {
+            const int c = cp + (cp >= j ? 1 : 0);
+            uint32_t acc[8];
+            tmem_ld8(trow + (uint32_t)(64 * c + 16 * cg + 8 * ph), acc);
+            tmem_ld_wait();
             uint4 v;
-            v.x = pack_half2(__uint_as_float(acc[8 * k + 0]), __uint_as_float(acc[8 * k + 1]));
-            v.y = pack_half2(__uint_as_float(acc[8 * k + 2]), __uint_as_float(acc[8 * k + 3]));
-            v.z = pack_half2(__uint_as_float(acc[8 * k + 4]), __uint_as_float(acc[8 * k + 5]));
-            v.w = pack_half2(__uint_as_float(acc[8 * k + 6]), __uint_as_float(acc[8 * k + 7]));
-            *reinterpret_cast<uint4*>(&sm.ah[(uint32_t)cp * B4_SLICE + (uint32_t)(2 * cg + k) * 2048u + (uint32_t)r * 16u]) = v;
+            v.x = pack_half2(__uint_as_float(acc[0]), __uint_as_float(acc[1]));
+            v.y = pack_half2(__uint_as_float(acc[2]), __uint_as_float(acc[3]));
+            v.z = pack_half2(__uint_as_float(acc[4]), __uint_as_float(acc[5]));
+            v.w = pack_half2(__uint_as_float(acc[6]), __uint_as_float(acc[7]));
+            *reinterpret_cast<uint4*>(&sm.ah[(uint32_t)ph * PUSH_BYTES + (uint32_t)cp * B4_HALF + (uint32_t)cg * 2048u +
+                                             (uint32_t)r * 16u]) = v;
           }
+          fence_proxy_async();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_local(extracted_s + 8u * ph);
         }
-        fence_proxy_async();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_local(extracted_s);
         B4_TICK(8);
       }
     }

@@ -79,6 +79,6 @@ if os.environ.get('AVSI_B4_TIMING'):
     for o, who, names in ((0, 'control', ['wait_slotfull', 'wait_stagedA0', 'mma0', 'wait_stagedA1', 'mma1', 'send_consumed',
                                           'wait_extracted', 'wait_consumed', 'push']),
                           (12, 'compute0', ['wait_slotfull+own', 'pass0', 'wait+write A0', 'pass1', 'wait+write A1', '-', '-',
-                                            'wait_done', 'extract'])):
+                                            'wait_done', 'extract', 'issue loads'])):
         print(who, '  '.join('%s %.0f' % (n, buf[o + i] / T) for i, n in enumerate(names)),
               ' total %.0f cyc/step' % (sum(buf[o:o + 12]) / T))
