@@ -72,6 +72,67 @@ def test_si_forward_loss_gradients(model_name, B, audio_len):
     _check_grads(model.canonical_gradients(), ograds, model_name)
 
 
+@pytest.mark.parametrize('model_name,B,audio_len', [('av-blstm', 150, 4800), ('a-blstm', 129, 2400)])
+def test_si_large_batch_tcgen05_path(model_name, B, audio_len):
+    """B >= 113 selects the tcgen05 4-CTA-cluster recurrence kernels (forward + BPTT) and, with M*N*K large enough,
+    the CTA-pair GEMM: same oracle, same tolerances; the last batch tile is ragged (150 = 128 + 22)."""
+    from oracle import blstm as oblstm
+    T = -(-audio_len // 192)
+    seq = np.full(B, T)
+    seq[3] = T - 2
+    model, batch, canon, inp = _build(model_name, B, audio_len, seed=B, seq_len=seq)
+    tsn, net_in = _oracle_inputs(batch, inp)
+    outs, ograds = oblstm.loss_and_grads('si', dict(net_in=net_in, target=tsn, mask=batch['mask'], seq_len=batch['seq_len']),
+                                         canon, 3)
+    assert rel_l2(model.target_spec_norm.cpu().numpy(), tsn) < 1e-5
+    assert rel_l2(model.prediction.cpu().numpy(), outs['prediction']) < TOL
+    assert abs(float(model.loss) - float(outs['loss'])) < TOL * abs(float(outs['loss']))
+    _check_grads(model.canonical_gradients(), ograds, model_name + ' B=%d' % B)
+
+
+def test_mtl_large_batch_tcgen05_path():
+    from oracle import blstm as oblstm
+    B, audio_len = 130, 11520        # T = 60 >= 2 * 24 + 1 label states
+    model, batch, canon, inp = _build('av-blstm-ssnn-ctc', B, audio_len, seed=33, ctc_loss=0.05)
+    tsn, net_in = _oracle_inputs(batch, inp)
+    outs, ograds = oblstm.loss_and_grads(
+        'mtl', dict(net_in=net_in, target=tsn, mask=batch['mask'], seq_len=batch['seq_len'], labels=batch['labels'],
+                    lab_len=batch['lab_len']), canon, 3, ctc_weight=0.05)
+    assert rel_l2(model.prediction.cpu().numpy(), outs['prediction']) < TOL
+    assert abs(float(model.loss) - float(outs['loss'])) < TOL * float(outs['loss'])
+    _check_grads(model.canonical_gradients(), ograds, 'mtl B=130')
+
+
+def test_full_size_batch_consistent_with_small_batch_kernels():
+    """BASELINE shape (3 s utterances, T = 250) at B = 256: utterances computed inside the big batch (tcgen05
+    recurrence, CTA-pair GEMMs) agree with the same utterances run alone through the small-batch kernels
+    (mma.sync recurrence, one-tile GEMM) -- a size-independent property, no oracle needed; and the summed loss
+    sums are additive over a split of the batch."""
+    from avsi_b200 import av_sync, models, synth
+    from avsi_b200.layout import init_canonical
+    B = 256
+    batch = synth.make_batch(B, audio_len=48000, seed=77)
+    cfg = synth.default_config('av-blstm', batch_size=B, audio_len=48000)
+
+    def run(idx):
+        sub = {k: batch[k][idx] for k in ('wav', 'mask', 'landmarks', 'vmean', 'vstd', 'seq_len')}
+        video = av_sync.video_pipeline(sub['landmarks'], batch['T'], sub['vmean'], sub['vstd'])
+        m = models.StackedBLSTMModel(sub['seq_len'], sub['wav'], sub['mask'], batch['mean'], batch['std'], 0.0, cfg,
+                                     video_features=video, input='av')
+        m.assign_vars(init_canonical(m.engine.layout, seed=5, bias_scale=0.05))
+        pred = m.prediction.cpu().numpy()
+        sums = m._loss_pass(False)['sums'].cpu().numpy().copy()
+        return pred, sums
+    big, sums_big = run(np.arange(B))
+    pick = np.array([0, 100, 127, 128, 255])
+    small, _ = run(pick)
+    assert rel_l2(big[pick], small) < TOL
+    lo, s_lo = run(np.arange(0, 130))
+    hi, s_hi = run(np.arange(130, B))
+    assert rel_l2(np.concatenate([lo, hi]), big) < TOL
+    assert np.allclose(s_lo[:6] + s_hi[:6], sums_big[:6], rtol=2e-3)
+
+
 def test_si_full_length_utterance():
     """GRID shape: 3 s, T = 250 -- error growth over the 250-step chain stays inside the budget."""
     from oracle import blstm as oblstm
