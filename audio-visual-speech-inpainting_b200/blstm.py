@@ -218,6 +218,21 @@ class BLSTMEngine(object):
                 cur = nxt
         return g
 
+    def sgd_step(self, lr, momentum=None, grad_unscale=1.0, unscale_dev=None, l2=0.0):
+        """tf.train.GradientDescentOptimizer / MomentumOptimizer(0.9) update (models.py:169-173)."""
+        lib = _lib.load()
+        self.step_count += 1
+        n = self.layout.n_params_padded
+        acc = None
+        if momentum is not None:
+            if not hasattr(self, 'momentum_acc'):
+                self.momentum_acc = torch.zeros(n, dtype=torch.float32, device=self.device)
+            acc = self.momentum_acc
+        with _lib.span('sgd'):
+            _lib.check(lib.avsi_sgd_momentum(_p(self.theta), _p(self.grad), _p(acc), n, lr, momentum or 0.0, grad_unscale,
+                                             _p(unscale_dev), l2, _lib.stream_ptr()), 'avsi_sgd_momentum')
+            self.refresh_half()
+
     # ---- update -------------------------------------------------------------------------------
     def adam_step(self, lr=1e-3, grad_unscale=1.0, unscale_dev=None, l2=0.0, b1=0.9, b2=0.999, eps=1e-8):
         lib = _lib.load()

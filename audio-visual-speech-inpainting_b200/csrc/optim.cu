@@ -23,6 +23,24 @@ adam_tf_kernel(float* __restrict__ theta, const float* __restrict__ g, float* __
   }
 }
 
+// tf.train.GradientDescentOptimizer / MomentumOptimizer(momentum) (models.py:169-173):
+//   sgd:       theta -= lr * g
+//   momentum:  accum = momentum * accum + g ; theta -= lr * accum          (TF ApplyMomentum, use_nesterov = False)
+__global__ void __launch_bounds__(256)
+sgd_momentum_kernel(float* __restrict__ theta, const float* __restrict__ g, float* __restrict__ accum, long long n,
+                    float lr, float momentum, float unscale, const float* __restrict__ unscale_dev, float l2) {
+  const float us = unscale * (unscale_dev ? *unscale_dev : 1.f);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float th = theta[i];
+    float gi = fmaf(g[i], us, l2 * th);
+    if (accum) {
+      gi = fmaf(momentum, accum[i], gi);
+      accum[i] = gi;
+    }
+    theta[i] = th - lr * gi;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 cast_weights_kernel(const float* __restrict__ w, int R, int C, uint16_t* __restrict__ w16,
                     uint16_t* __restrict__ w16t) {
@@ -73,6 +91,18 @@ extern "C" int avsi_adam_tf(float* theta, const float* g, float* m, float* v, in
   adam_tf_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(theta, g, m, v, (long long)n, (float)lr_t, (float)b1, (float)(1.0 - b1),
                                                           (float)b2, (float)(1.0 - b2), (float)eps,
                                                           grad_unscale, grad_unscale_dev, l2);
+  AVSI_LAUNCH_CHECK();
+  return AVSI_OK;
+}
+
+extern "C" int avsi_sgd_momentum(float* theta, const float* g, float* accum, int64_t n, double lr, double momentum,
+                                 float grad_unscale, const float* grad_unscale_dev, float l2, void* stream) {
+  using namespace avsi;
+  AVSI_REQUIRE(theta && g, "null pointer");
+  AVSI_REQUIRE(n > 0, "n > 0");
+  int blocks = (int)min((long long)(n + 255) / 256, (long long)num_sms() * 8);
+  sgd_momentum_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(theta, g, accum, (long long)n, (float)lr, (float)momentum,
+                                                               grad_unscale, grad_unscale_dev, l2);
   AVSI_LAUNCH_CHECK();
   return AVSI_OK;
 }

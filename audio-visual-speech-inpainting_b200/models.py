@@ -270,8 +270,8 @@ class StackedBLSTMModel(object):
         return out
 
     def train_op(self):
-        if self.optimizer_choice != 'adam':
-            print('Optimizer must be adam in this build (sgd / momentum not implemented). Closing...')
+        if self.optimizer_choice not in ('adam', 'sgd', 'momentum'):
+            print('Optimizer must be either sgd, momentum or adam. Closing...')         # models.py:175-176
             sys.exit(1)
         out = self.compute_gradients()
         world = 1
@@ -284,8 +284,13 @@ class StackedBLSTMModel(object):
             with _lib.span('grad_allreduce', nbytes=self.engine.grad.numel() * 4):
                 parallel.all_reduce_flat(self.engine.grad, self.process_group)
         host, dev = self._grad_unscale(out, world)
-        self.engine.adam_step(lr=self.starter_learning_rate, grad_unscale=host, unscale_dev=dev,
-                              l2=self.regularization)
+        if self.optimizer_choice == 'adam':
+            # Adam is given the constant starter rate (models.py:168); the decayed rate applies to sgd / momentum only
+            self.engine.adam_step(lr=self.starter_learning_rate, grad_unscale=host, unscale_dev=dev,
+                                  l2=self.regularization)
+        else:
+            self.engine.sgd_step(self.learning_rate, 0.9 if self.optimizer_choice == 'momentum' else None,
+                                 grad_unscale=host, unscale_dev=dev, l2=self.regularization)
         self.global_step += 1
 
     def canonical_gradients(self):

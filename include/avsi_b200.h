@@ -194,6 +194,10 @@ int avsi_ctc_loss(const float* logits, int ldl, int col0, int C, const int32_t* 
 int avsi_adam_tf(float* theta, const float* g, float* m, float* v, int64_t n, double lr, double b1,
                  double b2, double eps, int step, float grad_unscale, const float* grad_unscale_dev,
                  float l2, void* stream);
+/* tf.train.GradientDescentOptimizer (accum == NULL) / MomentumOptimizer(momentum = 0.9) (models.py:169-173):
+ * accum = momentum * accum + g ; theta -= lr * accum.  lr is the (host-evaluated) staircase exponential decay. */
+int avsi_sgd_momentum(float* theta, const float* g, float* accum, int64_t n, double lr, double momentum,
+                      float grad_unscale, const float* grad_unscale_dev, float l2, void* stream);
 /* fp32 -> fp16 copies of a weight matrix W [R,C]: w16 [R,C] and (optional) w16t [C,R]. */
 int avsi_cast_weights(const float* w, int R, int C, uint16_t* w16, uint16_t* w16t, void* stream);
 

@@ -217,3 +217,29 @@ def test_variables_roundtrip_and_inference_mode():
     assert enh.shape == (2, 4800) and torch.isfinite(enh).all()
     with pytest.raises(Exception):
         m2.train_op()
+
+
+@pytest.mark.parametrize('opt', ['sgd', 'momentum'])
+def test_sgd_and_momentum_updates(opt):
+    """models.py:165-173: staircase exponential decay of the rate, GradientDescent / Momentum(0.9) updates."""
+    model, batch, canon, inp = _build('a-blstm', 3, 2400, seed=2)
+    model.optimizer_choice = opt
+    model.starter_learning_rate, model.learning_decay, model.updating_step = 0.5, 0.5, 2
+    theta0 = model.engine.theta.clone()
+    acc = torch.zeros_like(theta0)
+    expect = theta0.clone()
+    for step in range(3):
+        lr = 0.5 * 0.5 ** (step // 2)
+        assert abs(model.learning_rate - lr) < 1e-12
+        model.compute_gradients()
+        n = model.engine.layout.n_params_padded
+        g = model.engine.grad[:n].clone() / (3 * batch['T'] * 257)
+        model._cache = {}
+        model.train_op()
+        if opt == 'momentum':
+            acc = 0.9 * acc + g
+            expect = expect - lr * acc
+        else:
+            expect = expect - lr * g
+        assert rel_l2(model.engine.theta.cpu().numpy(), expect.cpu().numpy()) < 1e-5
+        model.feed(target_sources=batch['wav'])
