@@ -1,0 +1,86 @@
+"""TFRecord data manager with the reference's interface (dataset_reader.py:12-60), without TensorFlow.
+
+`DataManager.get_dataset(file_list, shuffle, seed)` / `get_iterator(dataset, batch_size, n_epochs)` keep their
+names and argument meaning; instead of graph tensors the iterator is a Python generator of numpy batches in the
+reference's order (dataset_reader.py:77-79):
+
+    (sequence_length i32 [B], labels_length i32 [B], target_audio_wav i32 [B,N], sample_path [B] bytes,
+     labels f32 [B,Lmax], video_features f32 [B,T,V], mask f32 [B,T,F])
+
+Exhaustion raises StopIteration where the reference's loop catches tf.errors.OutOfRangeError.  Data parallel runs
+pass `rank` / `world` so that each process reads files[rank::world]."""
+import random
+
+import numpy as np
+
+from . import parallel
+from .tfrecord_io import parse_sequence_example, read_records
+
+
+class _Dataset(object):
+    def __init__(self, files, parse, shuffle, buffer_size, seed):
+        self.files, self.parse, self.shuffle, self.buffer_size, self.seed = list(files), parse, shuffle, buffer_size, seed
+
+    def samples(self):
+        def raw():
+            for f in self.files:
+                for rec in read_records(f):
+                    yield self.parse(rec)
+        if not self.shuffle:
+            for s in raw():
+                yield s
+            return
+        rng = random.Random(self.seed)                       # tf.data shuffle: a buffer of buffer_size elements
+        buf = []
+        for s in raw():
+            buf.append(s)
+            if len(buf) >= self.buffer_size:
+                yield buf.pop(rng.randrange(len(buf)))
+        while buf:
+            yield buf.pop(rng.randrange(len(buf)))
+
+
+class DataManager(object):
+    """Utilities to read TFRecords"""
+
+    def __init__(self, num_audio_samples=48000, audio_feat_size=257, video_feat_size=136, buffer_size=1000, mode='fixed',
+                 rank=0, world=1, **unused):
+        if mode != 'fixed':
+            raise NotImplementedError("only the 'fixed' TFRecord mode works in the reference (SURVEY.md 2.4)")
+        self.num_audio_samples, self.audio_feat_size, self.video_feat_size = num_audio_samples, audio_feat_size, video_feat_size
+        self.buffer_size, self.mode, self.rank, self.world = buffer_size, mode, rank, world
+
+    def read_data_format_fixed(self, sample):
+        ctx, seq = parse_sequence_example(sample)
+        wav = np.asarray(ctx['target_audio_wav'], np.float32)
+        if wav.shape[0] != self.num_audio_samples:
+            raise ValueError('target_audio_wav has %d samples, expected %d' % (wav.shape[0], self.num_audio_samples))
+        return (np.int32(ctx['sequence_length'][0]), np.int32(ctx['labels_length'][0]), wav.astype(np.int32),
+                ctx['sample_path'][0] if ctx['sample_path'] else b'',
+                np.concatenate(seq['labels']).astype(np.float32) if seq.get('labels') else np.zeros(0, np.float32),
+                np.stack(seq['video_features']).astype(np.float32), np.stack(seq['mask']).astype(np.float32))
+
+    def get_dataset(self, file_list, shuffle=True, seed=None):
+        files = parallel.shard_list(file_list, self.rank, self.world) if self.world > 1 else list(file_list)
+        return _Dataset(files, self.read_data_format_fixed, shuffle, self.buffer_size, seed)
+
+    def get_iterator(self, dataset, batch_size=16, n_epochs=None, drop_remainder=False):
+        def batches():
+            epoch = 0
+            while n_epochs is None or epoch < n_epochs:
+                cur = []
+                for s in dataset.samples():
+                    cur.append(s)
+                    if len(cur) == batch_size:
+                        yield _collate(cur)
+                        cur = []
+                if cur and not drop_remainder:
+                    yield _collate(cur)
+                epoch += 1
+        return dataset, batches()
+
+
+def _collate(samples):
+    cols = list(zip(*samples))
+    return (np.asarray(cols[0], np.int32), np.asarray(cols[1], np.int32), np.stack(cols[2]), list(cols[3]),
+            np.stack(cols[4]), np.stack(cols[5]), np.stack(cols[6]))

@@ -380,6 +380,26 @@ class StackedBLSTMSSNNCTCLossModel(StackedBLSTMModel):
         return 1.0, out['scales'][2:3]
 
     @property
+    def per(self):
+        """Phone error rate per utterance: edit distance(decoded, labels) / label length (models.py:1718 uses
+        tf.edit_distance on the beam-search output; here on the best-path decoding, host side, off the hot loop)."""
+        dec = self.decoding
+        labels = self._fed['labels'].cpu().numpy()
+        lens = self._fed['labels_lengths'].cpu().numpy()
+        out = np.zeros(len(dec), np.float32)
+        for b in range(len(dec)):
+            hyp = [int(x) for x in dec[b] if x >= 0]
+            ref = [int(x) for x in labels[b, :int(lens[b])]]
+            prev = list(range(len(ref) + 1))
+            for i, h in enumerate(hyp, 1):
+                cur = [i] + [0] * len(ref)
+                for jx, r in enumerate(ref, 1):
+                    cur[jx] = min(prev[jx] + 1, cur[jx - 1] + 1, prev[jx - 1] + (h != r))
+                prev = cur
+            out[b] = prev[-1] / max(1, len(ref))
+        return out
+
+    @property
     def decoding(self):
         """Best-path (greedy) CTC decoding; the reference's beam search (width 20, models.py:1627) is a
         monitoring op kept off the training hot loop."""

@@ -1,0 +1,246 @@
+"""train(config_file): the reference's training job (training.py:23 / training_ctc.py:23, the loop the CLI's
+`training` sub-command runs) on the B200 hot path.
+
+Same config file, same experiment folder layout (`netmodel/{ckpt,sinet,config.txt,audio_features_*.npy}`,
+`training_log.txt`), same console / log-file lines, same schedule (epochs over one pass of the shuffled training
+TFRecords, validation pass, best-validation checkpoint `sinet`, early stopping, `ckpt` every 1000 steps, NaN / Inf
+exit code 1).  The session run per step becomes model.feed(...) + model.train_op().  Differences, all host side:
+checkpoints are `.npz` files keyed by the TF variable names (checkpoint.py); PER is computed from the best-path
+decoding at the logging steps and on the validation set instead of a beam search on every step; TensorBoard
+scalars are written when torch.utils.tensorboard is importable.  Under torchrun every rank trains on
+files[rank::world] with the gradient all-reduce of parallel.py; rank 0 logs and saves."""
+import os
+import random
+import shutil
+import sys
+from glob import glob
+from time import time
+
+import numpy as np
+
+from . import checkpoint
+from .config_utils import check_trainconfiguration, load_configfile
+from .dataset_reader import DataManager
+from .models import MODEL_REGISTRY
+
+
+class _RunningAverage(object):
+    """Averages weighted by the number of masked frames of the batch (training_ctc.py:285-297)."""
+
+    def __init__(self):
+        self.n, self.vals = 0, None
+
+    def add(self, frames, vals):
+        vals = np.asarray(vals, np.float64)
+        if self.vals is None:
+            self.n, self.vals = frames, vals
+        else:
+            prev = self.n
+            self.n += frames
+            self.vals = (self.vals * prev + vals * frames) / max(self.n, 1)
+        return self.vals
+
+
+def build_model(config, batch, mean, std, is_training=True, device='cuda', process_group=None):
+    """Instantiate the model class `config['model']` names on the tensors of a first batch."""
+    name = config['model']
+    if name not in MODEL_REGISTRY:
+        print('Model selection must be "a-blstm", "v-blstm", "av-blstm" or a "-ctc" variant of them. Closing...')
+        sys.exit(1)
+    cls, inp = MODEL_REGISTRY[name]
+    seq, lab_len, wav, _, labels, video, mask = batch
+    kw = dict(video_features=video, input=inp, is_training=is_training, device=device, process_group=process_group)
+    if cls.MTL:
+        model = cls(seq, lab_len, wav.astype(np.float32), mask, labels, mean, std, 0.0, config, **kw)
+    else:
+        model = cls(seq, wav.astype(np.float32), mask, mean, std, 0.0, config, **kw)
+    model.build_graph(name)
+    return model
+
+
+def feed_batch(model, batch):
+    seq, lab_len, wav, _, labels, video, mask = batch
+    kw = dict(sequence_lengths=seq, target_sources=wav.astype(np.float32), masks=mask, video_features=video)
+    if model.MTL:
+        kw.update(labels_lengths=lab_len, labels=labels)
+    model.feed(**kw)
+    return np.count_nonzero(mask[:, :, 0] == 0)                 # masked frames of the batch
+
+
+def _losses(model, want_per):
+    loss, hole = float(model.loss), float(model.loss_hole)
+    ctc = float(model.ctc_loss) if model.MTL else 0.0
+    per = float(model.per.mean()) if (model.MTL and want_per) else 0.0
+    return loss, hole, ctc, per
+
+
+def train(config_file, max_steps=None):
+    """Train the speech inpainting model."""
+    import torch
+    import torch.distributed as dist
+    config = check_trainconfiguration(load_configfile(config_file))
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    pg = dist.group.WORLD if world > 1 else None
+    data_path_train = os.path.join(config['root_folder'], 'training-set')
+    data_path_val = os.path.join(config['root_folder'], 'validation-set')
+    exp_path = config['exp_folder']
+    exp_name = os.path.basename(exp_path)
+    checkpoints_dir = os.path.join(exp_path, 'netmodel')
+    log_path = os.path.join(exp_path, 'training_log.txt')
+
+    def manager():
+        return DataManager(num_audio_samples=config['audio_len'], audio_feat_size=config['audio_feat_dim'],
+                           video_feat_size=config['video_feat_dim'], buffer_size=4000, mode='fixed', rank=rank, world=world)
+    train_files = sorted(glob(os.path.join(data_path_train, '*.tfrecord')))
+    val_files = sorted(glob(os.path.join(data_path_val, '*.tfrecord')))
+    audio_feat_mean = np.load(config['audio_feat_mean']).astype(np.float32)
+    audio_feat_std = np.load(config['audio_feat_std']).astype(np.float32)
+    per_rank_batch = max(1, config['batch_size'] // world)
+
+    if rank == 0:
+        os.makedirs(checkpoints_dir, exist_ok=True)
+        os.makedirs(os.path.join(exp_path, 'tfboard'), exist_ok=True)
+        dest_config_file = os.path.join(checkpoints_dir, 'config.txt')
+        if os.path.abspath(dest_config_file) != os.path.abspath(config_file):
+            shutil.copy(config_file, dest_config_file)
+        shutil.copy(config['audio_feat_mean'], os.path.join(checkpoints_dir, 'audio_features_mean.npy'))
+        shutil.copy(config['audio_feat_std'], os.path.join(checkpoints_dir, 'audio_features_std.npy'))
+    log = open(log_path, 'a') if rank == 0 else None
+    tb = None
+    if rank == 0:
+        try:
+            from torch.utils.tensorboard import SummaryWriter
+            tb = SummaryWriter(os.path.join(exp_path, 'tfboard'))
+        except Exception:
+            tb = None
+
+    seq_lengths_train = np.load(os.path.join(data_path_train, 'seq_lengths.npy'))
+    seq_lengths_val = np.load(os.path.join(data_path_val, 'seq_lengths.npy'))
+    train_size, val_size = len(seq_lengths_train), len(seq_lengths_val)
+    n_steps_epoch = max(1, int(train_size / config['batch_size']))
+    n_steps = n_steps_epoch * config['max_n_epochs']
+
+    # model on the shape of a first batch
+    _, probe = manager().get_iterator(manager().get_dataset(train_files, shuffle=False), batch_size=per_rank_batch, n_epochs=1)
+    model = build_model(config, next(probe), audio_feat_mean, audio_feat_std, True, process_group=pg)
+    print('Model building done.')
+    if config.get('model_ckp'):
+        try:
+            checkpoint.restore(model, config['model_ckp'])
+            print('Model variables restored.')
+        except ValueError:
+            print('{:s} is not a valid checkpoint. Closing...'.format(config['model_ckp']))
+            sys.exit(2)
+    header = ['+-- EXPERIMENT NAME - {:s} --+'.format(exp_name), '## Model type: {:s}'.format(config['model']),
+              '## Network dimensions: {:s}'.format(str(config['net_dim'])), '## Optimizer: {:s}'.format(config['optimizer_type']),
+              '## Starter learning rate: {:.6f}'.format(config['starter_learning_rate']),
+              '## Learning rate update steps: {:d}'.format(config['lr_updating_steps']),
+              '## Learning rate decay: {:.6f}'.format(config['lr_decay']),
+              '## CTC-loss coefficient: {:.6f}'.format(float(config.get('ctc_loss', 0))),
+              '## L2 regularization coefficient: {:.6f}'.format(config['l2']),
+              '## Dropout rate (no dropout if 0): {:.6f}'.format(config['dropout_rate']),
+              '## Training dataset: {:s}'.format(data_path_train), '## Training size: {:d}'.format(train_size),
+              '## Validation dataset: {:s}'.format(data_path_val), '## Validation size: {:d}'.format(val_size),
+              '## Batch size: {:d}'.format(config['batch_size']),
+              '## Approximated number of steps per epoch: {:d}'.format(n_steps_epoch),
+              '## Number of training epochs: {:d}'.format(config['max_n_epochs']),
+              '## Approximated total number of steps: {:d}'.format(n_steps)]
+    if rank == 0:
+        if not config.get('model_ckp'):
+            log.write('\n'.join(header) + '\n')
+            log.write('\nEpoch\tLR\tTraining loss\tTraining PER \tValidation loss\tValidation PER[TIME]\n')
+        print('\n' + '\n'.join(header[:-1]) + '\n')
+
+    tot_step = model.global_step
+    epoch_counter = int(tot_step / n_steps_epoch)
+    best_val_checkpoint, best_val_loss, cneg_epochs = (0, 0), -1.0, 0
+    train_start_time = time()
+    stop = False
+    for n_epoch in range(config['max_n_epochs']):
+        epoch_counter += 1
+        epoch_start_time = time()
+        files = list(train_files)
+        random.shuffle(files)
+        _, train_it = manager().get_iterator(manager().get_dataset(files, shuffle=True), batch_size=per_rank_batch, n_epochs=1)
+        if rank == 0:
+            print('-> Epoch {:d}'.format(epoch_counter))
+        avg, n_step, lr = _RunningAverage(), 0, model.learning_rate
+        for batch in train_it:
+            n_step += 1
+            tot_step += 1
+            frames = feed_batch(model, batch)
+            lr = model.learning_rate
+            model.train_op()
+            log_now = (n_step % 200 == 0 or n_step == 1)
+            loss, loss_ipt, loss_ctc, per = _losses(model, log_now)
+            if np.isnan(loss):
+                print('GOT INSTABILITY: loss is NaN. Leaving...')
+                sys.exit(1)
+            if np.isinf(loss):
+                print('GOT INSTABILITY: loss is inf. Leaving...')
+                sys.exit(1)
+            tr = avg.add(frames, [loss, loss_ipt, loss_ctc, per if log_now else (avg.vals[3] if avg.vals is not None else 0.0)])
+            if rank == 0 and log_now:
+                print('Step[{:7d}] Loss[{:3.5f}|{:3.5f}|{:3.5f}] PER[{:.5f}] LR[{:.6f}] Epoch training time[{:.2f}]'
+                      .format(tot_step, tr[0], tr[1], tr[2], tr[3], lr, time() - epoch_start_time))
+            if rank == 0 and n_step % 1000 == 0:
+                print('Model checkpoint saved in file %s' % checkpoint.save(model, os.path.join(checkpoints_dir, 'ckpt')))
+            if max_steps is not None and tot_step >= max_steps:
+                stop = True
+                break
+        tr = avg.vals if avg.vals is not None else np.zeros(4)
+        epoch_duration = time() - epoch_start_time
+        if rank == 0:
+            print('Completed epoch {:d} at step {:d} --> Training loss: {:3.5f} - {:3.5f} - {:3.5f}; PER: {:3.5f}'
+                  .format(epoch_counter, tot_step, tr[0], tr[1], tr[2], tr[3]))
+            print('Epoch training time (seconds) = {:.6f}'.format(epoch_duration))
+            print('Start validation set evaluation...')
+        # ---- validation: same model, no update ----------------------------------------------------------------
+        _, val_it = manager().get_iterator(manager().get_dataset(val_files, shuffle=False), batch_size=per_rank_batch, n_epochs=1)
+        vavg, n_vstep = _RunningAverage(), 0
+        for batch in val_it:
+            n_vstep += 1
+            frames = feed_batch(model, batch)
+            va = vavg.add(frames, _losses(model, True))
+            if rank == 0 and (n_vstep % 200 == 0 or n_vstep == 1):
+                print('Step[{:7d}] Loss[{:3.5f}]'.format(n_vstep, va[1]))
+        va = vavg.vals if vavg.vals is not None else np.zeros(4)
+        if world > 1:                                            # average the validation figures over the ranks
+            t = torch.tensor(np.concatenate([va * vavg.n, [vavg.n]]), dtype=torch.float64, device=model.device)
+            dist.all_reduce(t)
+            va = (t[:4] / t[4].clamp(min=1)).cpu().numpy()
+        if rank == 0:
+            print('done.')
+            print('Validation loss: {:3.5f}; PER: {:3.5f}. Best loss so far {:2.5f} [Epoch {:d} (step {:d})]'
+                  .format(va[1], va[3], best_val_loss, best_val_checkpoint[0], best_val_checkpoint[1]))
+        if best_val_checkpoint == (0, 0) or va[1] < best_val_loss:
+            if rank == 0:
+                print('Model saved in file %s' % checkpoint.save(model, os.path.join(checkpoints_dir, 'sinet')))
+            best_val_checkpoint, best_val_loss, cneg_epochs = (epoch_counter, tot_step), va[1], 0
+        else:
+            cneg_epochs += 1
+        if rank == 0:
+            if tb is not None:
+                for tag, val in (('Training loss full', tr[0]), ('Training loss inpainting', tr[1]), ('Training loss CTC', tr[2]),
+                                 ('Training loss PER', tr[3]), ('Validation loss', va[0]), ('Validation loss inpainting', va[1]),
+                                 ('Validation loss CTC', va[2]), ('Validation loss PER', va[3])):
+                    tb.add_scalar(tag, float(val), epoch_counter)
+                tb.flush()
+            print('')
+            log.write('{:d}\t{:.6f}\t{:.6f}|{:.6f}|{:.6f}\t{:.6f}\t{:.6f}|{:.6f}|{:.6f}\t{:.6f}\t[{:.2f}]\n'
+                      .format(epoch_counter, lr, tr[0], tr[1], tr[2], tr[3], va[0], va[1], va[2], va[3], epoch_duration))
+            log.flush()
+        if stop or cneg_epochs >= config['n_earlystop_epochs']:
+            break
+    if rank == 0:
+        if cneg_epochs >= config['n_earlystop_epochs']:
+            print('+---- Done training: early stopped ----+')
+        else:
+            print('+---- Done training: epoch limit reached ----+')
+        print('Total training time: {:.2f} s'.format(time() - train_start_time))
+        print('{:d} epochs, {:d} steps.'.format(epoch_counter, tot_step))
+        print('Best validation checkpoint: {:d} ({:d}) - Loss: {:.5f}'.format(best_val_checkpoint[0], best_val_checkpoint[1],
+                                                                               best_val_loss))
+        log.close()
+    return model

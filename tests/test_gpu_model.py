@@ -243,3 +243,68 @@ def test_sgd_and_momentum_updates(opt):
             expect = expect - lr * g
         assert rel_l2(model.engine.theta.cpu().numpy(), expect.cpu().numpy()) < 1e-5
         model.feed(target_sources=batch['wav'])
+
+
+def _write_dataset(root, n_train, n_val, audio_len, seed):
+    """Synthetic GRID-like TFRecord folders + normalisation files + config file for train()."""
+    import os
+    from avsi_b200 import synth, tfrecord_io as tio
+    from oracle import video as ovideo
+    T = -(-audio_len // 192)
+    for split, n, sd in (('training-set', n_train, seed), ('validation-set', n_val, seed + 1), ('test-set', n_val, seed + 2)):
+        d = os.path.join(root, split)
+        os.makedirs(d)
+        b = synth.make_batch(n, audio_len=audio_len, seed=sd)
+        for i in range(n):
+            vid = ovideo.video_features(b['landmarks'][i].astype(np.float64), T, b['vmean'][i], b['vstd'][i])
+            rec = tio.serialize_sample_fixed(T, int(b['lab_len'][i]), b['wav'][i], vid, b['mask'][i], b['labels'][i],
+                                             '%s_%03d' % (split[:2], i))
+            tio.write_records(os.path.join(d, 'data_%05d.tfrecord' % (i + 1)), [rec])
+        np.save(os.path.join(d, 'seq_lengths.npy'), np.full(n, T))
+    np.save(os.path.join(root, 'mean.npy'), np.full(257, 6.0))
+    np.save(os.path.join(root, 'std.npy'), np.full(257, 2.0))
+    return T
+
+
+@pytest.mark.parametrize('model_name', ['av-blstm', 'av-blstm-ssnn-ctc'])
+def test_train_infer_mask_app_jobs(tmp_path, model_name, capsys):
+    """The drop-in job entry points: train(config_file) on TFRecords, checkpoint under TF names,
+    infer(...) writing enhanced wavs, mask_app(...) writing masked wavs."""
+    import os
+    from scipy.io import wavfile
+    from avsi_b200 import checkpoint, inference, masking, training
+    root = str(tmp_path / 'data')
+    os.makedirs(root)
+    audio_len = 9600
+    T = _write_dataset(root, 12, 4, audio_len, seed=40)
+    exp = str(tmp_path / 'exp' / 'run1')
+    cfg = str(tmp_path / 'blstm.config')
+    with open(cfg, 'w') as f:
+        f.write('# test config\nroot_folder = %s\nexp_folder = %s\nmodel = %s\naudio_feat_dim = 257\nvideo_feat_dim = 136\n'
+                'audio_len = %d\nbatch_size = 4\nnet_dim = [250,250,250]\nstarter_learning_rate = 0.001\nmax_n_epochs = 3\n'
+                'n_earlystop_epochs = 5\nlr_decay = 1.0\noptimizer_type = adam\nl2 = 0.0\ndropout_rate = 0.0\nctc_loss = 0.001\n'
+                'audio_feat_mean = %s\naudio_feat_std = %s\n' % (root, exp, model_name, audio_len,
+                                                                os.path.join(root, 'mean.npy'), os.path.join(root, 'std.npy')))
+    model = training.train(cfg)
+    out = capsys.readouterr().out
+    assert '+---- Done training: epoch limit reached ----+' in out and 'Model saved in file' in out
+    log = open(os.path.join(exp, 'training_log.txt')).read().splitlines()
+    rows = [l for l in log if l[:1].isdigit()]
+    assert len(rows) == 3 and rows[0].split('\t')[0] == '1'
+    first, last = float(rows[0].split('\t')[2].split('|')[0]), float(rows[-1].split('\t')[2].split('|')[0])
+    assert np.isfinite(last) and last < first                                   # the training loss went down
+    for fn in ('config.txt', 'audio_features_mean.npy', 'audio_features_std.npy', 'sinet.npz'):
+        assert os.path.exists(os.path.join(exp, 'netmodel', fn)), fn
+    ck = checkpoint.load(os.path.join(exp, 'netmodel', 'sinet'))
+    pre = model_name + '/cudnn_lstm/stack_bidirectional_rnn/cell_0/bidirectional_rnn/fw/cudnn_compatible_lstm_cell/'
+    assert ck[pre + 'kernel'].shape == (393 + 250, 1000) and ck[pre + 'kernel/Adam_1'].shape == (643, 1000)
+    assert int(ck[model_name + '/Variable']) == 9 and 'beta1_power' in ck
+    # inference job: restores sinet, writes one wav per test utterance
+    audio_out = str(tmp_path / 'audio')
+    hole = inference.infer(os.path.join(exp, 'netmodel'), os.path.join(root, 'test-set'), audio_out, 'enh', batch_size=2)
+    assert np.isfinite(hole)
+    rate, w = wavfile.read(os.path.join(audio_out, 'te_000', 'enhanced', 'enh.wav'))
+    assert rate == 16000 and w.dtype == np.int16 and len(w) == T * 192
+    assert masking.mask_app(os.path.join(root, 'test-set'), audio_out, num_audio_samples=audio_len, batch_size=4) == 4
+    rate, mw = wavfile.read(os.path.join(audio_out, 'te_003', 'masked.wav'))
+    assert len(mw) == T * 192 and np.abs(mw.astype(np.int32)).max() > 0
