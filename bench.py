@@ -143,8 +143,6 @@ def main():
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    if rank == 0:
-        __graft_entry__.build()
     torch.cuda.set_device(local_rank)
     pg = None
     if world > 1:
@@ -152,6 +150,9 @@ def main():
         if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', 'WARN'):
             os.environ.pop('NCCL_DEBUG')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    if rank == 0:
+        __graft_entry__.build()                 # no-op when the in-tree library is current; the others wait for it
+    if world > 1:
         dist.barrier()
         pg = dist.group.WORLD
     from avsi_b200 import _lib, av_sync, models, synth
