@@ -317,6 +317,15 @@ __global__ void __launch_bounds__(FE_THREADS, 2) frontend_train_kernel(avsi_fron
 #pragma unroll
       for (int m = 0; m < 17; ++m) mv[m] = 1.f;
     }
+    // video row of this frame (the second input stream): same early request
+    float vv[9];
+    if (HAS_VIDEO) {
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+        const int c = q + 16 * i;
+        vv[i] = (live && c < p.V) ? __ldg(p.video + row_bt * p.V + c) : 0.f;
+      }
+    }
     // ---- window; samples 384..511 are zero ----------------------------------------------------------------
     cpx v[16];
 #pragma unroll
@@ -373,8 +382,16 @@ __global__ void __launch_bounds__(FE_THREADS, 2) frontend_train_kernel(avsi_fron
     }
     if (live) {
       if (HAS_VIDEO) {
-        const float* vs = p.video + row_bt * p.V;
-        for (int c = q; c < p.V; c += 16) xrow[257 + c] = __half_as_ushort(__float2half_rn(__ldg(vs + c)));
+        if (p.V <= 144) {
+#pragma unroll
+          for (int i = 0; i < 9; ++i) {
+            const int c = q + 16 * i;
+            if (c < p.V) xrow[257 + c] = __half_as_ushort(__float2half_rn(vv[i]));
+          }
+        } else {
+          const float* vs = p.video + row_bt * p.V;
+          for (int c = q; c < p.V; c += 16) xrow[257 + c] = __half_as_ushort(__float2half_rn(__ldg(vs + c)));
+        }
       }
       for (int c = 257 + (HAS_VIDEO ? p.V : 0) + q; c < p.ldx; c += 16) xrow[c] = 0;
     }
