@@ -169,12 +169,16 @@ class StackedBLSTMModel(object):
         return self._bt(0, self.audio_feat_dim)
 
     # ---- loss (models.py:127-159) --------------------------------------------------------------------
-    def _loss_pass(self, want_grad):
-        key = 'loss_grad' if want_grad else 'loss'
-        if key in self._cache:
-            return self._cache[key]
-        if 'loss_grad' in self._cache:
-            return self._cache['loss_grad']
+    def _loss_pass(self, want_grad, want_pred=True):
+        """One launch of the loss kernel(s).  The training step asks for gradients only (want_pred=False): the
+        [B,T,F] prediction tensor is then not written (a fifth of the kernel's HBM traffic)."""
+        for key in (('loss_grad', 'loss_grad_nopred') if want_grad else ('loss', 'loss_grad')):
+            c = self._cache.get(key)
+            if c is not None and (c['prediction'] is not None or not want_pred):
+                return c
+        key = ('loss_grad' if want_pred else 'loss_grad_nopred') if want_grad else 'loss'
+        if not want_grad and not want_pred and 'loss_grad_nopred' in self._cache:
+            return self._cache['loss_grad_nopred']
         lib = _lib.load()
         fr = self._front()
         ws, B, T = fr['ws'], fr['B'], fr['T']
@@ -183,7 +187,7 @@ class StackedBLSTMModel(object):
         masks, seq = self._need('masks', 'sequence_lengths')
         L = self.engine.layout
         self._sums.zero_()
-        pred = torch.empty(B, T, F, dtype=torch.float32, device=self.device)
+        pred = torch.empty(B, T, F, dtype=torch.float32, device=self.device) if want_pred else None
         out = {'prediction': pred}
         scales = None
         if self.MTL:
@@ -225,7 +229,7 @@ class StackedBLSTMModel(object):
         return self._loss_pass(False)['prediction']
 
     def _sum(self, i):
-        return self._loss_pass(False)['sums'][i]
+        return self._loss_pass(False, want_pred=False)['sums'][i]
 
     @property
     def loss_hole(self):
@@ -265,7 +269,7 @@ class StackedBLSTMModel(object):
         """forward + loss + backward; leaves the (scaled) gradient in engine.grad."""
         if not self.is_training:
             raise _lib.AvsiError('model was built with is_training=False')
-        out = self._loss_pass(True)
+        out = self._loss_pass(True, want_pred=False)
         self.engine.backward(self._front()['ws'])
         return out
 
@@ -370,7 +374,7 @@ class StackedBLSTMSSNNCTCLossModel(StackedBLSTMModel):
 
     @property
     def ctc_loss(self):
-        return self._loss_pass(False)['ctc_nll'].mean()                   # models.py:1950-1953
+        return self._loss_pass(False, want_pred=False)['ctc_nll'].mean()   # models.py:1950-1953
 
     @property
     def loss_func(self):

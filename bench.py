@@ -217,7 +217,7 @@ def main():
         model.train_op()
         freed[sl].record(cur)
         n = model.engine.layout.n_params_padded
-        src = model.engine.grad[n + 4:n + 5].double() if pg is not None else model._loss_pass(True)['sums'][4:5]
+        src = model.engine.grad[n + 4:n + 5].double() if pg is not None else model._loss_pass(True, want_pred=False)['sums'][4:5]
         if i > 0:                                             # read the previous step's loss (already on the host)
             loss_evt[1 - sl].synchronize()
             e2e_state['losses'].append(float(loss_pin[1 - sl]))
