@@ -70,6 +70,7 @@ SIGNATURES = {
                              c_int, c_float, c_void_p, c_float, c_void_p]),
     'avsi_sgd_momentum': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double, c_float, c_void_p, c_float,
                                   c_void_p]),
+    'avsi_cast_to_f32': (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p]),
     'avsi_cast_weights': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
 }
 

@@ -64,6 +64,24 @@ cast_weights_kernel(const float* __restrict__ w, int R, int C, uint16_t* __restr
   }
 }
 
+// Host-side batches may arrive in their storage dtypes (int16 samples as in target.wav, int32 as dataset_reader.py:78
+// yields them, uint8 {0,1} masks): widened to the fp32 tensors of the feed contract on the device, so the PCIe copy
+// moves 2 / 1 bytes per element instead of 4.
+template <typename S>
+__global__ void __launch_bounds__(256) cast_to_f32_kernel(const S* __restrict__ src, long long n, float* __restrict__ dst) {
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += (long long)gridDim.x * blockDim.x * 4) {
+    if (i + 3 < n) {
+      float4 v = make_float4((float)src[i], (float)src[i + 1], (float)src[i + 2], (float)src[i + 3]);
+      if (((uintptr_t)(dst + i) & 15) == 0) *reinterpret_cast<float4*>(dst + i) = v;
+      else {
+        dst[i] = v.x; dst[i + 1] = v.y; dst[i + 2] = v.z; dst[i + 3] = v.w;
+      }
+    } else {
+      for (long long k = i; k < n; ++k) dst[k] = (float)src[k];
+    }
+  }
+}
+
 __global__ void mtl_scales_kernel(const float* __restrict__ hole_count, int B, float ctc_w, float* __restrict__ out) {
   // out[0] = S  (scale of the L1 dlogits), out[1] = S * (w/B) * holes (scale of the CTC dlogits),
   // out[2] = 1 / (S * holes)  (optimiser unscale), out[3] = holes
@@ -103,6 +121,19 @@ extern "C" int avsi_sgd_momentum(float* theta, const float* g, float* accum, int
   int blocks = (int)min((long long)(n + 255) / 256, (long long)num_sms() * 8);
   sgd_momentum_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(theta, g, accum, (long long)n, (float)lr, (float)momentum,
                                                                grad_unscale, grad_unscale_dev, l2);
+  AVSI_LAUNCH_CHECK();
+  return AVSI_OK;
+}
+
+extern "C" int avsi_cast_to_f32(const void* src, int src_type, int64_t n, float* dst, void* stream) {
+  using namespace avsi;
+  AVSI_REQUIRE(src && dst && n > 0, "args");
+  AVSI_REQUIRE(src_type >= 0 && src_type <= 2, "src_type: 0 = int16, 1 = uint8, 2 = int32");
+  int blocks = (int)min((long long)(n / 4 + 255) / 256 + 1, (long long)num_sms() * 16);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (src_type == 0) cast_to_f32_kernel<int16_t><<<blocks, 256, 0, st>>>((const int16_t*)src, (long long)n, dst);
+  else if (src_type == 1) cast_to_f32_kernel<uint8_t><<<blocks, 256, 0, st>>>((const uint8_t*)src, (long long)n, dst);
+  else cast_to_f32_kernel<int32_t><<<blocks, 256, 0, st>>>((const int32_t*)src, (long long)n, dst);
   AVSI_LAUNCH_CHECK();
   return AVSI_OK;
 }

@@ -71,16 +71,29 @@ class StackedBLSTMModel(object):
         self._sums = torch.zeros(8, dtype=torch.float64, device=self.device)
         self._cache = {}
         self._fed = {}
+        self._widen = {}
         self.feed(sequence_lengths=sequence_lengths, target_sources=target_sources, masks=masks,
                   audio_features_mean=audio_feat_mean, audio_features_std=audio_feat_std,
                   dropout_rate=dropout_rate, video_features=video_features)
 
     # ---- feed contract (training_ctc.py:67-77, 264-275) -------------------------------------------
-    def _to_dev(self, x, dtype):
+    _COMPACT = {torch.int16: 0, torch.uint8: 1, torch.bool: 1, torch.int32: 2}
+
+    def _to_dev(self, x, dtype, name=None):
         if x is None:
             return None
         if not torch.is_tensor(x):
             x = torch.as_tensor(np.asarray(x))
+        if dtype == torch.float32 and x.dtype in self._COMPACT:
+            # storage dtypes (int16 / int32 samples, uint8 masks) cross PCIe as they are and are widened on the device
+            src = x.view(torch.uint8) if x.dtype == torch.bool else x
+            src = src.to(device=self.device, non_blocking=True).contiguous()
+            buf = self._widen.get(name)
+            if buf is None or buf.shape != src.shape:
+                buf = self._widen[name] = torch.empty(src.shape, dtype=torch.float32, device=self.device)
+            _lib.check(_lib.load().avsi_cast_to_f32(_p(src), self._COMPACT[x.dtype], src.numel(), _p(buf), _lib.stream_ptr()),
+                       'avsi_cast_to_f32')
+            return buf
         return x.to(device=self.device, dtype=dtype, non_blocking=True).contiguous()
 
     def feed(self, **kw):
@@ -91,7 +104,7 @@ class StackedBLSTMModel(object):
             if v is None:
                 continue
             if k in f32:
-                self._fed[k] = self._to_dev(v, torch.float32)
+                self._fed[k] = self._to_dev(v, torch.float32, k)
             elif k in i32:
                 self._fed[k] = self._to_dev(v, torch.int32)
             elif k == 'dropout_rate':

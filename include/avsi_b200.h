@@ -198,6 +198,9 @@ int avsi_adam_tf(float* theta, const float* g, float* m, float* v, int64_t n, do
  * accum = momentum * accum + g ; theta -= lr * accum.  lr is the (host-evaluated) staircase exponential decay. */
 int avsi_sgd_momentum(float* theta, const float* g, float* accum, int64_t n, double lr, double momentum,
                       float grad_unscale, const float* grad_unscale_dev, float l2, void* stream);
+/* Widen a batch that was copied to the device in its storage dtype (src_type 0 = int16 samples, 1 = uint8 masks,
+ * 2 = int32 samples as dataset_reader.py:78 yields them) to the fp32 tensor of the feed contract (training.py:69-71). */
+int avsi_cast_to_f32(const void* src, int src_type, int64_t n, float* dst, void* stream);
 /* fp32 -> fp16 copies of a weight matrix W [R,C]: w16 [R,C] and (optional) w16t [C,R]. */
 int avsi_cast_weights(const float* w, int R, int C, uint16_t* w16, uint16_t* w16t, void* stream);
 

@@ -308,3 +308,13 @@ def test_train_infer_mask_app_jobs(tmp_path, model_name, capsys):
     assert masking.mask_app(os.path.join(root, 'test-set'), audio_out, num_audio_samples=audio_len, batch_size=4) == 4
     rate, mw = wavfile.read(os.path.join(audio_out, 'te_003', 'masked.wav'))
     assert len(mw) == T * 192 and np.abs(mw.astype(np.int32)).max() > 0
+
+
+def test_feed_accepts_storage_dtypes():
+    """int16 / int32 samples and uint8 / bool masks are widened on the device: identical results to the fp32 feed."""
+    model, batch, canon, inp = _build('av-blstm', 3, 4800, seed=4)
+    ref = model.prediction.cpu().numpy().copy()
+    for wav_dt, mask_dt in ((np.int16, np.uint8), (np.int32, np.bool_)):
+        model.feed(target_sources=batch['wav'].astype(wav_dt), masks=batch['mask'].astype(mask_dt))
+        assert model._fed['target_sources'].dtype == torch.float32 and model._fed['masks'].dtype == torch.float32
+        assert np.array_equal(model.prediction.cpu().numpy(), ref)
