@@ -17,9 +17,9 @@ struct LerpPos {
   float w;
 };
 __device__ __forceinline__ LerpPos lerp_pos(int t, int L, int T) {
-  const long long num = (long long)t * L;
-  int i0 = (int)(num / T);
-  float w = (float)(num - (long long)i0 * T) / (float)T;
+  const unsigned num = (unsigned)t * (unsigned)L;            // t < T, T * L < 2^31 checked by the launcher
+  int i0 = (int)(num / (unsigned)T);
+  float w = (float)(num - (unsigned)i0 * (unsigned)T) / (float)T;
   if (i0 >= L - 1) {
     i0 = L - 1;
     w = 0.f;
@@ -32,11 +32,16 @@ __global__ void __launch_bounds__(256)
 video_features_kernel(const float* __restrict__ lm, const float* __restrict__ vmean, const float* __restrict__ vstd,
                       int B, int L, int D, int T, float* __restrict__ out) {
   const int dv = D / VEC;                            // vectors per frame
-  const long long n = (long long)B * T * dv;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int bt = (int)(idx / dv);
-    const int d = (int)(idx - (long long)bt * dv) * VEC;
+  // one frame (b, t) per group of `dv` consecutive threads of a block row: 32-bit index arithmetic only
+  const int frames_per_block = blockDim.x / dv;
+  const int fl = threadIdx.x / dv;
+  if (fl >= frames_per_block) return;
+  const int d = (threadIdx.x - fl * dv) * VEC;
+  const long long total = (long long)B * T;
+  for (long long bt0 = (long long)blockIdx.x * frames_per_block; bt0 < total; bt0 += (long long)gridDim.x * frames_per_block) {
+    const long long btl = bt0 + fl;
+    if (btl >= total) break;
+    const int bt = (int)btl;
     const int b = bt / T, t = bt - b * T;
     const float* src = lm + (long long)b * L * D + d;
     float mv[VEC];
@@ -91,9 +96,12 @@ extern "C" int avsi_video_features(const float* landmarks, const float* vmean, c
   using namespace avsi;
   AVSI_REQUIRE(landmarks && vmean && vstd && out, "null pointer");
   AVSI_REQUIRE(B > 0 && L > 0 && D > 0 && T > 0, "sizes");
+  AVSI_REQUIRE((long long)T * L < (1LL << 31) && (long long)B * T < (1LL << 31), "T * L and B * T must fit 31 bits");
   const bool vec = (D % 4 == 0) && ((uintptr_t)landmarks % 16 == 0) && ((uintptr_t)out % 16 == 0);
-  long long n = (long long)B * T * (vec ? D / 4 : D);
-  int blocks = (int)min((n + 255) / 256, (long long)num_sms() * 16);
+  const int dvh = vec ? D / 4 : D;
+  AVSI_REQUIRE(dvh <= 256, "D too large");
+  long long n = ((long long)B * T + (256 / dvh) - 1) / (256 / dvh);
+  int blocks = (int)min(n, (long long)num_sms() * 16);
   if (vec)
     video_features_kernel<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(landmarks, vmean, vstd, B, L, D, T, out);
   else
