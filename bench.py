@@ -172,13 +172,21 @@ def main():
         with _lib.span('video_features'):
             return av_sync.video_pipeline(src['landmarks'], T, src['vmean'], src['vstd'], device=dev)
 
-    model = models.StackedBLSTMModel(res['seq_len'], res['wav'], res['mask'], res['mean'], res['std'], 0.0, cfg,
-                                     video_features=video_of(res), input='av', is_training=True, device=dev,
-                                     process_group=pg)
+    cls, inp = models.MODEL_REGISTRY[args.model]
+    mtl = {}
+    if cls.MTL:                                   # configs[2]: AV-MTL-SI, joint CTC phone head (labels stay resident)
+        mtl = {'labels': torch.from_numpy(host['labels']).to(dev), 'lab_len': torch.from_numpy(host['lab_len']).to(dev)}
+        model = cls(res['seq_len'], mtl['lab_len'], res['wav'], res['mask'], mtl['labels'], res['mean'], res['std'], 0.0, cfg,
+                    video_features=video_of(res) if inp != 'a' else None, input=inp, is_training=True, device=dev,
+                    process_group=pg)
+    else:
+        model = cls(res['seq_len'], res['wav'], res['mask'], res['mean'], res['std'], 0.0, cfg,
+                    video_features=video_of(res) if inp != 'a' else None, input=inp, is_training=True, device=dev,
+                    process_group=pg)
 
     def step_resident():
         model.feed(sequence_lengths=res['seq_len'], target_sources=res['wav'], masks=res['mask'],
-                   video_features=video_of(res))
+                   video_features=video_of(res) if inp != 'a' else None)
         model.train_op()
 
     # ---- end-to-end step: every step's inputs come from pinned HOST buffers (H2D inside the timed region) and
@@ -223,7 +231,8 @@ def main():
         e2e_prefetch(i + 1)                                   # next step's H2D overlaps this step's kernels
         cur.wait_event(ready[sl])
         d = stage[sl]
-        model.feed(sequence_lengths=d['seq_len'], target_sources=d['wav'], masks=d['mask'], video_features=video_of(d))
+        model.feed(sequence_lengths=d['seq_len'], target_sources=d['wav'], masks=d['mask'],
+                   video_features=video_of(d) if inp != 'a' else None)
         model.train_op()
         freed[sl].record(cur)
         n = model.engine.layout.n_params_padded
