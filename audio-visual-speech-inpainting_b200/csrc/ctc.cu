@@ -29,7 +29,7 @@ ctc_kernel(const float* __restrict__ logits, int ldl, int col0, int C, const int
   __shared__ int ext[CTC_MAX_S];
   __shared__ unsigned char skip[CTC_MAX_S];
   __shared__ float st[2][CTC_MAX_S];
-  __shared__ float ab[CTC_MAX_S];
+  __shared__ float post[CTC_MAX_C];
   __shared__ float ll_sh;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int blank = C - 1;
@@ -42,6 +42,7 @@ ctc_kernel(const float* __restrict__ logits, int ldl, int col0, int C, const int
   float* alpha = ws_alpha + (long long)b * T * Smax;
 
   for (int s = tid; s < S; s += CTC_THREADS) ext[s] = (s & 1) ? labels[b * Lmax + (s >> 1)] : blank;
+  for (int c = tid; c < CTC_MAX_C; c += CTC_THREADS) post[c] = 0.f;
   __syncthreads();
   for (int s = tid; s < S; s += CTC_THREADS) skip[s] = (s >= 2 && ext[s] != blank && ext[s] != ext[s - 2]) ? 1 : 0;
 
@@ -79,14 +80,28 @@ ctc_kernel(const float* __restrict__ logits, int ldl, int col0, int C, const int
     alpha[s] = a;
   }
   __syncthreads();
+  // The recursions are a dependent chain of Tb steps: the global (L2) operands of step t+1 are requested during
+  // step t so that only shared-memory latency sits on the chain.  S <= 8 * CTC_THREADS (Lmax limit) -> <= 8 states per thread.
+  constexpr int SPT = CTC_MAX_S / CTC_THREADS;
+  float lp_next[SPT];
+#pragma unroll
+  for (int i = 0; i < SPT; ++i) {
+    const int s = tid + i * CTC_THREADS;
+    lp_next[i] = (s < S && Tb > 1) ? logp[C + ext[s]] : 0.f;
+  }
   for (int t = 1; t < Tb; ++t) {
     const float* prev = st[(t - 1) & 1];
     float* cur = st[t & 1];
-    for (int s = tid; s < S; s += CTC_THREADS) {
+#pragma unroll
+    for (int i = 0; i < SPT; ++i) {
+      const int s = tid + i * CTC_THREADS;
+      if (s >= S) break;
+      const float lp = lp_next[i];
+      if (t + 1 < Tb) lp_next[i] = logp[(t + 1) * C + ext[s]];
       float a = prev[s];
       if (s >= 1) a = lse2(a, prev[s - 1]);
       if (skip[s]) a = lse2(a, prev[s - 2]);
-      a = (a <= CTC_NEG) ? CTC_NEG : a + logp[t * C + ext[s]];
+      a = (a <= CTC_NEG) ? CTC_NEG : a + lp;
       cur[s] = a;
       alpha[(long long)t * Smax + s] = a;
     }
@@ -103,10 +118,28 @@ ctc_kernel(const float* __restrict__ logits, int ldl, int col0, int C, const int
   if (!dlogits) return;
 
   // ---- beta + gradient -------------------------------------------------------------------
+  float al_next[SPT], lpc_next = 0.f;               // operands of the next (earlier) frame, requested one step ahead
+#pragma unroll
+  for (int i = 0; i < SPT; ++i) {
+    const int s = tid + i * CTC_THREADS;
+    lp_next[i] = (s < S) ? logp[(Tb - 1) * C + ext[s]] : 0.f;
+    al_next[i] = (s < S) ? alpha[(long long)(Tb - 1) * Smax + s] : 0.f;
+  }
+  if (tid < C) lpc_next = logp[(Tb - 1) * C + tid];
   for (int t = Tb - 1; t >= 0; --t) {
     float* cur = st[t & 1];
     const float* nxt = st[(t + 1) & 1];
-    for (int s = tid; s < S; s += CTC_THREADS) {
+    const float lpc = lpc_next;
+    if (t > 0 && tid < C) lpc_next = logp[(t - 1) * C + tid];
+#pragma unroll
+    for (int i = 0; i < SPT; ++i) {
+      const int s = tid + i * CTC_THREADS;
+      if (s >= S) break;
+      const float lp = lp_next[i], al = al_next[i];
+      if (t > 0) {
+        lp_next[i] = logp[(t - 1) * C + ext[s]];
+        al_next[i] = alpha[(long long)(t - 1) * Smax + s];
+      }
       float bt;
       if (t == Tb - 1) {
         bt = (s == S - 1 || s == S - 2) ? 0.f : CTC_NEG;
@@ -115,29 +148,19 @@ ctc_kernel(const float* __restrict__ logits, int ldl, int col0, int C, const int
         if (s + 1 < S) bt = lse2(bt, nxt[s + 1]);
         if (s + 2 < S && skip[s + 2]) bt = lse2(bt, nxt[s + 2]);
       }
-      bt = (bt <= CTC_NEG) ? CTC_NEG : bt + logp[t * C + ext[s]];
+      bt = (bt <= CTC_NEG) ? CTC_NEG : bt + lp;
       cur[s] = bt;
-      ab[s] = alpha[(long long)t * Smax + s] + bt;
+      // posterior mass of state s: alpha * beta / (y_t(ext_s) * p(l|x)); alpha*beta counts y_t twice -> subtract lp once.
+      // It is a probability (<= 1): no max-shift needed; scattered into its class with a shared-memory atomic.
+      const float e = al + bt - lp - ll;
+      if (feasible && al > CTC_NEG && bt > CTC_NEG) atomicAdd(&post[ext[s]], __expf(fminf(e, 0.f)));
     }
     __syncthreads();
-    // class posterior: thread c sums the positions that carry class c
+    // gradient of the NLL wrt the logits: softmax - posterior
     for (int c = tid; c < C; c += CTC_THREADS) {
-      float mx = CTC_NEG;
-      for (int s = (c == blank) ? 0 : 1; s < S; s += 2)
-        if (ext[s] == c) mx = fmaxf(mx, ab[s]);
-      float grad;
-      const float lp = logp[t * C + c];
-      if (!feasible) {
-        grad = 0.f;
-      } else if (mx <= -1e29f) {
-        grad = expf(lp);
-      } else {
-        float sum = 0.f;
-        for (int s = (c == blank) ? 0 : 1; s < S; s += 2)
-          if (ext[s] == c) sum += expf(ab[s] - mx);
-        // alpha*beta counts y_t(c) twice -> subtract lp once
-        grad = expf(lp) - expf(mx + logf(sum) - lp - ll);
-      }
+      const float lp = (c == tid) ? lpc : logp[t * C + c];
+      const float grad = feasible ? (__expf(lp) - post[c]) : 0.f;
+      post[c] = 0.f;
       dlogits[((long long)t * B + b) * ldd + dcol0 + c] = __half_as_ushort(__float2half_rn(scale * grad));
     }
     __syncthreads();
