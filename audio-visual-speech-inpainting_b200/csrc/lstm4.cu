@@ -73,14 +73,14 @@ __device__ __forceinline__ float act_tanh(float x) {
 __device__ unsigned long long g_l4_timing[16];
 #define L4_TICK(i)                                         \
   do {                                                     \
-    if (timing) {                                          \
+    if (TIMING && timing) {                                \
       const long long now_ = clock64();                    \
       tacc[i] += (unsigned long long)(now_ - tprev);       \
       tprev = now_;                                        \
     }                                                      \
   } while (0)
 
-template <int ACT>
+template <int ACT, bool TIMING>
 __global__ void __cluster_dims__(L4_CL, 1, 1) __launch_bounds__(L4_THREADS, 1)
 lstm4_fwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whh, const float* __restrict__ bias,
                  uint16_t* __restrict__ y, float* __restrict__ cst, int T, int B) {
@@ -131,7 +131,7 @@ lstm4_fwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whh,
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&sm.tmem_slot);
   cluster_sync_all();                               // every CTA's barriers are initialised and armed
-  const bool timing = (blockIdx.x == 0) && (tid == 0 || tid == L4_CWARPS * 32);
+  const bool timing = TIMING && (blockIdx.x == 0) && (tid == 0 || tid == L4_CWARPS * 32);
   unsigned long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long tprev = clock64();
 
@@ -297,23 +297,29 @@ lstm4_fwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whh,
 
 int launch_lstm4_fwd(uint16_t* gates, const uint16_t* whh, const float* bias, uint16_t* y, float* cst, int T, int B,
                      cudaStream_t st) {
-  static int act_mode = -1;
-  if (act_mode < 0) {
+  // AVSI_LSTM_ACT=exact: ex2/rcp activations; AVSI_L4_TIMING=1: in-kernel phase timers (profiles/bench_lstm.py)
+  static int mode = -1;
+  if (mode < 0) {
     const char* e = getenv("AVSI_LSTM_ACT");
-    act_mode = (e && !strcmp(e, "exact")) ? 1 : 0;
+    const char* t = getenv("AVSI_L4_TIMING");
+    mode = ((e && !strcmp(e, "exact")) ? 1 : 0) | ((t && t[0] == '1') ? 2 : 0);
   }
   const int smem = (int)sizeof(Lstm4Smem) + 128;
-  static bool attr_done = false;
-  if (!attr_done) {
-    AVSI_CUDA(cudaFuncSetAttribute(lstm4_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    AVSI_CUDA(cudaFuncSetAttribute(lstm4_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_done = true;
-  }
   const int grid = 2 * ((B + L4_BT - 1) / L4_BT) * L4_CL;
-  if (act_mode == 1)
-    lstm4_fwd_kernel<1><<<grid, L4_THREADS, smem, st>>>(gates, whh, bias, y, cst, T, B);
-  else
-    lstm4_fwd_kernel<0><<<grid, L4_THREADS, smem, st>>>(gates, whh, bias, y, cst, T, B);
+  static bool attr_done[4] = {false, false, false, false};
+#define L4_LAUNCH(ACT_, TIM_)                                                                                          \
+  do {                                                                                                                 \
+    if (!attr_done[mode]) {                                                                                            \
+      AVSI_CUDA(cudaFuncSetAttribute(lstm4_fwd_kernel<ACT_, TIM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+      attr_done[mode] = true;                                                                                          \
+    }                                                                                                                  \
+    lstm4_fwd_kernel<ACT_, TIM_><<<grid, L4_THREADS, smem, st>>>(gates, whh, bias, y, cst, T, B);                      \
+  } while (0)
+  if (mode == 0) L4_LAUNCH(0, false);
+  else if (mode == 1) L4_LAUNCH(1, false);
+  else if (mode == 2) L4_LAUNCH(0, true);
+  else L4_LAUNCH(1, true);
+#undef L4_LAUNCH
   AVSI_LAUNCH_CHECK();
   return AVSI_OK;
 }

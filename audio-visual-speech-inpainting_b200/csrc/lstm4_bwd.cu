@@ -55,13 +55,14 @@ struct Lstm4BwdSmem {
 __device__ unsigned long long g_b4_timing[24];
 #define B4_TICK(i)                                         \
   do {                                                     \
-    if (timing) {                                          \
+    if (TIMING && timing) {                                \
       const long long now_ = clock64();                    \
       tacc[i] += (unsigned long long)(now_ - tprev);       \
       tprev = now_;                                        \
     }                                                      \
   } while (0)
 
+template <bool TIMING>
 __global__ void __cluster_dims__(B4_CL, 1, 1) __launch_bounds__(B4_THREADS, 1)
 lstm4_bwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whhT, const float* __restrict__ cst,
                  const uint16_t* __restrict__ dy, float* __restrict__ dbias, int T, int B) {
@@ -118,7 +119,7 @@ lstm4_bwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whhT
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&sm.tmem_slot);
   cluster_sync_all();
-  const bool timing = (blockIdx.x == 0) && (tid == 0 || tid == B4_CWARPS * 32);
+  const bool timing = TIMING && (blockIdx.x == 0) && (tid == 0 || tid == B4_CWARPS * 32);
   unsigned long long tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   long long tprev = clock64();
 
@@ -408,14 +409,23 @@ lstm4_bwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whhT
 
 int launch_lstm4_bwd(uint16_t* gates, const uint16_t* whhT, const float* cst, const uint16_t* dy, float* dbias, int T,
                      int B, cudaStream_t st) {
+  static int timing = -1;               // AVSI_B4_TIMING=1: in-kernel phase timers (profiles/bench_lstm.py)
+  if (timing < 0) {
+    const char* t = getenv("AVSI_B4_TIMING");
+    timing = (t && t[0] == '1') ? 1 : 0;
+  }
   const int smem = (int)sizeof(Lstm4BwdSmem) + 128;
   static bool attr_done = false;
   if (!attr_done) {
-    AVSI_CUDA(cudaFuncSetAttribute(lstm4_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    AVSI_CUDA(cudaFuncSetAttribute(lstm4_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    AVSI_CUDA(cudaFuncSetAttribute(lstm4_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_done = true;
   }
   const int grid = 2 * ((B + B4_BT - 1) / B4_BT) * B4_CL;
-  lstm4_bwd_kernel<<<grid, B4_THREADS, smem, st>>>(gates, whhT, cst, dy, dbias, T, B);
+  if (timing)
+    lstm4_bwd_kernel<true><<<grid, B4_THREADS, smem, st>>>(gates, whhT, cst, dy, dbias, T, B);
+  else
+    lstm4_bwd_kernel<false><<<grid, B4_THREADS, smem, st>>>(gates, whhT, cst, dy, dbias, T, B);
   AVSI_LAUNCH_CHECK();
   return AVSI_OK;
 }
