@@ -441,7 +441,7 @@ int launch_lstm4_fwd(uint16_t* gates, const uint16_t* whh, const float* bias, ui
 // which forward kernel: tcgen05 (128-row tiles) once the batch no longer fits 16-row mma.sync tiles
 // in one wave of clusters.  AVSI_LSTM_FWD=mma|tc overrides (A/B measurements only).
 // returns 0 = mma.sync register-resident kernel (small batches: 16-row tiles, shortest step), 2 = tcgen05 4-CTA
-// kernel (lstm4.cu).  AVSI_LSTM_FWD=mma|l4 overrides (A/B measurements only).
+// kernel (lstm4.cu).  AVSI_LSTM_FWD=mma|l4 overrides (A/B measurements and tests).
 static int fwd_kernel_choice(int B) {
   static int mode = -1;
   if (mode < 0) {
@@ -450,7 +450,7 @@ static int fwd_kernel_choice(int B) {
   }
   if (mode == 1) return 0;
   if (mode == 3) return 2;
-  return pick_bt(B) > 16 ? 2 : 0;
+  return pick_bt(B) > 32 ? 2 : 0;      // measured crossover: 16/32-row mma.sync tiles win while they fit one wave (B <= 224)
 }
 
 }  // namespace avsi
@@ -487,7 +487,7 @@ extern "C" int avsi_lstm_bwd(uint16_t* gates, const uint16_t* whhT, const float*
     const char* e = getenv("AVSI_LSTM_BWD");
     bmode = (e && !strcmp(e, "mma")) ? 1 : ((e && !strcmp(e, "l4")) ? 2 : 0);
   }
-  if (bmode == 2 || (bmode == 0 && bt > 16)) return launch_lstm4_bwd(gates, whhT, cst, dy, dbias, T, B, st);
+  if (bmode == 2 || (bmode == 0 && bt > 32)) return launch_lstm4_bwd(gates, whhT, cst, dy, dbias, T, B, st);
   if (bt == 16) return launch_bwd<16>(gates, whhT, cst, dy, dbias, T, B, st);
   if (bt == 32) return launch_bwd<32>(gates, whhT, cst, dy, dbias, T, B, st);
   return launch_bwd<64>(gates, whhT, cst, dy, dbias, T, B, st);

@@ -436,7 +436,7 @@ def _lstm_reference(P, Whh, bias, R):
     return Y.detach().numpy(), C.detach().numpy(), G.detach().numpy(), Pt.grad.numpy(), bt.grad.numpy()
 
 
-@pytest.mark.parametrize('T,B', [(6, 16), (9, 5), (40, 37), (12, 130), (7, 300), (2, 128), (1, 200)])
+@pytest.mark.parametrize('T,B', [(6, 16), (9, 5), (40, 37), (12, 130), (7, 300), (2, 128), (1, 200), (5, 225), (3, 257), (1, 400)])
 def test_lstm_recurrence_fwd_bwd(T, B):
     from avsi_b200 import _lib
     lib = _lib.load()
