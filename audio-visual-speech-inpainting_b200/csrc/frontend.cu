@@ -255,7 +255,7 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-template <bool HAS_VIDEO>
+template <bool HAS_VIDEO, bool HOLES>
 __global__ void __launch_bounds__(FE_THREADS, 2) frontend_train_kernel(avsi_frontend_args p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FrontendTrainSmem& sm = *reinterpret_cast<FrontendTrainSmem*>(smem_raw);
@@ -307,15 +307,20 @@ __global__ void __launch_bounds__(FE_THREADS, 2) frontend_train_kernel(avsi_fron
     const int t = live ? (int)(g - (long long)b * p.T) : 0;
     const long long row_bt = g, row_tb = (long long)t * p.B + b;
     // mask row of this frame: requested now, used after the transform
-    float mv[17];
+    // thread q owns the bin pairs (k, 256 - k), k = q + 16 m, m = 0..7 (+ the self-mirrored bin 128 for q == 0):
+    // X[k] = E + W O and X[256 - k] = conj(E - W O) share Z[k], Z[256 - k] and the twiddle product
+    float mva[8], mvb[8], mv128 = 1.f;
     if (live) {
       const float* mrow = p.mask + row_bt * 257;
 #pragma unroll
-      for (int m = 0; m < 16; ++m) mv[m] = __ldg(mrow + q + 16 * m);
-      mv[16] = (q == 0) ? __ldg(mrow + 256) : 1.f;
+      for (int m = 0; m < 8; ++m) {
+        mva[m] = __ldg(mrow + q + 16 * m);
+        mvb[m] = __ldg(mrow + 256 - q - 16 * m);
+      }
+      if (q == 0) mv128 = __ldg(mrow + 128);
     } else {
 #pragma unroll
-      for (int m = 0; m < 17; ++m) mv[m] = 1.f;
+      for (int m = 0; m < 8; ++m) mva[m] = mvb[m] = 1.f;
     }
     // video row of this frame (the second input stream): same early request
     float vv[9];
@@ -339,8 +344,9 @@ __global__ void __launch_bounds__(FE_THREADS, 2) frontend_train_kernel(avsi_fron
     for (int n1 = 12; n1 < 16; ++n1) v[n1] = cpx{0.f, 0.f};
     fft16<false>(v);
     float2* xc = sm.xch[fl];
+    xc[q] = make_float2(v[0].x, v[0].y);                       // W256^0 = 1
 #pragma unroll
-    for (int k1 = 0; k1 < 16; ++k1) {
+    for (int k1 = 1; k1 < 16; ++k1) {
       const float2 w = sm.tw1[k1][q];
       const cpx r = cmul(v[k1], cpx{w.x, w.y});
       xc[k1 * FE_XROW + q] = make_float2(r.x, r.y);
@@ -359,26 +365,33 @@ __global__ void __launch_bounds__(FE_THREADS, 2) frontend_train_kernel(avsi_fron
     // ---- real-FFT split + |.| + log + normalise + mask ------------------------------------------------------------
     float* srow = p.spec_out + row_bt * 257;
     uint16_t* xrow = p.xh_out + row_tb * p.ldx;
-#pragma unroll
-    for (int m = 0; m < 17; ++m) {
-      if (m == 16 && q != 0) break;
-      const int k = (m < 16) ? (q + 16 * m) : 256;
-      const float2 zk = xc[k & 255], zn = xc[(256 - k) & 255];
-      const cpx e = {0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y)};
-      const cpx d = {0.5f * (zk.x - zn.x), 0.5f * (zk.y + zn.y)};
-      const cpx o = {d.y, -d.x};
-      const float2 w = sm.tw[k];
-      const cpx X = cadd(e, cmul(o, cpx{w.x, w.y}));
+    auto emit = [&](int k, float xr, float xi, float mval) {
+      // |X| = sqrt(0.25 (xr^2 + xi^2)) for the un-halved sums; log; normalise; mask; fp32 target + fp16 network input
       float mag, lg;
-      asm("sqrt.approx.f32 %0, %1;" : "=f"(mag) : "f"(X.x * X.x + X.y * X.y));
+      asm("sqrt.approx.f32 %0, %1;" : "=f"(mag) : "f"(0.25f * fmaf(xr, xr, xi * xi)));
       asm("lg2.approx.f32 %0, %1;" : "=f"(lg) : "f"(mag + 1e-6f));
       const float2 nr = sm.nrm[k];
       const float val = fmaf(lg * 0.69314718055994531f, nr.x, nr.y);
       if (live) {
         srow[k] = val;
-        xrow[k] = __half_as_ushort(__float2half_rn(val * mv[m]));
-        holes += 1.f - mv[m];
+        xrow[k] = __half_as_ushort(__float2half_rn(val * mval));
+        if (HOLES) holes += 1.f - mval;
       }
+    };
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      const int k = q + 16 * m;                                // 0 .. 127
+      const float2 zk = xc[k], zn = xc[(256 - k) & 255];
+      const float ex = zk.x + zn.x, ey = zk.y - zn.y;          // 2 E
+      const float dx = zk.x - zn.x, dy = zk.y + zn.y;          // 2 D ; 2 O = -i 2 D = (dy, -dx)
+      const float2 w = sm.tw[k];
+      const float px = dy * w.x + dx * w.y, py = dy * w.y - dx * w.x;    // 2 W O
+      emit(k, ex + px, ey + py, mva[m]);
+      emit(256 - k, ex - px, ey - py, mvb[m]);                 // |conj(.)| = |.|
+    }
+    if (q == 0) {                                              // bin 128 mirrors itself: W512^128 = -i
+      const float2 z = xc[128];
+      emit(128, 2.f * z.x, -2.f * z.y, mv128);
     }
     if (live) {
       if (HAS_VIDEO) {
@@ -397,7 +410,7 @@ __global__ void __launch_bounds__(FE_THREADS, 2) frontend_train_kernel(avsi_fron
     }
     __syncwarp();
   }
-  if (p.hole_count) {
+  if (HOLES) {
     holes = warp_sum(holes);
     if ((tid & 31) == 0 && holes != 0.f) atomicAdd(p.hole_count, holes);
   }
@@ -435,16 +448,19 @@ extern "C" int avsi_frontend_fwd(const avsi_frontend_args* a, void* stream) {
     const int tsm = (int)sizeof(FrontendTrainSmem);
     static bool tattr = false;
     if (!tattr) {
-      AVSI_CUDA(cudaFuncSetAttribute(frontend_train_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tsm));
-      AVSI_CUDA(cudaFuncSetAttribute(frontend_train_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tsm));
+      AVSI_CUDA(cudaFuncSetAttribute(frontend_train_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tsm));
+      AVSI_CUDA(cudaFuncSetAttribute(frontend_train_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tsm));
+      AVSI_CUDA(cudaFuncSetAttribute(frontend_train_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tsm));
+      AVSI_CUDA(cudaFuncSetAttribute(frontend_train_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tsm));
       tattr = true;
     }
     long long tg = (long long)num_sms() * 2;
     if (tg > groups) tg = groups;
-    if (a->video)
-      frontend_train_kernel<true><<<(unsigned)tg, FE_THREADS, tsm, (cudaStream_t)stream>>>(*a);
-    else
-      frontend_train_kernel<false><<<(unsigned)tg, FE_THREADS, tsm, (cudaStream_t)stream>>>(*a);
+    cudaStream_t fst = (cudaStream_t)stream;
+    if (a->video && a->hole_count) frontend_train_kernel<true, true><<<(unsigned)tg, FE_THREADS, tsm, fst>>>(*a);
+    else if (a->video) frontend_train_kernel<true, false><<<(unsigned)tg, FE_THREADS, tsm, fst>>>(*a);
+    else if (a->hole_count) frontend_train_kernel<false, true><<<(unsigned)tg, FE_THREADS, tsm, fst>>>(*a);
+    else frontend_train_kernel<false, false><<<(unsigned)tg, FE_THREADS, tsm, fst>>>(*a);
     AVSI_LAUNCH_CHECK();
     return AVSI_OK;
   }

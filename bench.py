@@ -292,6 +292,8 @@ def main():
     torch.cuda.current_stream().wait_stream(copy_stream)
     torch.cuda.synchronize()
 
+    if not all(np.isfinite(x) for x in e2e_state['losses']):
+        raise SystemExit('bench: non-finite loss fetched in the end-to-end steps: %r' % e2e_state['losses'][-3:])
     if rank != 0:
         if pg is not None:
             dist.destroy_process_group()
@@ -350,6 +352,9 @@ def main():
                                 % ((pin['wav'].numel() + pin['mask'].numel()) * 4 / 1e6, T * B * (3 * 2048 * 2 + 3 * 512 * 6) / 1e9)},
         'e2e': {'value': utt / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 8,
                 'host_dtypes': {k: str(pin[k].dtype).replace('torch.', '') for k in ('wav', 'mask', 'landmarks')}},
+        # the e2e steps train on the same batch: the fetched losses must be finite and go down (work is not skipped)
+        'e2e_loss_first_last': [e2e_state['losses'][0] / (B * T * 257), e2e_state['losses'][-1] / (B * T * 257)]
+        if e2e_state['losses'] else None,
         'gpu_launches': launches,
         'clocks': clocks,
         'roofline': roof(dominant) if dominant else None,
