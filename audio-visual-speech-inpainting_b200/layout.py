@@ -38,7 +38,7 @@ class ParamLayout(object):
         self.in_dim, self.hidden, self.n_layers = in_dim, hidden, n_layers
         self.out_dim, self.n_classes = out_dim, n_classes
         self.n_out = out_dim + n_classes
-        self.k0p = round_up(in_dim, 64)                  # layer-0 K, padded for 64-wide TMA boxes
+        self.k0p = round_up(in_dim, 8)                   # layer-0 K: 16-byte row pitch (TMA zero-fills the last 64-wide box)
         self.nop = round_up(self.n_out, 64)              # head rows; also K of the dY GEMM
         self.blocks = []                                 # (name, offset, shape)
         off = 0
