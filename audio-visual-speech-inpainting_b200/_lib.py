@@ -71,7 +71,8 @@ SIGNATURES = {
     'avsi_sgd_momentum': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double, c_float, c_void_p, c_float,
                                   c_void_p]),
     'avsi_cast_to_f32': (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p]),
-    'avsi_cast_weights': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    'avsi_cast_weights': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    'avsi_gate_bias_prescale': (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
 }
 
 _lib = None

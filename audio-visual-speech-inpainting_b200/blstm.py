@@ -82,6 +82,7 @@ class BLSTMEngine(object):
             self.half['wihT%d' % l] = torch.zeros(kp, NG, dtype=torch.float16, device=self.device)
             self.half['whh%d' % l] = torch.zeros(NG, HP, dtype=torch.float16, device=self.device)
             self.half['whhT%d' % l] = torch.zeros(HP, NG, dtype=torch.float16, device=self.device)
+        self.bias_fwd = [torch.zeros(NG, dtype=torch.float32, device=self.device) for _ in range(L.n_layers)]
         self.half['head'] = torch.zeros(L.nop, NY, dtype=torch.float16, device=self.device)
         self.half['headT'] = torch.zeros(NY, L.nop, dtype=torch.float16, device=self.device)
         self._ws = {}
@@ -109,12 +110,16 @@ class BLSTMEngine(object):
         L = self.layout
         for l in range(L.n_layers):
             kp = L.layer_k(l)
+            # forward copies (wih, whh) and the projection bias carry the 1/2 of the sigmoid gates; the transposed
+            # copies read by the backward GEMMs / BPTT do not
             _lib.check(lib.avsi_cast_weights(_p(self.view(self.theta, 'wih%d' % l)), NG, kp, _p(self.half['wih%d' % l]),
-                                             _p(self.half['wihT%d' % l]), st), 'avsi_cast_weights')
+                                             _p(self.half['wihT%d' % l]), 1, st), 'avsi_cast_weights')
             _lib.check(lib.avsi_cast_weights(_p(self.view(self.theta, 'whh%d' % l)), NG, HP, _p(self.half['whh%d' % l]),
-                                             _p(self.half['whhT%d' % l]), st), 'avsi_cast_weights')
+                                             _p(self.half['whhT%d' % l]), 1, st), 'avsi_cast_weights')
+            _lib.check(lib.avsi_gate_bias_prescale(_p(self.view(self.theta, 'b%d' % l)), NG, _p(self.bias_fwd[l]), st),
+                       'avsi_gate_bias_prescale')
         _lib.check(lib.avsi_cast_weights(_p(self.view(self.theta, 'head_w')), L.nop, NY, _p(self.half['head']),
-                                         _p(self.half['headT']), st), 'avsi_cast_weights')
+                                         _p(self.half['headT']), 0, st), 'avsi_cast_weights')
 
     # ---- workspaces ---------------------------------------------------------------------------
     def workspace(self, T, B, training=True):
@@ -158,13 +163,13 @@ class BLSTMEngine(object):
             G = ws['G'][l if training else 0]
             C = ws['C'][l if training else 0]
             kp = L.layer_k(l)
-            gemm(_p(x), ldx, _p(self.half['wih%d' % l]), kp, _p(G), NG, None, M, NG, kp, 0, 0, tag='gemm_proj_fwd',
-                 layout=C_IL)
+            gemm(_p(x), ldx, _p(self.half['wih%d' % l]), kp, _p(G), NG, None, M, NG, kp, 0, 0,
+                 tag='gemm_proj_fwd', layout=C_IL)
             # HBM-bound at large batch: per row the kernel reads G (4096 B), writes the activated gates (4096 B),
             # c_t (2048 B) and h_t (1024 B); the recurrent product adds 2*M*2048*256 flops
             with _lib.span('lstm_fwd', nbytes=M * (2 * NG * 2 + NY * 4 + NY * 2), flops=2 * M * NG * HP):
-                _lib.check(lib.avsi_lstm_fwd(_p(G), _p(self.half['whh%d' % l]), _p(self.view(self.theta, 'b%d' % l)),
-                                             _p(ws['Y'][l]), _p(C), T, B, _lib.stream_ptr()), 'avsi_lstm_fwd')
+                _lib.check(lib.avsi_lstm_fwd(_p(G), _p(self.half['whh%d' % l]), _p(self.bias_fwd[l]), _p(ws['Y'][l]), _p(C),
+                                             T, B, _lib.stream_ptr()), 'avsi_lstm_fwd')
             x, ldx = ws['Y'][l], NY
         gemm(_p(x), NY, _p(self.half['head']), NY, _p(ws['logits']), L.nop, _p(self.view(self.theta, 'head_b')),
              M, L.n_out, NY, 0, 1, tag='gemm_head_fwd')

@@ -98,7 +98,8 @@ lstm_fwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whh, 
       wf[kt][nt][1] = *reinterpret_cast<const uint32_t*>(wrow + kt * 16 + uu * 2 + 8);
     }
   }
-  float bq[4];
+
+  float bq[4];                                     // prescaled bias (i, f, o halved like the pre-activations)
 #pragma unroll
   for (int q = 0; q < 4; ++q) bq[q] = bias[dir * LS_G + u * 4 + q];
 
@@ -161,10 +162,11 @@ lstm_fwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whh, 
         const int rl = mt * 16 + g + rh * 8;
         const int row = b0 + rl;
         const float2 p_ig = unpack_half2(pre[mt][rh].x), p_fo = unpack_half2(pre[mt][rh].y);
-        const float gi = fsigmoid(acc[mt][0][rh * 2 + 0] + p_ig.x + bq[0]);
+        // the i, f, o columns of the pre-activations, the bias and the W_hh rows arrive pre-halved
+        const float gi = fsigmoid(2.f * (acc[mt][0][rh * 2 + 0] + p_ig.x + bq[0]));
         const float gg = ftanh(acc[mt][0][rh * 2 + 1] + p_ig.y + bq[1]);
-        const float gf = fsigmoid(acc[mt][1][rh * 2 + 0] + p_fo.x + bq[2]);
-        const float go = fsigmoid(acc[mt][1][rh * 2 + 1] + p_fo.y + bq[3]);
+        const float gf = fsigmoid(2.f * (acc[mt][1][rh * 2 + 0] + p_fo.x + bq[2]));
+        const float go = fsigmoid(2.f * (acc[mt][1][rh * 2 + 1] + p_fo.y + bq[3]));
         const float c = gf * c_state[mt][rh] + gi * gg;
         c_state[mt][rh] = c;
         const float h = go * ftanh(c);

@@ -43,7 +43,7 @@ sgd_momentum_kernel(float* __restrict__ theta, const float* __restrict__ g, floa
 
 __global__ void __launch_bounds__(256)
 cast_weights_kernel(const float* __restrict__ w, int R, int C, uint16_t* __restrict__ w16,
-                    uint16_t* __restrict__ w16t) {
+                    uint16_t* __restrict__ w16t, int halve_sigmoid_rows) {
   // 32x32 tile transpose through shared memory; also writes the straight copy
   __shared__ float tile[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
@@ -53,7 +53,11 @@ cast_weights_kernel(const float* __restrict__ w, int R, int C, uint16_t* __restr
     int r = r0 + ty + 8 * i, c = c0 + tx;
     float x = (r < R && c < C) ? w[(long long)r * C + c] : 0.f;
     tile[ty + 8 * i][tx] = x;
-    if (w16 && r < R && c < C) w16[(long long)r * C + c] = __half_as_ushort(__float2half_rn(x));
+    // forward operand copies of the gate matrices carry the 1/2 of sigma(z) = 1/2 tanh(z/2) + 1/2: rows (gate
+    // columns) i, f, o are halved (exact in fp16), row g (index 1 of [i,g,f,o]) is not; the transposed copy that
+    // the backward GEMMs read stays unscaled
+    const float sc = (halve_sigmoid_rows && (r & 3) != 1) ? 0.5f : 1.f;
+    if (w16 && r < R && c < C) w16[(long long)r * C + c] = __half_as_ushort(__float2half_rn(x * sc));
   }
   if (!w16t) return;
   __syncthreads();
@@ -80,6 +84,11 @@ __global__ void __launch_bounds__(256) cast_to_f32_kernel(const S* __restrict__ 
       for (long long k = i; k < n; ++k) dst[k] = (float)src[k];
     }
   }
+}
+
+__global__ void gate_bias_prescale_kernel(const float* __restrict__ b, int n, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = b[i] * (((i & 3) != 1) ? 0.5f : 1.f);
 }
 
 __global__ void mtl_scales_kernel(const float* __restrict__ hole_count, int B, float ctc_w, float* __restrict__ out) {
@@ -138,12 +147,21 @@ extern "C" int avsi_cast_to_f32(const void* src, int src_type, int64_t n, float*
   return AVSI_OK;
 }
 
-extern "C" int avsi_cast_weights(const float* w, int R, int C, uint16_t* w16, uint16_t* w16t, void* stream) {
+extern "C" int avsi_cast_weights(const float* w, int R, int C, uint16_t* w16, uint16_t* w16t, int halve_sigmoid_rows,
+                                 void* stream) {
   using namespace avsi;
   AVSI_REQUIRE(w && (w16 || w16t), "null pointer");
   AVSI_REQUIRE(R > 0 && C > 0, "sizes");
   dim3 grid((C + 31) / 32, (R + 31) / 32);
-  cast_weights_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, R, C, w16, w16t);
+  cast_weights_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, R, C, w16, w16t, halve_sigmoid_rows);
+  AVSI_LAUNCH_CHECK();
+  return AVSI_OK;
+}
+
+extern "C" int avsi_gate_bias_prescale(const float* bias, int n, float* out, void* stream) {
+  using namespace avsi;
+  AVSI_REQUIRE(bias && out && n > 0, "args");
+  gate_bias_prescale_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(bias, n, out);
   AVSI_LAUNCH_CHECK();
   return AVSI_OK;
 }

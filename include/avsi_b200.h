@@ -121,7 +121,7 @@ int avsi_feature_stats(const float* x, int ldx, const float* mask, int ldm, int6
  * 1902-1912) and their gradients.
  *   C[M,N] (+)= A . B^T      trans == 0: A [M,K] (lda), B [N,K] (ldb), both K-contiguous
  *   C[M,N] (+)= A^T . B      trans == 1: A [K,M] (lda), B [K,N] (ldb), both MN-contiguous
- *   out_mode 0: C f16 = acc ; 1: C f32 = acc + bias[N] (bias may be NULL) ; 2: C f32 += acc (atomic)
+ *   out_mode 0: C f16 = acc (+ bias[N] if not NULL) ; 1: C f32 = acc + bias[N] (bias may be NULL) ; 2: C f32 += acc (atomic)
  *   split_k > 1 only with out_mode 2.  lda/ldb multiples of 8 elements; A,B 16-byte aligned.
  *   layout bit 0: A is stored interleaved ("IL": [rows/32][lda/8][32][8] halves, rows padded to 32 with
  *   zeros) instead of row-major; layout bit 1: the f16 output C (out_mode 0) is written interleaved with
@@ -138,9 +138,12 @@ int avsi_gemm_f16(const uint16_t* A, int lda, const uint16_t* B, int ldb, void* 
  * thread-block cluster feeding tcgen05.mma, or registers of an 8-CTA cluster for small batches).
  * HP = 256 (H padded), gate columns are laid out [dir][unit][i,g,f,o] (column = dir*1024 + unit*4 + gate).
  *   gates [T*B, 2048] f16   INTERLEAVED storage ([rows/32][2048/8][32][8], rows padded to 32 with zeros):
- *                           in: x.W_ih^T pre-activations (avsi_gemm_f16 layout bit 1) ; out: activated gates (in place)
- *   whh   [2,1024,256] f16  recurrent weights, [dir][gate column][h_in]
- *   bias  [2048] f32
+ *                           in: x.W_ih^T pre-activations with the i, f, o columns pre-halved (avsi_gemm_f16 layout
+ *                           bit 1 on the prescaled weight copy, see avsi_cast_weights) ;
+ *                           out: activated gates i, g, f, o (in place)
+ *   whh   [2,1024,256] f16  recurrent weights, [dir][gate column][h_in], i, f, o rows pre-halved likewise
+ *   bias  [2048] f32        prescaled likewise (avsi_gate_bias_prescale).  The tcgen05 kernel feeds it through the
+ *                           tensor core (padding unit 255 of h is held at 1.0, column 255 of its W_hh copy = bias)
  *   y     [T*B, 512] f16    out: h_t, row-major, columns dir*256 + unit
  *   cst   [T*B, 512] f32    out: c_t (stash for BPTT), INTERLEAVED with 4-float chunks ([rows/32][512/4][32][4])
  * Backward: dy [T*B,512] f16 (scaled dL/dy), whhT [256,2048] f16 (whh^T) -> gates becomes dgates
@@ -202,7 +205,14 @@ int avsi_sgd_momentum(float* theta, const float* g, float* accum, int64_t n, dou
  * 2 = int32 samples as dataset_reader.py:78 yields them) to the fp32 tensor of the feed contract (training.py:69-71). */
 int avsi_cast_to_f32(const void* src, int src_type, int64_t n, float* dst, void* stream);
 /* fp32 -> fp16 copies of a weight matrix W [R,C]: w16 [R,C] and (optional) w16t [C,R]. */
-int avsi_cast_weights(const float* w, int R, int C, uint16_t* w16, uint16_t* w16t, void* stream);
+int avsi_cast_weights(const float* w, int R, int C, uint16_t* w16, uint16_t* w16t, int halve_sigmoid_rows,
+                      void* stream);
+/* halve_sigmoid_rows != 0 (gate matrices W_ih, W_hh, rows = gate columns [unit][i,g,f,o]): rows i, f, o of w16 are
+ * multiplied by 1/2 (exact), so that the forward recurrence evaluates sigma(z) = 1/2 tanh(z') + 1/2 on the
+ * pre-halved z' without a multiply; w16t (read by the backward GEMMs) is never scaled.
+ * avsi_gate_bias_prescale: out[n] = bias[n] * (1/2 for i, f, o columns, 1 for g) -- the bias vector the projection
+ * GEMM adds in its epilogue (avsi_gemm_f16 out_mode 0 with bias). */
+int avsi_gate_bias_prescale(const float* bias, int n, float* out, void* stream);
 
 #ifdef __cplusplus
 }

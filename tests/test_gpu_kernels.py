@@ -90,6 +90,38 @@ def test_gemm_f16(M, N, K, trans, out_mode, split_k, ldc_pad):
         assert np.all(got[:, N:] == fill)
 
 
+def test_gemm_f16_output_bias_and_gate_prescale():
+    """Projection epilogue: f16 output = acc + bias (row-major and interleaved); avsi_cast_weights with
+    halve_sigmoid_rows halves rows i, f, o of the straight copy only; avsi_gate_bias_prescale likewise."""
+    from avsi_b200 import _lib, blstm
+    lib = _lib.load()
+    rng = np.random.default_rng(8)
+    d = dev()
+    M, N, K = 300, 512, 128
+    A = rng.standard_normal((M, K)).astype(np.float16)
+    W = rng.standard_normal((N, K)).astype(np.float32)
+    bvec = rng.standard_normal(N).astype(np.float32)
+    Wt = torch.from_numpy(W).to(d)
+    w16 = torch.empty(N, K, dtype=torch.float16, device=d)
+    w16t = torch.empty(K, N, dtype=torch.float16, device=d)
+    _lib.check(lib.avsi_cast_weights(_lib.ptr(Wt), N, K, _lib.ptr(w16), _lib.ptr(w16t), 1, _lib.stream_ptr()), 'cast')
+    bs = torch.empty(N, device=d)
+    _lib.check(lib.avsi_gate_bias_prescale(_lib.ptr(torch.from_numpy(bvec).to(d)), N, _lib.ptr(bs), _lib.stream_ptr()), 'bias')
+    sc = np.where(np.arange(N) % 4 == 1, 1.0, 0.5).astype(np.float32)
+    assert np.array_equal(w16.cpu().numpy(), (W * sc[:, None]).astype(np.float16))
+    assert np.array_equal(w16t.cpu().numpy(), W.T.astype(np.float16))
+    assert np.array_equal(bs.cpu().numpy(), bvec * sc)
+    ref = A.astype(np.float64) @ w16.cpu().numpy().astype(np.float64).T + (bvec * sc).astype(np.float64)
+    for layout in (0, 2):
+        rows = -(-M // 32) * 32 if layout else M
+        C = torch.zeros(rows, N, dtype=torch.float16, device=d)
+        blstm.gemm(torch.from_numpy(A).to(d).data_ptr(), K, w16.data_ptr(), K, C.data_ptr(), N, bs.data_ptr(), M, N, K, 0, 0,
+                   layout=layout)
+        sync()
+        got = (blstm.from_il(C, M) if layout else C).cpu().numpy().astype(np.float64)
+        assert rel_l2(got, ref) < 2e-3
+
+
 GEMM_IL_CASES = [
     # M, N, K, trans, out_mode, split_k, layout   (layout bit 0: A interleaved, bit 1: f16 output interleaved)
     (1000, 2048, 448, 0, 0, 1, 2),        # projection: row-major X -> interleaved G
@@ -392,7 +424,7 @@ def test_adam_tf_and_cast():
     assert rel_l2(tm.cpu().numpy(), rm) < 1e-6 and rel_l2(tv.cpu().numpy(), rv) < 1e-6
     W = torch.from_numpy(rng.standard_normal((291, 77)).astype(np.float32)).to(d)
     w16, w16t = torch.empty(291, 77, dtype=torch.float16, device=d), torch.empty(77, 291, dtype=torch.float16, device=d)
-    _lib.check(lib.avsi_cast_weights(_lib.ptr(W), 291, 77, _lib.ptr(w16), _lib.ptr(w16t), _lib.stream_ptr()), 'cast')
+    _lib.check(lib.avsi_cast_weights(_lib.ptr(W), 291, 77, _lib.ptr(w16), _lib.ptr(w16t), 0, _lib.stream_ptr()), 'cast')
     sync()
     assert torch.equal(w16, W.half()) and torch.equal(w16t, W.half().t())
 
@@ -452,10 +484,16 @@ def test_lstm_recurrence_fwd_bwd(T, B):
     R = rng.standard_normal((T, B, 2, 256)).astype(np.float16)
     R[..., H:] = 0
     from avsi_b200 import blstm
-    gates = blstm.to_il(torch.from_numpy(P.reshape(T * B, 2048).copy()).to(d))      # interleaved gate tensor
-    whh = torch.from_numpy(Whh.reshape(2048, 256)).to(d)
-    whhT = whh.t().contiguous()
-    tb = torch.from_numpy(bias.reshape(2048)).to(d)
+    # kernel contract (include/avsi_b200.h): the pre-activations hold the bias, and the i, f, o columns of the
+    # pre-activations and rows of W_hh are pre-halved (sigma(z) = 1/2 tanh(z/2) + 1/2); BPTT reads the unscaled W_hh^T
+    scale = np.array([0.5, 1.0, 0.5, 0.5], np.float32)
+    Pin = (P.astype(np.float32) * scale).astype(np.float16)                        # exact: powers of two
+    gates = blstm.to_il(torch.from_numpy(Pin.reshape(T * B, 2048).copy()).to(d))    # interleaved gate tensor
+    whh_true = torch.from_numpy(Whh.reshape(2048, 256)).to(d)
+    whh = torch.from_numpy((Whh.reshape(2, 256, 4, 256).astype(np.float32) * scale[None, None, :, None])
+                           .astype(np.float16).reshape(2048, 256)).to(d)
+    whhT = whh_true.t().contiguous()
+    tb = torch.from_numpy((bias * scale).reshape(2048).astype(np.float32)).to(d)   # prescaled like the pre-activations
     y = torch.full((T * B, 512), 3.0, dtype=torch.float16, device=d)
     cst = torch.zeros((-(-T * B // 32) * 32, 512), dtype=torch.float32, device=d)                # interleaved (4-float chunks)
     _lib.check(lib.avsi_lstm_fwd(_lib.ptr(gates), _lib.ptr(whh), _lib.ptr(tb), _lib.ptr(y), _lib.ptr(cst), T, B,
