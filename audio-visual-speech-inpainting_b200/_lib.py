@@ -27,7 +27,7 @@ class FrontendArgs(Structure):
         ('stft_out', c_void_p), ('spec_out', c_void_p), ('feat_out', c_void_p),
         ('xh_out', c_void_p), ('ldx', c_int),
         ('logmel_out', c_void_p), ('mel_w', c_void_p), ('n_mel', c_int), ('mel_eps', c_float),
-        ('hole_count', c_void_p), ('xh_video_only', c_int),
+        ('hole_count', c_void_p), ('xh_video_only', c_int), ('xh_skip_pad', c_int),
     ]
 
 

@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(FE_THREADS) frontend_kernel(avsi_frontend_args
         if (p.xh_out) p.xh_out[row_tb * p.ldx + (p.xh_video_only ? 0 : p.F) + c] = __half_as_ushort(__float2half_rn(x));
       }
     }
-    if (live && p.xh_out)
+    if (live && p.xh_out && !p.xh_skip_pad)
       for (int c = (p.xh_video_only ? p.V : I) + q; c < p.ldx; c += 16) p.xh_out[row_tb * p.ldx + c] = 0;
     // ---- log-mel ------------------------------------------------------------------------------
     if (want_mel) {
@@ -406,7 +406,8 @@ __global__ void __launch_bounds__(FE_THREADS, 2) frontend_train_kernel(avsi_fron
           for (int c = q; c < p.V; c += 16) xrow[257 + c] = __half_as_ushort(__float2half_rn(__ldg(vs + c)));
         }
       }
-      for (int c = 257 + (HAS_VIDEO ? p.V : 0) + q; c < p.ldx; c += 16) xrow[c] = 0;
+      if (!p.xh_skip_pad)
+        for (int c = 257 + (HAS_VIDEO ? p.V : 0) + q; c < p.ldx; c += 16) xrow[c] = 0;
     }
     __syncwarp();
   }

@@ -50,23 +50,7 @@ struct GemmSmem {
 };
 
 // one warp-lane's 32 consecutive accumulator columns [n0, n0+32) of output row `row`
-__device__ __forceinline__ void epilogue_store(const GemmParams& p, int row, int n0, bool full, uint32_t (&r)[32]) {
-  if (p.out_mode == 0 && p.bias) {                     // gate projections: + (prescaled) bias before the fp16 rounding
-    if (full && ((uintptr_t)(p.bias + n0) & 15) == 0) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {                    // warp-uniform address: one broadcast 16-byte load per 4 columns
-        const float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j);
-        r[4 * j + 0] = __float_as_uint(__uint_as_float(r[4 * j + 0]) + bv.x);
-        r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + bv.y);
-        r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + bv.z);
-        r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + bv.w);
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (n0 + j < p.N) r[j] = __float_as_uint(__uint_as_float(r[j]) + __ldg(p.bias + n0 + j));
-    }
-  }
+__device__ __forceinline__ void epilogue_store(const GemmParams& p, int row, int n0, bool full, const uint32_t (&r)[32]) {
   if (p.out_mode == 0 && p.c_il) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -401,31 +385,14 @@ gemm_f16_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int row = m_blk * 2 * GEMM_BM + (int)rank * GEMM_BM + quarter * 32 + lane;
       const bool row_ok = row < p.M && kb1 > kb0;
 #pragma unroll 1
-      const bool fast_bias = p.out_mode == 0 && p.bias != nullptr && (p.N % 32 == 0) && (((uintptr_t)p.bias & 15) == 0);
-      GemmParams pe = p;
-      if (fast_bias) pe.bias = nullptr;                 // added here, with the loads issued ahead of the TMEM read
 #pragma unroll 1
       for (int c = chalf * (BN / 32 / NSPLIT); c < (chalf + 1) * (BN / 32 / NSPLIT); ++c) {
-        const int n0 = n_blk * BN + c * 32;
-        float4 bv[8];
-        if (fast_bias && n0 < p.N) {
-#pragma unroll
-          for (int jx = 0; jx < 8; ++jx) bv[jx] = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + jx);
-        }
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
         tmem_ld_wait();
+        const int n0 = n_blk * BN + c * 32;
         if (!row_ok || n0 >= p.N) continue;
-        if (fast_bias) {
-#pragma unroll
-          for (int jx = 0; jx < 8; ++jx) {
-            r[4 * jx + 0] = __float_as_uint(__uint_as_float(r[4 * jx + 0]) + bv[jx].x);
-            r[4 * jx + 1] = __float_as_uint(__uint_as_float(r[4 * jx + 1]) + bv[jx].y);
-            r[4 * jx + 2] = __float_as_uint(__uint_as_float(r[4 * jx + 2]) + bv[jx].z);
-            r[4 * jx + 3] = __float_as_uint(__uint_as_float(r[4 * jx + 3]) + bv[jx].w);
-          }
-        }
-        epilogue_store(pe, row, n0, n0 + 32 <= p.N, r);
+        epilogue_store(p, row, n0, n0 + 32 <= p.N, r);
       }
       tc_fence_before();
       __syncwarp();

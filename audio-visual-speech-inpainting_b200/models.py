@@ -142,7 +142,7 @@ class StackedBLSTMModel(object):
         res = ap.fused_features(wav, self.frame_len, self.hop, T=T, F=self.audio_feat_dim, mean=mean, std=std,
                                 mask=masks, video=video, power=1.0, log=True, want_stft=want_stft, want_spec=True,
                                 xh_out=ws['x0'], ldx=self.engine.layout.k0p, hole_count=hole,
-                                xh_video_only=(self.input_type == 'v'))
+                                xh_video_only=(self.input_type == 'v'), xh_skip_pad=True)
         out = {'ws': ws, 'B': B, 'T': T, 'target_spec_norm': res['spec'], 'target_stft': res['stft'], 'hole': hole}
         self._cache[key] = out
         if want_stft:

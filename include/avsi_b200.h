@@ -77,6 +77,8 @@ typedef struct {
   float* logmel_out; const float* mel_w; int n_mel; float mel_eps;
   float* hole_count;   /* optional [1] f32 device accumulator: += sum(1 - mask) (caller zeroes) */
   int xh_video_only;   /* input='v' (models.py:42-43): xh_out holds only the video columns, from column 0 */
+  int xh_skip_pad;     /* != 0: the zero padding columns [I, ldx) of xh_out are NOT rewritten (the caller zeroed the
+                          buffer once and nothing else writes them): saves 12 % of the row at ldx = 448 */
 } avsi_frontend_args;
 int avsi_frontend_fwd(const avsi_frontend_args* args, void* stream);
 
@@ -121,7 +123,7 @@ int avsi_feature_stats(const float* x, int ldx, const float* mask, int ldm, int6
  * 1902-1912) and their gradients.
  *   C[M,N] (+)= A . B^T      trans == 0: A [M,K] (lda), B [N,K] (ldb), both K-contiguous
  *   C[M,N] (+)= A^T . B      trans == 1: A [K,M] (lda), B [K,N] (ldb), both MN-contiguous
- *   out_mode 0: C f16 = acc (+ bias[N] if not NULL) ; 1: C f32 = acc + bias[N] (bias may be NULL) ; 2: C f32 += acc (atomic)
+ *   out_mode 0: C f16 = acc ; 1: C f32 = acc + bias[N] (bias may be NULL) ; 2: C f32 += acc (atomic)
  *   split_k > 1 only with out_mode 2.  lda/ldb multiples of 8 elements; A,B 16-byte aligned.
  *   layout bit 0: A is stored interleaved ("IL": [rows/32][lda/8][32][8] halves, rows padded to 32 with
  *   zeros) instead of row-major; layout bit 1: the f16 output C (out_mode 0) is written interleaved with
@@ -210,8 +212,7 @@ int avsi_cast_weights(const float* w, int R, int C, uint16_t* w16, uint16_t* w16
 /* halve_sigmoid_rows != 0 (gate matrices W_ih, W_hh, rows = gate columns [unit][i,g,f,o]): rows i, f, o of w16 are
  * multiplied by 1/2 (exact), so that the forward recurrence evaluates sigma(z) = 1/2 tanh(z') + 1/2 on the
  * pre-halved z' without a multiply; w16t (read by the backward GEMMs) is never scaled.
- * avsi_gate_bias_prescale: out[n] = bias[n] * (1/2 for i, f, o columns, 1 for g) -- the bias vector the projection
- * GEMM adds in its epilogue (avsi_gemm_f16 out_mode 0 with bias). */
+ * avsi_gate_bias_prescale: out[n] = bias[n] * (1/2 for i, f, o columns, 1 for g) -- the bias vector avsi_lstm_fwd takes. */
 int avsi_gate_bias_prescale(const float* bias, int n, float* out, void* stream);
 
 #ifdef __cplusplus

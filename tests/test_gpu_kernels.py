@@ -90,9 +90,9 @@ def test_gemm_f16(M, N, K, trans, out_mode, split_k, ldc_pad):
         assert np.all(got[:, N:] == fill)
 
 
-def test_gemm_f16_output_bias_and_gate_prescale():
-    """Projection epilogue: f16 output = acc + bias (row-major and interleaved); avsi_cast_weights with
-    halve_sigmoid_rows halves rows i, f, o of the straight copy only; avsi_gate_bias_prescale likewise."""
+def test_gate_prescale_of_forward_copies():
+    """avsi_cast_weights with halve_sigmoid_rows halves rows i, f, o of the straight copy only (the transposed copy
+    the backward GEMMs read is untouched); avsi_gate_bias_prescale does the same to the bias vector."""
     from avsi_b200 import _lib, blstm
     lib = _lib.load()
     rng = np.random.default_rng(8)
@@ -111,15 +111,6 @@ def test_gemm_f16_output_bias_and_gate_prescale():
     assert np.array_equal(w16.cpu().numpy(), (W * sc[:, None]).astype(np.float16))
     assert np.array_equal(w16t.cpu().numpy(), W.T.astype(np.float16))
     assert np.array_equal(bs.cpu().numpy(), bvec * sc)
-    ref = A.astype(np.float64) @ w16.cpu().numpy().astype(np.float64).T + (bvec * sc).astype(np.float64)
-    for layout in (0, 2):
-        rows = -(-M // 32) * 32 if layout else M
-        C = torch.zeros(rows, N, dtype=torch.float16, device=d)
-        blstm.gemm(torch.from_numpy(A).to(d).data_ptr(), K, w16.data_ptr(), K, C.data_ptr(), N, bs.data_ptr(), M, N, K, 0, 0,
-                   layout=layout)
-        sync()
-        got = (blstm.from_il(C, M) if layout else C).cpu().numpy().astype(np.float64)
-        assert rel_l2(got, ref) < 2e-3
 
 
 GEMM_IL_CASES = [
