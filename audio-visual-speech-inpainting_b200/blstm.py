@@ -5,8 +5,9 @@ Host-side orchestration of the sm_100a kernels for the network of models.py:89-1
 gradient.  torch is used for device memory, streams and (in parallel.py) NCCL only; every
 arithmetic op is a kernel from libavsi_b200.so.  No autograd: the backward schedule is explicit.
 
-Per layer l (time-major rows r = t*B + b, fp16 activations, fp32 accumulate):
-  forward   G_l = X_l . Wih_l^T                  tcgen05 GEMM  [T*B,Kp] x [2048,Kp]^T -> f16
+Per layer l (time-major rows r = t*B + b, fp16 activations, fp32 accumulate; G_l and C_l are stored in the
+interleaved layout of common.cuh, the forward weight copies / bias carry the 1/2 of the sigmoid gates):
+  forward   G_l = X_l . Wih_l^T                  tcgen05 GEMM  [T*B,Kp] x [2048,Kp]^T -> f16 (interleaved)
             (Y_l, C_l, G_l<-gates) = recur(G_l)  cluster-persistent LSTM kernel
   head      logits = Y_last . Whead^T + b        tcgen05 GEMM -> f32
   backward  G_l <- dgates = bptt(G_l, C_l, dY_l) cluster-persistent BPTT kernel

@@ -1,10 +1,13 @@
-// fp16 x fp16 -> fp32 GEMM on the 5th-gen tensor cores (tcgen05.mma kind::f16, cta_group::1).
+// fp16 x fp16 -> fp32 GEMMs on the 5th-gen tensor cores (tcgen05.mma kind::f16, accumulators in TMEM, operands
+// staged by TMA).
 //
 // Replaces the cuBLAS/cuDNN contractions behind CudnnLSTM's input projections
 // (models.py:95-104), the tf.matmul heads (models.py:117-123, 1902-1912) and their gradients.
 //
-// Structure (one 128 x BN output tile per CTA, 2 CTAs co-resident per SM so one CTA's
-// epilogue overlaps the other's main loop):
+// Two kernels share the operand / epilogue code:
+//   gemm_f16_2sm_kernel  (below, the hot one: projections, dX, dW) persistent CTA pairs, cta_group::2, 256 x 256 tiles
+//   gemm_f16_kernel      (first) small or narrow problems (head GEMM, tests): one 128 x BN tile per CTA, cta_group::1,
+//                        2 CTAs co-resident per SM so one CTA's epilogue overlaps the other's main loop:
 //   warp 0      TMA producer: cp.async.bulk.tensor.2d (SWIZZLE_128B) into a STAGES-deep ring
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer, tcgen05.commit -> mbarriers
 //   warps 2..5  epilogue: tcgen05.ld (32 lanes x 32 columns) -> registers -> global
