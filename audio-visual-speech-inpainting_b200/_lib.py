@@ -27,7 +27,7 @@ class FrontendArgs(Structure):
         ('stft_out', c_void_p), ('spec_out', c_void_p), ('feat_out', c_void_p),
         ('xh_out', c_void_p), ('ldx', c_int),
         ('logmel_out', c_void_p), ('mel_w', c_void_p), ('n_mel', c_int), ('mel_eps', c_float),
-        ('hole_count', c_void_p), ('xh_video_only', c_int), ('xh_skip_pad', c_int),
+        ('hole_count', c_void_p), ('xh_video_only', c_int), ('mel_masked', c_int), ('xh_skip_pad', c_int),
     ]
 
 
@@ -51,6 +51,8 @@ SIGNATURES = {
     'avsi_sizeof_istft_args': (c_int, []),
     'avsi_frontend_fwd': (c_int, [POINTER(FrontendArgs), c_void_p]),
     'avsi_istft_fwd': (c_int, [POINTER(IstftArgs), c_void_p]),
+    'avsi_features_to_x0': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int,
+                                    c_void_p]),
     'avsi_video_features': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'avsi_expand_mask': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'avsi_feature_stats': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

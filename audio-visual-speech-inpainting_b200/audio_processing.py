@@ -67,7 +67,8 @@ def _f32(t, device):
 
 def fused_features(sources, frame_len, hop, T=None, F=257, mean=None, std=None, mask=None, video=None,
                    power=1.0, log=True, want_stft=False, stft_masked=False, want_spec=True, want_feat=False,
-                   xh_out=None, ldx=0, mel=None, mel_eps=1e-6, hole_count=None, xh_video_only=False, xh_skip_pad=False):
+                   xh_out=None, ldx=0, mel=None, mel_eps=1e-6, hole_count=None, xh_video_only=False, xh_skip_pad=False,
+                   mel_masked=False):
     """One launch of the fused front end.  Returns dict(stft, spec, feat, logmel) (missing = None).
 
     sources [B,N] f32 CUDA; mask [B,T,F]; video [B,T,V]; xh_out optional preallocated
@@ -114,6 +115,7 @@ def fused_features(sources, frame_len, hop, T=None, F=257, mean=None, std=None, 
     a.n_mel, a.mel_eps = n_mel, float(mel_eps)
     a.hole_count = hole_count.data_ptr() if hole_count is not None else None
     a.xh_video_only = int(bool(xh_video_only))
+    a.mel_masked = int(bool(mel_masked))
     a.xh_skip_pad = int(bool(xh_skip_pad))          # the engine's x0 workspace is zero-initialised once
     # algorithmic bytes of this launch: every requested input / output once
     nbytes = 4 * B * N + (4 * B * T * F if mask is not None else 0) + 4 * B * T * V

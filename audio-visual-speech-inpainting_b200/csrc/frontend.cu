@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(FE_THREADS) frontend_kernel(avsi_frontend_args
         mag = sqrtf(s);
         if (p.power != 1.f) mag = powf(mag, p.power);
       }
-      if (want_mel) sm.pw[fl][k] = mag;
+      if (want_mel) sm.pw[fl][k] = p.mel_masked ? mag * mval : mag;
       if (!live || k >= p.F) continue;
       float val = p.log_flag ? logf(mag + 1e-6f) : mag;
       if (p.mean) val = (val - __ldg(p.mean + k)) / __ldg(p.stdev + k);

@@ -73,6 +73,23 @@ video_features_kernel(const float* __restrict__ lm, const float* __restrict__ vm
   }
 }
 
+// (feat - mean) / std  ++ video  ->  time-major fp16 rows (the ASR model's input assembly, models_asr.py:37-49)
+__global__ void __launch_bounds__(256)
+features_to_x0_kernel(const float* __restrict__ feat, const float* __restrict__ mean, const float* __restrict__ stdev,
+                      const float* __restrict__ video, int B, int T, int F, int V, uint16_t* __restrict__ x0, int ldx) {
+  const long long rows = (long long)B * T;
+  for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+    const int b = (int)(r / T), t = (int)(r - (long long)b * T);
+    uint16_t* dst = x0 + ((long long)t * B + b) * ldx;
+    for (int c = threadIdx.x; c < ldx; c += blockDim.x) {
+      float v = 0.f;
+      if (c < F) v = (feat[r * F + c] - __ldg(mean + c)) / __ldg(stdev + c);
+      else if (video && c < F + V) v = video[r * V + (c - F)];
+      dst[c] = __half_as_ushort(__float2half_rn(v));
+    }
+  }
+}
+
 __global__ void expand_mask_kernel(const int32_t* __restrict__ iv, int B, int K, int T, int F,
                                    float* __restrict__ mask) {
   const long long n = (long long)B * T * F;
@@ -106,6 +123,18 @@ extern "C" int avsi_video_features(const float* landmarks, const float* vmean, c
     video_features_kernel<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(landmarks, vmean, vstd, B, L, D, T, out);
   else
     video_features_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(landmarks, vmean, vstd, B, L, D, T, out);
+  AVSI_LAUNCH_CHECK();
+  return AVSI_OK;
+}
+
+extern "C" int avsi_features_to_x0(const float* feat, const float* mean, const float* stdev, const float* video, int B,
+                                   int T, int F, int V, uint16_t* x0, int ldx, void* stream) {
+  using namespace avsi;
+  AVSI_REQUIRE(feat && mean && stdev && x0, "null pointer");
+  AVSI_REQUIRE(B > 0 && T > 0 && F > 0 && V >= 0 && ldx >= F + (video ? V : 0), "sizes");
+  long long rows = (long long)B * T;
+  int blocks = (int)min(rows, (long long)num_sms() * 16);
+  features_to_x0_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(feat, mean, stdev, video, B, T, F, V, x0, ldx);
   AVSI_LAUNCH_CHECK();
   return AVSI_OK;
 }

@@ -34,7 +34,7 @@ class StackedBLSTMModel(object):
 
     def __init__(self, sequence_lengths, target_sources, masks, audio_feat_mean, audio_feat_std, dropout_rate,
                  config, audio_features=None, video_features=None, input='a', is_training=True, device='cuda',
-                 process_group=None):
+                 process_group=None, _out_dim=None):
         if audio_features is not None:
             raise NotImplementedError('precomputed audio_features (two-step model) are out of scope')
         if input not in ('a', 'v', 'av'):
@@ -64,7 +64,8 @@ class StackedBLSTMModel(object):
         in_dim = {'a': self.audio_feat_dim, 'v': self.video_feat_dim,
                   'av': self.audio_feat_dim + self.video_feat_dim}[input]
         self.num_classes = config['num_asr_labels'] if self.MTL else 0
-        self.engine = BLSTMEngine(in_dim, self.net_dim[0], self.num_layers, self.audio_feat_dim, self.num_classes,
+        self.engine = BLSTMEngine(in_dim, self.net_dim[0], self.num_layers,
+                                  self.audio_feat_dim if _out_dim is None else _out_dim, self.num_classes,
                                   device=self.device)
         self.engine.load_canonical(init_canonical(self.engine.layout, seed=config.get('seed', 0)))
         self.global_step = 0

@@ -77,6 +77,8 @@ typedef struct {
   float* logmel_out; const float* mel_w; int n_mel; float mel_eps;
   float* hole_count;   /* optional [1] f32 device accumulator: += sum(1 - mask) (caller zeroes) */
   int xh_video_only;   /* input='v' (models.py:42-43): xh_out holds only the video columns, from column 0 */
+  int mel_masked;      /* != 0: the power spectrum is multiplied by the mask before the mel projection
+                          (models_asr.py:33-36, apply_mask) */
   int xh_skip_pad;     /* != 0: the zero padding columns [I, ldx) of xh_out are NOT rewritten (the caller zeroed the
                           buffer once and nothing else writes them): saves 12 % of the row at ldx = 448 */
 } avsi_frontend_args;
@@ -95,6 +97,12 @@ typedef struct {
   float* out;
 } avsi_istft_args;
 int avsi_istft_fwd(const avsi_istft_args* args, void* stream);
+
+/* Normalised features -> time-major fp16 network input (models_asr.py:37-49, the ASR model's input assembly):
+ *   x0[t*B + b, 0:F] = (feat[b,t,:] - mean) / std ; x0[.., F:F+V] = video[b,t,:] (video may be NULL); columns up to
+ *   ldx are zeroed.  feat [B,T,F] f32, mean/std [F] f32. */
+int avsi_features_to_x0(const float* feat, const float* mean, const float* stdev, const float* video, int B, int T,
+                        int F, int V, uint16_t* x0, int ldx, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Landmark stream -> network video features.  Replaces inc_fps /

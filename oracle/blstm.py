@@ -143,12 +143,25 @@ def forward_mtl(net_in, target, mask, seq_len, labels, lab_len, params, n_layers
                 ctc_loss=ctc_loss, ctc_nll=nll, rnn=rnn)
 
 
+def forward_asr(net_in, seq_len, labels, lab_len, params, n_layers, l2=0.0):
+    """models_asr.StackedBLSTMModel (models_asr.py:87-160): BLSTM stack -> logits head -> mean CTC NLL."""
+    B, T, _ = net_in.shape
+    rnn = blstm_stack(net_in, params, n_layers)
+    logits = (rnn.reshape(B * T, -1) @ params['logits/weights'] + params['logits/biases']).reshape(B, T, -1)
+    nll = octc.ctc_nll_torch(logits.transpose(0, 1), labels, lab_len, seq_len)                # models_asr.py:146-148
+    ctc_loss = nll.mean()
+    reg = sum(0.5 * (p ** 2).sum() for p in params.values()) if l2 else 0.0
+    return dict(inference=logits, ctc_loss=ctc_loss, ctc_nll=nll, loss=ctc_loss + l2 * reg, rnn=rnn)
+
+
 def loss_and_grads(kind, inputs, params_np, n_layers, dtype=torch.float64, **kw):
     """Run forward + autograd.  Returns (outputs as numpy, grads {name: numpy})."""
     params = to_torch(params_np, dtype, requires_grad=True)
     tin = {k: (torch.tensor(np.asarray(v), dtype=dtype) if np.asarray(v).dtype.kind == 'f' else torch.tensor(np.asarray(v)))
            for k, v in inputs.items()}
-    if kind == 'si':
+    if kind == 'asr':
+        out = forward_asr(tin['net_in'], tin['seq_len'], tin['labels'].long(), tin['lab_len'], params, n_layers, **kw)
+    elif kind == 'si':
         out = forward_si(tin['net_in'], tin['target'], tin['mask'], tin['seq_len'], params, n_layers, **kw)
     else:
         out = forward_mtl(tin['net_in'], tin['target'], tin['mask'], tin['seq_len'], tin['labels'].long(),

@@ -49,6 +49,30 @@ def test_si_gradients_match_finite_differences():
     assert outs['prediction'][1, 4].tolist() == [0.0] * F
 
 
+def test_asr_mode_is_ctc_of_head_logits_and_differentiates():
+    """models_asr.py:87-160 restated: loss = mean CTC NLL of the head logits; gradient checked by central differences
+    and the NLL against torch's own CTC on the same logits."""
+    rng = np.random.default_rng(2)
+    B, T, I, H, C = 2, 9, 5, 3, 6
+    params = blstm.init_params(I, H, 2, out_dim=C, seed=9, bias_scale=0.1)
+    inputs = dict(net_in=rng.standard_normal((B, T, I)), seq_len=np.array([9, 7]), labels=np.array([[0, 1, 1], [4, 2, 0]]),
+                  lab_len=np.array([3, 2]))
+    outs, grads = blstm.loss_and_grads('asr', inputs, params, 2)
+    lg = torch.tensor(outs['inference']).transpose(0, 1)
+    ref = torch.nn.functional.ctc_loss(torch.log_softmax(lg, 2), torch.tensor(inputs['labels']), torch.tensor(inputs['seq_len']),
+                                       torch.tensor(inputs['lab_len']), blank=C - 1, reduction='none')
+    assert np.allclose(outs['ctc_nll'], ref.numpy(), atol=1e-9) and abs(outs['loss'] - ref.mean().item()) < 1e-9
+    eps = 1e-6
+    for name, idx in ((blstm.cell_prefix(1, 'fw') + '/kernel', (2, 7)), ('logits/weights', (4, 1)),
+                      (blstm.cell_prefix(0, 'bw') + '/bias', (5,))):
+        p2 = {k: v.copy() for k, v in params.items()}
+        p2[name][idx] += eps
+        lp = blstm.loss_and_grads('asr', inputs, p2, 2)[0]['loss']
+        p2[name][idx] -= 2 * eps
+        lm = blstm.loss_and_grads('asr', inputs, p2, 2)[0]['loss']
+        assert abs((lp - lm) / (2 * eps) - grads[name][idx]) < 1e-7, name
+
+
 def test_ctc_three_ways():
     rng = np.random.default_rng(0)
     T, B, C = 30, 3, 34
