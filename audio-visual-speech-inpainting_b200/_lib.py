@@ -28,6 +28,7 @@ class FrontendArgs(Structure):
         ('xh_out', c_void_p), ('ldx', c_int),
         ('logmel_out', c_void_p), ('mel_w', c_void_p), ('n_mel', c_int), ('mel_eps', c_float),
         ('hole_count', c_void_p), ('xh_video_only', c_int), ('mel_masked', c_int), ('xh_skip_pad', c_int),
+        ('mel_bands', c_void_p),
     ]
 
 

@@ -57,6 +57,38 @@ def linear_to_mel_weight_matrix(num_mel_bins=80, num_spec_bins=257, sample_rate=
     return np.concatenate([np.zeros((1, num_mel_bins)), w], axis=0)
 
 
+_BANDS = {}
+_MEL = {}
+
+
+def _mel_bands(mel):
+    """Band form of a mel matrix [n_bins, n_mel] for the fused log-mel kernel (avsi_frontend_args.mel_bands): every
+    filter of linear_to_mel_weight_matrix is non-zero on one contiguous bin range.  None when it does not fit."""
+    key = (mel.data_ptr(), tuple(mel.shape), mel._version, str(mel.device))
+    if key not in _BANDS:
+        m = mel.detach().cpu().numpy().astype(np.float32)
+        n_bins, n_mel = m.shape
+        packed = None
+        if n_mel < 128 and n_bins <= 257:
+            hdr = np.zeros(256, np.int32)
+            ws = []
+            n = 0
+            for j in range(n_mel):
+                nz = np.nonzero(m[:, j])[0]
+                lo, hi = (int(nz[0]), int(nz[-1]) + 1) if nz.size else (0, 0)
+                hdr[j], hdr[128 + j] = lo, n
+                ws.append(m[lo:hi, j])
+                n += hi - lo
+            hdr[128 + n_mel] = n
+            if n <= 1024:
+                buf = np.concatenate([hdr.view(np.float32)] + ws) if ws else hdr.view(np.float32)
+                packed = torch.from_numpy(np.ascontiguousarray(buf)).to(mel.device)
+        if len(_BANDS) > 16:
+            _BANDS.clear()
+        _BANDS[key] = packed
+    return _BANDS[key]
+
+
 def _f32(t, device):
     if t is None:
         return None
@@ -116,6 +148,8 @@ def fused_features(sources, frame_len, hop, T=None, F=257, mean=None, std=None, 
     a.hole_count = hole_count.data_ptr() if hole_count is not None else None
     a.xh_video_only = int(bool(xh_video_only))
     a.mel_masked = int(bool(mel_masked))
+    bands = _mel_bands(mel) if mel is not None else None
+    a.mel_bands = bands.data_ptr() if bands is not None else None
     a.xh_skip_pad = int(bool(xh_skip_pad))          # the engine's x0 workspace is zero-initialised once
     # algorithmic bytes of this launch: every requested input / output once
     nbytes = 4 * B * N + (4 * B * T * F if mask is not None else 0) + 4 * B * T * V
@@ -173,8 +207,11 @@ def log_mel_features(sources, sample_rate=16000, window_size=25, step_size=10, n
     """Fused `fbanks` path of audio_feat_preprocessing.py:49-50 / models_asr.py:31-37:
     power-2 spectrogram -> mel projection -> log, one kernel."""
     frame_len, hop = ms_to_samples(window_size, sample_rate), ms_to_samples(step_size, sample_rate)
-    m = linear_to_mel_weight_matrix(num_mel_bins, 257, sample_rate, lower_edge_freq, upper_edge_freq)
-    mel = torch.tensor(m, dtype=torch.float32, device=sources.device).contiguous()
+    key = (str(sources.device), num_mel_bins, sample_rate, lower_edge_freq, upper_edge_freq)
+    if key not in _MEL:
+        m = linear_to_mel_weight_matrix(num_mel_bins, 257, sample_rate, lower_edge_freq, upper_edge_freq)
+        _MEL[key] = torch.tensor(m, dtype=torch.float32, device=sources.device).contiguous()
+    mel = _MEL[key]
     res = fused_features(sources, frame_len, hop, power=2.0, log=False, want_spec=False, mel=mel, mel_eps=eps)
     return res['logmel']
 

@@ -244,6 +244,8 @@ struct FrontendTrainSmem {
   float2 nrm[260];                      // (1/std, -mean/std) per bin
   float2 xch[FE_FRAMES][FE_XCH];
   float2 wavb[2][FE_FRAMES][192];       // sample pairs of the frame, double buffered
+  int mlo[128], moff[128];              // log-mel variant: first bin and weight offset of every mel filter
+  float mw[1024];                       // band weights
 };
 
 __device__ __forceinline__ void cp_async8_zfill(uint32_t dst, const void* src, int src_bytes) {
@@ -255,7 +257,10 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-template <bool HAS_VIDEO, bool HOLES>
+// MEL = true is the `fbanks` variant (models_asr.py:30-36, audio_feat_preprocessing.py:49-50): power spectrum (x mask
+// when mel_masked) -> band-form mel projection out of shared memory -> log; the only HBM traffic is the samples in and
+// [B,T,n_mel] out.
+template <bool HAS_VIDEO, bool HOLES, bool MEL>
 __global__ void __launch_bounds__(FE_THREADS, 2) frontend_train_kernel(avsi_frontend_args p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FrontendTrainSmem& sm = *reinterpret_cast<FrontendTrainSmem*>(smem_raw);
@@ -263,10 +268,22 @@ __global__ void __launch_bounds__(FE_THREADS, 2) frontend_train_kernel(avsi_fron
   for (int i = tid; i < 512; i += FE_THREADS) sm.tw[i] = reinterpret_cast<const float2*>(p.twiddle)[i];
   sm.tw1[tid >> 4][tid & 15] = reinterpret_cast<const float2*>(p.twiddle)[(2 * (tid & 15) * (tid >> 4)) & 511];
   for (int i = tid; i < 192; i += FE_THREADS) sm.win2[i] = make_float2(p.window[2 * i], p.window[2 * i + 1]);
-  for (int i = tid; i < 257; i += FE_THREADS) {
-    const float is = 1.0f / p.stdev[i];
-    sm.nrm[i] = make_float2(is, -p.mean[i] * is);
+  if (!MEL) {
+    for (int i = tid; i < 257; i += FE_THREADS) {
+      const float is = 1.0f / p.stdev[i];
+      sm.nrm[i] = make_float2(is, -p.mean[i] * is);
+    }
+  } else {
+    const int* hdr = reinterpret_cast<const int*>(p.mel_bands);
+    if (tid < 128) {
+      sm.mlo[tid] = hdr[tid];
+      sm.moff[tid] = hdr[128 + tid];
+    }
+    const int nw = hdr[128 + p.n_mel];
+    const float* wsrc = reinterpret_cast<const float*>(hdr + 256);
+    for (int i = tid; i < nw; i += FE_THREADS) sm.mw[i] = wsrc[i];
   }
+  const bool masked = !MEL || (p.mel_masked && p.mask);
   __syncthreads();
 
   const int fl = tid >> 4, q = tid & 15;
@@ -310,7 +327,7 @@ __global__ void __launch_bounds__(FE_THREADS, 2) frontend_train_kernel(avsi_fron
     // thread q owns the bin pairs (k, 256 - k), k = q + 16 m, m = 0..7 (+ the self-mirrored bin 128 for q == 0):
     // X[k] = E + W O and X[256 - k] = conj(E - W O) share Z[k], Z[256 - k] and the twiddle product
     float mva[8], mvb[8], mv128 = 1.f;
-    if (live) {
+    if (live && masked) {
       const float* mrow = p.mask + row_bt * 257;
 #pragma unroll
       for (int m = 0; m < 8; ++m) {
@@ -363,9 +380,14 @@ __global__ void __launch_bounds__(FE_THREADS, 2) frontend_train_kernel(avsi_fron
     for (int k2 = 0; k2 < 16; ++k2) xc[q + 16 * k2] = make_float2(v[k2].x, v[k2].y);
     __syncwarp();
     // ---- real-FFT split + |.| + log + normalise + mask ------------------------------------------------------------
-    float* srow = p.spec_out + row_bt * 257;
-    uint16_t* xrow = p.xh_out + row_tb * p.ldx;
+    float* srow = MEL ? nullptr : p.spec_out + row_bt * 257;
+    uint16_t* xrow = MEL ? nullptr : p.xh_out + row_tb * p.ldx;
     auto emit = [&](int k, float xr, float xi, float mval) {
+      if (MEL) {
+        // power spectrum, parked in the .x slot of Z[k] (Z[k] and Z[256 - k] are read by this thread only, before this)
+        xc[k].x = 0.25f * fmaf(xr, xr, xi * xi) * mval;
+        return;
+      }
       // |X| = sqrt(0.25 (xr^2 + xi^2)) for the un-halved sums; log; normalise; mask; fp32 target + fp16 network input
       float mag, lg;
       asm("sqrt.approx.f32 %0, %1;" : "=f"(mag) : "f"(0.25f * fmaf(xr, xr, xi * xi)));
@@ -393,7 +415,18 @@ __global__ void __launch_bounds__(FE_THREADS, 2) frontend_train_kernel(avsi_fron
       const float2 z = xc[128];
       emit(128, 2.f * z.x, -2.f * z.y, mv128);
     }
-    if (live) {
+    if (MEL) {
+      __syncwarp();
+      if (live) {
+        float* orow = p.logmel_out + row_bt * p.n_mel;
+        for (int mb = q; mb < p.n_mel; mb += 16) {
+          const int lo = sm.mlo[mb], o = sm.moff[mb], n = sm.moff[mb + 1] - o;
+          float acc = 0.f;
+          for (int i = 0; i < n; ++i) acc = fmaf(xc[lo + i].x, sm.mw[o + i], acc);
+          orow[mb] = __logf(acc + p.mel_eps);
+        }
+      }
+    } else if (live) {
       if (HAS_VIDEO) {
         if (p.V <= 144) {
 #pragma unroll
@@ -445,23 +478,30 @@ extern "C" int avsi_frontend_fwd(const avsi_frontend_args* a, void* stream) {
                           a->mean && a->mask && a->spec_out && a->xh_out && !a->stft_out && !a->feat_out &&
                           !a->logmel_out && !a->xh_video_only && (a->N % 2 == 0) &&
                           ((uintptr_t)a->wav % 8 == 0);
-  if (train_path) {
+  // log-mel variant of the same kernel: power-2 spectrum -> band-form mel -> log, nothing else requested
+  const bool mel_path = a->frame_len == 384 && a->hop == 192 && a->power == 2.f && !a->log_flag && a->logmel_out &&
+                        a->mel_bands && a->n_mel > 0 && a->n_mel < 128 && !a->spec_out && !a->xh_out && !a->stft_out &&
+                        !a->feat_out && !a->hole_count && (a->N % 2 == 0) && ((uintptr_t)a->wav % 8 == 0) &&
+                        (!a->mel_masked || !a->mask || a->F == 257);
+  if (train_path || mel_path) {
     const int tsm = (int)sizeof(FrontendTrainSmem);
     static bool tattr = false;
     if (!tattr) {
-      AVSI_CUDA(cudaFuncSetAttribute(frontend_train_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tsm));
-      AVSI_CUDA(cudaFuncSetAttribute(frontend_train_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tsm));
-      AVSI_CUDA(cudaFuncSetAttribute(frontend_train_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tsm));
-      AVSI_CUDA(cudaFuncSetAttribute(frontend_train_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tsm));
+      AVSI_CUDA(cudaFuncSetAttribute(frontend_train_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tsm));
+      AVSI_CUDA(cudaFuncSetAttribute(frontend_train_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tsm));
+      AVSI_CUDA(cudaFuncSetAttribute(frontend_train_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tsm));
+      AVSI_CUDA(cudaFuncSetAttribute(frontend_train_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tsm));
+      AVSI_CUDA(cudaFuncSetAttribute(frontend_train_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tsm));
       tattr = true;
     }
     long long tg = (long long)num_sms() * 2;
     if (tg > groups) tg = groups;
     cudaStream_t fst = (cudaStream_t)stream;
-    if (a->video && a->hole_count) frontend_train_kernel<true, true><<<(unsigned)tg, FE_THREADS, tsm, fst>>>(*a);
-    else if (a->video) frontend_train_kernel<true, false><<<(unsigned)tg, FE_THREADS, tsm, fst>>>(*a);
-    else if (a->hole_count) frontend_train_kernel<false, true><<<(unsigned)tg, FE_THREADS, tsm, fst>>>(*a);
-    else frontend_train_kernel<false, false><<<(unsigned)tg, FE_THREADS, tsm, fst>>>(*a);
+    if (mel_path) frontend_train_kernel<false, false, true><<<(unsigned)tg, FE_THREADS, tsm, fst>>>(*a);
+    else if (a->video && a->hole_count) frontend_train_kernel<true, true, false><<<(unsigned)tg, FE_THREADS, tsm, fst>>>(*a);
+    else if (a->video) frontend_train_kernel<true, false, false><<<(unsigned)tg, FE_THREADS, tsm, fst>>>(*a);
+    else if (a->hole_count) frontend_train_kernel<false, true, false><<<(unsigned)tg, FE_THREADS, tsm, fst>>>(*a);
+    else frontend_train_kernel<false, false, false><<<(unsigned)tg, FE_THREADS, tsm, fst>>>(*a);
     AVSI_LAUNCH_CHECK();
     return AVSI_OK;
   }

@@ -81,6 +81,10 @@ typedef struct {
                           (models_asr.py:33-36, apply_mask) */
   int xh_skip_pad;     /* != 0: the zero padding columns [I, ldx) of xh_out are NOT rewritten (the caller zeroed the
                           buffer once and nothing else writes them): saves 12 % of the row at ldx = 448 */
+  const void* mel_bands; /* optional band form of mel_w (each mel filter is non-zero on one contiguous range of bins):
+                          int32 lo[128] (first bin of filter j), int32 off[128] (offset of its weights; off[n_mel] =
+                          total count <= 1024), then the weights as f32.  Enables the fused log-mel kernel
+                          (power = 2, log_flag = 0, logmel_out only); NULL = dense projection in the general kernel */
 } avsi_frontend_args;
 int avsi_frontend_fwd(const avsi_frontend_args* args, void* stream);
 

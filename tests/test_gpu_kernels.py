@@ -241,6 +241,35 @@ def test_frontend_power2_logmel_and_plain_stft():
     assert rel_l2(np.exp(sp), np.exp(ref_sp)) < 1e-5
 
 
+@pytest.mark.parametrize('B,N,masked', [(3, 48000, False), (5, 4802, True), (2, 320000, True), (1, 100, False),
+                                        (3, 4801, True)])
+def test_frontend_fused_logmel_24_12(B, N, masked):
+    """The `fbanks` variant at the models' 24 ms / 12 ms framing (models_asr.py:30-36): power-2 spectrum (x mask) ->
+    mel-80 -> log in the fused kernel (band-form mel out of shared memory); odd N takes the general kernel (dense mel)."""
+    from avsi_b200 import audio_processing as ap
+    from oracle import stft as ostft
+    rng = np.random.default_rng(B + N)
+    d = dev()
+    T = -(-N // 192)
+    wav = np.round(rng.normal(0, 3000, (B, N))).astype(np.float32)
+    mask = np.ones((B, T, 257), np.float32)
+    for b in range(B):
+        a0 = int(rng.integers(0, max(1, T - 2)))
+        mask[b, a0:a0 + max(1, T // 5)] = 0
+    mel = torch.tensor(ap.linear_to_mel_weight_matrix(), dtype=torch.float32, device=d)
+    res = ap.fused_features(torch.from_numpy(wav).to(d), 384, 192, T=T, F=257, mask=torch.from_numpy(mask).to(d) if masked else None,
+                            power=2.0, log=False, want_spec=False, mel=mel, mel_masked=masked)
+    st = ostft.get_stft(wav.astype(np.float64), window_size=24, step_size=12)
+    spec = np.abs(st) ** 2
+    if masked:
+        spec = spec * mask
+    ref = ostft.get_log_mel_spectrogram(spec)
+    lm = res['logmel'].cpu().numpy()
+    assert lm.shape == ref.shape == (B, T, 80)
+    assert rel_l2(np.exp(lm), np.exp(ref)) < 1e-5
+    assert np.abs(lm - ref).max() < 1e-4 * max(1.0, np.abs(ref).max())
+
+
 def test_mask_app_chain_matches_docs_fixtures(golden_dir):
     """masking.py:41-45,93-95 on the GPU: STFT -> x mask -> iSTFT -> int16 == shipped masked.wav +-1 LSB."""
     from avsi_b200 import audio_processing as ap
