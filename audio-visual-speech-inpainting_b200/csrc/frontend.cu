@@ -236,14 +236,92 @@ __global__ void __launch_bounds__(FE_THREADS) frontend_kernel(avsi_frontend_args
 //     no scoreboard stall at the head of the iteration;
 //   * the mask row of a frame is requested before its FFT and consumed after it;
 //   * zero-padded FFT inputs (samples 384..511) are compile-time zeros, the first radix-16 pass is pruned;
-//   * sqrt / log are single MUFU ops (sqrt.approx, lg2.approx: <= 2 ulp, the 1e-5 budget is on relative L2).
+//   * complex arithmetic is PACKED fp32x2 (FADD2 / FMUL2 / FFMA2 on (re, im) register pairs; the half swap of a
+//     quarter turn or a complex product is a free operand swizzle): half the issue slots of the scalar butterflies;
+//   * sqrt / log are single MUFU ops (sqrt.approx.ftz, lg2.approx.ftz: <= 2 ulp, the 1e-5 budget is on relative L2);
+//   * (b, t) of a thread's frame advance incrementally (no division in the loop); a thread past the last frame
+//     recomputes the last frame (same values to the same addresses) instead of carrying predicates.
+typedef unsigned long long c2;          // packed complex / pair: lo = re (or first), hi = im (or second)
+
+__device__ __forceinline__ c2 pk(float lo, float hi) {
+  c2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk(c2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ c2 swp(c2 v) {
+  float a, b;
+  upk(v, a, b);
+  return pk(b, a);
+}
+__device__ __forceinline__ c2 add2(c2 a, c2 b) {
+  c2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ c2 sub2(c2 a, c2 b) {
+  c2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ c2 mul2(c2 a, c2 b) {
+  c2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ c2 fma2(c2 a, c2 b, c2 c) {
+  c2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// v * (wr + i wi) with the constant given as (wr, wr) and (-wi, wi)
+__device__ __forceinline__ c2 cmul2(c2 v, c2 wrr, c2 wii) { return fma2(swp(v), wii, mul2(v, wrr)); }
+
+__device__ __forceinline__ void fft4p(c2& a, c2& b, c2& c, c2& d, const c2 pm, const c2 mp) {
+  // forward radix-4, natural order; pm = (1, -1), mp = (-1, 1): s1 -/+ i (b - d) as one FFMA2 on the swapped pair
+  const c2 s0 = add2(a, c), s1 = sub2(a, c), s2 = add2(b, d), t = swp(sub2(b, d));
+  a = add2(s0, s2);
+  c = sub2(s0, s2);
+  b = fma2(t, pm, s1);
+  d = fma2(t, mp, s1);
+}
+
+__device__ __forceinline__ void fft16p(c2 (&v)[16]) {
+  const float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, r2 = 0.70710678118654752f;
+  const c2 pm = pk(1.f, -1.f), mp = pk(-1.f, 1.f);
+#pragma unroll
+  for (int n2 = 0; n2 < 4; ++n2) fft4p(v[n2], v[4 + n2], v[8 + n2], v[12 + n2], pm, mp);
+  // forward twiddles W16^(n2 k1): w1 = (c1,-s1), w2 = (r2,-r2), w3 = (s1,-c1), w6 = (-r2,-r2), w9 = (-c1, s1)
+  const c2 w1r = pk(c1, c1), w1i = pk(s1, -s1), w2r = pk(r2, r2), w2i = pk(r2, -r2), w3r = pk(s1, s1), w3i = pk(c1, -c1);
+  const c2 w6r = pk(-r2, -r2), w9r = pk(-c1, -c1), w9i = pk(-s1, s1);
+  v[5] = cmul2(v[5], w1r, w1i);
+  v[6] = cmul2(v[6], w2r, w2i);
+  v[7] = cmul2(v[7], w3r, w3i);
+  v[9] = cmul2(v[9], w2r, w2i);
+  v[10] = mul2(swp(v[10]), pm);           // W16^4 = -i
+  v[11] = cmul2(v[11], w6r, w2i);
+  v[13] = cmul2(v[13], w3r, w3i);
+  v[14] = cmul2(v[14], w6r, w2i);
+  v[15] = cmul2(v[15], w9r, w9i);
+#pragma unroll
+  for (int k1 = 0; k1 < 4; ++k1) fft4p(v[4 * k1 + 0], v[4 * k1 + 1], v[4 * k1 + 2], v[4 * k1 + 3], pm, mp);
+  c2 t[16];
+#pragma unroll
+  for (int k1 = 0; k1 < 4; ++k1)
+#pragma unroll
+    for (int k2 = 0; k2 < 4; ++k2) t[k1 + 4 * k2] = v[4 * k1 + k2];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = t[i];
+}
+
 struct FrontendTrainSmem {
-  float2 tw[512];
-  float2 tw1[16][16];                   // step-1 twiddles W256^(q k1) as [k1][q]: conflict-free (tw[(2 q k1) & 511] is not)
-  float2 win2[192];                     // window as (w[2n], w[2n+1]) pairs
-  float2 nrm[260];                      // (1/std, -mean/std) per bin
-  float2 xch[FE_FRAMES][FE_XCH];
-  float2 wavb[2][FE_FRAMES][192];       // sample pairs of the frame, double buffered
+  float2 tw1p[16][16];                  // step-1 twiddles W256^(q k1) as [k1][q]
+  float2 twp[128];                      // split twiddles W512^k
+  ulonglong2 nrm2[128];                 // ((ln2/std_k, ln2/std_{256-k}), (-mean_k/std_k, -mean_{256-k}/std_{256-k}))
+  float2 nrm128;                        // the self-mirrored bin
+  c2 win2[192];                         // window as (w[2n], w[2n+1]) pairs
+  c2 xch[FE_FRAMES][FE_XCH];
+  c2 wavb[2][FE_FRAMES][192];           // sample pairs of the frame, double buffered
   int mlo[128], moff[128];              // log-mel variant: first bin and weight offset of every mel filter
   float mw[1024];                       // band weights
 };
@@ -251,10 +329,23 @@ struct FrontendTrainSmem {
 __device__ __forceinline__ void cp_async8_zfill(uint32_t dst, const void* src, int src_bytes) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
 }
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ float sqrt_ftz(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float lg2_ftz(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
 }
 
 // MEL = true is the `fbanks` variant (models_asr.py:30-36, audio_feat_preprocessing.py:49-50): power spectrum (x mask
@@ -265,13 +356,19 @@ __global__ void __launch_bounds__(FE_THREADS, 2) frontend_train_kernel(avsi_fron
   extern __shared__ __align__(16) unsigned char smem_raw[];
   FrontendTrainSmem& sm = *reinterpret_cast<FrontendTrainSmem*>(smem_raw);
   const int tid = threadIdx.x;
-  for (int i = tid; i < 512; i += FE_THREADS) sm.tw[i] = reinterpret_cast<const float2*>(p.twiddle)[i];
-  sm.tw1[tid >> 4][tid & 15] = reinterpret_cast<const float2*>(p.twiddle)[(2 * (tid & 15) * (tid >> 4)) & 511];
-  for (int i = tid; i < 192; i += FE_THREADS) sm.win2[i] = make_float2(p.window[2 * i], p.window[2 * i + 1]);
+  const float2* twg = reinterpret_cast<const float2*>(p.twiddle);
+  sm.tw1p[tid >> 4][tid & 15] = twg[(2 * (tid & 15) * (tid >> 4)) & 511];
+  if (tid < 128) sm.twp[tid] = twg[tid];
+  for (int i = tid; i < 192; i += FE_THREADS) sm.win2[i] = pk(p.window[2 * i], p.window[2 * i + 1]);
   if (!MEL) {
-    for (int i = tid; i < 257; i += FE_THREADS) {
-      const float is = 1.0f / p.stdev[i];
-      sm.nrm[i] = make_float2(is, -p.mean[i] * is);
+    const float ln2 = 0.69314718055994531f;
+    if (tid < 128) {
+      const float ia = 1.0f / p.stdev[tid], ib = 1.0f / p.stdev[256 - tid];
+      sm.nrm2[tid] = make_ulonglong2(pk(ia * ln2, ib * ln2), pk(-p.mean[tid] * ia, -p.mean[256 - tid] * ib));
+    }
+    if (tid == 128) {
+      const float is = 1.0f / p.stdev[128];
+      sm.nrm128 = make_float2(is * ln2, -p.mean[128] * is);
     }
   } else {
     const int* hdr = reinterpret_cast<const int*>(p.mel_bands);
@@ -287,54 +384,83 @@ __global__ void __launch_bounds__(FE_THREADS, 2) frontend_train_kernel(avsi_fron
   __syncthreads();
 
   const int fl = tid >> 4, q = tid & 15;
-  const long long total = (long long)p.B * p.T;
-  const long long stride = (long long)gridDim.x * FE_FRAMES;
+  const int total = p.B * p.T;                     // < 2^31 (checked by the launcher)
+  const int stride = (int)gridDim.x * FE_FRAMES;
+  const int dT = stride % p.T, dB = stride / p.T;
   float holes = 0.f;
 
-  auto issue = [&](long long g0, int buf) {
-    const long long g = g0 + fl;
-    const bool live = g < total;
-    const int b = live ? (int)(g / p.T) : 0;
-    const int t = live ? (int)(g - (long long)b * p.T) : 0;
-    const long long base = (long long)b * p.N + (long long)t * p.hop;
-    const int avail = live ? (int)min((long long)384, (long long)p.N - (long long)t * p.hop) : 0;
-    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&sm.wavb[buf][fl][0]);
+  // frame of this thread in the group starting at g0; past the end it is the last frame again
+  int g0 = (int)blockIdx.x * FE_FRAMES;
+  int b, t;
+  {
+    const int g = min(g0 + fl, total - 1);
+    b = g / p.T;
+    t = g - b * p.T;
+  }
+  auto advance = [&](int& bb, int& tt, int g0n) {
+    if (g0n + fl >= total) {
+      bb = p.B - 1;
+      tt = p.T - 1;
+      return;
+    }
+    tt += dT;
+    bb += dB;
+    if (tt >= p.T) {
+      tt -= p.T;
+      bb += 1;
+    }
+  };
+  auto issue = [&](int bb, int tt, int buf) {
+    const long long base = (long long)bb * p.N + (long long)tt * p.hop;
+    const int avail = p.N - tt * p.hop;
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&sm.wavb[buf][fl][q]);
+    const float* src = p.wav + base + 2 * q;
+    if (avail >= 384) {
 #pragma unroll
-    for (int n1 = 0; n1 < 12; ++n1) {
-      const int i0 = 32 * n1 + 2 * q;
-      const int nb = max(0, min(8, (avail - i0) * 4));
-      cp_async8_zfill(dst + (uint32_t)(16 * n1 + q) * 8u, p.wav + (nb > 0 ? base + i0 : 0), nb);
+      for (int n1 = 0; n1 < 12; ++n1) cp_async8(dst + (uint32_t)(128 * n1), src + 32 * n1);
+    } else {
+#pragma unroll
+      for (int n1 = 0; n1 < 12; ++n1) {
+        const int nb = max(0, min(8, (avail - 32 * n1 - 2 * q) * 4));
+        cp_async8_zfill(dst + (uint32_t)(128 * n1), nb > 0 ? (const void*)(src + 32 * n1) : (const void*)p.wav, nb);
+      }
     }
     cp_async_commit();
   };
 
-  long long g0 = (long long)blockIdx.x * FE_FRAMES;
+  const c2 pm = pk(1.f, -1.f), mp = pk(-1.f, 1.f);
   int buf = 0;
-  if (g0 < total) issue(g0, 0);
+  if (g0 < total) issue(b, t, 0);
   for (; g0 < total; g0 += stride, buf ^= 1) {
+    const bool live = g0 + fl < total;
+    int bn = b, tn = t;
     if (g0 + stride < total) {
-      issue(g0 + stride, buf ^ 1);
+      advance(bn, tn, g0 + stride);
+      issue(bn, tn, buf ^ 1);
       cp_async_wait<1>();
     } else {
       cp_async_wait<0>();
     }
-    const long long g = g0 + fl;
-    const bool live = g < total;
-    const int b = live ? (int)(g / p.T) : 0;
-    const int t = live ? (int)(g - (long long)b * p.T) : 0;
-    const long long row_bt = g, row_tb = (long long)t * p.B + b;
+    const long long row_bt = (long long)b * p.T + t, row_tb = (long long)t * p.B + b;
     // mask row of this frame: requested now, used after the transform
     // thread q owns the bin pairs (k, 256 - k), k = q + 16 m, m = 0..7 (+ the self-mirrored bin 128 for q == 0):
     // X[k] = E + W O and X[256 - k] = conj(E - W O) share Z[k], Z[256 - k] and the twiddle product
     float mva[8], mvb[8], mv128 = 1.f;
-    if (live && masked) {
-      const float* mrow = p.mask + row_bt * 257;
+    if (masked) {
+      const float* mrow = p.mask + row_bt * 257 + q;
+      const float* mrev = p.mask + row_bt * 257 + 256 - q;
 #pragma unroll
       for (int m = 0; m < 8; ++m) {
-        mva[m] = __ldg(mrow + q + 16 * m);
-        mvb[m] = __ldg(mrow + 256 - q - 16 * m);
+        mva[m] = __ldg(mrow + 16 * m);
+        mvb[m] = __ldg(mrev - 16 * m);
       }
       if (q == 0) mv128 = __ldg(mrow + 128);
+      if (HOLES && live) {
+        float h = 1.f - mv128;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) h += (1.f - mva[m]) + (1.f - mvb[m]);
+        holes += h;
+      }
     } else {
 #pragma unroll
       for (int m = 0; m < 8; ++m) mva[m] = mvb[m] = 1.f;
@@ -345,104 +471,118 @@ __global__ void __launch_bounds__(FE_THREADS, 2) frontend_train_kernel(avsi_fron
 #pragma unroll
       for (int i = 0; i < 9; ++i) {
         const int c = q + 16 * i;
-        vv[i] = (live && c < p.V) ? __ldg(p.video + row_bt * p.V + c) : 0.f;
+        vv[i] = (c < p.V) ? __ldg(p.video + row_bt * p.V + c) : 0.f;
       }
     }
     // ---- window; samples 384..511 are zero ----------------------------------------------------------------
-    cpx v[16];
+    c2 v[16];
 #pragma unroll
-    for (int n1 = 0; n1 < 12; ++n1) {
-      const float2 x = sm.wavb[buf][fl][16 * n1 + q];
-      const float2 w = sm.win2[16 * n1 + q];
-      v[n1].x = x.x * w.x;
-      v[n1].y = x.y * w.y;
-    }
+    for (int n1 = 0; n1 < 12; ++n1) v[n1] = mul2(sm.wavb[buf][fl][16 * n1 + q], sm.win2[16 * n1 + q]);
 #pragma unroll
-    for (int n1 = 12; n1 < 16; ++n1) v[n1] = cpx{0.f, 0.f};
-    fft16<false>(v);
-    float2* xc = sm.xch[fl];
-    xc[q] = make_float2(v[0].x, v[0].y);                       // W256^0 = 1
+    for (int n1 = 12; n1 < 16; ++n1) v[n1] = 0ull;
+    fft16p(v);
+    c2* xc = sm.xch[fl];
+    xc[q] = v[0];                                              // W256^0 = 1
 #pragma unroll
     for (int k1 = 1; k1 < 16; ++k1) {
-      const float2 w = sm.tw1[k1][q];
-      const cpx r = cmul(v[k1], cpx{w.x, w.y});
-      xc[k1 * FE_XROW + q] = make_float2(r.x, r.y);
+      const float2 w = sm.tw1p[k1][q];
+      xc[k1 * FE_XROW + q] = cmul2(v[k1], pk(w.x, w.x), pk(-w.y, w.y));
     }
     __syncwarp();
 #pragma unroll
-    for (int n2 = 0; n2 < 16; ++n2) {
-      const float2 a = xc[q * FE_XROW + n2];
-      v[n2] = cpx{a.x, a.y};
-    }
-    fft16<false>(v);
-    __syncwarp();
+    for (int n2 = 0; n2 < 16; ++n2) v[n2] = xc[q * FE_XROW + n2];
+    fft16p(v);
+    // thread q now holds Z[q + 16 k2] in v[k2].  The mirror Z[256 - k] of its bins k = q + 16 m, m = 0..7, is
+    // v[15 - m] of lane (16 - q) & 15 (q != 0); lane 0 mirrors into itself: Z[256 - 16 m] = v[16 - m] (Z[0] for m = 0),
+    // so lane 0 publishes those instead -- one shuffle per pair, no second trip through shared memory
+    c2 zm[8];
+    {
+      const int src = (16 - q) & 15;
 #pragma unroll
-    for (int k2 = 0; k2 < 16; ++k2) xc[q + 16 * k2] = make_float2(v[k2].x, v[k2].y);
-    __syncwarp();
+      for (int m = 0; m < 8; ++m) {
+        const c2 own = (m == 0) ? v[0] : v[16 - m];
+        zm[m] = __shfl_sync(0xffffffffu, q == 0 ? own : v[15 - m], src, 16);
+      }
+    }
+    if (MEL) __syncwarp();                                      // the power spectrum reuses the exchange buffer
     // ---- real-FFT split + |.| + log + normalise + mask ------------------------------------------------------------
-    float* srow = MEL ? nullptr : p.spec_out + row_bt * 257;
-    uint16_t* xrow = MEL ? nullptr : p.xh_out + row_tb * p.ldx;
-    auto emit = [&](int k, float xr, float xi, float mval) {
-      if (MEL) {
-        // power spectrum, parked in the .x slot of Z[k] (Z[k] and Z[256 - k] are read by this thread only, before this)
-        xc[k].x = 0.25f * fmaf(xr, xr, xi * xi) * mval;
-        return;
-      }
-      // |X| = sqrt(0.25 (xr^2 + xi^2)) for the un-halved sums; log; normalise; mask; fp32 target + fp16 network input
-      float mag, lg;
-      asm("sqrt.approx.f32 %0, %1;" : "=f"(mag) : "f"(0.25f * fmaf(xr, xr, xi * xi)));
-      asm("lg2.approx.f32 %0, %1;" : "=f"(lg) : "f"(mag + 1e-6f));
-      const float2 nr = sm.nrm[k];
-      const float val = fmaf(lg * 0.69314718055994531f, nr.x, nr.y);
-      if (live) {
-        srow[k] = val;
-        xrow[k] = __half_as_ushort(__float2half_rn(val * mval));
-        if (HOLES) holes += 1.f - mval;
-      }
-    };
+    float* srow = MEL ? nullptr : p.spec_out + row_bt * 257 + q;
+    float* srev = MEL ? nullptr : p.spec_out + row_bt * 257 + 256 - q;
+    uint16_t* xrow = MEL ? nullptr : p.xh_out + row_tb * p.ldx + q;
+    uint16_t* xrev = MEL ? nullptr : p.xh_out + row_tb * p.ldx + 256 - q;
+    float* pwr = reinterpret_cast<float*>(xc);
 #pragma unroll
     for (int m = 0; m < 8; ++m) {
       const int k = q + 16 * m;                                // 0 .. 127
-      const float2 zk = xc[k], zn = xc[(256 - k) & 255];
-      const float ex = zk.x + zn.x, ey = zk.y - zn.y;          // 2 E
-      const float dx = zk.x - zn.x, dy = zk.y + zn.y;          // 2 D ; 2 O = -i 2 D = (dy, -dx)
-      const float2 w = sm.tw[k];
-      const float px = dy * w.x + dx * w.y, py = dy * w.y - dx * w.x;    // 2 W O
-      emit(k, ex + px, ey + py, mva[m]);
-      emit(256 - k, ex - px, ey - py, mvb[m]);                 // |conj(.)| = |.|
+      const c2 zk = v[m], zn = zm[m];
+      const c2 e2 = fma2(zn, pm, zk);                          // 2 E = (zk.x + zn.x, zk.y - zn.y)
+      const c2 d2 = fma2(zn, mp, zk);                          // 2 D = (zk.x - zn.x, zk.y + zn.y); 2 O = -i 2 D
+      const float2 w = sm.twp[k];
+      const c2 pp = fma2(swp(d2), pk(w.x, -w.x), mul2(d2, pk(w.y, w.y)));   // 2 W O
+      const c2 x1 = add2(e2, pp), x2 = sub2(e2, pp);           // 2 X[k], 2 conj X[256 - k]
+      float a0, a1, b0, b1;
+      upk(mul2(x1, x1), a0, a1);
+      upk(mul2(x2, x2), b0, b1);
+      const float s1 = a0 + a1, s2 = b0 + b1;                  // 4 |X|^2
+      if (MEL) {
+        // power spectrum, parked in the .x slot of Z[k] (Z[k] and Z[256 - k] are read by this thread only, above)
+        pwr[k] = 0.25f * s1 * mva[m];
+        pwr[256 - k] = 0.25f * s2 * mvb[m];
+        continue;
+      }
+      // |X| = sqrt(s) / 2; log(|X| + 1e-6); normalise (ln 2 folded into 1/std); mask
+      float m1, m2;
+      upk(fma2(pk(sqrt_ftz(s1), sqrt_ftz(s2)), pk(0.5f, 0.5f), pk(1e-6f, 1e-6f)), m1, m2);
+      const ulonglong2 nr = sm.nrm2[k];
+      const c2 val = fma2(pk(lg2_ftz(m1), lg2_ftz(m2)), nr.x, nr.y);
+      float v1, v2, h1, h2;
+      upk(val, v1, v2);
+      upk(mul2(val, pk(mva[m], mvb[m])), h1, h2);
+      srow[16 * m] = v1;
+      srev[-16 * m] = v2;
+      xrow[16 * m] = __half_as_ushort(__float2half_rn(h1));
+      xrev[-16 * m] = __half_as_ushort(__float2half_rn(h2));
     }
-    if (q == 0) {                                              // bin 128 mirrors itself: W512^128 = -i
-      const float2 z = xc[128];
-      emit(128, 2.f * z.x, -2.f * z.y, mv128);
+    if (q == 0) {                                              // bin 128 mirrors itself: W512^128 = -i, |X| = |Z[128]|
+      float zx, zy;
+      upk(v[8], zx, zy);
+      const float s = fmaf(zx, zx, zy * zy);
+      if (MEL) {
+        pwr[128] = s * mv128;
+      } else {
+        const float val = fmaf(lg2_ftz(sqrt_ftz(s) + 1e-6f), sm.nrm128.x, sm.nrm128.y);
+        srow[128] = val;
+        xrow[128] = __half_as_ushort(__float2half_rn(val * mv128));
+      }
     }
     if (MEL) {
       __syncwarp();
-      if (live) {
-        float* orow = p.logmel_out + row_bt * p.n_mel;
-        for (int mb = q; mb < p.n_mel; mb += 16) {
-          const int lo = sm.mlo[mb], o = sm.moff[mb], n = sm.moff[mb + 1] - o;
-          float acc = 0.f;
-          for (int i = 0; i < n; ++i) acc = fmaf(xc[lo + i].x, sm.mw[o + i], acc);
-          orow[mb] = __logf(acc + p.mel_eps);
-        }
+      float* orow = p.logmel_out + row_bt * p.n_mel;
+      for (int mb = q; mb < p.n_mel; mb += 16) {
+        const int lo = sm.mlo[mb], o = sm.moff[mb], n = sm.moff[mb + 1] - o;
+        float acc = 0.f;
+        for (int i = 0; i < n; ++i) acc = fmaf(pwr[lo + i], sm.mw[o + i], acc);
+        orow[mb] = __logf(acc + p.mel_eps);
       }
-    } else if (live) {
+    } else {
       if (HAS_VIDEO) {
         if (p.V <= 144) {
 #pragma unroll
           for (int i = 0; i < 9; ++i) {
             const int c = q + 16 * i;
-            if (c < p.V) xrow[257 + c] = __half_as_ushort(__float2half_rn(vv[i]));
+            if (c < p.V) xrow[257 - q + c] = __half_as_ushort(__float2half_rn(vv[i]));
           }
         } else {
           const float* vs = p.video + row_bt * p.V;
-          for (int c = q; c < p.V; c += 16) xrow[257 + c] = __half_as_ushort(__float2half_rn(__ldg(vs + c)));
+          for (int c = q; c < p.V; c += 16) xrow[257 - q + c] = __half_as_ushort(__float2half_rn(__ldg(vs + c)));
         }
       }
       if (!p.xh_skip_pad)
-        for (int c = 257 + (HAS_VIDEO ? p.V : 0) + q; c < p.ldx; c += 16) xrow[c] = 0;
+        for (int c = 257 + (HAS_VIDEO ? p.V : 0) + q; c < p.ldx; c += 16) xrow[c - q] = 0;
     }
     __syncwarp();
+    b = bn;
+    t = tn;
   }
   if (HOLES) {
     holes = warp_sum(holes);
@@ -484,6 +624,7 @@ extern "C" int avsi_frontend_fwd(const avsi_frontend_args* a, void* stream) {
                         !a->feat_out && !a->hole_count && (a->N % 2 == 0) && ((uintptr_t)a->wav % 8 == 0) &&
                         (!a->mel_masked || !a->mask || a->F == 257);
   if (train_path || mel_path) {
+    AVSI_REQUIRE(total < (1LL << 31) - (1LL << 24), "B*T must fit 32 bits");
     const int tsm = (int)sizeof(FrontendTrainSmem);
     static bool tattr = false;
     if (!tattr) {
