@@ -153,8 +153,11 @@ class BLSTMEngine(object):
         return ws
 
     # ---- forward ------------------------------------------------------------------------------
-    def forward(self, ws):
-        """ws['x0'] (time-major fp16 network input) -> ws['logits'] [T*B, nop] fp32."""
+    def forward(self, ws, dropout=None):
+        """ws['x0'] (time-major fp16 network input) -> ws['logits'] [T*B, nop] fp32.
+
+        dropout = (rate, seed, offset): tf.nn.dropout on the last layer's outputs ahead of the head (models.py:117);
+        the mask is a function of (seed, offset) only, backward() regenerates it."""
         lib = _lib.load()
         L = self.layout
         T, B, M = ws['T'], ws['B'], ws['M']
@@ -172,6 +175,15 @@ class BLSTMEngine(object):
                 _lib.check(lib.avsi_lstm_fwd(_p(G), _p(self.half['whh%d' % l]), _p(self.bias_fwd[l]), _p(ws['Y'][l]), _p(C),
                                              T, B, _lib.stream_ptr()), 'avsi_lstm_fwd')
             x, ldx = ws['Y'][l], NY
+        ws['drop'] = None
+        if dropout is not None and dropout[0] > 0.0:
+            if 'Ydrop' not in ws:
+                ws['Ydrop'] = torch.empty(M, NY, dtype=torch.float16, device=self.device)
+            with _lib.span('dropout', nbytes=2 * M * NY * 2):
+                _lib.check(lib.avsi_dropout_f16(_p(x), NY, _p(ws['Ydrop']), NY, M, NY, float(dropout[0]), int(dropout[1]),
+                                                int(dropout[2]), None, _lib.stream_ptr()), 'avsi_dropout_f16')
+            x = ws['Ydrop']
+            ws['drop'] = (float(dropout[0]), int(dropout[1]), int(dropout[2]))
         gemm(_p(x), NY, _p(self.half['head']), NY, _p(ws['logits']), L.nop, _p(self.view(self.theta, 'head_b')),
              M, L.n_out, NY, 0, 1, tag='gemm_head_fwd')
         return ws['logits']
@@ -187,13 +199,18 @@ class BLSTMEngine(object):
             self.grad.zero_()
         g = self.grad
         dl = ws['dlogits']
-        ylast = ws['Y'][L.n_layers - 1]
+        drop = ws.get('drop')
+        ylast = ws['Ydrop'] if drop else ws['Y'][L.n_layers - 1]
         # head: dW = dlogits^T . Y ; db = colsum(dlogits) ; dY = dlogits . Whead
         gemm(_p(dl), L.nop, _p(ylast), NY, _p(self.view(g, 'head_w')), NY, None, L.n_out, NY, M, 1, 2,
              pick_split_k(L.n_out, NY, M), tag='gemm_dw')
         _lib.check(lib.avsi_colsum_f16(_p(dl), L.nop, M, 0, L.n_out, _p(self.view(g, 'head_b')), st()), 'avsi_colsum_f16')
         dY = ws['dY'][0]
         gemm(_p(dl), L.nop, _p(self.half['headT']), L.nop, _p(dY), NY, None, M, NY, L.nop, 0, 0, tag='gemm_dx')
+        if drop:
+            with _lib.span('dropout', nbytes=2 * M * NY * 2):
+                _lib.check(lib.avsi_dropout_f16(_p(dY), NY, _p(dY), NY, M, NY, drop[0], drop[1], drop[2], None, st()),
+                           'avsi_dropout_f16')
         cur = 0
         for l in range(L.n_layers - 1, -1, -1):
             G, C, Y = ws['G'][l], ws['C'][l], ws['Y'][l]

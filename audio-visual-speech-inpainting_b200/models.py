@@ -69,6 +69,8 @@ class StackedBLSTMModel(object):
                                   device=self.device)
         self.engine.load_canonical(init_canonical(self.engine.layout, seed=config.get('seed', 0)))
         self.global_step = 0
+        self.dropout_seed = int(config.get('seed', 0))
+        self._feeds = 0
         self._sums = torch.zeros(8, dtype=torch.float64, device=self.device)
         self._cache = {}
         self._fed = {}
@@ -109,13 +111,34 @@ class StackedBLSTMModel(object):
             elif k in i32:
                 self._fed[k] = self._to_dev(v, torch.int32)
             elif k == 'dropout_rate':
-                if float(v) != 0.0:
-                    raise NotImplementedError('dropout_rate != 0 is not supported (0.0 in every shipped config)')
-                self._fed[k] = 0.0
+                if not 0.0 <= float(v) < 1.0:
+                    raise ValueError('dropout_rate must be in [0, 1)')
+                self._fed[k] = float(v)
             else:
                 raise KeyError('unknown feed name %r' % k)
         self._cache = {}
+        self._feeds += 1                     # a new sess.run: a new dropout mask (tf.nn.dropout draws per run)
         return self
+
+    def _dropout(self):
+        """(rate, seed, offset) of the current feed, or None: tf.nn.dropout(rnn_outputs, rate) of models.py:117."""
+        rate = self._fed.get('dropout_rate', 0.0)
+        return (rate, self.dropout_seed, self._feeds) if rate > 0.0 else None
+
+    def dropout_keep_mask(self):
+        """The keep mask of the current feed as bool [B, T, 2H] (fw units, then bw units), or None.  For parity tests."""
+        d = self._dropout()
+        if d is None:
+            return None
+        fr = self._front()
+        from .blstm import HP, NY
+        M, H = fr['T'] * fr['B'], self.net_dim[-1]
+        ones = torch.ones(M, NY, dtype=torch.float16, device=self.device)
+        keep = torch.empty(M, NY, dtype=torch.uint8, device=self.device)
+        _lib.check(_lib.load().avsi_dropout_f16(_p(ones), NY, _p(ones), NY, M, NY, d[0], d[1], d[2], _p(keep),
+                                                _lib.stream_ptr()), 'avsi_dropout_f16')
+        k = keep.view(fr['T'], fr['B'], 2, HP)[:, :, :, :H].reshape(fr['T'], fr['B'], 2 * H)
+        return k.permute(1, 0, 2).bool()
 
     def _need(self, *names):
         for n in names:
@@ -170,7 +193,7 @@ class StackedBLSTMModel(object):
     def _logits(self):
         if 'logits' not in self._cache:
             fr = self._front()
-            self._cache['logits'] = self.engine.forward(fr['ws'])
+            self._cache['logits'] = self.engine.forward(fr['ws'], dropout=self._dropout())
         return self._cache['logits']
 
     def _bt(self, lo, n):

@@ -58,9 +58,11 @@ def build_model(config, batch, mean, std, is_training=True, device='cuda', proce
     return model
 
 
-def feed_batch(model, batch):
+def feed_batch(model, batch, dropout_rate=0.0):
+    """dropout_rate: config['dropout_rate'] on training steps, 0.0 on validation / inference (training.py:241, 303, 314)."""
     seq, lab_len, wav, _, labels, video, mask = batch
-    kw = dict(sequence_lengths=seq, target_sources=wav.astype(np.float32), masks=mask, video_features=video)
+    kw = dict(sequence_lengths=seq, target_sources=wav.astype(np.float32), masks=mask, video_features=video,
+              dropout_rate=dropout_rate)
     if model.MTL:
         kw.update(labels_lengths=lab_len, labels=labels)
     model.feed(**kw)
@@ -169,7 +171,7 @@ def train(config_file, max_steps=None):
         for batch in train_it:
             n_step += 1
             tot_step += 1
-            frames = feed_batch(model, batch)
+            frames = feed_batch(model, batch, dropout_rate=config['dropout_rate'])
             lr = model.learning_rate
             model.train_op()
             log_now = (n_step % 200 == 0 or n_step == 1)

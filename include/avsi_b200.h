@@ -189,6 +189,13 @@ int avsi_masked_l1(const float* logits, int ldl, const float* target, const floa
  * out[3] = holes.  loss = loss_hole + ctc_weight * mean_b(nll_b)  (models.py:1955). */
 int avsi_mtl_scales(const float* hole_count, int B, float ctc_weight, float* out, void* stream);
 
+/* Inverted dropout of the BLSTM outputs ahead of the head(s): tf.nn.dropout(rnn_outputs, rate=dropout_rate) at
+ * models.py:117, :1901, models_asr.py:120.  dst[r,c] = keep ? src[r,c] / (1 - rate) : 0 with keep = (u >= rate),
+ * u = Philox-4x32-10(seed; offset, element) -- a pure function of its arguments, so the backward pass applies the
+ * same call to dY.  src/dst f16 [rows, ld] (may alias), cols % 8 == 0; keep_out optional u8 [rows, cols]. */
+int avsi_dropout_f16(const void* src, int ld_src, void* dst, int ld_dst, int64_t rows, int cols, float rate,
+                     uint64_t seed, uint64_t offset, void* keep_out, void* stream);
+
 /* Column sums: out[n] += sum_r X[r, col0 + n] (f16 in, f32 out) -- bias gradients. */
 int avsi_colsum_f16(const uint16_t* X, int ldx, int rows, int col0, int ncols, float* out, void* stream);
 

@@ -105,12 +105,22 @@ def sequence_mask(seq_len, T, dtype):
     return (torch.arange(T)[None, :] < torch.as_tensor(seq_len)[:, None]).to(dtype)
 
 
-def forward_si(net_in, target, mask, seq_len, params, n_layers, l2=0.0):
+def _dropout(rnn, drop):
+    """tf.nn.dropout(rnn_outputs, rate) (models.py:117, :1901; models_asr.py:120) with a GIVEN keep mask:
+    drop = (keep [B,T,2H] of {0,1}, rate) -> rnn * keep / (1 - rate).  TF's own random stream is not reproducible
+    outside TF; parity is on the semantics, with the mask the CUDA kernel drew."""
+    if drop is None:
+        return rnn
+    keep, rate = drop
+    return rnn * torch.as_tensor(np.asarray(keep, np.float64), dtype=rnn.dtype) / (1.0 - float(rate))
+
+
+def forward_si(net_in, target, mask, seq_len, params, n_layers, l2=0.0, drop=None):
     """StackedBLSTMModel (models.py:89-159).  All inputs torch tensors.
 
     Returns dict(inference, prediction, loss, loss_func, loss_hole, loss_valid)."""
     B, T, F = target.shape
-    rnn = blstm_stack(net_in, params, n_layers)
+    rnn = _dropout(blstm_stack(net_in, params, n_layers), drop)
     inference = (rnn.reshape(B * T, -1) @ params['logits/weights'] + params['logits/biases']).reshape(B, T, F)
     prediction = sequence_mask(seq_len, T, target.dtype)[:, :, None] * inference           # :135-137
     ad = (target - prediction).abs()
@@ -122,11 +132,11 @@ def forward_si(net_in, target, mask, seq_len, params, n_layers, l2=0.0):
                 loss_func=loss_func, loss_hole=loss_hole, loss_valid=loss_valid, rnn=rnn)
 
 
-def forward_mtl(net_in, target, mask, seq_len, labels, lab_len, params, n_layers, ctc_weight, l2=0.0):
+def forward_mtl(net_in, target, mask, seq_len, labels, lab_len, params, n_layers, ctc_weight, l2=0.0, drop=None):
     """StackedBLSTMSSNNCTCLossModel (models.py:1873-1963), the runnable MTL model.
     Blank label = n_classes - 1 (tf.nn.ctc_loss convention)."""
     B, T, F = target.shape
-    rnn = blstm_stack(net_in, params, n_layers)
+    rnn = _dropout(blstm_stack(net_in, params, n_layers), drop)
     flat = rnn.reshape(B * T, -1)
     logits_ipt = (flat @ params['inpainting/weights'] + params['inpainting/biases']).reshape(B, T, F)
     logits_asr = (flat @ params['asr/weights'] + params['asr/biases']).reshape(B, T, -1)
@@ -143,10 +153,10 @@ def forward_mtl(net_in, target, mask, seq_len, labels, lab_len, params, n_layers
                 ctc_loss=ctc_loss, ctc_nll=nll, rnn=rnn)
 
 
-def forward_asr(net_in, seq_len, labels, lab_len, params, n_layers, l2=0.0):
+def forward_asr(net_in, seq_len, labels, lab_len, params, n_layers, l2=0.0, drop=None):
     """models_asr.StackedBLSTMModel (models_asr.py:87-160): BLSTM stack -> logits head -> mean CTC NLL."""
     B, T, _ = net_in.shape
-    rnn = blstm_stack(net_in, params, n_layers)
+    rnn = _dropout(blstm_stack(net_in, params, n_layers), drop)
     logits = (rnn.reshape(B * T, -1) @ params['logits/weights'] + params['logits/biases']).reshape(B, T, -1)
     nll = octc.ctc_nll_torch(logits.transpose(0, 1), labels, lab_len, seq_len)                # models_asr.py:146-148
     ctc_loss = nll.mean()

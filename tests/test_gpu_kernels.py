@@ -588,3 +588,53 @@ def test_feature_stats_counts_and_large():
     assert n == cnt
     assert np.allclose(mean, xs.sum(0) / cnt, rtol=1e-12, atol=1e-14)
     assert np.allclose(std, np.sqrt((xs ** 2).sum(0) / cnt - (xs.sum(0) / cnt) ** 2), rtol=1e-10)
+
+
+from philox_ref import philox4x32_10 as _philox4x32_10  # noqa: E402
+
+
+@pytest.mark.parametrize('rate', [0.0, 0.25, 0.5])
+def test_dropout_kernel(rate):
+    """avsi_dropout_f16 (tf.nn.dropout of models.py:117): keep = (u >= rate) from Philox-4x32-10 keyed by (seed; offset,
+    chunk) -- bit-exact against the Python restatement; kept values scaled by 1/(1-rate); deterministic in (seed, offset)."""
+    from avsi_b200 import _lib
+    lib = _lib.load()
+    d = dev()
+    rows, cols, ld = 301, 512, 512
+    g = torch.Generator(device='cpu').manual_seed(3)
+    x = torch.randn(rows, ld, generator=g).half().to(d)
+    seed, offset = 0x123456789ABCDEF, 77
+
+    def run(src, seed, offset, inplace=False):
+        dst = src if inplace else torch.empty_like(src)
+        keep = torch.empty(rows, cols, dtype=torch.uint8, device=d)
+        _lib.check(lib.avsi_dropout_f16(_lib.ptr(src), ld, _lib.ptr(dst), ld, rows, cols, rate, seed, offset, _lib.ptr(keep),
+                                        _lib.stream_ptr()), 'avsi_dropout_f16')
+        return dst, keep
+    y, keep = run(x, seed, offset)
+    y2, keep2 = run(x, seed, offset)
+    assert torch.equal(y, y2) and torch.equal(keep, keep2)
+    k = keep.bool()
+    ref = torch.where(k, (x.float() * (1.0 / (1.0 - rate))), torch.zeros_like(x, dtype=torch.float32)).half()
+    assert torch.equal(y, ref)
+    frac = k.float().mean().item()
+    n = rows * cols
+    assert abs(frac - (1 - rate)) <= 5 * np.sqrt(max(rate * (1 - rate), 1e-12) / n) + 1e-9
+    if rate > 0:
+        _, keep3 = run(x, seed, offset + 1)
+        _, keep4 = run(x, seed + 1, offset)
+        assert not torch.equal(keep, keep3) and not torch.equal(keep, keep4)
+        # bit-exact against the restatement on the first chunks: chunk i (8 halves) draws two Philox blocks with
+        # counter (i_lo, i_hi, offset_lo, 2*offset_hi + {0,1}) and key (seed_lo, seed_hi)
+        thresh = int(rate * 4294967296.0)
+        kh = keep.cpu().numpy().reshape(-1, 8)
+        for i in (0, 1, 63, 64, 5000):
+            r = []
+            for half in (0, 1):
+                r += _philox4x32_10([i & 0xFFFFFFFF, i >> 32, offset & 0xFFFFFFFF, ((offset >> 32) << 1) | half],
+                                    [seed & 0xFFFFFFFF, seed >> 32])
+            assert [int(v >= thresh) for v in r] == kh[i].tolist(), i
+    # in place (the backward pass applies the mask to dY in place)
+    z = x.clone()
+    z, _ = run(z, seed, offset, inplace=True)
+    assert torch.equal(z, y)

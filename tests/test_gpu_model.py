@@ -379,3 +379,35 @@ def test_asr_model_forward_loss_gradients(inp, apply_mask, B):
     th0 = model.engine.theta.clone()
     model.train_op()
     assert not torch.equal(th0, model.engine.theta) and model.per.shape == (B,)
+
+
+@pytest.mark.parametrize('model_name,B', [('av-blstm', 4), ('av-blstm-ssnn-ctc', 230)])
+def test_dropout_forward_and_gradients(model_name, B):
+    """dropout_rate > 0 (tf.nn.dropout on the BLSTM outputs ahead of the heads, models.py:117 / :1901): the oracle is
+    given the keep mask the kernel drew; outputs, loss and gradients then agree to the usual tolerances.  Every feed
+    (= sess.run) draws a new mask."""
+    from oracle import blstm as oblstm
+    audio_len = 11520 if 'ctc' in model_name else 4800
+    kw = dict(ctc_loss=0.05) if 'ctc' in model_name else {}
+    model, batch, canon, inp = _build(model_name, B, audio_len, seed=60 + B, **kw)
+    rate = 0.3
+    model.feed(dropout_rate=rate)
+    keep = model.dropout_keep_mask().cpu().numpy()
+    assert keep.shape == (B, batch['T'], 500) and abs(keep.mean() - (1 - rate)) < 0.01
+    tsn, net_in = _oracle_inputs(batch, inp)
+    if 'ctc' in model_name:
+        outs, ograds = oblstm.loss_and_grads(
+            'mtl', dict(net_in=net_in, target=tsn, mask=batch['mask'], seq_len=batch['seq_len'], labels=batch['labels'],
+                        lab_len=batch['lab_len']), canon, 3, ctc_weight=0.05, drop=(keep, rate))
+    else:
+        outs, ograds = oblstm.loss_and_grads('si', dict(net_in=net_in, target=tsn, mask=batch['mask'],
+                                                        seq_len=batch['seq_len']), canon, 3, drop=(keep, rate))
+    assert rel_l2(model.prediction.cpu().numpy(), outs['prediction']) < TOL
+    assert abs(float(model.loss) - float(outs['loss'])) < TOL * abs(float(outs['loss']))
+    _check_grads(model.canonical_gradients(), ograds, model_name + ' dropout')
+    p1 = model.prediction.cpu().numpy()
+    model.feed(dropout_rate=rate)                      # next run: another mask
+    assert not np.array_equal(model.dropout_keep_mask().cpu().numpy(), keep)
+    assert not np.array_equal(model.prediction.cpu().numpy(), p1)
+    model.feed(dropout_rate=0.0)
+    assert model.dropout_keep_mask() is None
