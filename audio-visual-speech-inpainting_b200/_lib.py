@@ -56,6 +56,8 @@ SIGNATURES = {
                                     c_void_p]),
     'avsi_video_features': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'avsi_expand_mask': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'avsi_ctc_beam_search_host': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,
+                                          c_void_p, c_void_p, c_void_p, c_int]),
     'avsi_dropout_f16': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_float, c_uint64, c_uint64, c_void_p,
                                  c_void_p]),
     'avsi_feature_stats': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -624,9 +624,9 @@ extern "C" int avsi_gemm_f16(const uint16_t* A, int lda, const uint16_t* B, int 
   static int use_2sm = -1;
   if (use_2sm < 0) {
     const char* e = getenv("AVSI_GEMM_2SM");
-    use_2sm = (e && e[0] == '0') ? 0 : 1;
+    use_2sm = (e && e[0] == '0') ? 0 : (e && e[0] == '2') ? 2 : 1;
   }
-  if (use_2sm && N >= 256 && ((N + 255) / 256) * 256 * 3 <= N * 4 && (long long)M * N * K >= (1LL << 29)) {
+  if (use_2sm && N >= 256 && (use_2sm == 2 || ((N + 255) / 256) * 256 * 3 <= N * 4) && (long long)M * N * K >= (1LL << 29)) {
     // split-K only as far as needed to give every SM pair a work item
     const int m_t = (M + 255) / 256, n_t = (N + 255) / 256, kbt = (K + GEMM_BK - 1) / GEMM_BK;
     if (out_mode == 2) {

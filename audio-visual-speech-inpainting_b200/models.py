@@ -423,7 +423,7 @@ class StackedBLSTMSSNNCTCLossModel(StackedBLSTMModel):
     @property
     def per(self):
         """Phone error rate per utterance: edit distance(decoded, labels) / label length (models.py:1718 uses
-        tf.edit_distance on the beam-search output; here on the best-path decoding, host side, off the hot loop)."""
+        tf.edit_distance on the beam-search output), host side, off the hot loop."""
         dec = self.decoding
         labels = self._fed['labels'].cpu().numpy()
         lens = self._fed['labels_lengths'].cpu().numpy()
@@ -440,28 +440,45 @@ class StackedBLSTMSSNNCTCLossModel(StackedBLSTMModel):
             out[b] = prev[-1] / max(1, len(ref))
         return out
 
-    @property
-    def decoding(self):
-        """Best-path (greedy) CTC decoding; the reference's beam search (width 20, models.py:1627) is a
-        monitoring op kept off the training hot loop."""
+    BEAM_WIDTH = 20                          # models.py:1627, :2027
+    decoder = 'beam'                         # 'greedy' = best-path decoding (cheaper monitoring)
+
+    def _decode(self, col0):
+        """`decoding` of the reference: tf.nn.ctc_beam_search_decoder(tm_logits, sequence_lengths, beam_width)
+        (top path, merge_repeated=True) -> dense int32 [B, max decoded length] padded with -1.  Host side, as in
+        TensorFlow; it runs when the driver asks for `decoding` / `per`, never inside train_op."""
+        import ctypes
         fr = self._front()
-        logits = self._logits().view(fr['T'], fr['B'], -1)[:, :, self.audio_feat_dim:self.audio_feat_dim + self.num_classes]
-        best = logits.argmax(dim=2).t().cpu().numpy()
-        seq = self._fed['sequence_lengths'].cpu().numpy()
-        blank = self.num_classes - 1
-        outs = []
-        for b in range(best.shape[0]):
-            prev, seqo = -1, []
-            for k in best[b, :int(seq[b])]:
-                if k != prev and k != blank:
-                    seqo.append(int(k))
-                prev = k
-            outs.append(seqo)
+        T, B, C = fr['T'], fr['B'], self.num_classes
+        seq = np.ascontiguousarray(self._fed['sequence_lengths'].cpu().numpy(), np.int32)
+        logits = self._logits()
+        if self.decoder == 'greedy':
+            best = logits.view(T, B, -1)[:, :, col0:col0 + C].argmax(dim=2).t().cpu().numpy()
+            outs = []
+            for b in range(B):
+                prev, seqo = -1, []
+                for k in best[b, :int(seq[b])]:
+                    if k != prev and k != C - 1:
+                        seqo.append(int(k))
+                    prev = k
+                outs.append(seqo)
+        else:
+            host = np.ascontiguousarray(logits.detach().cpu().numpy(), np.float32)       # [T*B, nop] time-major
+            out = np.empty((B, T), np.int32)
+            n = np.zeros(B, np.int32)
+            vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+            _lib.check(_lib.load().avsi_ctc_beam_search_host(vp(host), T, B, host.shape[1], col0, C, vp(seq), self.BEAM_WIDTH,
+                                                             1, T, vp(out), vp(n), None, 0), 'avsi_ctc_beam_search_host')
+            outs = [out[b, :n[b]].tolist() for b in range(B)]
         width = max([len(o) for o in outs] + [1])
-        dense = -np.ones((len(outs), width), np.int32)
+        dense = -np.ones((B, width), np.int32)
         for b, o in enumerate(outs):
             dense[b, :len(o)] = o
         return dense
+
+    @property
+    def decoding(self):
+        return self._decode(self.audio_feat_dim)
 
 
 # In the reference, StackedBLSTMCTCLossModel.inference is broken (models.py:1565-1566 uses an undefined

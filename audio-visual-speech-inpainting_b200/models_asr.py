@@ -4,7 +4,7 @@ Same constructor signature and attribute names as the reference class: power-2 s
 apply_mask) -> log-mel-80 -> normalisation -> (concat video) -> stacked BLSTM -> `logits` head -> mean CTC loss,
 Adam / SGD / Momentum.  Every stage reuses the kernels of the inpainting path: the fused front end's `fbanks`
 variant, avsi_features_to_x0, the projection GEMMs, the recurrence kernels, the CTC kernel.  The beam-search
-decoder of models_asr.py:132-135 is replaced by best-path decoding (monitoring only, off the training step)."""
+decoder of models_asr.py:132-135 runs on the host (avsi_ctc_beam_search_host), off the training step."""
 import numpy as np
 import torch
 
@@ -120,25 +120,11 @@ class StackedBLSTMModel(_InpaintingModel):
     def _grad_unscale(self, out, world):
         return 1.0 / (self.GRAD_SCALE * self._front()['B'] * world), None
 
-    per = _MTLModel.per                      # edit distance of the best-path decoding (models_asr.py:162-166)
+    per = _MTLModel.per                      # edit distance of the decoding against the labels (models_asr.py:162-166)
+    decoder = 'beam'
+    BEAM_WIDTH = 100                         # tf.nn.ctc_beam_search_decoder default (models_asr.py:132-135)
+    _decode = _MTLModel._decode
 
     @property
     def decoding(self):
-        fr = self._front()
-        logits = self._logits().view(fr['T'], fr['B'], -1)[:, :, :self.num_classes]
-        best = logits.argmax(dim=2).t().cpu().numpy()
-        seq = self._fed['sequence_lengths'].cpu().numpy()
-        blank = self.num_classes - 1
-        outs = []
-        for b in range(best.shape[0]):
-            prev, so = -1, []
-            for k in best[b, :int(seq[b])]:
-                if k != prev and k != blank:
-                    so.append(int(k))
-                prev = k
-            outs.append(so)
-        width = max([len(o) for o in outs] + [1])
-        dense = -np.ones((len(outs), width), np.int32)
-        for b, o in enumerate(outs):
-            dense[b, :len(o)] = o
-        return dense
+        return self._decode(0)

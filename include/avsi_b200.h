@@ -212,6 +212,16 @@ int avsi_ctc_loss(const float* logits, int ldl, int col0, int C, const int32_t* 
                   const float* grad_scale_dev, float* nll, uint16_t* dlogits, int ldd, int dcol0,
                   void* workspace, void* stream);
 
+/* CTC prefix beam search, HOST memory in and out (the reference's decoder is a CPU op too and runs at logging /
+ * validation steps only): tf.nn.ctc_beam_search_decoder(tm_logits, sequence_lengths, beam_width=20) at
+ * models.py:1627, :2027, models_asr.py:139.  logits [T*B, ldl] f32 time-major on the host, classes at columns
+ * col0 .. col0+C-1, blank = C-1; out [B, max_out] i32 padded with -1 (tf.sparse.to_dense(default_value=-1)),
+ * out_len [B], log_prob [B] optional.  merge_repeated != 0 collapses consecutive equal labels of the emitted
+ * path (TF-1 default).  n_threads <= 0: all host cores. */
+int avsi_ctc_beam_search_host(const float* logits, int T, int B, int ldl, int col0, int C, const int* seq_len,
+                              int beam_width, int merge_repeated, int max_out, int* out, int* out_len,
+                              float* log_prob, int n_threads);
+
 /* ------------------------------------------------------------------------------------
  * Optimiser.  Replaces tf.train.AdamOptimizer ApplyAdam (models.py:168,178), TF epsilon-hat form.
  *   g is multiplied by grad_unscale first; l2 adds l2 * theta to the gradient (models.py:153-158). */

@@ -142,3 +142,56 @@ def greedy_decode(logits_tbc, seq_len, blank=None):
     blank = C - 1 if blank is None else blank
     best = logits.argmax(2)
     return [_collapse(list(best[:int(seq_len[b]), b]), blank) for b in range(B)]
+
+
+def ctc_beam_search(logits, beam_width=20, merge_repeated=True):
+    """tf.nn.ctc_beam_search_decoder(inputs, sequence_length, beam_width=20, top_paths=1, merge_repeated=True) as the
+    reference calls it (models.py:1627, :2027; models_asr.py:139), restated: prefix beam search over the log-softmax
+    of logits [T, C], blank = C - 1, every label extended at every frame.  Returns (labels, log_prob).
+    merge_repeated is TF-1's post-processing: consecutive equal labels of the emitted path are collapsed."""
+    lg = np.asarray(logits, np.float64)
+    T, C = lg.shape
+    blank = C - 1
+    lp = lg - (lg.max(1, keepdims=True) + np.log(np.exp(lg - lg.max(1, keepdims=True)).sum(1, keepdims=True)))
+    beam = {(): (0.0, -np.inf)}                       # prefix -> (log p ending in blank, log p ending in its last label)
+    for t in range(T):
+        nxt = {}
+
+        def add(key, pb, pnb):
+            ob, onb = nxt.get(key, (-np.inf, -np.inf))
+            nxt[key] = (np.logaddexp(ob, pb), np.logaddexp(onb, pnb))
+        for y, (pb, pnb) in beam.items():
+            tot = np.logaddexp(pb, pnb)
+            add(y, tot + lp[t, blank], pnb + lp[t, y[-1]] if y else -np.inf)
+            for c in range(C):
+                if c == blank:
+                    continue
+                frm = pb if (y and y[-1] == c) else tot
+                if frm > -np.inf:
+                    add(y + (c,), -np.inf, frm + lp[t, c])
+        items = sorted(nxt.items(), key=lambda kv: (-np.logaddexp(*kv[1]), kv[0]))
+        beam = dict(items[:beam_width])
+    best, (pb, pnb) = max(beam.items(), key=lambda kv: np.logaddexp(*kv[1]))
+    out = [c for i, c in enumerate(best) if not (merge_repeated and i > 0 and c == best[i - 1])]
+    return out, float(np.logaddexp(pb, pnb))
+
+
+def ctc_best_labeling_bruteforce(logits):
+    """argmax over LABELINGS of the total alignment probability, by enumerating all C**T alignments (tiny cases)."""
+    import itertools
+    lg = np.asarray(logits, np.float64)
+    T, C = lg.shape
+    blank = C - 1
+    lp = lg - np.log(np.exp(lg).sum(1, keepdims=True))
+    tot = {}
+    for path in itertools.product(range(C), repeat=T):
+        lab, prev = [], -1
+        for k in path:
+            if k != prev and k != blank:
+                lab.append(k)
+            prev = k
+        p = float(sum(lp[t, k] for t, k in enumerate(path)))
+        key = tuple(lab)
+        tot[key] = np.logaddexp(tot.get(key, -np.inf), p)
+    best = max(tot.items(), key=lambda kv: kv[1])
+    return list(best[0]), float(best[1]), tot

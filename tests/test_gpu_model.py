@@ -165,8 +165,31 @@ def test_mtl_forward_loss_gradients(model_name):
     assert abs(float(model.ctc_loss) - float(outs['ctc_loss'])) < TOL * float(outs['ctc_loss'])
     assert abs(float(model.loss) - float(outs['loss'])) < TOL * float(outs['loss'])
     _check_grads(model.canonical_gradients(), ograds, model_name)
+    # `decoding` = beam search (width 20, merge_repeated) on the asr logits, `per` = edit distance / label length:
+    # the host routine on the CUDA logits against the restatement on the SAME logits (near-ties between beams could
+    # otherwise flip with the 2e-3 logit tolerance), plus greedy decoding against the oracle's best path
+    from oracle import ctc as octc
     dec = model.decoding
+    got_asr = asr.cpu().numpy()
     assert dec.shape[0] == B and dec.max() < 33
+    for b in range(B):
+        ref, _ = octc.ctc_beam_search(got_asr[b, :int(batch['seq_len'][b])], beam_width=20, merge_repeated=True)
+        assert [int(x) for x in dec[b] if x >= 0] == ref, b
+    per = model.per
+    for b in range(B):
+        hyp = [int(x) for x in dec[b] if x >= 0]
+        lab = [int(x) for x in batch['labels'][b, :int(batch['lab_len'][b])]]
+        d = np.zeros((len(hyp) + 1, len(lab) + 1), np.int64)
+        d[:, 0], d[0, :] = np.arange(len(hyp) + 1), np.arange(len(lab) + 1)
+        for i in range(1, len(hyp) + 1):
+            for j in range(1, len(lab) + 1):
+                d[i, j] = min(d[i - 1, j] + 1, d[i, j - 1] + 1, d[i - 1, j - 1] + (hyp[i - 1] != lab[j - 1]))
+        assert abs(per[b] - d[-1, -1] / max(1, len(lab))) < 1e-6
+    model.decoder = 'greedy'
+    greedy = octc.greedy_decode(np.transpose(got_asr, (1, 0, 2)), batch['seq_len'])
+    gd = model.decoding
+    for b in range(B):
+        assert [int(x) for x in gd[b] if x >= 0] == [int(x) for x in greedy[b]]
 
 
 def test_train_step_matches_oracle_adam_and_learns():
