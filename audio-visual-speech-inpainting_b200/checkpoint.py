@@ -2,8 +2,10 @@
 
 tf.train.Saver() in the reference writes every global variable: the model variables in canonical layout, the
 unnamed global step `Variable`, and the Adam slots `<var>/Adam`, `<var>/Adam_1`, `beta1_power`, `beta2_power`
-(training.py:114,267,335).  TensorFlow's bundle format needs TF; the same name -> array mapping is stored as one
-`.npz` per checkpoint (`netmodel/ckpt.npz`, `netmodel/sinet.npz`), '/' in names kept as-is via a name table."""
+(training.py:114,267,335).  Two containers hold the same name -> array mapping: one `.npz` per checkpoint
+(`netmodel/ckpt.npz`, `netmodel/sinet.npz`; '/' in names kept as-is via a name table) and TensorFlow's own tensor
+bundle (`sinet.index` + `sinet.data-00000-of-00001`, tf_bundle.py) so that checkpoints move between the two
+implementations in either direction.  `load` / `restore` take either; `save(..., fmt='tf')` writes the bundle."""
 import json
 import os
 
@@ -26,11 +28,16 @@ def _adam_slots(model):
     return out
 
 
-def save(model, path, with_optimizer=True):
-    """Write `<path>.npz` (path as given to saver.save in the reference, e.g. .../netmodel/sinet)."""
+def save(model, path, with_optimizer=True, fmt='npz'):
+    """Write `<path>.npz`, or with fmt='tf' the tensor bundle `<path>.index` / `<path>.data-00000-of-00001`
+    (path as given to saver.save in the reference, e.g. .../netmodel/sinet)."""
     variables = dict(model.all_vars)
     if with_optimizer and model.optimizer_choice == 'adam':
         variables.update(_adam_slots(model))
+    if fmt == 'tf':
+        from . import tf_bundle
+        variables.pop('__adam_step__', None)                 # not a TF variable: recovered from beta1_power
+        return tf_bundle.write_bundle(path, {k: np.asarray(v) for k, v in variables.items()})
     names = sorted(variables)
     arrays = {'v%05d' % i: np.asarray(variables[n]) for i, n in enumerate(names)}
     arrays['__names__'] = np.frombuffer(json.dumps(names).encode(), np.uint8)
@@ -41,6 +48,9 @@ def save(model, path, with_optimizer=True):
 
 def load(path):
     """`<path>.npz` -> {tf variable name: array}.  Raises ValueError like saver.restore on a bad checkpoint."""
+    if os.path.exists(path + '.index'):
+        from . import tf_bundle
+        return tf_bundle.read_bundle(path)
     f = path if path.endswith('.npz') else path + '.npz'
     if not os.path.exists(f):
         raise ValueError('%s is not a valid checkpoint' % path)
@@ -54,8 +64,13 @@ def restore(model, path, train_vars_only=False):
     import torch
     variables = load(path)
     model.assign_vars(variables)
-    if train_vars_only or '__adam_step__' not in variables:
+    if train_vars_only:
         return model
+    if '__adam_step__' not in variables:
+        if 'beta1_power' not in variables:
+            return model
+        # a TensorFlow bundle: Adam's step count is beta1_power = 0.9 ** t
+        variables['__adam_step__'] = int(round(np.log(max(float(variables['beta1_power']), 1e-300)) / np.log(0.9)))
     eng = model.engine
     want = eng.layout.canonical_shapes()
     m = {k: variables[model._scoped(k) + '/Adam'] for k in want}

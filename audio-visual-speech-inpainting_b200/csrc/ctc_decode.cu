@@ -131,3 +131,36 @@ extern "C" int avsi_ctc_beam_search_host(const float* logits, int T, int B, int 
   }
   return AVSI_OK;
 }
+
+// CRC-32C (Castagnoli) over host memory, slicing-by-8: TFRecord frames (tfrecord_utils.py via tf.python_io) and the
+// tensor-bundle checkpoints of tf.train.Saver (training.py:114,267,335) checksum every record / tensor with it.
+extern "C" uint32_t avsi_crc32c_host(const void* data, uint64_t n, uint32_t crc) {
+  static uint32_t tab[8][256];
+  static std::atomic<int> ready(0);
+  if (!ready.load(std::memory_order_acquire)) {
+    uint32_t t[8][256];
+    for (uint32_t i = 0; i < 256; ++i) {
+      uint32_t c = i;
+      for (int k = 0; k < 8; ++k) c = (c & 1) ? (c >> 1) ^ 0x82F63B78u : c >> 1;
+      t[0][i] = c;
+    }
+    for (uint32_t i = 0; i < 256; ++i)
+      for (int s = 1; s < 8; ++s) t[s][i] = (t[s - 1][i] >> 8) ^ t[0][t[s - 1][i] & 0xFF];
+    for (int s = 0; s < 8; ++s)
+      for (int i = 0; i < 256; ++i) tab[s][i] = t[s][i];
+    ready.store(1, std::memory_order_release);
+  }
+  const unsigned char* p = static_cast<const unsigned char*>(data);
+  uint32_t c = ~crc;
+  while (n >= 8) {
+    const uint32_t lo = (uint32_t)p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16 | (uint32_t)p[3] << 24;
+    const uint32_t hi = (uint32_t)p[4] | (uint32_t)p[5] << 8 | (uint32_t)p[6] << 16 | (uint32_t)p[7] << 24;
+    const uint32_t x = c ^ lo;
+    c = tab[7][x & 0xFF] ^ tab[6][(x >> 8) & 0xFF] ^ tab[5][(x >> 16) & 0xFF] ^ tab[4][x >> 24] ^
+        tab[3][hi & 0xFF] ^ tab[2][(hi >> 8) & 0xFF] ^ tab[1][(hi >> 16) & 0xFF] ^ tab[0][hi >> 24];
+    p += 8;
+    n -= 8;
+  }
+  while (n--) c = tab[0][(c ^ *p++) & 0xFF] ^ (c >> 8);
+  return ~c;
+}

@@ -71,6 +71,7 @@ class StackedBLSTMModel(object):
         self.global_step = 0
         self.dropout_seed = int(config.get('seed', 0))
         self._feeds = 0
+        self._stale = False
         self._sums = torch.zeros(8, dtype=torch.float64, device=self.device)
         self._cache = {}
         self._fed = {}
@@ -117,6 +118,7 @@ class StackedBLSTMModel(object):
             else:
                 raise KeyError('unknown feed name %r' % k)
         self._cache = {}
+        self._stale = False
         self._feeds += 1                     # a new sess.run: a new dropout mask (tf.nn.dropout draws per run)
         return self
 
@@ -306,6 +308,12 @@ class StackedBLSTMModel(object):
         """forward + loss + backward; leaves the (scaled) gradient in engine.grad."""
         if not self.is_training:
             raise _lib.AvsiError('model was built with is_training=False')
+        if self._stale:
+            # the weights moved since these activations were computed (train_op without a new feed): run again.
+            # Reads between the two calls keep returning the values of the run that produced the update, as
+            # sess.run([train_op, loss]) does
+            self._cache = {k: v for k, v in self._cache.items() if k.startswith('front')}
+            self._stale = False
         out = self._loss_pass(True, want_pred=False)
         self.engine.backward(self._front()['ws'])
         return out
@@ -333,6 +341,7 @@ class StackedBLSTMModel(object):
             self.engine.sgd_step(self.learning_rate, 0.9 if self.optimizer_choice == 'momentum' else None,
                                  grad_unscale=host, unscale_dev=dev, l2=self.regularization)
         self.global_step += 1
+        self._stale = True
 
     def canonical_gradients(self):
         """d loss / d variable in the reference's canonical layout (float64 numpy), for parity tests."""
@@ -387,6 +396,7 @@ class StackedBLSTMModel(object):
         if gs is not None:
             self.global_step = int(gs)
         self._cache = {}
+        self._stale = False
 
 
 class StackedBLSTMSSNNCTCLossModel(StackedBLSTMModel):

@@ -222,6 +222,11 @@ int avsi_ctc_beam_search_host(const float* logits, int T, int B, int ldl, int co
                               int beam_width, int merge_repeated, int max_out, int* out, int* out_len,
                               float* log_prob, int n_threads);
 
+/* CRC-32C (Castagnoli) of n bytes of HOST memory, continuing from `crc` (0 to start): the checksum of TFRecord
+ * frames (tfrecord_utils.py:19-41 via tf.python_io.TFRecordWriter) and of tf.train.Saver tensor bundles
+ * (training.py:114,267,335).  Known answer: "123456789" -> 0xE3069283. */
+uint32_t avsi_crc32c_host(const void* data, uint64_t n, uint32_t crc);
+
 /* ------------------------------------------------------------------------------------
  * Optimiser.  Replaces tf.train.AdamOptimizer ApplyAdam (models.py:168,178), TF epsilon-hat form.
  *   g is multiplied by grad_unscale first; l2 adds l2 * theta to the gradient (models.py:153-158). */

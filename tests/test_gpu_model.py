@@ -434,3 +434,29 @@ def test_dropout_forward_and_gradients(model_name, B):
     assert not np.array_equal(model.prediction.cpu().numpy(), p1)
     model.feed(dropout_rate=0.0)
     assert model.dropout_keep_mask() is None
+
+
+def test_checkpoint_round_trip_through_tf_bundle(tmp_path):
+    """saver.save / saver.restore through TensorFlow's own container (tf_bundle.py): variables under the TF names,
+    the global step, the Adam slots and the step count recovered from beta1_power."""
+    from avsi_b200 import checkpoint, tf_bundle
+    model, batch, canon, inp = _build('av-blstm-ssnn-ctc', 3, 11520, seed=9, ctc_loss=0.05)
+    for _ in range(3):
+        model.train_op()
+    prefix = str(tmp_path / 'netmodel' / 'sinet')
+    checkpoint.save(model, prefix, fmt='tf')
+    raw = tf_bundle.read_bundle(prefix)
+    pre = 'cudnn_lstm/stack_bidirectional_rnn/cell_0/bidirectional_rnn/fw/cudnn_compatible_lstm_cell/kernel'
+    assert any(k.endswith(pre) for k in raw) and any(k.endswith(pre + '/Adam_1') for k in raw)
+    assert abs(float(raw['beta1_power']) - 0.9 ** 3) < 1e-6
+    other, _, _, _ = _build('av-blstm-ssnn-ctc', 3, 11520, seed=10, ctc_loss=0.05)
+    checkpoint.restore(other, prefix)
+    assert torch.equal(other.engine.theta, model.engine.theta)
+    assert torch.equal(other.engine.adam_m, model.engine.adam_m) and torch.equal(other.engine.adam_v, model.engine.adam_v)
+    assert other.engine.step_count == 3 and other.global_step == model.global_step == 3
+    # a further step on both: `model` steps again on the same feed (activations recomputed with the moved weights),
+    # `other` from the restored state; split-K accumulation order is the only difference allowed (atol = 1 % of lr)
+    model.train_op()
+    other.feed(**{k: v for k, v in model._fed.items()})
+    other.train_op()
+    assert torch.allclose(other.engine.theta, model.engine.theta, rtol=0, atol=1e-5)
