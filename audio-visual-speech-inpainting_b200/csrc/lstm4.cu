@@ -84,7 +84,7 @@ __device__ unsigned long long g_l4_timing[16];
 template <int ACT, bool TIMING>
 __global__ void __cluster_dims__(L4_CL, 1, 1) __launch_bounds__(L4_THREADS, 1)
 lstm4_fwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whh, const float* __restrict__ bias,
-                 uint16_t* __restrict__ y, float* __restrict__ cst, int T, int B) {
+                 uint16_t* __restrict__ y, float* __restrict__ cst, int T, int B, int PREFETCH) {
   extern __shared__ unsigned char l4_smem_raw[];
   const uint32_t raw_s = smem_u32(l4_smem_raw);
   const uint32_t base_s = (raw_s + 127u) & ~127u;
@@ -218,6 +218,14 @@ lstm4_fwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whh,
             pre[p][i] = *reinterpret_cast<const uint4*>(gates + il16(grow, col0 + 8 * i, 2 * L4_G));
         }
       }
+      // the lines of the NEXT step are pulled into L2 now (a whole step ahead), so that its loads -- issued only
+      // when this step's epilogue is done -- are L2 hits instead of DRAM reads queued behind the stores
+      if (PREFETCH && row_ok && s + 1 < T && (lane & 7) == 0) {          // one lane per 128-byte line
+        const long long gn = (long long)(dir ? (t - 1) : (t + 1)) * B + row;
+        const int col0 = dir * L4_G + (j * 64 + cg * 16) * 4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) prefetch_l2(gates + il16(gn, col0 + 8 * i, 2 * L4_G));
+      }
       L4_TICK(0);
       if (s > 0) {
         mbar_wait(done_s, (uint32_t)((s - 1) & 1));
@@ -318,6 +326,11 @@ int launch_lstm4_fwd(uint16_t* gates, const uint16_t* whh, const float* bias, ui
     const char* t = getenv("AVSI_L4_TIMING");
     mode = ((e && !strcmp(e, "exact")) ? 1 : 0) | ((t && t[0] == '1') ? 2 : 0);
   }
+  static int pf = -1;                                // AVSI_L4_PREFETCH=0: no L2 prefetch of the next step (A/B runs)
+  if (pf < 0) {
+    const char* e = getenv("AVSI_L4_PREFETCH");
+    pf = (e && e[0] == '0') ? 0 : 1;
+  }
   const int smem = (int)sizeof(Lstm4Smem) + 128;
   const int grid = 2 * ((B + L4_BT - 1) / L4_BT) * L4_CL;
   static bool attr_done[4] = {false, false, false, false};
@@ -327,7 +340,7 @@ int launch_lstm4_fwd(uint16_t* gates, const uint16_t* whh, const float* bias, ui
       AVSI_CUDA(cudaFuncSetAttribute(lstm4_fwd_kernel<ACT_, TIM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
       attr_done[mode] = true;                                                                                          \
     }                                                                                                                  \
-    lstm4_fwd_kernel<ACT_, TIM_><<<grid, L4_THREADS, smem, st>>>(gates, whh, bias, y, cst, T, B);                      \
+    lstm4_fwd_kernel<ACT_, TIM_><<<grid, L4_THREADS, smem, st>>>(gates, whh, bias, y, cst, T, B, pf);                   \
   } while (0)
   if (mode == 0) L4_LAUNCH(0, false);
   else if (mode == 1) L4_LAUNCH(1, false);
