@@ -19,7 +19,7 @@ struct LerpPos {
 __device__ __forceinline__ LerpPos lerp_pos(int t, int L, int T) {
   const unsigned num = (unsigned)t * (unsigned)L;            // t < T, T * L < 2^31 checked by the launcher
   int i0 = (int)(num / (unsigned)T);
-  float w = (float)(num - (unsigned)i0 * (unsigned)T) / (float)T;
+  float w = (float)(num - (unsigned)i0 * (unsigned)T) * (1.0f / (float)T);   // same expression as the incremental walk
   if (i0 >= L - 1) {
     i0 = L - 1;
     w = 0.f;
@@ -27,49 +27,94 @@ __device__ __forceinline__ LerpPos lerp_pos(int t, int L, int T) {
   return {i0, min(i0 + 1, L - 1), w};
 }
 
+// One thread per (utterance, chunk of VF_CHUNK output frames, VEC feature columns): it walks its frames in order, so
+// the interpolation position advances incrementally (no division by T per frame), the landmark rows of frame t-1 are
+// the registers left by the previous iteration, and mean / std are loaded once.  A warp's lanes are consecutive column
+// vectors of one row: 16-byte loads and stores, coalesced.  HBM-bound on the [B,T,D] output.
+
 template <int VEC>
 __global__ void __launch_bounds__(256)
 video_features_kernel(const float* __restrict__ lm, const float* __restrict__ vmean, const float* __restrict__ vstd,
-                      int B, int L, int D, int T, float* __restrict__ out) {
-  const int dv = D / VEC;                            // vectors per frame
-  // one frame (b, t) per group of `dv` consecutive threads of a block row: 32-bit index arithmetic only
-  const int frames_per_block = blockDim.x / dv;
-  const int fl = threadIdx.x / dv;
-  if (fl >= frames_per_block) return;
-  const int d = (threadIdx.x - fl * dv) * VEC;
-  const long long total = (long long)B * T;
-  for (long long bt0 = (long long)blockIdx.x * frames_per_block; bt0 < total; bt0 += (long long)gridDim.x * frames_per_block) {
-    const long long btl = bt0 + fl;
-    if (btl >= total) break;
-    const int bt = (int)btl;
-    const int b = bt / T, t = bt - b * T;
+                      int B, int L, int D, int T, float* __restrict__ out, int VF_CHUNK) {
+  const int dv = D / VEC;                            // column vectors per frame
+  const int nchunk = (T + VF_CHUNK - 1) / VF_CHUNK;
+  const long long total = (long long)B * nchunk * dv;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    // chunk-major order: the lanes of a warp share the chunk, hence t, the interpolation position and every
+    // branch below; they differ in (utterance, column vector) only
+    const int v = (int)(idx % dv);
+    const long long bc = idx / dv;
+    const int b = (int)(bc % B), t0 = (int)(bc / B) * VF_CHUNK, t1 = min(T, t0 + VF_CHUNK);
+    const int d = v * VEC;
     const float* src = lm + (long long)b * L * D + d;
-    float mv[VEC];
+    float mean[VEC], sd[VEC], inv[VEC];
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) mv[k] = 0.f;
-    if (t > 0) {
-      const LerpPos p1 = lerp_pos(t, L, T), p0 = lerp_pos(t - 1, L, T);
-      float a1[VEC], b1[VEC], a0[VEC], b0[VEC];
-      if (VEC == 4) {
-        *reinterpret_cast<float4*>(a1) = __ldg(reinterpret_cast<const float4*>(src + (long long)p1.i0 * D));
-        *reinterpret_cast<float4*>(b1) = __ldg(reinterpret_cast<const float4*>(src + (long long)p1.i1 * D));
-        *reinterpret_cast<float4*>(a0) = __ldg(reinterpret_cast<const float4*>(src + (long long)p0.i0 * D));
-        *reinterpret_cast<float4*>(b0) = __ldg(reinterpret_cast<const float4*>(src + (long long)p0.i1 * D));
-      } else {
-        a1[0] = __ldg(src + (long long)p1.i0 * D);
-        b1[0] = __ldg(src + (long long)p1.i1 * D);
-        a0[0] = __ldg(src + (long long)p0.i0 * D);
-        b0[0] = __ldg(src + (long long)p0.i1 * D);
-      }
-#pragma unroll
-      for (int k = 0; k < VEC; ++k)
-        mv[k] = (a1[k] - a0[k]) + (p1.w * (b1[k] - a1[k]) - p0.w * (b0[k] - a0[k]));
+    for (int k = 0; k < VEC; ++k) {
+      mean[k] = __ldg(vmean + b * D + d + k);
+      sd[k] = __ldg(vstd + b * D + d + k);
+      inv[k] = 1.0f / sd[k];
     }
-    float o[VEC];
+    const float inv_T = 1.0f / (float)T;
+    auto load = [&](int i, float (&x)[VEC]) {
+      if (VEC == 4) *reinterpret_cast<float4*>(x) = __ldg(reinterpret_cast<const float4*>(src + (long long)i * D));
+      else x[0] = __ldg(src + (long long)i * D);
+    };
+    // state of frame t - 1 (frame t0 - 1 for the first iteration; unused when t0 == 0: the motion of frame 0 is 0)
+    LerpPos pp = lerp_pos(t0 > 0 ? t0 - 1 : 0, L, T);
+    float a0[VEC], b0[VEC];
+    load(pp.i0, a0);
+    load(pp.i1, b0);
+    unsigned num = (unsigned)t0 * (unsigned)L;       // t * L, tracked as quotient / remainder by T
+    int q = (int)(num / (unsigned)T);
+    unsigned rem = num - (unsigned)q * (unsigned)T;
+    float* dst = out + ((long long)b * T + t0) * D + d;
+    for (int t = t0; t < t1; ++t) {
+      LerpPos p1;
+      p1.i0 = q;
+      p1.w = (float)rem * inv_T;
+      if (q >= L - 1) {
+        p1.i0 = L - 1;
+        p1.w = 0.f;
+      }
+      p1.i1 = min(p1.i0 + 1, L - 1);
+      float a1[VEC], b1[VEC];
+      if (p1.i0 == pp.i0) {
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) o[k] = (mv[k] - __ldg(vmean + b * D + d + k)) / __ldg(vstd + b * D + d + k);
-    if (VEC == 4) *reinterpret_cast<float4*>(out + (long long)bt * D + d) = *reinterpret_cast<float4*>(o);
-    else out[(long long)bt * D + d] = o[0];
+        for (int k = 0; k < VEC; ++k) {
+          a1[k] = a0[k];
+          b1[k] = b0[k];
+        }
+      } else if (p1.i0 == pp.i1) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) a1[k] = b0[k];
+        load(p1.i1, b1);
+      } else {
+        load(p1.i0, a1);
+        load(p1.i1, b1);
+      }
+      float o[VEC];
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        // frame 0 has no motion: exactly -mean / std; elsewhere the reciprocal (1 ulp) keeps the loop free of divisions
+        o[k] = (t > 0) ? ((a1[k] - a0[k]) + (p1.w * (b1[k] - a1[k]) - pp.w * (b0[k] - a0[k])) - mean[k]) * inv[k]
+                       : (0.f - mean[k]) / sd[k];
+      }
+      if (VEC == 4) *reinterpret_cast<float4*>(dst) = *reinterpret_cast<float4*>(o);
+      else dst[0] = o[0];
+      dst += D;
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        a0[k] = a1[k];
+        b0[k] = b1[k];
+      }
+      pp = p1;
+      rem += (unsigned)L;
+      while (rem >= (unsigned)T) {
+        rem -= (unsigned)T;
+        ++q;
+      }
+    }
   }
 }
 
@@ -116,13 +161,18 @@ extern "C" int avsi_video_features(const float* landmarks, const float* vmean, c
   AVSI_REQUIRE((long long)T * L < (1LL << 31) && (long long)B * T < (1LL << 31), "T * L and B * T must fit 31 bits");
   const bool vec = (D % 4 == 0) && ((uintptr_t)landmarks % 16 == 0) && ((uintptr_t)out % 16 == 0);
   const int dvh = vec ? D / 4 : D;
-  AVSI_REQUIRE(dvh <= 256, "D too large");
-  long long n = ((long long)B * T + (256 / dvh) - 1) / (256 / dvh);
-  int blocks = (int)min(n, (long long)num_sms() * 16);
+  static int VF_CHUNK = 0;
+  if (!VF_CHUNK) {
+    const char* e = getenv("AVSI_VF_CHUNK");
+    VF_CHUNK = e ? atoi(e) : 32;
+    if (VF_CHUNK < 1) VF_CHUNK = 32;
+  }
+  const long long work = (long long)B * ((T + VF_CHUNK - 1) / VF_CHUNK) * dvh;
+  int blocks = (int)min((work + 255) / 256, (long long)num_sms() * 16);
   if (vec)
-    video_features_kernel<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(landmarks, vmean, vstd, B, L, D, T, out);
+    video_features_kernel<4><<<blocks, 256, 0, (cudaStream_t)stream>>>(landmarks, vmean, vstd, B, L, D, T, out, VF_CHUNK);
   else
-    video_features_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(landmarks, vmean, vstd, B, L, D, T, out);
+    video_features_kernel<1><<<blocks, 256, 0, (cudaStream_t)stream>>>(landmarks, vmean, vstd, B, L, D, T, out, VF_CHUNK);
   AVSI_LAUNCH_CHECK();
   return AVSI_OK;
 }
