@@ -8,6 +8,7 @@
 namespace avsi {
 
 constexpr int L1_THREADS = 256;
+constexpr int L1_UNROLL = 4;
 
 __global__ void __launch_bounds__(L1_THREADS)
 masked_l1_kernel(const float* __restrict__ logits, int ldl, const float* __restrict__ target,
@@ -29,8 +30,22 @@ masked_l1_kernel(const float* __restrict__ logits, int ldl, const float* __restr
     const float* tg = target + r * F;
     const float* mk = mask + r * F;
     uint16_t* dl = dlogits ? dlogits + ((long long)t * B + b) * ldd : nullptr;
-    for (int k = lane; k < F; k += 32) {
-      const float x = lg[k], y = tg[k], m = mk[k];
+    for (int k0 = lane; k0 < F; k0 += 32 * L1_UNROLL) {
+     // the loads of L1_UNROLL column groups are requested before the first is used (12 lines in flight per warp)
+     float xv[L1_UNROLL], yv[L1_UNROLL], mv[L1_UNROLL];
+#pragma unroll
+     for (int u = 0; u < L1_UNROLL; ++u) {
+       const int k = k0 + 32 * u;
+       const bool ok = k < F;
+       xv[u] = ok ? __ldg(lg + k) : 0.f;
+       yv[u] = ok ? __ldg(tg + k) : 0.f;
+       mv[u] = ok ? __ldg(mk + k) : 0.f;
+     }
+#pragma unroll
+     for (int u = 0; u < L1_UNROLL; ++u) {
+      const int k = k0 + 32 * u;
+      if (k >= F) break;
+      const float x = xv[u], y = yv[u], m = mv[u];
       float pred = (mode == 0) ? x : (y * m + x * (1.f - m));
       pred *= sm;
       const float d = y - pred;
@@ -47,6 +62,7 @@ masked_l1_kernel(const float* __restrict__ logits, int ldl, const float* __restr
         float w = (mode == 0) ? sm : sm * (1.f - m);
         dl[k] = __half_as_ushort(__float2half_rn(grad_scale * sg * w));
       }
+     }
     }
   }
   __shared__ double red[5][L1_THREADS / 32];
