@@ -127,11 +127,28 @@ def run_reference(args):
     line = {'impl': 'reference', 'metric': METRIC, 'value': cb['value'], 'unit': UNIT, 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'AV-SI train step (configs[1]): 3 s 16 kHz utterances, 75-frame landmarks, '
-                                   '3x BLSTM-250, L1, Adam', 'batch_per_step': CPU_SAMPLE_B},
+            'config': workload_config(args, max(1, args.gpus)),       # the arm's workload; each step times a bounded sample of it
             'cpu_baseline': cb,
             'e2e': {'value': cb['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line))
+
+
+def workload_config(args, world):
+    """`config` of the JSON line, shared by both arms: names the workload, no model hyper-parameters."""
+    B, N = args.batch, args.audio_len
+    T = -(-N // 192)
+    mtl = 'ctc' in args.model
+    inp = args.model.split('-')[0]
+    what = {'a': 'masked log-spectrogram', 'v': 'upsampled landmark motion vectors',
+            'av': 'masked log-spectrogram ++ upsampled landmark motion vectors'}[inp]
+    name = 'AV-MTL-SI train step (configs[2], joint CTC phone head)' if mtl else \
+        '%s-SI train step (configs[%d])' % (inp.upper(), 4 if N > 48000 else 1)
+    return {'workload': '%s: %g s 16 kHz utterances + 75-frame landmark streams, %s, 3x BLSTM-250, %s, TF-form Adam'
+                        % (name, N / 16000.0, what, 'hole L1 + CTC loss' if mtl else 'L1 loss'),
+            'model': args.model, 'batch_per_gpu': B, 'global_batch': B * world, 'frames': T,
+            'parallelism': 'dp%d' % world,
+            'l2_policy': 'inputs larger than L2 (wav+mask %.0f MB per step, activations %.1f GB)'
+                         % (B * (N + T * 257) * 4 / 1e6, T * B * (3 * 2048 * 2 + 3 * 512 * 6) / 1e9)}
 
 
 def main():
@@ -343,13 +360,8 @@ def main():
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
         'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f16', 'data': 'synthetic',
-        'config': {'workload': 'AV-SI train step (configs[1]): 3 s 16 kHz utterances + 75-frame landmark streams, '
-                               'masked log-spectrogram ++ upsampled motion vectors, 3x BLSTM-250, L1 loss, TF-form Adam',
-                   'model': args.model, 'batch_per_gpu': B, 'global_batch': B * world, 'frames': T,
-                   'parallelism': 'dp%d' % world, 'arithmetic': 'fp16 operands, fp32 accumulate / state',
-                   'l2_policy': 'inputs larger than L2 (wav+mask %.0f MB per step, activations %.1f GB)'
-                                % ((pin['wav'].numel() + pin['mask'].numel()) * 4 / 1e6, T * B * (3 * 2048 * 2 + 3 * 512 * 6) / 1e9)},
+        'dtype': 'f16', 'data': 'synthetic', 'arithmetic': 'fp16 operands, fp32 accumulate / state',
+        'config': workload_config(args, world),
         'e2e': {'value': utt / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 8,
                 'host_dtypes': {k: str(pin[k].dtype).replace('torch.', '') for k in ('wav', 'mask', 'landmarks')}},
         # the e2e steps train on the same batch: the fetched losses must be finite and go down (work is not skipped)
