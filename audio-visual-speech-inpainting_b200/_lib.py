@@ -59,6 +59,9 @@ SIGNATURES = {
     'avsi_ctc_beam_search_host': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,
                                           c_void_p, c_void_p, c_void_p, c_int]),
     'avsi_crc32c_host': (c_uint32, [c_void_p, c_uint64, c_uint32]),
+    'avsi_preemphasis': (c_int, [c_void_p, c_int, c_int, c_float, c_void_p, c_void_p]),
+    'avsi_mfcc': (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
+    'avsi_delta_features': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'avsi_dropout_f16': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_float, c_uint64, c_uint64, c_void_p,
                                  c_void_p]),
     'avsi_feature_stats': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -4,7 +4,7 @@ compute_mean_std_features(...) keeps the reference signature (audio_feat_preproc
 contract (`<out_prefix>_mean.npy`, `<out_prefix>_std.npy` in `audio_folder`, optional per-sample `.npy` dumps,
 `mask.npy` per sample for apply_mask).  Instead of one TF session run per file, files of equal length are
 batched through the fused front end and the float64 sums of :102-107 are accumulated on the GPU
-(avsi_feature_stats).  `stft`, `mfcc`, deltas and pre-emphasis are not on the hot path and raise.
+(avsi_feature_stats).  `mfcc`, delta features and pre-emphasis are thin kernels on top (csrc/features_extra.cu).
 """
 import os
 from glob import glob
@@ -51,32 +51,35 @@ class FeatureStats(object):
         return mean, std, int(round(n))
 
 
-def _features(batch, ftype, sample_rate, window_size, step_size, num_mel_bins):
-    """batch [B,N] f32 CUDA -> [B,T,F] features of the given type."""
+def _features(batch, ftype, sample_rate, window_size, step_size, num_mel_bins, num_mfcc=13, preemph=0, delta=0):
+    """batch [B,N] f32 CUDA -> [B,T,F] features of the given type (audio_feat_preprocessing.py:36-62)."""
     frame_len, hop = ap.ms_to_samples(window_size, sample_rate), ap.ms_to_samples(step_size, sample_rate)
+    if preemph > 0:
+        batch = ap.preemphasis(batch, alpha=preemph)
     if ftype == 'spec':
-        return ap.fused_features(batch, frame_len, hop, log=True, want_spec=True)['spec']
-    if ftype == 'fbanks':
-        return ap.log_mel_features(batch, sample_rate, window_size, step_size, num_mel_bins)
-    raise NotImplementedError('feature type %r is outside the hot path (only "spec" and "fbanks")' % ftype)
+        feats = ap.fused_features(batch, frame_len, hop, log=True, want_spec=True)['spec']
+    else:
+        feats = ap.log_mel_features(batch, sample_rate, window_size, step_size, num_mel_bins)
+        if ftype == 'mfcc':
+            feats = ap.get_mfcc(feats, num_mfcc)
+    if delta > 0:
+        feats = ap.add_delta_features(feats, n_delta=delta, N=2)
+    return feats
 
 
 def compute_mean_std_features(audio_folder, file_prefix, out_prefix, type='spec', sample_rate=16e3, n_fft=512,
                               window_size=25, step_size=10, preemph=0, num_mel_bins=80, num_mfcc=13, delta=0,
                               apply_mask=False, save_feat=False, file_ext='wav', batch_size=64, device='cuda'):
     from scipy.io import wavfile
-    if type not in ('spec', 'fbanks'):
-        if type in ('stft', 'mfcc'):
-            raise NotImplementedError('type %r is outside the hot path' % type)
+    if type not in ('spec', 'fbanks', 'mfcc'):
+        # 'stft' included: the reference falls through to this exit for it as well (audio_feat_preprocessing.py:44-61)
         print('Type must be "stft", "spec", "fbanks" or "mfcc". Closing...')
         raise SystemExit(1)
-    if preemph > 0 or delta > 0:
-        raise NotImplementedError('pre-emphasis / delta features are outside the hot path')
     if n_fft != 512:
         raise _lib.AvsiError('only n_fft = 512 is supported')
     sample_rate = int(sample_rate)
     audio_sample_dirs = sorted(d for d in glob(os.path.join(audio_folder, '*')) if os.path.isdir(d))
-    feat_dim = 257 if type == 'spec' else num_mel_bins
+    feat_dim = {'spec': 257, 'fbanks': num_mel_bins, 'mfcc': num_mfcc}[type] * (delta + 1)
     stats = FeatureStats(feat_dim, device)
     print('Computing features...')
     # files of equal length share a batch (GRID: every utterance has 48000 samples)
@@ -89,7 +92,7 @@ def compute_mean_std_features(audio_folder, file_prefix, out_prefix, type='spec'
         for i in range(0, len(items), batch_size):
             chunk = items[i:i + batch_size]
             wav = torch.from_numpy(np.stack([s for _, s in chunk])).to(device)
-            feats = _features(wav, type, sample_rate, window_size, step_size, num_mel_bins)
+            feats = _features(wav, type, sample_rate, window_size, step_size, num_mel_bins, num_mfcc, preemph, delta)
             if apply_mask:
                 for k, (d, _) in enumerate(chunk):
                     mask = torch.from_numpy(np.load(os.path.join(d, 'mask.npy')).astype(np.float32)).to(device)
@@ -111,3 +114,31 @@ def compute_mean_std_features(audio_folder, file_prefix, out_prefix, type='spec'
     np.save(os.path.join(audio_folder, out_prefix + '_std.npy'), feat_std)
     print('Normalization data files saved.')
     return feat_mean, feat_std
+
+
+def save_features(audio_folder, type='spec', sample_rate=16e3, n_fft=512, window_size=25, step_size=10, preemph=0,
+                  num_mel_bins=80, num_mfcc=13, delta=0, file_ext='wav', device='cuda'):
+    """audio_feat_preprocessing.py:130-196: features of every `<audio_folder>/*.<ext>` saved next to it as `.npy`."""
+    from scipy.io import wavfile
+    if type not in ('stft', 'spec', 'fbanks', 'mfcc'):
+        print('Type must be "spec", "fbanks" or "mfcc". Closing...')
+        raise SystemExit(1)
+    if n_fft != 512:
+        raise _lib.AvsiError('only n_fft = 512 is supported')
+    sample_rate = int(sample_rate)
+    files = sorted(glob(os.path.join(audio_folder, '*.' + file_ext)))
+    print('Computing and saving features...')
+    for audio_file in files:
+        rate, samples = wavfile.read(audio_file)
+        samples = np.asarray(ap.downsampling(samples, rate, sample_rate), np.float32)
+        wav = torch.from_numpy(samples[None]).to(device)
+        if type == 'stft':
+            if preemph > 0:
+                wav = ap.preemphasis(wav, alpha=preemph)
+            feat = ap.get_stft(wav, sample_rate, window_size, step_size, n_fft)
+            if delta > 0:
+                raise _lib.AvsiError('delta features of a complex STFT are not defined')
+        else:
+            feat = _features(wav, type, sample_rate, window_size, step_size, num_mel_bins, num_mfcc, preemph, delta)
+        np.save(os.path.splitext(audio_file)[0] + '.npy', feat[0].cpu().numpy())
+    print('done. Audio files processed:', len(files))

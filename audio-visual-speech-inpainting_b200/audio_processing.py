@@ -202,6 +202,51 @@ def get_log_mel_spectrogram(spectrograms, sample_rate=16000, num_spec_bins=257, 
     return torch.log(torch.tensordot(spectrograms, m, dims=1) + eps)
 
 
+def preemphasis(sources, alpha=0.95):
+    """audio_processing.py:19-22 -> CUDA f32 [B, N]."""
+    x = _f32(sources, sources.device if torch.is_tensor(sources) and sources.is_cuda else torch.device('cuda'))
+    if not x.is_cuda:
+        raise _lib.AvsiError('preemphasis needs CUDA tensors (no CPU fallback)')
+    y = torch.empty_like(x)
+    _lib.check(_lib.load().avsi_preemphasis(_lib.ptr(x), x.shape[0], x.shape[1], float(alpha), _lib.ptr(y), _lib.stream_ptr()),
+               'avsi_preemphasis')
+    return y
+
+
+def get_mfcc(log_mel_spectrograms, num_mfccs=13, out_shape=[0, 0, 0]):
+    """audio_processing.py:74-81: DCT-II of the log-mel rows (tf.signal.mfccs_from_log_mel_spectrograms), first num_mfccs."""
+    x = log_mel_spectrograms
+    if not (torch.is_tensor(x) and x.is_cuda):
+        raise _lib.AvsiError('get_mfcc needs a CUDA tensor (no CPU fallback)')
+    x = x.float().contiguous()
+    out = torch.empty(x.shape[:-1] + (num_mfccs,), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().avsi_mfcc(_lib.ptr(x), x.numel() // x.shape[-1], x.shape[-1], num_mfccs, _lib.ptr(out),
+                                     _lib.stream_ptr()), 'avsi_mfcc')
+    return _sliced(out, out_shape)
+
+
+def delta(features, N=2):
+    """audio_processing.py:84-93 on [B, T, F]."""
+    return add_delta_features(features, n_delta=1, N=N)[:, :, features.shape[2]:]
+
+
+def add_delta_features(features, n_delta=2, N=2):
+    """audio_processing.py:96-103: [B, T, F] -> [B, T, F * (n_delta + 1)] (features, delta, delta-delta, ...)."""
+    x = features
+    if not (torch.is_tensor(x) and x.is_cuda):
+        raise _lib.AvsiError('add_delta_features needs a CUDA tensor (no CPU fallback)')
+    x = x.float().contiguous()
+    B, T, F = x.shape
+    ld = F * (n_delta + 1)
+    out = torch.empty(B, T, ld, dtype=torch.float32, device=x.device)
+    out[:, :, :F] = x
+    lib = _lib.load()
+    for i in range(n_delta):
+        src = out.data_ptr() + 4 * F * i
+        _lib.check(lib.avsi_delta_features(src, ld, src + 4 * F, ld, B, T, F, N, _lib.stream_ptr()), 'avsi_delta_features')
+    return out
+
+
 def log_mel_features(sources, sample_rate=16000, window_size=25, step_size=10, num_mel_bins=80,
                      lower_edge_freq=125, upper_edge_freq=7600, eps=1e-6):
     """Fused `fbanks` path of audio_feat_preprocessing.py:49-50 / models_asr.py:31-37:

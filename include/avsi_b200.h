@@ -88,6 +88,15 @@ typedef struct {
 } avsi_frontend_args;
 int avsi_frontend_fwd(const avsi_frontend_args* args, void* stream);
 
+/* Remaining feature transforms of audio_processing.py (next row 8f.4); f32, caller-owned device memory.
+ *   avsi_preemphasis     y[b,n] = x[b,n] - alpha * x[b,n-1], x[b,-1] = 0          preemphasis, audio_processing.py:19-22
+ *   avsi_mfcc            DCT-II of the log-mel rows * rsqrt(2 n_mel), first n_mfcc   get_mfcc :74-81
+ *   avsi_delta_features  sum_{i<=N} i (f[t+i] - f[t-i]) / (2 sum i^2), edge frames replicated   delta :84-93
+ *                        (src/dst rows of ld_src/ld_dst floats: add_delta_features writes the orders side by side) */
+int avsi_preemphasis(const float* src, int B, int N, float alpha, float* dst, void* stream);
+int avsi_mfcc(const float* logmel, int64_t rows, int n_mel, int n_mfcc, float* out, void* stream);
+int avsi_delta_features(const float* src, int ld_src, float* dst, int ld_dst, int B, int T, int F, int N, void* stream);
+
 /* Waveform reconstruction (next row 8f.1): get_sources / reconstruct_sources
  * audio_processing.py:145-164, enhanced_sources models.py:181-197.
  *   mag [B,T,F] f32 (or pred with denorm: mag = exp(pred*std+mean) when mean != NULL)

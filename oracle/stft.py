@@ -95,6 +95,44 @@ def get_log_mel_spectrogram(spectrograms, sample_rate=16000, num_spec_bins=257, 
     return np.log(np.tensordot(spectrograms, m.astype(spectrograms.dtype), axes=1) + eps)
 
 
+def preemphasis(sources, alpha=0.95):
+    """audio_processing.py:19-22: sources - alpha * [0, sources[:, :-1]]."""
+    x = np.asarray(sources, np.float64)
+    return x - alpha * np.concatenate([np.zeros((x.shape[0], 1)), x[:, :-1]], axis=1)
+
+
+def get_mfcc(log_mel_spectrograms, num_mfccs=13):
+    """audio_processing.py:74-81: tf.signal.mfccs_from_log_mel_spectrograms = DCT-II (tf.signal.dct type 2, norm=None:
+    X_k = 2 sum_n x_n cos(pi k (2n+1) / (2N))) scaled by rsqrt(2 N), first num_mfccs coefficients."""
+    x = np.asarray(log_mel_spectrograms, np.float64)
+    N = x.shape[-1]
+    n = np.arange(N)
+    k = np.arange(N)[:, None]
+    dct = 2.0 * np.cos(np.pi * k * (2 * n + 1) / (2.0 * N))          # [k, n]
+    return (x @ dct.T / np.sqrt(2.0 * N))[..., :num_mfccs]
+
+
+def delta(features, N=2):
+    """audio_processing.py:84-93, line by line: one frame of SYMMETRIC padding per i, on the already padded tensor."""
+    f = np.asarray(features, np.float64)
+    denominator = 2 * sum(i ** 2 for i in range(1, N + 1))
+    acc = np.zeros_like(f)
+    padded = f
+    for i in range(1, N + 1):
+        padded = np.pad(padded, [(0, 0), (1, 1), (0, 0)], mode='symmetric')
+        acc += i * (padded[:, i * 2:, :] - padded[:, :-i * 2, :])
+    return acc / denominator
+
+
+def add_delta_features(features, n_delta=2, N=2):
+    """audio_processing.py:96-103."""
+    full, cur = [np.asarray(features, np.float64)], np.asarray(features, np.float64)
+    for _ in range(n_delta):
+        cur = delta(cur, N)
+        full.append(cur)
+    return np.concatenate(full, axis=2)
+
+
 def inverse_stft_window(frame_len, hop, dtype=np.float64):
     """tf.contrib.signal.inverse_stft_window_fn(hop)(frame_len) with a Hann forward window."""
     w = hann_periodic(frame_len)

@@ -638,3 +638,59 @@ def test_dropout_kernel(rate):
     z = x.clone()
     z, _ = run(z, seed, offset, inplace=True)
     assert torch.equal(z, y)
+
+
+def test_preemphasis_mfcc_delta_features():
+    """audio_processing.py:19-22, 74-103: pre-emphasis, MFCC (DCT-II of the log-mel rows, TF scaling) and
+    delta / delta-delta features against the line-by-line numpy restatement; scipy's DCT as a second opinion."""
+    from scipy.fft import dct
+    from avsi_b200 import audio_processing as ap
+    from oracle import stft as ostft
+    rng = np.random.default_rng(11)
+    d = dev()
+    wav = np.round(rng.normal(0, 3000, (3, 4000))).astype(np.float32)
+    got = ap.preemphasis(torch.from_numpy(wav).to(d), alpha=0.95).cpu().numpy()
+    assert rel_l2(got, ostft.preemphasis(wav, 0.95)) < 1e-6 and got[0, 0] == wav[0, 0]
+    logmel = rng.normal(5, 3, (2, 37, 80)).astype(np.float32)
+    ref = ostft.get_mfcc(logmel, 13)
+    assert np.allclose(ref, (dct(logmel.astype(np.float64), type=2, norm=None, axis=-1) / np.sqrt(160.0))[..., :13], atol=1e-9)
+    got = ap.get_mfcc(torch.from_numpy(logmel).to(d), 13).cpu().numpy()
+    assert got.shape == (2, 37, 13) and rel_l2(got, ref) < 1e-5
+    for (B, T, F, nd) in ((2, 37, 13, 2), (1, 1, 5, 1), (3, 3, 80, 3), (2, 250, 257, 2)):
+        x = rng.standard_normal((B, T, F)).astype(np.float32)
+        got = ap.add_delta_features(torch.from_numpy(x).to(d), n_delta=nd, N=2).cpu().numpy()
+        ref = ostft.add_delta_features(x, n_delta=nd, N=2)
+        assert got.shape == ref.shape == (B, T, F * (nd + 1))
+        assert np.array_equal(got[:, :, :F], x) and np.abs(got - ref).max() < 1e-5 * max(1.0, np.abs(ref).max())
+    one = ap.delta(torch.from_numpy(x).to(d)).cpu().numpy()
+    assert np.abs(one - ostft.delta(x)).max() < 1e-5
+
+
+def test_mean_std_features_mfcc_with_deltas(tmp_path):
+    """compute_mean_std_features(type='mfcc', preemph, delta) and save_features: the statistics of the composed features
+    equal the float64 restatement's (audio_feat_preprocessing.py:23-115, 130-196)."""
+    from scipy.io import wavfile
+    from avsi_b200 import audio_feat_preprocessing as afp
+    from oracle import stft as ostft
+    rng = np.random.default_rng(12)
+    feats = []
+    for i in range(3):
+        dd = tmp_path / ('s%d' % i)
+        dd.mkdir()
+        wav = np.round(rng.normal(0, 3000, 8000)).astype(np.int16)
+        wavfile.write(str(dd / 'target.wav'), 16000, wav)
+        wavfile.write(str(tmp_path / ('f%d.wav' % i)), 16000, wav)
+        x = ostft.preemphasis(wav[None].astype(np.float64), 0.97)
+        st = ostft.get_stft(x, window_size=25, step_size=10)
+        f = ostft.get_mfcc(ostft.get_log_mel_spectrogram(ostft.get_spectrogram(st, power=2)), 13)
+        feats.append(ostft.add_delta_features(f, n_delta=2, N=2)[0])
+    mean, std = afp.compute_mean_std_features(str(tmp_path), 'target', 'mfcc_norm', type='mfcc', preemph=0.97, delta=2)
+    allf = np.concatenate(feats, 0)
+    assert mean.shape == (39,) and np.allclose(mean, allf.mean(0), rtol=1e-4, atol=1e-4)
+    assert np.allclose(std, allf.std(0), rtol=1e-4, atol=1e-4)
+    assert np.allclose(np.load(str(tmp_path / 'mfcc_norm_mean.npy')), mean)
+    afp.save_features(str(tmp_path), type='mfcc', preemph=0.97, delta=2)
+    saved = np.load(str(tmp_path / 'f1.npy'))
+    assert saved.shape == feats[1].shape and np.abs(saved - feats[1]).max() < 1e-3 * np.abs(feats[1]).max()
+    with pytest.raises(SystemExit):
+        afp.compute_mean_std_features(str(tmp_path), 'target', 'x', type='stft')
