@@ -97,3 +97,31 @@ def time_train_steps(batch, steps=1, warmup=0, threads=None):
         train_step(params, state, wav, mask, mean, std, video, warmup + s + 1)
     dt = (time.perf_counter() - t0) / max(steps, 1)
     return wav.shape[0] / dt, threads, dt
+
+
+def time_inference(batch, steps=3, warmup=1, threads=None):
+    """BASELINE configs[0]: A-SI inference (`prediction` of the is_training=False graph, models.py:106-138) on the host
+    cores.  batch: numpy wav, mask, mean, std, seq_len.  Returns (utt/s, cores, seconds/step)."""
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    wav, mask = torch.from_numpy(batch['wav']), torch.from_numpy(batch['mask'])
+    mean, std = torch.from_numpy(batch['mean']), torch.from_numpy(batch['std'])
+    seq = torch.from_numpy(batch['seq_len'].astype('int64'))
+    params = make_params(mask.shape[2])
+
+    def run():
+        with torch.no_grad():
+            tsn, x = frontend(wav, mask, mean, std, None)
+            B, T, F = tsn.shape
+            for l in range(3):
+                kf, bf, kb, bb = params[4 * l:4 * l + 4]
+                x = torch.cat([_direction(x, kf, bf, False), _direction(x, kb, bb, True)], dim=2)
+            pred = (x.reshape(B * T, -1) @ params[-2] + params[-1]).reshape(B, T, F)
+            return pred * (torch.arange(T)[None, :] < seq[:, None]).float()[:, :, None]
+    for _ in range(warmup):
+        run()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        run()
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return wav.shape[0] / dt, threads, dt
