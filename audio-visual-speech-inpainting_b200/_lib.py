@@ -63,7 +63,7 @@ SIGNATURES = {
     'avsi_mfcc': (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
     'avsi_delta_features': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'avsi_dropout_f16': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_float, c_uint64, c_uint64, c_void_p,
-                                 c_void_p]),
+                                 c_int, c_void_p]),
     'avsi_feature_stats': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     'avsi_gemm_f16': (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p,
                               c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),

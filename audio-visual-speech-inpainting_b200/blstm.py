@@ -144,7 +144,8 @@ class BLSTMEngine(object):
         ws['logits'] = torch.zeros(M, L.nop, dtype=torch.float32, device=dev)
         if training:
             ws['dlogits'] = torch.zeros(M, L.nop, dtype=torch.float16, device=dev)
-            ws['dY'] = [torch.empty(M, NY, dtype=torch.float16, device=dev) for _ in range(2)]
+            # dL/dy of a layer: INTERLEAVED like G (written by the dX GEMMs with C_IL, read by the BPTT kernel)
+            ws['dY'] = [torch.zeros(Mp, NY, dtype=torch.float16, device=dev) for _ in range(2)]
             nbytes = int(_lib.load().avsi_lstm_bwd_scratch_bytes(B))
             ws['scratch'] = torch.empty(max(nbytes, 16) // 4, dtype=torch.float32, device=dev)
         if len(self._ws) > 4:
@@ -181,7 +182,7 @@ class BLSTMEngine(object):
                 ws['Ydrop'] = torch.empty(M, NY, dtype=torch.float16, device=self.device)
             with _lib.span('dropout', nbytes=2 * M * NY * 2):
                 _lib.check(lib.avsi_dropout_f16(_p(x), NY, _p(ws['Ydrop']), NY, M, NY, float(dropout[0]), int(dropout[1]),
-                                                int(dropout[2]), None, _lib.stream_ptr()), 'avsi_dropout_f16')
+                                                int(dropout[2]), None, 0, _lib.stream_ptr()), 'avsi_dropout_f16')
             x = ws['Ydrop']
             ws['drop'] = (float(dropout[0]), int(dropout[1]), int(dropout[2]))
         gemm(_p(x), NY, _p(self.half['head']), NY, _p(ws['logits']), L.nop, _p(self.view(self.theta, 'head_b')),
@@ -206,10 +207,10 @@ class BLSTMEngine(object):
              pick_split_k(L.n_out, NY, M), tag='gemm_dw')
         _lib.check(lib.avsi_colsum_f16(_p(dl), L.nop, M, 0, L.n_out, _p(self.view(g, 'head_b')), st()), 'avsi_colsum_f16')
         dY = ws['dY'][0]
-        gemm(_p(dl), L.nop, _p(self.half['headT']), L.nop, _p(dY), NY, None, M, NY, L.nop, 0, 0, tag='gemm_dx')
+        gemm(_p(dl), L.nop, _p(self.half['headT']), L.nop, _p(dY), NY, None, M, NY, L.nop, 0, 0, tag='gemm_dx', layout=C_IL)
         if drop:
             with _lib.span('dropout', nbytes=2 * M * NY * 2):
-                _lib.check(lib.avsi_dropout_f16(_p(dY), NY, _p(dY), NY, M, NY, drop[0], drop[1], drop[2], None, st()),
+                _lib.check(lib.avsi_dropout_f16(_p(dY), NY, _p(dY), NY, M, NY, drop[0], drop[1], drop[2], None, 3, st()),
                            'avsi_dropout_f16')
         cur = 0
         for l in range(L.n_layers - 1, -1, -1):
@@ -237,7 +238,7 @@ class BLSTMEngine(object):
             if l > 0:
                 nxt = 1 - cur
                 gemm(_p(G), NG, _p(self.half['wihT%d' % l]), NG, _p(ws['dY'][nxt]), NY, None, M, NY, NG, 0, 0,
-                     tag='gemm_dx', layout=A_IL)
+                     tag='gemm_dx', layout=A_IL | C_IL)
                 cur = nxt
         return g
 

@@ -23,12 +23,16 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
 __global__ void __launch_bounds__(256)
 dropout_f16_kernel(const uint16_t* __restrict__ src, int ld_src, uint16_t* __restrict__ dst, int ld_dst, long long rows,
                    int chunks_per_row, uint32_t thresh, float scale, uint2 key, unsigned long long offset,
-                   uint8_t* __restrict__ keep_out) {
+                   uint8_t* __restrict__ keep_out, int layout) {
   const long long total = rows * chunks_per_row;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / chunks_per_row;
     const int ch = (int)(i - r * chunks_per_row);
-    const uint4 in = *reinterpret_cast<const uint4*>(src + r * ld_src + ch * 8);
+    // layout bit 0 / 1: src / dst is INTERLEAVED (common.cuh il16, ld = logical row length); the mask is a function of
+    // the logical (row, chunk) either way
+    const long long so = (layout & 1) ? il16(r, ch * 8, ld_src) : r * ld_src + ch * 8;
+    const long long dofs = (layout & 2) ? il16(r, ch * 8, ld_dst) : r * ld_dst + ch * 8;
+    const uint4 in = *reinterpret_cast<const uint4*>(src + so);
     const uint32_t w[4] = {in.x, in.y, in.z, in.w};
     uint32_t rnd[8];
     {
@@ -47,7 +51,7 @@ dropout_f16_kernel(const uint16_t* __restrict__ src, int ld_src, uint16_t* __res
       o[j] = *reinterpret_cast<const uint32_t*>(&h);
       kbits |= (k0 ? 1u : 0u) << (2 * j) | (k1 ? 1u : 0u) << (2 * j + 1);
     }
-    *reinterpret_cast<uint4*>(dst + r * ld_dst + ch * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<uint4*>(dst + dofs) = make_uint4(o[0], o[1], o[2], o[3]);
     if (keep_out) {
       uint2 kb;
       kb.x = (kbits & 1u) | ((kbits >> 1 & 1u) << 8) | ((kbits >> 2 & 1u) << 16) | ((kbits >> 3 & 1u) << 24);
@@ -60,12 +64,14 @@ dropout_f16_kernel(const uint16_t* __restrict__ src, int ld_src, uint16_t* __res
 }  // namespace avsi
 
 extern "C" int avsi_dropout_f16(const void* src, int ld_src, void* dst, int ld_dst, int64_t rows, int cols, float rate,
-                                uint64_t seed, uint64_t offset, void* keep_out, void* stream) {
+                                uint64_t seed, uint64_t offset, void* keep_out, int layout, void* stream) {
   using namespace avsi;
   AVSI_REQUIRE(src && dst, "null pointer");
   AVSI_REQUIRE(rows > 0 && cols > 0 && cols % 8 == 0 && ld_src >= cols && ld_dst >= cols, "sizes (cols multiple of 8)");
   AVSI_REQUIRE(ld_src % 8 == 0 && ld_dst % 8 == 0 && (uintptr_t)src % 16 == 0 && (uintptr_t)dst % 16 == 0, "16-byte rows");
   AVSI_REQUIRE(rate >= 0.f && rate < 1.f, "rate in [0, 1)");
+  AVSI_REQUIRE(!(layout & 1) || ld_src == cols, "interleaved src: ld = cols");
+  AVSI_REQUIRE(!(layout & 2) || ld_dst == cols, "interleaved dst: ld = cols");
   AVSI_REQUIRE(!keep_out || (uintptr_t)keep_out % 8 == 0, "keep_out alignment");
   // keep = (u >= rate) with u uniform on [0, 1) in 2^-32 steps
   const double t = (double)rate * 4294967296.0;
@@ -75,7 +81,7 @@ extern "C" int avsi_dropout_f16(const void* src, int ld_src, void* dst, int ld_d
   if (blocks > (long long)num_sms() * 16) blocks = (long long)num_sms() * 16;
   dropout_f16_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
       (const uint16_t*)src, ld_src, (uint16_t*)dst, ld_dst, rows, cols / 8, thresh, 1.0f / (1.0f - rate),
-      make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), offset, (uint8_t*)keep_out);
+      make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)), offset, (uint8_t*)keep_out, layout);
   AVSI_LAUNCH_CHECK();
   return AVSI_OK;
 }

@@ -264,7 +264,7 @@ lstm_bwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whhT,
         if (row < B) {
           const long long r = (long long)t * B + row;
           gt[mt][rh] = *reinterpret_cast<const uint2*>(gates + il16(r, dir * LS_G + u * 4, 2 * LS_G));
-          dyv[mt][rh] = __half2float(__ushort_as_half(dy[r * (2 * LS_HP) + dir * LS_HP + u]));
+          dyv[mt][rh] = __half2float(__ushort_as_half(dy[il16(r, dir * LS_HP + u, 2 * LS_HP)]));   // interleaved dL/dy
           if (has_prev) cprev[mt][rh] = cst[il32((long long)tp * B + row, dir * LS_HP + u, 2 * LS_HP)];
           if (s == 0) c_cur[mt][rh] = cst[il32(r, dir * LS_HP + u, 2 * LS_HP)];
         }

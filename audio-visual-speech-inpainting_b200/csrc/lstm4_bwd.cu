@@ -219,7 +219,7 @@ lstm4_bwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whhT
 #pragma unroll
           for (int i = 0; i < 4; ++i)
             G4[i] = *reinterpret_cast<const uint4*>(gates + il16(grow, dir * B4_G + ug0 * 4 + 8 * i, 2 * B4_G));
-          DY = *reinterpret_cast<const uint4*>(dy + grow * (2 * B4_HP) + dir * B4_HP + ug0);
+          DY = *reinterpret_cast<const uint4*>(dy + il16(grow, dir * B4_HP + ug0, 2 * B4_HP));   // interleaved dL/dy
           if (has_prev) {
             const float4 a = *reinterpret_cast<const float4*>(cst + il32(gprev, dir * B4_HP + ug0, 2 * B4_HP));
             const float4 b = *reinterpret_cast<const float4*>(cst + il32(gprev, dir * B4_HP + ug0 + 4, 2 * B4_HP));

@@ -137,7 +137,7 @@ class StackedBLSTMModel(object):
         M, H = fr['T'] * fr['B'], self.net_dim[-1]
         ones = torch.ones(M, NY, dtype=torch.float16, device=self.device)
         keep = torch.empty(M, NY, dtype=torch.uint8, device=self.device)
-        _lib.check(_lib.load().avsi_dropout_f16(_p(ones), NY, _p(ones), NY, M, NY, d[0], d[1], d[2], _p(keep),
+        _lib.check(_lib.load().avsi_dropout_f16(_p(ones), NY, _p(ones), NY, M, NY, d[0], d[1], d[2], _p(keep), 0,
                                                 _lib.stream_ptr()), 'avsi_dropout_f16')
         k = keep.view(fr['T'], fr['B'], 2, HP)[:, :, :, :H].reshape(fr['T'], fr['B'], 2 * H)
         return k.permute(1, 0, 2).bool()

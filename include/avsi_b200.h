@@ -169,7 +169,8 @@ int avsi_gemm_f16(const uint16_t* A, int lda, const uint16_t* B, int ldb, void* 
  *                           tensor core (padding unit 255 of h is held at 1.0, column 255 of its W_hh copy = bias)
  *   y     [T*B, 512] f16    out: h_t, row-major, columns dir*256 + unit
  *   cst   [T*B, 512] f32    out: c_t (stash for BPTT), INTERLEAVED with 4-float chunks ([rows/32][512/4][32][4])
- * Backward: dy [T*B,512] f16 (scaled dL/dy), whhT [256,2048] f16 (whh^T) -> gates becomes dgates
+ * Backward: dy [T*B,512] f16 (scaled dL/dy), INTERLEAVED like the gates ([rows/32][512/8][32][8]: a warp's 32 rows x
+ * 8 units are 512 contiguous bytes; avsi_gemm_f16 writes it with layout bit 1), whhT [256,2048] f16 (whh^T) -> gates becomes dgates
  * (in place), dbias[2048] f32 += column sums, scratch >= avsi_lstm_bwd_scratch_bytes(B). */
 int avsi_lstm_fwd(uint16_t* gates, const uint16_t* whh, const float* bias, uint16_t* y, float* cst,
                   int T, int B, void* stream);
@@ -201,9 +202,10 @@ int avsi_mtl_scales(const float* hole_count, int B, float ctc_weight, float* out
 /* Inverted dropout of the BLSTM outputs ahead of the head(s): tf.nn.dropout(rnn_outputs, rate=dropout_rate) at
  * models.py:117, :1901, models_asr.py:120.  dst[r,c] = keep ? src[r,c] / (1 - rate) : 0 with keep = (u >= rate),
  * u = Philox-4x32-10(seed; offset, element) -- a pure function of its arguments, so the backward pass applies the
- * same call to dY.  src/dst f16 [rows, ld] (may alias), cols % 8 == 0; keep_out optional u8 [rows, cols]. */
+ * same call to dY.  src/dst f16 [rows, ld] (may alias), cols % 8 == 0; keep_out optional u8 [rows, cols];
+ * layout bit 0 / bit 1: src / dst is stored INTERLEAVED like the gate tensor (then ld = cols). */
 int avsi_dropout_f16(const void* src, int ld_src, void* dst, int ld_dst, int64_t rows, int cols, float rate,
-                     uint64_t seed, uint64_t offset, void* keep_out, void* stream);
+                     uint64_t seed, uint64_t offset, void* keep_out, int layout, void* stream);
 
 /* Column sums: out[n] += sum_r X[r, col0 + n] (f16 in, f32 out) -- bias gradients. */
 int avsi_colsum_f16(const uint16_t* X, int ldx, int rows, int col0, int ncols, float* out, void* stream);

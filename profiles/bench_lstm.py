@@ -21,7 +21,7 @@ for B in BS:
     bias = torch.zeros(2048, device=d)
     y = torch.empty(T * B, 512, dtype=torch.float16, device=d)
     cst = torch.empty(-(-T * B // 32) * 32, 512, device=d)
-    dy = torch.randn(T * B, 512, device=d).half()
+    dy = torch.randn(-(-T * B // 32) * 32, 512, device=d).half()          # interleaved dL/dy (values are random anyway)
     dbias = torch.zeros(2048, device=d)
     scratch = torch.empty(16, device=d)
 

@@ -528,7 +528,7 @@ def test_lstm_recurrence_fwd_bwd(T, B):
     assert rel_l2(Yg, Yr) < 1e-3 and rel_l2(Cg, Cr) < 1e-3 and rel_l2(Gg, Gr) < 1e-3, msg
     assert np.all(Yg[..., H:] == 0) and np.all(Cg[..., H:] == 0)       # padded units stay exactly zero
     # backward
-    dy = torch.from_numpy(R.reshape(T * B, 512)).to(d)
+    dy = blstm.to_il(torch.from_numpy(R.reshape(T * B, 512)).to(d))                      # dL/dy is interleaved like the gates
     dbias = torch.zeros(2048, device=d)
     scratch = torch.empty(int(lib.avsi_lstm_bwd_scratch_bytes(B)) // 4 + 4, device=d)
     _lib.check(lib.avsi_lstm_bwd(_lib.ptr(gates), _lib.ptr(whhT), _lib.ptr(cst), _lib.ptr(dy), _lib.ptr(dbias),
@@ -609,7 +609,7 @@ def test_dropout_kernel(rate):
         dst = src if inplace else torch.empty_like(src)
         keep = torch.empty(rows, cols, dtype=torch.uint8, device=d)
         _lib.check(lib.avsi_dropout_f16(_lib.ptr(src), ld, _lib.ptr(dst), ld, rows, cols, rate, seed, offset, _lib.ptr(keep),
-                                        _lib.stream_ptr()), 'avsi_dropout_f16')
+                                        0, _lib.stream_ptr()), 'avsi_dropout_f16')
         return dst, keep
     y, keep = run(x, seed, offset)
     y2, keep2 = run(x, seed, offset)
@@ -638,6 +638,12 @@ def test_dropout_kernel(rate):
     z = x.clone()
     z, _ = run(z, seed, offset, inplace=True)
     assert torch.equal(z, y)
+    # interleaved storage (dY): same mask per logical element
+    from avsi_b200 import blstm
+    xi = blstm.to_il(x)
+    _lib.check(lib.avsi_dropout_f16(_lib.ptr(xi), cols, _lib.ptr(xi), cols, rows, cols, rate, seed, offset, None, 3,
+                                    _lib.stream_ptr()), 'avsi_dropout_f16')
+    assert torch.equal(blstm.from_il(xi, rows), y)
 
 
 def test_preemphasis_mfcc_delta_features():
