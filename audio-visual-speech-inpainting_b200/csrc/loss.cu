@@ -81,25 +81,50 @@ masked_l1_kernel(const float* __restrict__ logits, int ldl, const float* __restr
   if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(sums + 5, (double)rows * F);
 }
 
-__global__ void __launch_bounds__(256)
+// Column sums of an f16 matrix (bias gradients): a thread owns 8 consecutive columns (one 16-byte load per row) and every
+// 8th ... row of its block's slab, so a warp reads whole 512-byte row segments; fp32 partials meet in shared memory and
+// leave as one atomicAdd per column and block.  HBM-bound: the matrix is read once.
+constexpr int CS_VECS = 64;                       // column vectors (x 8 columns) per block
+constexpr int CS_ROWS = 4;                        // row lanes per block (256 threads)
+
+__global__ void __launch_bounds__(CS_VECS * CS_ROWS)
 colsum_f16_kernel(const uint16_t* __restrict__ X, int ldx, int rows, int col0, int ncols,
                   float* __restrict__ out) {
-  // block handles 32 columns x a slab of rows; threads (32 cols x 8 row lanes)
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int rl = threadIdx.x >> 5;
-  float acc = 0.f;
-  if (c < ncols) {
-    for (long long r = (long long)blockIdx.y * 8 + rl; r < rows; r += (long long)gridDim.y * 8)
-      acc += __half2float(__ushort_as_half(X[r * ldx + col0 + c]));
-  }
-  __shared__ float red[8][33];
-  red[rl][threadIdx.x & 31] = acc;
-  __syncthreads();
-  if (rl == 0 && c < ncols) {
-    float v = 0.f;
+  const int v = threadIdx.x % CS_VECS, rl = threadIdx.x / CS_VECS;
+  const int c = (blockIdx.x * CS_VECS + v) * 8;                     // first of this thread's 8 columns (relative to col0)
+  float acc[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v += red[i][threadIdx.x & 31];
-    atomicAdd(out + c, v);
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  const long long rows_per = ((long long)rows + gridDim.y - 1) / gridDim.y;
+  const long long r0 = (long long)blockIdx.y * rows_per, r1 = min((long long)rows, r0 + rows_per);
+  if (c < ncols) {
+    const bool vec = (c + 8 <= ncols) && (((col0 + c) & 7) == 0) && ((ldx & 7) == 0);
+    for (long long r = r0 + rl; r < r1; r += CS_ROWS) {
+      const uint16_t* src = X + r * ldx + col0 + c;
+      if (vec) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(src));
+        const float2 a = unpack_half2(q.x), b2 = unpack_half2(q.y), c2 = unpack_half2(q.z), d = unpack_half2(q.w);
+        acc[0] += a.x; acc[1] += a.y; acc[2] += b2.x; acc[3] += b2.y;
+        acc[4] += c2.x; acc[5] += c2.y; acc[6] += d.x; acc[7] += d.y;
+      } else {
+        for (int i = 0; i < 8 && c + i < ncols; ++i) acc[i] += __half2float(__ushort_as_half(__ldg(src + i)));
+      }
+    }
+  }
+  __shared__ float red[CS_ROWS][CS_VECS][9];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[rl][v][i] = acc[i];
+  __syncthreads();
+  if (rl == 0 && c < ncols && r1 > r0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (c + i < ncols) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < CS_ROWS; ++k) t += red[k][v][i];
+        atomicAdd(out + c + i, t);
+      }
+    }
   }
 }
 
@@ -127,9 +152,12 @@ extern "C" int avsi_colsum_f16(const uint16_t* X, int ldx, int rows, int col0, i
   using namespace avsi;
   AVSI_REQUIRE(X && out, "null pointer");
   AVSI_REQUIRE(rows > 0 && ncols > 0 && ldx >= col0 + ncols, "sizes");
-  dim3 grid((ncols + 31) / 32, (unsigned)min((long long)(rows + 255) / 256, (long long)64));
-  if (grid.y == 0) grid.y = 1;
-  colsum_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, ldx, rows, col0, ncols, out);
+  const unsigned gx = (unsigned)((ncols + CS_VECS * 8 - 1) / (CS_VECS * 8));
+  long long gy = ((long long)num_sms() * 8 + gx - 1) / gx;                       // ~8 blocks per SM in total
+  if (gy > (rows + 63) / 64) gy = (rows + 63) / 64;
+  if (gy < 1) gy = 1;
+  dim3 grid(gx, (unsigned)gy);
+  colsum_f16_kernel<<<grid, CS_VECS * CS_ROWS, 0, (cudaStream_t)stream>>>(X, ldx, rows, col0, ncols, out);
   AVSI_LAUNCH_CHECK();
   return AVSI_OK;
 }

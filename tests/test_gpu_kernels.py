@@ -459,6 +459,13 @@ def test_colsum():
     sync()
     ref = X[:, 3:294].double().sum(0).cpu().numpy() + 1.0
     assert np.abs(out.cpu().numpy() - ref).max() < 1e-3
+    # aligned vector path (col0 = 0, the head-bias gradient's call), ragged column count, many rows, one row
+    for rows, ld, c0, nc in ((50000, 320, 0, 257), (1, 64, 8, 17), (333, 2048, 1024, 1024)):
+        X = torch.randn(rows, ld, device=d).half()
+        out = torch.zeros(nc, device=d)
+        _lib.check(lib.avsi_colsum_f16(_lib.ptr(X), ld, rows, c0, nc, _lib.ptr(out), _lib.stream_ptr()), 'colsum')
+        ref = X[:, c0:c0 + nc].double().sum(0).cpu().numpy()
+        assert np.abs(out.cpu().numpy() - ref).max() < 2e-3 * max(1.0, np.sqrt(rows) / 10), (rows, ld, c0, nc)
 
 
 # ------------------------------------------------------------------------------------------ LSTM recurrence
