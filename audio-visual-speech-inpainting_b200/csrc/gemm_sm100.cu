@@ -213,14 +213,44 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     tc_fence_after();
     const int row = m_blk * GEMM_BM + quarter * 32 + lane;
     const bool row_ok = row < p.M;
+    // fp32 row-major output (the head's logits): a thread owns a ROW of the accumulator, so a direct store instruction
+    // scatters 32 x 16 bytes over 32 rows.  The pipeline's shared memory is idle once the accumulator is complete: each
+    // warp turns its 32 x 32 block through a padded tile there and stores 4 full 128-byte row segments per instruction.
+    const bool via_smem = (p.out_mode == 1) && (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
+                          (S::BAR_OFFSET >= 4 * 32 * 36 * 4);
+    float* tile = reinterpret_cast<float*>(smem_dyn + (smem_base - smem_u32(smem_dyn))) + (warp - 2) * (32 * 36);
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t r[32];
       tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(c * 32), r);
       tmem_ld_wait();
       const int n0 = n_blk * BN + c * 32;
-      if (!row_ok || n0 >= p.N) continue;
+      if (n0 >= p.N) continue;                       // uniform for the warp
       const bool full = (n0 + 32 <= p.N);
+      if (via_smem && full) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(tile + lane * 36 + 4 * j) =
+              make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                          __uint_as_float(r[4 * j + 3]));
+        __syncwarp();
+        const int cl = (lane & 7) * 4;               // this lane's 4 columns of the block
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias)                                  // (the bias is a view into the flat parameter buffer: no alignment promise)
+          bv = make_float4(__ldg(p.bias + n0 + cl), __ldg(p.bias + n0 + cl + 1), __ldg(p.bias + n0 + cl + 2),
+                           __ldg(p.bias + n0 + cl + 3));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rl = 4 * i + (lane >> 3);        // row of the block
+          const int grow = m_blk * GEMM_BM + quarter * 32 + rl;
+          float4 v = *reinterpret_cast<const float4*>(tile + rl * 36 + cl);
+          v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+          if (grow < p.M) *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + (long long)grow * p.ldc + n0 + cl) = v;
+        }
+        __syncwarp();
+        continue;
+      }
+      if (!row_ok) continue;
       epilogue_store(p, row, n0, full, r);
     }
   }
