@@ -67,7 +67,7 @@ SIGNATURES = {
     'avsi_feature_stats': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     'avsi_gemm_f16': (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p,
                               c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
-    'avsi_lstm_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    'avsi_lstm_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     'avsi_lstm_bwd_scratch_bytes': (c_int64, [c_int]),
     'avsi_lstm_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     'avsi_masked_l1': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,

@@ -15,6 +15,8 @@ interleaved layout of common.cuh, the forward weight copies / bias carry the 1/2
             dY_{l-1} = G_l . Wih_l               tcgen05 GEMM -> f16
 Gradients are computed on loss-scaled fp16 activations gradients and unscaled inside Adam.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -29,7 +31,7 @@ def _p(t):
     return _lib.ptr(t)
 
 
-A_IL, C_IL = 1, 2     # avsi_gemm_f16 layout bits: A operand / f16 output stored interleaved (include/avsi_b200.h)
+A_IL, C_IL, B_IL = 1, 2, 4     # avsi_gemm_f16 layout bits: A operand / f16 output / B operand stored interleaved (include/avsi_b200.h)
 
 
 def gemm(A, lda, B, ldb, C, ldc, bias, M, N, K, trans, out_mode, split_k=1, tag='gemm', layout=0):
@@ -140,6 +142,12 @@ class BLSTMEngine(object):
         # contractions are then plain row-shifted views (h_{-1} = h_T = 0)
         ws['Ybuf'] = [torch.zeros(M + 2 * B, NY, dtype=torch.float16, device=dev) for _ in range(L.n_layers)]
         ws['Y'] = [yb[B:B + M] for yb in ws['Ybuf']]
+        # AVSI_Y_IL=1 (B a multiple of 32): the layer outputs are stored INTERLEAVED like G (the zero frames and the row
+        # shifts by B are then whole 32-row blocks); the recurrence kernel stores 512-byte runs instead of 32 scattered
+        # sectors per warp and the GEMMs read Y through their interleaved A / B operand paths.  Measured on the same
+        # box (profiles/README.md): forward recurrence -0.10 ms per step, but the un-swizzled operand tiles cost the
+        # dW / projection GEMMs 0.30 ms -- off by default
+        ws['y_il'] = 1 if (B % 32 == 0 and os.environ.get('AVSI_Y_IL', '0') == '1') else 0
         ws['C'] = [torch.zeros(Mp, NY, dtype=torch.float32, device=dev) for _ in range(L.n_layers if training else 1)]
         ws['logits'] = torch.zeros(M, L.nop, dtype=torch.float32, device=dev)
         if training:
@@ -163,18 +171,19 @@ class BLSTMEngine(object):
         L = self.layout
         T, B, M = ws['T'], ws['B'], ws['M']
         training = len(ws['G']) == L.n_layers
+        yil = ws['y_il']
         x, ldx = ws['x0'], L.k0p
         for l in range(L.n_layers):
             G = ws['G'][l if training else 0]
             C = ws['C'][l if training else 0]
             kp = L.layer_k(l)
             gemm(_p(x), ldx, _p(self.half['wih%d' % l]), kp, _p(G), NG, None, M, NG, kp, 0, 0,
-                 tag='gemm_proj_fwd', layout=C_IL)
+                 tag='gemm_proj_fwd', layout=C_IL | (A_IL if (l > 0 and yil) else 0))
             # HBM-bound at large batch: per row the kernel reads G (4096 B), writes the activated gates (4096 B),
             # c_t (2048 B) and h_t (1024 B); the recurrent product adds 2*M*2048*256 flops
             with _lib.span('lstm_fwd', nbytes=M * (2 * NG * 2 + NY * 4 + NY * 2), flops=2 * M * NG * HP):
                 _lib.check(lib.avsi_lstm_fwd(_p(G), _p(self.half['whh%d' % l]), _p(self.bias_fwd[l]), _p(ws['Y'][l]), _p(C),
-                                             T, B, _lib.stream_ptr()), 'avsi_lstm_fwd')
+                                             T, B, yil, _lib.stream_ptr()), 'avsi_lstm_fwd')
             x, ldx = ws['Y'][l], NY
         ws['drop'] = None
         if dropout is not None and dropout[0] > 0.0:
@@ -182,11 +191,11 @@ class BLSTMEngine(object):
                 ws['Ydrop'] = torch.empty(M, NY, dtype=torch.float16, device=self.device)
             with _lib.span('dropout', nbytes=2 * M * NY * 2):
                 _lib.check(lib.avsi_dropout_f16(_p(x), NY, _p(ws['Ydrop']), NY, M, NY, float(dropout[0]), int(dropout[1]),
-                                                int(dropout[2]), None, 0, _lib.stream_ptr()), 'avsi_dropout_f16')
+                                                int(dropout[2]), None, 3 if yil else 0, _lib.stream_ptr()), 'avsi_dropout_f16')
             x = ws['Ydrop']
             ws['drop'] = (float(dropout[0]), int(dropout[1]), int(dropout[2]))
         gemm(_p(x), NY, _p(self.half['head']), NY, _p(ws['logits']), L.nop, _p(self.view(self.theta, 'head_b')),
-             M, L.n_out, NY, 0, 1, tag='gemm_head_fwd')
+             M, L.n_out, NY, 0, 1, tag='gemm_head_fwd', layout=A_IL if yil else 0)
         return ws['logits']
 
     # ---- backward -----------------------------------------------------------------------------
@@ -203,8 +212,10 @@ class BLSTMEngine(object):
         drop = ws.get('drop')
         ylast = ws['Ydrop'] if drop else ws['Y'][L.n_layers - 1]
         # head: dW = dlogits^T . Y ; db = colsum(dlogits) ; dY = dlogits . Whead
+        yil = ws['y_il']
+        bil = B_IL if yil else 0
         gemm(_p(dl), L.nop, _p(ylast), NY, _p(self.view(g, 'head_w')), NY, None, L.n_out, NY, M, 1, 2,
-             pick_split_k(L.n_out, NY, M), tag='gemm_dw')
+             pick_split_k(L.n_out, NY, M), tag='gemm_dw', layout=bil)
         _lib.check(lib.avsi_colsum_f16(_p(dl), L.nop, M, 0, L.n_out, _p(self.view(g, 'head_b')), st()), 'avsi_colsum_f16')
         dY = ws['dY'][0]
         gemm(_p(dl), L.nop, _p(self.half['headT']), L.nop, _p(dY), NY, None, M, NY, L.nop, 0, 0, tag='gemm_dx', layout=C_IL)
@@ -223,18 +234,21 @@ class BLSTMEngine(object):
             x, ldx = (ws['x0'], L.k0p) if l == 0 else (ws['Y'][l - 1], NY)
             # dWih = dG^T . X
             gemm(_p(G), NG, _p(x), ldx, _p(self.view(g, 'wih%d' % l)), kp, None, NG, kp, M, 1, 2,
-                 pick_split_k(NG, kp, M), tag='gemm_dw', layout=A_IL)
+                 pick_split_k(NG, kp, M), tag='gemm_dw', layout=A_IL | (bil if l > 0 else 0))
             # dWhh[dir] = dG[dir]^T . h_prev  (fw: h_{t-1}, bw: h_{t+1}): row-shifted views of the zero-framed Y
             if T > 1:
                 gw = self.view(g, 'whh%d' % l)
                 sk = pick_split_k(GATES * HP, HP, M, 148)
                 yb = ws['Ybuf'][l].data_ptr()
                 gemm(G.data_ptr(), NG, yb, NY, _p(gw), HP, None, GATES * HP, HP, M, 1, 2, sk, tag='gemm_dw',
-                     layout=A_IL)
+                     layout=A_IL | bil)
                 a_bw = G.data_ptr() + (GATES * HP // 8) * 512            # IL column offset: 512 B per 8-column chunk
-                b_bw = yb + (2 * B * NY + HP) * 2
+                if yil:     # row 2B of Ybuf = 2B/32 row blocks of NY/8 chunks of 512 B; column HP = HP/8 chunks further
+                    b_bw = yb + ((2 * B // 32) * (NY // 8) + HP // 8) * 512
+                else:
+                    b_bw = yb + (2 * B * NY + HP) * 2
                 gemm(a_bw, NG, b_bw, NY, gw.data_ptr() + GATES * HP * HP * 4, HP, None, GATES * HP, HP, M, 1, 2, sk,
-                     tag='gemm_dw', layout=A_IL)
+                     tag='gemm_dw', layout=A_IL | bil)
             if l > 0:
                 nxt = 1 - cur
                 gemm(_p(G), NG, _p(self.half['wihT%d' % l]), NG, _p(ws['dY'][nxt]), NY, None, M, NY, NG, 0, 0,

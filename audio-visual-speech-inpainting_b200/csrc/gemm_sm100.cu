@@ -17,6 +17,8 @@
 //   layout & 1  A is stored INTERLEAVED (common.cuh il16: [rows/32][cols/8][32][8]); one 3-D TMA box per
 //               stage lands it as SWIZZLE_NONE core matrices: K-major [k-chunk][128 rows][16 B] (trans 0,
 //               LBO 2048 / SBO 128) or MN-major [m-chunk][64 k-rows][16 B] (trans 1, LBO 128 / SBO 1024)
+//   layout & 4  B is stored interleaved likewise (trans = 1 only: the [K, N] operand of the dW contractions, e.g. the
+//               layer outputs Y); tile = [n-chunk][64 k-rows][16 B], the mirror image of the interleaved A^T tile
 //   layout & 2  the f16 output (out_mode 0) is written interleaved: a warp's 32 rows x 8 columns are one
 //               contiguous 512-byte store
 // Shared-memory matrix descriptors follow the canonical SWIZZLE_128B layouts
@@ -40,7 +42,7 @@ struct GemmParams {
   const float* bias;
   int ldc, M, N, K;
   int trans, out_mode, split_k;
-  int a_il, c_il;
+  int a_il, c_il, b_il;
 };
 
 template <int BN, int STAGES>
@@ -174,8 +176,11 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
             for (int a = 0; a < GEMM_BM / 64; ++a) tma_load_2d(sa + a * 8192, &tmA, full_bar(s), m_blk * GEMM_BM + 64 * a, k0);
           }
+          if (p.b_il) tma_load_3d(sb, &tmB, full_bar(s), 0, k0 >> 5, n_blk * (BN / 8));
+          else {
 #pragma unroll
-          for (int b = 0; b < BN / 64; ++b) tma_load_2d(sb + b * 8192, &tmB, full_bar(s), n_blk * BN + 64 * b, k0);
+            for (int b = 0; b < BN / 64; ++b) tma_load_2d(sb + b * 8192, &tmB, full_bar(s), n_blk * BN + 64 * b, k0);
+          }
         }
       }
     }
@@ -199,7 +204,8 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int k = 0; k < GEMM_BK / 16; ++k) {
           const uint64_t da = p.a_il ? make_smem_desc(sa + k * a_kstep, a_lbo, a_sbo, 0u)
                                      : make_smem_desc(sa + k * kstep, lbo, 1024u);
-          const uint64_t db = make_smem_desc(sb + k * kstep, lbo, 1024u);
+          const uint64_t db = p.b_il ? make_smem_desc(sb + k * a_kstep, a_lbo, a_sbo, 0u)
+                                     : make_smem_desc(sb + k * kstep, lbo, 1024u);
           umma_f16(tmem_base, da, db, idesc, (i > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(empty_bar(s));               // frees the smem slot when these MMAs retire
@@ -361,8 +367,11 @@ gemm_f16_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
               for (int a = 0; a < GEMM_BM / 64; ++a) tma_load_2d_2sm(sa + a * 8192, &tmA, lead_full, m0 + 64 * a, k0);
             }
+            if (p.b_il) tma_load_3d_2sm(sb, &tmB, lead_full, 0, k0 >> 5, n0 / 8);
+            else {
 #pragma unroll
-            for (int b = 0; b < BN / 128; ++b) tma_load_2d_2sm(sb + b * 8192, &tmB, lead_full, n0 + 64 * b, k0);
+              for (int b = 0; b < BN / 128; ++b) tma_load_2d_2sm(sb + b * 8192, &tmB, lead_full, n0 + 64 * b, k0);
+            }
           }
         }
       }
@@ -394,7 +403,8 @@ gemm_f16_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int k = 0; k < GEMM_BK / 16; ++k) {
             const uint64_t da = p.a_il ? make_smem_desc(sa + k * a_kstep, a_lbo, a_sbo, 0u)
                                        : make_smem_desc(sa + k * kstep, lbo, 1024u);
-            const uint64_t db = make_smem_desc(sb + k * kstep, lbo, 1024u);
+            const uint64_t db = p.b_il ? make_smem_desc(sb + k * a_kstep, a_lbo, a_sbo, 0u)
+                                       : make_smem_desc(sb + k * kstep, lbo, 1024u);
             umma_f16_2sm(td, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit_2sm(empty_bar(s), (uint16_t)3);                    // frees the slot in both CTAs
@@ -623,9 +633,10 @@ extern "C" int avsi_gemm_f16(const uint16_t* A, int lda, const uint16_t* B, int 
   AVSI_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "lda/ldb multiples of 8");
   AVSI_REQUIRE(((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0), "A/B 16-byte aligned");
   AVSI_REQUIRE(ldc >= N, "ldc >= N");
-  AVSI_REQUIRE(layout >= 0 && layout <= 3, "layout");
+  AVSI_REQUIRE(layout >= 0 && layout <= 7, "layout");
   AVSI_REQUIRE(!(layout & 2) || (out_mode == 0 && ldc % 8 == 0), "interleaved output needs out_mode 0 and ldc % 8 == 0");
-  GemmParams p{C, bias, ldc, M, N, K, trans, out_mode, split_k, layout & 1, (layout >> 1) & 1};
+  AVSI_REQUIRE(!(layout & 4) || (trans == 1 && ldb % 8 == 0), "interleaved B needs trans = 1 and ldb % 8 == 0");
+  GemmParams p{C, bias, ldc, M, N, K, trans, out_mode, split_k, layout & 1, (layout >> 1) & 1, (layout >> 2) & 1};
   cudaStream_t st = (cudaStream_t)stream;
 
   static int debug_simt = -1;
@@ -686,7 +697,8 @@ extern "C" int avsi_gemm_f16(const uint16_t* A, int lda, const uint16_t* B, int 
       rc2 = (layout & 1) ? get_tmap_il(A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, GEMM_BK / 32, GEMM_BM / 8, &ta2)
                          : get_tmap(A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, GEMM_BK, &ta2);
       if (rc2) return rc2;
-      rc2 = get_tmap(B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, GEMM_BK, &tb2);
+      rc2 = (layout & 4) ? get_tmap_il(B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, GEMM_BK / 32, 128 / 8, &tb2)
+                         : get_tmap(B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, GEMM_BK, &tb2);
       if (rc2) return rc2;
     }
     return launch_gemm_2sm<256>(ta2, tb2, p, st);
@@ -707,7 +719,8 @@ extern "C" int avsi_gemm_f16(const uint16_t* A, int lda, const uint16_t* B, int 
     rc = (layout & 1) ? get_tmap_il(A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, GEMM_BK / 32, GEMM_BM / 8, &ta)
                       : get_tmap(A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, GEMM_BK, &ta);
     if (rc) return rc;
-    rc = get_tmap(B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, GEMM_BK, &tb);
+    rc = (layout & 4) ? get_tmap_il(B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, GEMM_BK / 32, (uint32_t)bn / 8, &tb)
+                      : get_tmap(B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, GEMM_BK, &tb);
     if (rc) return rc;
   }
   if (bn == 256) return launch_gemm<256, 4>(ta, tb, p, st);

@@ -64,7 +64,7 @@ struct LstmFwdSmem {
 template <int BT>
 __global__ void __cluster_dims__(LS_CL, 1, 1) __launch_bounds__(LS_THREADS, 1)
 lstm_fwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whh, const float* __restrict__ bias,
-                uint16_t* __restrict__ y, float* __restrict__ cst, int T, int B) {
+                uint16_t* __restrict__ y, float* __restrict__ cst, int T, int B, int y_il) {
   constexpr int MT = BT / 16;
   constexpr uint32_t PHASE_BYTES = BT * LS_HP * 2;
   extern __shared__ __align__(16) unsigned char ls_smem[];
@@ -185,7 +185,9 @@ lstm_fwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whh, 
           *reinterpret_cast<uint2*>(gates + il16(r, dir * LS_G + u * 4, 2 * LS_G)) =
               make_uint2(pack_half2(gi, gg), pack_half2(gf, go));
           cst[il32(r, dir * LS_HP + u, 2 * LS_HP)] = c;
-          if (uu == 0) *reinterpret_cast<uint2*>(y + r * (2 * LS_HP) + dir * LS_HP + u_base) = make_uint2(lo, hi);
+          if (uu == 0)
+            *reinterpret_cast<uint2*>(y + (y_il ? il16(r, dir * LS_HP + u_base, 2 * LS_HP) : r * (2 * LS_HP) + dir * LS_HP + u_base)) =
+                make_uint2(lo, hi);
         }
       }
   }
@@ -406,7 +408,7 @@ static int pick_bt(int B) {
 }
 
 template <int BT>
-static int launch_fwd(uint16_t* gates, const uint16_t* whh, const float* bias, uint16_t* y, float* cst, int T, int B,
+static int launch_fwd(uint16_t* gates, const uint16_t* whh, const float* bias, uint16_t* y, float* cst, int T, int B, int y_il,
                       cudaStream_t st) {
   static bool attr_done = false;
   const int smem = (int)sizeof(LstmFwdSmem<BT>);
@@ -415,7 +417,7 @@ static int launch_fwd(uint16_t* gates, const uint16_t* whh, const float* bias, u
     attr_done = true;
   }
   const int grid = 2 * ((B + BT - 1) / BT) * LS_CL;
-  lstm_fwd_kernel<BT><<<grid, LS_THREADS, smem, st>>>(gates, whh, bias, y, cst, T, B);
+  lstm_fwd_kernel<BT><<<grid, LS_THREADS, smem, st>>>(gates, whh, bias, y, cst, T, B, y_il);
   AVSI_LAUNCH_CHECK();
   return AVSI_OK;
 }
@@ -438,7 +440,7 @@ static int launch_bwd(uint16_t* gates, const uint16_t* whhT, const float* cst, c
 int launch_lstm4_bwd(uint16_t* gates, const uint16_t* whhT, const float* cst, const uint16_t* dy, float* dbias, int T,
                      int B, cudaStream_t st);   // lstm4_bwd.cu
 int launch_lstm4_fwd(uint16_t* gates, const uint16_t* whh, const float* bias, uint16_t* y, float* cst, int T, int B,
-                     cudaStream_t st);     // lstm4.cu
+                     int y_il, cudaStream_t st);     // lstm4.cu
 
 // which forward kernel: tcgen05 (128-row tiles) once the batch no longer fits 16-row mma.sync tiles
 // in one wave of clusters.  AVSI_LSTM_FWD=mma|tc overrides (A/B measurements only).
@@ -458,17 +460,17 @@ static int fwd_kernel_choice(int B) {
 }  // namespace avsi
 
 extern "C" int avsi_lstm_fwd(uint16_t* gates, const uint16_t* whh, const float* bias, uint16_t* y, float* cst,
-                             int T, int B, void* stream) {
+                             int T, int B, int y_il, void* stream) {
   using namespace avsi;
   AVSI_REQUIRE(gates && whh && bias && y && cst, "null pointer");
   AVSI_REQUIRE(T > 0 && B > 0, "T,B > 0");
   const int bt = pick_bt(B);
   cudaStream_t st = (cudaStream_t)stream;
   const int kc = fwd_kernel_choice(B);
-  if (kc == 2) return launch_lstm4_fwd(gates, whh, bias, y, cst, T, B, st);
-  if (bt == 16) return launch_fwd<16>(gates, whh, bias, y, cst, T, B, st);
-  if (bt == 32) return launch_fwd<32>(gates, whh, bias, y, cst, T, B, st);
-  return launch_fwd<64>(gates, whh, bias, y, cst, T, B, st);
+  if (kc == 2) return launch_lstm4_fwd(gates, whh, bias, y, cst, T, B, y_il, st);
+  if (bt == 16) return launch_fwd<16>(gates, whh, bias, y, cst, T, B, y_il, st);
+  if (bt == 32) return launch_fwd<32>(gates, whh, bias, y, cst, T, B, y_il, st);
+  return launch_fwd<64>(gates, whh, bias, y, cst, T, B, y_il, st);
 }
 
 extern "C" int64_t avsi_lstm_bwd_scratch_bytes(int B) {

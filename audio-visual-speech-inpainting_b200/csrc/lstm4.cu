@@ -84,7 +84,7 @@ __device__ unsigned long long g_l4_timing[16];
 template <int ACT, bool TIMING>
 __global__ void __cluster_dims__(L4_CL, 1, 1) __launch_bounds__(L4_THREADS, 1)
 lstm4_fwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whh, const float* __restrict__ bias,
-                 uint16_t* __restrict__ y, float* __restrict__ cst, int T, int B, int PREFETCH) {
+                 uint16_t* __restrict__ y, float* __restrict__ cst, int T, int B, int PREFETCH, int y_il) {
   extern __shared__ unsigned char l4_smem_raw[];
   const uint32_t raw_s = smem_u32(l4_smem_raw);
   const uint32_t base_s = (raw_s + 127u) & ~127u;
@@ -300,8 +300,15 @@ lstm4_fwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whh,
         }
         L4_TICK(2 + p);
       }
-      if (row_ok)                                    // h_t of the warp's 16 units: one 32-byte store per row
-        st_global_v8(y + grow * (2 * L4_HP) + dir * L4_HP + j * 64 + cg * 16, hv[0], hv[1]);
+      if (row_ok) {
+        const int u0 = dir * L4_HP + j * 64 + cg * 16;
+        if (y_il) {                                  // interleaved y: two 512-byte runs per warp instead of 32 scattered sectors
+          *reinterpret_cast<uint4*>(y + il16(grow, u0, 2 * L4_HP)) = hv[0];
+          *reinterpret_cast<uint4*>(y + il16(grow, u0 + 8, 2 * L4_HP)) = hv[1];
+        } else {                                     // h_t of the warp's 16 units: one 32-byte store per row
+          st_global_v8(y + grow * (2 * L4_HP) + u0, hv[0], hv[1]);
+        }
+      }
       L4_TICK(4);
     }
     if (timing) {
@@ -318,7 +325,7 @@ lstm4_fwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whh,
 }
 
 int launch_lstm4_fwd(uint16_t* gates, const uint16_t* whh, const float* bias, uint16_t* y, float* cst, int T, int B,
-                     cudaStream_t st) {
+                     int y_il, cudaStream_t st) {
   // AVSI_LSTM_ACT=exact: ex2/rcp activations; AVSI_L4_TIMING=1: in-kernel phase timers (profiles/bench_lstm.py)
   static int mode = -1;
   if (mode < 0) {
@@ -340,7 +347,7 @@ int launch_lstm4_fwd(uint16_t* gates, const uint16_t* whh, const float* bias, ui
       AVSI_CUDA(cudaFuncSetAttribute(lstm4_fwd_kernel<ACT_, TIM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
       attr_done[mode] = true;                                                                                          \
     }                                                                                                                  \
-    lstm4_fwd_kernel<ACT_, TIM_><<<grid, L4_THREADS, smem, st>>>(gates, whh, bias, y, cst, T, B, pf);                   \
+    lstm4_fwd_kernel<ACT_, TIM_><<<grid, L4_THREADS, smem, st>>>(gates, whh, bias, y, cst, T, B, pf, y_il);                   \
   } while (0)
   if (mode == 0) L4_LAUNCH(0, false);
   else if (mode == 1) L4_LAUNCH(1, false);

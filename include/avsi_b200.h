@@ -148,7 +148,8 @@ int avsi_feature_stats(const float* x, int ldx, const float* mask, int ldm, int6
  *   split_k > 1 only with out_mode 2.  lda/ldb multiples of 8 elements; A,B 16-byte aligned.
  *   layout bit 0: A is stored interleaved ("IL": [rows/32][lda/8][32][8] halves, rows padded to 32 with
  *   zeros) instead of row-major; layout bit 1: the f16 output C (out_mode 0) is written interleaved with
- *   row length ldc.  IL is the layout of the gate tensors G / dG shared with the recurrence kernels. */
+ *   row length ldc; layout bit 2: B is stored interleaved likewise (trans == 1 only).  IL is the layout of the
+ *   gate tensors G / dG, of dL/dy and (optionally) of the layer outputs y shared with the recurrence kernels. */
 int avsi_gemm_f16(const uint16_t* A, int lda, const uint16_t* B, int ldb, void* C, int ldc,
                   const float* bias, int M, int N, int K, int trans, int out_mode, int split_k,
                   int layout, void* stream);
@@ -167,13 +168,14 @@ int avsi_gemm_f16(const uint16_t* A, int lda, const uint16_t* B, int ldb, void* 
  *   whh   [2,1024,256] f16  recurrent weights, [dir][gate column][h_in], i, f, o rows pre-halved likewise
  *   bias  [2048] f32        prescaled likewise (avsi_gate_bias_prescale).  The tcgen05 kernel feeds it through the
  *                           tensor core (padding unit 255 of h is held at 1.0, column 255 of its W_hh copy = bias)
- *   y     [T*B, 512] f16    out: h_t, row-major, columns dir*256 + unit
+ *   y     [T*B, 512] f16    out: h_t, columns dir*256 + unit; row-major, or with y_il != 0 INTERLEAVED like the gates
+ *                           (rows padded to 32; the consumers are avsi_gemm_f16 with layout bits 0 / 2)
  *   cst   [T*B, 512] f32    out: c_t (stash for BPTT), INTERLEAVED with 4-float chunks ([rows/32][512/4][32][4])
  * Backward: dy [T*B,512] f16 (scaled dL/dy), INTERLEAVED like the gates ([rows/32][512/8][32][8]: a warp's 32 rows x
  * 8 units are 512 contiguous bytes; avsi_gemm_f16 writes it with layout bit 1), whhT [256,2048] f16 (whh^T) -> gates becomes dgates
  * (in place), dbias[2048] f32 += column sums, scratch >= avsi_lstm_bwd_scratch_bytes(B). */
 int avsi_lstm_fwd(uint16_t* gates, const uint16_t* whh, const float* bias, uint16_t* y, float* cst,
-                  int T, int B, void* stream);
+                  int T, int B, int y_il, void* stream);
 int64_t avsi_lstm_bwd_scratch_bytes(int B);
 int avsi_lstm_bwd(uint16_t* gates, const uint16_t* whhT, const float* cst, const uint16_t* dy,
                   float* dbias, void* scratch, int T, int B, void* stream);

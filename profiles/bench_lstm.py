@@ -12,6 +12,7 @@ from avsi_b200 import _lib
 lib = _lib.load()
 d = torch.device('cuda:0')
 T = int(sys.argv[1]) if len(sys.argv) > 1 else 250
+Y_IL = int(os.environ.get('AVSI_Y_IL', '0'))          # 1: interleaved layer outputs (B % 32 == 0)
 BS = [int(x) for x in (sys.argv[2] if len(sys.argv) > 2 else '16,64,112,128,224,448,512,896').split(',')]
 for B in BS:
     g0 = torch.randn(-(-T * B // 32) * 32, 2048, device=d).half()
@@ -27,7 +28,7 @@ for B in BS:
 
     def fwd():
         _lib.check(lib.avsi_lstm_fwd(_lib.ptr(gates), _lib.ptr(whh), _lib.ptr(bias), _lib.ptr(y), _lib.ptr(cst), T, B,
-                                     _lib.stream_ptr()))
+                                     Y_IL if B % 32 == 0 else 0, _lib.stream_ptr()))
 
     def bwd():
         _lib.check(lib.avsi_lstm_bwd(_lib.ptr(gates), _lib.ptr(whhT), _lib.ptr(cst), _lib.ptr(dy), _lib.ptr(dbias),

@@ -120,6 +120,10 @@ GEMM_IL_CASES = [
     (777, 512, 2048, 0, 0, 1, 3),
     (2048, 400, 1000, 1, 2, 3, 1),        # dW: interleaved dG (MN-major) x row-major X, split-K
     (1024, 256, 2100, 1, 2, 1, 1),
+    (2048, 512, 1000, 1, 2, 3, 5),        # dW_ih of a deeper layer: interleaved dG x INTERLEAVED layer outputs (B operand)
+    (1024, 256, 2100, 1, 2, 1, 5),        # dW_hh shape (CTA-pair kernel)
+    (296, 512, 640, 1, 2, 2, 4),          # head dW: row-major dlogits x interleaved Y (lda multiple of 8)
+    (128, 64, 96, 1, 2, 1, 5),            # one-tile kernel, narrow tile
 ]
 
 
@@ -143,6 +147,8 @@ def test_gemm_f16_interleaved(M, N, K, trans, out_mode, split_k, layout):
     At, Bt = torch.from_numpy(A).to(d), torch.from_numpy(Bm).to(d)
     if layout & 1:
         At = blstm.to_il(At)
+    if layout & 4:
+        Bt = blstm.to_il(Bt)
     if out_mode == 0:
         rows = -(-M // 32) * 32 if layout & 2 else M
         C = torch.zeros((rows, N), dtype=torch.float16, device=d)
@@ -495,7 +501,8 @@ def _lstm_reference(P, Whh, bias, R):
     return Y.detach().numpy(), C.detach().numpy(), G.detach().numpy(), Pt.grad.numpy(), bt.grad.numpy()
 
 
-@pytest.mark.parametrize('T,B', [(6, 16), (9, 5), (40, 37), (12, 130), (7, 300), (2, 128), (1, 200), (5, 225), (3, 257), (1, 400)])
+@pytest.mark.parametrize('T,B', [(6, 16), (9, 5), (40, 37), (12, 130), (7, 300), (2, 128), (1, 200), (5, 225), (3, 257), (1, 400),
+                                 (4, 256), (3, 288), (5, 64)])
 def test_lstm_recurrence_fwd_bwd(T, B):
     from avsi_b200 import _lib
     lib = _lib.load()
@@ -523,9 +530,13 @@ def test_lstm_recurrence_fwd_bwd(T, B):
     tb = torch.from_numpy((bias * scale).reshape(2048).astype(np.float32)).to(d)   # prescaled like the pre-activations
     y = torch.full((T * B, 512), 3.0, dtype=torch.float16, device=d)
     cst = torch.zeros((-(-T * B // 32) * 32, 512), dtype=torch.float32, device=d)                # interleaved (4-float chunks)
-    _lib.check(lib.avsi_lstm_fwd(_lib.ptr(gates), _lib.ptr(whh), _lib.ptr(tb), _lib.ptr(y), _lib.ptr(cst), T, B,
+    # layer outputs: row-major, or interleaved like the gates when the batch is a multiple of 32 (the engine's choice)
+    y_il = 1 if B % 32 == 0 else 0
+    _lib.check(lib.avsi_lstm_fwd(_lib.ptr(gates), _lib.ptr(whh), _lib.ptr(tb), _lib.ptr(y), _lib.ptr(cst), T, B, y_il,
                                  _lib.stream_ptr()), 'lstm_fwd')
     sync()
+    if y_il:
+        y = blstm.from_il(y, T * B)
     Yr, Cr, Gr, dPr, dbr = _lstm_reference(P.astype(np.float64), Whh.astype(np.float64), bias.astype(np.float64),
                                            R.astype(np.float64))
     Yg = y.cpu().numpy().astype(np.float64).reshape(T, B, 2, 256)
