@@ -98,6 +98,37 @@ def test_library_exports_every_declared_symbol():
     assert loaded.avsi_sizeof_istft_args() == ctypes.sizeof(_lib.IstftArgs)
 
 
+def test_ctypes_signatures_match_the_header():
+    """Every prototype of include/avsi_b200.h has as many parameters, of the same kind (pointer / integer / float), as
+    its ctypes mirror in _lib.SIGNATURES: an ABI drift between the two would corrupt arguments silently."""
+    from avsi_b200 import _lib
+    header = open(os.path.join(ROOT, 'include', 'avsi_b200.h')).read()
+    header = re.sub(r'/\*.*?\*/', ' ', header, flags=re.S)
+    protos = re.findall(r'\b[A-Za-z_][A-Za-z0-9_ ]*?[ *]+(avsi_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;', header)
+    assert len(protos) == len(_lib.SIGNATURES), (len(protos), len(_lib.SIGNATURES))
+
+    def kind_c(param):
+        param = param.strip()
+        if '*' in param:
+            return 'ptr'
+        base = param.rsplit(' ', 1)[0].strip() if ' ' in param else param
+        if base in ('float', 'double'):
+            return base
+        return 'int64' if ('64' in base) else 'int32'
+
+    def kind_py(t):
+        name = getattr(t, '__name__', str(t))
+        if name in ('c_void_p', 'c_char_p') or name.startswith('LP_'):
+            return 'ptr'
+        return {'c_float': 'float', 'c_double': 'double', 'c_int': 'int32', 'c_int32': 'int32', 'c_uint32': 'int32', 'c_uint': 'int32',
+                'c_int64': 'int64', 'c_uint64': 'int64', 'c_long': 'int64', 'c_ulong': 'int64'}[name]
+    for name, params in protos:
+        params = params.strip()
+        c_kinds = [] if params in ('', 'void') else [kind_c(x) for x in params.split(',')]
+        py_kinds = [kind_py(t) for t in _lib.SIGNATURES[name][1]]
+        assert c_kinds == py_kinds, (name, c_kinds, py_kinds)
+
+
 def test_product_path_fails_loudly_without_gpu():
     import torch
     from avsi_b200 import _lib
