@@ -69,6 +69,22 @@ def feed_batch(model, batch, dropout_rate=0.0):
     return np.count_nonzero(mask[:, :, 0] == 0)                 # masked frames of the batch
 
 
+def _save(model, path, config):
+    """saver.save(sess, path) (training.py:267,335).  `checkpoint_format` in the config file picks the container: 'npz'
+    (default), 'tf' = TensorFlow's own tensor bundle (`<path>.index` + `.data-00000-of-00001`, loadable by the
+    reference's saver.restore), or 'both'."""
+    fmt = str(config.get('checkpoint_format', 'npz')).lower()
+    if fmt not in ('npz', 'tf', 'both'):
+        print('checkpoint_format must be "npz", "tf" or "both". Closing...')
+        sys.exit(1)
+    out = path
+    if fmt in ('npz', 'both'):
+        out = checkpoint.save(model, path)
+    if fmt in ('tf', 'both'):
+        out = checkpoint.save(model, path, fmt='tf')
+    return out
+
+
 def _losses(model, want_per):
     loss, hole = float(model.loss), float(model.loss_hole)
     ctc = float(model.ctc_loss) if model.MTL else 0.0
@@ -187,7 +203,7 @@ def train(config_file, max_steps=None):
                 print('Step[{:7d}] Loss[{:3.5f}|{:3.5f}|{:3.5f}] PER[{:.5f}] LR[{:.6f}] Epoch training time[{:.2f}]'
                       .format(tot_step, tr[0], tr[1], tr[2], tr[3], lr, time() - epoch_start_time))
             if rank == 0 and n_step % 1000 == 0:
-                print('Model checkpoint saved in file %s' % checkpoint.save(model, os.path.join(checkpoints_dir, 'ckpt')))
+                print('Model checkpoint saved in file %s' % _save(model, os.path.join(checkpoints_dir, 'ckpt'), config))
             if max_steps is not None and tot_step >= max_steps:
                 stop = True
                 break
@@ -218,7 +234,7 @@ def train(config_file, max_steps=None):
                   .format(va[1], va[3], best_val_loss, best_val_checkpoint[0], best_val_checkpoint[1]))
         if best_val_checkpoint == (0, 0) or va[1] < best_val_loss:
             if rank == 0:
-                print('Model saved in file %s' % checkpoint.save(model, os.path.join(checkpoints_dir, 'sinet')))
+                print('Model saved in file %s' % _save(model, os.path.join(checkpoints_dir, 'sinet'), config))
             best_val_checkpoint, best_val_loss, cneg_epochs = (epoch_counter, tot_step), va[1], 0
         else:
             cneg_epochs += 1
