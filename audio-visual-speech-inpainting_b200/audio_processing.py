@@ -7,7 +7,6 @@ the reference's.  ``fused_features`` is the one-launch path the models use; the 
 functions exist for drop-in use (masking.py, audio_feat_preprocessing.py) and run the same
 kernel with different outputs enabled.
 """
-import math
 
 import numpy as np
 import torch

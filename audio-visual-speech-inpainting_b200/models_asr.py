@@ -5,7 +5,6 @@ apply_mask) -> log-mel-80 -> normalisation -> (concat video) -> stacked BLSTM ->
 Adam / SGD / Momentum.  Every stage reuses the kernels of the inpainting path: the fused front end's `fbanks`
 variant, avsi_features_to_x0, the projection GEMMs, the recurrence kernels, the CTC kernel.  The beam-search
 decoder of models_asr.py:132-135 runs on the host (avsi_ctc_beam_search_host), off the training step."""
-import numpy as np
 import torch
 
 from . import _lib

@@ -13,7 +13,6 @@ import math
 import os
 import time
 
-import numpy as np
 import torch
 
 
