@@ -9,23 +9,67 @@ reference's order (dataset_reader.py:77-79):
 
 Exhaustion raises StopIteration where the reference's loop catches tf.errors.OutOfRangeError.  Data parallel runs
 pass `rank` / `world` so that each process reads files[rank::world] (SURVEY.md 8e)."""
+import os
 import random
 
 import numpy as np
 
 from . import parallel
-from .tfrecord_io import parse_sequence_example, read_records
+from .tfrecord_io import parse_av_batch, parse_av_sample, parse_sequence_example, read_records
+
+
+def _native_available():
+    from . import tfrecord_io
+    return tfrecord_io._native() is not None
 
 
 class _Dataset(object):
-    def __init__(self, files, parse, shuffle, buffer_size, seed):
+    def __init__(self, files, parse, shuffle, buffer_size, seed, workers=1):
         self.files, self.parse, self.shuffle, self.buffer_size, self.seed = list(files), parse, shuffle, buffer_size, seed
+        self.workers = workers
 
-    def samples(self):
-        def raw():
+    def raw_records(self):
+        """The record payloads in the order samples() parses them (file order, or through the shuffle buffer)."""
+        def records():
             for f in self.files:
                 for rec in read_records(f):
+                    yield rec
+        if not self.shuffle:
+            for r in records():
+                yield r
+            return
+        rng = random.Random(self.seed)
+        buf = []
+        for r in records():
+            buf.append(r)
+            if len(buf) >= self.buffer_size:
+                yield buf.pop(rng.randrange(len(buf)))
+        while buf:
+            yield buf.pop(rng.randrange(len(buf)))
+
+    def samples(self):
+        def records():
+            for f in self.files:
+                for rec in read_records(f):
+                    yield rec
+
+        def raw():
+            # records are parsed by a small thread pool, a bounded window ahead and in order (the native parser
+            # releases the GIL): the consumer sees the same sequence as a serial loop
+            if self.workers <= 1:
+                for rec in records():
                     yield self.parse(rec)
+                return
+            from collections import deque
+            from concurrent.futures import ThreadPoolExecutor
+            with ThreadPoolExecutor(max_workers=self.workers) as pool:
+                window = deque()
+                for rec in records():
+                    window.append(pool.submit(self.parse, rec))
+                    if len(window) >= 4 * self.workers:
+                        yield window.popleft().result()
+                while window:
+                    yield window.popleft().result()
         if not self.shuffle:
             for s in raw():
                 yield s
@@ -44,13 +88,21 @@ class DataManager(object):
     """Utilities to read TFRecords"""
 
     def __init__(self, num_audio_samples=48000, audio_feat_size=257, video_feat_size=136, buffer_size=1000, mode='fixed',
-                 rank=0, world=1, **unused):
+                 rank=0, world=1, num_parallel_calls=None, **unused):
         if mode != 'fixed':
             raise NotImplementedError("only the 'fixed' TFRecord mode works in the reference (SURVEY.md 2.4)")
         self.num_audio_samples, self.audio_feat_size, self.video_feat_size = num_audio_samples, audio_feat_size, video_feat_size
         self.buffer_size, self.mode, self.rank, self.world = buffer_size, mode, rank, world
+        # parser threads (tf.data's num_parallel_calls of dataset_reader.py:55); default: up to 8 host cores
+        self.workers = num_parallel_calls if num_parallel_calls else max(1, min(8, os.cpu_count() or 1))
 
     def read_data_format_fixed(self, sample):
+        fast = parse_av_sample(sample, self.num_audio_samples, self.audio_feat_size, self.video_feat_size)
+        if fast is not None:
+            seq_len, lab_len, wav, path, labels, video, mask = fast
+            if wav.shape[0] != self.num_audio_samples:
+                raise ValueError('target_audio_wav has %d samples, expected %d' % (wav.shape[0], self.num_audio_samples))
+            return (np.int32(seq_len), np.int32(lab_len), wav.astype(np.int32), path, labels, video, mask)
         ctx, seq = parse_sequence_example(sample)
         wav = np.asarray(ctx['target_audio_wav'], np.float32)
         if wav.shape[0] != self.num_audio_samples:
@@ -62,9 +114,42 @@ class DataManager(object):
 
     def get_dataset(self, file_list, shuffle=True, seed=None):
         files = parallel.shard_list(file_list, self.rank, self.world) if self.world > 1 else list(file_list)
-        return _Dataset(files, self.read_data_format_fixed, shuffle, self.buffer_size, seed)
+        return _Dataset(files, self.read_data_format_fixed, shuffle, self.buffer_size, seed, self.workers)
 
     def get_iterator(self, dataset, batch_size=16, n_epochs=None, drop_remainder=False):
+        def fast_batches():
+            # whole batches parsed natively into their arrays by a thread pool, one batch ahead of the consumer
+            import itertools
+            import queue
+            import threading
+            from concurrent.futures import ThreadPoolExecutor
+            q = queue.Queue(maxsize=2)
+
+            def produce():
+                try:
+                    with ThreadPoolExecutor(max_workers=self.workers) as pool:
+                        epoch = 0
+                        while n_epochs is None or epoch < n_epochs:
+                            recs = dataset.raw_records()
+                            while True:
+                                chunk = list(itertools.islice(recs, batch_size))
+                                if not chunk or (drop_remainder and len(chunk) < batch_size):
+                                    break
+                                q.put(parse_av_batch(chunk, self.num_audio_samples, self.audio_feat_size,
+                                                     self.video_feat_size, pool))
+                            epoch += 1
+                    q.put(None)
+                except BaseException as e:                    # noqa: BLE001 -- re-raised in the consumer
+                    q.put(e)
+            threading.Thread(target=produce, daemon=True).start()
+            while True:
+                item = q.get()
+                if item is None:
+                    return
+                if isinstance(item, BaseException):
+                    raise item
+                yield item
+
         def batches():
             epoch = 0
             while n_epochs is None or epoch < n_epochs:
@@ -77,7 +162,8 @@ class DataManager(object):
                 if cur and not drop_remainder:
                     yield _collate(cur)
                 epoch += 1
-        return dataset, batches()
+        native = parse_av_sample is not None and _native_available()
+        return dataset, (fast_batches() if native else batches())
 
 
 def _collate(samples):

@@ -17,6 +17,7 @@ import struct
 import numpy as np
 
 _CRC_TABLE = None
+_NATIVE = None
 
 
 def _crc_table():
@@ -33,7 +34,24 @@ def _crc_table():
     return _CRC_TABLE
 
 
+def _native():
+    """The library's host routines (CRC-32C, SequenceExample parser), or None when it cannot be loaded."""
+    global _NATIVE
+    if _NATIVE is None:
+        try:
+            from . import _lib
+            _NATIVE = _lib.load()
+        except Exception:                                  # noqa: BLE001 -- the pure-Python code below is complete
+            _NATIVE = False
+    return _NATIVE or None
+
+
 def crc32c(data):
+    if len(data) >= 1024:
+        lib = _native()
+        if lib is not None:
+            raw = bytes(data) if not isinstance(data, bytes) else data
+            return int(lib.avsi_crc32c_host(raw, len(raw), 0))
     tab = _crc_table()
     c = 0xFFFFFFFF
     for b in data:
@@ -211,3 +229,73 @@ def serialize_sample_fixed(seq_len, lab_len, target_audio_wav, video_features, m
         {'mask': [np.asarray(r, np.float32) for r in mask],
          'video_features': [np.asarray(r, np.float32) for r in video_features],
          'labels': [np.array([l], np.float32) for l in labels]})
+
+
+def parse_av_sample(data, num_audio_samples=48000, audio_feat_size=257, video_feat_size=136, max_frames=None,
+                    max_labels=64):
+    """One record of the reference's TFRecords -> (seq_len, lab_len, wav f32 [N], sample_path bytes, labels f32 [L],
+    video f32 [T, V], mask f32 [T, F]) through the library's host parser (avsi_parse_av_sample_host); None when the
+    library is unavailable (callers fall back to parse_sequence_example)."""
+    import ctypes
+    lib = _native()
+    if lib is None:
+        return None
+    if max_frames is None:
+        max_frames = max(1, len(data) // (4 * (audio_feat_size + 1)))      # a mask row costs > 4 F bytes
+    wav = np.empty(num_audio_samples, np.float32)
+    mask = np.empty(max_frames * audio_feat_size, np.float32)
+    video = np.empty(max_frames * max(video_feat_size, 1), np.float32)
+    labels = np.empty(max_labels, np.float32)
+    path = ctypes.create_string_buffer(512)
+    meta = np.zeros(9, np.int64)
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    raw = bytes(data) if not isinstance(data, bytes) else data
+    rc = lib.avsi_parse_av_sample_host(raw, len(raw), vp(wav), wav.size, vp(mask), mask.size, vp(video), video.size,
+                                       vp(labels), labels.size, path, 512, vp(meta))
+    if rc != 0:
+        raise ValueError('malformed TFRecord payload: %s' % lib.avsi_last_error().decode(errors='replace'))
+    seq_len, lab_len, n_wav, mr, mc, vr, vc, nl, pl = (int(x) for x in meta)
+    return (seq_len, lab_len, wav[:n_wav], path.raw[:min(pl, 512)], labels[:nl].copy(),
+            video[:vr * vc].reshape(vr, vc) if vr else np.zeros((0, video_feat_size), np.float32),
+            mask[:mr * mc].reshape(mr, mc) if mr else np.zeros((0, audio_feat_size), np.float32))
+
+
+def parse_av_batch(records, num_audio_samples=48000, audio_feat_size=257, video_feat_size=136, pool=None):
+    """A list of records -> the DataManager's 7-tuple, every record parsed by the library straight into its row of the
+    batch arrays (no per-sample arrays, no stacking); `pool` (a ThreadPoolExecutor) spreads the rows over host cores,
+    the C call runs without the GIL.  None when the library is unavailable.  All records must share T and the padded
+    label count (true of the reference's 'fixed' TFRecords)."""
+    import ctypes
+    lib = _native()
+    if lib is None:
+        return None
+    first = parse_av_sample(records[0], num_audio_samples, audio_feat_size, video_feat_size)
+    T, L = first[6].shape[0], first[4].shape[0]
+    V = first[5].shape[1] if first[5].size else video_feat_size
+    B = len(records)
+    wav = np.empty((B, num_audio_samples), np.float32)
+    mask = np.empty((B, T, audio_feat_size), np.float32)
+    video = np.empty((B, T, V), np.float32)
+    labels = np.zeros((B, max(L, 1)), np.float32)
+    meta = np.zeros((B, 9), np.int64)
+    paths = [ctypes.create_string_buffer(512) for _ in range(B)]
+    vp = lambda a: ctypes.c_void_p(a.ctypes.data)
+
+    def one(i):
+        raw = records[i] if isinstance(records[i], bytes) else bytes(records[i])
+        rc = lib.avsi_parse_av_sample_host(raw, len(raw), vp(wav[i]), wav.shape[1], vp(mask[i]), mask[i].size, vp(video[i]),
+                                           video[i].size, vp(labels[i]), labels.shape[1], paths[i], 512, vp(meta[i]))
+        if rc != 0:
+            raise ValueError('malformed TFRecord payload in record %d of the batch' % i)
+        m = meta[i]
+        if m[2] != num_audio_samples:
+            raise ValueError('target_audio_wav has %d samples, expected %d' % (m[2], num_audio_samples))
+        if m[3] != T or m[4] != audio_feat_size or m[5] != T or m[6] != V or m[7] != L:
+            raise ValueError('records of one batch differ in shape (T, F, V, labels): %s' % (m[3:8].tolist(),))
+    if pool is not None and B > 1:
+        list(pool.map(one, range(B)))
+    else:
+        for i in range(B):
+            one(i)
+    return (meta[:, 0].astype(np.int32), meta[:, 1].astype(np.int32), wav.astype(np.int32),
+            [paths[i].raw[:min(int(meta[i, 8]), 512)] for i in range(B)], labels[:, :L], video, mask)

@@ -235,6 +235,16 @@ int avsi_ctc_beam_search_host(const float* logits, int T, int B, int ldl, int co
                               int beam_width, int merge_repeated, int max_out, int* out, int* out_len,
                               float* log_prob, int n_threads);
 
+/* One serialized tf.train.SequenceExample of the reference's TFRecords (tfrecord_utils.py:19-41, read by
+ * dataset_reader.py:62-79) parsed on the HOST straight into caller buffers (capacities in floats):
+ *   wav <- context target_audio_wav; mask / video <- feature lists mask / video_features, row after row;
+ *   labels <- feature list labels (one float per row); path <- context sample_path (not NUL-terminated).
+ *   meta[9] = {sequence_length, labels_length, n_wav, mask_rows, mask_cols, video_rows, video_cols, n_labels, path_len}.
+ * Returns non-zero on malformed input, ragged rows or a buffer too small.  Thread safe. */
+int avsi_parse_av_sample_host(const void* rec, uint64_t len, float* wav, int64_t wav_cap, float* mask, int64_t mask_cap,
+                              float* video, int64_t video_cap, float* labels, int64_t labels_cap, char* path,
+                              int path_cap, int64_t* meta);
+
 /* CRC-32C (Castagnoli) of n bytes of HOST memory, continuing from `crc` (0 to start): the checksum of TFRecord
  * frames (tfrecord_utils.py:19-41 via tf.python_io.TFRecordWriter) and of tf.train.Saver tensor bundles
  * (training.py:114,267,335).  Known answer: "123456789" -> 0xE3069283. */
