@@ -94,6 +94,12 @@ def _losses(model, want_per):
 
 def train(config_file, max_steps=None):
     """Train the speech inpainting model."""
+    return _train(config_file, max_steps, build_model, feed_batch, _losses)
+
+
+def _train(config_file, max_steps, build_model, feed_batch, _losses):
+    """The training job of training.py / training_ctc.py; `training_asr.train` runs it with the phone-recognition model's
+    hooks (model construction, feed, the monitored loss tuple whose entry 1 selects the best validation checkpoint)."""
     import torch
     import torch.distributed as dist
     config = check_trainconfiguration(load_configfile(config_file))

@@ -467,3 +467,37 @@ def test_checkpoint_round_trip_through_tf_bundle(tmp_path):
     other.feed(**{k: v for k, v in model._fed.items()})
     other.train_op()
     assert torch.allclose(other.engine.theta, model.engine.theta, rtol=0, atol=1e-5)
+
+
+def test_train_asr_job(tmp_path, capsys):
+    """training_asr.train(config_file) (training_asr.py:23): the shared job loop with the phone-recognition model --
+    log-mel statistics as normalisation files, CTC loss / PER as monitored figures, checkpoint under the `asr/<model>` scope."""
+    import os
+    from avsi_b200 import checkpoint, training_asr
+    root = str(tmp_path / 'data')
+    os.makedirs(root)
+    audio_len = 11520                                  # T = 60 >= 2 * 24 + 1 label states
+    _write_dataset(root, 6, 3, audio_len, seed=70)
+    np.save(os.path.join(root, 'fb_mean.npy'), np.full(80, 8.0))
+    np.save(os.path.join(root, 'fb_std.npy'), np.full(80, 2.5))
+    exp = str(tmp_path / 'exp' / 'asr1')
+    cfg = str(tmp_path / 'blstm_asr.config')
+    with open(cfg, 'w') as f:
+        f.write('root_folder = %s\nexp_folder = %s\nmodel = a-blstm\naudio_feat_dim = 257\nvideo_feat_dim = 136\n'
+                'audio_len = %d\nbatch_size = 3\nnet_dim = [250,250]\nstarter_learning_rate = 0.001\nmax_n_epochs = 2\n'
+                'n_earlystop_epochs = 5\nlr_decay = 1.0\noptimizer_type = adam\nl2 = 0.0\ndropout_rate = 0.0\n'
+                'audio_feat_mean = %s\naudio_feat_std = %s\n' % (root, exp, audio_len, os.path.join(root, 'fb_mean.npy'),
+                                                                os.path.join(root, 'fb_std.npy')))
+    model = training_asr.train(cfg)
+    out = capsys.readouterr().out
+    assert '+---- Done training: epoch limit reached ----+' in out and 'Model saved in file' in out
+    rows = [l for l in open(os.path.join(exp, 'training_log.txt')).read().splitlines() if l[:1].isdigit()]
+    assert len(rows) == 2
+    ctc = [float(r.split('\t')[2].split('|')[1]) for r in rows]
+    assert np.isfinite(ctc).all() and ctc[1] < ctc[0]                        # the CTC loss went down
+    ck = checkpoint.load(os.path.join(exp, 'netmodel', 'sinet'))
+    pre = 'asr/a-blstm/cudnn_lstm/stack_bidirectional_rnn/cell_0/bidirectional_rnn/fw/cudnn_compatible_lstm_cell/'
+    assert ck[pre + 'kernel'].shape == (80 + 250, 1000)
+    # `sinet` is the best-validation checkpoint: written after epoch 1 (step 2) and again after epoch 2 only if it improved
+    assert ck['asr/a-blstm/logits/weights'].shape == (500, 34) and int(ck['asr/a-blstm/Variable']) in (2, 4)
+    assert model.per.shape == (3,)
