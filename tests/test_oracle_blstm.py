@@ -111,3 +111,25 @@ def test_adam_tf_epsilon_hat_form():
     t.grad = torch.tensor(g)
     opt.step()
     assert np.allclose(th1, t.detach().numpy(), atol=1e-7)      # same up to where epsilon enters
+
+
+def test_mtl_gradients_match_finite_differences():
+    """models.py:1873-1963 restated (hole-normalised L1 + weighted mean CTC): central differences on both heads and a cell."""
+    rng = np.random.default_rng(6)
+    B, T, I, H, F, C = 2, 8, 5, 3, 4, 5
+    params = blstm.init_params(I, H, 2, out_dim=F, n_classes=C, seed=11, bias_scale=0.1)
+    mask = np.ones((B, T, F))
+    mask[:, 2:5] = 0
+    inputs = dict(net_in=rng.standard_normal((B, T, I)), target=rng.standard_normal((B, T, F)), mask=mask,
+                  seq_len=np.array([8, 7]), labels=np.array([[0, 1, 1], [3, 2, 0]]), lab_len=np.array([3, 2]))
+    outs, grads = blstm.loss_and_grads('mtl', inputs, params, 2, ctc_weight=0.3)
+    assert abs(outs['loss'] - (outs['loss_hole'] + 0.3 * outs['ctc_loss'])) < 1e-12
+    eps = 1e-6
+    for name, idx in (('inpainting/weights', (1, 2)), ('asr/weights', (4, 3)), ('asr/biases', (1,)),
+                      (blstm.cell_prefix(0, 'fw') + '/kernel', (6, 10))):
+        p2 = {k: v.copy() for k, v in params.items()}
+        p2[name][idx] += eps
+        lp = blstm.loss_and_grads('mtl', inputs, p2, 2, ctc_weight=0.3)[0]['loss']
+        p2[name][idx] -= 2 * eps
+        lm = blstm.loss_and_grads('mtl', inputs, p2, 2, ctc_weight=0.3)[0]['loss']
+        assert abs((lp - lm) / (2 * eps) - grads[name][idx]) < 1e-7, name

@@ -99,3 +99,25 @@ def test_masked_crc_known_answer():
     big = bytes(range(256)) * 64                                           # takes the library routine when it is built
     from avsi_b200 import tfrecord_io
     assert tf_bundle.crc32c(big) == tfrecord_io.crc32c(big)
+
+
+def test_training_driver_checkpoint_formats(tmp_path):
+    """training._save honours `checkpoint_format` (npz | tf | both); both containers hold the same variables."""
+    from avsi_b200 import checkpoint, training
+
+    class FakeModel(object):
+        optimizer_choice = 'sgd'                               # no Adam slots to export
+        all_vars = {'av-blstm/logits/weights': np.arange(12, dtype=np.float32).reshape(3, 4),
+                    'av-blstm/Variable': np.asarray(7, np.int32)}
+    for fmt, files in (('npz', ['ck.npz']), ('tf', ['ck.index', 'ck.data-00000-of-00001']),
+                       ('both', ['ck.npz', 'ck.index', 'ck.data-00000-of-00001'])):
+        d = tmp_path / fmt
+        d.mkdir()
+        training._save(FakeModel(), str(d / 'ck'), {'checkpoint_format': fmt})
+        assert sorted(os.listdir(str(d))) == sorted(files + (['checkpoint'] if fmt != 'npz' else []))
+        got = checkpoint.load(str(d / 'ck'))
+        assert set(got) == set(FakeModel.all_vars)
+        for k, v in FakeModel.all_vars.items():
+            assert np.array_equal(got[k], v) and got[k].dtype == v.dtype
+    with pytest.raises(SystemExit):
+        training._save(FakeModel(), str(tmp_path / 'x'), {'checkpoint_format': 'hdf5'})
