@@ -74,15 +74,21 @@ SIGNATURES = {
     'avsi_lstm_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     'avsi_masked_l1': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
-    'avsi_mtl_scales': (c_int, [c_void_p, c_int, c_float, c_void_p, c_void_p]),
+    'avsi_mtl_scales': (c_int, [c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p]),
     'avsi_colsum_f16': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'avsi_ctc_workspace_bytes': (c_int64, [c_int, c_int, c_int]),
     'avsi_ctc_loss': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int,
                               c_float, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     'avsi_adam_tf': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double, c_double, c_double,
-                             c_int, c_float, c_void_p, c_float, c_void_p]),
+                             c_int, c_float, c_void_p, c_float, c_void_p, c_void_p]),
     'avsi_sgd_momentum': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double, c_float, c_void_p, c_float,
-                                  c_void_p]),
+                                  c_void_p, c_void_p]),
+    'avsi_grad_guard_init': (c_int, [c_void_p, c_void_p]),
+    'avsi_grad_guard_check': (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    'avsi_grad_guard_update': (c_int, [c_void_p, c_int, c_void_p]),
+    'avsi_reload_env': (None, []),
+    'avsi_debug_lstm4_timing': (c_int, [c_void_p]),
+    'avsi_debug_lstm4_bwd_timing': (c_int, [c_void_p]),
     'avsi_cast_to_f32': (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p]),
     'avsi_cast_weights': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     'avsi_gate_bias_prescale': (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
@@ -109,6 +115,16 @@ def load():
         raise AvsiError('ctypes struct mirrors do not match include/avsi_b200.h (rebuild the library)')
     _lib = lib
     return lib
+
+
+def set_env(**kw):
+    """Set / clear (value None) AVSI_* switches of the library inside this process and make it re-read them."""
+    for k, v in kw.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = str(v)
+    load().avsi_reload_env()
 
 
 def check(rc, what=''):

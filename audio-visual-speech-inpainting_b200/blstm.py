@@ -31,6 +31,11 @@ def _p(t):
     return _lib.ptr(t)
 
 
+def ctypes_ptr(addr):
+    import ctypes
+    return ctypes.c_void_p(int(addr))
+
+
 A_IL, C_IL, B_IL = 1, 2, 4     # avsi_gemm_f16 layout bits: A operand / f16 output / B operand stored interleaved (include/avsi_b200.h)
 
 
@@ -77,6 +82,10 @@ class BLSTMEngine(object):
         self.adam_m = torch.zeros(n, dtype=torch.float32, device=self.device)
         self.adam_v = torch.zeros(n, dtype=torch.float32, device=self.device)
         self.step_count = 0
+        # overflow guard of the fp16 gradient path (include/avsi_b200.h: avsi_grad_guard_*): 8 device words
+        self.guard = torch.zeros(8, dtype=torch.int32, device=self.device)
+        _lib.check(_lib.load().avsi_grad_guard_init(_p(self.guard), _lib.stream_ptr()), 'avsi_grad_guard_init')
+        self.guard_growth_interval = 2000
         # fp16 operand copies
         self.half = {}
         for l in range(L.n_layers):
@@ -256,6 +265,25 @@ class BLSTMEngine(object):
                 cur = nxt
         return g
 
+    # ---- overflow guard ------------------------------------------------------------------------
+    @property
+    def guard_scale_ptr(self):
+        """Device address of the guard's dynamic scale s (a float32): the grad_scale_dev of the loss kernels."""
+        return ctypes_ptr(self.guard.data_ptr() + 16)
+
+    def guard_state(self):
+        """(steps skipped, current dynamic scale) -- synchronises; for logging and tests."""
+        g = self.guard.cpu()
+        return int(g[1]), float(g[4:5].view(torch.float32)[0])
+
+    def _guard_check(self):
+        _lib.check(_lib.load().avsi_grad_guard_check(_p(self.grad), self.layout.n_params_padded, _p(self.guard),
+                                                     _lib.stream_ptr()), 'avsi_grad_guard_check')
+
+    def _guard_update(self):
+        _lib.check(_lib.load().avsi_grad_guard_update(_p(self.guard), int(self.guard_growth_interval), _lib.stream_ptr()),
+                   'avsi_grad_guard_update')
+
     def sgd_step(self, lr, momentum=None, grad_unscale=1.0, unscale_dev=None, l2=0.0):
         """tf.train.GradientDescentOptimizer / MomentumOptimizer(0.9) update (models.py:169-173)."""
         lib = _lib.load()
@@ -267,8 +295,10 @@ class BLSTMEngine(object):
                 self.momentum_acc = torch.zeros(n, dtype=torch.float32, device=self.device)
             acc = self.momentum_acc
         with _lib.span('sgd'):
+            self._guard_check()
             _lib.check(lib.avsi_sgd_momentum(_p(self.theta), _p(self.grad), _p(acc), n, lr, momentum or 0.0, grad_unscale,
-                                             _p(unscale_dev), l2, _lib.stream_ptr()), 'avsi_sgd_momentum')
+                                             _p(unscale_dev), l2, _p(self.guard), _lib.stream_ptr()), 'avsi_sgd_momentum')
+            self._guard_update()
             self.refresh_half()
 
     # ---- update -------------------------------------------------------------------------------
@@ -277,7 +307,9 @@ class BLSTMEngine(object):
         self.step_count += 1
         n = self.layout.n_params_padded
         with _lib.span('adam'):
+            self._guard_check()
             _lib.check(lib.avsi_adam_tf(_p(self.theta), _p(self.grad), _p(self.adam_m), _p(self.adam_v), n, lr, b1, b2,
-                                        eps, self.step_count, grad_unscale, _p(unscale_dev), l2, _lib.stream_ptr()),
-                       'avsi_adam_tf')
+                                        eps, self.step_count, grad_unscale, _p(unscale_dev), l2, _p(self.guard),
+                                        _lib.stream_ptr()), 'avsi_adam_tf')
+            self._guard_update()
             self.refresh_half()

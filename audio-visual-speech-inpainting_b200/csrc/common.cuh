@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <atomic>
 
 #include "../../include/avsi_b200.h"
@@ -13,6 +14,24 @@ namespace avsi {
 
 extern thread_local char g_last_error[512];
 extern std::atomic<long long> g_launch_count;
+extern std::atomic<int> g_env_gen;      // bumped by avsi_reload_env(): the cached AVSI_* tuning switches are re-read
+
+// `static` cache of an integer derived from the environment, re-evaluated after avsi_reload_env()
+#define AVSI_ENV_CACHE(var, expr)                        \
+  static int var##_gen_ = -1;                            \
+  static int var = 0;                                    \
+  if (var##_gen_ != avsi::g_env_gen.load()) {            \
+    var = (expr);                                        \
+    var##_gen_ = avsi::g_env_gen.load();                 \
+  }
+inline int env_is(const char* name, const char* value) {
+  const char* e = getenv(name);
+  return (e && !strcmp(e, value)) ? 1 : 0;
+}
+inline int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
 
 inline int set_error(int code, const char* fmt, const char* a = "", const char* b = "") {
   snprintf(g_last_error, sizeof(g_last_error), fmt, a, b);

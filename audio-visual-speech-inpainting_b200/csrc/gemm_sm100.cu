@@ -639,11 +639,7 @@ extern "C" int avsi_gemm_f16(const uint16_t* A, int lda, const uint16_t* B, int 
   GemmParams p{C, bias, ldc, M, N, K, trans, out_mode, split_k, layout & 1, (layout >> 1) & 1, (layout >> 2) & 1};
   cudaStream_t st = (cudaStream_t)stream;
 
-  static int debug_simt = -1;
-  if (debug_simt < 0) {
-    const char* e = getenv("AVSI_GEMM_DEBUG_SIMT");
-    debug_simt = (e && e[0] == '1') ? 1 : 0;
-  }
+  AVSI_ENV_CACHE(debug_simt, env_is("AVSI_GEMM_DEBUG_SIMT", "1"));
   if (debug_simt && layout == 0) {
     GemmParams q = p;
     q.split_k = 1;
@@ -656,17 +652,9 @@ extern "C" int avsi_gemm_f16(const uint16_t* A, int lda, const uint16_t* B, int 
   // tile width: wide tiles for wide outputs, narrow ones so that small-N problems still fill the chip
   // tile width: 128 (3 stages, 2 CTAs/SM) by default; 256 (4 stages, 1 CTA/SM) for long-K problems
   // where the main loop dominates; 64 for narrow outputs.  AVSI_GEMM_BN overrides (tuning only).
-  static int bn_env = -1;
-  if (bn_env < 0) {
-    const char* e = getenv("AVSI_GEMM_BN");
-    bn_env = e ? atoi(e) : 0;
-  }
+  AVSI_ENV_CACHE(bn_env, env_int("AVSI_GEMM_BN", 0));
   // large problems: persistent CTA-pair kernel (256 x 256 tiles, cta_group::2).  AVSI_GEMM_2SM=0 disables it.
-  static int use_2sm = -1;
-  if (use_2sm < 0) {
-    const char* e = getenv("AVSI_GEMM_2SM");
-    use_2sm = (e && e[0] == '0') ? 0 : (e && e[0] == '2') ? 2 : 1;
-  }
+  AVSI_ENV_CACHE(use_2sm, env_is("AVSI_GEMM_2SM", "0") ? 0 : (env_is("AVSI_GEMM_2SM", "2") ? 2 : 1));
   if (use_2sm && N >= 256 && (use_2sm == 2 || ((N + 255) / 256) * 256 * 3 <= N * 4) && (long long)M * N * K >= (1LL << 29)) {
     // split-K only as far as needed to give every SM pair a work item
     const int m_t = (M + 255) / 256, n_t = (N + 255) / 256, kbt = (K + GEMM_BK - 1) / GEMM_BK;

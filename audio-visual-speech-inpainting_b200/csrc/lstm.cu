@@ -447,11 +447,7 @@ int launch_lstm4_fwd(uint16_t* gates, const uint16_t* whh, const float* bias, ui
 // returns 0 = mma.sync register-resident kernel (small batches: 16-row tiles, shortest step), 2 = tcgen05 4-CTA
 // kernel (lstm4.cu).  AVSI_LSTM_FWD=mma|l4 overrides (A/B measurements and tests).
 static int fwd_kernel_choice(int B) {
-  static int mode = -1;
-  if (mode < 0) {
-    const char* e = getenv("AVSI_LSTM_FWD");
-    mode = (e && !strcmp(e, "mma")) ? 1 : ((e && !strcmp(e, "l4")) ? 3 : 0);
-  }
+  AVSI_ENV_CACHE(mode, env_is("AVSI_LSTM_FWD", "mma") ? 1 : (env_is("AVSI_LSTM_FWD", "l4") ? 3 : 0));
   if (mode == 1) return 0;
   if (mode == 3) return 2;
   return pick_bt(B) > 32 ? 2 : 0;      // measured crossover: 16/32-row mma.sync tiles win while they fit one wave (B <= 224)
@@ -486,11 +482,8 @@ extern "C" int avsi_lstm_bwd(uint16_t* gates, const uint16_t* whhT, const float*
   AVSI_REQUIRE(T > 0 && B > 0, "T,B > 0");
   const int bt = pick_bt(B);
   cudaStream_t st = (cudaStream_t)stream;
-  static int bmode = -1;               // AVSI_LSTM_BWD=mma|l4 overrides (A/B measurements only)
-  if (bmode < 0) {
-    const char* e = getenv("AVSI_LSTM_BWD");
-    bmode = (e && !strcmp(e, "mma")) ? 1 : ((e && !strcmp(e, "l4")) ? 2 : 0);
-  }
+  // AVSI_LSTM_BWD=mma|l4 overrides (A/B measurements and the parity tests of the tcgen05 path at small batches)
+  AVSI_ENV_CACHE(bmode, env_is("AVSI_LSTM_BWD", "mma") ? 1 : (env_is("AVSI_LSTM_BWD", "l4") ? 2 : 0));
   if (bmode == 2 || (bmode == 0 && bt > 32)) return launch_lstm4_bwd(gates, whhT, cst, dy, dbias, T, B, st);
   if (bt == 16) return launch_bwd<16>(gates, whhT, cst, dy, dbias, T, B, st);
   if (bt == 32) return launch_bwd<32>(gates, whhT, cst, dy, dbias, T, B, st);

@@ -327,17 +327,8 @@ lstm4_fwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whh,
 int launch_lstm4_fwd(uint16_t* gates, const uint16_t* whh, const float* bias, uint16_t* y, float* cst, int T, int B,
                      int y_il, cudaStream_t st) {
   // AVSI_LSTM_ACT=exact: ex2/rcp activations; AVSI_L4_TIMING=1: in-kernel phase timers (profiles/bench_lstm.py)
-  static int mode = -1;
-  if (mode < 0) {
-    const char* e = getenv("AVSI_LSTM_ACT");
-    const char* t = getenv("AVSI_L4_TIMING");
-    mode = ((e && !strcmp(e, "exact")) ? 1 : 0) | ((t && t[0] == '1') ? 2 : 0);
-  }
-  static int pf = -1;                                // AVSI_L4_PREFETCH=0: no L2 prefetch of the next step (A/B runs)
-  if (pf < 0) {
-    const char* e = getenv("AVSI_L4_PREFETCH");
-    pf = (e && e[0] == '0') ? 0 : 1;
-  }
+  AVSI_ENV_CACHE(mode, env_is("AVSI_LSTM_ACT", "exact") | (env_is("AVSI_L4_TIMING", "1") << 1));
+  AVSI_ENV_CACHE(pf, env_is("AVSI_L4_PREFETCH", "0") ? 0 : 1);   // AVSI_L4_PREFETCH=0: no L2 prefetch of the next step (A/B runs)
   const int smem = (int)sizeof(Lstm4Smem) + 128;
   const int grid = 2 * ((B + L4_BT - 1) / L4_BT) * L4_CL;
   static bool attr_done[4] = {false, false, false, false};

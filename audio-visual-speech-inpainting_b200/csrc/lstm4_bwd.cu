@@ -409,11 +409,7 @@ lstm4_bwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whhT
 
 int launch_lstm4_bwd(uint16_t* gates, const uint16_t* whhT, const float* cst, const uint16_t* dy, float* dbias, int T,
                      int B, cudaStream_t st) {
-  static int timing = -1;               // AVSI_B4_TIMING=1: in-kernel phase timers (profiles/bench_lstm.py)
-  if (timing < 0) {
-    const char* t = getenv("AVSI_B4_TIMING");
-    timing = (t && t[0] == '1') ? 1 : 0;
-  }
+  AVSI_ENV_CACHE(timing, env_is("AVSI_B4_TIMING", "1"));   // in-kernel phase timers (profiles/bench_lstm.py)
   const int smem = (int)sizeof(Lstm4BwdSmem) + 128;
   static bool attr_done = false;
   if (!attr_done) {

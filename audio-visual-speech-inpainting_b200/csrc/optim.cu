@@ -9,9 +9,14 @@ namespace avsi {
 
 __global__ void __launch_bounds__(256)
 adam_tf_kernel(float* __restrict__ theta, const float* __restrict__ g, float* __restrict__ m,
-               float* __restrict__ v, long long n, float lr_t, float b1, float omb1, float b2, float omb2, float eps,
-               float unscale, const float* __restrict__ unscale_dev, float l2) {
-  const float us = unscale * (unscale_dev ? *unscale_dev : 1.f);
+               float* __restrict__ v, long long n, double lr, int step, double b1d, double b2d, float eps,
+               float unscale, const float* __restrict__ unscale_dev, float l2, const int32_t* __restrict__ guard) {
+  if (guard && guard[0] != 0) return;            // non-finite gradient (avsi_grad_guard): the step is skipped as a whole
+  // lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t) in double; t counts the updates actually applied (skipped steps excluded)
+  const int t = step - (guard ? guard[1] : 0);
+  const float lr_t = (float)(lr * sqrt(1.0 - pow(b2d, (double)t)) / (1.0 - pow(b1d, (double)t)));
+  const float b1 = (float)b1d, omb1 = (float)(1.0 - b1d), b2 = (float)b2d, omb2 = (float)(1.0 - b2d);
+  const float us = unscale * (unscale_dev ? *unscale_dev : 1.f) * (guard ? __int_as_float(guard[5]) : 1.f);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float th = theta[i];
     float gi = fmaf(g[i], us, l2 * th);
@@ -28,8 +33,10 @@ adam_tf_kernel(float* __restrict__ theta, const float* __restrict__ g, float* __
 //   momentum:  accum = momentum * accum + g ; theta -= lr * accum          (TF ApplyMomentum, use_nesterov = False)
 __global__ void __launch_bounds__(256)
 sgd_momentum_kernel(float* __restrict__ theta, const float* __restrict__ g, float* __restrict__ accum, long long n,
-                    float lr, float momentum, float unscale, const float* __restrict__ unscale_dev, float l2) {
-  const float us = unscale * (unscale_dev ? *unscale_dev : 1.f);
+                    float lr, float momentum, float unscale, const float* __restrict__ unscale_dev, float l2,
+                    const int32_t* __restrict__ guard) {
+  if (guard && guard[0] != 0) return;
+  const float us = unscale * (unscale_dev ? *unscale_dev : 1.f) * (guard ? __int_as_float(guard[5]) : 1.f);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float th = theta[i];
     float gi = fmaf(g[i], us, l2 * th);
@@ -39,6 +46,36 @@ sgd_momentum_kernel(float* __restrict__ theta, const float* __restrict__ g, floa
     }
     theta[i] = th - lr * gi;
   }
+}
+
+// Overflow guard of the fp16 gradient path.  The activations' gradients (dlogits, dY, dG) are fp16 and flow loss-scaled;
+// a run-away dh saturates at 65504 -> inf -> NaN in the weight gradients.  guard = 8 words:
+//   [0] i32 non-finite flag of THIS step   [1] i32 steps skipped so far   [2] i32 finite steps since the last change
+//   [4] f32 dynamic scale s (multiplies the loss gradient fed to the backward pass, a power of two <= 1)
+//   [5] f32 1 / s (folded into the optimiser's unscale)
+// grad_guard_check sets [0]; the optimiser kernels return without touching theta / m / v when it is set;
+// grad_guard_update (after the optimiser) halves s on a skipped step and doubles it back (up to 1) after
+// `growth_interval` finite steps -- all on the device, no host synchronisation in the step.
+__global__ void __launch_bounds__(256) grad_guard_check_kernel(const float* __restrict__ g, long long n, int32_t* __restrict__ guard) {
+  bool bad = false;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float x = g[i];
+    bad |= !(fabsf(x) <= 3.0e38f);               // inf or NaN
+  }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(guard, 1);
+}
+__global__ void grad_guard_update_kernel(int32_t* __restrict__ guard, int growth_interval) {
+  float s = __int_as_float(guard[4]);
+  if (guard[0] != 0) {
+    guard[1] += 1;
+    guard[2] = 0;
+    s = fmaxf(s * 0.5f, 5.9604645e-08f);         // 2^-24
+  } else if (++guard[2] >= growth_interval && s < 1.f) {
+    guard[2] = 0;
+    s *= 2.f;
+  }
+  guard[4] = __float_as_int(s);
+  guard[5] = __float_as_int(1.f / s);
 }
 
 __global__ void __launch_bounds__(256)
@@ -91,15 +128,17 @@ __global__ void gate_bias_prescale_kernel(const float* __restrict__ b, int n, fl
   if (i < n) out[i] = b[i] * (((i & 3) != 1) ? 0.5f : 1.f);
 }
 
-__global__ void mtl_scales_kernel(const float* __restrict__ hole_count, int B, float ctc_w, float* __restrict__ out) {
+__global__ void mtl_scales_kernel(const float* __restrict__ hole_count, int B, float ctc_w, float* __restrict__ out,
+                                  const int32_t* __restrict__ guard) {
   // out[0] = S  (scale of the L1 dlogits), out[1] = S * (w/B) * holes (scale of the CTC dlogits),
   // out[2] = 1 / (S * holes)  (optimiser unscale), out[3] = holes
   float holes = fmaxf(*hole_count, 1.f);
   float rel = ctc_w / (float)B * holes;         // CTC gradient relative to the +-1 L1 gradient
   float S = 1.f;
   while (rel * S > 64.f) S *= 0.5f;             // keep fp16 dlogits far from 65504
-  out[0] = S;
-  out[1] = S * rel;
+  const float dyn = guard ? __int_as_float(guard[4]) : 1.f;     // dynamic scale of the overflow guard (its inverse is
+  out[0] = S * dyn;                                             // applied by the optimiser kernel from guard[5])
+  out[1] = S * rel * dyn;
   out[2] = 1.f / (S * holes);
   out[3] = holes;
 }
@@ -108,28 +147,26 @@ __global__ void mtl_scales_kernel(const float* __restrict__ hole_count, int B, f
 
 extern "C" int avsi_adam_tf(float* theta, const float* g, float* m, float* v, int64_t n, double lr, double b1,
                             double b2, double eps, int step, float grad_unscale, const float* grad_unscale_dev,
-                            float l2, void* stream) {
+                            float l2, const int32_t* guard, void* stream) {
   using namespace avsi;
   AVSI_REQUIRE(theta && g && m && v, "null pointer");
   AVSI_REQUIRE(n > 0 && step >= 1, "n > 0, step >= 1");
-  // lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t), evaluated in double on the host
-  double lr_t = lr * sqrt(1.0 - pow(b2, (double)step)) / (1.0 - pow(b1, (double)step));
   int blocks = (int)min((long long)(n + 255) / 256, (long long)num_sms() * 8);
-  adam_tf_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(theta, g, m, v, (long long)n, (float)lr_t, (float)b1, (float)(1.0 - b1),
-                                                          (float)b2, (float)(1.0 - b2), (float)eps,
-                                                          grad_unscale, grad_unscale_dev, l2);
+  adam_tf_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(theta, g, m, v, (long long)n, lr, step, b1, b2, (float)eps,
+                                                          grad_unscale, grad_unscale_dev, l2, guard);
   AVSI_LAUNCH_CHECK();
   return AVSI_OK;
 }
 
 extern "C" int avsi_sgd_momentum(float* theta, const float* g, float* accum, int64_t n, double lr, double momentum,
-                                 float grad_unscale, const float* grad_unscale_dev, float l2, void* stream) {
+                                 float grad_unscale, const float* grad_unscale_dev, float l2, const int32_t* guard,
+                                 void* stream) {
   using namespace avsi;
   AVSI_REQUIRE(theta && g, "null pointer");
   AVSI_REQUIRE(n > 0, "n > 0");
   int blocks = (int)min((long long)(n + 255) / 256, (long long)num_sms() * 8);
   sgd_momentum_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(theta, g, accum, (long long)n, (float)lr, (float)momentum,
-                                                               grad_unscale, grad_unscale_dev, l2);
+                                                               grad_unscale, grad_unscale_dev, l2, guard);
   AVSI_LAUNCH_CHECK();
   return AVSI_OK;
 }
@@ -166,10 +203,41 @@ extern "C" int avsi_gate_bias_prescale(const float* bias, int n, float* out, voi
   return AVSI_OK;
 }
 
-extern "C" int avsi_mtl_scales(const float* hole_count, int B, float ctc_weight, float* out, void* stream) {
+extern "C" int avsi_grad_guard_init(int32_t* guard, void* stream) {
+  using namespace avsi;
+  AVSI_REQUIRE(guard, "null pointer");
+  const float one = 1.f;
+  int32_t h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  memcpy(&h[4], &one, 4);
+  memcpy(&h[5], &one, 4);
+  AVSI_CUDA(cudaMemcpyAsync(guard, h, sizeof(h), cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  AVSI_CUDA(cudaStreamSynchronize((cudaStream_t)stream));       // h is a stack buffer
+  return AVSI_OK;
+}
+
+extern "C" int avsi_grad_guard_check(const float* g, int64_t n, int32_t* guard, void* stream) {
+  using namespace avsi;
+  AVSI_REQUIRE(g && guard && n > 0, "args");
+  AVSI_CUDA(cudaMemsetAsync(guard, 0, 4, (cudaStream_t)stream));
+  int blocks = (int)min((long long)(n + 255) / 256, (long long)num_sms() * 8);
+  grad_guard_check_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(g, (long long)n, guard);
+  AVSI_LAUNCH_CHECK();
+  return AVSI_OK;
+}
+
+extern "C" int avsi_grad_guard_update(int32_t* guard, int growth_interval, void* stream) {
+  using namespace avsi;
+  AVSI_REQUIRE(guard && growth_interval > 0, "args");
+  grad_guard_update_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(guard, growth_interval);
+  AVSI_LAUNCH_CHECK();
+  return AVSI_OK;
+}
+
+extern "C" int avsi_mtl_scales(const float* hole_count, int B, float ctc_weight, float* out, const int32_t* guard,
+                               void* stream) {
   using namespace avsi;
   AVSI_REQUIRE(hole_count && out && B > 0, "args");
-  mtl_scales_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(hole_count, B, ctc_weight, out);
+  mtl_scales_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(hole_count, B, ctc_weight, out, guard);
   AVSI_LAUNCH_CHECK();
   return AVSI_OK;
 }

@@ -112,8 +112,10 @@ class DataManager(object):
                 np.concatenate(seq['labels']).astype(np.float32) if seq.get('labels') else np.zeros(0, np.float32),
                 np.stack(seq['video_features']).astype(np.float32), np.stack(seq['mask']).astype(np.float32))
 
-    def get_dataset(self, file_list, shuffle=True, seed=None):
-        files = parallel.shard_list(file_list, self.rank, self.world) if self.world > 1 else list(file_list)
+    def get_dataset(self, file_list, shuffle=True, seed=None, keep_order=False):
+        """keep_order: the caller passes the SAME (e.g. seed-shuffled) order on every rank; the shard is then taken from
+        that order instead of the sorted list."""
+        files = parallel.shard_list(file_list, self.rank, self.world, keep_order) if self.world > 1 else list(file_list)
         return _Dataset(files, self.read_data_format_fixed, shuffle, self.buffer_size, seed, self.workers)
 
     def get_iterator(self, dataset, batch_size=16, n_epochs=None, drop_remainder=False):

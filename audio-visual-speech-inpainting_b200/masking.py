@@ -29,7 +29,7 @@ def masked_waveforms(wav, mask, oracle_phase=False, window_size=24, step_size=12
                                step_size=step_size)
 
 
-def mask_app(data_path, audio_path, tfrecord_mode='fixed', oracle_phase=False, audio_feat_dim=257, video_feat_dim=136,
+def mask_app(data_path, audio_path, tfrecord_mode='fixed', oracle_phase=True, audio_feat_dim=257, video_feat_dim=136,
              num_audio_samples=48000, batch_size=1):
     from scipy.io import wavfile
     dm = DataManager(num_audio_samples=num_audio_samples, audio_feat_size=audio_feat_dim, video_feat_size=video_feat_dim,

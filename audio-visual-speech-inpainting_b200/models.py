@@ -71,6 +71,7 @@ class StackedBLSTMModel(object):
         self.global_step = 0
         self.dropout_seed = int(config.get('seed', 0))
         self._feeds = 0
+        self._feed_step, self._feeds_at_step = -1, 0
         self._stale = False
         self._sums = torch.zeros(8, dtype=torch.float64, device=self.device)
         self._cache = {}
@@ -125,7 +126,18 @@ class StackedBLSTMModel(object):
     def _dropout(self):
         """(rate, seed, offset) of the current feed, or None: tf.nn.dropout(rnn_outputs, rate) of models.py:117."""
         rate = self._fed.get('dropout_rate', 0.0)
-        return (rate, self.dropout_seed, self._feeds) if rate > 0.0 else None
+        if rate <= 0.0:
+            return None
+        # Philox offset = (rank, global step, feeds since that step): distinct masks on every rank, and the stream
+        # continues where it was after a checkpoint resume (global_step is restored, the feed counter is not)
+        rank = 0
+        if self.process_group is not None:
+            import torch.distributed as dist
+            rank = dist.get_rank(self.process_group)
+        if self._feed_step != self.global_step:
+            self._feed_step, self._feeds_at_step = self.global_step, self._feeds
+        sub = (self._feeds - self._feeds_at_step) & 0xFF
+        return (rate, self.dropout_seed, (rank << 48) | ((self.global_step & 0xFFFFFFFFFF) << 8) | sub)
 
     def dropout_keep_mask(self):
         """The keep mask of the current feed as bool [B, T, 2H] (fw units, then bw units), or None.  For parity tests."""
@@ -231,18 +243,25 @@ class StackedBLSTMModel(object):
         scales = None
         if self.MTL:
             scales = torch.empty(4, dtype=torch.float32, device=self.device)
+            # the hole normaliser sum(1-m) is GLOBAL (models.py:1947 on the whole batch): the local count of the front end
+            # is cloned and all-reduced ONCE per feed (the reduced value is cached beside the local one, so re-evaluating
+            # the loss on the same feed neither reduces twice nor issues a collective the other ranks do not)
             hole = fr['hole']
             world = 1
             if self.process_group is not None:
                 import torch.distributed as dist
-                dist.all_reduce(hole, group=self.process_group)
                 world = dist.get_world_size(self.process_group)
+                if fr.get('hole_global') is None:
+                    fr['hole_global'] = hole.clone()
+                    dist.all_reduce(fr['hole_global'], group=self.process_group)
+                hole = fr['hole_global']
             _lib.check(lib.avsi_mtl_scales(_p(hole), B * world, float(self.ctc_loss_weight), _p(scales),
-                                           _lib.stream_ptr()), 'avsi_mtl_scales')
+                                           _p(self.engine.guard), _lib.stream_ptr()), 'avsi_mtl_scales')
         dl = ws['dlogits'] if (want_grad and 'dlogits' in ws) else None
         with _lib.span('masked_l1'):
             _lib.check(lib.avsi_masked_l1(_p(logits), L.nop, _p(fr['target_spec_norm']), _p(masks), _p(seq), B, T, F,
-                                          1 if self.MTL else 0, 1.0, _p(scales) if self.MTL else None, _p(self._sums),
+                                          1 if self.MTL else 0, 1.0,
+                                          _p(scales) if self.MTL else self.engine.guard_scale_ptr, _p(self._sums),
                                           _p(pred), _p(dl), L.nop, _lib.stream_ptr()), 'avsi_masked_l1')
         if self.MTL:
             labels, lab_len = self._need('labels', 'labels_lengths')
@@ -318,20 +337,25 @@ class StackedBLSTMModel(object):
         self.engine.backward(self._front()['ws'])
         return out
 
+    def _reduce_gradients(self, out):
+        """Data parallel: ONE all-reduce per step over the flat fp32 gradient with the loss scalars riding in its tail.
+        Returns the world size."""
+        if self.process_group is None:
+            return 1
+        import torch.distributed as dist
+        from . import parallel
+        world = dist.get_world_size(self.process_group)
+        parallel.pack_loss_tail(self.engine.grad, self.engine.layout.n_params_padded, out['sums'])
+        with _lib.span('grad_allreduce', nbytes=self.engine.grad.numel() * 4):
+            parallel.all_reduce_flat(self.engine.grad, self.process_group)
+        return world
+
     def train_op(self):
         if self.optimizer_choice not in ('adam', 'sgd', 'momentum'):
             print('Optimizer must be either sgd, momentum or adam. Closing...')         # models.py:175-176
             sys.exit(1)
         out = self.compute_gradients()
-        world = 1
-        if self.process_group is not None:
-            import torch.distributed as dist
-            from . import parallel
-            world = dist.get_world_size(self.process_group)
-            # ONE all-reduce per step: flat fp32 gradient with the loss scalars riding in its tail
-            parallel.pack_loss_tail(self.engine.grad, self.engine.layout.n_params_padded, out['sums'])
-            with _lib.span('grad_allreduce', nbytes=self.engine.grad.numel() * 4):
-                parallel.all_reduce_flat(self.engine.grad, self.process_group)
+        world = self._reduce_gradients(out)
         host, dev = self._grad_unscale(out, world)
         if self.optimizer_choice == 'adam':
             # Adam is given the constant starter rate (models.py:168); the decayed rate applies to sgd / momentum only
@@ -343,13 +367,15 @@ class StackedBLSTMModel(object):
         self.global_step += 1
         self._stale = True
 
-    def canonical_gradients(self):
-        """d loss / d variable in the reference's canonical layout (float64 numpy), for parity tests."""
+    def canonical_gradients(self, reduce=False):
+        """d loss / d variable in the reference's canonical layout (float64 numpy), for parity tests.  reduce=True (data
+        parallel): the gradient of the GLOBAL batch's loss, after the all-reduce train_op would issue."""
         out = self.compute_gradients()
-        host, dev = self._grad_unscale(out, 1)
+        world = self._reduce_gradients(out) if reduce else 1
+        host, dev = self._grad_unscale(out, world)
         if dev is not None:
             host = host * float(dev.item())
-        return self.engine.export_canonical_grads(host)
+        return self.engine.export_canonical_grads(host / self.engine.guard_state()[1])
 
     # ---- waveform reconstruction (models.py:181-197) -----------------------------------------------------
     def _enhanced(self, oracle_phase):

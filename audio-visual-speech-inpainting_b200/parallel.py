@@ -12,9 +12,41 @@ import torch
 LOSS_TAIL = 8          # loss scalars riding behind the gradient in the same buffer
 
 
-def shard_list(items, rank, world):
-    """Rank r reads items[r::world] of the sorted list (replaces training.py:47-49's single glob)."""
-    return sorted(items)[rank::world]
+def shard_list(items, rank, world, keep_order=False):
+    """Rank r reads items[r::world] (replaces training.py:47-49's single glob).  The list is sorted first unless the
+    caller vouches that every rank passes it in the SAME order (keep_order=True: the per-epoch shuffle of
+    training.py:212-214 done with a rank-consistent seed survives the sharding)."""
+    items = list(items) if keep_order else sorted(items)
+    return items[rank::world]
+
+
+def lockstep(batches, batch_size, group=None, device='cpu'):
+    """Yield from this rank's batch generator only while EVERY rank of `group` still has a full batch.
+
+    Each rank reads its own shard, so the ranks can run out at different steps or end on a smaller batch
+    (N_train % (world * batch) != 0).  A rank that left the loop while the others are still inside the gradient
+    all-reduce would dead-lock the job, and a smaller last batch would be normalised by the wrong global count.  Every
+    step the ranks therefore agree (one MIN all-reduce of a flag) whether all of them hold a batch of exactly
+    `batch_size` utterances; the first step on which one does not ends the epoch everywhere, the ragged tail is dropped.
+    Single process (no group, torch.distributed not initialised): plain iteration, partial batches included."""
+    import torch.distributed as dist
+    if group is None and not dist.is_initialized():
+        for b in batches:
+            yield b
+        return
+    it = iter(batches)
+    flag = torch.zeros(1, dtype=torch.int32, device=device)
+    while True:
+        b = next(it, None)
+        ok = b is not None and len(b[0]) == batch_size
+        flag.fill_(1 if ok else 0)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) == 0:
+            close = getattr(it, 'close', None)
+            if close is not None:
+                close()
+            return
+        yield b
 
 
 def shard_batch(n, rank, world):

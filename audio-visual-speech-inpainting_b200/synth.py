@@ -45,11 +45,13 @@ def make_batch(B, audio_len=48000, hop=192, F=257, V=136, video_frames=75, seed=
     }
 
 
-def default_config(model='av-blstm', batch_size=8, audio_len=48000, net_dim=(250, 250, 250), ctc_loss=0.001):
+def default_config(model='av-blstm', batch_size=8, audio_len=48000, net_dim=(250, 250, 250), ctc_loss=0.001, **over):
     """The shipped hyper-parameters (scripts/config/blstm*.config) as a dict, post check_trainconfiguration."""
-    return {
+    cfg = {
         'model': model, 'audio_feat_dim': 257, 'video_feat_dim': 136, 'audio_len': audio_len,
         'batch_size': batch_size, 'net_dim': list(net_dim), 'dropout_rate': 0.0, 'optimizer_type': 'adam',
         'starter_learning_rate': 0.001, 'lr_updating_steps': 10000, 'lr_decay': 1.0, 'l2': 0.0,
         'num_asr_labels': 34, 'ctc_loss': ctc_loss, 'seed': 0,
     }
+    cfg.update(over)
+    return cfg

@@ -8,7 +8,9 @@ exit code 1).  The session run per step becomes model.feed(...) + model.train_op
 checkpoints are `.npz` files keyed by the TF variable names (checkpoint.py); PER is computed from the best-path
 decoding at the logging steps and on the validation set instead of a beam search on every step; TensorBoard
 scalars are written when torch.utils.tensorboard is importable.  Under torchrun every rank trains on
-files[rank::world] with the gradient all-reduce of parallel.py; rank 0 logs and saves."""
+files[rank::world] (of a per-epoch shuffle every rank draws with the same seed) in lock step -- the ranks agree every
+step that all of them still hold a full batch, the ragged tail of an epoch is dropped (parallel.lockstep) -- with the
+gradient all-reduce of parallel.py; rank 0 logs and saves."""
 import os
 import random
 import shutil
@@ -18,7 +20,7 @@ from time import time
 
 import numpy as np
 
-from . import checkpoint
+from . import checkpoint, parallel
 from .config_utils import check_trainconfiguration, load_configfile
 from .dataset_reader import DataManager
 from .models import MODEL_REGISTRY
@@ -185,8 +187,15 @@ def _train(config_file, max_steps, build_model, feed_batch, _losses):
         epoch_counter += 1
         epoch_start_time = time()
         files = list(train_files)
-        random.shuffle(files)
-        _, train_it = manager().get_iterator(manager().get_dataset(files, shuffle=True), batch_size=per_rank_batch, n_epochs=1)
+        if world > 1:
+            # the same permutation on every rank (training.py:212 shuffles with the process-global generator): the
+            # shards files[rank::world] of it are disjoint and change from epoch to epoch
+            random.Random(int(config.get('seed', 0)) * 1000003 + epoch_counter).shuffle(files)
+        else:
+            random.shuffle(files)
+        _, train_it = manager().get_iterator(manager().get_dataset(files, shuffle=True, keep_order=True),
+                                             batch_size=per_rank_batch, n_epochs=1)
+        train_it = parallel.lockstep(train_it, per_rank_batch, pg, model.device)
         if rank == 0:
             print('-> Epoch {:d}'.format(epoch_counter))
         avg, n_step, lr = _RunningAverage(), 0, model.learning_rate
@@ -222,6 +231,7 @@ def _train(config_file, max_steps, build_model, feed_batch, _losses):
             print('Start validation set evaluation...')
         # ---- validation: same model, no update ----------------------------------------------------------------
         _, val_it = manager().get_iterator(manager().get_dataset(val_files, shuffle=False), batch_size=per_rank_batch, n_epochs=1)
+        val_it = parallel.lockstep(val_it, per_rank_batch, pg, model.device)   # the MTL loss all-reduces its hole count
         vavg, n_vstep = _RunningAverage(), 0
         for batch in val_it:
             n_vstep += 1

@@ -37,6 +37,14 @@ const char* avsi_last_error(void);
 const char* avsi_version(void);
 /* Number of kernel launches issued by this library since load (all threads). */
 int64_t avsi_launch_count(void);
+/* The AVSI_* tuning / test switches (AVSI_LSTM_FWD / AVSI_LSTM_BWD = mma | l4 kernel selection, AVSI_LSTM_ACT,
+ * AVSI_GEMM_2SM, AVSI_GEMM_BN, phase timers) are read from the environment once and cached; call this after
+ * changing them inside a running process. */
+void avsi_reload_env(void);
+/* Debug: cycles per phase summed over the steps of the last tcgen05 recurrence launch with AVSI_L4_TIMING=1 /
+ * AVSI_B4_TIMING=1 (profiles/bench_lstm.py).  out16 / out24: HOST arrays. */
+int avsi_debug_lstm4_timing(unsigned long long* out16);
+int avsi_debug_lstm4_bwd_timing(unsigned long long* out24);
 /* sizeof() of the argument structs below, for FFI bindings to self-check their mirrors. */
 int avsi_sizeof_frontend_args(void);
 int avsi_sizeof_istft_args(void);
@@ -199,7 +207,9 @@ int avsi_masked_l1(const float* logits, int ldl, const float* target, const floa
 /* MTL gradient scales from the hole count: out[0] = S (L1 dlogits scale, a power of two),
  * out[1] = S*(ctc_weight/B)*holes (CTC dlogits scale), out[2] = 1/(S*holes) (optimiser unscale),
  * out[3] = holes.  loss = loss_hole + ctc_weight * mean_b(nll_b)  (models.py:1955). */
-int avsi_mtl_scales(const float* hole_count, int B, float ctc_weight, float* out, void* stream);
+/* guard (optional): the overflow-guard state below; its dynamic scale multiplies out[0] and out[1]. */
+int avsi_mtl_scales(const float* hole_count, int B, float ctc_weight, float* out, const int32_t* guard,
+                    void* stream);
 
 /* Inverted dropout of the BLSTM outputs ahead of the head(s): tf.nn.dropout(rnn_outputs, rate=dropout_rate) at
  * models.py:117, :1901, models_asr.py:120.  dst[r,c] = keep ? src[r,c] / (1 - rate) : 0 with keep = (u >= rate),
@@ -255,11 +265,25 @@ uint32_t avsi_crc32c_host(const void* data, uint64_t n, uint32_t crc);
  *   g is multiplied by grad_unscale first; l2 adds l2 * theta to the gradient (models.py:153-158). */
 int avsi_adam_tf(float* theta, const float* g, float* m, float* v, int64_t n, double lr, double b1,
                  double b2, double eps, int step, float grad_unscale, const float* grad_unscale_dev,
-                 float l2, void* stream);
+                 float l2, const int32_t* guard, void* stream);
 /* tf.train.GradientDescentOptimizer (accum == NULL) / MomentumOptimizer(momentum = 0.9) (models.py:169-173):
  * accum = momentum * accum + g ; theta -= lr * accum.  lr is the (host-evaluated) staircase exponential decay. */
 int avsi_sgd_momentum(float* theta, const float* g, float* accum, int64_t n, double lr, double momentum,
-                      float grad_unscale, const float* grad_unscale_dev, float l2, void* stream);
+                      float grad_unscale, const float* grad_unscale_dev, float l2, const int32_t* guard,
+                      void* stream);
+/* Overflow guard of the fp16 gradient path (no counterpart in the reference, whose graph is fp32: there a run-away
+ * gradient ends in the NaN exit of training.py:244-249; here dlogits / dY / dG are loss-scaled fp16 and would
+ * saturate first).  guard = 8 device words: [0] i32 non-finite flag of this step, [1] i32 steps skipped so far,
+ * [2] i32 finite steps since the last scale change, [4] f32 dynamic scale s (power of two <= 1, fed to the loss
+ * kernels as grad_scale_dev / to avsi_mtl_scales), [5] f32 1/s (applied by the optimiser kernels).
+ *   avsi_grad_guard_init    s = 1, counters 0 (synchronises the stream).
+ *   avsi_grad_guard_check   [0] = any(!isfinite(g[0..n)))   -- run on the all-reduced gradient, before the optimiser;
+ *                           the optimiser kernels leave theta / m / v untouched when [0] != 0 (guard may be NULL).
+ *   avsi_grad_guard_update  after the optimiser: skipped step -> s /= 2, else after growth_interval finite steps
+ *                           s = min(2 s, 1).  All on the device: the step needs no host synchronisation. */
+int avsi_grad_guard_init(int32_t* guard, void* stream);
+int avsi_grad_guard_check(const float* g, int64_t n, int32_t* guard, void* stream);
+int avsi_grad_guard_update(int32_t* guard, int growth_interval, void* stream);
 /* Widen a batch that was copied to the device in its storage dtype (src_type 0 = int16 samples, 1 = uint8 masks,
  * 2 = int32 samples as dataset_reader.py:78 yields them) to the fp32 tensor of the feed contract (training.py:69-71). */
 int avsi_cast_to_f32(const void* src, int src_type, int64_t n, float* dst, void* stream);

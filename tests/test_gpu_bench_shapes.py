@@ -1,0 +1,170 @@
+"""Parity WHERE THE BENCHMARK RUNS.
+
+bench.py times B = 2048 utterances of T = 250 frames (BASELINE configs[1]) and, for configs[4], T = 1667: at those
+sizes the step runs the tcgen05 4-CTA-cluster recurrence / BPTT kernels (lstm4.cu, lstm4_bwd.cu) and the CTA-pair
+GEMMs.  The float64 oracle cannot run 2048 x 250 frames in seconds, so:
+
+  * the tcgen05 kernels are forced at a small batch (AVSI_LSTM_FWD / AVSI_LSTM_BWD = l4, re-read through
+    avsi_reload_env) and compared with the oracle -- outputs AND gradients, <= 2e-3 relative L2 -- over the full
+    250- and 1667-step chains, SI and MTL (the BPTT kernel ships the peers' partial dh as fp16 every step: this is
+    where its error growth over the chain is measured);
+  * the exact bench launch (B = 2048, T = 250: 16 row tiles, 32 clusters) runs on a batch that TILES 8 distinct
+    utterances 256 times: every one of the 2048 predictions must match the oracle's for its utterance, and the
+    gradient of the mean loss equals the oracle's gradient on the 8 distinct utterances (a mean over identical
+    copies), so the whole parameter gradient of the bench-shaped step is checked against float64;
+  * large-magnitude weights: the static loss scale does not overflow fp16 for recurrent weights 3x Glorot, and when
+    the activations' gradients DO overflow (head weights x 4e4) the overflow guard skips the step, halves the scale
+    and training continues with gradients that match the oracle again.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_l2
+from test_gpu_model import TOL, _build, _check_grads, _oracle_inputs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture
+def l4_forced():
+    from avsi_b200 import _lib
+    _lib.set_env(AVSI_LSTM_FWD='l4', AVSI_LSTM_BWD='l4')
+    yield
+    _lib.set_env(AVSI_LSTM_FWD=None, AVSI_LSTM_BWD=None)
+
+
+def chain_parity(model_name, B, audio_len, seed, **build_kw):
+    """(rel-L2 of prediction, of the full gradient, worst per-variable gradient) of the CUDA model against the oracle."""
+    from oracle import blstm as oblstm
+    mtl = model_name.endswith('ctc')
+    model, batch, canon, inp = _build(model_name, B, audio_len, seed=seed, **(dict(ctc_loss=0.05) if mtl else {}),
+                                      **build_kw)
+    tsn, net_in = _oracle_inputs(batch, inp)
+    oin = dict(net_in=net_in, target=tsn, mask=batch['mask'], seq_len=batch['seq_len'])
+    if mtl:
+        oin.update(labels=batch['labels'], lab_len=batch['lab_len'])
+        outs, ograds = oblstm.loss_and_grads('mtl', oin, canon, 3, ctc_weight=0.05)
+    else:
+        outs, ograds = oblstm.loss_and_grads('si', oin, canon, 3)
+    e_pred = rel_l2(model.prediction.cpu().numpy(), outs['prediction'])
+    e_loss = abs(float(model.loss) - float(outs['loss'])) / abs(float(outs['loss']))
+    grads = model.canonical_gradients()
+    ga = np.concatenate([grads[k].ravel() for k in sorted(ograds)])
+    gb = np.concatenate([ograds[k].ravel() for k in sorted(ograds)])
+    worst = max((rel_l2(grads[k], ograds[k]), k) for k in ograds if np.linalg.norm(ograds[k]) > 0)
+    return dict(pred=e_pred, loss=e_loss, grad=rel_l2(ga, gb), worst=worst[0], worst_name=worst[1],
+                model=model, grads=grads, ograds=ograds)
+
+
+@pytest.mark.parametrize('model_name,audio_len', [('av-blstm', 48000), ('av-blstm-ssnn-ctc', 48000),
+                                                  ('av-blstm', 320000), ('av-blstm-ssnn-ctc', 320000)])
+def test_tcgen05_recurrence_full_chains_vs_oracle(l4_forced, model_name, audio_len):
+    """T = 250 (BASELINE configs[1]) and T = 1667 (configs[4], 20 s) through lstm4_fwd / lstm4_bwd at B = 3."""
+    r = chain_parity(model_name, 3, audio_len, seed=41)
+    assert r['pred'] < TOL, r['pred']
+    assert r['loss'] < TOL, r['loss']
+    _check_grads(r['grads'], r['ograds'], '%s T=%d (tcgen05 path)' % (model_name, -(-audio_len // 192)))
+
+
+def test_tcgen05_and_mma_recurrences_agree_on_long_chain(l4_forced):
+    """The same 1667-step problem through both kernel families: the small-batch mma.sync kernels (fp32 partial dh
+    exchange) and the tcgen05 ones (fp16 partials) stay within the budget of EACH OTHER as well."""
+    from avsi_b200 import _lib
+    r4 = chain_parity('av-blstm', 2, 320000, seed=43)
+    _lib.set_env(AVSI_LSTM_FWD='mma', AVSI_LSTM_BWD='mma')
+    rm = chain_parity('av-blstm', 2, 320000, seed=43)
+    assert rm['pred'] < TOL and rm['grad'] < TOL
+    ga = np.concatenate([r4['grads'][k].ravel() for k in sorted(r4['grads'])])
+    gb = np.concatenate([rm['grads'][k].ravel() for k in sorted(rm['grads'])])
+    assert rel_l2(ga, gb) < TOL
+
+
+def test_bench_launch_b2048_t250_every_row_tile_vs_oracle():
+    """The exact launch bench.py times (B = 2048, T = 250, AV-SI): 8 distinct utterances tiled over the 2048 batch
+    rows (utterance b = distinct[b % 8], so every 128-row tile of every cluster holds all 8)."""
+    from avsi_b200 import av_sync, models, synth
+    from avsi_b200.layout import init_canonical
+    from oracle import blstm as oblstm
+    U, B, audio_len = 8, 2048, 48000
+    small = synth.make_batch(U, audio_len=audio_len, seed=77)
+    T = small['T']
+    idx = np.arange(B) % U
+    cfg = synth.default_config('av-blstm', batch_size=B, audio_len=audio_len)
+    video = av_sync.video_pipeline(small['landmarks'], T, small['vmean'], small['vstd'])
+    vid_big = video[torch.as_tensor(idx, device=video.device)] if torch.is_tensor(video) else video[idx]
+    model = models.StackedBLSTMModel(small['seq_len'][idx], small['wav'][idx], small['mask'][idx], small['mean'],
+                                     small['std'], 0.0, cfg, video_features=vid_big, input='av')
+    canon = init_canonical(model.engine.layout, seed=78, bias_scale=0.05)
+    model.assign_vars(canon)
+    tsn, net_in = _oracle_inputs(small, 'av')
+    outs, ograds = oblstm.loss_and_grads('si', dict(net_in=net_in, target=tsn, mask=small['mask'], seq_len=small['seq_len']),
+                                         canon, 3)
+    ref = torch.from_numpy(outs['prediction']).to(model.device)                      # [8, T, F] float64
+    pred = model.prediction.double().view(B // U, U, T, -1)                          # row b = tile * 8 + utterance
+    err = (pred - ref[None]).flatten(2).norm(dim=2) / ref.flatten(1).norm(dim=1)[None]  # per (tile, utterance)
+    assert float(err.max()) < TOL, float(err.max())
+    assert abs(float(model.loss) - float(outs['loss'])) < TOL * abs(float(outs['loss']))
+    _check_grads(model.canonical_gradients(), ograds, 'av-blstm B=2048 T=250')
+    # and the optimiser step from that gradient: finite, guard untouched
+    model.train_op()
+    skipped, scale = model.engine.guard_state()
+    assert skipped == 0 and scale == 1.0
+    assert bool(torch.isfinite(model.engine.theta).all())
+
+
+def _scaled(canon, pattern, factor, rows=None):
+    out = {k: np.array(v, copy=True) for k, v in canon.items()}
+    for k in out:
+        if pattern in k:
+            if rows is None:
+                out[k] *= factor
+            else:
+                out[k][rows(out[k]):] *= factor
+    return out
+
+
+def test_large_norm_recurrent_weights_do_not_overflow_the_static_scale(l4_forced):
+    """Recurrent kernels 3x their Glorot range (saturating gates, |dh| growing along the chain): T = 250, the loss-scaled
+    fp16 gradients stay finite, the guard never fires, parity holds."""
+    from oracle import blstm as oblstm
+    model, batch, canon, inp = _build('av-blstm', 3, 48000, seed=51)
+    H = 250
+    big = _scaled(canon, '/kernel', 3.0, rows=lambda k: k.shape[0] - H)              # the h rows of [x ; h]
+    model.assign_vars(big)
+    tsn, net_in = _oracle_inputs(batch, inp)
+    outs, ograds = oblstm.loss_and_grads('si', dict(net_in=net_in, target=tsn, mask=batch['mask'], seq_len=batch['seq_len']),
+                                         big, 3)
+    assert rel_l2(model.prediction.cpu().numpy(), outs['prediction']) < TOL
+    _check_grads(model.canonical_gradients(), ograds, 'av-blstm, 3x recurrent weights', tol=2 * TOL)
+    model.train_op()
+    assert model.engine.guard_state() == (0, 1.0)
+    assert bool(torch.isfinite(model.engine.theta).all())
+
+
+def test_overflow_guard_skips_and_recovers():
+    """Head weights x 4e4: dY = dlogits . W_head^T exceeds 65504 in fp16 -> NaN weight gradients.  The guard must skip
+    those steps (weights and Adam state untouched), halve the scale until the backward pass is finite, and the
+    gradients at the reduced scale must match the oracle."""
+    from oracle import blstm as oblstm
+    model, batch, canon, inp = _build('av-blstm', 4, 9600, seed=52)
+    big = _scaled(canon, 'logits/weights', 4.0e4)
+    model.assign_vars(big)
+    theta0 = model.engine.theta.clone()
+    model.train_op()                                   # overflows: skipped
+    skipped, scale = model.engine.guard_state()
+    assert skipped == 1 and scale == 0.5
+    assert torch.equal(model.engine.theta, theta0)
+    assert float(model.engine.adam_m.abs().max()) == 0.0
+    for _ in range(12):
+        model.train_op()
+    skipped, scale = model.engine.guard_state()
+    assert 1 <= skipped <= 10 and scale == 0.5 ** skipped
+    assert bool(torch.isfinite(model.engine.theta).all()) and not torch.equal(model.engine.theta, theta0)
+    # parity of the gradient at the reduced scale, on the weights as they are now
+    now = model.engine.export_canonical()
+    model.feed(dropout_rate=0.0)                       # same tensors, a fresh evaluation
+    tsn, net_in = _oracle_inputs(batch, inp)
+    outs, ograds = oblstm.loss_and_grads('si', dict(net_in=net_in, target=tsn, mask=batch['mask'], seq_len=batch['seq_len']),
+                                         now, 3)
+    _check_grads(model.canonical_gradients(), ograds, 'av-blstm after guard back-off')

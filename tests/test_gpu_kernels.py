@@ -443,7 +443,7 @@ def test_adam_tf_and_cast():
     rth, rm, rv = th.astype(np.float64), m.astype(np.float64), v.astype(np.float64)
     for step in (1, 2, 3):
         _lib.check(lib.avsi_adam_tf(_lib.ptr(tth), _lib.ptr(tg), _lib.ptr(tm), _lib.ptr(tv), n, 1e-3, 0.9, 0.999, 1e-8,
-                                    step, 1.0 / 16, _lib.ptr(us), 0.0, _lib.stream_ptr()), 'adam')
+                                    step, 1.0 / 16, _lib.ptr(us), 0.0, None, _lib.stream_ptr()), 'adam')
         rth, rm, rv = oadam.adam_tf_step(rth, g.astype(np.float64) / 64.0, rm, rv, step)
     sync()
     assert np.abs(tth.cpu().numpy() - rth).max() < 1e-6
@@ -453,6 +453,55 @@ def test_adam_tf_and_cast():
     _lib.check(lib.avsi_cast_weights(_lib.ptr(W), 291, 77, _lib.ptr(w16), _lib.ptr(w16t), 0, _lib.stream_ptr()), 'cast')
     sync()
     assert torch.equal(w16, W.half()) and torch.equal(w16t, W.half().t())
+
+
+def test_grad_guard_skips_nonfinite_steps_and_rescales():
+    """Overflow guard of the fp16 gradient path: a step whose (all-reduced) gradient holds an inf / NaN leaves theta,
+    m and v untouched, halves the dynamic loss scale and is not counted by Adam's bias correction; finite steps apply
+    g * unscale / s exactly like the unguarded kernel; after `growth_interval` finite steps the scale doubles back."""
+    from avsi_b200 import _lib
+    from oracle import adam as oadam
+    lib = _lib.load()
+    rng = np.random.default_rng(11)
+    d = dev()
+    n = 50001
+    th = rng.standard_normal(n).astype(np.float32)
+    g = rng.standard_normal(n).astype(np.float32)
+    tth = torch.from_numpy(th.copy()).to(d)
+    tm, tv = torch.zeros(n, device=d), torch.zeros(n, device=d)
+    guard = torch.zeros(8, dtype=torch.int32, device=d)
+    _lib.check(lib.avsi_grad_guard_init(_lib.ptr(guard), _lib.stream_ptr()), 'init')
+
+    def state():
+        gh = guard.cpu()
+        return int(gh[0]), int(gh[1]), float(gh[4:5].view(torch.float32)[0]), float(gh[5:6].view(torch.float32)[0])
+
+    def step(grad, k):
+        tg = torch.from_numpy(grad).to(d)
+        _lib.check(lib.avsi_grad_guard_check(_lib.ptr(tg), n, _lib.ptr(guard), _lib.stream_ptr()), 'check')
+        _lib.check(lib.avsi_adam_tf(_lib.ptr(tth), _lib.ptr(tg), _lib.ptr(tm), _lib.ptr(tv), n, 1e-3, 0.9, 0.999, 1e-8, k, 1.0,
+                                    None, 0.0, _lib.ptr(guard), _lib.stream_ptr()), 'adam')
+        _lib.check(lib.avsi_grad_guard_update(_lib.ptr(guard), 2, _lib.stream_ptr()), 'update')
+        sync()
+    assert state() == (0, 0, 1.0, 1.0)
+    rth, rm, rv = th.astype(np.float64), np.zeros(n), np.zeros(n)
+    step(g, 1)
+    rth, rm, rv = oadam.adam_tf_step(rth, g.astype(np.float64), rm, rv, 1)
+    assert np.abs(tth.cpu().numpy() - rth).max() < 1e-6 and state() == (0, 0, 1.0, 1.0)
+    for bad_value in (np.inf, np.nan):
+        gb = g.copy()
+        gb[n - 7] = bad_value
+        before = (tth.clone(), tm.clone(), tv.clone())
+        step(gb, 2)
+        assert torch.equal(tth, before[0]) and torch.equal(tm, before[1]) and torch.equal(tv, before[2])
+    assert state() == (1, 2, 0.25, 4.0)
+    # the backward pass now runs at scale 1/4: the gradient arrives multiplied by s and is unscaled by 1/s;
+    # host step counter 4, two skipped -> bias correction of update 2
+    step(g * 0.25, 4)
+    rth, rm, rv = oadam.adam_tf_step(rth, g.astype(np.float64), rm, rv, 2)
+    assert np.abs(tth.cpu().numpy() - rth).max() < 1e-6
+    step(g * 0.25, 5)                                 # second finite step in a row: growth_interval = 2 -> s doubles
+    assert state() == (0, 2, 0.5, 2.0)
 
 
 def test_colsum():

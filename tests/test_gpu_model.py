@@ -331,8 +331,9 @@ def test_train_infer_mask_app_jobs(tmp_path, model_name, capsys):
         assert os.path.exists(os.path.join(exp, 'netmodel', fn)), fn
     ck = checkpoint.load(os.path.join(exp, 'netmodel', 'sinet'))
     pre = model_name + '/cudnn_lstm/stack_bidirectional_rnn/cell_0/bidirectional_rnn/fw/cudnn_compatible_lstm_cell/'
-    assert ck[pre + 'kernel'].shape == (393 + 250, 1000) and ck[pre + 'kernel/Adam_1'].shape == (643, 1000)
-    assert int(ck[model_name + '/Variable']) == 9 and 'beta1_power' in ck
+    assert ck[pre + 'kernel'].shape == (393 + 250, 1000)
+    assert ck[model_name + '/' + pre + 'kernel/Adam_1'].shape == (643, 1000)       # slot scope nests in the model scope
+    assert int(ck[model_name + '/Variable']) == 9 and (model_name + '/optimizer/beta1_power') in ck
     # inference job: restores sinet, writes one wav per test utterance
     audio_out = str(tmp_path / 'audio')
     hole = inference.infer(os.path.join(exp, 'netmodel'), os.path.join(root, 'test-set'), audio_out, 'enh', batch_size=2)
@@ -455,7 +456,8 @@ def test_checkpoint_round_trip_through_tf_bundle(tmp_path):
     raw = tf_bundle.read_bundle(prefix)
     pre = 'cudnn_lstm/stack_bidirectional_rnn/cell_0/bidirectional_rnn/fw/cudnn_compatible_lstm_cell/kernel'
     assert any(k.endswith(pre) for k in raw) and any(k.endswith(pre + '/Adam_1') for k in raw)
-    assert abs(float(raw['beta1_power']) - 0.9 ** 3) < 1e-6
+    b1p = [k for k in raw if k.endswith('beta1_power')]
+    assert len(b1p) == 1 and abs(float(raw[b1p[0]]) - 0.9 ** 4) < 1e-6      # TF: beta1^(t+1) after t steps
     other, _, _, _ = _build('av-blstm-ssnn-ctc', 3, 11520, seed=10, ctc_loss=0.05)
     checkpoint.restore(other, prefix)
     assert torch.equal(other.engine.theta, model.engine.theta)
@@ -467,6 +469,53 @@ def test_checkpoint_round_trip_through_tf_bundle(tmp_path):
     other.feed(**{k: v for k, v in model._fed.items()})
     other.train_op()
     assert torch.allclose(other.engine.theta, model.engine.theta, rtol=0, atol=1e-5)
+
+
+def test_restore_reference_style_checkpoints(tmp_path):
+    """What a checkpoint written by the reference's TRAINING graph looks like to us: canonical weights (CudnnLSTMSaveable),
+    the global step, Adam slots of the opaque cuDNN blob only, float32 beta powers.  Weights and step restore, the
+    moments restart (warning), nothing raises KeyError; a checkpoint lacking a weight raises ValueError (what
+    training.py:154-166 catches); a momentum run saves and restores its accumulator."""
+    from avsi_b200 import checkpoint
+    model, batch, canon, inp = _build('av-blstm', 3, 2400, seed=12)
+    model.build_graph('av-blstm')
+    ref_like = {('av-blstm/' + k): np.asarray(v, np.float32) for k, v in canon.items()}
+    ref_like['av-blstm/Variable'] = np.asarray(1500, np.int32)
+    ref_like['av-blstm/av-blstm/cudnn_lstm/opaque_kernel/Adam'] = np.zeros(10, np.float32)
+    ref_like['av-blstm/av-blstm/cudnn_lstm/opaque_kernel/Adam_1'] = np.zeros(10, np.float32)
+    ref_like['av-blstm/optimizer/beta1_power'] = np.asarray(0.9 ** 1501, np.float32)          # underflows to 0
+    ref_like['av-blstm/optimizer/beta2_power'] = np.asarray(0.999 ** 1501, np.float32)
+    names = sorted(ref_like)
+    import json
+    arrays = {'v%05d' % i: ref_like[n] for i, n in enumerate(names)}
+    arrays['__names__'] = np.frombuffer(json.dumps(names).encode(), np.uint8)
+    np.savez(str(tmp_path / 'ref.npz'), **arrays)
+    checkpoint.restore(model, str(tmp_path / 'ref'))
+    assert model.global_step == 1500 and model.engine.step_count == 1500              # from `Variable`: beta1_power is 0
+    assert float(model.engine.adam_m.abs().max()) == 0.0
+    got = model.engine.export_canonical()
+    assert all(np.array_equal(got[k], np.asarray(canon[k], np.float32)) for k in canon)
+    ref_like['av-blstm/optimizer/beta1_power'] = np.asarray(0.9 ** 8, np.float32)             # a young checkpoint: t = 7
+    assert checkpoint._adam_step_from(ref_like, model) == 7
+    broken = dict(ref_like)
+    del broken['av-blstm/logits/weights']
+    names = sorted(broken)
+    arrays = {'v%05d' % i: broken[n] for i, n in enumerate(names)}
+    arrays['__names__'] = np.frombuffer(json.dumps(names).encode(), np.uint8)
+    np.savez(str(tmp_path / 'broken.npz'), **arrays)
+    with pytest.raises(ValueError):
+        checkpoint.restore(model, str(tmp_path / 'broken'))
+    # momentum accumulator round trip
+    mom, _, _, _ = _build('av-blstm', 3, 2400, seed=12, optimizer_type='momentum')
+    mom.build_graph('av-blstm')
+    mom.train_op()
+    mom.train_op()
+    checkpoint.save(mom, str(tmp_path / 'mom'))
+    other, _, _, _ = _build('av-blstm', 3, 2400, seed=13, optimizer_type='momentum')
+    other.build_graph('av-blstm')
+    checkpoint.restore(other, str(tmp_path / 'mom'))
+    assert torch.equal(other.engine.momentum_acc, mom.engine.momentum_acc) and float(mom.engine.momentum_acc.abs().max()) > 0
+    assert torch.equal(other.engine.theta, mom.engine.theta)
 
 
 def test_train_asr_job(tmp_path, capsys):

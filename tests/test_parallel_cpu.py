@@ -90,3 +90,66 @@ def test_shard_batch_rejects_ragged():
     assert parallel.shard_batch(8, 1, 4) == (2, 4)
     with pytest.raises(ValueError):
         parallel.shard_batch(10, 0, 4)
+
+
+def _lockstep_worker(rank, world, port, out):
+    """Ragged shards: rank 0 holds 5 full batches + a partial one, rank 1 holds 4 full batches.  Both must leave the
+    loop after 4 steps, having issued the same number of collectives (the all-reduce inside the loop must not hang)."""
+    import torch.distributed as dist
+    from avsi_b200 import parallel
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        bs = 3
+        n_full = 5 if rank == 0 else 4
+
+        def gen():
+            for i in range(n_full):
+                yield (np.arange(bs), 'full%d' % i)
+            if rank == 0:
+                yield (np.arange(bs - 1), 'partial')
+        steps, total = 0, torch.zeros(1, dtype=torch.float64)
+        for b in parallel.lockstep(gen(), bs, None, 'cpu'):
+            assert len(b[0]) == bs
+            g = torch.full((1,), float(rank + 1), dtype=torch.float64)
+            dist.all_reduce(g)                        # stands for the gradient all-reduce of the step
+            total += g
+            steps += 1
+        # a second epoch right after (validation pass): still in step
+        steps2 = sum(1 for _ in parallel.lockstep(iter([(np.arange(bs), 'v')] * (2 + rank)), bs, None, 'cpu'))
+        out[rank] = (steps, float(total), steps2)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_lockstep_drops_the_ragged_tail_on_every_rank_gloo_world2():
+    world = 2
+    ctx = mp.get_context('spawn')
+    mgr = ctx.Manager()
+    out = mgr.dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_lockstep_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert dict(out) == {0: (4, 12.0, 2), 1: (4, 12.0, 2)}
+
+
+def test_lockstep_is_plain_iteration_without_a_process_group():
+    from avsi_b200 import parallel
+    got = list(parallel.lockstep(iter([(np.arange(3),), (np.arange(2),)]), 3))
+    assert [len(b[0]) for b in got] == [3, 2]                 # single process: the partial batch is kept
+
+
+def test_shard_list_keeps_a_rank_consistent_shuffle():
+    import random
+    from avsi_b200 import parallel
+    files = ['f%02d' % i for i in range(10)]
+    shuffled = list(files)
+    random.Random(5).shuffle(shuffled)
+    a, b = parallel.shard_list(shuffled, 0, 2, keep_order=True), parallel.shard_list(shuffled, 1, 2, keep_order=True)
+    assert a == shuffled[0::2] and b == shuffled[1::2] and sorted(a + b) == files
+    assert parallel.shard_list(shuffled, 0, 2) == files[0::2]
