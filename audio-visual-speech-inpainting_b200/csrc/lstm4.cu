@@ -54,6 +54,9 @@ struct Lstm4Smem {
   unsigned long long afree[2];        // all 4 CTAs' chains of the step retired (multicast commit), by step parity
   unsigned long long staged[2];       // the 16 compute warps have written half p of h_t into the local A tile
   uint32_t tmem_slot;
+  // BULK variant: per-warp staging of one pass's activated gates [4 column chunks][32 rows][16 B] = the 2 KB run they
+  // occupy in the interleaved global layout, written to HBM by ONE cp.async.bulk per warp and pass
+  alignas(128) unsigned char gstage[L4_CWARPS][2048];
 };
 
 // ACT = 0: tanh.approx.f32 (1 MUFU per activation, 2^-11 relative -- the precision h_t is stored in)
@@ -81,7 +84,9 @@ __device__ unsigned long long g_l4_timing[16];
     }                                                      \
   } while (0)
 
-template <int ACT, bool TIMING>
+// BULK (B % 32 == 0: a warp's 32 rows are one row block of the interleaved layout): the activated gates leave through
+// shared memory + cp.async.bulk (async proxy) instead of 4 STG.128 per thread and pass
+template <int ACT, bool TIMING, bool BULK>
 __global__ void __cluster_dims__(L4_CL, 1, 1) __launch_bounds__(L4_THREADS, 1)
 lstm4_fwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whh, const float* __restrict__ bias,
                  uint16_t* __restrict__ y, float* __restrict__ cst, int T, int B, int PREFETCH, int y_il) {
@@ -237,41 +242,47 @@ lstm4_fwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whh,
 #pragma unroll
       for (int p = 0; p < 2; ++p) {
         const int ul0 = cg * 16 + p * 8;            // first local unit of this pass (a warp owns 16 contiguous units)
-        uint32_t acc[32];
-        if (s > 0) {
-          tmem_ld32(td + (uint32_t)(ul0 * 4), acc);
-          tmem_ld_wait();
-        } else {                                    // h_{-1} = 0: no chain ran, the bias comes from global memory once
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 b4 = *reinterpret_cast<const float4*>(bias + dir * L4_G + (j * 64 + ul0 + i) * 4);
-            acc[4 * i + 0] = __float_as_uint(b4.x);
-            acc[4 * i + 1] = __float_as_uint(b4.y);
-            acc[4 * i + 2] = __float_as_uint(b4.z);
-            acc[4 * i + 3] = __float_as_uint(b4.w);
-          }
-        }
         uint4 gout[4];
-        float cout[8], hout[8];
+        float hout[8];
+        // the 32 accumulator columns of a pass are read in two halves of 4 units: 16 live accumulator registers instead
+        // of 32 (with 17 warps per CTA the budget is 96 registers per thread; the 32-column read spilled, and the
+        // spill reloads queue behind the step's global stores in the LSU)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const uint4 pv = pre[p][i >> 1];
-          const float2 ig = unpack_half2((i & 1) ? pv.z : pv.x), fo = unpack_half2((i & 1) ? pv.w : pv.y);
-          const float gi = act_sigmoid_half<ACT>(__uint_as_float(acc[4 * i + 0]) + ig.x);
-          const float gg = act_tanh<ACT>(__uint_as_float(acc[4 * i + 1]) + ig.y);
-          const float gf = act_sigmoid_half<ACT>(__uint_as_float(acc[4 * i + 2]) + fo.x);
-          const float go = act_sigmoid_half<ACT>(__uint_as_float(acc[4 * i + 3]) + fo.y);
-          const float cc = fmaf(gf, c_state[p][i], gi * gg);
-          c_state[p][i] = cc;
-          cout[i] = cc;
-          hout[i] = go * act_tanh<ACT>(cc);
-          const uint32_t g0 = pack_half2(gi, gg), g1 = pack_half2(gf, go);
-          if (i & 1) {
-            gout[i >> 1].z = g0;
-            gout[i >> 1].w = g1;
-          } else {
-            gout[i >> 1].x = g0;
-            gout[i >> 1].y = g1;
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t acc[16];
+          if (s > 0) {
+            tmem_ld16(td + (uint32_t)((ul0 + 4 * hh) * 4), acc);
+            tmem_ld_wait();
+          } else {                                  // h_{-1} = 0: no chain ran, the bias comes from global memory once
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 b4 = *reinterpret_cast<const float4*>(bias + dir * L4_G + (j * 64 + ul0 + 4 * hh + i) * 4);
+              acc[4 * i + 0] = __float_as_uint(b4.x);
+              acc[4 * i + 1] = __float_as_uint(b4.y);
+              acc[4 * i + 2] = __float_as_uint(b4.z);
+              acc[4 * i + 3] = __float_as_uint(b4.w);
+            }
+          }
+#pragma unroll
+          for (int ii = 0; ii < 4; ++ii) {
+            const int i = 4 * hh + ii;
+            const uint4 pv = pre[p][i >> 1];
+            const float2 ig = unpack_half2((i & 1) ? pv.z : pv.x), fo = unpack_half2((i & 1) ? pv.w : pv.y);
+            const float gi = act_sigmoid_half<ACT>(__uint_as_float(acc[4 * ii + 0]) + ig.x);
+            const float gg = act_tanh<ACT>(__uint_as_float(acc[4 * ii + 1]) + ig.y);
+            const float gf = act_sigmoid_half<ACT>(__uint_as_float(acc[4 * ii + 2]) + fo.x);
+            const float go = act_sigmoid_half<ACT>(__uint_as_float(acc[4 * ii + 3]) + fo.y);
+            const float cc = fmaf(gf, c_state[p][i], gi * gg);
+            c_state[p][i] = cc;
+            hout[i] = go * act_tanh<ACT>(cc);
+            const uint32_t g0 = pack_half2(gi, gg), g1 = pack_half2(gf, go);
+            if (i & 1) {
+              gout[i >> 1].z = g0;
+              gout[i >> 1].w = g1;
+            } else {
+              gout[i >> 1].x = g0;
+              gout[i >> 1].y = g1;
+            }
           }
         }
         hv[p] = make_uint4(pack_half2(hout[0], hout[1]), pack_half2(hout[2], hout[3]),
@@ -288,15 +299,31 @@ lstm4_fwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whh,
           __syncwarp();
           if (lane == 0) mbar_arrive_local(staged_s + 8u * p);
         }
+        if (BULK) {
+          // the previous pass's bulk store of this warp has read the staging block (it was issued a whole pass ago)
+          if (lane == 0) bulk_wait_read0();
+          __syncwarp();
+          unsigned char* stg = &sm.gstage[w][0];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(stg + i * 512 + lane * 16) = gout[i];
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && row_ok) {               // lane 0 = first row of the block; B % 32 == 0: the warp is all valid or all out
+            bulk_store_s2g(gates + il16(grow, dir * L4_G + (j * 64 + ul0) * 4, 2 * L4_G), smem_u32(stg), 2048u);
+            bulk_commit();
+          }
+        }
         if (row_ok) {
           const int ug0 = j * 64 + ul0;
+          if (!BULK) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            *reinterpret_cast<uint4*>(gates + il16(grow, dir * L4_G + ug0 * 4 + 8 * i, 2 * L4_G)) = gout[i];
+            for (int i = 0; i < 4; ++i)
+              *reinterpret_cast<uint4*>(gates + il16(grow, dir * L4_G + ug0 * 4 + 8 * i, 2 * L4_G)) = gout[i];
+          }
           *reinterpret_cast<float4*>(cst + il32(grow, dir * L4_HP + ug0, 2 * L4_HP)) =
-              make_float4(cout[0], cout[1], cout[2], cout[3]);
+              make_float4(c_state[p][0], c_state[p][1], c_state[p][2], c_state[p][3]);
           *reinterpret_cast<float4*>(cst + il32(grow, dir * L4_HP + ug0 + 4, 2 * L4_HP)) =
-              make_float4(cout[4], cout[5], cout[6], cout[7]);
+              make_float4(c_state[p][4], c_state[p][5], c_state[p][6], c_state[p][7]);
         }
         L4_TICK(2 + p);
       }
@@ -315,6 +342,7 @@ lstm4_fwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whh,
 #pragma unroll
       for (int i = 0; i < 8; ++i) g_l4_timing[8 + i] = tacc[i];
     }
+    if (BULK && lane == 0) bulk_wait0();
   }
   tc_fence_before();
   cluster_sync_all();                                // no CTA exits while peers may still address its smem
@@ -329,21 +357,29 @@ int launch_lstm4_fwd(uint16_t* gates, const uint16_t* whh, const float* bias, ui
   // AVSI_LSTM_ACT=exact: ex2/rcp activations; AVSI_L4_TIMING=1: in-kernel phase timers (profiles/bench_lstm.py)
   AVSI_ENV_CACHE(mode, env_is("AVSI_LSTM_ACT", "exact") | (env_is("AVSI_L4_TIMING", "1") << 1));
   AVSI_ENV_CACHE(pf, env_is("AVSI_L4_PREFETCH", "0") ? 0 : 1);   // AVSI_L4_PREFETCH=0: no L2 prefetch of the next step (A/B runs)
+  AVSI_ENV_CACHE(bulk_env, env_int("AVSI_L4_BULK", 0));           // AVSI_L4_BULK=1: gates through shared memory + cp.async.bulk (measured: no gain, profiles/README.md)
+  const int bulk = (bulk_env && B % 32 == 0) ? 1 : 0;
   const int smem = (int)sizeof(Lstm4Smem) + 128;
   const int grid = 2 * ((B + L4_BT - 1) / L4_BT) * L4_CL;
-  static bool attr_done[4] = {false, false, false, false};
-#define L4_LAUNCH(ACT_, TIM_)                                                                                          \
+  static bool attr_done[8] = {false, false, false, false, false, false, false, false};
+#define L4_LAUNCH(ACT_, TIM_, BULK_)                                                                                    \
   do {                                                                                                                 \
-    if (!attr_done[mode]) {                                                                                            \
-      AVSI_CUDA(cudaFuncSetAttribute(lstm4_fwd_kernel<ACT_, TIM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-      attr_done[mode] = true;                                                                                          \
+    if (!attr_done[mode * 2 + BULK_]) {                                                                                \
+      AVSI_CUDA(cudaFuncSetAttribute(lstm4_fwd_kernel<ACT_, TIM_, BULK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+      attr_done[mode * 2 + BULK_] = true;                                                                              \
     }                                                                                                                  \
-    lstm4_fwd_kernel<ACT_, TIM_><<<grid, L4_THREADS, smem, st>>>(gates, whh, bias, y, cst, T, B, pf, y_il);                   \
+    lstm4_fwd_kernel<ACT_, TIM_, BULK_><<<grid, L4_THREADS, smem, st>>>(gates, whh, bias, y, cst, T, B, pf, y_il);      \
   } while (0)
-  if (mode == 0) L4_LAUNCH(0, false);
-  else if (mode == 1) L4_LAUNCH(1, false);
-  else if (mode == 2) L4_LAUNCH(0, true);
-  else L4_LAUNCH(1, true);
+#define L4_LAUNCH2(ACT_, TIM_)            \
+  do {                                    \
+    if (bulk) L4_LAUNCH(ACT_, TIM_, true); \
+    else L4_LAUNCH(ACT_, TIM_, false);    \
+  } while (0)
+  if (mode == 0) L4_LAUNCH2(0, false);
+  else if (mode == 1) L4_LAUNCH2(1, false);
+  else if (mode == 2) L4_LAUNCH2(0, true);
+  else L4_LAUNCH2(1, true);
+#undef L4_LAUNCH2
 #undef L4_LAUNCH
   AVSI_LAUNCH_CHECK();
   return AVSI_OK;

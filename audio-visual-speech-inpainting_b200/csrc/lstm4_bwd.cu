@@ -62,7 +62,10 @@ __device__ unsigned long long g_b4_timing[24];
     }                                                      \
   } while (0)
 
-template <bool TIMING>
+// LATE: the second half's inputs are requested AFTER the first half's A-tile hand-over instead of before it.
+// fence.proxy.async compiles to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC (ptxas 12.9): issued ahead of the hand-over, the loads
+// in flight would have to return before the fence retires, i.e. before the first MMA chain can start.
+template <bool TIMING, bool LATE>
 __global__ void __cluster_dims__(B4_CL, 1, 1) __launch_bounds__(B4_THREADS, 1)
 lstm4_bwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whhT, const float* __restrict__ cst,
                  const uint16_t* __restrict__ dy, float* __restrict__ dbias, int T, int B) {
@@ -323,7 +326,7 @@ lstm4_bwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whhT
             pk[i >> 1].y = p1;
           }
         }
-        if (h == 0) load_inputs(1, g4, cprev, dyv);   // second half's inputs: in flight during the A-half hand-over
+        if (!LATE && h == 0) load_inputs(1, g4, cprev, dyv);   // second half's inputs: in flight during the A-half hand-over
         if (has_prev) {                               // park c_{t_prev} and dc for the next step
           tmem_st8(trow + B4_TM_C + (uint32_t)ul0, cnew);
           tmem_st8(trow + B4_TM_DC + (uint32_t)ul0, dnew);
@@ -349,6 +352,7 @@ lstm4_bwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whhT
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_local(stagedA_s + 8u * h);
+        if (LATE && h == 0) load_inputs(1, g4, cprev, dyv);    // L2 hits (prefetched a step ahead), under the first MMA chain
         B4_TICK(2 + 2 * h);
       }
       // ---- the partial of this step: other owners' columns -> fp16 staging -> (control thread) DSMEM push ----
@@ -411,17 +415,24 @@ int launch_lstm4_bwd(uint16_t* gates, const uint16_t* whhT, const float* cst, co
                      int B, cudaStream_t st) {
   AVSI_ENV_CACHE(timing, env_is("AVSI_B4_TIMING", "1"));   // in-kernel phase timers (profiles/bench_lstm.py)
   const int smem = (int)sizeof(Lstm4BwdSmem) + 128;
+  AVSI_ENV_CACHE(late, env_int("AVSI_B4_LATE", 0));        // AVSI_B4_LATE=1: second half's loads after the hand-over (measured 3 % slower, profiles/README.md)
   static bool attr_done = false;
   if (!attr_done) {
-    AVSI_CUDA(cudaFuncSetAttribute(lstm4_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    AVSI_CUDA(cudaFuncSetAttribute(lstm4_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    AVSI_CUDA(cudaFuncSetAttribute(lstm4_bwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    AVSI_CUDA(cudaFuncSetAttribute(lstm4_bwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    AVSI_CUDA(cudaFuncSetAttribute(lstm4_bwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    AVSI_CUDA(cudaFuncSetAttribute(lstm4_bwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_done = true;
   }
   const int grid = 2 * ((B + B4_BT - 1) / B4_BT) * B4_CL;
-  if (timing)
-    lstm4_bwd_kernel<true><<<grid, B4_THREADS, smem, st>>>(gates, whhT, cst, dy, dbias, T, B);
+  if (timing && late)
+    lstm4_bwd_kernel<true, true><<<grid, B4_THREADS, smem, st>>>(gates, whhT, cst, dy, dbias, T, B);
+  else if (timing)
+    lstm4_bwd_kernel<true, false><<<grid, B4_THREADS, smem, st>>>(gates, whhT, cst, dy, dbias, T, B);
+  else if (late)
+    lstm4_bwd_kernel<false, true><<<grid, B4_THREADS, smem, st>>>(gates, whhT, cst, dy, dbias, T, B);
   else
-    lstm4_bwd_kernel<false><<<grid, B4_THREADS, smem, st>>>(gates, whhT, cst, dy, dbias, T, B);
+    lstm4_bwd_kernel<false, false><<<grid, B4_THREADS, smem, st>>>(gates, whhT, cst, dy, dbias, T, B);
   AVSI_LAUNCH_CHECK();
   return AVSI_OK;
 }

@@ -226,4 +226,17 @@ __device__ __forceinline__ void bulk_copy_to_cta(uint32_t remote_dst, uint32_t l
                ::"r"(remote_dst), "r"(local_src), "r"(bytes), "r"(remote_mbar) : "memory");
 }
 
+// bulk store: local shared -> global through the async proxy (TMA engine), tracked by the thread's bulk async-group.
+// The generic-proxy writes that filled the source must be followed by fence.proxy.async before this is issued.
+__device__ __forceinline__ void bulk_store_s2g(void* gdst, uint32_t local_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(local_src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed bulk groups of this thread have finished READING their shared-memory source (it may be overwritten)
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 }  // namespace avsi

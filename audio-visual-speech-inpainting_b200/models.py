@@ -160,6 +160,28 @@ class StackedBLSTMModel(object):
                 raise _lib.AvsiError('tensor %r has not been fed' % n)
         return [self._fed[n] for n in names]
 
+    def _check_shapes(self, wav, masks, mean, std, seq, video):
+        """What TensorFlow's shape inference / concat checks catch in the reference graph; here the kernels take raw
+        pointers, so a mismatch would be an out-of-bounds read.  Values (labels, lengths) are clamped in the kernels."""
+        B, F = wav.shape[0], self.audio_feat_dim
+        if wav.dim() != 2 or masks.dim() != 3 or masks.shape[0] != B or masks.shape[2] != F:
+            raise ValueError('target_sources must be [B,N] and masks [B,T,%d]; got %s and %s'
+                             % (F, tuple(wav.shape), tuple(masks.shape)))
+        if mean.numel() != F or std.numel() != F:
+            raise ValueError('audio_features_mean / _std must hold %d values' % F)
+        if seq.numel() != B:
+            raise ValueError('sequence_lengths must hold one entry per utterance')
+        if video is not None and (video.dim() != 3 or tuple(video.shape[:2]) != tuple(masks.shape[:2])
+                                  or video.shape[2] != self.video_feat_dim):
+            raise ValueError('video_features must be [B,T,%d] with the B, T of masks; got %s vs masks %s'
+                             % (self.video_feat_dim, tuple(video.shape), tuple(masks.shape)))
+        if self.MTL or 'labels' in self._fed:
+            labels, lab_len = self._fed.get('labels'), self._fed.get('labels_lengths')
+            if labels is not None and (labels.dim() != 2 or labels.shape[0] != B):
+                raise ValueError('labels must be [B,Lmax]')
+            if lab_len is not None and lab_len.numel() != B:
+                raise ValueError('labels_lengths must hold one entry per utterance')
+
     # ---- front end (models.py:30-45) -----------------------------------------------------------------
     def _front(self, want_stft=False):
         key = 'front_stft' if want_stft else 'front'
@@ -172,6 +194,7 @@ class StackedBLSTMModel(object):
         video = self._fed.get('video_features') if self.input_type in ('v', 'av') else None
         if self.input_type != 'a' and video is None:
             raise _lib.AvsiError("video_features must be fed for input='%s'" % self.input_type)
+        self._check_shapes(wav, masks, mean, std, seq, video)
         ws = self.engine.workspace(T, B, self.is_training)
         hole = None
         if self.MTL:
@@ -327,14 +350,16 @@ class StackedBLSTMModel(object):
         """forward + loss + backward; leaves the (scaled) gradient in engine.grad."""
         if not self.is_training:
             raise _lib.AvsiError('model was built with is_training=False')
-        if self._stale:
-            # the weights moved since these activations were computed (train_op without a new feed): run again.
+        if self._stale or self._cache.get('bwd_done'):
+            # the weights moved since these activations were computed (train_op without a new feed), or a previous
+            # backward pass on this feed has already overwritten the stashed gates in place with dG: run again.
             # Reads between the two calls keep returning the values of the run that produced the update, as
             # sess.run([train_op, loss]) does
             self._cache = {k: v for k, v in self._cache.items() if k.startswith('front')}
             self._stale = False
         out = self._loss_pass(True, want_pred=False)
         self.engine.backward(self._front()['ws'])
+        self._cache['bwd_done'] = True
         return out
 
     def _reduce_gradients(self, out):

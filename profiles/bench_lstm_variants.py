@@ -1,0 +1,67 @@
+#!/usr/bin/env python
+"""A/B of the tcgen05 recurrence kernels' store paths: plain STG stores vs shared-memory
+staging + cp.async.bulk for the forward kernel's gates (AVSI_L4_BULK), and the position of the BPTT kernel's
+second-half loads relative to its proxy fence (AVSI_B4_LATE), one layer, CUDA events, same box, same process.  Also checks that
+both variants write bit-identical tensors.    usage: python profiles/bench_lstm_variants.py [T] [B1,B2,...]"""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from avsi_b200 import _lib
+
+lib = _lib.load()
+d = torch.device('cuda:0')
+T = int(sys.argv[1]) if len(sys.argv) > 1 else 250
+BS = [int(x) for x in (sys.argv[2] if len(sys.argv) > 2 else '2048').split(',')]
+out = []
+for B in BS:
+    Mp = -(-T * B // 32) * 32
+    g0 = torch.randn(Mp, 2048, device=d).half()
+    whh = (torch.randn(2048, 256, device=d) * 0.05).half()
+    whhT = whh.t().contiguous()
+    bias = torch.zeros(2048, device=d)
+    dy = torch.randn(Mp, 512, device=d).half()
+    scratch = torch.empty(16, device=d)
+    ref = {}
+    variants = [('stg', dict(AVSI_L4_BULK=0, AVSI_B4_LATE=0)), ('stg+late', dict(AVSI_L4_BULK=0, AVSI_B4_LATE=1)),
+                ('bulk+late', dict(AVSI_L4_BULK=1, AVSI_B4_LATE=1))]
+    for name, env in variants + variants:
+        _lib.set_env(AVSI_LSTM_FWD='l4', AVSI_LSTM_BWD='l4', **env)
+        gates = g0.clone()
+        y = torch.zeros(T * B, 512, dtype=torch.float16, device=d)
+        cst = torch.zeros(Mp, 512, device=d)
+        dbias = torch.zeros(2048, device=d)
+        res = {'fwd': [], 'bwd': []}
+        for it in range(6):
+            gates.copy_(g0)
+            dbias.zero_()
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            e[0].record()
+            _lib.check(lib.avsi_lstm_fwd(_lib.ptr(gates), _lib.ptr(whh), _lib.ptr(bias), _lib.ptr(y), _lib.ptr(cst), T, B, 0,
+                                         _lib.stream_ptr()))
+            e[1].record()
+            if it == 5:
+                torch.cuda.synchronize()
+                act = gates.clone()
+            _lib.check(lib.avsi_lstm_bwd(_lib.ptr(gates), _lib.ptr(whhT), _lib.ptr(cst), _lib.ptr(dy), _lib.ptr(dbias),
+                                         _lib.ptr(scratch), T, B, _lib.stream_ptr()))
+            e[2].record()
+            torch.cuda.synchronize()
+            if 2 <= it < 5:
+                res['fwd'].append(e[0].elapsed_time(e[1]))
+                res['bwd'].append(e[1].elapsed_time(e[2]))
+        cur = dict(act=act, y=y.clone(), c=cst.clone(), dg=gates.clone(), db=dbias.clone())
+        same = None
+        if ref:
+            same = {k: bool(torch.equal(cur[k], ref[k])) for k in ('act', 'y', 'c', 'dg')}
+            same['db_close'] = bool(torch.allclose(cur['db'], ref['db'], rtol=1e-3, atol=1e-2))
+        else:
+            ref = cur
+        row = dict(B=B, T=T, variant=name, fwd_ms=min(res['fwd']), bwd_ms=min(res['bwd']),
+                   fwd_us_step=1e3 * min(res['fwd']) / T, bwd_us_step=1e3 * min(res['bwd']) / T, same_as_first=same)
+        out.append(row)
+        print(json.dumps(row), flush=True)
+_lib.set_env(AVSI_LSTM_FWD=None, AVSI_LSTM_BWD=None, AVSI_L4_BULK=None, AVSI_B4_LATE=None)

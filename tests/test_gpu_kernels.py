@@ -429,6 +429,66 @@ def test_ctc_matches_oracle():
         assert np.all(g[:, :, :col0] == 5.0) and np.all(g[:, :, col0 + C:] == 5.0)
 
 
+def test_ctc_long_utterance_gradient_precision():
+    """20 s utterances (T = 1667, BASELINE configs[4]): log alpha reaches ~ -5800, where an fp32 ulp is 5e-4, and the
+    recursion is a 1667-link chain.  The kernel re-centres alpha / beta every few frames with the shifts kept in double and
+    uses the accurate expf / log1pf: the gradient stays within 3e-4 of the float64 oracle for peaked (std 2) and for
+    near-uniform (std 0.3, a randomly initialised head) logits -- it was 6e-3 without the re-centring and 2e-3 with the
+    fast exponential -- and the NLL within 1e-6 relative."""
+    from avsi_b200 import _lib
+    from oracle import ctc as octc
+    lib = _lib.load()
+    rng = np.random.default_rng(8)
+    d = dev()
+    T, B, C, Lmax = 1667, 3, 34, 50
+    lab_len = np.array([24, 12, 1], np.int32)
+    labels = np.zeros((B, Lmax), np.int32)
+    for b in range(B):
+        labels[b, :lab_len[b]] = rng.integers(0, C - 1, lab_len[b])
+    seq = np.array([T, T - 100, T], np.int32)
+    ldl = 64
+    tl, tn, ts = (torch.from_numpy(a).to(d) for a in (labels, lab_len, seq))
+    ws = torch.empty(int(lib.avsi_ctc_workspace_bytes(B, T, Lmax)) // 4 + 4, device=d)
+    for std in (0.3, 2.0):
+        logits = (rng.standard_normal((T, B, C)) * std).astype(np.float32)
+        lg = torch.zeros(T * B, ldl, device=d)
+        lg[:, :C] = torch.from_numpy(logits.reshape(T * B, C)).to(d)
+        nll = torch.empty(B, device=d)
+        dl = torch.zeros(T * B, ldl, dtype=torch.float16, device=d)
+        _lib.check(lib.avsi_ctc_loss(_lib.ptr(lg), ldl, 0, C, _lib.ptr(tl), Lmax, _lib.ptr(tn), _lib.ptr(ts), B, T, 8.0,
+                                     None, _lib.ptr(nll), _lib.ptr(dl), ldl, 0, _lib.ptr(ws), _lib.stream_ptr()), 'ctc')
+        sync()
+        x = torch.tensor(logits.astype(np.float64), requires_grad=True)
+        rn = octc.ctc_nll_torch(x, torch.from_numpy(labels).long(), torch.from_numpy(lab_len), torch.from_numpy(seq))
+        rn.sum().backward()
+        rg = x.grad.numpy()
+        assert np.allclose(nll.cpu().numpy(), rn.detach().numpy(), rtol=1e-6, atol=0), std
+        g = dl.cpu().numpy().astype(np.float64).reshape(T, B, ldl)[:, :, :C] / 8.0
+        assert rel_l2(g, rg) < 3e-4, (std, rel_l2(g, rg))                       # fp16 storage of the result: 2^-11 per entry
+        assert rel_l2(g.sum(0), rg.sum(0)) < 3e-4, (std, rel_l2(g.sum(0), rg.sum(0)))   # what the asr bias gradient sees
+    # a label outside [0, C - 1) (TF: InvalidArgument): that utterance alone comes back infeasible, nothing is corrupted
+    bad = labels.copy()
+    bad[1, 3] = C + 1000
+    bad[2, 0] = -5
+    tb = torch.from_numpy(bad).to(d)
+    nll2 = torch.empty(B, device=d)
+    dl2 = torch.ones(T * B, ldl, dtype=torch.float16, device=d)
+    _lib.check(lib.avsi_ctc_loss(_lib.ptr(lg), ldl, 0, C, _lib.ptr(tb), Lmax, _lib.ptr(tn), _lib.ptr(ts), B, T, 8.0,
+                                 None, _lib.ptr(nll2), _lib.ptr(dl2), ldl, 0, _lib.ptr(ws), _lib.stream_ptr()), 'ctc')
+    sync()
+    n2 = nll2.cpu().numpy()
+    assert np.isinf(n2[1]) and np.isinf(n2[2]) and abs(n2[0] - float(nll[0])) < 1e-3
+    g2 = dl2.float().view(T, B, ldl)
+    assert float(g2[:, 1:, :C].abs().max()) == 0.0 and torch.equal(g2[:, 0, :C], dl.float().view(T, B, ldl)[:, 0, :C])
+    x = torch.tensor(logits.astype(np.float64), requires_grad=True)
+    rn = octc.ctc_nll_torch(x, torch.from_numpy(labels).long(), torch.from_numpy(lab_len), torch.from_numpy(seq))
+    rn.sum().backward()
+    rg = x.grad.numpy()
+    assert np.allclose(nll.cpu().numpy(), rn.detach().numpy(), rtol=1e-6, atol=0)
+    g = dl.cpu().numpy().astype(np.float64).reshape(T, B, ldl)[:, :, :C] / 8.0
+    assert rel_l2(g, rg) < 1e-3, rel_l2(g, rg)
+
+
 def test_adam_tf_and_cast():
     from avsi_b200 import _lib
     from oracle import adam as oadam
