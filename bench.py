@@ -8,7 +8,10 @@ A step = one pass of the hot path over one synthetic GRID-shaped batch (3 s, 16 
 frames): landmark upsampling + motion vectors -> fused STFT front end -> 3-layer BLSTM forward ->
 masked-L1 -> BPTT -> (NCCL gradient all-reduce) -> TF-form Adam.  `value` times it with inputs
 resident in HBM; `e2e` times the same step through the public model API from pinned HOST buffers
-(H2D of wav / mask / landmarks and D2H of the loss inside the timed region).  Prints ONE JSON line.
+(H2D of wav / mask / landmarks and D2H of the loss inside the timed region) with the reference's fp32 placeholder
+dtypes (training.py:69-71), `e2e_compact` the same with the samples / masks crossing PCIe as int16 / uint8.
+`extra` holds few-step runs of the other BASELINE configurations on the same GPUs: AV-MTL-SI (configs[2]),
+20 s utterances (configs[4]) and the batch sweep of configs[1].  Prints ONE JSON line.
 """
 import argparse
 import json
@@ -23,7 +26,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = 'AV-SI training utterances/sec'
 UNIT = 'utterances/s'
-CPU_SAMPLE_B = 8
+CPU_SAMPLE_B = 64          # utterances per CPU-arm step (the largest batch whose step stays within seconds on 16 cores)
 
 
 def parse_args():
@@ -36,9 +39,9 @@ def parse_args():
     ap.add_argument('--audio-len', type=int, default=48000)
     ap.add_argument('--model', default='av-blstm')
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--e2e-fp32', action='store_true',
-                    help='stage the e2e host batch as fp32 wav / fp32 mask (the reference placeholder dtypes) instead of '
-                         'the storage dtypes int16 / uint8')
+    ap.add_argument('--no-extras', action='store_true', help='skip the few-step runs of configs[2] / [4] / batch sweep')
+    ap.add_argument('--long-batch', type=int, default=int(os.environ.get('AVSI_BENCH_LONG_BATCH', 2048)),
+                    help='utterances per GPU of the 20 s extra (configs[4])')
     return ap.parse_args()
 
 
@@ -114,7 +117,7 @@ def cpu_baseline(args, steps=1, warmup=0):
     b['video'] = np.stack([ovideo.video_features(b['landmarks'][i].astype(np.float64), b['T'], b['vmean'][i], b['vstd'][i])
                            for i in range(B)]).astype(np.float32)
     ups, cores, dt = cpu_port.time_train_steps(b, steps=steps, warmup=warmup)
-    return {'value': ups, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+    return {'value': ups, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample_batch': B,
             'sample': '%d step(s) of a %d-utterance AV-SI train step (fwd+bwd+Adam, fp32 torch-CPU port of the '
                       'reference TF graph; TF 1.x itself is not installable here), %.2f s/step' % (steps, B, dt)}, dt
 
@@ -123,11 +126,13 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    cb, dt = cpu_baseline(args, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    cb, dt = cpu_baseline(args, steps=max(1, min(args.steps, 4)), warmup=min(args.warmup, 1))
     line = {'impl': 'reference', 'metric': METRIC, 'value': cb['value'], 'unit': UNIT, 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': workload_config(args, max(1, args.gpus)),       # the arm's workload; each step times a bounded sample of it
+            # the GPU arm's workload; each CPU step times a bounded sample of it (cpu_baseline.sample_batch utterances, not
+            # batch_per_gpu: a 2048-utterance step would take ~2 minutes on these cores) -- `same_config` is by workload only
+            'config': dict(workload_config(args, max(1, args.gpus)), cpu_sample_batch=CPU_SAMPLE_B),
             'cpu_baseline': cb,
             'e2e': {'value': cb['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line))
@@ -149,6 +154,225 @@ def workload_config(args, world):
             'parallelism': 'dp%d' % world,
             'l2_policy': 'inputs larger than L2 (wav+mask %.0f MB per step, activations %.1f GB)'
                          % (B * (N + T * 257) * 4 / 1e6, T * B * (3 * 2048 * 2 + 3 * 512 * 6) / 1e9)}
+
+
+class Workload(object):
+    """One synthetic GRID-shaped workload on this rank's GPU: host batch, resident copies, model, the resident step and
+    the end-to-end step (inputs from pinned HOST buffers every step, loss read back every step)."""
+    E2E_KEYS = ('wav', 'mask', 'landmarks', 'vmean', 'vstd', 'seq_len')
+
+    def __init__(self, model_name, B, audio_len, pg, dev, rank, world, unique=None, want_e2e=False):
+        import numpy as np
+        import torch
+        from avsi_b200 import _lib, av_sync, models, synth
+        self.torch, self._lib, self.av_sync = torch, _lib, av_sync
+        self.B, self.pg, self.dev, self.world = B, pg, dev, world
+        n_unique = min(B, unique) if unique else B
+        host = synth.make_batch(n_unique, audio_len=audio_len, seed=rank)      # rank-offset data, identical weights
+        self.T = T = host['T']
+        cfg = synth.default_config(model_name, batch_size=B * world, audio_len=audio_len)
+        keys = ('wav', 'mask', 'landmarks', 'vmean', 'vstd', 'seq_len', 'mean', 'std')
+        if n_unique == B:
+            self.host = host
+            self.pin = {k: torch.from_numpy(np.ascontiguousarray(host[k])).pin_memory() for k in keys} if want_e2e else None
+            self.res = {k: (self.pin[k] if want_e2e else torch.from_numpy(np.ascontiguousarray(host[k]))).to(dev) for k in keys}
+        else:
+            # long utterances: a few distinct utterances tiled over the batch ON THE DEVICE (drawing 2048 x 320000 samples
+            # on the host takes longer than the timed steps); every kernel still processes B distinct rows of memory
+            assert not want_e2e
+            self.host, self.pin = host, None
+            idx = torch.arange(B, device=dev) % n_unique
+            small = {k: torch.from_numpy(np.ascontiguousarray(host[k])).to(dev) for k in keys}
+            self.res = {k: (small[k][idx].contiguous() if k not in ('mean', 'std') else small[k]) for k in keys}
+        self.cls, self.inp = models.MODEL_REGISTRY[model_name]
+        res = self.res
+        video = self.video_of(res) if self.inp != 'a' else None
+        if self.cls.MTL:                              # configs[2]: AV-MTL-SI, joint CTC phone head (labels stay resident)
+            lab = np.ascontiguousarray(host['labels'][np.arange(B) % n_unique])
+            ll = np.ascontiguousarray(host['lab_len'][np.arange(B) % n_unique])
+            self.labels, self.lab_len = torch.from_numpy(lab).to(dev), torch.from_numpy(ll).to(dev)
+            self.model = self.cls(res['seq_len'], self.lab_len, res['wav'], res['mask'], self.labels, res['mean'], res['std'],
+                                  0.0, cfg, video_features=video, input=self.inp, is_training=True, device=dev, process_group=pg)
+        else:
+            self.model = self.cls(res['seq_len'], res['wav'], res['mask'], res['mean'], res['std'], 0.0, cfg,
+                                  video_features=video, input=self.inp, is_training=True, device=dev, process_group=pg)
+
+    def video_of(self, src):
+        with self._lib.span('video_features'):
+            return self.av_sync.video_pipeline(src['landmarks'], self.T, src['vmean'], src['vstd'], device=self.dev)
+
+    def step_resident(self):
+        res = self.res
+        self.model.feed(sequence_lengths=res['seq_len'], target_sources=res['wav'], masks=res['mask'],
+                        video_features=self.video_of(res) if self.inp != 'a' else None)
+        self.model.train_op()
+
+    def timed(self, fn, steps, profile=False):
+        """K calls of fn bracketed by barrier + synchronize on both sides, CUDA events, MAX over ranks."""
+        import torch.distributed as dist
+        torch, _lib = self.torch, self._lib
+        torch.cuda.synchronize()
+        if self.pg is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = _lib.launch_count()
+        if profile:
+            _lib.profile_start()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        prof = _lib.profile_stop() if profile else None
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=self.dev)
+        if self.pg is not None:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), _lib.launch_count() - n0, prof
+
+    def run_resident(self, steps, warmup, profile=True):
+        for _ in range(max(warmup, 3)):
+            self.step_resident()
+        return self.timed(self.step_resident, steps, profile=profile)
+
+    def run_e2e(self, steps, fp32):
+        """End-to-end steps: every step's inputs come from pinned HOST buffers (H2D inside the timed region) and every
+        step's loss is read back to the host.  The copy of step k+1 runs on a side stream while step k computes (two
+        device staging sets) and the loss of step k is fetched one step late (pinned, non-blocking), so that neither
+        transfer stalls the kernels.  fp32 = True stages the placeholders of training.py:69-71 as they are (fp32 samples,
+        fp32 masks); False stages the storage dtypes (int16 samples as in target.wav / dataset_reader.py:78, uint8 {0,1}
+        masks), widened to the fp32 feed tensors on the device (avsi_cast_to_f32, inside the timed step).
+        Returns (ms, h2d bytes per step, host dtypes, losses)."""
+        import numpy as np
+        torch = self.torch
+        model, dev, inp = self.model, self.dev, self.inp
+        pin = dict(self.pin)
+        if not fp32:
+            pin['wav'] = torch.from_numpy(self.host['wav'].astype(np.int16)).pin_memory()
+            pin['mask'] = torch.from_numpy(self.host['mask'].astype(np.uint8)).pin_memory()
+        keys = self.E2E_KEYS
+        copy_stream = torch.cuda.Stream(device=dev)
+        stage = [{k: torch.empty(pin[k].shape, dtype=pin[k].dtype, device=dev) for k in keys} for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        freed = [torch.cuda.Event() for _ in range(2)]
+        loss_pin = torch.zeros(2, dtype=torch.float64).pin_memory()
+        loss_evt = [torch.cuda.Event() for _ in range(2)]
+        st = {'i': 0, 'losses': []}
+
+        def prefetch(i):
+            sl = i % 2
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(freed[sl])                 # the step that last used this staging set is done
+                for k in keys:
+                    stage[sl][k].copy_(pin[k], non_blocking=True)
+                ready[sl].record(copy_stream)
+
+        def reset():
+            torch.cuda.synchronize()
+            st['i'] = 0
+            for sl in range(2):
+                freed[sl].record(torch.cuda.current_stream())
+            prefetch(0)
+
+        def step():
+            i = st['i']
+            sl = i % 2
+            cur = torch.cuda.current_stream()
+            prefetch(i + 1)                                       # next step's H2D overlaps this step's kernels
+            cur.wait_event(ready[sl])
+            d = stage[sl]
+            model.feed(sequence_lengths=d['seq_len'], target_sources=d['wav'], masks=d['mask'],
+                       video_features=self.video_of(d) if inp != 'a' else None)
+            model.train_op()
+            freed[sl].record(cur)
+            n = model.engine.layout.n_params_padded
+            src = model.engine.grad[n + 4:n + 5].double() if self.pg is not None else \
+                model._loss_pass(True, want_pred=False)['sums'][4:5]
+            if i > 0:                                             # read the previous step's loss (already on the host)
+                loss_evt[1 - sl].synchronize()
+                st['losses'].append(float(loss_pin[1 - sl]))
+            loss_pin[sl:sl + 1].copy_(src, non_blocking=True)
+            loss_evt[sl].record(cur)
+            st['i'] = i + 1
+
+        def drain():
+            i = st['i']
+            if i > 0:
+                loss_evt[(i - 1) % 2].synchronize()
+                st['losses'].append(float(loss_pin[(i - 1) % 2]))
+
+        reset()
+        for _ in range(2):
+            step()
+        drain()
+        reset()                                                   # the first H2D of the timed run is inside the region's lead-in
+        st['losses'] = []
+
+        def run():
+            step()
+            if st['i'] == steps:
+                drain()
+        ms, _, _ = self.timed(run, steps)
+        torch.cuda.current_stream().wait_stream(copy_stream)
+        torch.cuda.synchronize()
+        if not all(np.isfinite(x) for x in st['losses']):
+            raise SystemExit('bench: non-finite loss fetched in the end-to-end steps: %r' % st['losses'][-3:])
+        h2d = sum(pin[k].numel() * pin[k].element_size() for k in keys)
+        dtypes = {k: str(pin[k].dtype).replace('torch.', '') for k in ('wav', 'mask', 'landmarks')}
+        return ms, h2d, dtypes, st['losses']
+
+    def close(self):
+        torch = self.torch
+        self.model = self.res = self.pin = self.host = None
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+
+
+def kernel_table(prof, steps):
+    kernels = {}
+    tot = sum(v['ms'] for v in prof.values()) or 1.0
+    for name, v in sorted(prof.items(), key=lambda kv: -kv[1]['ms']):
+        kernels[name] = {'ms_per_step': v['ms'] / steps, 'share': v['ms'] / tot, 'launches_per_step': v['launches'] / steps}
+    return kernels
+
+
+def library_digest():
+    """sha256 of the CUDA sources the in-tree library was built from (the build stamp); ncu-derived figures carry it."""
+    try:
+        return open(os.path.join(ROOT, 'audio-visual-speech-inpainting_b200', 'csrc', 'build', 'stamp.txt')).read().strip()[:16]
+    except Exception:
+        return None
+
+
+def run_extras(args, pg, dev, rank, world, pk):
+    """Few-step runs of the other BASELINE configurations on the same GPUs (resident inputs, CUDA events, max over ranks):
+    configs[2] AV-MTL-SI with the CTC phone head, configs[4] 20 s utterances, and the batch sweep of configs[1]."""
+    out = {}
+    flop_utt = {48000: 6.62e9}
+
+    def one(tag, model_name, B, audio_len, steps, unique=None):
+        wl = Workload(model_name, B, audio_len, pg, dev, rank, world, unique=unique)
+        ms, launches, prof = wl.run_resident(steps, 3)
+        T = wl.T
+        wl.close()
+        utt = B * world * steps
+        r = {'model': model_name, 'batch_per_gpu': B, 'global_batch': B * world, 'frames': T, 'steps': steps,
+             'value': utt / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms / steps, 'gpu_launches': launches,
+             'kernels': {k: round(v['ms_per_step'], 3) for k, v in list(kernel_table(prof, steps).items())[:6]}}
+        # whole-step fraction of the tensor roofline: 6.62 GFLOP per 3 s AV-SI utterance (SURVEY.md 8d), linear in T
+        r['frac_of_tensor_roofline'] = r['value'] / world * 6.62e9 * (T / 250.0) / (pk['bf16_tflops_sustained'] * 1e12)
+        out[tag] = r
+    one('mtl', 'av-blstm-ssnn-ctc', args.batch, 48000, 4)
+    one('long_utterance', 'av-blstm', args.long_batch, 320000, 3, unique=64)
+    sweep = {}
+    for b in (8, 32, 128, 512):
+        wl = Workload(args.model, b, 48000, pg, dev, rank, world)
+        ms, _, _ = wl.run_resident(6, 3, profile=False)
+        wl.close()
+        sweep[str(b)] = {'value': b * world * 6 / (ms * 1e-3), 'ms_per_step': ms / 6}
+    out['batch_sweep'] = {'workload': 'configs[1] at other per-GPU batch sizes (B <= 224: mma.sync recurrence kernels)', 'unit': UNIT,
+                          'per_gpu_batch': sweep}
+    return out
 
 
 def main():
@@ -175,167 +399,52 @@ def main():
     if world > 1:
         dist.barrier()
         pg = dist.group.WORLD
-    from avsi_b200 import _lib, av_sync, models, synth
     dev = torch.device('cuda', local_rank)
     B = args.batch
-    host = synth.make_batch(B, audio_len=args.audio_len, seed=rank)      # rank-offset data, identical weights
-    T = host['T']
-    cfg = synth.default_config(args.model, batch_size=B * world, audio_len=args.audio_len)
-    pin = {k: torch.from_numpy(np.ascontiguousarray(host[k])).pin_memory()
-           for k in ('wav', 'mask', 'landmarks', 'vmean', 'vstd', 'seq_len', 'mean', 'std')}
-    res = {k: v.to(dev) for k, v in pin.items()}
-
-    def video_of(src):
-        with _lib.span('video_features'):
-            return av_sync.video_pipeline(src['landmarks'], T, src['vmean'], src['vstd'], device=dev)
-
-    cls, inp = models.MODEL_REGISTRY[args.model]
-    mtl = {}
-    if cls.MTL:                                   # configs[2]: AV-MTL-SI, joint CTC phone head (labels stay resident)
-        mtl = {'labels': torch.from_numpy(host['labels']).to(dev), 'lab_len': torch.from_numpy(host['lab_len']).to(dev)}
-        model = cls(res['seq_len'], mtl['lab_len'], res['wav'], res['mask'], mtl['labels'], res['mean'], res['std'], 0.0, cfg,
-                    video_features=video_of(res) if inp != 'a' else None, input=inp, is_training=True, device=dev,
-                    process_group=pg)
-    else:
-        model = cls(res['seq_len'], res['wav'], res['mask'], res['mean'], res['std'], 0.0, cfg,
-                    video_features=video_of(res) if inp != 'a' else None, input=inp, is_training=True, device=dev,
-                    process_group=pg)
-
-    def step_resident():
-        model.feed(sequence_lengths=res['seq_len'], target_sources=res['wav'], masks=res['mask'],
-                   video_features=video_of(res) if inp != 'a' else None)
-        model.train_op()
-
-    # ---- end-to-end step: every step's inputs come from pinned HOST buffers (H2D inside the timed region) and
-    # every step's loss is read back to the host.  The copy of step k+1 runs on a side stream while step k
-    # computes (two device staging sets), and the loss of step k is fetched one step late (pinned, non-blocking),
-    # so that neither transfer stalls the kernels.
-    E2E_KEYS = ('wav', 'mask', 'landmarks', 'vmean', 'vstd', 'seq_len')
-    # host staging dtypes: the samples are int16-valued (target.wav, dataset_reader.py:78) and the mask is {0,1}; by
-    # default they cross PCIe as int16 / uint8 and are widened to the fp32 feed tensors on the device
-    # (avsi_cast_to_f32, inside the timed step).  --e2e-fp32 stages the fp32 placeholders of training.py:69-71 instead.
-    if not args.e2e_fp32:
-        pin = dict(pin)
-        pin['wav'] = torch.from_numpy(host['wav'].astype(np.int16)).pin_memory()
-        pin['mask'] = torch.from_numpy(host['mask'].astype(np.uint8)).pin_memory()
-    copy_stream = torch.cuda.Stream(device=dev)
-    stage = [{k: torch.empty(pin[k].shape, dtype=pin[k].dtype, device=dev) for k in E2E_KEYS} for _ in range(2)]
-    ready = [torch.cuda.Event() for _ in range(2)]
-    freed = [torch.cuda.Event() for _ in range(2)]
-    loss_pin = torch.zeros(2, dtype=torch.float64).pin_memory()
-    loss_evt = [torch.cuda.Event() for _ in range(2)]
-    e2e_state = {'i': 0, 'losses': []}
-
-    def e2e_prefetch(i):
-        sl = i % 2
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(freed[sl])                 # the step that last used this staging set is done
-            for k in E2E_KEYS:
-                stage[sl][k].copy_(pin[k], non_blocking=True)
-            ready[sl].record(copy_stream)
-
-    def e2e_reset():
-        torch.cuda.synchronize()
-        e2e_state['i'] = 0
-        for sl in range(2):
-            freed[sl].record(torch.cuda.current_stream())
-        e2e_prefetch(0)
-
-    def step_e2e():
-        i = e2e_state['i']
-        sl = i % 2
-        cur = torch.cuda.current_stream()
-        e2e_prefetch(i + 1)                                   # next step's H2D overlaps this step's kernels
-        cur.wait_event(ready[sl])
-        d = stage[sl]
-        model.feed(sequence_lengths=d['seq_len'], target_sources=d['wav'], masks=d['mask'],
-                   video_features=video_of(d) if inp != 'a' else None)
-        model.train_op()
-        freed[sl].record(cur)
-        n = model.engine.layout.n_params_padded
-        src = model.engine.grad[n + 4:n + 5].double() if pg is not None else model._loss_pass(True, want_pred=False)['sums'][4:5]
-        if i > 0:                                             # read the previous step's loss (already on the host)
-            loss_evt[1 - sl].synchronize()
-            e2e_state['losses'].append(float(loss_pin[1 - sl]))
-        loss_pin[sl:sl + 1].copy_(src, non_blocking=True)
-        loss_evt[sl].record(cur)
-        e2e_state['i'] = i + 1
-
-    def e2e_drain():
-        i = e2e_state['i']
-        if i > 0:
-            loss_evt[(i - 1) % 2].synchronize()
-            e2e_state['losses'].append(float(loss_pin[(i - 1) % 2]))
-
-    def timed(fn, steps, profile=False):
-        torch.cuda.synchronize()
-        if pg is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n0 = _lib.launch_count()
-        if profile:
-            _lib.profile_start()
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        prof = _lib.profile_stop() if profile else None
-        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        if pg is not None:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()), _lib.launch_count() - n0, prof
+    wl = Workload(args.model, B, args.audio_len, pg, dev, rank, world, want_e2e=True)
+    T = wl.T
 
     for _ in range(max(args.warmup, 3)):
-        step_resident()
+        wl.step_resident()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
         time.sleep(0.15)
-    ms, launches, prof = timed(step_resident, args.steps, profile=True)
+    ms, launches, prof = wl.timed(wl.step_resident, args.steps, profile=True)
     clocks = sampler.stop() if rank == 0 else None
-    e2e_reset()
-    for _ in range(2):
-        step_e2e()
-    e2e_drain()
-    e2e_reset()                                               # the first H2D of the timed run is inside the region's lead-in
+    # end to end, twice: with the reference's fp32 placeholders (the headline `e2e`) and with compact host staging
+    ms_e2e, h2d, dtypes, losses = wl.run_e2e(args.steps, fp32=True)
+    ms_e2c, h2d_c, dtypes_c, _ = wl.run_e2e(args.steps, fp32=False)
+    wl.close()
+    pk = peaks()
+    extras = None if args.no_extras else run_extras(args, pg, dev, rank, world, pk)
 
-    def e2e_run():
-        step_e2e()
-        if e2e_state['i'] == args.steps:
-            e2e_drain()
-    ms_e2e, _, _ = timed(e2e_run, args.steps)
-    torch.cuda.current_stream().wait_stream(copy_stream)
-    torch.cuda.synchronize()
-
-    if not all(np.isfinite(x) for x in e2e_state['losses']):
-        raise SystemExit('bench: non-finite loss fetched in the end-to-end steps: %r' % e2e_state['losses'][-3:])
     if rank != 0:
         if pg is not None:
             dist.destroy_process_group()
         return
-    pk = peaks()
     utt = B * world * args.steps
     value = utt / (ms * 1e-3)
-    h2d = sum(pin[k].numel() * pin[k].element_size() for k in ('wav', 'mask', 'landmarks', 'vmean', 'vstd', 'seq_len'))
-    kernels = {}
-    tot = sum(v['ms'] for v in prof.values()) or 1.0
-    for name, v in sorted(prof.items(), key=lambda kv: -kv[1]['ms']):
-        kernels[name] = {'ms_per_step': v['ms'] / args.steps, 'share': v['ms'] / tot, 'launches_per_step': v['launches'] / args.steps}
+    kernels = kernel_table(prof, args.steps)
 
-    traffic = {}
+    # roofline.traffic: dram bytes per launch from the committed ncu --set full captures, valid only for the library
+    # build they were taken on (profiles/ncu_traffic.json carries the source digest; a stale file yields null)
+    traffic, traffic_note = {}, 'no ncu capture of this workload committed'
     try:
         tj = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')))
         if tj['workload'] == {'batch': B, 'audio_len': args.audio_len}:
-            traffic = tj
+            if tj.get('library_digest') in (None, library_digest()):
+                traffic, traffic_note = tj, 'profiles/ncu_traffic.json (%s)' % tj.get('captures', 'ncu --set full')
+            else:
+                traffic_note = 'profiles/ncu_traffic.json is from another build of the kernels (digest %s): not used' % tj.get('library_digest')
     except Exception:
-        traffic = {}
+        pass
 
     def roof(name):
         r = roof_(name)
         if r is not None:
             r['traffic'] = traffic.get(name)
+            r['traffic_source'] = traffic_note
         return r
 
     def roof_(name):
@@ -364,19 +473,26 @@ def main():
         'dtype': 'f16', 'data': 'synthetic', 'arithmetic': 'fp16 operands, fp32 accumulate / state',
         'config': workload_config(args, world),
         'e2e': {'value': utt / (ms_e2e * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 8,
-                'host_dtypes': {k: str(pin[k].dtype).replace('torch.', '') for k in ('wav', 'mask', 'landmarks')}},
+                'host_dtypes': dtypes, 'staging': 'fp32 placeholders of the reference feed contract (training.py:69-71)'},
+        'e2e_compact': {'value': utt / (ms_e2c * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d_c, 'd2h_bytes_per_step': 8,
+                        'host_dtypes': dtypes_c,
+                        'staging': 'samples int16 / masks uint8 on the host (narrowed outside the timed region), widened on the device'},
         # the e2e steps train on the same batch: the fetched losses must be finite and go down (work is not skipped)
-        'e2e_loss_first_last': [e2e_state['losses'][0] / (B * T * 257), e2e_state['losses'][-1] / (B * T * 257)]
-        if e2e_state['losses'] else None,
+        'e2e_loss_first_last': [losses[0] / (B * T * 257), losses[-1] / (B * T * 257)] if losses else None,
         'gpu_launches': launches,
         'clocks': clocks,
         'roofline': roof(dominant) if dominant else None,
         'roofline_frontend': roof('frontend'),
         'roofline_gemm_proj': roof('gemm_proj_fwd'),
+        # whole step against the tensor roofline: 6.62 GFLOP per AV-SI utterance
+        'step_frac_of_tensor_roofline': value / world * 6.62e9 * (T / 250.0) / (pk['bf16_tflops_sustained'] * 1e12),
         'kernels': kernels,
+        'library_digest': library_digest(),
     }
+    if extras is not None:
+        line['extra'] = extras
     if not args.no_cpu_baseline and world == 1:
-        line['cpu_baseline'], _ = cpu_baseline(args, steps=3, warmup=0)
+        line['cpu_baseline'], _ = cpu_baseline(args, steps=2, warmup=0)
     elif world == 1:
         line['cpu_baseline'] = None
     print(json.dumps(line))
