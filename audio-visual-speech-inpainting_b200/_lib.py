@@ -54,6 +54,7 @@ SIGNATURES = {
     'avsi_istft_fwd': (c_int, [POINTER(IstftArgs), c_void_p]),
     'avsi_features_to_x0': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int,
                                     c_void_p]),
+    'avsi_tile_embedding': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
     'avsi_video_features': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'avsi_expand_mask': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'avsi_ctc_beam_search_host': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_int,

@@ -128,10 +128,27 @@ features_to_x0_kernel(const float* __restrict__ feat, const float* __restrict__ 
     uint16_t* dst = x0 + ((long long)t * B + b) * ldx;
     for (int c = threadIdx.x; c < ldx; c += blockDim.x) {
       float v = 0.f;
-      if (c < F) v = (feat[r * F + c] - __ldg(mean + c)) / __ldg(stdev + c);
-      else if (video && c < F + V) v = video[r * V + (c - F)];
+      if (c < F) {
+        v = feat[r * F + c];
+        if (mean) v = (v - __ldg(mean + c)) / __ldg(stdev + c);
+      } else if (video && c < F + V) {
+        v = video[r * V + (c - F)];
+      }
       dst[c] = __half_as_ushort(__float2half_rn(v));
     }
+  }
+}
+
+// per-utterance vector (speaker embedding) replicated over the frames: x0[t*B + b, col0 : col0 + E] = emb[b, :]
+// (tf.tile(tf.expand_dims(embeddings, 1), [1, T, 1]) + tf.concat of models.py:1204-1206 / :846-849)
+__global__ void __launch_bounds__(256)
+tile_embedding_kernel(const float* __restrict__ emb, int B, int T, int E, uint16_t* __restrict__ x0, int ldx, int col0) {
+  const long long n = (long long)T * B * E;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+    const int e = (int)(idx % E);
+    const long long r = idx / E;                    // time-major row t*B + b
+    const int b = (int)(r % B);
+    x0[r * ldx + col0 + e] = __half_as_ushort(__float2half_rn(__ldg(emb + (long long)b * E + e)));
   }
 }
 
@@ -180,11 +197,23 @@ extern "C" int avsi_video_features(const float* landmarks, const float* vmean, c
 extern "C" int avsi_features_to_x0(const float* feat, const float* mean, const float* stdev, const float* video, int B,
                                    int T, int F, int V, uint16_t* x0, int ldx, void* stream) {
   using namespace avsi;
-  AVSI_REQUIRE(feat && mean && stdev && x0, "null pointer");
+  AVSI_REQUIRE(feat && x0, "null pointer");
+  AVSI_REQUIRE((mean == nullptr) == (stdev == nullptr), "mean and stdev: both or neither");
   AVSI_REQUIRE(B > 0 && T > 0 && F > 0 && V >= 0 && ldx >= F + (video ? V : 0), "sizes");
   long long rows = (long long)B * T;
   int blocks = (int)min(rows, (long long)num_sms() * 16);
   features_to_x0_kernel<<<blocks, 128, 0, (cudaStream_t)stream>>>(feat, mean, stdev, video, B, T, F, V, x0, ldx);
+  AVSI_LAUNCH_CHECK();
+  return AVSI_OK;
+}
+
+extern "C" int avsi_tile_embedding(const float* emb, int B, int T, int E, uint16_t* x0, int ldx, int col0, void* stream) {
+  using namespace avsi;
+  AVSI_REQUIRE(emb && x0, "null pointer");
+  AVSI_REQUIRE(B > 0 && T > 0 && E > 0 && col0 >= 0 && ldx >= col0 + E, "sizes");
+  const long long n = (long long)T * B * E;
+  int blocks = (int)min((n + 255) / 256, (long long)num_sms() * 16);
+  tile_embedding_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(emb, B, T, E, x0, ldx, col0);
   AVSI_LAUNCH_CHECK();
   return AVSI_OK;
 }

@@ -88,15 +88,29 @@ class DataManager(object):
     """Utilities to read TFRecords"""
 
     def __init__(self, num_audio_samples=48000, audio_feat_size=257, video_feat_size=136, buffer_size=1000, mode='fixed',
-                 rank=0, world=1, num_parallel_calls=None, **unused):
+                 rank=0, world=1, num_parallel_calls=None, embedding_size=0, **unused):
         if mode != 'fixed':
             raise NotImplementedError("only the 'fixed' TFRecord mode works in the reference (SURVEY.md 2.4)")
         self.num_audio_samples, self.audio_feat_size, self.video_feat_size = num_audio_samples, audio_feat_size, video_feat_size
         self.buffer_size, self.mode, self.rank, self.world = buffer_size, mode, rank, world
+        # dataset_reader_emb.py:12-81: records that also carry a per-utterance `embedding` (512 floats); the batches are
+        # then the 8-tuple (seq_len, lab_len, wav, embedding, sample_path, labels, video, mask) of :79-81
+        self.embedding_size = int(embedding_size or 0)
         # parser threads (tf.data's num_parallel_calls of dataset_reader.py:55); default: up to 8 host cores
         self.workers = num_parallel_calls if num_parallel_calls else max(1, min(8, os.cpu_count() or 1))
 
     def read_data_format_fixed(self, sample):
+        if self.embedding_size:
+            ctx, seq = parse_sequence_example(sample)
+            wav = np.asarray(ctx['target_audio_wav'], np.float32)
+            emb = np.asarray(ctx['embedding'], np.float32)
+            if wav.shape[0] != self.num_audio_samples or emb.shape[0] != self.embedding_size:
+                raise ValueError('target_audio_wav / embedding have %d / %d values, expected %d / %d'
+                                 % (wav.shape[0], emb.shape[0], self.num_audio_samples, self.embedding_size))
+            return (np.int32(ctx['sequence_length'][0]), np.int32(ctx['labels_length'][0]), wav.astype(np.int32), emb,
+                    ctx['sample_path'][0] if ctx['sample_path'] else b'',
+                    np.concatenate(seq['labels']).astype(np.float32) if seq.get('labels') else np.zeros(0, np.float32),
+                    np.stack(seq['video_features']).astype(np.float32), np.stack(seq['mask']).astype(np.float32))
         fast = parse_av_sample(sample, self.num_audio_samples, self.audio_feat_size, self.video_feat_size)
         if fast is not None:
             seq_len, lab_len, wav, path, labels, video, mask = fast
@@ -164,11 +178,14 @@ class DataManager(object):
                 if cur and not drop_remainder:
                     yield _collate(cur)
                 epoch += 1
-        native = parse_av_sample is not None and _native_available()
+        native = parse_av_sample is not None and _native_available() and not self.embedding_size
         return dataset, (fast_batches() if native else batches())
 
 
 def _collate(samples):
     cols = list(zip(*samples))
+    if len(cols) == 8:                                   # with embedding (dataset_reader_emb.py:79-81)
+        return (np.asarray(cols[0], np.int32), np.asarray(cols[1], np.int32), np.stack(cols[2]), np.stack(cols[3]),
+                list(cols[4]), np.stack(cols[5]), np.stack(cols[6]), np.stack(cols[7]))
     return (np.asarray(cols[0], np.int32), np.asarray(cols[1], np.int32), np.stack(cols[2]), list(cols[3]),
             np.stack(cols[4]), np.stack(cols[5]), np.stack(cols[6]))

@@ -34,9 +34,7 @@ class StackedBLSTMModel(object):
 
     def __init__(self, sequence_lengths, target_sources, masks, audio_feat_mean, audio_feat_std, dropout_rate,
                  config, audio_features=None, video_features=None, input='a', is_training=True, device='cuda',
-                 process_group=None, _out_dim=None):
-        if audio_features is not None:
-            raise NotImplementedError('precomputed audio_features (two-step model) are out of scope')
+                 process_group=None, _out_dim=None, embeddings=None):
         if input not in ('a', 'v', 'av'):
             raise ValueError("input must be 'a', 'v' or 'av'")
         self.config = config
@@ -63,6 +61,13 @@ class StackedBLSTMModel(object):
         self.hop = ap.ms_to_samples(12, 16000)
         in_dim = {'a': self.audio_feat_dim, 'v': self.video_feat_dim,
                   'av': self.audio_feat_dim + self.video_feat_dim}[input]
+        # audio_features given (models.py:34-37): the network's audio input is that tensor instead of the masked target
+        # spectrogram -- the two-step model feeds the video-only model's prediction (models.py:258-262)
+        self.external_audio_features = audio_features is not None
+        # a per-utterance vector replicated over the frames and appended to the network input (models.py:1204-1206)
+        self.base_in_dim = in_dim
+        self.embedding_dim = 0 if embeddings is None else int(np.asarray(embeddings.shape)[-1])
+        in_dim += self.embedding_dim
         self.num_classes = config['num_asr_labels'] if self.MTL else 0
         self.engine = BLSTMEngine(in_dim, self.net_dim[0], self.num_layers,
                                   self.audio_feat_dim if _out_dim is None else _out_dim, self.num_classes,
@@ -79,7 +84,8 @@ class StackedBLSTMModel(object):
         self._widen = {}
         self.feed(sequence_lengths=sequence_lengths, target_sources=target_sources, masks=masks,
                   audio_features_mean=audio_feat_mean, audio_features_std=audio_feat_std,
-                  dropout_rate=dropout_rate, video_features=video_features)
+                  dropout_rate=dropout_rate, video_features=video_features, audio_features=audio_features,
+                  embeddings=embeddings)
 
     # ---- feed contract (training_ctc.py:67-77, 264-275) -------------------------------------------
     _COMPACT = {torch.int16: 0, torch.uint8: 1, torch.bool: 1, torch.int32: 2}
@@ -103,7 +109,8 @@ class StackedBLSTMModel(object):
 
     def feed(self, **kw):
         """Set the tensors of the next batch; unknown names raise.  None values are ignored."""
-        f32 = ('target_sources', 'masks', 'audio_features_mean', 'audio_features_std', 'video_features')
+        f32 = ('target_sources', 'masks', 'audio_features_mean', 'audio_features_std', 'video_features', 'audio_features',
+               'embeddings')
         i32 = ('sequence_lengths', 'labels_lengths', 'labels')
         for k, v in kw.items():
             if v is None:
@@ -200,10 +207,29 @@ class StackedBLSTMModel(object):
         if self.MTL:
             hole = self._cache.setdefault('hole', torch.zeros(1, dtype=torch.float32, device=self.device))
             hole.zero_()
+        L = self.engine.layout
+        ext = self._fed.get('audio_features') if self.external_audio_features else None
+        if self.external_audio_features and ext is None:
+            raise _lib.AvsiError('audio_features must be fed (the model was built with precomputed audio features)')
         res = ap.fused_features(wav, self.frame_len, self.hop, T=T, F=self.audio_feat_dim, mean=mean, std=std,
                                 mask=masks, video=video, power=1.0, log=True, want_stft=want_stft, want_spec=True,
-                                xh_out=ws['x0'], ldx=self.engine.layout.k0p, hole_count=hole,
+                                xh_out=None if ext is not None else ws['x0'], ldx=L.k0p, hole_count=hole,
                                 xh_video_only=(self.input_type == 'v'), xh_skip_pad=True)
+        if ext is not None:
+            # network input = [given audio features ; video] (models.py:34-45), no normalisation, no mask
+            if tuple(ext.shape) != (B, T, self.audio_feat_dim):
+                raise ValueError('audio_features must be [B,T,%d]; got %s' % (self.audio_feat_dim, tuple(ext.shape)))
+            if self.input_type == 'v':
+                raise ValueError("precomputed audio_features make no sense with input='v'")
+            _lib.check(_lib.load().avsi_features_to_x0(_p(ext), None, None, _p(video), B, T, self.audio_feat_dim,
+                                                       0 if video is None else video.shape[2], _p(ws['x0']), L.k0p,
+                                                       _lib.stream_ptr()), 'avsi_features_to_x0')
+        if self.embedding_dim:
+            emb = self._fed.get('embeddings')
+            if emb is None or tuple(emb.shape) != (B, self.embedding_dim):
+                raise ValueError('embeddings must be fed as [B,%d]' % self.embedding_dim)
+            _lib.check(_lib.load().avsi_tile_embedding(_p(emb), B, T, self.embedding_dim, _p(ws['x0']), L.k0p,
+                                                       self.base_in_dim, _lib.stream_ptr()), 'avsi_tile_embedding')
         out = {'ws': ws, 'B': B, 'T': T, 'target_spec_norm': res['spec'], 'target_stft': res['stft'], 'hole': hole}
         self._cache[key] = out
         if want_stft:
@@ -416,6 +442,31 @@ class StackedBLSTMModel(object):
     def enhanced_sources_oracle_phase(self):
         return self._enhanced(True)
 
+    # ---- TensorBoard summaries (models.py:199-219) -----------------------------------------------------------
+    N_SUMMARY_SAMPLES = 10
+
+    @staticmethod
+    def _spec_image(x, n):
+        """tf.map_fn(tf.image.flip_up_down, expand_dims(transpose(x, [0, 2, 1]), 3)): [B,T,F] -> [n,F,T,1], low bins at the bottom."""
+        return x[:n].transpose(1, 2).flip(1).unsqueeze(3).contiguous()
+
+    @property
+    def summaries(self):
+        """The tensors behind tf.summary.merge_all() of models.py:199-219, under the reference's tags: three spectrogram
+        images (target, enhanced, mask; frequency axis flipped, at most 10 samples) and the target / enhanced waveforms
+        normalised to their peak, at 16 kHz.  {tag: (kind, CUDA tensor)}; training.py writes them to the event file."""
+        n = self.N_SUMMARY_SAMPLES
+        masks, wav = self._need('masks', 'target_sources')
+        enh = self.enhanced_sources
+        out = {
+            'summary/Target_spectrogram': ('image', self._spec_image(self.target_spec_norm, n)),
+            'summary/Enhanced_spectrogram': ('image', self._spec_image(self.prediction, n)),
+            'summary/Mask': ('image', self._spec_image(masks, n)),
+            'summary/Target_audio': ('audio', (wav / wav.abs().amax(dim=1, keepdim=True))[:n]),
+            'summary/Enhanced_audio': ('audio', (enh / enh.abs().amax(dim=1, keepdim=True))[:n]),
+        }
+        return out
+
     # ---- variables / checkpoints (SURVEY.md 5.1) --------------------------------------------------------------
     def build_graph(self, var_scope=''):
         self.var_scope = var_scope
@@ -542,6 +593,91 @@ class StackedBLSTMSSNNCTCLossModel(StackedBLSTMModel):
         return self._decode(self.audio_feat_dim)
 
 
+class StackedBLSTMEmbeddingModel(StackedBLSTMModel):
+    """Inpainting BLSTM with an external speaker embedding (models.py:1120-1472, `integration_layer` = 0, the shipped
+    default): the 512-d vector of the utterance (dataset_reader_emb.py:63-81) is replicated over the frames and
+    concatenated to the network input (models.py:1204-1206).  No extra variables: the layer-0 kernel simply has
+    I_0 = in_dim + 512 input rows.  integration_layer >= 1 (embedding injected after the first BLSTM layer,
+    models.py:1228-1290) is not built."""
+
+    def __init__(self, sequence_lengths, target_sources, masks, audio_feat_mean, audio_feat_std, dropout_rate, config,
+                 audio_features=None, video_features=None, embeddings=None, input='a', is_training=True, device='cuda',
+                 process_group=None):
+        if embeddings is None:
+            raise ValueError('StackedBLSTMEmbeddingModel needs `embeddings` [B,E]')
+        if config.get('integration_layer', 0):
+            raise NotImplementedError('integration_layer >= 1 (models.py:1228-1290) is not built')
+        super(StackedBLSTMEmbeddingModel, self).__init__(
+            sequence_lengths, target_sources, masks, audio_feat_mean, audio_feat_std, dropout_rate, config,
+            audio_features=audio_features, video_features=video_features, input=input, is_training=is_training,
+            device=device, process_group=process_group, embeddings=embeddings)
+
+
+class StackedBLSTM2StepsModel(object):
+    """2-steps speech inpainting BLSTM model (models.py:240-317): a video-only model `v-blstm` predicts the spectrogram
+    from the landmark motion vectors; its prediction replaces the masked spectrogram as the audio input of the
+    audio-visual model `av-blstm-twosteps`, which is the one that is trained (train_vars = the av model's variables
+    only, models.py:295; the video model is restored from `model_ckp_vnet`, training.py:115-116,153-156)."""
+    MTL = False
+
+    def __init__(self, sequence_lengths, target_sources, masks, audio_feat_mean, audio_feat_std, dropout_rate, config,
+                 video_features, is_training=True, device='cuda', process_group=None):
+        self.config = config
+        # the video model only ever runs forward here (its variables are not in train_vars): inference workspace
+        self.video_model = StackedBLSTMModel(sequence_lengths, target_sources, masks, audio_feat_mean, audio_feat_std,
+                                             0.0, config, video_features=video_features, input='v', is_training=False,
+                                             device=device)
+        self.video_model.build_graph('v-blstm')
+        self.av_model = StackedBLSTMModel(sequence_lengths, target_sources, masks, audio_feat_mean, audio_feat_std,
+                                          dropout_rate, config, audio_features=self.video_model.prediction,
+                                          video_features=video_features, input='av', is_training=is_training, device=device,
+                                          process_group=process_group)
+        self.av_model.build_graph('av-blstm-twosteps')
+        self.is_training = is_training
+        self.var_scope = ''
+        self.device = self.av_model.device
+        self.optimizer_choice = self.av_model.optimizer_choice
+
+    def feed(self, **kw):
+        vkw = {k: v for k, v in kw.items() if k != 'dropout_rate'}
+        self.video_model.feed(dropout_rate=0.0, **vkw)
+        self.av_model.feed(audio_features=self.video_model.prediction, **kw)
+        return self
+
+    def build_graph(self, var_scope=''):
+        self.var_scope = var_scope
+
+    # models.py:281-296: everything but video_prediction is the av model's
+    video_prediction = property(lambda self: self.video_model.prediction)
+    engine = property(lambda self: self.av_model.engine)
+
+    def __getattr__(self, name):
+        if name in ('target_spec_norm', 'inference', 'prediction', 'loss', 'loss_func', 'loss_hole', 'loss_valid',
+                    'learning_rate', 'global_step', 'enhanced_sources', 'enhanced_sources_oracle_phase', 'train_vars',
+                    'train_op', 'compute_gradients', 'canonical_gradients', 'dropout_keep_mask', 'summaries', '_fed',
+                    '_loss_pass'):
+            return getattr(self.av_model, name)
+        raise AttributeError(name)
+
+    @property
+    def all_vars(self):
+        v = dict(self.av_model.all_vars)
+        v.update(self.video_model.train_vars)
+        return v
+
+    def assign_vars(self, variables):
+        """Both sub-models when the checkpoint holds them; a checkpoint of the video model alone (`model_ckp_vnet`)
+        or of the av model alone restores that part."""
+        done = 0
+        for m in (self.video_model, self.av_model):
+            if any(k.startswith(m.var_scope + '/') for k in variables):
+                m.assign_vars(variables)
+                done += 1
+        if not done:
+            raise KeyError('no variable of scope v-blstm/ or av-blstm-twosteps/')
+        self.feed()                                   # the av model's audio input is the video model's (new) prediction
+
+
 # In the reference, StackedBLSTMCTCLossModel.inference is broken (models.py:1565-1566 uses an undefined
 # attribute); its intended semantics are those of the SSNN-CTC class without the embedding.
 StackedBLSTMCTCLossModel = StackedBLSTMSSNNCTCLossModel
@@ -552,4 +688,8 @@ MODEL_REGISTRY = {
     'av-blstm-ctc': (StackedBLSTMCTCLossModel, 'av'),
     'a-blstm-ssnn-ctc': (StackedBLSTMSSNNCTCLossModel, 'a'), 'v-blstm-ssnn-ctc': (StackedBLSTMSSNNCTCLossModel, 'v'),
     'av-blstm-ssnn-ctc': (StackedBLSTMSSNNCTCLossModel, 'av'),
+    # training_emb.py:98-110 / training_ctc.py:80-136
+    'a-blstm-emb': (StackedBLSTMEmbeddingModel, 'a'), 'v-blstm-emb': (StackedBLSTMEmbeddingModel, 'v'),
+    'av-blstm-emb': (StackedBLSTMEmbeddingModel, 'av'),
+    'av-blstm-twosteps': (StackedBLSTM2StepsModel, 'av'),
 }

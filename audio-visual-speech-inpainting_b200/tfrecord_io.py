@@ -221,11 +221,15 @@ def write_records(path, records):
             f.write(ln + struct.pack('<I', masked_crc(ln)) + data + struct.pack('<I', masked_crc(data)))
 
 
-def serialize_sample_fixed(seq_len, lab_len, target_audio_wav, video_features, mask, labels, sample_path):
-    """Same keys and value kinds as tfrecord_utils.py:19-41 (the 'fixed' mode, the only working one -- SURVEY.md 2.4)."""
+def serialize_sample_fixed(seq_len, lab_len, target_audio_wav, video_features, mask, labels, sample_path, embedding=None):
+    """Same keys and value kinds as tfrecord_utils.py:19-41 (the 'fixed' mode, the only working one -- SURVEY.md 2.4);
+    with `embedding`, the context of tfrecord_emb_utils.py:19-43 (one more float feature)."""
+    ctx = {'sequence_length': np.array([seq_len], np.int64), 'labels_length': np.array([lab_len], np.int64),
+           'target_audio_wav': np.asarray(target_audio_wav, np.float32), 'sample_path': sample_path.encode()}
+    if embedding is not None:
+        ctx['embedding'] = np.asarray(embedding, np.float32)
     return build_sequence_example(
-        {'sequence_length': np.array([seq_len], np.int64), 'labels_length': np.array([lab_len], np.int64),
-         'target_audio_wav': np.asarray(target_audio_wav, np.float32), 'sample_path': sample_path.encode()},
+        ctx,
         {'mask': [np.asarray(r, np.float32) for r in mask],
          'video_features': [np.asarray(r, np.float32) for r in video_features],
          'labels': [np.array([l], np.float32) for l in labels]})

@@ -50,9 +50,17 @@ def build_model(config, batch, mean, std, is_training=True, device='cuda', proce
         print('Model selection must be "a-blstm", "v-blstm", "av-blstm" or a "-ctc" variant of them. Closing...')
         sys.exit(1)
     cls, inp = MODEL_REGISTRY[name]
-    seq, lab_len, wav, _, labels, video, mask = batch
+    seq, lab_len, wav, emb, _, labels, video, mask = _unpack(batch)
     kw = dict(video_features=video, input=inp, is_training=is_training, device=device, process_group=process_group)
-    if cls.MTL:
+    if name.endswith('-emb'):                                   # training_emb.py:98-110
+        if emb is None:
+            print('Model "{:s}" needs TFRecords with an `embedding` feature (tfrecord_emb_utils.py). Closing...'.format(name))
+            sys.exit(1)
+        model = cls(seq, wav.astype(np.float32), mask, mean, std, 0.0, config, embeddings=emb, **kw)
+    elif name == 'av-blstm-twosteps':                           # training.py:99-101
+        model = cls(seq, wav.astype(np.float32), mask, mean, std, 0.0, config, video, is_training=is_training,
+                    device=device, process_group=process_group)
+    elif cls.MTL:
         model = cls(seq, lab_len, wav.astype(np.float32), mask, labels, mean, std, 0.0, config, **kw)
     else:
         model = cls(seq, wav.astype(np.float32), mask, mean, std, 0.0, config, **kw)
@@ -60,13 +68,24 @@ def build_model(config, batch, mean, std, is_training=True, device='cuda', proce
     return model
 
 
+def _unpack(batch):
+    """(seq_len, lab_len, wav, embedding | None, paths, labels, video, mask) from a 7-tuple (dataset_reader.py:77-79) or the
+    8-tuple with embeddings (dataset_reader_emb.py:79-81)."""
+    if len(batch) == 8:
+        return batch
+    seq, lab_len, wav, paths, labels, video, mask = batch
+    return seq, lab_len, wav, None, paths, labels, video, mask
+
+
 def feed_batch(model, batch, dropout_rate=0.0):
     """dropout_rate: config['dropout_rate'] on training steps, 0.0 on validation / inference (training.py:241, 303, 314)."""
-    seq, lab_len, wav, _, labels, video, mask = batch
+    seq, lab_len, wav, emb, _, labels, video, mask = _unpack(batch)
     kw = dict(sequence_lengths=seq, target_sources=wav.astype(np.float32), masks=mask, video_features=video,
               dropout_rate=dropout_rate)
     if model.MTL:
         kw.update(labels_lengths=lab_len, labels=labels)
+    if getattr(model, 'embedding_dim', 0):
+        kw.update(embeddings=emb)
     model.feed(**kw)
     return np.count_nonzero(mask[:, :, 0] == 0)                 # masked frames of the batch
 
@@ -99,7 +118,7 @@ def train(config_file, max_steps=None):
     return _train(config_file, max_steps, build_model, feed_batch, _losses)
 
 
-def _train(config_file, max_steps, build_model, feed_batch, _losses):
+def _train(config_file, max_steps, build_model, feed_batch, _losses, best_name='sinet'):
     """The training job of training.py / training_ctc.py; `training_asr.train` runs it with the phone-recognition model's
     hooks (model construction, feed, the monitored loss tuple whose entry 1 selects the best validation checkpoint)."""
     import torch
@@ -117,7 +136,8 @@ def _train(config_file, max_steps, build_model, feed_batch, _losses):
 
     def manager():
         return DataManager(num_audio_samples=config['audio_len'], audio_feat_size=config['audio_feat_dim'],
-                           video_feat_size=config['video_feat_dim'], buffer_size=4000, mode='fixed', rank=rank, world=world)
+                           video_feat_size=config['video_feat_dim'], buffer_size=4000, mode='fixed', rank=rank, world=world,
+                           embedding_size=512 if str(config['model']).endswith('-emb') else 0)    # training_emb.py:46
     train_files = sorted(glob(os.path.join(data_path_train, '*.tfrecord')))
     val_files = sorted(glob(os.path.join(data_path_val, '*.tfrecord')))
     audio_feat_mean = np.load(config['audio_feat_mean']).astype(np.float32)
@@ -151,6 +171,13 @@ def _train(config_file, max_steps, build_model, feed_batch, _losses):
     _, probe = manager().get_iterator(manager().get_dataset(train_files, shuffle=False), batch_size=per_rank_batch, n_epochs=1)
     model = build_model(config, next(probe), audio_feat_mean, audio_feat_std, True, process_group=pg)
     print('Model building done.')
+    if config.get('model_ckp_vnet') and hasattr(model, 'video_model'):      # training.py:115-116,153-159 (two-step model)
+        try:
+            checkpoint.restore(model.video_model, config['model_ckp_vnet'], train_vars_only=True)
+            print('Visual model variables restored.')
+        except ValueError:
+            print('{:s} is not a valid checkpoint. Closing...'.format(config['model_ckp_vnet']))
+            sys.exit(2)
     if config.get('model_ckp'):
         try:
             checkpoint.restore(model, config['model_ckp'])
@@ -232,11 +259,17 @@ def _train(config_file, max_steps, build_model, feed_batch, _losses):
         # ---- validation: same model, no update ----------------------------------------------------------------
         _, val_it = manager().get_iterator(manager().get_dataset(val_files, shuffle=False), batch_size=per_rank_batch, n_epochs=1)
         val_it = parallel.lockstep(val_it, per_rank_batch, pg, model.device)   # the MTL loss all-reduces its hole count
-        vavg, n_vstep = _RunningAverage(), 0
+        vavg, n_vstep, summaries = _RunningAverage(), 0, None
         for batch in val_it:
             n_vstep += 1
             frames = feed_batch(model, batch)
             va = vavg.add(frames, _losses(model, True))
+            if n_vstep == 1 and rank == 0 and tb is not None and hasattr(model, 'summaries'):
+                # model.summaries of the first validation batch (training.py:295-304): images + audio, once per epoch
+                try:
+                    summaries = {k: (kind, t.detach().float().cpu()) for k, (kind, t) in model.summaries.items()}
+                except Exception as e:                           # noqa: BLE001 -- monitoring must not stop the job
+                    print('summaries skipped: %s' % e)
             if rank == 0 and (n_vstep % 200 == 0 or n_vstep == 1):
                 print('Step[{:7d}] Loss[{:3.5f}]'.format(n_vstep, va[1]))
         va = vavg.vals if vavg.vals is not None else np.zeros(4)
@@ -250,7 +283,7 @@ def _train(config_file, max_steps, build_model, feed_batch, _losses):
                   .format(va[1], va[3], best_val_loss, best_val_checkpoint[0], best_val_checkpoint[1]))
         if best_val_checkpoint == (0, 0) or va[1] < best_val_loss:
             if rank == 0:
-                print('Model saved in file %s' % _save(model, os.path.join(checkpoints_dir, 'sinet'), config))
+                print('Model saved in file %s' % _save(model, os.path.join(checkpoints_dir, best_name), config))
             best_val_checkpoint, best_val_loss, cneg_epochs = (epoch_counter, tot_step), va[1], 0
         else:
             cneg_epochs += 1
@@ -260,6 +293,14 @@ def _train(config_file, max_steps, build_model, feed_batch, _losses):
                                  ('Training loss PER', tr[3]), ('Validation loss', va[0]), ('Validation loss inpainting', va[1]),
                                  ('Validation loss CTC', va[2]), ('Validation loss PER', va[3])):
                     tb.add_scalar(tag, float(val), epoch_counter)
+                for tag, (kind, t) in (summaries or {}).items():       # tb_writer.add_summary(summaries, epoch) (training.py:352)
+                    for i in range(t.shape[0]):
+                        if kind == 'image':
+                            img = t[i, :, :, 0]
+                            img = (img - img.min()) / (img.max() - img.min()).clamp(min=1e-12)   # tf.summary.image scales to [0, 255]
+                            tb.add_image('%s/image/%d' % (tag, i), img.unsqueeze(0), epoch_counter)
+                        else:
+                            tb.add_audio('%s/audio/%d' % (tag, i), t[i].clamp(-1, 1).unsqueeze(0), epoch_counter, sample_rate=16000)
                 tb.flush()
             print('')
             log.write('{:d}\t{:.6f}\t{:.6f}|{:.6f}|{:.6f}\t{:.6f}\t{:.6f}|{:.6f}|{:.6f}\t{:.6f}\t[{:.2f}]\n'

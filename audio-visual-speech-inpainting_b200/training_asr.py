@@ -43,4 +43,4 @@ def _losses(model, want_per):
 
 def train(config_file, max_steps=None):
     """Train the phone-recognition model."""
-    return _training._train(config_file, max_steps, build_model, feed_batch, _losses)
+    return _training._train(config_file, max_steps, build_model, feed_batch, _losses, best_name='asrnet')   # training_asr.py:308

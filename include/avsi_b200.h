@@ -121,9 +121,15 @@ int avsi_istft_fwd(const avsi_istft_args* args, void* stream);
 
 /* Normalised features -> time-major fp16 network input (models_asr.py:37-49, the ASR model's input assembly):
  *   x0[t*B + b, 0:F] = (feat[b,t,:] - mean) / std ; x0[.., F:F+V] = video[b,t,:] (video may be NULL); columns up to
- *   ldx are zeroed.  feat [B,T,F] f32, mean/std [F] f32. */
+ *   ldx are zeroed.  feat [B,T,F] f32, mean/std [F] f32 or both NULL (features taken as they are: the two-step model's
+ *   audio_features = video_model.prediction, models.py:258-262). */
 int avsi_features_to_x0(const float* feat, const float* mean, const float* stdev, const float* video, int B, int T,
                         int F, int V, uint16_t* x0, int ldx, void* stream);
+
+/* Per-utterance vector replicated over the frames into columns [col0, col0 + E) of the time-major fp16 network input:
+ * tf.tile(tf.expand_dims(embeddings, 1), [1, T, 1]) + tf.concat([net_inputs, tiles], 2) of the embedding models
+ * (models.py:1204-1206; the SSNN models' speaker embedding, models.py:846-849).  emb [B,E] f32. */
+int avsi_tile_embedding(const float* emb, int B, int T, int E, uint16_t* x0, int ldx, int col0, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Landmark stream -> network video features.  Replaces inc_fps /

@@ -518,6 +518,85 @@ def test_restore_reference_style_checkpoints(tmp_path):
     assert torch.equal(other.engine.theta, mom.engine.theta)
 
 
+def test_embedding_model_forward_loss_gradients():
+    """StackedBLSTMEmbeddingModel (models.py:1120-1472, integration_layer 0): the utterance's 512-d embedding replicated
+    over the frames and concatenated to the network input; layer-0 kernel [(393 + 512) + 250, 1000]."""
+    from avsi_b200 import av_sync, models, synth
+    from avsi_b200.layout import init_canonical
+    from oracle import blstm as oblstm
+    B, audio_len = 3, 4800
+    batch = synth.make_batch(B, audio_len=audio_len, seed=14)
+    T = batch['T']
+    emb = (np.random.default_rng(3).standard_normal((B, 512)) * 0.5).astype(np.float32)
+    cfg = synth.default_config('av-blstm-emb', batch_size=B, audio_len=audio_len)
+    video = av_sync.video_pipeline(batch['landmarks'], T, batch['vmean'], batch['vstd'])
+    cls, inp = models.MODEL_REGISTRY['av-blstm-emb']
+    model = cls(batch['seq_len'], batch['wav'], batch['mask'], batch['mean'], batch['std'], 0.0, cfg, video_features=video,
+                embeddings=emb, input=inp)
+    assert model.engine.layout.in_dim == 393 + 512
+    canon = init_canonical(model.engine.layout, seed=15, bias_scale=0.05)
+    model.assign_vars(canon)
+    assert canon['cudnn_lstm/stack_bidirectional_rnn/cell_0/bidirectional_rnn/fw/cudnn_compatible_lstm_cell/kernel'].shape == (905 + 250, 1000)
+    tsn, net_in = _oracle_inputs(batch, 'av')
+    net_in = np.concatenate([net_in, np.repeat(emb[:, None, :].astype(np.float64), T, axis=1)], 2)
+    outs, ograds = oblstm.loss_and_grads('si', dict(net_in=net_in, target=tsn, mask=batch['mask'], seq_len=batch['seq_len']),
+                                         canon, 3)
+    assert rel_l2(model.net_inputs.cpu().numpy(), net_in) < 1e-3
+    assert rel_l2(model.prediction.cpu().numpy(), outs['prediction']) < TOL
+    assert abs(float(model.loss) - float(outs['loss'])) < TOL * abs(float(outs['loss']))
+    _check_grads(model.canonical_gradients(), ograds, 'av-blstm-emb')
+    with pytest.raises(ValueError):
+        model.feed(embeddings=emb[:, :100])
+        model.prediction
+
+
+def test_two_step_model_forward_loss_gradients_and_summaries():
+    """StackedBLSTM2StepsModel (models.py:240-317): v-blstm predicts the spectrogram from the motion vectors, its
+    prediction is the audio input of av-blstm-twosteps; only the av model's variables are trained."""
+    from avsi_b200 import av_sync, models, synth
+    from avsi_b200.layout import init_canonical
+    from oracle import blstm as oblstm
+    B, audio_len = 3, 4800
+    batch = synth.make_batch(B, audio_len=audio_len, seed=16)
+    T = batch['T']
+    cfg = synth.default_config('av-blstm-twosteps', batch_size=B, audio_len=audio_len)
+    video = av_sync.video_pipeline(batch['landmarks'], T, batch['vmean'], batch['vstd'])
+    model = models.StackedBLSTM2StepsModel(batch['seq_len'], batch['wav'], batch['mask'], batch['mean'], batch['std'], 0.0,
+                                           cfg, video)
+    model.build_graph('av-blstm-twosteps')
+    canon_v = init_canonical(model.video_model.engine.layout, seed=17, bias_scale=0.05)
+    canon_av = init_canonical(model.av_model.engine.layout, seed=18, bias_scale=0.05)
+    variables = {'v-blstm/' + k: v for k, v in canon_v.items()}
+    variables.update({'av-blstm-twosteps/' + k: v for k, v in canon_av.items()})
+    model.assign_vars(variables)
+    tsn, net_in = _oracle_inputs(batch, 'av')
+    vid = net_in[:, :, 257:]
+    common = dict(target=tsn, mask=batch['mask'], seq_len=batch['seq_len'])
+    outs_v, _ = oblstm.loss_and_grads('si', dict(net_in=vid, **common), canon_v, 3)
+    outs, ograds = oblstm.loss_and_grads('si', dict(net_in=np.concatenate([outs_v['prediction'], vid], 2), **common), canon_av, 3)
+    assert rel_l2(model.video_prediction.cpu().numpy(), outs_v['prediction']) < TOL
+    assert rel_l2(model.prediction.cpu().numpy(), outs['prediction']) < TOL
+    assert abs(float(model.loss) - float(outs['loss'])) < TOL * abs(float(outs['loss']))
+    _check_grads(model.canonical_gradients(), ograds, 'av-blstm-twosteps')
+    assert set(model.train_vars) == {'av-blstm-twosteps/' + k for k in canon_av}            # models.py:295
+    assert any(k.startswith('v-blstm/') for k in model.all_vars)
+    v0 = model.video_model.engine.theta.clone()
+    a0 = model.av_model.engine.theta.clone()
+    model.train_op()
+    assert torch.equal(model.video_model.engine.theta, v0) and not torch.equal(model.av_model.engine.theta, a0)
+    # summaries (models.py:199-219): flipped [n,F,T,1] images and peak-normalised audio
+    model.feed(dropout_rate=0.0)
+    sm = model.summaries
+    assert set(sm) == {'summary/Target_spectrogram', 'summary/Enhanced_spectrogram', 'summary/Mask',
+                       'summary/Target_audio', 'summary/Enhanced_audio'}
+    kind, img = sm['summary/Target_spectrogram']
+    tgt = model.target_spec_norm
+    assert kind == 'image' and tuple(img.shape) == (B, 257, T, 1)
+    assert torch.equal(img[1, :, :, 0], tgt[1].t().flip(0))
+    kind, aud = sm['summary/Enhanced_audio']
+    assert kind == 'audio' and tuple(aud.shape) == (B, audio_len) and abs(float(aud.abs().max()) - 1.0) < 1e-6
+
+
 def test_train_asr_job(tmp_path, capsys):
     """training_asr.train(config_file) (training_asr.py:23): the shared job loop with the phone-recognition model --
     log-mel statistics as normalisation files, CTC loss / PER as monitored figures, checkpoint under the `asr/<model>` scope."""
@@ -544,9 +623,55 @@ def test_train_asr_job(tmp_path, capsys):
     assert len(rows) == 2
     ctc = [float(r.split('\t')[2].split('|')[1]) for r in rows]
     assert np.isfinite(ctc).all() and ctc[1] < ctc[0]                        # the CTC loss went down
-    ck = checkpoint.load(os.path.join(exp, 'netmodel', 'sinet'))
+    ck = checkpoint.load(os.path.join(exp, 'netmodel', 'asrnet'))                    # training_asr.py:308
     pre = 'asr/a-blstm/cudnn_lstm/stack_bidirectional_rnn/cell_0/bidirectional_rnn/fw/cudnn_compatible_lstm_cell/'
     assert ck[pre + 'kernel'].shape == (80 + 250, 1000)
     # `sinet` is the best-validation checkpoint: written after epoch 1 (step 2) and again after epoch 2 only if it improved
     assert ck['asr/a-blstm/logits/weights'].shape == (500, 34) and int(ck['asr/a-blstm/Variable']) in (2, 4)
     assert model.per.shape == (3,)
+
+
+def test_inference_siasr_job(tmp_path, capsys):
+    """inference_siasr_ctc.infer(...) (inference_siasr_ctc.py:22, the CLI's `inference_siasr`): inpainting model -> enhanced
+    waveform -> phone recogniser ON the enhanced waveform -> `enhanced/<prefix>.wav` + `transcriptions/<prefix>.lbl`."""
+    import os
+    from scipy.io import wavfile
+    from avsi_b200 import inference_siasr_ctc, training, training_asr
+    root = str(tmp_path / 'data')
+    os.makedirs(root)
+    audio_len = 11520
+    T = _write_dataset(root, 4, 2, audio_len, seed=90)
+    np.save(os.path.join(root, 'fb_mean.npy'), np.full(80, 8.0))
+    np.save(os.path.join(root, 'fb_std.npy'), np.full(80, 2.5))
+    common = ('audio_feat_dim = 257\nvideo_feat_dim = 136\naudio_len = %d\nbatch_size = 2\nstarter_learning_rate = 0.001\n'
+              'max_n_epochs = 1\nn_earlystop_epochs = 5\nlr_decay = 1.0\noptimizer_type = adam\nl2 = 0.0\ndropout_rate = 0.0\n' % audio_len)
+    exp_si, exp_asr = str(tmp_path / 'exp' / 'si'), str(tmp_path / 'exp' / 'asr')
+    cfg_si, cfg_asr = str(tmp_path / 'si.config'), str(tmp_path / 'asr.config')
+    with open(cfg_si, 'w') as f:
+        f.write('root_folder = %s\nexp_folder = %s\nmodel = av-blstm\nnet_dim = [250,250,250]\n%saudio_feat_mean = %s\naudio_feat_std = %s\n'
+                % (root, exp_si, common, os.path.join(root, 'mean.npy'), os.path.join(root, 'std.npy')))
+    with open(cfg_asr, 'w') as f:
+        f.write('root_folder = %s\nexp_folder = %s\nmodel = a-blstm\nnet_dim = [250,250]\n%saudio_feat_mean = %s\naudio_feat_std = %s\n'
+                % (root, exp_asr, common, os.path.join(root, 'fb_mean.npy'), os.path.join(root, 'fb_std.npy')))
+    training.train(cfg_si)
+    training_asr.train(cfg_asr)
+    assert os.path.exists(os.path.join(exp_asr, 'netmodel', 'asrnet.npz'))
+    dict_file = str(tmp_path / 'dictionary.txt')
+    with open(dict_file, 'w') as f:
+        f.write('\n'.join('w%d P%02d P%02d' % (i, i, (i * 7) % 33) for i in range(33)))   # 33 phoneme symbols + 33 words
+    # the reference's load_dictionary sorts the distinct symbols: ids index that list
+    from avsi_b200.transcription2phonemes import get_labels, get_phonemes_from_labels, load_dictionary
+    d = load_dictionary(dict_file)
+    assert d[:3] == ['P00', 'P01', 'P02'] and len(d) == 66
+    assert get_phonemes_from_labels(get_labels('P03,SP,P01', d), d) == ['P03', 'P01']
+    capsys.readouterr()
+    audio_out = str(tmp_path / 'audio')
+    hole, asr, per = inference_siasr_ctc.infer(os.path.join(exp_si, 'netmodel'), os.path.join(exp_asr, 'netmodel'),
+                                               os.path.join(root, 'test-set'), audio_out, 'exp0', dict_file, batch_size=2)
+    out = capsys.readouterr().out
+    assert 'Loss hole:' in out and 'PER:' in out and np.isfinite([hole, asr, per]).all() and per >= 0.0
+    for name in ('te_000', 'te_001'):
+        rate, w = wavfile.read(os.path.join(audio_out, name, 'enhanced', 'exp0.wav'))
+        assert rate == 16000 and w.dtype == np.int16 and len(w) == T * 192
+        lbl = open(os.path.join(audio_out, name, 'transcriptions', 'exp0.lbl')).read()
+        assert lbl == '' or all(tok in d for tok in lbl.split(','))
