@@ -54,6 +54,12 @@ SIGNATURES = {
     'avsi_istft_fwd': (c_int, [POINTER(IstftArgs), c_void_p]),
     'avsi_features_to_x0': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int,
                                     c_void_p]),
+    'avsi_cast_pad_f16': (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_int64, c_void_p]),
+    'avsi_leaky_relu': (c_int, [c_void_p, c_int64, c_float, c_void_p, c_void_p]),
+    'avsi_leaky_relu_bwd': (c_int, [c_void_p, c_void_p, c_int64, c_float, c_void_p, c_void_p]),
+    'avsi_masked_time_mean': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    'avsi_masked_time_mean_bwd': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'avsi_time_sum': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'avsi_tile_embedding': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p]),
     'avsi_video_features': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'avsi_expand_mask': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),

@@ -69,11 +69,11 @@ def pick_split_k(m_rows, n_cols, k, target_ctas=296):
 
 
 class BLSTMEngine(object):
-    def __init__(self, in_dim, hidden=250, n_layers=3, out_dim=257, n_classes=0, device='cuda'):
+    def __init__(self, in_dim, hidden=250, n_layers=3, out_dim=257, n_classes=0, device='cuda', dense=()):
         if not torch.cuda.is_available():
             raise _lib.AvsiError('BLSTMEngine needs a CUDA device (there is no CPU fallback)')
         _lib.load()
-        self.layout = ParamLayout(in_dim, hidden, n_layers, out_dim, n_classes)
+        self.layout = ParamLayout(in_dim, hidden, n_layers, out_dim, n_classes, dense=dense)
         self.device = torch.device(device)
         L = self.layout
         n = L.n_params_padded
@@ -97,6 +97,10 @@ class BLSTMEngine(object):
         self.bias_fwd = [torch.zeros(NG, dtype=torch.float32, device=self.device) for _ in range(L.n_layers)]
         self.half['head'] = torch.zeros(L.nop, NY, dtype=torch.float16, device=self.device)
         self.half['headT'] = torch.zeros(NY, L.nop, dtype=torch.float16, device=self.device)
+        for k in range(len(L.dense)):                 # dense layers: [fan_out, Kp] and its transpose [Kp, fan_out]
+            fo, kp = L.index['dw%d' % k][1]
+            self.half['dw%d' % k] = torch.zeros(fo, kp, dtype=torch.float16, device=self.device)
+            self.half['dwT%d' % k] = torch.zeros(kp, fo, dtype=torch.float16, device=self.device)
         self._ws = {}
 
     # ---- parameters ---------------------------------------------------------------------------
@@ -132,6 +136,10 @@ class BLSTMEngine(object):
                        'avsi_gate_bias_prescale')
         _lib.check(lib.avsi_cast_weights(_p(self.view(self.theta, 'head_w')), L.nop, NY, _p(self.half['head']),
                                          _p(self.half['headT']), 0, st), 'avsi_cast_weights')
+        for k in range(len(L.dense)):
+            fo, kp = L.index['dw%d' % k][1]
+            _lib.check(lib.avsi_cast_weights(_p(self.view(self.theta, 'dw%d' % k)), fo, kp, _p(self.half['dw%d' % k]),
+                                             _p(self.half['dwT%d' % k]), 0, st), 'avsi_cast_weights')
 
     # ---- workspaces ---------------------------------------------------------------------------
     def workspace(self, T, B, training=True):

@@ -32,7 +32,10 @@ def cell_prefix(layer, direction):
 
 
 class ParamLayout(object):
-    def __init__(self, in_dim, hidden, n_layers, out_dim=257, n_classes=0):
+    def __init__(self, in_dim, hidden, n_layers, out_dim=257, n_classes=0, dense=()):
+        """dense: extra fully connected layers (name_w, name_b, fan_in, fan_out) living in the same flat buffer -- the
+        speaker-embedding MLP of the SSNN models (models.py:804-809).  Canonical shape [fan_in, fan_out]; stored transposed
+        as block `dw{k}` [fan_out, fan_in rounded up to 8] (the K-major B operand of the forward GEMM) + `db{k}` [fan_out]."""
         if hidden > HP:
             raise ValueError('hidden size %d > %d not supported by the recurrence kernel' % (hidden, HP))
         self.in_dim, self.hidden, self.n_layers = in_dim, hidden, n_layers
@@ -52,6 +55,11 @@ class ParamLayout(object):
         for name, shp in (('head_w', (self.nop, 2 * HP)), ('head_b', (self.nop,))):
             self.blocks.append((name, off, shp))
             off += int(np.prod(shp))
+        self.dense = [tuple(d) for d in dense]
+        for k, (_, _, fan_in, fan_out) in enumerate(self.dense):
+            for name, shp in (('dw%d' % k, (fan_out, round_up(fan_in, 8))), ('db%d' % k, (fan_out,))):
+                self.blocks.append((name, off, shp))
+                off += int(np.prod(shp))
         self.n_params_padded = off
         self.index = {n: (o, s) for n, o, s in self.blocks}
 
@@ -79,6 +87,9 @@ class ParamLayout(object):
         for scope, _, n in self.head_names():
             shapes[scope + '/weights'] = (2 * H, n)
             shapes[scope + '/biases'] = (n,)
+        for name_w, name_b, fan_in, fan_out in self.dense:
+            shapes[name_w] = (fan_in, fan_out)
+            shapes[name_b] = (fan_out,)
         return shapes
 
     def n_params(self):
@@ -121,6 +132,9 @@ class ParamLayout(object):
         for scope, r0, n in self.head_names():
             hw[np.ix_(np.arange(r0, r0 + n), kcols)] = np.asarray(params[scope + '/weights'], dtype).T
             hb[r0:r0 + n] = np.asarray(params[scope + '/biases'], dtype)
+        for k, (name_w, name_b, fan_in, fan_out) in enumerate(self.dense):
+            self.view(flat, 'dw%d' % k)[:, :fan_in] = np.asarray(params[name_w], dtype).T
+            self.view(flat, 'db%d' % k)[:] = np.asarray(params[name_b], dtype)
         return flat
 
     # ---- internal -> canonical ------------------------------------------------------------
@@ -149,6 +163,9 @@ class ParamLayout(object):
         for scope, r0, n in self.head_names():
             out[scope + '/weights'] = hw[np.ix_(np.arange(r0, r0 + n), kcols)].T.copy()
             out[scope + '/biases'] = hb[r0:r0 + n].copy()
+        for k, (name_w, name_b, fan_in, fan_out) in enumerate(self.dense):
+            out[name_w] = self.view(flat, 'dw%d' % k)[:, :fan_in].T.copy()
+            out[name_b] = self.view(flat, 'db%d' % k).copy()
         return out
 
     def pad_mask(self):
@@ -167,13 +184,15 @@ def init_canonical(layout, seed=1, bias_scale=0.0):
         if name.endswith('/kernel'):
             lim = np.sqrt(6.0 / (shp[0] + shp[1]))
             params[name] = rng.uniform(-lim, lim, shp)
-        elif name.endswith('/weights'):
+        elif '/weights' in name:
             w = rng.standard_normal(shp)
             bad = np.abs(w) > 2.0
             while bad.any():
                 w[bad] = rng.standard_normal(int(bad.sum()))
                 bad = np.abs(w) > 2.0
-            params[name] = w / np.sqrt(shp[0])
+            # heads: stddev 1/sqrt(fan_in) (models.py:119); speaker_embedding/weights_1: 1/sqrt(audio_feat_dim) with
+            # fan_in = 2 * audio_feat_dim (models.py:804)
+            params[name] = w / np.sqrt(shp[0] / 2.0 if name.endswith('speaker_embedding/weights_1') else shp[0])
         else:
             params[name] = bias_scale * rng.standard_normal(shp)
     return params

@@ -71,7 +71,7 @@ class StackedBLSTMModel(object):
         self.num_classes = config['num_asr_labels'] if self.MTL else 0
         self.engine = BLSTMEngine(in_dim, self.net_dim[0], self.num_layers,
                                   self.audio_feat_dim if _out_dim is None else _out_dim, self.num_classes,
-                                  device=self.device)
+                                  device=self.device, dense=self._dense_layers())
         self.engine.load_canonical(init_canonical(self.engine.layout, seed=config.get('seed', 0)))
         self.global_step = 0
         self.dropout_seed = int(config.get('seed', 0))
@@ -86,6 +86,10 @@ class StackedBLSTMModel(object):
                   audio_features_mean=audio_feat_mean, audio_features_std=audio_feat_std,
                   dropout_rate=dropout_rate, video_features=video_features, audio_features=audio_features,
                   embeddings=embeddings)
+
+    def _dense_layers(self):
+        """Extra fully connected layers living in the engine's flat parameter buffer (the SSNN models' MLP)."""
+        return ()
 
     # ---- feed contract (training_ctc.py:67-77, 264-275) -------------------------------------------
     _COMPACT = {torch.int16: 0, torch.uint8: 1, torch.bool: 1, torch.int32: 2}
@@ -225,9 +229,7 @@ class StackedBLSTMModel(object):
                                                        0 if video is None else video.shape[2], _p(ws['x0']), L.k0p,
                                                        _lib.stream_ptr()), 'avsi_features_to_x0')
         if self.embedding_dim:
-            emb = self._fed.get('embeddings')
-            if emb is None or tuple(emb.shape) != (B, self.embedding_dim):
-                raise ValueError('embeddings must be fed as [B,%d]' % self.embedding_dim)
+            emb = self._embedding_vectors(res, B, T)
             _lib.check(_lib.load().avsi_tile_embedding(_p(emb), B, T, self.embedding_dim, _p(ws['x0']), L.k0p,
                                                        self.base_in_dim, _lib.stream_ptr()), 'avsi_tile_embedding')
         out = {'ws': ws, 'B': B, 'T': T, 'target_spec_norm': res['spec'], 'target_stft': res['stft'], 'hole': hole}
@@ -235,6 +237,13 @@ class StackedBLSTMModel(object):
         if want_stft:
             self._cache['front'] = out
         return out
+
+    def _embedding_vectors(self, res, B, T):
+        """[B, embedding_dim] f32 vectors to replicate over the frames: here the fed `embeddings` placeholder."""
+        emb = self._fed.get('embeddings')
+        if emb is None or tuple(emb.shape) != (B, self.embedding_dim):
+            raise ValueError('embeddings must be fed as [B,%d]' % self.embedding_dim)
+        return emb
 
     @property
     def target_spec_norm(self):
@@ -385,8 +394,13 @@ class StackedBLSTMModel(object):
             self._stale = False
         out = self._loss_pass(True, want_pred=False)
         self.engine.backward(self._front()['ws'])
+        self._backward_extra(self._front())
         self._cache['bwd_done'] = True
         return out
+
+    def _backward_extra(self, fr):
+        """Gradients of variables outside the BLSTM stack (the SSNN models' MLP); engine.grad already holds the stack's."""
+        return None
 
     def _reduce_gradients(self, out):
         """Data parallel: ONE all-reduce per step over the flat fp32 gradient with the loss scalars riding in its tail.
@@ -613,6 +627,125 @@ class StackedBLSTMEmbeddingModel(StackedBLSTMModel):
             device=device, process_group=process_group, embeddings=embeddings)
 
 
+class StackedBLSTMSSNNModel(StackedBLSTMModel):
+    """Speech inpainting BLSTM model with SSNN (models.py:718-1117, `integration_layer` = 0, the shipped default): a
+    speaker embedding is computed FROM THE CORRUPTED INPUT by a small trainable network and appended to every frame of
+    the BLSTM input.
+
+        inp   = add_delta_features(audio_features, n_delta=1, N=2)          [B,T,2F]                 (models.py:819)
+        l1    = leaky_relu(inp . W1 + b1, 0.3) ; l2 = leaky_relu(l1 . W2 + b2, 0.3) ; l3 = l2 . W3 + b3     (:821-825)
+        emb_b = sum_t l3[b,t] m[b,t] / (sum_t m[b,t] + 1),  m = masks[:, :, 0]                      (:832-836)
+        BLSTM input = concat(net_inputs, tile(emb))                                                 (:846-849)
+
+    Variables `speaker_embedding/weights_{1,2,3}`, `biases_{1,2,3}` ([2F,200], [200,200], [200,200]) train with the rest:
+    the three dense layers run on the tcgen05 GEMM forward and backward, the gradient of emb is the time-sum of
+    dG_0 . W_ih0[embedding columns]."""
+    EMB = 200
+
+    def __init__(self, sequence_lengths, target_sources, masks, audio_feat_mean, audio_feat_std, dropout_rate, config,
+                 audio_features=None, video_features=None, input='a', is_training=True, device='cuda', process_group=None):
+        if config.get('integration_layer', 0):
+            raise NotImplementedError('integration_layer >= 1 (models.py:879-925) is not built')
+        self._F2 = 2 * config['audio_feat_dim']
+
+        class _Shape(object):                          # the base constructor only reads embeddings.shape[-1]
+            shape = (0, self.EMB)
+        super(StackedBLSTMSSNNModel, self).__init__(
+            sequence_lengths, target_sources, masks, audio_feat_mean, audio_feat_std, dropout_rate, config,
+            audio_features=audio_features, video_features=video_features, input=input, is_training=is_training,
+            device=device, process_group=process_group, embeddings=_Shape())
+
+    def feed(self, **kw):
+        kw.pop('embeddings', None)                    # the embedding is computed, never fed
+        return super(StackedBLSTMSSNNModel, self).feed(**kw)
+
+    def _dense_layers(self):
+        E = self.EMB
+        return (('speaker_embedding/weights_1', 'speaker_embedding/biases_1', self._F2, E),
+                ('speaker_embedding/weights_2', 'speaker_embedding/biases_2', E, E),
+                ('speaker_embedding/weights_3', 'speaker_embedding/biases_3', E, E))
+
+    def _embedding_vectors(self, res, B, T):
+        from .blstm import gemm
+        lib, st = _lib.load(), _lib.stream_ptr
+        eng, E, F = self.engine, self.EMB, self.audio_feat_dim
+        M = B * T
+        masks = self._need('masks')[0]
+        ext = self._fed.get('audio_features') if self.external_audio_features else None
+        # audio_features = target_spec_norm * masks (models.py:733-734) unless given
+        af = ext if ext is not None else ap.fused_features(
+            self._need('target_sources')[0], self.frame_len, self.hop, T=T, F=F, mean=self._need('audio_features_mean')[0],
+            std=self._need('audio_features_std')[0], mask=masks, power=1.0, log=True, want_spec=False, want_feat=True)['feat']
+        inp = ap.add_delta_features(af[:, :, :F], n_delta=1, N=2)                   # [B,T,2F] f32
+        kp = eng.layout.index['dw0'][1][1]
+        s = self._ssnn = {'B': B, 'T': T}
+        new = lambda *shape, **kw: torch.empty(*shape, device=self.device, **kw)
+        s['a0'] = new(M, kp, dtype=torch.float16)
+        _lib.check(lib.avsi_cast_pad_f16(_p(inp), self._F2, self._F2, _p(s['a0']), kp, M, st()), 'avsi_cast_pad_f16')
+        x, ldx, K = s['a0'], kp, self._F2
+        for k in range(3):
+            z = s['z%d' % k] = new(M, E, dtype=torch.float32)
+            gemm(_p(x), ldx, _p(eng.half['dw%d' % k]), eng.layout.index['dw%d' % k][1][1], _p(z), E,
+                 _p(eng.view(eng.theta, 'db%d' % k)), M, E, K, 0, 1, tag='gemm_ssnn')
+            if k < 2:
+                a = s['a%d' % (k + 1)] = new(M, E, dtype=torch.float16)
+                _lib.check(lib.avsi_leaky_relu(_p(z), M * E, 0.3, _p(a), st()), 'avsi_leaky_relu')
+                x, ldx, K = a, E, E
+        emb = new(B, E, dtype=torch.float32)
+        s['inv_den'] = new(B, dtype=torch.float32)
+        _lib.check(lib.avsi_masked_time_mean(_p(s['z2']), _p(masks), masks.shape[2], B, T, E, _p(emb), _p(s['inv_den']), st()),
+                   'avsi_masked_time_mean')
+        s['emb'] = emb
+        return emb
+
+    @property
+    def speaker_embedding(self):
+        """[B,200] (models.py:836); `speaker_embedding_ext` = the per-frame outputs times the mask (:833)."""
+        self._front()
+        return self._ssnn['emb']
+
+    @property
+    def speaker_embedding_ext(self):
+        self._front()
+        s = self._ssnn
+        m = self._need('masks')[0][:, :, :1]
+        return s['z2'].view(s['B'], s['T'], self.EMB) * m
+
+    def _backward_extra(self, fr):
+        from .blstm import A_IL, NG, gemm, pick_split_k
+        lib, st = _lib.load(), _lib.stream_ptr
+        eng, E, s = self.engine, self.EMB, self._ssnn
+        B, T = s['B'], s['T']
+        M = B * T
+        L = eng.layout
+        ws = fr['ws']
+        masks = self._need('masks')[0]
+        new = lambda *shape, **kw: torch.empty(*shape, device=self.device, **kw)
+        # d emb: columns [base_in_dim, +E) of dX_0 = dG_0 . W_ih0, summed over the frames (the embedding was replicated)
+        dxe = new(M, E, dtype=torch.float32)
+        wT = eng.half['wihT0'].data_ptr() + self.base_in_dim * NG * 2               # rows = input columns of layer 0
+        gemm(_p(ws['G'][0]), NG, wT, NG, _p(dxe), E, None, M, E, NG, 0, 1, tag='gemm_ssnn', layout=A_IL)
+        demb = new(B, E, dtype=torch.float32)
+        _lib.check(lib.avsi_time_sum(_p(dxe), E, T, B, E, _p(demb), st()), 'avsi_time_sum')
+        d = new(M, E, dtype=torch.float16)                                          # d l3 (batch-major rows)
+        _lib.check(lib.avsi_masked_time_mean_bwd(_p(demb), _p(masks), masks.shape[2], _p(s['inv_den']), B, T, E, _p(d), st()),
+                   'avsi_masked_time_mean_bwd')
+        g = eng.grad
+        for k in (2, 1, 0):
+            a_in = s['a%d' % k]
+            kp = L.index['dw%d' % k][1][1]
+            lda = a_in.shape[1]
+            # dW_k^T [E, kp] += d^T . a_in ; db_k = colsum(d) ; d a_in = d . W_k^T
+            gemm(_p(d), E, _p(a_in), lda, _p(eng.view(g, 'dw%d' % k)), kp, None, E, lda if k else kp, M, 1, 2,
+                 pick_split_k(E, kp, M), tag='gemm_ssnn')
+            _lib.check(lib.avsi_colsum_f16(_p(d), E, M, 0, E, _p(eng.view(g, 'db%d' % k)), st()), 'avsi_colsum_f16')
+            if k > 0:
+                da = new(M, E, dtype=torch.float32)
+                gemm(_p(d), E, _p(eng.half['dwT%d' % k]), E, _p(da), E, None, M, E, E, 0, 1, tag='gemm_ssnn')
+                d = new(M, E, dtype=torch.float16)
+                _lib.check(lib.avsi_leaky_relu_bwd(_p(s['z%d' % (k - 1)]), _p(da), M * E, 0.3, _p(d), st()), 'avsi_leaky_relu_bwd')
+
+
 class StackedBLSTM2StepsModel(object):
     """2-steps speech inpainting BLSTM model (models.py:240-317): a video-only model `v-blstm` predicts the spectrogram
     from the landmark motion vectors; its prediction replaces the masked spectrogram as the audio input of the
@@ -692,4 +825,6 @@ MODEL_REGISTRY = {
     'a-blstm-emb': (StackedBLSTMEmbeddingModel, 'a'), 'v-blstm-emb': (StackedBLSTMEmbeddingModel, 'v'),
     'av-blstm-emb': (StackedBLSTMEmbeddingModel, 'av'),
     'av-blstm-twosteps': (StackedBLSTM2StepsModel, 'av'),
+    'a-blstm-ssnn': (StackedBLSTMSSNNModel, 'a'), 'v-blstm-ssnn': (StackedBLSTMSSNNModel, 'v'),
+    'av-blstm-ssnn': (StackedBLSTMSSNNModel, 'av'),
 }

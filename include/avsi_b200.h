@@ -126,6 +126,22 @@ int avsi_istft_fwd(const avsi_istft_args* args, void* stream);
 int avsi_features_to_x0(const float* feat, const float* mean, const float* stdev, const float* video, int B, int T,
                         int F, int V, uint16_t* x0, int ldx, void* stream);
 
+/* Speaker-embedding sub-network of the SSNN models (models.py:800-842): what sits between its dense layers (which run
+ * on avsi_gemm_f16), forward and backward.  Rows batch-major (r = b*T + t).
+ *   avsi_cast_pad_f16          f32 [rows, cols] (pitch ld_src) -> f16 [rows, ld_dst], columns >= cols zero
+ *   avsi_leaky_relu            tf.nn.leaky_relu(z, alpha) -> f16          avsi_leaky_relu_bwd   dz = da * (z > 0 ? 1 : alpha) -> f16
+ *   avsi_masked_time_mean      out[b,n] = sum_t x[b,t,n] m[b,t] / (sum_t m[b,t] + 1), m[b,t] = mask[(b*T+t)*mask_ld]  (:834-836)
+ *   avsi_masked_time_mean_bwd  dx[b,t,n] = d_out[b,n] m[b,t] inv_den[b] -> f16
+ *   avsi_time_sum              out[b,n] = sum_t x[(t*B+b)*ld + n]: gradient of a vector replicated over the frames */
+int avsi_cast_pad_f16(const float* src, int ld_src, int cols, uint16_t* dst, int ld_dst, int64_t rows, void* stream);
+int avsi_leaky_relu(const float* z, int64_t n, float alpha, uint16_t* out, void* stream);
+int avsi_leaky_relu_bwd(const float* z, const float* da, int64_t n, float alpha, uint16_t* dz, void* stream);
+int avsi_masked_time_mean(const float* x, const float* mask, int mask_ld, int B, int T, int N, float* out,
+                          float* inv_den, void* stream);
+int avsi_masked_time_mean_bwd(const float* d_out, const float* mask, int mask_ld, const float* inv_den, int B, int T,
+                              int N, uint16_t* dx, void* stream);
+int avsi_time_sum(const float* x, int ld, int T, int B, int N, float* out, void* stream);
+
 /* Per-utterance vector replicated over the frames into columns [col0, col0 + E) of the time-major fp16 network input:
  * tf.tile(tf.expand_dims(embeddings, 1), [1, T, 1]) + tf.concat([net_inputs, tiles], 2) of the embedding models
  * (models.py:1204-1206; the SSNN models' speaker embedding, models.py:846-849).  emb [B,E] f32. */

@@ -132,6 +132,31 @@ def forward_si(net_in, target, mask, seq_len, params, n_layers, l2=0.0, drop=Non
                 loss_func=loss_func, loss_hole=loss_hole, loss_valid=loss_valid, rnn=rnn)
 
 
+def speaker_embedding(delta_inp, mask, params):
+    """StackedBLSTMSSNNModel.speaker_embedding (models.py:800-842).  delta_inp = add_delta_features(audio_features, 1, 2)
+    [B,T,2F] (a constant of the parameters), mask [B,T,F].  Returns (embedding [B,200], per-frame masked outputs [B,T,200])."""
+    lrelu = torch.nn.functional.leaky_relu
+    B, T, _ = delta_inp.shape
+    x = delta_inp.reshape(B * T, -1)
+    l1 = lrelu(x @ params['speaker_embedding/weights_1'] + params['speaker_embedding/biases_1'], 0.3)      # :821-822
+    l2 = lrelu(l1 @ params['speaker_embedding/weights_2'] + params['speaker_embedding/biases_2'], 0.3)     # :823-824
+    l3 = l2 @ params['speaker_embedding/weights_3'] + params['speaker_embedding/biases_3']                 # :825
+    emb_mask = mask[:, :, 0]                                                                               # :832
+    ext = l3.reshape(B, T, -1) * emb_mask[:, :, None]                                                      # :833
+    return ext.sum(1) / (emb_mask.sum(1) + 1)[:, None], ext                                                # :834-835
+
+
+def forward_si_ssnn(net_in, delta_inp, target, mask, seq_len, params, n_layers, l2=0.0):
+    """StackedBLSTMSSNNModel with integration_layer 0 (models.py:844-849): the embedding tiled over the frames and
+    concatenated to the network input; everything after is forward_si."""
+    emb, ext = speaker_embedding(delta_inp, mask, params)
+    x = torch.cat([net_in, emb[:, None, :].expand(-1, net_in.shape[1], -1)], dim=2)
+    out = forward_si(x, target, mask, seq_len, params, n_layers, l2=l2)
+    out['speaker_embedding'] = emb
+    out['speaker_embedding_ext'] = ext
+    return out
+
+
 def forward_mtl(net_in, target, mask, seq_len, labels, lab_len, params, n_layers, ctc_weight, l2=0.0, drop=None):
     """StackedBLSTMSSNNCTCLossModel (models.py:1873-1963), the runnable MTL model.
     Blank label = n_classes - 1 (tf.nn.ctc_loss convention)."""
@@ -173,6 +198,8 @@ def loss_and_grads(kind, inputs, params_np, n_layers, dtype=torch.float64, **kw)
         out = forward_asr(tin['net_in'], tin['seq_len'], tin['labels'].long(), tin['lab_len'], params, n_layers, **kw)
     elif kind == 'si':
         out = forward_si(tin['net_in'], tin['target'], tin['mask'], tin['seq_len'], params, n_layers, **kw)
+    elif kind == 'ssnn':
+        out = forward_si_ssnn(tin['net_in'], tin['delta_inp'], tin['target'], tin['mask'], tin['seq_len'], params, n_layers, **kw)
     else:
         out = forward_mtl(tin['net_in'], tin['target'], tin['mask'], tin['seq_len'], tin['labels'].long(),
                           tin['lab_len'], params, n_layers, **kw)

@@ -550,6 +550,61 @@ def test_embedding_model_forward_loss_gradients():
         model.prediction
 
 
+@pytest.mark.parametrize('model_name,B,audio_len', [('av-blstm-ssnn', 3, 4800), ('a-blstm-ssnn', 230, 1920)])
+def test_ssnn_model_forward_loss_gradients(model_name, B, audio_len):
+    """StackedBLSTMSSNNModel (models.py:718-1117, integration_layer 0): the speaker embedding computed from the corrupted
+    spectrogram by the trainable 3-layer network and appended to every input frame -- forward values, the embedding
+    itself and the gradients of ALL variables (BLSTM stack, head, speaker_embedding/*) against the float64 oracle."""
+    from avsi_b200 import av_sync, models, synth
+    from avsi_b200.layout import init_canonical
+    from oracle import blstm as oblstm
+    from oracle import stft as ostft
+    batch = synth.make_batch(B, audio_len=audio_len, seed=24)
+    T = batch['T']
+    cfg = synth.default_config(model_name, batch_size=B, audio_len=audio_len)
+    cls, inp = models.MODEL_REGISTRY[model_name]
+    video = av_sync.video_pipeline(batch['landmarks'], T, batch['vmean'], batch['vstd'])
+    model = cls(batch['seq_len'], batch['wav'], batch['mask'], batch['mean'], batch['std'], 0.0, cfg,
+                video_features=video if inp != 'a' else None, input=inp)
+    base = {'a': 257, 'av': 393}[inp]
+    assert model.engine.layout.in_dim == base + 200
+    canon = init_canonical(model.engine.layout, seed=25, bias_scale=0.05)
+    assert canon['speaker_embedding/weights_1'].shape == (514, 200) and canon['speaker_embedding/biases_3'].shape == (200,)
+    model.assign_vars(canon)
+    tsn, net_in = _oracle_inputs(batch, inp)
+    audio_feat = tsn * batch['mask']
+    delta_inp = ostft.add_delta_features(audio_feat, n_delta=1, N=2)
+    outs, ograds = oblstm.loss_and_grads('ssnn', dict(net_in=net_in, delta_inp=delta_inp, target=tsn, mask=batch['mask'],
+                                                      seq_len=batch['seq_len']), canon, 3)
+    assert rel_l2(model.speaker_embedding.cpu().numpy(), outs['speaker_embedding']) < TOL
+    assert rel_l2(model.speaker_embedding_ext.cpu().numpy(), outs['speaker_embedding_ext']) < TOL
+    assert rel_l2(model.prediction.cpu().numpy(), outs['prediction']) < TOL
+    assert abs(float(model.loss) - float(outs['loss'])) < TOL * abs(float(outs['loss']))
+    grads = model.canonical_gradients()
+    # The whole gradient against the full-precision oracle: TOL.  Per variable the first dense layer is the delicate one:
+    # leaky ReLU has a kink, so a pre-activation whose sign differs between fp16-operand and float64 arithmetic switches its
+    # derivative between 1 and 0.3 (the same in any arithmetic narrower than the oracle's).  The kernels' own arithmetic
+    # is therefore held per variable to 2 x TOL against the oracle evaluated AT THE OPERANDS THE TENSOR CORES SEE (inputs
+    # and matrices rounded through fp16), and to 5 x TOL against the full-precision one.
+    ga = np.concatenate([grads[k].ravel() for k in sorted(ograds)])
+    gb = np.concatenate([ograds[k].ravel() for k in sorted(ograds)])
+    assert rel_l2(ga, gb) < TOL, rel_l2(ga, gb)
+    canon16 = {k: (_through_f16(v) if ('kernel' in k or 'weights' in k) else v) for k, v in canon.items()}
+    _, ograds16 = oblstm.loss_and_grads('ssnn', dict(net_in=_through_f16(net_in), delta_inp=_through_f16(delta_inp), target=tsn,
+                                                     mask=batch['mask'], seq_len=batch['seq_len']), canon16, 3)
+    for k in ograds:
+        if np.linalg.norm(ograds[k]) > 0:
+            assert rel_l2(grads[k], ograds16[k]) < 2 * TOL, (k, rel_l2(grads[k], ograds16[k]))
+            assert rel_l2(grads[k], ograds[k]) < 5 * TOL, (k, rel_l2(grads[k], ograds[k]))
+    assert all(np.linalg.norm(ograds[k]) > 0 for k in ('speaker_embedding/weights_1', 'speaker_embedding/weights_3',
+                                                       'speaker_embedding/biases_2'))
+    th0 = model.engine.theta.clone()
+    model.train_op()
+    moved = model.engine.export_canonical()
+    assert not np.array_equal(moved['speaker_embedding/weights_2'], canon['speaker_embedding/weights_2'].astype(np.float32))
+    assert not torch.equal(th0, model.engine.theta)
+
+
 def test_two_step_model_forward_loss_gradients_and_summaries():
     """StackedBLSTM2StepsModel (models.py:240-317): v-blstm predicts the spectrogram from the motion vectors, its
     prediction is the audio input of av-blstm-twosteps; only the av model's variables are trained."""
