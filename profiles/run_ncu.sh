@@ -2,9 +2,9 @@
 # Profiling recipe (B200_PROFILING.md): plain run first, then the launch list, then --set full
 # captures of the top kernels.  Run under gpurun on ONE GPU; outputs land in gpurun_out/.
 # usage: bash profiles/run_ncu.sh <tag> [batch]
-TAG=${1:-r01}
+TAG=${1:-r02}
 BATCH=${2:-2048}
-CMD="python bench.py --steps 1 --warmup 3 --batch $BATCH --no-cpu-baseline"
+CMD="python bench.py --steps 1 --warmup 3 --batch $BATCH --no-cpu-baseline --no-extras"
 mkdir -p gpurun_out
 $CMD > gpurun_out/ncu_plain_$TAG.json 2> gpurun_out/ncu_plain_$TAG.err || { echo "plain run failed"; tail -5 gpurun_out/ncu_plain_$TAG.err; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > /dev/null 2>&1
