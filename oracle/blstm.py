@@ -132,24 +132,33 @@ def forward_si(net_in, target, mask, seq_len, params, n_layers, l2=0.0, drop=Non
                 loss_func=loss_func, loss_hole=loss_hole, loss_valid=loss_valid, rnn=rnn)
 
 
-def speaker_embedding(delta_inp, mask, params):
+def speaker_embedding(delta_inp, mask, params, slopes=None):
     """StackedBLSTMSSNNModel.speaker_embedding (models.py:800-842).  delta_inp = add_delta_features(audio_features, 1, 2)
-    [B,T,2F] (a constant of the parameters), mask [B,T,F].  Returns (embedding [B,200], per-frame masked outputs [B,T,200])."""
-    lrelu = torch.nn.functional.leaky_relu
+    [B,T,2F] (a constant of the parameters), mask [B,T,F].  Returns (embedding [B,200], per-frame masked outputs [B,T,200]).
+
+    slopes = (s1, s2), each [B*T,200] of {1, 0.3}: evaluate the two leaky ReLUs with a GIVEN activation pattern
+    (z * slope) instead of the sign of this evaluation's own pre-activations.  Identical wherever the signs agree; lets a
+    test separate the kink of the activation (a pre-activation within rounding error of 0 switches the derivative between
+    1 and 0.3) from the arithmetic of an implementation."""
     B, T, _ = delta_inp.shape
     x = delta_inp.reshape(B * T, -1)
-    l1 = lrelu(x @ params['speaker_embedding/weights_1'] + params['speaker_embedding/biases_1'], 0.3)      # :821-822
-    l2 = lrelu(l1 @ params['speaker_embedding/weights_2'] + params['speaker_embedding/biases_2'], 0.3)     # :823-824
+
+    def lrelu(z, k):
+        if slopes is None:
+            return torch.nn.functional.leaky_relu(z, 0.3)
+        return z * torch.as_tensor(np.asarray(slopes[k], np.float64), dtype=z.dtype)
+    l1 = lrelu(x @ params['speaker_embedding/weights_1'] + params['speaker_embedding/biases_1'], 0)        # :821-822
+    l2 = lrelu(l1 @ params['speaker_embedding/weights_2'] + params['speaker_embedding/biases_2'], 1)       # :823-824
     l3 = l2 @ params['speaker_embedding/weights_3'] + params['speaker_embedding/biases_3']                 # :825
     emb_mask = mask[:, :, 0]                                                                               # :832
     ext = l3.reshape(B, T, -1) * emb_mask[:, :, None]                                                      # :833
     return ext.sum(1) / (emb_mask.sum(1) + 1)[:, None], ext                                                # :834-835
 
 
-def forward_si_ssnn(net_in, delta_inp, target, mask, seq_len, params, n_layers, l2=0.0):
+def forward_si_ssnn(net_in, delta_inp, target, mask, seq_len, params, n_layers, l2=0.0, slopes=None):
     """StackedBLSTMSSNNModel with integration_layer 0 (models.py:844-849): the embedding tiled over the frames and
     concatenated to the network input; everything after is forward_si."""
-    emb, ext = speaker_embedding(delta_inp, mask, params)
+    emb, ext = speaker_embedding(delta_inp, mask, params, slopes)
     x = torch.cat([net_in, emb[:, None, :].expand(-1, net_in.shape[1], -1)], dim=2)
     out = forward_si(x, target, mask, seq_len, params, n_layers, l2=l2)
     out['speaker_embedding'] = emb
