@@ -68,6 +68,8 @@ SIGNATURES = {
     'avsi_parse_av_sample_host': (c_int, [c_void_p, c_uint64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
                                           c_void_p, c_int64, c_void_p, c_int, c_void_p]),
     'avsi_crc32c_host': (c_uint32, [c_void_p, c_uint64, c_uint32]),
+    'avsi_spectrogram': (c_int, [c_void_p, c_int64, c_float, c_int, c_void_p, c_void_p]),
+    'avsi_log_mel': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_float, c_void_p, c_void_p]),
     'avsi_preemphasis': (c_int, [c_void_p, c_int, c_int, c_float, c_void_p, c_void_p]),
     'avsi_mfcc': (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
     'avsi_delta_features': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),

@@ -182,12 +182,13 @@ def get_stft(sources, sample_rate=16000, window_size=25, step_size=10, n_fft=512
 
 
 def get_spectrogram(stfts, power=1, log=False, out_shape=[0, 0, 0]):
-    """audio_processing.py:45-56 on an already computed STFT tensor (element-wise, torch)."""
-    spec = torch.abs(stfts)
-    if power != 1:
-        spec = spec ** power
-    if log:
-        spec = torch.log(spec + 1e-6)
+    """audio_processing.py:45-56 on an already computed complex STFT tensor: one element-wise kernel."""
+    if not (torch.is_tensor(stfts) and stfts.is_cuda and stfts.is_complex()):
+        raise _lib.AvsiError('get_spectrogram needs a complex CUDA tensor (no CPU fallback)')
+    z = torch.view_as_real(stfts.to(torch.complex64).contiguous())
+    spec = torch.empty(stfts.shape, dtype=torch.float32, device=stfts.device)
+    _lib.check(_lib.load().avsi_spectrogram(_lib.ptr(z), spec.numel(), float(power), int(bool(log)), _lib.ptr(spec),
+                                            _lib.stream_ptr()), 'avsi_spectrogram')
     return _sliced(spec, out_shape)
 
 
@@ -196,9 +197,17 @@ def get_log_mel_spectrogram(spectrograms, sample_rate=16000, num_spec_bins=257, 
     """audio_processing.py:59-72 on a spectrogram tensor (out_shape is ignored there too)."""
     if upper_edge_freq is None:
         upper_edge_freq = sample_rate / 2
-    m = linear_to_mel_weight_matrix(num_mel_bins, num_spec_bins, sample_rate, lower_edge_freq, upper_edge_freq)
-    m = torch.tensor(m, dtype=spectrograms.dtype, device=spectrograms.device)
-    return torch.log(torch.tensordot(spectrograms, m, dims=1) + eps)
+    if not (torch.is_tensor(spectrograms) and spectrograms.is_cuda):
+        raise _lib.AvsiError('get_log_mel_spectrogram needs a CUDA tensor (no CPU fallback)')
+    key = (str(spectrograms.device), num_mel_bins, num_spec_bins, sample_rate, lower_edge_freq, upper_edge_freq)
+    if key not in _MEL:
+        m = linear_to_mel_weight_matrix(num_mel_bins, num_spec_bins, sample_rate, lower_edge_freq, upper_edge_freq)
+        _MEL[key] = torch.tensor(m, dtype=torch.float32, device=spectrograms.device).contiguous()
+    x = spectrograms.float().contiguous()
+    out = torch.empty(x.shape[:-1] + (num_mel_bins,), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.load().avsi_log_mel(_lib.ptr(x), _lib.ptr(_MEL[key]), x.numel() // x.shape[-1], x.shape[-1], num_mel_bins,
+                                        float(eps), _lib.ptr(out), _lib.stream_ptr()), 'avsi_log_mel')
+    return out
 
 
 def preemphasis(sources, alpha=0.95):

@@ -65,6 +65,35 @@ inline int grid_for(long long n) {
   return (int)(b < cap ? (b > 0 ? b : 1) : cap);
 }
 
+// get_spectrogram (audio_processing.py:45-50) on an already computed complex STFT: |z| ** power, log(. + 1e-6)
+__global__ void __launch_bounds__(256)
+spectrogram_kernel(const float2* __restrict__ stft, long long n, float power, int log_flag, float* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float2 z = stft[i];
+    float v = sqrtf(z.x * z.x + z.y * z.y);
+    if (power == 2.f) v = v * v;
+    else if (power != 1.f) v = powf(v, power);
+    out[i] = log_flag ? logf(v + 1e-6f) : v;
+  }
+}
+
+// get_log_mel_spectrogram (audio_processing.py:59-66) on a spectrogram tensor: log(spec . M + eps), M [nbins, n_mel] dense f32
+// (tf.tensordot + tf.log).  One warp per row; fp32 accumulation in bin order.
+__global__ void __launch_bounds__(256)
+log_mel_kernel(const float* __restrict__ spec, const float* __restrict__ mel_w, long long rows, int nbins, int n_mel,
+               float eps, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  for (long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows;
+       r += (long long)gridDim.x * (blockDim.x >> 5)) {
+    const float* x = spec + r * nbins;
+    for (int m = lane; m < n_mel; m += 32) {
+      float acc = 0.f;
+      for (int k = 0; k < nbins; ++k) acc = fmaf(__ldg(x + k), __ldg(mel_w + (long long)k * n_mel + m), acc);
+      out[r * n_mel + m] = logf(acc + eps);
+    }
+  }
+}
+
 }  // namespace avsi
 
 extern "C" int avsi_preemphasis(const float* src, int B, int N, float alpha, float* dst, void* stream) {
@@ -95,6 +124,25 @@ extern "C" int avsi_delta_features(const float* src, int ld_src, float* dst, int
   for (int i = 1; i <= N; ++i) den += 2 * i * i;
   delta_kernel<<<grid_for((long long)B * T * F), 256, 0, (cudaStream_t)stream>>>(src, ld_src, dst, ld_dst, B, T, F, N,
                                                                                 1.0f / (float)den);
+  AVSI_LAUNCH_CHECK();
+  return AVSI_OK;
+}
+
+extern "C" int avsi_spectrogram(const float* stft_c64, int64_t n, float power, int log_flag, float* out, void* stream) {
+  using namespace avsi;
+  AVSI_REQUIRE(stft_c64 && out && n > 0, "args");
+  int blocks = (int)min((long long)(n + 255) / 256, (long long)num_sms() * 16);
+  spectrogram_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(stft_c64), (long long)n, power, log_flag, out);
+  AVSI_LAUNCH_CHECK();
+  return AVSI_OK;
+}
+
+extern "C" int avsi_log_mel(const float* spec, const float* mel_w, int64_t rows, int nbins, int n_mel, float eps, float* out,
+                            void* stream) {
+  using namespace avsi;
+  AVSI_REQUIRE(spec && mel_w && out && rows > 0 && nbins > 0 && n_mel > 0, "args");
+  int blocks = (int)min((long long)(rows + 7) / 8, (long long)num_sms() * 16);
+  log_mel_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(spec, mel_w, (long long)rows, nbins, n_mel, eps, out);
   AVSI_LAUNCH_CHECK();
   return AVSI_OK;
 }

@@ -25,7 +25,7 @@ def masked_waveforms(wav, mask, oracle_phase=False, window_size=24, step_size=12
     phase_src = masked_stft
     if oracle_phase:
         phase_src = ap.fused_features(wav, frame_len, hop, T=T, F=F, log=False, want_stft=True, want_spec=False)['stft']
-    return ap.reconstruct_from(torch.abs(masked_stft), phase_src, num_samples=wav.shape[1], window_size=window_size,
+    return ap.reconstruct_from(ap.get_spectrogram(masked_stft), phase_src, num_samples=wav.shape[1], window_size=window_size,
                                step_size=step_size)
 
 

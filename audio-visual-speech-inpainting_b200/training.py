@@ -127,6 +127,8 @@ def _train(config_file, max_steps, build_model, feed_batch, _losses, best_name='
     rank = dist.get_rank() if dist.is_initialized() else 0
     world = dist.get_world_size() if dist.is_initialized() else 1
     pg = dist.group.WORLD if world > 1 else None
+    if world > 1:
+        parallel.bind_to_gpu_numa(torch.cuda.current_device())
     data_path_train = os.path.join(config['root_folder'], 'training-set')
     data_path_val = os.path.join(config['root_folder'], 'validation-set')
     exp_path = config['exp_folder']

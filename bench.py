@@ -388,6 +388,8 @@ def main():
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local_rank)
+    from avsi_b200 import parallel as _parallel
+    numa_cores = 0 if os.environ.get('AVSI_NO_NUMA_BIND') else _parallel.bind_to_gpu_numa(local_rank)
     pg = None
     if world > 1:
         # NCCL prints its version banner to STDOUT at NCCL_DEBUG=VERSION/WARN; stdout carries the one JSON line
@@ -488,6 +490,7 @@ def main():
         'step_frac_of_tensor_roofline': value / world * 6.62e9 * (T / 250.0) / (pk['bf16_tflops_sustained'] * 1e12),
         'kernels': kernels,
         'library_digest': library_digest(),
+        'host_cores_bound_to_gpu_numa_node': numa_cores,
     }
     if extras is not None:
         line['extra'] = extras

@@ -102,6 +102,13 @@ int avsi_frontend_fwd(const avsi_frontend_args* args, void* stream);
  *   avsi_delta_features  sum_{i<=N} i (f[t+i] - f[t-i]) / (2 sum i^2), edge frames replicated   delta :84-93
  *                        (src/dst rows of ld_src/ld_dst floats: add_delta_features writes the orders side by side) */
 int avsi_preemphasis(const float* src, int B, int N, float alpha, float* dst, void* stream);
+/* get_spectrogram / get_log_mel_spectrogram as stand-alone ops on tensors the caller already holds (audio_processing.py:45-50,
+ * :59-66; inside the models the same arithmetic is fused into avsi_frontend_fwd):
+ *   avsi_spectrogram  out = |stft| ** power, then log(. + 1e-6) if log_flag; stft_c64 = n complex64 values
+ *   avsi_log_mel      out[r, m] = log(sum_k spec[r, k] mel_w[k, m] + eps); spec [rows, nbins], mel_w [nbins, n_mel] f32 */
+int avsi_spectrogram(const float* stft_c64, int64_t n, float power, int log_flag, float* out, void* stream);
+int avsi_log_mel(const float* spec, const float* mel_w, int64_t rows, int nbins, int n_mel, float eps, float* out,
+                 void* stream);
 int avsi_mfcc(const float* logmel, int64_t rows, int n_mel, int n_mfcc, float* out, void* stream);
 int avsi_delta_features(const float* src, int ld_src, float* dst, int ld_dst, int B, int T, int F, int N, void* stream);
 

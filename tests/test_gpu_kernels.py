@@ -245,6 +245,20 @@ def test_frontend_power2_logmel_and_plain_stft():
     sp = ap.get_spectrogram(ap.get_stft(w, window_size=24, step_size=12), log=True).cpu().numpy()
     ref_sp = ostft.get_spectrogram(ostft.get_stft(wav.astype(np.float64), window_size=24, step_size=12), log=True)
     assert rel_l2(np.exp(sp), np.exp(ref_sp)) < 1e-5
+    # the stand-alone signatures of audio_processing.py:45-72 on tensors the caller already holds (own kernels, no torch math)
+    st24 = ap.get_stft(w, window_size=24, step_size=12)
+    ref24 = ostft.get_stft(wav.astype(np.float64), window_size=24, step_size=12)
+    for power in (1, 2, 0.5):
+        got = ap.get_spectrogram(st24, power=power, out_shape=[2, 50, 200]).cpu().numpy()
+        assert got.shape == (2, 50, 200)
+        assert rel_l2(got, ostft.get_spectrogram(ref24, power=power)[:2, :50, :200]) < 1e-5
+    pw = ap.get_spectrogram(st24, power=2)
+    lm2 = ap.get_log_mel_spectrogram(pw).cpu().numpy()
+    ref_lm2 = ostft.get_log_mel_spectrogram(ostft.get_spectrogram(ref24, power=2))
+    assert lm2.shape == ref_lm2.shape and rel_l2(np.exp(lm2), np.exp(ref_lm2)) < 1e-5
+    lm40 = ap.get_log_mel_spectrogram(pw, num_mel_bins=40, lower_edge_freq=20, upper_edge_freq=4000).cpu().numpy()
+    ref40 = ostft.get_log_mel_spectrogram(ostft.get_spectrogram(ref24, power=2), num_mel_bins=40, lower_edge_freq=20, upper_edge_freq=4000)
+    assert rel_l2(np.exp(lm40), np.exp(ref40)) < 1e-5
 
 
 @pytest.mark.parametrize('B,N,masked', [(3, 48000, False), (5, 4802, True), (2, 320000, True), (1, 100, False),
