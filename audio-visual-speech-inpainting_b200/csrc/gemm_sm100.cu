@@ -452,6 +452,7 @@ gemm_f16_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 // ---------------------------------------------------------------- debug / validation GEMM (CUDA cores)
+#ifdef AVSI_DEBUG_KERNELS   // CUDA-core bisecting kernel: compiled only into debug builds (nvcc -DAVSI_DEBUG_KERNELS), never into the product library
 // Same contract as the tensor-core kernel; selected only by AVSI_GEMM_DEBUG_SIMT=1 to bisect
 // failures.  Never used silently.
 __global__ void __launch_bounds__(256)
@@ -487,6 +488,8 @@ gemm_simt_kernel(const uint16_t* __restrict__ A, int lda, const uint16_t* __rest
 }
 
 // ---------------------------------------------------------------- host side
+#endif  // AVSI_DEBUG_KERNELS
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -639,6 +642,7 @@ extern "C" int avsi_gemm_f16(const uint16_t* A, int lda, const uint16_t* B, int 
   GemmParams p{C, bias, ldc, M, N, K, trans, out_mode, split_k, layout & 1, (layout >> 1) & 1, (layout >> 2) & 1};
   cudaStream_t st = (cudaStream_t)stream;
 
+#ifdef AVSI_DEBUG_KERNELS
   AVSI_ENV_CACHE(debug_simt, env_is("AVSI_GEMM_DEBUG_SIMT", "1"));
   if (debug_simt && layout == 0) {
     GemmParams q = p;
@@ -648,6 +652,7 @@ extern "C" int avsi_gemm_f16(const uint16_t* A, int lda, const uint16_t* B, int 
     AVSI_LAUNCH_CHECK();
     return AVSI_OK;
   }
+#endif
 
   // tile width: wide tiles for wide outputs, narrow ones so that small-N problems still fill the chip
   // tile width: 128 (3 stages, 2 CTAs/SM) by default; 256 (4 stages, 1 CTA/SM) for long-K problems

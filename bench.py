@@ -344,6 +344,26 @@ def library_digest():
         return None
 
 
+KERNEL_SOURCES = {      # bench span name -> the CUDA sources its dominant kernel is built from (ncu figures are valid for these)
+    'lstm_bwd': ('lstm4_bwd.cu', 'common.cuh', 'sm100_ptx.cuh'),
+    'lstm_fwd': ('lstm4.cu', 'common.cuh', 'sm100_ptx.cuh'),
+    'frontend': ('frontend.cu', 'common.cuh'),
+    'gemm_proj_fwd': ('gemm_sm100.cu', 'common.cuh', 'sm100_ptx.cuh'),
+}
+
+
+def kernel_source_digest(name):
+    """sha256 (16 hex digits) of the sources of one kernel: ncu-derived per-kernel figures carry it and go stale with it."""
+    import hashlib
+    h = hashlib.sha256()
+    try:
+        for f in KERNEL_SOURCES[name]:
+            h.update(open(os.path.join(ROOT, 'audio-visual-speech-inpainting_b200', 'csrc', f), 'rb').read())
+    except Exception:
+        return None
+    return h.hexdigest()[:16]
+
+
 def run_extras(args, pg, dev, rank, world, pk):
     """Few-step runs of the other BASELINE configurations on the same GPUs (resident inputs, CUDA events, max over ranks):
     configs[2] AV-MTL-SI with the CTC phone head, configs[4] 20 s utterances, and the batch sweep of configs[1]."""
@@ -429,16 +449,20 @@ def main():
     value = utt / (ms * 1e-3)
     kernels = kernel_table(prof, args.steps)
 
-    # roofline.traffic: dram bytes per launch from the committed ncu --set full captures, valid only for the library
-    # build they were taken on (profiles/ncu_traffic.json carries the source digest; a stale file yields null)
-    traffic, traffic_note = {}, 'no ncu capture of this workload committed'
+    # roofline.traffic: dram bytes per launch from the committed ncu --set full captures, valid only for the kernel sources
+    # they were taken on (profiles/ncu_traffic.json carries a digest of each kernel's sources; a stale entry yields null)
+    traffic, traffic_note = {}, {}
     try:
         tj = json.load(open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')))
         if tj['workload'] == {'batch': B, 'audio_len': args.audio_len}:
-            if tj.get('library_digest') in (None, library_digest()):
-                traffic, traffic_note = tj, 'profiles/ncu_traffic.json (%s)' % tj.get('captures', 'ncu --set full')
-            else:
-                traffic_note = 'profiles/ncu_traffic.json is from another build of the kernels (digest %s): not used' % tj.get('library_digest')
+            for name in KERNEL_SOURCES:
+                if name not in tj:
+                    continue
+                if tj.get('source_digests', {}).get(name) == kernel_source_digest(name):
+                    traffic[name] = tj[name]
+                    traffic_note[name] = 'profiles/ncu_traffic.json (%s)' % tj.get('captures', 'ncu --set full')
+                else:
+                    traffic_note[name] = 'profiles/ncu_traffic.json was captured on other sources of this kernel: not used'
     except Exception:
         pass
 
@@ -446,7 +470,7 @@ def main():
         r = roof_(name)
         if r is not None:
             r['traffic'] = traffic.get(name)
-            r['traffic_source'] = traffic_note
+            r['traffic_source'] = traffic_note.get(name, 'no ncu capture of this kernel on this workload committed')
         return r
 
     def roof_(name):
