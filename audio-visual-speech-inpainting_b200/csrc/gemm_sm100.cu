@@ -283,21 +283,28 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 constexpr int G2_EPI_WARPS = 4;                  // one warp per TMEM lane quarter (8 warps were measured slower on the dW / dX shapes)
 constexpr int G2_THREADS = (2 + G2_EPI_WARPS) * 32;
 
-template <int BN>
+// WIDE: one 256 x 512 tile per CTA pair (two N = 256 MMAs per k-step into one 512-column accumulator) instead of
+// 256 x 256 with a double-buffered accumulator.  The operand bytes per flop drop by a quarter -- the CTA-pair kernel is
+// bound by the ~6300 B/clk the L2 feeds the SMs' TMA units chip-wide (tensor pipe 57 % active with 256 x 256 tiles) --
+// at the price of an epilogue that no longer overlaps the next tile's main loop: chosen for the long-K shapes (dW).
+template <int BN, bool WIDE>
 struct Gemm2Smem {
+  static constexpr int TN = WIDE ? 2 * BN : BN;                  // tile width
   static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;          // 16 KB: this CTA's 128 rows
-  static constexpr int B_BYTES = (BN / 2) * GEMM_BK * 2;         // this CTA's half of the B tile
+  static constexpr int BH_BYTES = (BN / 2) * GEMM_BK * 2;        // this CTA's half of one N = BN operand
+  static constexpr int B_BYTES = (TN / BN) * BH_BYTES;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 6 : 8;
+  static constexpr int STAGES = WIDE ? 4 : ((BN == 256) ? 6 : 8);
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + 512 + 1024;
 };
 
-template <int BN>
+template <int BN, bool WIDE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 gemm_f16_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
-  using S = Gemm2Smem<BN>;
+  using S = Gemm2Smem<BN, WIDE>;
   constexpr int STAGES = S::STAGES;
+  constexpr int TN = S::TN, NH = TN / BN;                  // tile width, N = BN operands per k-step
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + S::BAR_OFFSET;
@@ -314,7 +321,7 @@ gemm_f16_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int n_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
 
   const int m_tiles = (p.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
-  const int n_tiles = (p.N + BN - 1) / BN;
+  const int n_tiles = (p.N + TN - 1) / TN;
   const int kb_total = (p.K + GEMM_BK - 1) / GEMM_BK;
   const int chunk = (kb_total + p.split_k - 1) / p.split_k;
   const int n_work = m_tiles * n_tiles * p.split_k;        // work item = (k split, m tile, n tile), n fastest
@@ -341,34 +348,41 @@ gemm_f16_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (both CTAs)
+    // (An L2 prefetch cursor running 4..32 k-blocks ahead of these loads -- cp.async.bulk.prefetch.tensor -- was built and
+    // measured: 10-50 % SLOWER on every shape of the step, profiles/README.md; the ring is not starved by DRAM latency.)
     if (lane == 0) {
       int it = 0;
       for (int w = cluster_id; w < n_work; w += n_clusters) {
         const int n_blk = w % n_tiles, m_blk = (w / n_tiles) % m_tiles, ks = w / (n_tiles * m_tiles);
         const int kb0 = ks * chunk, kb1 = min(kb_total, kb0 + chunk);
         const int m0 = m_blk * 2 * GEMM_BM + (int)rank * GEMM_BM;       // this CTA's A rows
-        const int n0 = n_blk * BN + (int)rank * (BN / 2);                // this CTA's B rows
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(empty_bar(s), ph ^ 1);
           const uint32_t sa = smem_base + s * S::STAGE_BYTES;
-          const uint32_t sb = sa + S::A_BYTES;
           const uint32_t lead_full = map_to_cta(full_bar(s), 0);
           mbar_expect_tx_cluster(lead_full, S::STAGE_BYTES);
           const int k0 = kb * GEMM_BK;
           if (p.trans == 0) {
             if (p.a_il) tma_load_3d_2sm(sa, &tmA, lead_full, 0, m0 / 32, k0 >> 3);
             else tma_load_2d_2sm(sa, &tmA, lead_full, k0, m0);
-            tma_load_2d_2sm(sb, &tmB, lead_full, k0, n0);
           } else {
             if (p.a_il) tma_load_3d_2sm(sa, &tmA, lead_full, 0, k0 >> 5, m0 / 8);
             else {
 #pragma unroll
               for (int a = 0; a < GEMM_BM / 64; ++a) tma_load_2d_2sm(sa + a * 8192, &tmA, lead_full, m0 + 64 * a, k0);
             }
-            if (p.b_il) tma_load_3d_2sm(sb, &tmB, lead_full, 0, k0 >> 5, n0 / 8);
-            else {
+          }
+#pragma unroll
+          for (int h = 0; h < NH; ++h) {                                 // this CTA's half of each N = BN operand
+            const uint32_t sb = sa + S::A_BYTES + h * S::BH_BYTES;
+            const int n0 = n_blk * TN + h * BN + (int)rank * (BN / 2);
+            if (p.trans == 0) {
+              tma_load_2d_2sm(sb, &tmB, lead_full, k0, n0);
+            } else if (p.b_il) {
+              tma_load_3d_2sm(sb, &tmB, lead_full, 0, k0 >> 5, n0 / 8);
+            } else {
 #pragma unroll
               for (int b = 0; b < BN / 128; ++b) tma_load_2d_2sm(sb + b * 8192, &tmB, lead_full, n0 + 64 * b, k0);
             }
@@ -388,8 +402,8 @@ gemm_f16_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int w = cluster_id; w < n_work; w += n_clusters, ++tile) {
         const int ks = w / (n_tiles * m_tiles);
         const int kb0 = ks * chunk, kb1 = min(kb_total, kb0 + chunk);
-        const int acc = tile & 1;
-        mbar_wait(tempty_bar(acc), ((tile >> 1) & 1) ^ 1);               // both CTAs' epilogues drained this buffer
+        const int acc = WIDE ? 0 : (tile & 1);                           // WIDE: one 512-column accumulator, no double buffer
+        mbar_wait(tempty_bar(acc), ((WIDE ? tile : (tile >> 1)) & 1) ^ 1);   // both CTAs' epilogues drained this buffer
         tc_fence_after();
         const uint32_t td = tmem_base + (uint32_t)(acc * BN);
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
@@ -398,14 +412,17 @@ gemm_f16_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
           const uint32_t sa = smem_base + s * S::STAGE_BYTES;
-          const uint32_t sb = sa + S::A_BYTES;
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {
             const uint64_t da = p.a_il ? make_smem_desc(sa + k * a_kstep, a_lbo, a_sbo, 0u)
                                        : make_smem_desc(sa + k * kstep, lbo, 1024u);
-            const uint64_t db = p.b_il ? make_smem_desc(sb + k * a_kstep, a_lbo, a_sbo, 0u)
-                                       : make_smem_desc(sb + k * kstep, lbo, 1024u);
-            umma_f16_2sm(td, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+#pragma unroll
+            for (int h = 0; h < NH; ++h) {
+              const uint32_t sb = sa + S::A_BYTES + h * S::BH_BYTES;
+              const uint64_t db = p.b_il ? make_smem_desc(sb + k * a_kstep, a_lbo, a_sbo, 0u)
+                                         : make_smem_desc(sb + k * kstep, lbo, 1024u);
+              umma_f16_2sm(td + (uint32_t)(h * BN), da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
           }
           umma_commit_2sm(empty_bar(s), (uint16_t)3);                    // frees the slot in both CTAs
         }
@@ -422,18 +439,17 @@ gemm_f16_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int w = cluster_id; w < n_work; w += n_clusters, ++tile) {
       const int n_blk = w % n_tiles, m_blk = (w / n_tiles) % m_tiles, ks = w / (n_tiles * m_tiles);
       const int kb0 = ks * chunk, kb1 = min(kb_total, kb0 + chunk);
-      const int acc = tile & 1;
-      mbar_wait(tfull_bar(acc), (tile >> 1) & 1);
+      const int acc = WIDE ? 0 : (tile & 1);
+      mbar_wait(tfull_bar(acc), (WIDE ? tile : (tile >> 1)) & 1);
       tc_fence_after();
       const int row = m_blk * 2 * GEMM_BM + (int)rank * GEMM_BM + quarter * 32 + lane;
       const bool row_ok = row < p.M && kb1 > kb0;
 #pragma unroll 1
-#pragma unroll 1
-      for (int c = chalf * (BN / 32 / NSPLIT); c < (chalf + 1) * (BN / 32 / NSPLIT); ++c) {
+      for (int c = chalf * (TN / 32 / NSPLIT); c < (chalf + 1) * (TN / 32 / NSPLIT); ++c) {
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
         tmem_ld_wait();
-        const int n0 = n_blk * BN + c * 32;
+        const int n0 = n_blk * TN + c * 32;
         if (!row_ok || n0 >= p.N) continue;
         epilogue_store(p, row, n0, n0 + 32 <= p.N, r);
       }
@@ -605,19 +621,19 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   return AVSI_OK;
 }
 
-template <int BN>
+template <int BN, bool WIDE>
 static int launch_gemm_2sm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
-  using S = Gemm2Smem<BN>;
+  using S = Gemm2Smem<BN, WIDE>;
   static bool attr_done = false;
   if (!attr_done) {
-    AVSI_CUDA(cudaFuncSetAttribute(gemm_f16_2sm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    AVSI_CUDA(cudaFuncSetAttribute(gemm_f16_2sm_kernel<BN, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     attr_done = true;
   }
-  const int m_tiles = (p.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM), n_tiles = (p.N + BN - 1) / BN;
+  const int m_tiles = (p.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM), n_tiles = (p.N + S::TN - 1) / S::TN;
   const long long n_work = (long long)m_tiles * n_tiles * p.split_k;
   long long clusters = num_sms() / 2;
   if (clusters > n_work) clusters = n_work;
-  gemm_f16_2sm_kernel<BN><<<(unsigned)(2 * clusters), G2_THREADS, S::TOTAL, st>>>(ta, tb, p);
+  gemm_f16_2sm_kernel<BN, WIDE><<<(unsigned)(2 * clusters), G2_THREADS, S::TOTAL, st>>>(ta, tb, p);
   AVSI_LAUNCH_CHECK();
   return AVSI_OK;
 }
@@ -661,8 +677,15 @@ extern "C" int avsi_gemm_f16(const uint16_t* A, int lda, const uint16_t* B, int 
   // large problems: persistent CTA-pair kernel (256 x 256 tiles, cta_group::2).  AVSI_GEMM_2SM=0 disables it.
   AVSI_ENV_CACHE(use_2sm, env_is("AVSI_GEMM_2SM", "0") ? 0 : (env_is("AVSI_GEMM_2SM", "2") ? 2 : 1));
   if (use_2sm && N >= 256 && (use_2sm == 2 || ((N + 255) / 256) * 256 * 3 <= N * 4) && (long long)M * N * K >= (1LL << 29)) {
+    // 256 x 512 tiles (one accumulator, a quarter less operand traffic per flop) where the main loop is long enough to
+    // carry the un-overlapped epilogue and the output is at least 3/4 of a 512-wide tile: the split-K dW shapes, and
+    // fixed-K shapes with K >= 2048 (dX).  AVSI_GEMM_WIDE = 0 never, 2 whenever N allows (A/B runs).
+    AVSI_ENV_CACHE(wide_env, env_int("AVSI_GEMM_WIDE", 1));
+    const bool n_fits = (N % 512 == 0) || (N % 512 >= 384);
+    const bool wide = wide_env && N >= 384 && n_fits && (wide_env == 2 || out_mode == 2 || K >= 2048);
     // split-K only as far as needed to give every SM pair a work item
-    const int m_t = (M + 255) / 256, n_t = (N + 255) / 256, kbt = (K + GEMM_BK - 1) / GEMM_BK;
+    const int tn = wide ? 512 : 256;
+    const int m_t = (M + 255) / 256, n_t = (N + tn - 1) / tn, kbt = (K + GEMM_BK - 1) / GEMM_BK;
     if (out_mode == 2) {
       // split K so that the work items fill whole waves of SM pairs (80 items on 74 pairs would take two waves)
       const int pairs = num_sms() / 2, tiles = m_t * n_t;
@@ -694,7 +717,8 @@ extern "C" int avsi_gemm_f16(const uint16_t* A, int lda, const uint16_t* B, int 
                          : get_tmap(B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, GEMM_BK, &tb2);
       if (rc2) return rc2;
     }
-    return launch_gemm_2sm<256>(ta2, tb2, p, st);
+    if (wide) return launch_gemm_2sm<256, true>(ta2, tb2, p, st);
+    return launch_gemm_2sm<256, false>(ta2, tb2, p, st);
   }
   int bn = 128;
   if (N > 128 && K >= 4096) bn = 256;

@@ -486,6 +486,10 @@ def main():
                  'algorithmic_bytes_per_launch': v['bytes'] / v['launches']}
             if v['flops']:
                 r['tensor_tflops'] = v['flops'] / sec / 1e12
+            if name in ('lstm_bwd', 'lstm_fwd'):
+                r['note'] = ('the launch time of this kernel is independent of the number of clusters (1.55-1.60 ms at 4 and at 32): '
+                             'it sits on its per-cluster dependent chain, not on the HBM roofline; frac is reported against HBM '
+                             'because its DRAM traffic equals the algorithmic bytes (DESIGN.md section 4)')
             return r
         a = v['flops'] / sec / 1e12
         return {'kernel': name, 'bound': 'tensor', 'achieved': a, 'peak': pk['bf16_tflops_sustained'], 'unit': 'TFLOP/s',

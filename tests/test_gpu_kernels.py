@@ -36,6 +36,8 @@ GEMM_CASES = [
     (1024, 256, 996, 1, 2, 4, 0),
     (291, 512, 1000, 1, 2, 2, 0),
     (512, 2048, 8192, 0, 2, 2, 0),
+    (600, 1024, 3000, 1, 2, 2, 0),        # two 256 x 512 tiles per row block (the WIDE CTA-pair variant), ragged M
+    (520, 896, 2304, 0, 0, 1, 0),         # 512 + 384: the second wide tile is 3/4 full; fixed K >= 2048 -> WIDE
 ]
 
 
