@@ -467,6 +467,167 @@ gemm_f16_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
 }
 
+// ---------------------------------------------------------------- A-stationary CTA-pair kernel (K <= 512, trans = 0)
+// The gate projections are [M, K<=512] x [2048, K]^T: with 256 x 256 tiles every tile loads 256 KB of A and 256 KB of B for
+// 67 MFLOP, and the L2 -> SM path (~6300 B/clk chip-wide) keeps the tensor pipe at 57 %.  Here a CTA pair keeps its 256
+// rows of A (the whole K, 8 k-slices of 16 KB per CTA) in shared memory while it sweeps ALL n tiles of that row block:
+// only B streams (4-stage ring), A costs 1/n_tiles of what it did -- 44 % less operand traffic at N = 2048.
+// Work item = one 256-row block; per item n_tiles output tiles, accumulators double-buffered in TMEM as before.
+// A k-slice is released (a_empty) by the LAST n tile's MMAs of that slice, so the next row block's slice reloads under
+// the rest of that tile's main loop.
+struct GemmAStatSmem {
+  static constexpr int KS_MAX = 8;                               // k-slices of 64: K <= 512
+  static constexpr int A_SLICE = GEMM_BM * GEMM_BK * 2;          // 16 KB: this CTA's 128 rows x 64 k
+  static constexpr int B_BYTES = 128 * GEMM_BK * 2;              // this CTA's half of the 256-wide B tile
+  static constexpr int STAGES = 4;
+  static constexpr int B_OFFSET = KS_MAX * A_SLICE;              // 128 KB
+  static constexpr int BAR_OFFSET = B_OFFSET + STAGES * B_BYTES; // + 64 KB
+  static constexpr int TOTAL = BAR_OFFSET + 512 + 1024;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
+gemm_f16_2sm_astat_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmParams p) {
+  using S = GemmAStatSmem;
+  constexpr int STAGES = S::STAGES, BN = 256, KS = S::KS_MAX;
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t smem_base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + S::BAR_OFFSET;
+  auto bfull_bar = [&](int s) { return bar_base + 8u * s; };                          // leader CTA
+  auto bempty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };              // per CTA
+  auto afull_bar = [&](int k) { return bar_base + 8u * (2 * STAGES + k); };           // leader CTA
+  auto aempty_bar = [&](int k) { return bar_base + 8u * (2 * STAGES + KS + k); };     // per CTA
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 * KS + a); };  // per CTA
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 * KS + 2 + a); };   // leader CTA
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 2 * KS + 4);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_dyn + (tmem_slot - smem_u32(smem_dyn)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int n_clusters = gridDim.x >> 1, cluster_id = blockIdx.x >> 1;
+  const int m_tiles = (p.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const int kbt = (p.K + GEMM_BK - 1) / GEMM_BK;           // <= KS
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bfull_bar(s), 2);
+      mbar_init(bempty_bar(s), 1);
+    }
+    for (int k = 0; k < KS; ++k) {
+      mbar_init(afull_bar(k), 2);
+      mbar_init(aempty_bar(k), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 2 * G2_EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2sm(tmem_slot, 2 * BN);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      int it = 0, mi = 0;
+      for (int m_blk = cluster_id; m_blk < m_tiles; m_blk += n_clusters, ++mi) {
+        const int m0 = m_blk * 2 * GEMM_BM + (int)rank * GEMM_BM;
+        for (int n_blk = 0; n_blk < n_tiles; ++n_blk) {
+          const int n0 = n_blk * BN + (int)rank * (BN / 2);
+          for (int kb = 0; kb < kbt; ++kb, ++it) {
+            const int k0 = kb * GEMM_BK;
+            if (n_blk == 0) {                                            // this row block's A slice kb
+              mbar_wait(aempty_bar(kb), (uint32_t)((mi & 1) ^ 1));
+              const uint32_t lead_afull = map_to_cta(afull_bar(kb), 0);
+              mbar_expect_tx_cluster(lead_afull, S::A_SLICE);
+              const uint32_t sa = smem_base + kb * S::A_SLICE;
+              if (p.a_il) tma_load_3d_2sm(sa, &tmA, lead_afull, 0, m0 / 32, k0 >> 3);
+              else tma_load_2d_2sm(sa, &tmA, lead_afull, k0, m0);
+            }
+            const int s = it % STAGES;
+            mbar_wait(bempty_bar(s), (uint32_t)(((it / STAGES) & 1) ^ 1));
+            const uint32_t lead_bfull = map_to_cta(bfull_bar(s), 0);
+            mbar_expect_tx_cluster(lead_bfull, S::B_BYTES);
+            tma_load_2d_2sm(smem_base + S::B_OFFSET + s * S::B_BYTES, &tmB, lead_bfull, k0, n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA)
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = make_idesc(2 * GEMM_BM, BN, 0, 0);
+      int it = 0, mi = 0, tile = 0;
+      for (int m_blk = cluster_id; m_blk < m_tiles; m_blk += n_clusters, ++mi) {
+        for (int n_blk = 0; n_blk < n_tiles; ++n_blk, ++tile) {
+          const int acc = tile & 1;
+          mbar_wait(tempty_bar(acc), (uint32_t)(((tile >> 1) & 1) ^ 1));
+          tc_fence_after();
+          const uint32_t td = tmem_base + (uint32_t)(acc * BN);
+          for (int kb = 0; kb < kbt; ++kb, ++it) {
+            if (n_blk == 0) mbar_wait(afull_bar(kb), (uint32_t)(mi & 1));
+            const int s = it % STAGES;
+            mbar_wait(bfull_bar(s), (uint32_t)((it / STAGES) & 1));
+            tc_fence_after();
+            const uint32_t sa = smem_base + kb * S::A_SLICE;
+            const uint32_t sb = smem_base + S::B_OFFSET + s * S::B_BYTES;
+#pragma unroll
+            for (int k = 0; k < GEMM_BK / 16; ++k) {
+              const uint64_t da = p.a_il ? make_smem_desc(sa + k * 4096u, 2048u, 128u, 0u) : make_smem_desc(sa + k * 32u, 0u, 1024u);
+              const uint64_t db = make_smem_desc(sb + k * 32u, 0u, 1024u);
+              umma_f16_2sm(td, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit_2sm(bempty_bar(s), (uint16_t)3);
+            if (n_blk == n_tiles - 1) umma_commit_2sm(aempty_bar(kb), (uint16_t)3);   // slice free for the next row block
+          }
+          umma_commit_2sm(tfull_bar(acc), (uint16_t)3);
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..5, both CTAs)
+    const int quarter = warp & 3;
+    constexpr int NSPLIT = G2_EPI_WARPS / 4;
+    const int chalf = (warp - 2) >> 2;
+    const uint32_t lead_tempty0 = map_to_cta(tempty_bar(0), 0);
+    int tile = 0;
+    for (int m_blk = cluster_id; m_blk < m_tiles; m_blk += n_clusters) {
+      const int row = m_blk * 2 * GEMM_BM + (int)rank * GEMM_BM + quarter * 32 + lane;
+      const bool row_ok = row < p.M;
+      for (int n_blk = 0; n_blk < n_tiles; ++n_blk, ++tile) {
+        const int acc = tile & 1;
+        mbar_wait(tfull_bar(acc), (uint32_t)((tile >> 1) & 1));
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = chalf * (BN / 32 / NSPLIT); c < (chalf + 1) * (BN / 32 / NSPLIT); ++c) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c * 32), r);
+          tmem_ld_wait();
+          const int n0 = n_blk * BN + c * 32;
+          if (!row_ok || n0 >= p.N) continue;
+          epilogue_store(p, row, n0, n0 + 32 <= p.N, r);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(lead_tempty0 + 8u * acc);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 2 * BN);
+  }
+}
+
 // ---------------------------------------------------------------- debug / validation GEMM (CUDA cores)
 #ifdef AVSI_DEBUG_KERNELS   // CUDA-core bisecting kernel: compiled only into debug builds (nvcc -DAVSI_DEBUG_KERNELS), never into the product library
 // Same contract as the tensor-core kernel; selected only by AVSI_GEMM_DEBUG_SIMT=1 to bisect
@@ -638,6 +799,21 @@ static int launch_gemm_2sm(const CUtensorMap& ta, const CUtensorMap& tb, const G
   return AVSI_OK;
 }
 
+static int launch_gemm_2sm_astat(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+  using S = GemmAStatSmem;
+  static bool attr_done = false;
+  if (!attr_done) {
+    AVSI_CUDA(cudaFuncSetAttribute(gemm_f16_2sm_astat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    attr_done = true;
+  }
+  const long long m_tiles = (p.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);
+  long long clusters = num_sms() / 2;
+  if (clusters > m_tiles) clusters = m_tiles;
+  gemm_f16_2sm_astat_kernel<<<(unsigned)(2 * clusters), G2_THREADS, S::TOTAL, st>>>(ta, tb, p);
+  AVSI_LAUNCH_CHECK();
+  return AVSI_OK;
+}
+
 }  // namespace avsi
 
 extern "C" int avsi_gemm_f16(const uint16_t* A, int lda, const uint16_t* B, int ldb, void* C, int ldc,
@@ -717,6 +893,11 @@ extern "C" int avsi_gemm_f16(const uint16_t* A, int lda, const uint16_t* B, int 
                          : get_tmap(B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, GEMM_BK, &tb2);
       if (rc2) return rc2;
     }
+    // A-stationary sweep for the projection shape: trans = 0, the whole K in 8 k-slices, several n tiles to share A,
+    // enough row blocks to fill the chip.  AVSI_GEMM_ASTAT=0 disables it (A/B runs).
+    AVSI_ENV_CACHE(astat_env, env_int("AVSI_GEMM_ASTAT", 1));
+    if (astat_env && trans == 0 && out_mode != 2 && K <= GemmAStatSmem::KS_MAX * GEMM_BK && n_t >= 4 && m_t >= num_sms())
+      return launch_gemm_2sm_astat(ta2, tb2, p, st);
     if (wide) return launch_gemm_2sm<256, true>(ta2, tb2, p, st);
     return launch_gemm_2sm<256, false>(ta2, tb2, p, st);
   }

@@ -33,12 +33,16 @@ shapes = {
     'dW_ih IL[M,2048]^T x [M,512] -> f32 splitK': (lambda: gemm(p(G), NG, p(X), NY, p(dW), NY, None, NG, NY, M, 1, 2, pick_split_k(NG, NY, M), layout=A_IL), 2.0 * M * NG * NY),
     'dW_hh IL[M,1024]^T x [M,256] -> f32 splitK': (lambda: gemm(G.data_ptr(), NG, Ybuf.data_ptr(), NY, p(dWhh), 256, None, 1024, 256, M, 1, 2, pick_split_k(1024, 256, M, 148), layout=A_IL), 2.0 * M * 1024 * 256),
 }
-for wide in (0, 1, 2, 0, 1, 2):
-    _lib.set_env(AVSI_GEMM_WIDE=wide)
-    row = {'AVSI_GEMM_WIDE': wide}
+X0 = torch.randn(M, 448, device=d).half()
+W0 = (torch.randn(NG, 448, device=d) * 0.05).half()
+shapes['proj0 [M,448]x[2048,448]^T -> IL f16'] = (lambda: gemm(p(X0), 448, p(W0), 448, p(Gout), NG, None, M, NG, 448, 0, 0, layout=C_IL), 2.0 * M * NG * 448)
+# variants alternate launch by launch (the box's clocks drift under load: back-to-back blocks per variant are biased)
+variants = ((0, 0), (1, 0), (1, 1))
+times = {v: {n: [] for n in shapes} for v in variants}
+for it in range(13):
     for name, (fn, flops) in shapes.items():
-        ts = []
-        for it in range(5):
+        for v in variants:
+            _lib.set_env(AVSI_GEMM_WIDE=v[0], AVSI_GEMM_ASTAT=v[1])
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -46,7 +50,12 @@ for wide in (0, 1, 2, 0, 1, 2):
             e1.record()
             torch.cuda.synchronize()
             if it >= 1:
-                ts.append(e0.elapsed_time(e1))
-        row[name.split()[0]] = {'ms': min(ts), 'tflops': flops / min(ts) / 1e9}
+                times[v][name].append(e0.elapsed_time(e1))
+for v in variants:
+    row = {'AVSI_GEMM_WIDE': v[0], 'AVSI_GEMM_ASTAT': v[1]}
+    for name, (fn, flops) in shapes.items():
+        ts = sorted(times[v][name])
+        med = ts[len(ts) // 2]
+        row[name.split()[0]] = {'ms_median': round(med, 4), 'ms_min': round(ts[0], 4), 'tflops_median': round(flops / med / 1e9, 1)}
     print(json.dumps(row), flush=True)
-_lib.set_env(AVSI_GEMM_WIDE=None)
+_lib.set_env(AVSI_GEMM_WIDE=None, AVSI_GEMM_ASTAT=None)

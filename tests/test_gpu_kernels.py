@@ -38,6 +38,8 @@ GEMM_CASES = [
     (512, 2048, 8192, 0, 2, 2, 0),
     (600, 1024, 3000, 1, 2, 2, 0),        # two 256 x 512 tiles per row block (the WIDE CTA-pair variant), ragged M
     (520, 896, 2304, 0, 0, 1, 0),         # 512 + 384: the second wide tile is 3/4 full; fixed K >= 2048 -> WIDE
+    (38000, 1024, 448, 0, 0, 1, 0),       # >= 148 row blocks, K <= 512, 4 n tiles: the A-stationary projection kernel (7 k-slices, ragged M)
+    (38100, 1100, 512, 0, 1, 1, 4),       # same kernel, f32 + bias epilogue, ragged last n tile
 ]
 
 
@@ -118,6 +120,7 @@ def test_gate_prescale_of_forward_copies():
 GEMM_IL_CASES = [
     # M, N, K, trans, out_mode, split_k, layout   (layout bit 0: A interleaved, bit 1: f16 output interleaved)
     (1000, 2048, 448, 0, 0, 1, 2),        # projection: row-major X -> interleaved G
+    (37900, 2048, 512, 0, 0, 1, 2),       # the same at >= 148 row blocks: A-stationary kernel -> interleaved G
     (300, 512, 2048, 0, 0, 1, 1),         # dX: interleaved dG (K-major) -> row-major dY
     (777, 512, 2048, 0, 0, 1, 3),
     (2048, 400, 1000, 1, 2, 3, 1),        # dW: interleaved dG (MN-major) x row-major X, split-K
