@@ -28,14 +28,19 @@ __device__ __forceinline__ float lse2(float a, float b) {
   return m + log1pf(expf(fminf(a, b) - m));
 }
 
+// SPT = states per thread: ceil((2 Lmax + 1) / 128).  The reference pads labels to 50 (tfrecord_utils.py:101): 101 states,
+// SPT = 1 -- the per-state loops then have one iteration instead of eight predicated ones, and the state vectors take
+// SPT * 128 entries of shared memory instead of 1024 (more utterances per SM).
+template <int SPT>
 __global__ void __launch_bounds__(CTC_THREADS)
 ctc_kernel(const float* __restrict__ logits, int ldl, int col0, int C, const int32_t* __restrict__ labels, int Lmax,
            const int32_t* __restrict__ lab_len, const int32_t* __restrict__ seq_len, int B, int T, float grad_scale,
            const float* __restrict__ grad_scale_dev, float* __restrict__ nll, uint16_t* __restrict__ dlogits,
            int ldd, int dcol0, float* __restrict__ ws_logp, float* __restrict__ ws_alpha, double* __restrict__ ws_shift) {
-  __shared__ int ext[CTC_MAX_S];
-  __shared__ unsigned char skip[CTC_MAX_S];
-  __shared__ float st[2][CTC_MAX_S];
+  constexpr int NS = SPT * CTC_THREADS;             // states this instantiation can hold
+  __shared__ int ext[NS];
+  __shared__ unsigned char skip[NS];
+  __shared__ float st[2][NS];
   __shared__ float post[CTC_MAX_C];
   __shared__ float ll_sh;
   __shared__ float red[CTC_THREADS / 32];
@@ -108,7 +113,6 @@ ctc_kernel(const float* __restrict__ logits, int ldl, int col0, int C, const int
   __syncthreads();
   // The recursions are a dependent chain of Tb steps: the global (L2) operands of step t+1 are requested during
   // step t so that only shared-memory latency sits on the chain.  S <= 8 * CTC_THREADS (Lmax limit) -> <= 8 states per thread.
-  constexpr int SPT = CTC_MAX_S / CTC_THREADS;
   float lp_next[SPT];
 #pragma unroll
   for (int i = 0; i < SPT; ++i) {
@@ -276,9 +280,16 @@ extern "C" int avsi_ctc_loss(const float* logits, int ldl, int col0, int C, cons
   float* ws_alpha = ws_logp + (long long)B * T * CTC_MAX_C;
   const long long smax = (2LL * Lmax + 1 + 1) & ~1LL;
   double* ws_shift = reinterpret_cast<double*>(ws_alpha + (long long)B * T * smax);
-  ctc_kernel<<<B, CTC_THREADS, 0, (cudaStream_t)stream>>>(logits, ldl, col0, C, labels, Lmax, lab_len, seq_len, B, T,
-                                                         grad_scale, grad_scale_dev, nll, dlogits, ldd, dcol0,
-                                                         ws_logp, ws_alpha, ws_shift);
+  const int spt = (2 * Lmax + 1 + CTC_THREADS - 1) / CTC_THREADS;
+#define CTC_LAUNCH(SPT_)                                                                                              \
+  ctc_kernel<SPT_><<<B, CTC_THREADS, 0, (cudaStream_t)stream>>>(logits, ldl, col0, C, labels, Lmax, lab_len, seq_len, B, T, \
+                                                               grad_scale, grad_scale_dev, nll, dlogits, ldd, dcol0,  \
+                                                               ws_logp, ws_alpha, ws_shift)
+  if (spt <= 1) CTC_LAUNCH(1);
+  else if (spt <= 2) CTC_LAUNCH(2);
+  else if (spt <= 4) CTC_LAUNCH(4);
+  else CTC_LAUNCH(8);
+#undef CTC_LAUNCH
   AVSI_LAUNCH_CHECK();
   return AVSI_OK;
 }
