@@ -86,7 +86,12 @@ __device__ unsigned long long g_l4_timing[16];
 
 // BULK (B % 32 == 0: a warp's 32 rows are one row block of the interleaved layout): the activated gates leave through
 // shared memory + cp.async.bulk (async proxy) instead of 4 STG.128 per thread and pass
-template <int ACT, bool TIMING, bool BULK>
+// CFENCE: the generic -> async proxy fence is executed on the consumer side (the control thread, after its acquire of
+//   the hand-over barrier, with no memory operations of its own in flight) instead of by each of the 512 writers, where
+//   MEMBAR.ALL.CTA waits for the thread's global loads and stores.
+// BPF (B % 32 == 0): the next steps' pre-activation lines are pulled into L2 by four 16 KB cp.async.bulk.prefetch of the
+//   control thread instead of eight CCTL per compute thread (LSU queue slots).
+template <int ACT, bool TIMING, bool BULK, bool CFENCE, bool BPF>
 __global__ void __cluster_dims__(L4_CL, 1, 1) __launch_bounds__(L4_THREADS, 1)
 lstm4_fwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whh, const float* __restrict__ bias,
                  uint16_t* __restrict__ y, float* __restrict__ cst, int T, int B, int PREFETCH, int y_il) {
@@ -157,21 +162,29 @@ lstm4_fwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whh,
         dst_a[d] = map_to_cta(a_s, (uint32_t)d);
         dst_bar[d] = map_to_cta(hfull_s, (uint32_t)d);
       }
-      for (int s = 0; s + 1 < T; ++s) {
-        // ---- ship h_s, one half at a time, as soon as the warps have staged it -------------------------------
+      // 16 KB runs of this CTA's 256 gate columns (interleaved layout: one run per 32-row block) of chain step sp
+      auto prefetch_step = [&](int sp) {
+        const int tt = dir ? (T - 1 - sp) : sp;
 #pragma unroll
-        for (int p = 0; p < 2; ++p) {
+        for (int rb = 0; rb < 4; ++rb)
+          if (b0 + 32 * rb < B)
+            bulk_prefetch_l2(gates + il16((long long)tt * B + b0 + 32 * rb, dir * L4_G + j * L4_NC, 2 * L4_G), 16384u);
+      };
+      if (BPF)
+        for (int sp = 1; sp < PREFETCH && sp < T; ++sp) prefetch_step(sp);
+      for (int s = 0; s + 1 < T; ++s) {
+        if (BPF && s + PREFETCH < T) prefetch_step(s + PREFETCH);      // PREFETCH = distance in steps
+        const uint32_t td = tmem_base + (uint32_t)(((s + 1) & 1) * L4_NC);
+        auto push_half = [&](int p) {          // ship half p of h_s as soon as the warps have staged it
           mbar_wait(staged_s + 8u * p, (uint32_t)(s & 1));
+          if (CFENCE) fence_proxy_async();
           L4_TICK(p);
           const uint32_t off = (uint32_t)(16 * p + 4 * j) * L4_A_LBO;
 #pragma unroll
           for (int d = 0; d < L4_CL; ++d)
             if (d != j) bulk_copy_to_cta(dst_a[d] + off, a_s + off, L4_HALF_BYTES, dst_bar[d] + 8u * p);
-        }
-        // ---- the chain of step s+1, K-half by K-half as the peers' halves land ---------------------------------------
-        const uint32_t td = tmem_base + (uint32_t)(((s + 1) & 1) * L4_NC);
-#pragma unroll
-        for (int p = 0; p < 2; ++p) {
+        };
+        auto mma_half = [&](int p) {           // K-half p of the chain of step s+1, once the peers' halves have landed
           mbar_wait(hfull_s + 8u * p, (uint32_t)(s & 1));
           if (s + 2 < T) mbar_expect_tx(hfull_s + 8u * p, PUSH_BYTES);    // re-arm for round s+1
           L4_TICK(2 + 2 * p);
@@ -183,7 +196,13 @@ lstm4_fwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whh,
                      make_smem_desc(w_s + kc * L4_W_LBO, L4_W_LBO, L4_W_SBO, 0u), idesc, (p > 0 || ks > 0) ? 1u : 0u);
           }
           L4_TICK(3 + 2 * p);
-        }
+        };
+        // (issuing the first K-half before the second push, i.e. under the second cell-update pass, was measured 13 % SLOWER:
+        // the chain's TMEM / shared-memory traffic slows that pass down by more than the overlap gains, profiles/README.md)
+        push_half(0);
+        push_half(1);
+        mma_half(0);
+        mma_half(1);
         umma_commit(done_s);
         umma_commit_mc(afree_s + 8u * (s & 1), (uint16_t)0xF);
       }
@@ -225,7 +244,7 @@ lstm4_fwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whh,
       }
       // the lines of the NEXT step are pulled into L2 now (a whole step ahead), so that its loads -- issued only
       // when this step's epilogue is done -- are L2 hits instead of DRAM reads queued behind the stores
-      if (PREFETCH && row_ok && s + 1 < T && (lane & 7) == 0) {          // one lane per 128-byte line
+      if (!BPF && PREFETCH && row_ok && s + 1 < T && (lane & 7) == 0) {          // one lane per 128-byte line
         const long long gn = (long long)(dir ? (t - 1) : (t + 1)) * B + row;
         const int col0 = dir * L4_G + (j * 64 + cg * 16) * 4;
 #pragma unroll
@@ -294,8 +313,8 @@ lstm4_fwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whh,
           uint4 ha = hv[p];
           if (p == 1 && cg == 3 && j == L4_CL - 1) ha.w = (ha.w & 0xFFFFu) | 0x3C000000u;   // unit 255 := 1.0 (bias slot)
           *reinterpret_cast<uint4*>(&sm.a[(uint32_t)(16 * p + 4 * j + cg) * L4_A_LBO + (uint32_t)r * 16u]) = ha;
-          fence_proxy_async();                       // generic-proxy writes -> visible to UMMA / bulk copies
-          if (p == 1) tc_fence_before();             // our tcgen05.ld's precede the chain that reuses this buffer
+          if (!CFENCE) fence_proxy_async();          // generic-proxy writes -> visible to UMMA / bulk copies
+          tc_fence_before();                         // our tcgen05.ld's precede the chain that reuses this buffer
           __syncwarp();
           if (lane == 0) mbar_arrive_local(staged_s + 8u * p);
         }
@@ -356,31 +375,40 @@ int launch_lstm4_fwd(uint16_t* gates, const uint16_t* whh, const float* bias, ui
                      int y_il, cudaStream_t st) {
   // AVSI_LSTM_ACT=exact: ex2/rcp activations; AVSI_L4_TIMING=1: in-kernel phase timers (profiles/bench_lstm.py)
   AVSI_ENV_CACHE(mode, env_is("AVSI_LSTM_ACT", "exact") | (env_is("AVSI_L4_TIMING", "1") << 1));
-  AVSI_ENV_CACHE(pf, env_is("AVSI_L4_PREFETCH", "0") ? 0 : 1);   // AVSI_L4_PREFETCH=0: no L2 prefetch of the next step (A/B runs)
+  AVSI_ENV_CACHE(pf, env_int("AVSI_L4_PREFETCH", 1));            // L2 prefetch distance in steps (bulk variant; the per-thread variant always looks one step ahead); 0: none
   AVSI_ENV_CACHE(bulk_env, env_int("AVSI_L4_BULK", 0));           // AVSI_L4_BULK=1: gates through shared memory + cp.async.bulk (measured: no gain, profiles/README.md)
+  AVSI_ENV_CACHE(cfence, env_int("AVSI_L4_CFENCE", 1));           // 0: proxy fence in the 512 writers (round-1 form, A/B runs)
+  AVSI_ENV_CACHE(bpf_env, env_int("AVSI_L4_BPF", 1));             // 0: per-thread L2 prefetch
   const int bulk = (bulk_env && B % 32 == 0) ? 1 : 0;
+  const int bpf = (bpf_env && pf && B % 32 == 0) ? 1 : 0;
   const int smem = (int)sizeof(Lstm4Smem) + 128;
   const int grid = 2 * ((B + L4_BT - 1) / L4_BT) * L4_CL;
-  static bool attr_done[8] = {false, false, false, false, false, false, false, false};
-#define L4_LAUNCH(ACT_, TIM_, BULK_)                                                                                    \
-  do {                                                                                                                 \
-    if (!attr_done[mode * 2 + BULK_]) {                                                                                \
-      AVSI_CUDA(cudaFuncSetAttribute(lstm4_fwd_kernel<ACT_, TIM_, BULK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-      attr_done[mode * 2 + BULK_] = true;                                                                              \
-    }                                                                                                                  \
-    lstm4_fwd_kernel<ACT_, TIM_, BULK_><<<grid, L4_THREADS, smem, st>>>(gates, whh, bias, y, cst, T, B, pf, y_il);      \
-  } while (0)
-#define L4_LAUNCH2(ACT_, TIM_)            \
-  do {                                    \
-    if (bulk) L4_LAUNCH(ACT_, TIM_, true); \
-    else L4_LAUNCH(ACT_, TIM_, false);    \
-  } while (0)
-  if (mode == 0) L4_LAUNCH2(0, false);
-  else if (mode == 1) L4_LAUNCH2(1, false);
-  else if (mode == 2) L4_LAUNCH2(0, true);
-  else L4_LAUNCH2(1, true);
-#undef L4_LAUNCH2
-#undef L4_LAUNCH
+  auto launch = [&](auto kern) -> int {
+    static const void* prepared[16];                               // kernels whose shared-memory limit is already raised
+    static int n_prepared = 0;
+    bool seen = false;
+    for (int i = 0; i < n_prepared; ++i) seen |= (prepared[i] == (const void*)kern);
+    if (!seen) {
+      AVSI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      if (n_prepared < 16) prepared[n_prepared++] = (const void*)kern;
+    }
+    kern<<<grid, L4_THREADS, smem, st>>>(gates, whh, bias, y, cst, T, B, pf, y_il);
+    return AVSI_OK;
+  };
+  const int act = mode & 1;
+  int rc;
+  if (mode & 2) {                                                  // phase timers: default variant only
+    rc = act ? launch(lstm4_fwd_kernel<1, true, false, true, false>) : launch(lstm4_fwd_kernel<0, true, false, true, false>);
+  } else if (bulk) {
+    rc = act ? launch(lstm4_fwd_kernel<1, false, true, false, false>) : launch(lstm4_fwd_kernel<0, false, true, false, false>);
+  } else if (act) {
+    rc = bpf ? launch(lstm4_fwd_kernel<1, false, false, true, true>) : launch(lstm4_fwd_kernel<1, false, false, true, false>);
+  } else if (!cfence) {
+    rc = launch(lstm4_fwd_kernel<0, false, false, false, false>);
+  } else {
+    rc = bpf ? launch(lstm4_fwd_kernel<0, false, false, true, true>) : launch(lstm4_fwd_kernel<0, false, false, true, false>);
+  }
+  if (rc != AVSI_OK) return rc;
   AVSI_LAUNCH_CHECK();
   return AVSI_OK;
 }

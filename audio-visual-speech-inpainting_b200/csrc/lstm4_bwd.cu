@@ -65,10 +65,14 @@ __device__ unsigned long long g_b4_timing[24];
 // LATE: the second half's inputs are requested AFTER the first half's A-tile hand-over instead of before it.
 // fence.proxy.async compiles to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC (ptxas 12.9): issued ahead of the hand-over, the loads
 // in flight would have to return before the fence retires, i.e. before the first MMA chain can start.
-template <bool TIMING, bool LATE>
+// CFENCE: the generic -> async proxy fence is executed by the consumer (the control thread, after its acquire of the
+//   hand-over barrier) instead of by each of the 512 writers, whose fence would wait for their loads and stores in flight.
+// BPF (B % 32 == 0): the next steps' gate / cell-state / dL/dy lines are pulled into L2 by cp.async.bulk.prefetch of the
+//   control thread (contiguous 16 / 8 / 4 KB runs of the interleaved layouts) instead of 12 CCTL per compute thread.
+template <bool TIMING, bool LATE, bool CFENCE, bool BPF>
 __global__ void __cluster_dims__(B4_CL, 1, 1) __launch_bounds__(B4_THREADS, 1)
 lstm4_bwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whhT, const float* __restrict__ cst,
-                 const uint16_t* __restrict__ dy, float* __restrict__ dbias, int T, int B) {
+                 const uint16_t* __restrict__ dy, float* __restrict__ dbias, int T, int B, int PFD) {
   extern __shared__ unsigned char b4_smem_raw[];
   const uint32_t raw_s = smem_u32(b4_smem_raw);
   const uint32_t base_s = (raw_s + 127u) & ~127u;
@@ -141,7 +145,23 @@ lstm4_bwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whhT
         peer_delivered[cp] = map_to_cta(delivered_s, (uint32_t)c);
         peer_consumed[cp] = map_to_cta(consumed_s, (uint32_t)c);
       }
+      // chain step sp: gates / dL/dy of its frame, cell state of the frame before it in chain order
+      auto prefetch_step = [&](int sp) {
+        const int tt = dir ? sp : (T - 1 - sp), tq = dir ? (tt + 1) : (tt - 1);
+#pragma unroll
+        for (int rb = 0; rb < 4; ++rb)
+          if (b0 + 32 * rb < B) {
+            const long long g = (long long)tt * B + b0 + 32 * rb;
+            bulk_prefetch_l2(gates + il16(g, dir * B4_G + 256 * j, 2 * B4_G), 16384u);
+            bulk_prefetch_l2(dy + il16(g, dir * B4_HP + 64 * j, 2 * B4_HP), 4096u);
+            if (sp + 1 < T)
+              bulk_prefetch_l2(cst + il32((long long)tq * B + b0 + 32 * rb, dir * B4_HP + 64 * j, 2 * B4_HP), 8192u);
+          }
+      };
+      if (BPF)
+        for (int sp = 1; sp < PFD && sp < T; ++sp) prefetch_step(sp);
       for (int s = 0; s < T; ++s) {
+        if (BPF && s + PFD < T) prefetch_step(s + PFD);               // PFD = prefetch distance in steps
         if (s > 0) {
 #pragma unroll
           for (int ph = 0; ph < 2; ++ph) {                             // peers' partials of step s-1 (both halves) are here
@@ -155,6 +175,7 @@ lstm4_bwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whhT
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           mbar_wait(stagedA_s + 8u * h, (uint32_t)(s & 1));
+          if (CFENCE) fence_proxy_async();
           B4_TICK(1 + 2 * h);
           tc_fence_after();
 #pragma unroll
@@ -181,6 +202,7 @@ lstm4_bwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whhT
 #pragma unroll
           for (int ph = 0; ph < 2; ++ph) {
             mbar_wait(extracted_s + 8u * ph, (uint32_t)(s & 1));
+            if (CFENCE) fence_proxy_async();
             B4_TICK(6);
             if (ph == 0 && s > 0) mbar_wait(consumed_s, (uint32_t)((s - 1) & 1));   // peers' slots are free again
             B4_TICK(7);
@@ -236,7 +258,7 @@ lstm4_bwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whhT
       uint4 g4[4], dyv;
       float cprev[8];
       load_inputs(0, g4, cprev, dyv);
-      if (row_ok && has_prev && (lane & 7) == 0) {     // one lane per 128-byte line of the interleaved runs
+      if (!BPF && row_ok && has_prev && (lane & 7) == 0) {     // one lane per 128-byte line of the interleaved runs
         const int tn = dir ? (t + 1) : (t - 1), tnp = dir ? (t + 2) : (t - 2);
         const long long gn = (long long)tn * B + row, gnp = (long long)tnp * B + row;
         const int ug = 64 * j + 16 * cg;
@@ -348,7 +370,7 @@ lstm4_bwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whhT
         for (int i = 0; i < 4; ++i)
           *reinterpret_cast<uint4*>(&sm.ah[(uint32_t)(cg * 4 + i) * 2048u + (uint32_t)r * 16u]) = pk[i];
         if (has_prev) tmem_st_wait();
-        fence_proxy_async();
+        if (!CFENCE) fence_proxy_async();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_local(stagedA_s + 8u * h);
@@ -363,21 +385,24 @@ lstm4_bwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whhT
         // first the columns the receivers need for their first pass, shipped while the second half is converted
 #pragma unroll
         for (int ph = 0; ph < 2; ++ph) {
+          uint32_t acc[3][8];                         // the three owners' columns in flight together
 #pragma unroll
           for (int cp = 0; cp < 3; ++cp) {
             const int c = cp + (cp >= j ? 1 : 0);
-            uint32_t acc[8];
-            tmem_ld8(trow + (uint32_t)(64 * c + 16 * cg + 8 * ph), acc);
-            tmem_ld_wait();
+            tmem_ld8(trow + (uint32_t)(64 * c + 16 * cg + 8 * ph), acc[cp]);
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int cp = 0; cp < 3; ++cp) {
             uint4 v;
-            v.x = pack_half2(__uint_as_float(acc[0]), __uint_as_float(acc[1]));
-            v.y = pack_half2(__uint_as_float(acc[2]), __uint_as_float(acc[3]));
-            v.z = pack_half2(__uint_as_float(acc[4]), __uint_as_float(acc[5]));
-            v.w = pack_half2(__uint_as_float(acc[6]), __uint_as_float(acc[7]));
+            v.x = pack_half2(__uint_as_float(acc[cp][0]), __uint_as_float(acc[cp][1]));
+            v.y = pack_half2(__uint_as_float(acc[cp][2]), __uint_as_float(acc[cp][3]));
+            v.z = pack_half2(__uint_as_float(acc[cp][4]), __uint_as_float(acc[cp][5]));
+            v.w = pack_half2(__uint_as_float(acc[cp][6]), __uint_as_float(acc[cp][7]));
             *reinterpret_cast<uint4*>(&sm.ah[(uint32_t)ph * PUSH_BYTES + (uint32_t)cp * B4_HALF + (uint32_t)cg * 2048u +
                                              (uint32_t)r * 16u]) = v;
           }
-          fence_proxy_async();
+          if (!CFENCE) fence_proxy_async();
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_local(extracted_s + 8u * ph);
@@ -416,23 +441,29 @@ int launch_lstm4_bwd(uint16_t* gates, const uint16_t* whhT, const float* cst, co
   AVSI_ENV_CACHE(timing, env_is("AVSI_B4_TIMING", "1"));   // in-kernel phase timers (profiles/bench_lstm.py)
   const int smem = (int)sizeof(Lstm4BwdSmem) + 128;
   AVSI_ENV_CACHE(late, env_int("AVSI_B4_LATE", 0));        // AVSI_B4_LATE=1: second half's loads after the hand-over (measured 3 % slower, profiles/README.md)
-  static bool attr_done = false;
-  if (!attr_done) {
-    AVSI_CUDA(cudaFuncSetAttribute(lstm4_bwd_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    AVSI_CUDA(cudaFuncSetAttribute(lstm4_bwd_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    AVSI_CUDA(cudaFuncSetAttribute(lstm4_bwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    AVSI_CUDA(cudaFuncSetAttribute(lstm4_bwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_done = true;
-  }
+  AVSI_ENV_CACHE(cfence, env_int("AVSI_B4_CFENCE", 1));    // 0: proxy fence in the 512 writers (round-1 form, A/B runs)
+  AVSI_ENV_CACHE(bpf_env, env_int("AVSI_B4_BPF", 1));      // 0: per-thread L2 prefetch
+  AVSI_ENV_CACHE(pfd, env_int("AVSI_B4_PFD", 1));          // its distance in steps
+  const int bpf = (bpf_env && pfd > 0 && B % 32 == 0) ? 1 : 0;
   const int grid = 2 * ((B + B4_BT - 1) / B4_BT) * B4_CL;
-  if (timing && late)
-    lstm4_bwd_kernel<true, true><<<grid, B4_THREADS, smem, st>>>(gates, whhT, cst, dy, dbias, T, B);
-  else if (timing)
-    lstm4_bwd_kernel<true, false><<<grid, B4_THREADS, smem, st>>>(gates, whhT, cst, dy, dbias, T, B);
-  else if (late)
-    lstm4_bwd_kernel<false, true><<<grid, B4_THREADS, smem, st>>>(gates, whhT, cst, dy, dbias, T, B);
-  else
-    lstm4_bwd_kernel<false, false><<<grid, B4_THREADS, smem, st>>>(gates, whhT, cst, dy, dbias, T, B);
+  auto launch = [&](auto kern) -> int {
+    static const void* prepared[8];                        // kernels whose shared-memory limit is already raised
+    static int n_prepared = 0;
+    bool seen = false;
+    for (int i = 0; i < n_prepared; ++i) seen |= (prepared[i] == (const void*)kern);
+    if (!seen) {
+      AVSI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      if (n_prepared < 8) prepared[n_prepared++] = (const void*)kern;
+    }
+    kern<<<grid, B4_THREADS, smem, st>>>(gates, whhT, cst, dy, dbias, T, B, pfd);
+    return AVSI_OK;
+  };
+  int rc;
+  if (timing) rc = launch(lstm4_bwd_kernel<true, false, true, false>);
+  else if (late) rc = launch(lstm4_bwd_kernel<false, true, true, false>);
+  else if (!cfence) rc = launch(lstm4_bwd_kernel<false, false, false, false>);
+  else rc = bpf ? launch(lstm4_bwd_kernel<false, false, true, true>) : launch(lstm4_bwd_kernel<false, false, true, false>);
+  if (rc != AVSI_OK) return rc;
   AVSI_LAUNCH_CHECK();
   return AVSI_OK;
 }

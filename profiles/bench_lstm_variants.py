@@ -26,8 +26,20 @@ for B in BS:
     dy = torch.randn(Mp, 512, device=d).half()
     scratch = torch.empty(16, device=d)
     ref = {}
-    variants = [('stg', dict(AVSI_L4_BULK=0, AVSI_B4_LATE=0)), ('stg+late', dict(AVSI_L4_BULK=0, AVSI_B4_LATE=1)),
-                ('bulk+late', dict(AVSI_L4_BULK=1, AVSI_B4_LATE=1))]
+    if os.environ.get('AVSI_VARIANT_SET', '') == 'r02a':
+        variants = [('stg', dict(AVSI_L4_BULK=0, AVSI_B4_LATE=0)), ('stg+late', dict(AVSI_L4_BULK=0, AVSI_B4_LATE=1)),
+                    ('bulk+late', dict(AVSI_L4_BULK=1, AVSI_B4_LATE=1))]
+    elif os.environ.get('AVSI_VARIANT_SET', '') == 'r02h':   # (the late-store variants were slower and are gone from the code)
+        base = dict(AVSI_L4_BULK=0, AVSI_B4_LATE=0, AVSI_L4_CFENCE=0, AVSI_B4_CFENCE=0)
+        variants = [('writer-fence', dict(base)), ('consumer-fence', dict(base, AVSI_L4_CFENCE=1, AVSI_B4_CFENCE=1))]
+    elif os.environ.get('AVSI_VARIANT_SET', '') == 'r02i':   # (issuing the first K-half under the second pass was 13 % slower and is gone)
+        off = dict(AVSI_L4_BULK=0, AVSI_B4_LATE=0, AVSI_L4_CFENCE=0, AVSI_B4_CFENCE=0, AVSI_L4_BPF=0, AVSI_B4_BPF=0)
+        cf = dict(off, AVSI_L4_CFENCE=1, AVSI_B4_CFENCE=1)
+        variants = [('writer-fence', off), ('consumer-fence', cf), ('consumer-fence+bulk-prefetch', dict(cf, AVSI_L4_BPF=1, AVSI_B4_BPF=1))]
+    else:   # r02j: distance of the control thread's bulk L2 prefetch
+        cf = dict(AVSI_L4_BULK=0, AVSI_B4_LATE=0, AVSI_L4_CFENCE=1, AVSI_B4_CFENCE=1, AVSI_L4_BPF=0, AVSI_B4_BPF=0)
+        variants = [('per-thread-prefetch', cf)] + [('bulk-prefetch-%d' % k, dict(cf, AVSI_L4_BPF=1, AVSI_B4_BPF=1, AVSI_L4_PREFETCH=k, AVSI_B4_PFD=k))
+                                                     for k in (1, 2, 3, 4)]
     for name, env in variants + variants:
         _lib.set_env(AVSI_LSTM_FWD='l4', AVSI_LSTM_BWD='l4', **env)
         gates = g0.clone()
@@ -64,4 +76,5 @@ for B in BS:
                    fwd_us_step=1e3 * min(res['fwd']) / T, bwd_us_step=1e3 * min(res['bwd']) / T, same_as_first=same)
         out.append(row)
         print(json.dumps(row), flush=True)
-_lib.set_env(AVSI_LSTM_FWD=None, AVSI_LSTM_BWD=None, AVSI_L4_BULK=None, AVSI_B4_LATE=None)
+_lib.set_env(AVSI_LSTM_FWD=None, AVSI_LSTM_BWD=None, AVSI_L4_BULK=None, AVSI_B4_LATE=None, AVSI_L4_CFENCE=None,
+             AVSI_B4_CFENCE=None, AVSI_L4_BPF=None, AVSI_B4_BPF=None, AVSI_L4_PREFETCH=None, AVSI_B4_PFD=None)

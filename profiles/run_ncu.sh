@@ -8,7 +8,7 @@ CMD="python bench.py --steps 1 --warmup 3 --batch $BATCH --no-cpu-baseline --no-
 mkdir -p gpurun_out
 $CMD > gpurun_out/ncu_plain_$TAG.json 2> gpurun_out/ncu_plain_$TAG.err || { echo "plain run failed"; tail -5 gpurun_out/ncu_plain_$TAG.err; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > /dev/null 2>&1
-for K in lstm4_bwd_kernel lstm4_fwd_kernel gemm_f16_2sm_kernel frontend_train_kernel; do
+for K in lstm4_bwd_kernel lstm4_fwd_kernel gemm_f16_2sm_astat_kernel frontend_train_kernel; do
   ncu --set full --clock-control none --import-source on -k regex:$K -s 6 -c 1 -f -o gpurun_out/prof_${K}_$TAG $CMD > /dev/null 2>&1
 done
 ls -la gpurun_out/ | grep $TAG
