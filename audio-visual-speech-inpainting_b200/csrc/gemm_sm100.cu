@@ -736,8 +736,8 @@ static int get_tmap(const void* ptr, uint64_t d0, uint64_t d1, uint64_t ld, uint
 
 // 3-D tensor map over an interleaved fp16 matrix [rows x ld]: dims {256 (one 32-row x 8-col block, contiguous),
 // row blocks, column chunks}; box {256, brb, bcc}; no swizzle.  Rows / columns beyond the extents read as zero.
-static int get_tmap_il(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t brb, uint32_t bcc,
-                       CUtensorMap* out) {
+int get_tmap_il(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t brb, uint32_t bcc,
+                CUtensorMap* out) {
   static std::mutex mu;
   static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
   TmapKey key{ptr, rows, cols, ld, brb, bcc};

@@ -25,6 +25,7 @@
 //   consumed   3 remote arrives: every peer has READ its slots       -> I may push again
 //   stagedA[h] 16 warps wrote K-half h of the A tile ; freeA / done : tcgen05.commit of the two MMA chains
 //   extracted  16 warps converted the peers' partial columns into the staging area
+#include <string.h>
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 
@@ -69,9 +70,12 @@ __device__ unsigned long long g_b4_timing[24];
 //   hand-over barrier) instead of by each of the 512 writers, whose fence would wait for their loads and stores in flight.
 // BPF (B % 32 == 0): the next steps' gate / cell-state / dL/dy lines are pulled into L2 by cp.async.bulk.prefetch of the
 //   control thread (contiguous 16 / 8 / 4 KB runs of the interleaved layouts) instead of 12 CCTL per compute thread.
-template <bool TIMING, bool LATE, bool CFENCE, bool BPF>
+// STMA (B % 128 == 0, needs CFENCE): dG leaves through the A-half it is staged in anyway -- four TMA tensor stores of the
+//   control thread per half ([4 column chunks][4 row blocks][512 B] boxes of the interleaved layout) instead of four
+//   STG.128 per compute thread; freeA / done then also wait for the stores to have READ the A-half.
+template <bool TIMING, bool LATE, bool CFENCE, bool BPF, bool STMA>
 __global__ void __cluster_dims__(B4_CL, 1, 1) __launch_bounds__(B4_THREADS, 1)
-lstm4_bwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whhT, const float* __restrict__ cst,
+lstm4_bwd_kernel(const __grid_constant__ CUtensorMap tmG, uint16_t* __restrict__ gates, const uint16_t* __restrict__ whhT, const float* __restrict__ cst,
                  const uint16_t* __restrict__ dy, float* __restrict__ dbias, int T, int B, int PFD) {
   extern __shared__ unsigned char b4_smem_raw[];
   const uint32_t raw_s = smem_u32(b4_smem_raw);
@@ -98,8 +102,8 @@ lstm4_bwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whhT
     mbar_init(consumed_s, 3);
     mbar_init(stagedA_s, B4_CWARPS);
     mbar_init(stagedA_s + 8, B4_CWARPS);
-    mbar_init(freeA_s, 1);
-    mbar_init(done_s, 1);
+    mbar_init(freeA_s, STMA ? 2 : 1);
+    mbar_init(done_s, STMA ? 2 : 1);
     mbar_init(extracted_s, B4_CWARPS);
     mbar_init(extracted_s + 8, B4_CWARPS);
     mbar_init(slotread_s, B4_CWARPS);
@@ -178,6 +182,13 @@ lstm4_bwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whhT
           if (CFENCE) fence_proxy_async();
           B4_TICK(1 + 2 * h);
           tc_fence_after();
+          if (STMA) {                                                  // issued ahead of the chains: the reads overlap their issue
+            const int tt = dir ? s : (T - 1 - s);
+            const int rb0 = (int)(((long long)tt * B + b0) >> 5), cc0 = (dir * B4_G + 256 * j) / 8 + 4 * h;
+#pragma unroll
+            for (int cgk = 0; cgk < 4; ++cgk) tma_store_3d(&tmG, ah_s + (uint32_t)cgk * 8192u, 0, rb0, cc0 + 8 * cgk);
+            bulk_commit();
+          }
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)
             umma_f16(tmem_base, make_smem_desc(ah_s + (uint32_t)ks * 4096u, 2048u, 128u, 0u),
@@ -188,6 +199,10 @@ lstm4_bwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whhT
             umma_f16(tmem_base + B4_TM_BIAS + 16u * h, make_smem_desc(ah_s + (uint32_t)ks * 256u, 128u, 2048u, 0u),
                      make_smem_desc(ones_s, 0u, 0u, 0u), idesc_bias, (s > 0 || ks > 0) ? 1u : 0u);
           umma_commit(h == 0 ? freeA_s : done_s);                      // both chains read the A-half
+          if (STMA) {
+            bulk_wait_read0();                                         // the A-half may be overwritten once the chain retired
+            mbar_arrive_local(h == 0 ? freeA_s : done_s);
+          }
           B4_TICK(2 + 2 * h);
           if (h == 0 && s > 0) {
             // my warps read their slots at the start of the second half: tell the senders as early as possible
@@ -219,6 +234,7 @@ lstm4_bwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whhT
 #pragma unroll
       for (int i = 0; i < 12; ++i) g_b4_timing[i] = tacc[i];
     }
+    if (STMA && lane == 0) bulk_wait0();
     __syncwarp();
   } else {
     // ===================================================================== compute warps
@@ -353,7 +369,7 @@ lstm4_bwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whhT
           tmem_st8(trow + B4_TM_C + (uint32_t)ul0, cnew);
           tmem_st8(trow + B4_TM_DC + (uint32_t)ul0, dnew);
         }
-        if (row_ok) {
+        if (!STMA && row_ok) {
 #pragma unroll
           for (int i = 0; i < 4; ++i)
             *reinterpret_cast<uint4*>(gates + il16(grow, dir * B4_G + ug0 * 4 + 8 * i, 2 * B4_G)) = pk[i];
@@ -436,6 +452,8 @@ lstm4_bwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whhT
   }
 }
 
+int get_tmap_il(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t brb, uint32_t bcc, CUtensorMap* out);
+
 int launch_lstm4_bwd(uint16_t* gates, const uint16_t* whhT, const float* cst, const uint16_t* dy, float* dbias, int T,
                      int B, cudaStream_t st) {
   AVSI_ENV_CACHE(timing, env_is("AVSI_B4_TIMING", "1"));   // in-kernel phase timers (profiles/bench_lstm.py)
@@ -446,6 +464,14 @@ int launch_lstm4_bwd(uint16_t* gates, const uint16_t* whhT, const float* cst, co
   AVSI_ENV_CACHE(pfd, env_int("AVSI_B4_PFD", 1));          // its distance in steps
   const int bpf = (bpf_env && pfd > 0 && B % 32 == 0) ? 1 : 0;
   const int grid = 2 * ((B + B4_BT - 1) / B4_BT) * B4_CL;
+  AVSI_ENV_CACHE(stma_env, env_int("AVSI_B4_STMA", 1));    // 0: dG through per-thread STG.128
+  const int stma = (stma_env && cfence && B % 128 == 0) ? 1 : 0;
+  CUtensorMap tmG;
+  memset(&tmG, 0, sizeof(tmG));
+  if (stma) {
+    const int rc_map = get_tmap_il(gates, (uint64_t)T * B, 2 * B4_G, 2 * B4_G, 4, 4, &tmG);
+    if (rc_map != AVSI_OK) return rc_map;
+  }
   auto launch = [&](auto kern) -> int {
     static const void* prepared[8];                        // kernels whose shared-memory limit is already raised
     static int n_prepared = 0;
@@ -455,14 +481,15 @@ int launch_lstm4_bwd(uint16_t* gates, const uint16_t* whhT, const float* cst, co
       AVSI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       if (n_prepared < 8) prepared[n_prepared++] = (const void*)kern;
     }
-    kern<<<grid, B4_THREADS, smem, st>>>(gates, whhT, cst, dy, dbias, T, B, pfd);
+    kern<<<grid, B4_THREADS, smem, st>>>(tmG, gates, whhT, cst, dy, dbias, T, B, pfd);
     return AVSI_OK;
   };
   int rc;
-  if (timing) rc = launch(lstm4_bwd_kernel<true, false, true, false>);
-  else if (late) rc = launch(lstm4_bwd_kernel<false, true, true, false>);
-  else if (!cfence) rc = launch(lstm4_bwd_kernel<false, false, false, false>);
-  else rc = bpf ? launch(lstm4_bwd_kernel<false, false, true, true>) : launch(lstm4_bwd_kernel<false, false, true, false>);
+  if (timing) rc = launch(lstm4_bwd_kernel<true, false, true, false, false>);
+  else if (late) rc = launch(lstm4_bwd_kernel<false, true, true, false, false>);
+  else if (!cfence) rc = launch(lstm4_bwd_kernel<false, false, false, false, false>);
+  else if (stma) rc = bpf ? launch(lstm4_bwd_kernel<false, false, true, true, true>) : launch(lstm4_bwd_kernel<false, false, true, false, true>);
+  else rc = bpf ? launch(lstm4_bwd_kernel<false, false, true, true, false>) : launch(lstm4_bwd_kernel<false, false, true, false, false>);
   if (rc != AVSI_OK) return rc;
   AVSI_LAUNCH_CHECK();
   return AVSI_OK;

@@ -243,6 +243,11 @@ __device__ __forceinline__ void bulk_copy_to_cta(uint32_t remote_dst, uint32_t l
 __device__ __forceinline__ void bulk_store_s2g(void* gdst, uint32_t local_src, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(local_src), "r"(bytes) : "memory");
 }
+// TMA tensor store: shared memory box -> global through a 3-D tensor map, tracked by the thread's bulk async-group
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // all committed bulk groups of this thread have finished READING their shared-memory source (it may be overwritten)
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }

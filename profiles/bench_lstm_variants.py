@@ -36,10 +36,12 @@ for B in BS:
         off = dict(AVSI_L4_BULK=0, AVSI_B4_LATE=0, AVSI_L4_CFENCE=0, AVSI_B4_CFENCE=0, AVSI_L4_BPF=0, AVSI_B4_BPF=0)
         cf = dict(off, AVSI_L4_CFENCE=1, AVSI_B4_CFENCE=1)
         variants = [('writer-fence', off), ('consumer-fence', cf), ('consumer-fence+bulk-prefetch', dict(cf, AVSI_L4_BPF=1, AVSI_B4_BPF=1))]
-    else:   # r02j: distance of the control thread's bulk L2 prefetch
+    elif os.environ.get('AVSI_VARIANT_SET', '') == 'r02j':   # distance of the control thread's bulk L2 prefetch
         cf = dict(AVSI_L4_BULK=0, AVSI_B4_LATE=0, AVSI_L4_CFENCE=1, AVSI_B4_CFENCE=1, AVSI_L4_BPF=0, AVSI_B4_BPF=0)
         variants = [('per-thread-prefetch', cf)] + [('bulk-prefetch-%d' % k, dict(cf, AVSI_L4_BPF=1, AVSI_B4_BPF=1, AVSI_L4_PREFETCH=k, AVSI_B4_PFD=k))
                                                      for k in (1, 2, 3, 4)]
+    else:   # r02k: BPTT dG through TMA tensor stores of the control thread (out of the A-half) vs STG.128 per thread
+        variants = [('stg', dict(AVSI_B4_STMA=0)), ('tma-store', dict(AVSI_B4_STMA=1))]
     for name, env in variants + variants:
         _lib.set_env(AVSI_LSTM_FWD='l4', AVSI_LSTM_BWD='l4', **env)
         gates = g0.clone()
@@ -77,4 +79,4 @@ for B in BS:
         out.append(row)
         print(json.dumps(row), flush=True)
 _lib.set_env(AVSI_LSTM_FWD=None, AVSI_LSTM_BWD=None, AVSI_L4_BULK=None, AVSI_B4_LATE=None, AVSI_L4_CFENCE=None,
-             AVSI_B4_CFENCE=None, AVSI_L4_BPF=None, AVSI_B4_BPF=None, AVSI_L4_PREFETCH=None, AVSI_B4_PFD=None)
+             AVSI_B4_CFENCE=None, AVSI_L4_BPF=None, AVSI_B4_BPF=None, AVSI_L4_PREFETCH=None, AVSI_B4_PFD=None, AVSI_B4_STMA=None)
