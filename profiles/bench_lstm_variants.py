@@ -41,6 +41,8 @@ for B in BS:
         variants = [('per-thread-prefetch', cf)] + [('bulk-prefetch-%d' % k, dict(cf, AVSI_L4_BPF=1, AVSI_B4_BPF=1, AVSI_L4_PREFETCH=k, AVSI_B4_PFD=k))
                                                      for k in (1, 2, 3, 4)]
     else:   # r02k: BPTT dG through TMA tensor stores of the control thread (out of the A-half) vs STG.128 per thread
+        # (the same for the forward kernel's activated gates -- 32 KB staging per pass + 4 TMA stores, AVSI_L4_STMA -- was 16 %
+        # slower, r02l_*: the staging is refilled one pass later, before the store queued behind the DSMEM pushes has read it)
         variants = [('stg', dict(AVSI_B4_STMA=0)), ('tma-store', dict(AVSI_B4_STMA=1))]
     for name, env in variants + variants:
         _lib.set_env(AVSI_LSTM_FWD='l4', AVSI_LSTM_BWD='l4', **env)
