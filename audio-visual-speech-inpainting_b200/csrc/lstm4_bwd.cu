@@ -5,26 +5,27 @@
 // CTA j owns hidden units [64j, 64j+64) = 256 gate columns.  Per step (reverse chain order):
 //   dh      = dy_t + sum of the 4 CTAs' partial  dG_{t+1} . W_hh  restricted to the own 64 units
 //             (own partial straight from TMEM in fp32, 3 peers' partials as fp16 from shared-memory slots)
-//   dG_t    = cell backward (c_t, dc carried in fp32 registers)            -> global (interleaved) and
-//             the A operand tile in shared memory (K-major, K = own gate columns)
+//   dG_t    = cell backward (c_t, dc carried in fp32)  -> the A operand tile in shared memory (K-major, K = own gate
+//             columns) and, out of that tile, to global memory by TMA tensor stores of the control thread
 //   partial = dG_t[128 x 256 own gate cols] . W_hh^T slice [256 gate cols x 256 h_in]   (tcgen05, TMEM)
 //             issued as two K-halves so that the second half of the cell math overlaps the first MMA chain
-//   reduce-scatter: the partial columns of owner c go to CTA c as fp16 with ONE 16 KB bulk DSMEM copy each.
+//             (accumulator columns are ordered [pass][owner][warp][8 units])
+//   reduce-scatter: every compute thread converts the peers' columns of its row to fp16 straight out of TMEM and ships
+//             them with st.async (16 B per thread, owner and pass; complete_tx on the owner's slotfull barrier) -- no
+//             shared-memory staging, no hand-over to the control thread.
 // The bias gradient (column sums of dG over rows and time) costs nothing extra: it is a second, tiny MMA
 // chain  dG^T(view of the same A tile, MN-major) . ones  accumulating in 32 spare TMEM columns over all steps.
 //
 // Per-row state that must survive a step (c_t and the running dc of the 64 own units) is parked in 128 spare
 // TMEM columns (tcgen05.st / tcgen05.ld), which keeps 16 compute warps under 96 registers.
 //
-// Shared memory: W_hh^T slice 128 KB (resident for the whole sequence) + 48 KB A-half / push staging (aliased:
-// the A tile is dead once its MMA chain retired) + 48 KB partial slots = 224 KB.
+// Shared memory: W_hh^T slice 128 KB (resident for the whole sequence) + 32 KB A-half + 48 KB partial slots = 208 KB.
 // Hand-shakes (all mbarriers, no cluster barrier in the loop):
-//   slotfull[p] tx barriers, peers' partials of the previous step for the units of pass p have landed (the push is
-//              split so that the second half's transfer overlaps the first cell-backward pass)
-//   delivered  3 remote arrives: every peer has RECEIVED my last push -> staging / A tile may be overwritten
-//   consumed   3 remote arrives: every peer has READ its slots       -> I may push again
-//   stagedA[h] 16 warps wrote K-half h of the A tile ; freeA / done : tcgen05.commit of the two MMA chains
-//   extracted  16 warps converted the peers' partial columns into the staging area
+//   slotfull[p] tx barriers, peers' partials of the previous step for the units of pass p have landed
+//   consumed   3 remote arrives: every peer has READ its slots       -> my threads may write into them again
+//   stagedA[h] 16 warps wrote K-half h of the A tile ; freeA / done0 / done : tcgen05.commit of the first chain / the
+//              second chain / the second chain + its bias chain (freeA and done also count the TMA stores' read of the A-half)
+//   slotread   16 warps have read their slots (the control thread then tells the peers: consumed)
 #include <string.h>
 #include "common.cuh"
 #include "sm100_ptx.cuh"
@@ -39,16 +40,16 @@ constexpr int B4_CWARPS = 16;
 constexpr int B4_THREADS = (B4_CWARPS + 1) * 32;
 constexpr uint32_t B4_W_BYTES = 256 * 256 * 2;
 constexpr uint32_t B4_SLICE = B4_BT * 64 * 2;          // 16384: partial of one owner (64 units), fp16
-constexpr uint32_t B4_AH_BYTES = 3 * B4_SLICE;          // A-half (first 32 KB) aliased with the 3 staging slices
-// TMEM columns: [0,256) partial dh accumulator, [256,288) bias-gradient accumulators, [288,352) c_t, [352,416) dc
+constexpr uint32_t B4_AH_BYTES = 2 * B4_SLICE;          // A-half: [16 k-chunks][128 rows][16 B]
+// TMEM columns: [0,256) partial dh accumulator (unit 64c + 16cg + 8p + i at column 128p + 32c + 8cg + i), [256,288) bias-gradient accumulators, [288,352) c_t, [352,416) dc
 constexpr uint32_t B4_TM_BIAS = 256, B4_TM_C = 288, B4_TM_DC = 352;
 
 struct Lstm4BwdSmem {
   unsigned char wt[B4_W_BYTES];      // [k-chunk position 0..31][h_in n 0..255][16 B]
-  unsigned char ah[B4_AH_BYTES];     // A-half [16 k-chunks][128 rows][16 B]  |  staging [2 passes][3 owners][4 warps][128 rows][16 B]
+  unsigned char ah[B4_AH_BYTES];     // A-half [16 k-chunks][128 rows][16 B]
   unsigned char slots[3 * B4_SLICE]; // [2 passes][3 sources][4 warps][128 rows][16 B]
   unsigned char ones[128];           // 8 x 8 halves of 1.0 (B operand of the bias MMA, strides 0)
-  unsigned long long slotfull[2], delivered, consumed, stagedA[2], freeA, done, extracted[2], slotread;
+  unsigned long long slotfull[2], consumed, stagedA[2], freeA, done0, done, slotread;
   uint32_t tmem_slot;
 };
 
@@ -63,17 +64,15 @@ __device__ unsigned long long g_b4_timing[24];
     }                                                      \
   } while (0)
 
-// LATE: the second half's inputs are requested AFTER the first half's A-tile hand-over instead of before it.
-// fence.proxy.async compiles to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC (ptxas 12.9): issued ahead of the hand-over, the loads
-// in flight would have to return before the fence retires, i.e. before the first MMA chain can start.
 // CFENCE: the generic -> async proxy fence is executed by the consumer (the control thread, after its acquire of the
-//   hand-over barrier) instead of by each of the 512 writers, whose fence would wait for their loads and stores in flight.
+//   hand-over barrier) instead of by each of the 512 writers, whose fence (MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC under nvcc
+//   12.9) would wait for their loads in flight.
 // BPF (B % 32 == 0): the next steps' gate / cell-state / dL/dy lines are pulled into L2 by cp.async.bulk.prefetch of the
 //   control thread (contiguous 16 / 8 / 4 KB runs of the interleaved layouts) instead of 12 CCTL per compute thread.
 // STMA (B % 128 == 0, needs CFENCE): dG leaves through the A-half it is staged in anyway -- four TMA tensor stores of the
 //   control thread per half ([4 column chunks][4 row blocks][512 B] boxes of the interleaved layout) instead of four
 //   STG.128 per compute thread; freeA / done then also wait for the stores to have READ the A-half.
-template <bool TIMING, bool LATE, bool CFENCE, bool BPF, bool STMA>
+template <bool TIMING, bool CFENCE, bool BPF, bool STMA>
 __global__ void __cluster_dims__(B4_CL, 1, 1) __launch_bounds__(B4_THREADS, 1)
 lstm4_bwd_kernel(const __grid_constant__ CUtensorMap tmG, uint16_t* __restrict__ gates, const uint16_t* __restrict__ whhT, const float* __restrict__ cst,
                  const uint16_t* __restrict__ dy, float* __restrict__ dbias, int T, int B, int PFD) {
@@ -88,24 +87,22 @@ lstm4_bwd_kernel(const __grid_constant__ CUtensorMap tmG, uint16_t* __restrict__
 
   const uint32_t wt_s = smem_u32(&sm.wt[0]), ah_s = smem_u32(&sm.ah[0]), slots_s = smem_u32(&sm.slots[0]);
   const uint32_t ones_s = smem_u32(&sm.ones[0]);
-  const uint32_t slotfull_s = smem_u32(&sm.slotfull[0]), delivered_s = smem_u32(&sm.delivered);
+  const uint32_t slotfull_s = smem_u32(&sm.slotfull[0]);
   const uint32_t consumed_s = smem_u32(&sm.consumed), stagedA_s = smem_u32(&sm.stagedA[0]);
-  const uint32_t freeA_s = smem_u32(&sm.freeA), done_s = smem_u32(&sm.done);
-  const uint32_t extracted_s = smem_u32(&sm.extracted[0]), slotread_s = smem_u32(&sm.slotread);
+  const uint32_t freeA_s = smem_u32(&sm.freeA), done0_s = smem_u32(&sm.done0), done_s = smem_u32(&sm.done);
+  const uint32_t slotread_s = smem_u32(&sm.slotread);
   constexpr uint32_t B4_HALF = B4_SLICE / 2;            // 8192: one owner's partial for the units of one pass
   constexpr uint32_t PUSH_BYTES = 3 * B4_HALF;          // per pass
 
   if (tid == 0) {
     mbar_init(slotfull_s, 1);
     mbar_init(slotfull_s + 8, 1);
-    mbar_init(delivered_s, 3);
     mbar_init(consumed_s, 3);
     mbar_init(stagedA_s, B4_CWARPS);
     mbar_init(stagedA_s + 8, B4_CWARPS);
     mbar_init(freeA_s, STMA ? 2 : 1);
+    mbar_init(done0_s, 1);
     mbar_init(done_s, STMA ? 2 : 1);
-    mbar_init(extracted_s, B4_CWARPS);
-    mbar_init(extracted_s + 8, B4_CWARPS);
     mbar_init(slotread_s, B4_CWARPS);
     fence_barrier_init();
     if (T > 1) {
@@ -120,7 +117,9 @@ lstm4_bwd_kernel(const __grid_constant__ CUtensorMap tmG, uint16_t* __restrict__
     const int n = idx & 255, kpos = idx >> 8;
     const int h = kpos >> 4, cgk = (kpos >> 2) & 3, i = kpos & 3;
     const int gc = 32 * j + 8 * cgk + 4 * h + i;
-    const uint4 v = *reinterpret_cast<const uint4*>(whhT + (long long)n * (2 * B4_G) + dir * B4_G + gc * 8);
+    // accumulator column n = 128 pass + 32 owner + 8 warp + e  <->  hidden unit 64 owner + 16 warp + 8 pass + e
+    const int unit = 64 * ((n >> 5) & 3) + 16 * ((n >> 3) & 3) + 8 * (n >> 7) + (n & 7);
+    const uint4 v = *reinterpret_cast<const uint4*>(whhT + (long long)unit * (2 * B4_G) + dir * B4_G + gc * 8);
     *reinterpret_cast<uint4*>(&sm.wt[(uint32_t)kpos * 4096u + (uint32_t)n * 16u]) = v;
   }
   if (tid < 8) *reinterpret_cast<uint4*>(&sm.ones[tid * 16]) = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
@@ -139,16 +138,9 @@ lstm4_bwd_kernel(const __grid_constant__ CUtensorMap tmG, uint16_t* __restrict__
     if (lane == 0) {
       const uint32_t idesc_main = make_idesc(B4_BT, 256, 0, 0);
       const uint32_t idesc_bias = make_idesc(128, 16, 1, 0);          // A = MN-major view of the A-half (dG^T)
-      uint32_t peer_slot[3], peer_full[3], peer_delivered[3], peer_consumed[3];
+      uint32_t peer_consumed[3];
 #pragma unroll
-      for (int cp = 0; cp < 3; ++cp) {
-        const int c = cp + (cp >= j ? 1 : 0);                          // owner CTA of staging slice cp
-        const int src = (j < c) ? j : j - 1;                           // my slot index at CTA c
-        peer_slot[cp] = map_to_cta(slots_s + (uint32_t)src * B4_HALF, (uint32_t)c);
-        peer_full[cp] = map_to_cta(slotfull_s, (uint32_t)c);
-        peer_delivered[cp] = map_to_cta(delivered_s, (uint32_t)c);
-        peer_consumed[cp] = map_to_cta(consumed_s, (uint32_t)c);
-      }
+      for (int cp = 0; cp < 3; ++cp) peer_consumed[cp] = map_to_cta(consumed_s, (uint32_t)(cp + (cp >= j ? 1 : 0)));
       // chain step sp: gates / dL/dy of its frame, cell state of the frame before it in chain order
       auto prefetch_step = [&](int sp) {
         const int tt = dir ? sp : (T - 1 - sp), tq = dir ? (tt + 1) : (tt - 1);
@@ -166,14 +158,12 @@ lstm4_bwd_kernel(const __grid_constant__ CUtensorMap tmG, uint16_t* __restrict__
         for (int sp = 1; sp < PFD && sp < T; ++sp) prefetch_step(sp);
       for (int s = 0; s < T; ++s) {
         if (BPF && s + PFD < T) prefetch_step(s + PFD);               // PFD = prefetch distance in steps
-        if (s > 0) {
+        if (s > 0 && s + 1 < T) {
 #pragma unroll
-          for (int ph = 0; ph < 2; ++ph) {                             // peers' partials of step s-1 (both halves) are here
+          for (int ph = 0; ph < 2; ++ph) {                             // peers' partials of step s-1 are here: re-arm for step s
             mbar_wait(slotfull_s + 8u * ph, (uint32_t)((s - 1) & 1));
-            if (s + 1 < T) mbar_expect_tx(slotfull_s + 8u * ph, PUSH_BYTES);
+            mbar_expect_tx(slotfull_s + 8u * ph, PUSH_BYTES);
           }
-#pragma unroll
-          for (int cp = 0; cp < 3; ++cp) mbar_arrive_remote_relaxed(peer_delivered[cp]);
         }
         B4_TICK(0);
 #pragma unroll
@@ -189,11 +179,20 @@ lstm4_bwd_kernel(const __grid_constant__ CUtensorMap tmG, uint16_t* __restrict__
             for (int cgk = 0; cgk < 4; ++cgk) tma_store_3d(&tmG, ah_s + (uint32_t)cgk * 8192u, 0, rb0, cc0 + 8 * cgk);
             bulk_commit();
           }
+          if (h == 0) {
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks)
-            umma_f16(tmem_base, make_smem_desc(ah_s + (uint32_t)ks * 4096u, 2048u, 128u, 0u),
-                     make_smem_desc(wt_s + (uint32_t)(16 * h + 2 * ks) * 4096u, 4096u, 128u, 0u), idesc_main,
-                     (h > 0 || ks > 0) ? 1u : 0u);
+            for (int ks = 0; ks < 8; ++ks)
+              umma_f16(tmem_base, make_smem_desc(ah_s + (uint32_t)ks * 4096u, 2048u, 128u, 0u),
+                       make_smem_desc(wt_s + (uint32_t)(2 * ks) * 4096u, 4096u, 128u, 0u), idesc_main, ks > 0 ? 1u : 0u);
+          } else {
+            // second K-half; its commit does not wait for the bias chain.  (Issuing it as two N = 128 halves with a commit
+            // after the first -- the columns the receivers need first -- was measured 4 % slower: profiles/README.md)
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+              umma_f16(tmem_base, make_smem_desc(ah_s + (uint32_t)ks * 4096u, 2048u, 128u, 0u),
+                       make_smem_desc(wt_s + (uint32_t)(16 + 2 * ks) * 4096u, 4096u, 128u, 0u), idesc_main, 1u);
+            umma_commit(done0_s);
+          }
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)
             umma_f16(tmem_base + B4_TM_BIAS + 16u * h, make_smem_desc(ah_s + (uint32_t)ks * 256u, 128u, 2048u, 0u),
@@ -206,26 +205,10 @@ lstm4_bwd_kernel(const __grid_constant__ CUtensorMap tmG, uint16_t* __restrict__
           B4_TICK(2 + 2 * h);
           if (h == 0 && s > 0) {
             // my warps read their slots at the start of the second half: tell the senders as early as possible
-            // (every CTA's push waits for the peers' `consumed`; sending it after the own push would deadlock)
             mbar_wait(slotread_s, (uint32_t)((s - 1) & 1));
 #pragma unroll
             for (int cp = 0; cp < 3; ++cp) mbar_arrive_remote_relaxed(peer_consumed[cp]);
             B4_TICK(5);
-          }
-        }
-        if (s + 1 < T) {
-#pragma unroll
-          for (int ph = 0; ph < 2; ++ph) {
-            mbar_wait(extracted_s + 8u * ph, (uint32_t)(s & 1));
-            if (CFENCE) fence_proxy_async();
-            B4_TICK(6);
-            if (ph == 0 && s > 0) mbar_wait(consumed_s, (uint32_t)((s - 1) & 1));   // peers' slots are free again
-            B4_TICK(7);
-#pragma unroll
-            for (int cp = 0; cp < 3; ++cp)
-              bulk_copy_to_cta(peer_slot[cp] + (uint32_t)ph * PUSH_BYTES, ah_s + (uint32_t)ph * PUSH_BYTES + (uint32_t)cp * B4_HALF,
-                               B4_HALF, peer_full[cp] + 8u * ph);
-            B4_TICK(8);
           }
         }
       }
@@ -243,6 +226,14 @@ lstm4_bwd_kernel(const __grid_constant__ CUtensorMap tmG, uint16_t* __restrict__
     const int row = b0 + r;
     const bool row_ok = row < B;
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t peer_slot[3], peer_full[3];            // this thread's 16 bytes in my slot at owner c, and c's slotfull barriers
+#pragma unroll
+    for (int cp = 0; cp < 3; ++cp) {
+      const int c = cp + (cp >= j ? 1 : 0);
+      const int src = (j < c) ? j : j - 1;
+      peer_slot[cp] = map_to_cta(slots_s + (uint32_t)src * B4_HALF + (uint32_t)cg * 2048u + (uint32_t)r * 16u, (uint32_t)c);
+      peer_full[cp] = map_to_cta(slotfull_s, (uint32_t)c);
+    }
 
     for (int s = 0; s < T; ++s) {
       const int t = dir ? s : (T - 1 - s);          // reverse of the forward chain order
@@ -290,7 +281,7 @@ lstm4_bwd_kernel(const __grid_constant__ CUtensorMap tmG, uint16_t* __restrict__
       if (s > 0) {
         mbar_wait(slotfull_s, (uint32_t)((s - 1) & 1));
         tc_fence_after();
-        tmem_ld8(trow + (uint32_t)(64 * j + 16 * cg + 8), own1);
+        tmem_ld8(trow + (uint32_t)(128 + 32 * j + 8 * cg), own1);
         tmem_ld_wait();
       }
       B4_TICK(0);
@@ -314,7 +305,7 @@ lstm4_bwd_kernel(const __grid_constant__ CUtensorMap tmG, uint16_t* __restrict__
           uint32_t cc[8], dd[8], own[8];
           tmem_ld8(trow + B4_TM_C + (uint32_t)ul0, cc);
           tmem_ld8(trow + B4_TM_DC + (uint32_t)ul0, dd);
-          if (h == 0) tmem_ld8(trow + (uint32_t)ug0, own);
+          if (h == 0) tmem_ld8(trow + (uint32_t)(32 * j + 8 * cg), own);
           tmem_ld_wait();
           if (h == 1) mbar_wait(slotfull_s + 8u, (uint32_t)((s - 1) & 1));      // second half of the peers' partials
 #pragma unroll
@@ -364,7 +355,7 @@ lstm4_bwd_kernel(const __grid_constant__ CUtensorMap tmG, uint16_t* __restrict__
             pk[i >> 1].y = p1;
           }
         }
-        if (!LATE && h == 0) load_inputs(1, g4, cprev, dyv);   // second half's inputs: in flight during the A-half hand-over
+        if (h == 0) load_inputs(1, g4, cprev, dyv);   // second half's inputs: in flight during the A-half hand-over
         if (has_prev) {                               // park c_{t_prev} and dc for the next step
           tmem_st8(trow + B4_TM_C + (uint32_t)ul0, cnew);
           tmem_st8(trow + B4_TM_DC + (uint32_t)ul0, dnew);
@@ -375,13 +366,9 @@ lstm4_bwd_kernel(const __grid_constant__ CUtensorMap tmG, uint16_t* __restrict__
             *reinterpret_cast<uint4*>(gates + il16(grow, dir * B4_G + ug0 * 4 + 8 * i, 2 * B4_G)) = pk[i];
         }
         B4_TICK(1 + 2 * h);
-        // A-half: the chain that read it must have retired and (first half) the peers must have received the
-        // staging slices that alias it
-        if (h == 0) {
-          if (s > 0) mbar_wait(delivered_s, (uint32_t)((s - 1) & 1));
-        } else {
-          mbar_wait(freeA_s, (uint32_t)(s & 1));
-        }
+        // A-half: the chain that read it (and the TMA store out of it) must have retired -- the previous step's second
+        // chain was waited for at the end of that step
+        if (h == 1) mbar_wait(freeA_s, (uint32_t)(s & 1));
 #pragma unroll
         for (int i = 0; i < 4; ++i)
           *reinterpret_cast<uint4*>(&sm.ah[(uint32_t)(cg * 4 + i) * 2048u + (uint32_t)r * 16u]) = pk[i];
@@ -390,40 +377,36 @@ lstm4_bwd_kernel(const __grid_constant__ CUtensorMap tmG, uint16_t* __restrict__
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_local(stagedA_s + 8u * h);
-        if (LATE && h == 0) load_inputs(1, g4, cprev, dyv);    // L2 hits (prefetched a step ahead), under the first MMA chain
         B4_TICK(2 + 2 * h);
       }
-      // ---- the partial of this step: other owners' columns -> fp16 staging -> (control thread) DSMEM push ----
-      mbar_wait(done_s, (uint32_t)(s & 1));
-      tc_fence_after();
-      B4_TICK(7);
+      // ---- the partial of this step: the other owners' columns of this thread's row -> fp16 -> st.async into their slots ----
       if (has_prev) {
-        // first the columns the receivers need for their first pass, shipped while the second half is converted
 #pragma unroll
         for (int ph = 0; ph < 2; ++ph) {
+          mbar_wait(ph == 0 ? done0_s : done_s, (uint32_t)(s & 1));
+          tc_fence_after();
+          if (ph == 0) B4_TICK(7);
           uint32_t acc[3][8];                         // the three owners' columns in flight together
 #pragma unroll
           for (int cp = 0; cp < 3; ++cp) {
             const int c = cp + (cp >= j ? 1 : 0);
-            tmem_ld8(trow + (uint32_t)(64 * c + 16 * cg + 8 * ph), acc[cp]);
+            tmem_ld8(trow + (uint32_t)(128 * ph + 32 * c + 8 * cg), acc[cp]);
           }
           tmem_ld_wait();
+          if (ph == 0 && s > 0) mbar_wait(consumed_s, (uint32_t)((s - 1) & 1));     // the peers have read their slots of the last step
 #pragma unroll
-          for (int cp = 0; cp < 3; ++cp) {
-            uint4 v;
-            v.x = pack_half2(__uint_as_float(acc[cp][0]), __uint_as_float(acc[cp][1]));
-            v.y = pack_half2(__uint_as_float(acc[cp][2]), __uint_as_float(acc[cp][3]));
-            v.z = pack_half2(__uint_as_float(acc[cp][4]), __uint_as_float(acc[cp][5]));
-            v.w = pack_half2(__uint_as_float(acc[cp][6]), __uint_as_float(acc[cp][7]));
-            *reinterpret_cast<uint4*>(&sm.ah[(uint32_t)ph * PUSH_BYTES + (uint32_t)cp * B4_HALF + (uint32_t)cg * 2048u +
-                                             (uint32_t)r * 16u]) = v;
-          }
-          if (!CFENCE) fence_proxy_async();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_local(extracted_s + 8u * ph);
+          for (int cp = 0; cp < 3; ++cp)
+            st_async_v4(peer_slot[cp] + (uint32_t)ph * PUSH_BYTES,
+                        pack_half2(__uint_as_float(acc[cp][0]), __uint_as_float(acc[cp][1])),
+                        pack_half2(__uint_as_float(acc[cp][2]), __uint_as_float(acc[cp][3])),
+                        pack_half2(__uint_as_float(acc[cp][4]), __uint_as_float(acc[cp][5])),
+                        pack_half2(__uint_as_float(acc[cp][6]), __uint_as_float(acc[cp][7])), peer_full[cp] + 8u * ph);
         }
+        tc_fence_before();                            // the loads above precede the next step's first chain (accumulate = 0)
         B4_TICK(8);
+      } else {
+        mbar_wait(done_s, (uint32_t)(s & 1));         // last step: all chains retired before the bias columns are read
+        tc_fence_after();
       }
     }
     if (timing) {
@@ -458,7 +441,6 @@ int launch_lstm4_bwd(uint16_t* gates, const uint16_t* whhT, const float* cst, co
                      int B, cudaStream_t st) {
   AVSI_ENV_CACHE(timing, env_is("AVSI_B4_TIMING", "1"));   // in-kernel phase timers (profiles/bench_lstm.py)
   const int smem = (int)sizeof(Lstm4BwdSmem) + 128;
-  AVSI_ENV_CACHE(late, env_int("AVSI_B4_LATE", 0));        // AVSI_B4_LATE=1: second half's loads after the hand-over (measured 3 % slower, profiles/README.md)
   AVSI_ENV_CACHE(cfence, env_int("AVSI_B4_CFENCE", 1));    // 0: proxy fence in the 512 writers (round-1 form, A/B runs)
   AVSI_ENV_CACHE(bpf_env, env_int("AVSI_B4_BPF", 1));      // 0: per-thread L2 prefetch
   AVSI_ENV_CACHE(pfd, env_int("AVSI_B4_PFD", 1));          // its distance in steps
@@ -485,11 +467,10 @@ int launch_lstm4_bwd(uint16_t* gates, const uint16_t* whhT, const float* cst, co
     return AVSI_OK;
   };
   int rc;
-  if (timing) rc = launch(lstm4_bwd_kernel<true, false, true, false, false>);
-  else if (late) rc = launch(lstm4_bwd_kernel<false, true, true, false, false>);
-  else if (!cfence) rc = launch(lstm4_bwd_kernel<false, false, false, false, false>);
-  else if (stma) rc = bpf ? launch(lstm4_bwd_kernel<false, false, true, true, true>) : launch(lstm4_bwd_kernel<false, false, true, false, true>);
-  else rc = bpf ? launch(lstm4_bwd_kernel<false, false, true, true, false>) : launch(lstm4_bwd_kernel<false, false, true, false, false>);
+  if (timing) rc = launch(lstm4_bwd_kernel<true, true, false, false>);
+  else if (!cfence) rc = launch(lstm4_bwd_kernel<false, false, false, false>);
+  else if (stma) rc = bpf ? launch(lstm4_bwd_kernel<false, true, true, true>) : launch(lstm4_bwd_kernel<false, true, false, true>);
+  else rc = bpf ? launch(lstm4_bwd_kernel<false, true, true, false>) : launch(lstm4_bwd_kernel<false, true, false, false>);
   if (rc != AVSI_OK) return rc;
   AVSI_LAUNCH_CHECK();
   return AVSI_OK;

@@ -77,9 +77,8 @@ if os.environ.get('AVSI_B4_TIMING'):
     torch.cuda.synchronize()
     lib.avsi_debug_lstm4_bwd_timing.argtypes = [ctypes.c_void_p]
     lib.avsi_debug_lstm4_bwd_timing(buf)
-    for o, who, names in ((0, 'control', ['wait_slotfull', 'wait_stagedA0', 'mma0', 'wait_stagedA1', 'mma1', 'send_consumed',
-                                          'wait_extracted', 'wait_consumed', 'push']),
-                          (12, 'compute0', ['wait_slotfull+own', 'pass0', 'wait+write A0', 'pass1', 'wait+write A1', '-', '-',
-                                            'wait_done', 'extract', 'issue loads'])):
+    for o, who, names in ((0, 'control', ['wait_slotfull', 'wait_stagedA0', 'mma0', 'wait_stagedA1', 'mma1', 'send_consumed']),
+                          (12, 'compute0', ['wait_slotfull+own', 'pass0', 'write A0', 'pass1', 'wait+write A1', '-', '-',
+                                            'wait_done0', 'extract+st.async', 'issue loads'])):
         print(who, '  '.join('%s %.0f' % (n, buf[o + i] / T) for i, n in enumerate(names)),
               ' total %.0f cyc/step' % (sum(buf[o:o + 12]) / T))

@@ -40,10 +40,17 @@ for B in BS:
         cf = dict(AVSI_L4_BULK=0, AVSI_B4_LATE=0, AVSI_L4_CFENCE=1, AVSI_B4_CFENCE=1, AVSI_L4_BPF=0, AVSI_B4_BPF=0)
         variants = [('per-thread-prefetch', cf)] + [('bulk-prefetch-%d' % k, dict(cf, AVSI_L4_BPF=1, AVSI_B4_BPF=1, AVSI_L4_PREFETCH=k, AVSI_B4_PFD=k))
                                                      for k in (1, 2, 3, 4)]
-    else:   # r02k: BPTT dG through TMA tensor stores of the control thread (out of the A-half) vs STG.128 per thread
+    elif os.environ.get('AVSI_VARIANT_SET', '') == 'r02k':   # BPTT dG through TMA tensor stores of the control thread (out of the A-half) vs STG.128 per thread
         # (the same for the forward kernel's activated gates -- 32 KB staging per pass + 4 TMA stores, AVSI_L4_STMA -- was 16 %
         # slower, r02l_*: the staging is refilled one pass later, before the store queued behind the DSMEM pushes has read it)
         variants = [('stg', dict(AVSI_B4_STMA=0)), ('tma-store', dict(AVSI_B4_STMA=1))]
+    elif os.environ.get('AVSI_VARIANT_SET', '') == 'r02n':
+        # BPTT reduce-scatter by st.async straight out of TMEM (no staging / control-thread hop); second chain as two N = 128
+        # halves (AVSI_B4_NSPLIT, gone from the code: 1.382 vs 1.323 ms) -- logs r02n_*
+        variants = [('default', dict())]
+    else:   # current defaults against the round-1 forms that are still selectable
+        on = dict(AVSI_L4_CFENCE=1, AVSI_B4_CFENCE=1, AVSI_L4_BPF=1, AVSI_B4_BPF=1, AVSI_B4_STMA=1)
+        variants = [('default', on), ('writer-fence,stg,per-thread-prefetch', dict(on, AVSI_L4_CFENCE=0, AVSI_B4_CFENCE=0))]
     for name, env in variants + variants:
         _lib.set_env(AVSI_LSTM_FWD='l4', AVSI_LSTM_BWD='l4', **env)
         gates = g0.clone()
