@@ -310,10 +310,37 @@ def get_sources(mag_spectrograms, rec_ang_spectrograms, num_samples=48000, sampl
 
 
 def downsampling(samples, sample_rate, downsample_rate):
-    """audio_processing.py:9-16 (host-side scipy FFT resampling, offline data preparation)."""
-    from scipy import signal
-    secs = len(samples) / float(sample_rate)
+    """audio_processing.py:9-16: Fourier-domain resampling of a whole recording (scipy.signal.resample semantics) on the
+    GPU -- `avsi_resample_fft`, chirp-z DFTs of any length in complex double.  `samples`: 1-D array (or [batch, n] of equal
+    lengths); returns float64 like scipy."""
+    import numpy as np
+    x = np.asarray(samples)
+    n_in = x.shape[-1]
+    secs = n_in / float(sample_rate)
     num_samples = int(downsample_rate * secs)
-    if sample_rate != downsample_rate:
-        return signal.resample(samples, num_samples)
-    return samples
+    if sample_rate == downsample_rate:
+        return samples
+    return resample(x, num_samples)
+
+
+def resample(x, num):
+    """scipy.signal.resample(x, num) along the last axis for real x, on the GPU (float64 result)."""
+    import numpy as np
+    x = np.asarray(x)
+    if np.iscomplexobj(x):
+        raise ValueError('resample: real input only (the reference resamples wav samples)')
+    lead = x.shape[:-1]
+    n_in = x.shape[-1]
+    if n_in < 1 or num < 1:
+        raise ValueError('resample: empty input or output')
+    lib = _lib.load()
+    xd = torch.as_tensor(np.ascontiguousarray(x.reshape(-1, n_in), dtype=np.float64), device='cuda')
+    batch = xd.shape[0]
+    need = lib.avsi_resample_workspace_bytes(batch, n_in, num)
+    if need < 0:
+        raise ValueError('resample: unsupported sizes %d -> %d' % (n_in, num))
+    work = torch.empty(need, dtype=torch.uint8, device='cuda')
+    y = torch.empty(batch, num, dtype=torch.float64, device='cuda')
+    _lib.check(lib.avsi_resample_fft(_lib.ptr(xd), batch, n_in, _lib.ptr(y), num, _lib.ptr(work), need, _lib.stream_ptr()),
+               'avsi_resample_fft')
+    return y.cpu().numpy().reshape(lead + (num,))

@@ -310,14 +310,17 @@ class BLSTMEngine(object):
             self.refresh_half()
 
     # ---- update -------------------------------------------------------------------------------
-    def adam_step(self, lr=1e-3, grad_unscale=1.0, unscale_dev=None, l2=0.0, b1=0.9, b2=0.999, eps=1e-8):
+    def adam_step(self, lr=1e-3, grad_unscale=1.0, unscale_dev=None, l2=0.0, b1=0.9, b2=0.999, eps=1e-8,
+                  device_step=False):
+        """device_step: the update's number is read from the guard's call count on the device instead of being passed
+        from the host (the form a captured CUDA graph replays); the host mirror `step_count` still advances."""
         lib = _lib.load()
         self.step_count += 1
         n = self.layout.n_params_padded
         with _lib.span('adam'):
             self._guard_check()
             _lib.check(lib.avsi_adam_tf(_p(self.theta), _p(self.grad), _p(self.adam_m), _p(self.adam_v), n, lr, b1, b2,
-                                        eps, self.step_count, grad_unscale, _p(unscale_dev), l2, _p(self.guard),
+                                        eps, 0 if device_step else self.step_count, grad_unscale, _p(unscale_dev), l2, _p(self.guard),
                                         _lib.stream_ptr()), 'avsi_adam_tf')
             self._guard_update()
             self.refresh_half()

@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, 'csrc')
 LIB_PATH = os.path.join(HERE, 'libavsi_b200.so')
 BUILD_DIR = os.path.join(HERE, 'csrc', 'build')
 
-SOURCES = ['capi.cu', 'frontend.cu', 'istft.cu', 'video.cu', 'gemm_sm100.cu', 'lstm.cu', 'lstm4.cu', 'lstm4_bwd.cu', 'loss.cu', 'ctc.cu', 'optim.cu', 'stats.cu', 'dropout.cu', 'ctc_decode.cu', 'features_extra.cu', 'tfrecord_host.cu', 'ssnn.cu']
+SOURCES = ['capi.cu', 'frontend.cu', 'istft.cu', 'video.cu', 'gemm_sm100.cu', 'lstm.cu', 'lstm4.cu', 'lstm4_bwd.cu', 'loss.cu', 'ctc.cu', 'optim.cu', 'stats.cu', 'dropout.cu', 'ctc_decode.cu', 'features_extra.cu', 'tfrecord_host.cu', 'ssnn.cu', 'resample.cu']
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-std=c++17', '-O3', '-lineinfo',
               '-Xcompiler', '-fPIC']

@@ -13,7 +13,8 @@ adam_tf_kernel(float* __restrict__ theta, const float* __restrict__ g, float* __
                float unscale, const float* __restrict__ unscale_dev, float l2, const int32_t* __restrict__ guard) {
   if (guard && guard[0] != 0) return;            // non-finite gradient (avsi_grad_guard): the step is skipped as a whole
   // lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t) in double; t counts the updates actually applied (skipped steps excluded)
-  const int t = step - (guard ? guard[1] : 0);
+  // step == 0: the call count lives on the device (guard[3], bumped by grad_guard_update) -- what a captured CUDA graph replays
+  const int t = (step > 0 ? step : guard[3] + 1) - (guard ? guard[1] : 0);
   const float lr_t = (float)(lr * sqrt(1.0 - pow(b2d, (double)t)) / (1.0 - pow(b1d, (double)t)));
   const float b1 = (float)b1d, omb1 = (float)(1.0 - b1d), b2 = (float)b2d, omb2 = (float)(1.0 - b2d);
   const float us = unscale * (unscale_dev ? *unscale_dev : 1.f) * (guard ? __int_as_float(guard[5]) : 1.f);
@@ -51,6 +52,7 @@ sgd_momentum_kernel(float* __restrict__ theta, const float* __restrict__ g, floa
 // Overflow guard of the fp16 gradient path.  The activations' gradients (dlogits, dY, dG) are fp16 and flow loss-scaled;
 // a run-away dh saturates at 65504 -> inf -> NaN in the weight gradients.  guard = 8 words:
 //   [0] i32 non-finite flag of THIS step   [1] i32 steps skipped so far   [2] i32 finite steps since the last change
+//   [3] i32 optimiser calls completed (the device-resident step count of graph replays)
 //   [4] f32 dynamic scale s (multiplies the loss gradient fed to the backward pass, a power of two <= 1)
 //   [5] f32 1 / s (folded into the optimiser's unscale)
 // grad_guard_check sets [0]; the optimiser kernels return without touching theta / m / v when it is set;
@@ -74,6 +76,7 @@ __global__ void grad_guard_update_kernel(int32_t* __restrict__ guard, int growth
     guard[2] = 0;
     s *= 2.f;
   }
+  guard[3] += 1;
   guard[4] = __float_as_int(s);
   guard[5] = __float_as_int(1.f / s);
 }
@@ -150,7 +153,7 @@ extern "C" int avsi_adam_tf(float* theta, const float* g, float* m, float* v, in
                             float l2, const int32_t* guard, void* stream) {
   using namespace avsi;
   AVSI_REQUIRE(theta && g && m && v, "null pointer");
-  AVSI_REQUIRE(n > 0 && step >= 1, "n > 0, step >= 1");
+  AVSI_REQUIRE(n > 0 && (step >= 1 || (step == 0 && guard)), "n > 0, step >= 1 (or 0 with a guard: device-resident count)");
   int blocks = (int)min((long long)(n + 255) / 256, (long long)num_sms() * 8);
   adam_tf_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(theta, g, m, v, (long long)n, lr, step, b1, b2, (float)eps,
                                                           grad_unscale, grad_unscale_dev, l2, guard);

@@ -415,7 +415,7 @@ class StackedBLSTMModel(object):
             parallel.all_reduce_flat(self.engine.grad, self.process_group)
         return world
 
-    def train_op(self):
+    def train_op(self, _device_step=False):
         if self.optimizer_choice not in ('adam', 'sgd', 'momentum'):
             print('Optimizer must be either sgd, momentum or adam. Closing...')         # models.py:175-176
             sys.exit(1)
@@ -425,12 +425,67 @@ class StackedBLSTMModel(object):
         if self.optimizer_choice == 'adam':
             # Adam is given the constant starter rate (models.py:168); the decayed rate applies to sgd / momentum only
             self.engine.adam_step(lr=self.starter_learning_rate, grad_unscale=host, unscale_dev=dev,
-                                  l2=self.regularization)
+                                  l2=self.regularization, device_step=_device_step)
         else:
             self.engine.sgd_step(self.learning_rate, 0.9 if self.optimizer_choice == 'momentum' else None,
                                  grad_unscale=host, unscale_dev=dev, l2=self.regularization)
         self.global_step += 1
         self._stale = True
+
+    def capture_train_step(self):
+        """The whole training step of the CURRENT feed's shapes -- front end, BLSTM stack, loss, BPTT, optimiser: ~40 kernel
+        launches through ctypes -- captured once into a CUDA graph and replayed with one launch per step.  At the
+        reference's own batch sizes (8 ... 32 utterances, training_ctc.py) the step is a 1500-link dependent chain of
+        microsecond kernels and the host cannot always keep the launch queue ahead of it; a graph takes the host out.
+
+        Returns `step(**feeds)`: copies the named tensors into the captured input buffers (same shapes), replays, and
+        leaves `loss`, `loss_hole`, ... readable as after `train_op()`.  Requirements (raised, never silently eager):
+        Adam (the decayed learning rate of sgd / momentum is a host value per step), dropout_rate == 0 (the dropout
+        offset is a host counter), a single process, and at least one eager `train_op()` on these shapes beforehand
+        (workspaces, tensor maps and kernel attributes are created on first use)."""
+        if not self.is_training:
+            raise _lib.AvsiError('model was built with is_training=False')
+        if self.optimizer_choice != 'adam' or float(self._fed.get('dropout_rate', 0.0)) != 0.0 or self.process_group is not None:
+            raise _lib.AvsiError('capture_train_step needs optimizer adam, dropout_rate 0 and no process group')
+        if self.engine.step_count < 1:
+            raise _lib.AvsiError('run one eager train_op() on a feed of these shapes before capturing')
+        static = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in self._fed.items()}
+        self._fed = static
+        self._widen = {}
+        eng = self.engine
+        eng.guard[3] = eng.step_count                       # the device-resident update count takes over from the host's
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        steps_before, host_count = self.global_step, eng.step_count
+        with torch.cuda.stream(side):
+            self._cache, self._stale = {}, False
+            with torch.cuda.graph(graph, stream=side):
+                self.train_op(_device_step=True)
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        self.global_step, eng.step_count = steps_before, host_count   # capturing executes nothing
+        captured_cache = self._cache
+
+        def step(**feeds):
+            for k, v in feeds.items():
+                if v is None:
+                    continue
+                dst = static.get(k)
+                if not torch.is_tensor(dst):
+                    raise KeyError('feed %r is not part of the captured step' % k)
+                src = v if torch.is_tensor(v) else torch.as_tensor(np.asarray(v))
+                if tuple(src.shape) != tuple(dst.shape):
+                    raise ValueError('captured step: %s must keep shape %s, got %s' % (k, tuple(dst.shape), tuple(src.shape)))
+                dst.copy_(src, non_blocking=True)
+            self._fed, self._cache = static, captured_cache
+            graph.replay()
+            self._feeds += 1
+            self.global_step += 1
+            eng.step_count += 1
+            self._stale = True
+        step.graph = graph
+        return step
 
     def canonical_gradients(self, reduce=False):
         """d loss / d variable in the reference's canonical layout (float64 numpy), for parity tests.  reduce=True (data

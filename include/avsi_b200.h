@@ -110,6 +110,14 @@ int avsi_spectrogram(const float* stft_c64, int64_t n, float power, int log_flag
 int avsi_log_mel(const float* spec, const float* mel_w, int64_t rows, int nbins, int n_mel, float eps, float* out,
                  void* stream);
 int avsi_mfcc(const float* logmel, int64_t rows, int n_mel, int n_mfcc, float* out, void* stream);
+/* downsampling(samples, sample_rate, downsample_rate), audio_processing.py:9-16 = scipy.signal.resample(x, num) for real x
+ * (dataset preparation: audio_feat_preprocessing.py:82,189; tfrecord_utils.py): forward DFT of the n_in samples, first
+ * min(n_in, n_out)/2 + 1 bins with scipy's Nyquist rule, inverse real DFT of length n_out, times n_out / n_in.  Any lengths
+ * (both transforms are chirp-z convolutions on power-of-two FFTs), complex double arithmetic, `batch` recordings of equal
+ * length.  x [batch, n_in] f64, y [batch, n_out] f64, workspace: avsi_resample_workspace_bytes() bytes of device memory. */
+int64_t avsi_resample_workspace_bytes(int batch, int64_t n_in, int64_t n_out);
+int avsi_resample_fft(const double* x, int batch, int64_t n_in, double* y, int64_t n_out, void* workspace,
+                      int64_t workspace_bytes, void* stream);
 int avsi_delta_features(const float* src, int ld_src, float* dst, int ld_dst, int B, int T, int F, int N, void* stream);
 
 /* Waveform reconstruction (next row 8f.1): get_sources / reconstruct_sources
@@ -291,7 +299,9 @@ uint32_t avsi_crc32c_host(const void* data, uint64_t n, uint32_t crc);
 
 /* ------------------------------------------------------------------------------------
  * Optimiser.  Replaces tf.train.AdamOptimizer ApplyAdam (models.py:168,178), TF epsilon-hat form.
- *   g is multiplied by grad_unscale first; l2 adds l2 * theta to the gradient (models.py:153-158). */
+ *   g is multiplied by grad_unscale first; l2 adds l2 * theta to the gradient (models.py:153-158).
+ *   step = number of this update (>= 1), or 0 to take it from the guard's device-resident call count (guard word 3, bumped
+ *   by avsi_grad_guard_update): the form a captured CUDA graph of the training step replays. */
 int avsi_adam_tf(float* theta, const float* g, float* m, float* v, int64_t n, double lr, double b1,
                  double b2, double eps, int step, float grad_unscale, const float* grad_unscale_dev,
                  float l2, const int32_t* guard, void* stream);

@@ -818,6 +818,33 @@ def test_preemphasis_mfcc_delta_features():
     assert np.abs(one - ostft.delta(x)).max() < 1e-5
 
 
+def test_downsampling_fft_resample_matches_scipy():
+    """audio_processing.py:9-16: whole-recording Fourier resampling on the GPU (chirp-z DFTs in complex
+    double) against scipy.signal.resample -- the library the reference calls -- and the oracle restatement: the GRID case
+    (150 000 int16 samples at 50 kHz -> 48 000), even / odd lengths in both directions, tiny inputs, a batch."""
+    from scipy import signal
+    from avsi_b200 import audio_processing as ap
+    from oracle import resample as ores
+    rng = np.random.default_rng(23)
+    wav = np.round(rng.normal(0, 3000, 150000)).astype(np.int16)
+    got = ap.downsampling(wav, 50000, 16000)
+    ref = signal.resample(wav, 48000)
+    assert got.dtype == np.float64 and got.shape == (48000,)
+    assert rel_l2(got, ref) < 1e-12 and rel_l2(got, ores.downsampling(wav, 50000, 16000)) < 1e-12
+    assert ap.downsampling(wav, 16000, 16000) is wav
+    for nx, num in ((1000, 320), (1001, 320), (1000, 321), (999, 333), (320, 1000), (321, 1000), (320, 1001), (7, 3),
+                    (64, 64), (5, 8), (6, 4), (2, 1), (1, 5), (44100, 16000), (131072, 65536)):
+        x = rng.standard_normal(nx) * 1000.0
+        got = ap.resample(x, num)
+        ref = signal.resample(x, num)
+        assert got.shape == ref.shape and np.abs(got - ref).max() <= 1e-10 * max(1.0, np.abs(ref).max()), (nx, num)
+    xb = rng.standard_normal((3, 2, 4410)) * 100.0
+    got = ap.resample(xb, 1600)
+    assert got.shape == (3, 2, 1600) and np.abs(got - signal.resample(xb, 1600, axis=-1)).max() < 1e-9
+    with pytest.raises(ValueError):
+        ap.resample(x.astype(np.complex128), 10)
+
+
 def test_mean_std_features_mfcc_with_deltas(tmp_path):
     """compute_mean_std_features(type='mfcc', preemph, delta) and save_features: the statistics of the composed features
     equal the float64 restatement's (audio_feat_preprocessing.py:23-115, 130-196)."""

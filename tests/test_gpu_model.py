@@ -231,6 +231,53 @@ def test_train_step_matches_oracle_adam_and_learns():
     assert float((model.engine.theta.abs() * pad).max()) == 0.0
 
 
+@pytest.mark.parametrize('model_name,B', [('av-blstm', 8), ('av-blstm-ssnn-ctc', 4), ('av-blstm', 256)])
+def test_captured_train_step_equals_eager_steps(model_name, B):
+    """capture_train_step(): the CUDA-graph replay of feed -> train_op follows the eager steps -- same losses, same
+    weights after four updates on four different batches (the split-K atomics make neither run bit-reproducible), Adam's
+    bias correction advancing from the device-resident count, shape changes and unsupported settings refused."""
+    from avsi_b200 import _lib, av_sync, synth
+    eager, batch, canon, inp = _build(model_name, B, 4800, seed=3)
+    graphed, _, _, _ = _build(model_name, B, 4800, seed=3)
+    batches = [batch] + [synth.make_batch(B, audio_len=4800, seed=30 + i) for i in range(3)]
+
+    def feeds(b):
+        video = av_sync.video_pipeline(b['landmarks'], b['T'], b['vmean'], b['vstd'])
+        f = dict(target_sources=b['wav'], masks=b['mask'], sequence_lengths=b['seq_len'], video_features=video)
+        if eager.MTL:
+            f.update(labels=b['labels'], labels_lengths=b['lab_len'])
+        return f
+    with pytest.raises(_lib.AvsiError):
+        graphed.capture_train_step()                     # no eager step yet
+    losses_e, losses_g = [], []
+    for m in (eager, graphed):
+        m.feed(**feeds(batches[0]))
+        m.train_op()
+    step = graphed.capture_train_step()
+    assert graphed.global_step == 1 and graphed.engine.step_count == 1
+    for b in batches[1:]:
+        eager.feed(**feeds(b))
+        eager.train_op()
+        losses_e.append(float(eager.loss))
+        step(**feeds(b))
+        losses_g.append(float(graphed.loss))
+    assert graphed.global_step == eager.global_step == 4 and graphed.engine.step_count == 4
+    assert np.allclose(losses_g, losses_e, rtol=2e-4), (losses_g, losses_e)
+    we, wg = eager.engine.export_canonical(), graphed.engine.export_canonical()
+    moved = np.concatenate([(we[k] - canon[k]).ravel() for k in sorted(canon)])
+    diff = np.concatenate([(we[k] - wg[k]).ravel() for k in sorted(canon)])
+    assert np.linalg.norm(moved) > 0 and np.linalg.norm(diff) < 2e-2 * np.linalg.norm(moved)
+    # eager steps keep working on the same model afterwards, from the same count
+    graphed.feed(**feeds(batches[0]))
+    graphed.train_op()
+    assert graphed.global_step == 5 and np.isfinite(float(graphed.loss))
+    with pytest.raises(ValueError):
+        step(target_sources=batches[0]['wav'][:, :100])
+    graphed.optimizer_choice = 'sgd'
+    with pytest.raises(_lib.AvsiError):
+        graphed.capture_train_step()
+
+
 def test_variables_roundtrip_and_inference_mode():
     from avsi_b200 import av_sync, models, synth
     model, batch, canon, inp = _build('av-blstm', 2, 4800, seed=7)

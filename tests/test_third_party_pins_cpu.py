@@ -264,3 +264,22 @@ def test_mfcc_against_scipy_dct():
     ref = dct(logmel, type=2, norm=None, axis=-1) / np.sqrt(2.0 * 80)
     got = ostft.get_mfcc(logmel, 13)
     assert np.abs(got - ref[..., :13]).max() < 1e-12
+
+
+def test_resample_oracle_against_scipy_signal_resample():
+    """downsampling (audio_processing.py:9-16) delegates to scipy.signal.resample; scipy is in the image, so the oracle's
+    restatement of its real-input branch (bins kept, Nyquist doubling / halving, num / n_in) is held against scipy itself
+    on even and odd lengths in both directions, and at the GRID lengths (150 000 samples at 50 kHz -> 48 000)."""
+    from scipy import signal
+    from oracle import resample as ores
+    rng = np.random.default_rng(17)
+    for nx, num in ((150000, 48000), (1000, 320), (1001, 320), (1000, 321), (999, 333), (320, 1000), (321, 1000),
+                    (320, 1001), (7, 3), (64, 64), (5, 8), (6, 4), (2, 1), (1, 5)):
+        x = np.round(rng.normal(0, 3000, nx))
+        ref = signal.resample(x, num)
+        got = ores.resample(x, num)
+        assert got.shape == ref.shape and np.abs(got - ref).max() <= 1e-9 * max(1.0, np.abs(ref).max()), (nx, num)
+    wav = np.round(rng.normal(0, 3000, 150000)).astype(np.int16)
+    ref = signal.resample(wav, int(16000 * (len(wav) / 50000.0)))
+    assert np.abs(ores.downsampling(wav, 50000, 16000) - ref).max() < 1e-8
+    assert ores.downsampling(wav, 16000, 16000) is wav
