@@ -349,6 +349,8 @@ KERNEL_SOURCES = {      # bench span name -> the CUDA sources its dominant kerne
     'lstm_fwd': ('lstm4.cu', 'common.cuh', 'sm100_ptx.cuh'),
     'frontend': ('frontend.cu', 'common.cuh'),
     'gemm_proj_fwd': ('gemm_sm100.cu', 'common.cuh', 'sm100_ptx.cuh'),
+    'gemm_dw': ('gemm_sm100.cu', 'common.cuh', 'sm100_ptx.cuh'),
+    'gemm_dx': ('gemm_sm100.cu', 'common.cuh', 'sm100_ptx.cuh'),
 }
 
 
@@ -387,10 +389,23 @@ def run_extras(args, pg, dev, rank, world, pk):
     sweep = {}
     for b in (8, 32, 128, 512):
         wl = Workload(args.model, b, 48000, pg, dev, rank, world)
-        ms, _, _ = wl.run_resident(6, 3, profile=False)
+        ms, launches, _ = wl.run_resident(6, 3, profile=False)
+        sweep[str(b)] = {'value': b * world * 6 / (ms * 1e-3), 'ms_per_step': ms / 6, 'gpu_launches_per_step': launches / 6}
+        if pg is None:
+            # the same step replayed from ONE CUDA graph (models.capture_train_step): what the launch path costs at
+            # the reference's own batch sizes
+            step, res = wl.model.capture_train_step(), wl.res
+
+            def graphed():
+                step(sequence_lengths=res['seq_len'], target_sources=res['wav'], masks=res['mask'],
+                     video_features=wl.video_of(res) if wl.inp != 'a' else None)
+            for _ in range(3):
+                graphed()
+            msg, _, _ = wl.timed(graphed, 6)
+            sweep[str(b)].update(value_cuda_graph=b * world * 6 / (msg * 1e-3), ms_per_step_cuda_graph=msg / 6)
         wl.close()
-        sweep[str(b)] = {'value': b * world * 6 / (ms * 1e-3), 'ms_per_step': ms / 6}
-    out['batch_sweep'] = {'workload': 'configs[1] at other per-GPU batch sizes (B <= 224: mma.sync recurrence kernels)', 'unit': UNIT,
+    out['batch_sweep'] = {'workload': 'configs[1] at other per-GPU batch sizes (B <= 224: mma.sync recurrence kernels); '
+                                      '*_cuda_graph: the whole step replayed from one captured graph', 'unit': UNIT,
                           'per_gpu_batch': sweep}
     return out
 
@@ -487,7 +502,7 @@ def main():
             if v['flops']:
                 r['tensor_tflops'] = v['flops'] / sec / 1e12
             if name in ('lstm_bwd', 'lstm_fwd'):
-                r['note'] = ('the launch time of this kernel is independent of the number of clusters (1.55-1.60 ms at 4 and at 32): '
+                r['note'] = ('the launch time of this kernel is independent of the number of clusters (the same at 4 and at 32): '
                              'it sits on its per-cluster dependent chain, not on the HBM roofline; frac is reported against HBM '
                              'because its DRAM traffic equals the algorithmic bytes (DESIGN.md section 4)')
             return r
@@ -512,6 +527,8 @@ def main():
         'gpu_launches': launches,
         'clocks': clocks,
         'roofline': roof(dominant) if dominant else None,
+        'roofline_lstm_bwd': roof('lstm_bwd'),
+        'roofline_lstm_fwd': roof('lstm_fwd'),
         'roofline_frontend': roof('frontend'),
         'roofline_gemm_proj': roof('gemm_proj_fwd'),
         # whole step against the tensor roofline: 6.62 GFLOP per AV-SI utterance
