@@ -53,6 +53,35 @@ struct Lstm4BwdSmem {
   uint32_t tmem_slot;
 };
 
+// packed fp32x2 arithmetic (sm_100: one issue slot for two lanes)
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 pk2(float lo, float hi) {
+  f2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(f2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f2 add2(f2 a, f2 b) {
+  f2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f2 sub2(f2 a, f2 b) {
+  f2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+  f2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+  f2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
 // phase timers (cycles summed over steps) of CTA 0: control thread [0,12), compute thread 0 [12,24); debug only
 __device__ unsigned long long g_b4_timing[24];
 #define B4_TICK(i)                                         \
@@ -328,32 +357,38 @@ lstm4_bwd_kernel(const __grid_constant__ CUtensorMap tmG, uint16_t* __restrict__
           }
         }
         // ---- cell backward -------------------------------------------------------------------------------------
+        // two units at a time in packed fp32x2 (FADD2 / FMUL2 / FFMA2: half the issue slots of the scalar form -- the cell
+        // arithmetic is 40 % of this kernel's issue slots); unit pair k = units 2k, 2k+1 = the four words of g4[k]
         uint4 pk[4];
         uint32_t cnew[8], dnew[8];
         const uint32_t dyw[4] = {dyv.x, dyv.y, dyv.z, dyv.w};
+        const f2 one = pk2(1.f, 1.f);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const uint4 gv = g4[i >> 1];
-          const float2 ig = unpack_half2((i & 1) ? gv.z : gv.x), fo = unpack_half2((i & 1) ? gv.w : gv.y);
-          const float gi = ig.x, gg = ig.y, gf = fo.x, go = fo.y;
-          const float2 dy2 = unpack_half2(dyw[i >> 1]);
-          const float dh = ((i & 1) ? dy2.y : dy2.x) + dhrec[i];
-          const float tc = tanhf_fast(c_cur[i]);
-          const float d_o = dh * tc * go * (1.f - go);
-          const float dc = dc_st[i] + dh * go * (1.f - tc * tc);
-          const float d_i = dc * gg * gi * (1.f - gi);
-          const float d_g = dc * gi * (1.f - gg * gg);
-          const float d_f = dc * cprev[i] * gf * (1.f - gf);
-          dnew[i] = __float_as_uint(dc * gf);
-          cnew[i] = __float_as_uint(cprev[i]);
-          const uint32_t p0 = pack_half2(d_i, d_g), p1 = pack_half2(d_f, d_o);
-          if (i & 1) {
-            pk[i >> 1].z = p0;
-            pk[i >> 1].w = p1;
-          } else {
-            pk[i >> 1].x = p0;
-            pk[i >> 1].y = p1;
-          }
+        for (int k = 0; k < 4; ++k) {
+          const uint4 gv = g4[k];
+          const float2 ig0 = unpack_half2(gv.x), fo0 = unpack_half2(gv.y), ig1 = unpack_half2(gv.z), fo1 = unpack_half2(gv.w);
+          const f2 gi = pk2(ig0.x, ig1.x), gg = pk2(ig0.y, ig1.y), gf = pk2(fo0.x, fo1.x), go = pk2(fo0.y, fo1.y);
+          const float2 dy2 = unpack_half2(dyw[k]);
+          const f2 dh = add2(pk2(dy2.x, dy2.y), pk2(dhrec[2 * k], dhrec[2 * k + 1]));
+          const f2 tc = pk2(tanhf_fast(c_cur[2 * k]), tanhf_fast(c_cur[2 * k + 1]));
+          const f2 cp = pk2(cprev[2 * k], cprev[2 * k + 1]);
+          const f2 d_o = mul2(mul2(dh, tc), mul2(go, sub2(one, go)));
+          const f2 dc = fma2(mul2(dh, go), sub2(one, mul2(tc, tc)), pk2(dc_st[2 * k], dc_st[2 * k + 1]));
+          const f2 d_i = mul2(mul2(dc, gg), mul2(gi, sub2(one, gi)));
+          const f2 d_g = mul2(mul2(dc, gi), sub2(one, mul2(gg, gg)));
+          const f2 d_f = mul2(mul2(dc, cp), mul2(gf, sub2(one, gf)));
+          const f2 dn = mul2(dc, gf);
+          float a0, a1, b0, b1, c0, c1, e0, e1, n0, n1;
+          upk2(d_i, a0, a1);
+          upk2(d_g, b0, b1);
+          upk2(d_f, c0, c1);
+          upk2(d_o, e0, e1);
+          upk2(dn, n0, n1);
+          dnew[2 * k] = __float_as_uint(n0);
+          dnew[2 * k + 1] = __float_as_uint(n1);
+          cnew[2 * k] = __float_as_uint(cprev[2 * k]);
+          cnew[2 * k + 1] = __float_as_uint(cprev[2 * k + 1]);
+          pk[k] = make_uint4(pack_half2(a0, b0), pack_half2(c0, e0), pack_half2(a1, b1), pack_half2(c1, e1));
         }
         if (h == 0) load_inputs(1, g4, cprev, dyv);   // second half's inputs: in flight during the A-half hand-over
         if (has_prev) {                               // park c_{t_prev} and dc for the next step
