@@ -687,6 +687,52 @@ def test_lstm_recurrence_fwd_bwd(T, B):
     assert np.all(dG[:, :, :, H:] == 0)
 
 
+@pytest.mark.parametrize('T,B', [(33, 256), (250, 128)])
+def test_tcgen05_recurrence_data_paths_are_bit_identical(T, B):
+    """The asynchronous data paths of the tcgen05 recurrence kernels -- proxy fence on the consumer side, bulk L2 prefetch
+    by the control thread, BPTT dG through TMA tensor stores out of the A tile -- move the same bits as the round-1
+    forms they replaced (per-thread fences, prefetches and STG.128), which stay selectable: every output tensor of a
+    forward + BPTT launch is identical with the switches on and off (a hand-shake or proxy-ordering bug would show here)."""
+    from avsi_b200 import _lib
+    lib = _lib.load()
+    d = dev()
+    gen = torch.Generator(device='cpu').manual_seed(T + B)
+    Mp = -(-T * B // 32) * 32
+    g0 = torch.randn(Mp, 2048, generator=gen).half().to(d)
+    whh = (torch.randn(2048, 256, generator=gen) * 0.05).half().to(d)
+    whhT = whh.t().contiguous()
+    bias = torch.zeros(2048, device=d)
+    dy = torch.randn(Mp, 512, generator=gen).half().to(d)
+    scratch = torch.empty(int(lib.avsi_lstm_bwd_scratch_bytes(B)) // 4 + 4, device=d)
+    outs = []
+    try:
+        for env in (dict(), dict(AVSI_L4_CFENCE=0, AVSI_B4_CFENCE=0), dict(AVSI_L4_BPF=0, AVSI_B4_BPF=0, AVSI_B4_STMA=0),
+                    dict(AVSI_B4_STMA=0)):
+            _lib.set_env(AVSI_LSTM_FWD='l4', AVSI_LSTM_BWD='l4', AVSI_L4_CFENCE=None, AVSI_B4_CFENCE=None, AVSI_L4_BPF=None,
+                         AVSI_B4_BPF=None, AVSI_B4_STMA=None)
+            _lib.set_env(**env)
+            gates = g0.clone()
+            y = torch.zeros(T * B, 512, dtype=torch.float16, device=d)
+            cst = torch.zeros(Mp, 512, device=d)
+            dbias = torch.zeros(2048, device=d)
+            _lib.check(lib.avsi_lstm_fwd(_lib.ptr(gates), _lib.ptr(whh), _lib.ptr(bias), _lib.ptr(y), _lib.ptr(cst), T, B, 0,
+                                         _lib.stream_ptr()), 'lstm_fwd')
+            sync()
+            act = gates.clone()
+            _lib.check(lib.avsi_lstm_bwd(_lib.ptr(gates), _lib.ptr(whhT), _lib.ptr(cst), _lib.ptr(dy), _lib.ptr(dbias),
+                                         _lib.ptr(scratch), T, B, _lib.stream_ptr()), 'lstm_bwd')
+            sync()
+            outs.append((act, y, cst, gates, dbias))
+    finally:
+        _lib.set_env(AVSI_LSTM_FWD=None, AVSI_LSTM_BWD=None, AVSI_L4_CFENCE=None, AVSI_B4_CFENCE=None, AVSI_L4_BPF=None,
+                     AVSI_B4_BPF=None, AVSI_B4_STMA=None)
+    assert torch.isfinite(outs[0][3].float()).all() and float(outs[0][3].float().abs().max()) > 0
+    for o in outs[1:]:
+        for a, b in zip(outs[0][:4], o[:4]):
+            assert torch.equal(a, b)
+        assert torch.allclose(outs[0][4], o[4], rtol=1e-3, atol=1e-2)      # bias gradient: fp32 atomics across clusters
+
+
 # ------------------------------------------------------------------------------------------ feature statistics (a15)
 @pytest.mark.parametrize('ftype,apply_mask', [('spec', False), ('spec', True), ('fbanks', False)])
 def test_compute_mean_std_features_matches_oracle(tmp_path, ftype, apply_mask):
