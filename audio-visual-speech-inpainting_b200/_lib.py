@@ -85,6 +85,10 @@ SIGNATURES = {
     'avsi_lstm_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     'avsi_masked_l1': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    'avsi_head_l1': (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int,
+                             c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p,
+                             c_void_p, c_int, c_void_p]),
+    'avsi_head_l1_workspace_bytes': (c_int, []),
     'avsi_mtl_scales': (c_int, [c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p]),
     'avsi_colsum_f16': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'avsi_ctc_workspace_bytes': (c_int64, [c_int, c_int, c_int]),

@@ -179,8 +179,9 @@ class BLSTMEngine(object):
         return ws
 
     # ---- forward ------------------------------------------------------------------------------
-    def forward(self, ws, dropout=None):
+    def forward(self, ws, dropout=None, head=True):
         """ws['x0'] (time-major fp16 network input) -> ws['logits'] [T*B, nop] fp32.
+        head=False stops ahead of the head GEMM and returns its input (x, interleaved flag): head_l1() takes it from there.
 
         dropout = (rate, seed, offset): tf.nn.dropout on the last layer's outputs ahead of the head (models.py:117);
         the mask is a function of (seed, offset) only, backward() regenerates it."""
@@ -211,9 +212,26 @@ class BLSTMEngine(object):
                                                 int(dropout[2]), None, 3 if yil else 0, _lib.stream_ptr()), 'avsi_dropout_f16')
             x = ws['Ydrop']
             ws['drop'] = (float(dropout[0]), int(dropout[1]), int(dropout[2]))
+        if not head:
+            return x, yil
         gemm(_p(x), NY, _p(self.half['head']), NY, _p(ws['logits']), L.nop, _p(self.view(self.theta, 'head_b')),
              M, L.n_out, NY, 0, 1, tag='gemm_head_fwd', layout=A_IL if yil else 0)
         return ws['logits']
+
+    def head_l1(self, ws, x, yil, target, mask, seq_len, F, mode, grad_scale_dev, sums, logits_from_col):
+        """Head GEMM with the masked-L1 loss and its gradient in the epilogue (avsi_head_l1): writes ws['dlogits'][:, :F],
+        adds the six loss sums to `sums`, and writes ws['logits'] only from column `logits_from_col` on (what a CTC head
+        still reads).  The training step's replacement for forward(head=True) + avsi_masked_l1."""
+        lib = _lib.load()
+        L = self.layout
+        T, B, M = ws['T'], ws['B'], ws['M']
+        if 'l1_partial' not in ws:
+            ws['l1_partial'] = torch.zeros(int(lib.avsi_head_l1_workspace_bytes()) // 8, dtype=torch.float64, device=self.device)
+        with _lib.span('head_l1', nbytes=M * (NY * 2 + 2 * F * 4 + L.nop * 2), flops=2 * M * L.n_out * NY):
+            _lib.check(lib.avsi_head_l1(_p(x), NY, 1 if yil else 0, _p(self.half['head']), NY, _p(self.view(self.theta, 'head_b')),
+                                        M, L.n_out, NY, _p(ws['logits']), L.nop, int(logits_from_col), _p(target), _p(mask),
+                                        _p(seq_len), B, T, F, int(mode), 1.0, grad_scale_dev, _p(sums), _p(ws['l1_partial']),
+                                        _p(ws['dlogits']), L.nop, _lib.stream_ptr()), 'avsi_head_l1')
 
     # ---- backward -----------------------------------------------------------------------------
     def backward(self, ws, zero_grad=True):

@@ -37,13 +37,47 @@ constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_THREADS = 192;
 
+// Masked-L1 loss + gradient fused into the epilogue of the head GEMM (avsi_head_l1): the arguments of avsi_masked_l1
+// (loss.cu).  The fp32 logits then never reach HBM (655 MB written and read back per step at B = 2048), except the
+// columns >= logits_from_col that a second loss (CTC) still reads.
+struct L1Fuse {
+  const float* target;          // [B, T, F] f32
+  const float* mask;            // [B, T, F] f32
+  const int32_t* seq_len;       // [B]
+  const float* grad_scale_dev;  // optional device factor of the gradient
+  double* partial;              // [L1_PARTS][8] partial sums (zeroed by the launcher, reduced by l1_partials_kernel)
+  uint16_t* dlogits;            // [M, ldd] f16, columns < F written
+  int B, T, F, mode, ldd, logits_from_col;
+  float grad_scale;
+};
+constexpr int L1_PARTS = 64;
+
 struct GemmParams {
   void* C;
   const float* bias;
   int ldc, M, N, K;
   int trans, out_mode, split_k;
   int a_il, c_il, b_il;
+  int fuse_l1;
+  L1Fuse l1;
 };
+
+// one element of the masked-L1 loss (same arithmetic as masked_l1_kernel, loss.cu): x = logit, y = target, m = mask,
+// sm = 1 inside the utterance; returns the fp16 gradient word and adds to the five running sums
+__device__ __forceinline__ uint16_t l1_element(float x, float y, float m, float sm, int mode, float grad_scale, float (&acc)[5]) {
+  float pred = (mode == 0) ? x : (y * m + x * (1.f - m));
+  pred *= sm;
+  const float d = y - pred;
+  const float ad = fabsf(d);
+  acc[0] += ad * (1.f - m);
+  acc[1] += (1.f - m);
+  acc[2] += ad * m;
+  acc[3] += m;
+  acc[4] += ad;
+  const float sg = (d > 0.f) ? -1.f : ((d < 0.f) ? 1.f : 0.f);
+  const float w = (mode == 0) ? sm : sm * (1.f - m);
+  return __half_as_ushort(__float2half_rn(grad_scale * sg * w));
+}
 
 template <int BN, int STAGES>
 struct GemmSmem {
@@ -225,6 +259,8 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const bool via_smem = (p.out_mode == 1) && (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
                           (S::BAR_OFFSET >= 4 * 32 * 36 * 4);
     float* tile = reinterpret_cast<float*>(smem_dyn + (smem_base - smem_u32(smem_dyn))) + (warp - 2) * (32 * 36);
+    float l1acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    const float l1gs = p.fuse_l1 ? p.l1.grad_scale * (p.l1.grad_scale_dev ? *p.l1.grad_scale_dev : 1.f) : 0.f;
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t r[32];
@@ -245,6 +281,56 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (p.bias)                                  // (the bias is a view into the flat parameter buffer: no alignment promise)
           bv = make_float4(__ldg(p.bias + n0 + cl), __ldg(p.bias + n0 + cl + 1), __ldg(p.bias + n0 + cl + 2),
                            __ldg(p.bias + n0 + cl + 3));
+        if (p.fuse_l1) {
+          // masked-L1 on the fly: this lane holds 4 consecutive logits of 8 rows; target / mask rows are [b, t]-major
+          const L1Fuse& q = p.l1;
+          const int k0 = n0 + cl;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            float yv[4][4], mv[4][4], smv[4];
+            int grows[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {              // the loads of four rows are in flight together
+              const int rl = 4 * (4 * half + i) + (lane >> 3);
+              const int grow = m_blk * GEMM_BM + quarter * 32 + rl;
+              grows[i] = grow;
+              const int gr = grow < p.M ? grow : p.M - 1;
+              const int t = gr / q.B, b = gr - t * q.B;
+              smv[i] = (t < __ldg(q.seq_len + b)) ? 1.f : 0.f;
+              const long long base = ((long long)b * q.T + t) * q.F + k0;
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const bool ok = k0 + e < q.F;
+                yv[i][e] = ok ? __ldg(q.target + base + e) : 0.f;
+                mv[i][e] = ok ? __ldg(q.mask + base + e) : 0.f;
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int rl = 4 * (4 * half + i) + (lane >> 3);
+              const int grow = grows[i];
+              float4 v = *reinterpret_cast<const float4*>(tile + rl * 36 + cl);
+              v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+              if (grow >= p.M) continue;
+              const float xs[4] = {v.x, v.y, v.z, v.w};
+              uint16_t g[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) g[e] = (k0 + e < q.F) ? l1_element(xs[e], yv[i][e], mv[i][e], smv[i], q.mode, l1gs, l1acc) : (uint16_t)0;
+              uint16_t* dl = q.dlogits + (long long)grow * q.ldd + k0;
+              if (k0 + 4 <= q.F) {
+                *reinterpret_cast<uint2*>(dl) = make_uint2((uint32_t)g[0] | ((uint32_t)g[1] << 16), (uint32_t)g[2] | ((uint32_t)g[3] << 16));
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  if (k0 + e < q.F) dl[e] = g[e];
+              }
+              if (k0 + 4 > q.logits_from_col)          // columns another loss still reads as logits
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + (long long)grow * p.ldc + k0) = v;
+            }
+          }
+          __syncwarp();
+          continue;
+        }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int rl = 4 * i + (lane >> 3);        // row of the block
@@ -257,7 +343,31 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         continue;
       }
       if (!row_ok) continue;
+      if (p.fuse_l1) {
+        // partial column block (the last columns of the head): this lane owns a row
+        const L1Fuse& q = p.l1;
+        const int t = row / q.B, b = row - t * q.B;
+        const float sm = (t < __ldg(q.seq_len + b)) ? 1.f : 0.f;
+        const long long base = ((long long)b * q.T + t) * q.F;
+        for (int jj = 0; jj < 32 && n0 + jj < p.N; ++jj) {
+          const int k = n0 + jj;
+          const float x = __uint_as_float(r[jj]) + (p.bias ? __ldg(p.bias + k) : 0.f);
+          if (k < q.F)
+            q.dlogits[(long long)row * q.ldd + k] = l1_element(x, __ldg(q.target + base + k), __ldg(q.mask + base + k), sm, q.mode, l1gs, l1acc);
+          if (k >= q.logits_from_col) reinterpret_cast<float*>(p.C)[(long long)row * p.ldc + k] = x;
+        }
+        continue;
+      }
       epilogue_store(p, row, n0, full, r);
+    }
+    if (p.fuse_l1) {
+      // five sums: warp reduction in double, one atomic per warp and sum into one of L1_PARTS partial rows
+      double* dst = p.l1.partial + (size_t)(blockIdx.x % L1_PARTS) * 8;
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        const double v = warp_sum_d((double)l1acc[i]);
+        if (lane == 0 && v != 0.0) atomicAdd(dst + i, v);
+      }
     }
   }
   tc_fence_before();
@@ -266,6 +376,17 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     tc_fence_after();
     tmem_dealloc(tmem_base, BN);
   }
+}
+
+// folds the partial rows of a fused head + masked-L1 launch into sums[0..5] (sums[5] = number of loss elements)
+__global__ void l1_partials_kernel(const double* __restrict__ partial, double* __restrict__ sums, double count) {
+  const int i = threadIdx.x;
+  if (i < 5) {
+    double v = 0.0;
+    for (int pth = 0; pth < L1_PARTS; ++pth) v += partial[pth * 8 + i];
+    sums[i] += v;
+  }
+  if (i == 5) sums[5] += count;
 }
 
 // ---------------------------------------------------------------- persistent CTA-pair kernel
@@ -925,3 +1046,39 @@ extern "C" int avsi_gemm_f16(const uint16_t* A, int lda, const uint16_t* B, int 
   if (bn == 128) return launch_gemm<128, 3>(ta, tb, p, st);
   return launch_gemm<64, 4>(ta, tb, p, st);
 }
+
+// Head GEMM with the masked-L1 loss and its gradient in the epilogue (training step): logits = A[M,K] . W[N,K]^T + bias are
+// consumed where they are produced -- prediction, |target - prediction| sums and the fp16 gradient of avsi_masked_l1 -- and
+// only the columns >= logits_from_col (the phone-recognition head of the MTL models, read by avsi_ctc_loss) are written.
+extern "C" int avsi_head_l1(const uint16_t* A, int lda, int a_layout, const uint16_t* W, int ldw, const float* bias, int M, int N,
+                            int K, float* logits, int ldc, int logits_from_col, const float* target, const float* mask,
+                            const int32_t* seq_len, int B, int T, int F, int mode, float grad_scale,
+                            const float* grad_scale_dev, double* sums, double* partial_ws, uint16_t* dlogits, int ldd,
+                            void* stream) {
+  using namespace avsi;
+  AVSI_REQUIRE(A && W && logits && target && mask && seq_len && sums && partial_ws && dlogits, "null pointer");
+  AVSI_REQUIRE(M > 0 && N > 0 && K > 0 && B > 0 && T > 0 && (long long)B * T == M, "M = B * T");
+  AVSI_REQUIRE(F > 0 && F <= N && ldd >= F && ldd % 4 == 0, "F <= N, ldd >= F, ldd % 4 == 0");
+  AVSI_REQUIRE(mode == 0 || mode == 1, "mode");
+  AVSI_REQUIRE(lda % 8 == 0 && ldw % 8 == 0 && ((uintptr_t)A % 16 == 0) && ((uintptr_t)W % 16 == 0), "operand alignment");
+  AVSI_REQUIRE(ldc >= N && ldc % 4 == 0 && ((uintptr_t)logits % 16 == 0) && ((uintptr_t)dlogits % 8 == 0), "output alignment");
+  AVSI_REQUIRE(a_layout == 0 || a_layout == 1, "a_layout");
+  cudaStream_t st = (cudaStream_t)stream;
+  GemmParams p{logits, bias, ldc, M, N, K, 0, 1, 1, a_layout, 0, 0};
+  p.fuse_l1 = 1;
+  p.l1 = L1Fuse{target, mask, seq_len, grad_scale_dev, partial_ws, dlogits, B, T, F, mode, ldd, logits_from_col, grad_scale};
+  AVSI_CUDA(cudaMemsetAsync(partial_ws, 0, sizeof(double) * L1_PARTS * 8, st));
+  CUtensorMap ta, tb;
+  int rc = a_layout ? get_tmap_il(A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, GEMM_BM / 32, GEMM_BK / 8, &ta)
+                    : get_tmap(A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, GEMM_BK, GEMM_BM, &ta);
+  if (rc) return rc;
+  rc = get_tmap(W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, GEMM_BK, 128, &tb);
+  if (rc) return rc;
+  rc = launch_gemm<128, 3>(ta, tb, p, st);
+  if (rc) return rc;
+  l1_partials_kernel<<<1, 32, 0, st>>>(partial_ws, sums, (double)M * (double)F);
+  AVSI_LAUNCH_CHECK();
+  return AVSI_OK;
+}
+
+extern "C" int avsi_head_l1_workspace_bytes(void) { return (int)(sizeof(double) * avsi::L1_PARTS * 8); }

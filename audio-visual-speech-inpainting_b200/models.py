@@ -10,6 +10,7 @@ cached until the next ``feed``; ``train_op()`` runs forward + backward + optimis
 All arithmetic runs in the sm_100a kernels of libavsi_b200.so; there is no autograd and no
 CPU fallback.
 """
+import os
 import sys
 
 import numpy as np
@@ -292,7 +293,14 @@ class StackedBLSTMModel(object):
         fr = self._front()
         ws, B, T = fr['ws'], fr['B'], fr['T']
         F = self.audio_feat_dim
-        logits = self._logits()
+        # AVSI_FUSE_HEAD_L1=1 (experiment, off): in the training step the inpainting head and the masked-L1 loss run as ONE
+        # kernel (avsi_head_l1) -- the fp32 logits are consumed in the GEMM's epilogue instead of being written and read back
+        # (1.3 GB per step at B = 2048); only the phone head's columns are kept for the CTC kernel.  Measured SLOWER than the
+        # two launches (1.04 vs 0.35 + 0.40 ms): the one-tile-per-CTA kernel has 8 epilogue warps per SM to hide the loss's
+        # loads behind, the stand-alone loss kernel 64 (profiles/README.md).  Parity-tested all the same.
+        fused = (want_grad and not want_pred and 'logits' not in self._cache and 'dlogits' in ws
+                 and os.environ.get('AVSI_FUSE_HEAD_L1', '0') == '1')
+        logits = ws['logits'] if fused else self._logits()
         masks, seq = self._need('masks', 'sequence_lengths')
         L = self.engine.layout
         self._sums.zero_()
@@ -316,11 +324,17 @@ class StackedBLSTMModel(object):
             _lib.check(lib.avsi_mtl_scales(_p(hole), B * world, float(self.ctc_loss_weight), _p(scales),
                                            _p(self.engine.guard), _lib.stream_ptr()), 'avsi_mtl_scales')
         dl = ws['dlogits'] if (want_grad and 'dlogits' in ws) else None
-        with _lib.span('masked_l1'):
-            _lib.check(lib.avsi_masked_l1(_p(logits), L.nop, _p(fr['target_spec_norm']), _p(masks), _p(seq), B, T, F,
-                                          1 if self.MTL else 0, 1.0,
-                                          _p(scales) if self.MTL else self.engine.guard_scale_ptr, _p(self._sums),
-                                          _p(pred), _p(dl), L.nop, _lib.stream_ptr()), 'avsi_masked_l1')
+        if fused:
+            x, yil = self.engine.forward(ws, dropout=self._dropout(), head=False)
+            self.engine.head_l1(ws, x, yil, fr['target_spec_norm'], masks, seq, F, 1 if self.MTL else 0,
+                                _p(scales) if self.MTL else self.engine.guard_scale_ptr, self._sums,
+                                logits_from_col=(F // 4) * 4 if self.MTL else 1 << 30)
+        else:
+            with _lib.span('masked_l1'):
+                _lib.check(lib.avsi_masked_l1(_p(logits), L.nop, _p(fr['target_spec_norm']), _p(masks), _p(seq), B, T, F,
+                                              1 if self.MTL else 0, 1.0,
+                                              _p(scales) if self.MTL else self.engine.guard_scale_ptr, _p(self._sums),
+                                              _p(pred), _p(dl), L.nop, _lib.stream_ptr()), 'avsi_masked_l1')
         if self.MTL:
             labels, lab_len = self._need('labels', 'labels_lengths')
             Lmax = labels.shape[1]

@@ -238,6 +238,16 @@ int avsi_masked_l1(const float* logits, int ldl, const float* target, const floa
                    const int32_t* seq_len, int B, int T, int F, int mode, float grad_scale,
                    const float* grad_scale_dev, double* sums, float* prediction, uint16_t* dlogits,
                    int ldd, void* stream);
+/* The training step's fusion of the inpainting head with that loss: logits = A[M, K] . W[N, K]^T + bias (the tf.matmul head of
+ * models.py:117-123 / 1902-1912) are consumed in the GEMM's epilogue by the arithmetic of avsi_masked_l1 -- the six sums are
+ * ADDED to sums[0..5], dlogits[:, :F] is written -- and never stored, except the columns >= logits_from_col (the phone head
+ * read by avsi_ctc_loss; pass N or more for none).  M = B * T time-major rows; a_layout 1 = A stored interleaved;
+ * partial_ws: avsi_head_l1_workspace_bytes() bytes of device scratch. */
+int avsi_head_l1(const uint16_t* A, int lda, int a_layout, const uint16_t* W, int ldw, const float* bias, int M, int N, int K,
+                 float* logits, int ldc, int logits_from_col, const float* target, const float* mask, const int32_t* seq_len,
+                 int B, int T, int F, int mode, float grad_scale, const float* grad_scale_dev, double* sums,
+                 double* partial_ws, uint16_t* dlogits, int ldd, void* stream);
+int avsi_head_l1_workspace_bytes(void);
 /* grad_scale_dev (here and below): optional device scalar multiplied into grad_scale, so that
  * data-dependent normalisers (sum(1-m) of the MTL loss) never need a host round trip. */
 

@@ -278,6 +278,26 @@ def test_captured_train_step_equals_eager_steps(model_name, B):
         graphed.capture_train_step()
 
 
+@pytest.mark.parametrize('model_name,B', [('av-blstm', 5), ('av-blstm-ssnn-ctc', 3), ('a-blstm', 130)])
+def test_fused_head_l1_equals_two_launches(model_name, B, monkeypatch):
+    """avsi_head_l1 (AVSI_FUSE_HEAD_L1=1: head GEMM with the masked-L1 loss in its epilogue) against the default head GEMM +
+    avsi_masked_l1: the six loss sums, the CTC loss of the MTL model (it reads the phone columns the fused kernel still
+    writes) and the complete parameter gradient."""
+    res = {}
+    for fuse in ('0', '1'):
+        monkeypatch.setenv('AVSI_FUSE_HEAD_L1', fuse)
+        model, batch, canon, inp = _build(model_name, B, 4800, seed=11)
+        model.compute_gradients()
+        sums = model._loss_pass(False, want_pred=False)['sums'].cpu().numpy().copy()
+        grads = model.canonical_gradients()
+        res[fuse] = (sums, grads, float(model.loss))
+    assert np.allclose(res['0'][0][:6], res['1'][0][:6], rtol=1e-6)
+    assert abs(res['0'][2] - res['1'][2]) <= 1e-6 * abs(res['0'][2])
+    ga = np.concatenate([res['0'][1][k].ravel() for k in sorted(res['0'][1])])
+    gb = np.concatenate([res['1'][1][k].ravel() for k in sorted(res['0'][1])])
+    assert rel_l2(gb, ga) < 1e-5
+
+
 def test_variables_roundtrip_and_inference_mode():
     from avsi_b200 import av_sync, models, synth
     model, batch, canon, inp = _build('av-blstm', 2, 4800, seed=7)
