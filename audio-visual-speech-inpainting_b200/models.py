@@ -24,6 +24,17 @@ from .layout import init_canonical
 _p = _lib.ptr
 
 
+def edit_distance(hyp, ref):
+    """Levenshtein distance of two label sequences (tf.edit_distance, normalize=False, on dense sequences)."""
+    prev = list(range(len(ref) + 1))
+    for i, h in enumerate(hyp, 1):
+        cur = [i] + [0] * len(ref)
+        for jx, r in enumerate(ref, 1):
+            cur[jx] = min(prev[jx] + 1, cur[jx - 1] + 1, prev[jx - 1] + (h != r))
+        prev = cur
+    return prev[-1]
+
+
 class StackedBLSTMModel(object):
     """
     Speech inpainting BLSTM model
@@ -626,13 +637,7 @@ class StackedBLSTMSSNNCTCLossModel(StackedBLSTMModel):
         for b in range(len(dec)):
             hyp = [int(x) for x in dec[b] if x >= 0]
             ref = [int(x) for x in labels[b, :int(lens[b])]]
-            prev = list(range(len(ref) + 1))
-            for i, h in enumerate(hyp, 1):
-                cur = [i] + [0] * len(ref)
-                for jx, r in enumerate(ref, 1):
-                    cur[jx] = min(prev[jx] + 1, cur[jx - 1] + 1, prev[jx - 1] + (h != r))
-                prev = cur
-            out[b] = prev[-1] / max(1, len(ref))
+            out[b] = edit_distance(hyp, ref) / max(1, len(ref))
         return out
 
     BEAM_WIDTH = 20                          # models.py:1627, :2027

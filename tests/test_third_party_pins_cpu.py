@@ -283,3 +283,27 @@ def test_resample_oracle_against_scipy_signal_resample():
     ref = signal.resample(wav, int(16000 * (len(wav) / 50000.0)))
     assert np.abs(ores.downsampling(wav, 50000, 16000) - ref).max() < 1e-8
     assert ores.downsampling(wav, 16000, 16000) is wav
+
+
+def test_delta_preemphasis_edit_distance_against_torchaudio():
+    """Three more independent implementations that ship in the image (torchaudio): `delta` (audio_processing.py:84-93: SYMMETRIC
+    padding one frame at a time = edge replication, sum_i i (x[t+i] - x[t-i]) / (2 sum i^2)) = compute_deltas(win_length
+    2N + 1, mode 'replicate'); `preemphasis` (:19-22); the Levenshtein distance behind `per` (tf.edit_distance,
+    models.py:1718)."""
+    torchaudio = pytest.importorskip('torchaudio')
+    import torch
+    from avsi_b200 import models
+    from oracle import stft as ostft
+    rng = np.random.default_rng(29)
+    x = rng.standard_normal((3, 41, 13))
+    for N in (1, 2, 3):
+        ref = torchaudio.functional.compute_deltas(torch.from_numpy(x).permute(0, 2, 1), win_length=2 * N + 1,
+                                                   mode='replicate').permute(0, 2, 1).numpy()
+        assert np.abs(ostft.delta(x, N) - ref).max() < 1e-12
+    wav = rng.standard_normal((2, 500))
+    ref = torchaudio.functional.preemphasis(torch.from_numpy(wav), coeff=0.95).numpy()
+    assert np.abs(ostft.preemphasis(wav, 0.95) - ref).max() < 1e-12
+    for _ in range(50):
+        a = rng.integers(0, 5, rng.integers(0, 12)).tolist()
+        b = rng.integers(0, 5, rng.integers(0, 12)).tolist()
+        assert models.edit_distance(a, b) == torchaudio.functional.edit_distance(a, b)
