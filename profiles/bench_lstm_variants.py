@@ -48,6 +48,7 @@ for B in BS:
         # BPTT reduce-scatter by st.async straight out of TMEM (no staging / control-thread hop); second chain as two N = 128
         # halves (AVSI_B4_NSPLIT, gone from the code: 1.382 vs 1.323 ms) -- logs r02n_*
         variants = [('default', dict())]
+    # (r02u: the forward TMA store again with the first pass's store AHEAD of its pushes and the second BEHIND them: +7 %, log kept)
     else:   # current defaults against the round-1 forms that are still selectable
         on = dict(AVSI_L4_CFENCE=1, AVSI_B4_CFENCE=1, AVSI_L4_BPF=1, AVSI_B4_BPF=1, AVSI_B4_STMA=1)
         variants = [('default', on), ('writer-fence,stg,per-thread-prefetch', dict(on, AVSI_L4_CFENCE=0, AVSI_B4_CFENCE=0))]
