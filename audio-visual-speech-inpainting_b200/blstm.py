@@ -39,9 +39,10 @@ def ctypes_ptr(addr):
 A_IL, C_IL, B_IL = 1, 2, 4     # avsi_gemm_f16 layout bits: A operand / f16 output / B operand stored interleaved (include/avsi_b200.h)
 
 
-def gemm(A, lda, B, ldb, C, ldc, bias, M, N, K, trans, out_mode, split_k=1, tag='gemm', layout=0):
+def gemm(A, lda, B, ldb, C, ldc, bias, M, N, K, trans, out_mode, split_k=1, tag='gemm', layout=0, nbytes=0):
+    """nbytes: algorithmic operand bytes, given for the shapes that sit on the HBM roofline rather than the tensor one."""
     lib = _lib.load()
-    with _lib.span(tag, flops=2 * M * N * K):
+    with _lib.span(tag, nbytes=nbytes, flops=2 * M * N * K):
         _lib.check(lib.avsi_gemm_f16(A, lda, B, ldb, C, ldc, bias, M, N, K, trans, out_mode, split_k, layout,
                                      _lib.stream_ptr()), 'avsi_gemm_f16')
 
@@ -250,7 +251,7 @@ class BLSTMEngine(object):
         yil = ws['y_il']
         bil = B_IL if yil else 0
         gemm(_p(dl), L.nop, _p(ylast), NY, _p(self.view(g, 'head_w')), NY, None, L.n_out, NY, M, 1, 2,
-             pick_split_k(L.n_out, NY, M), tag='gemm_dw', layout=bil)
+             pick_split_k(L.n_out, NY, M), tag='gemm_dw_head', layout=bil)
         _lib.check(lib.avsi_colsum_f16(_p(dl), L.nop, M, 0, L.n_out, _p(self.view(g, 'head_b')), st()), 'avsi_colsum_f16')
         dY = ws['dY'][0]
         gemm(_p(dl), L.nop, _p(self.half['headT']), L.nop, _p(dY), NY, None, M, NY, L.nop, 0, 0, tag='gemm_dx', layout=C_IL)
@@ -269,21 +270,23 @@ class BLSTMEngine(object):
             x, ldx = (ws['x0'], L.k0p) if l == 0 else (ws['Y'][l - 1], NY)
             # dWih = dG^T . X
             gemm(_p(G), NG, _p(x), ldx, _p(self.view(g, 'wih%d' % l)), kp, None, NG, kp, M, 1, 2,
-                 pick_split_k(NG, kp, M), tag='gemm_dw', layout=A_IL | (bil if l > 0 else 0))
+                 pick_split_k(NG, kp, M), tag='gemm_dw_ih', layout=A_IL | (bil if l > 0 else 0))
             # dWhh[dir] = dG[dir]^T . h_prev  (fw: h_{t-1}, bw: h_{t+1}): row-shifted views of the zero-framed Y
             if T > 1:
                 gw = self.view(g, 'whh%d' % l)
                 sk = pick_split_k(GATES * HP, HP, M, 148)
                 yb = ws['Ybuf'][l].data_ptr()
-                gemm(G.data_ptr(), NG, yb, NY, _p(gw), HP, None, GATES * HP, HP, M, 1, 2, sk, tag='gemm_dw',
-                     layout=A_IL | bil)
+                # (HBM-bound: one direction's dG, 2048 B per row, and its half of Y, 512 B, are read once for 0.27 TFLOP)
+                hh_bytes = M * (GATES * HP * 2 + HP * 2)
+                gemm(G.data_ptr(), NG, yb, NY, _p(gw), HP, None, GATES * HP, HP, M, 1, 2, sk, tag='gemm_dw_hh',
+                     layout=A_IL | bil, nbytes=hh_bytes)
                 a_bw = G.data_ptr() + (GATES * HP // 8) * 512            # IL column offset: 512 B per 8-column chunk
                 if yil:     # row 2B of Ybuf = 2B/32 row blocks of NY/8 chunks of 512 B; column HP = HP/8 chunks further
                     b_bw = yb + ((2 * B // 32) * (NY // 8) + HP // 8) * 512
                 else:
                     b_bw = yb + (2 * B * NY + HP) * 2
                 gemm(a_bw, NG, b_bw, NY, gw.data_ptr() + GATES * HP * HP * 4, HP, None, GATES * HP, HP, M, 1, 2, sk,
-                     tag='gemm_dw', layout=A_IL | bil)
+                     tag='gemm_dw_hh', layout=A_IL | bil, nbytes=hh_bytes)
             if l > 0:
                 nxt = 1 - cur
                 gemm(_p(G), NG, _p(self.half['wihT%d' % l]), NG, _p(ws['dY'][nxt]), NY, None, M, NY, NG, 0, 0,

@@ -349,7 +349,9 @@ KERNEL_SOURCES = {      # bench span name -> the CUDA sources its dominant kerne
     'lstm_fwd': ('lstm4.cu', 'common.cuh', 'sm100_ptx.cuh'),
     'frontend': ('frontend.cu', 'common.cuh'),
     'gemm_proj_fwd': ('gemm_sm100.cu', 'common.cuh', 'sm100_ptx.cuh'),
-    'gemm_dw': ('gemm_sm100.cu', 'common.cuh', 'sm100_ptx.cuh'),
+    'gemm_dw_ih': ('gemm_sm100.cu', 'common.cuh', 'sm100_ptx.cuh'),
+    'gemm_dw_hh': ('gemm_sm100.cu', 'common.cuh', 'sm100_ptx.cuh'),
+    'gemm_dw_head': ('gemm_sm100.cu', 'common.cuh', 'sm100_ptx.cuh'),
     'gemm_dx': ('gemm_sm100.cu', 'common.cuh', 'sm100_ptx.cuh'),
 }
 
@@ -531,6 +533,9 @@ def main():
         'roofline_lstm_fwd': roof('lstm_fwd'),
         'roofline_frontend': roof('frontend'),
         'roofline_gemm_proj': roof('gemm_proj_fwd'),
+        'roofline_gemm_dw_ih': roof('gemm_dw_ih'),
+        'roofline_gemm_dw_hh': roof('gemm_dw_hh'),
+        'roofline_gemm_dx': roof('gemm_dx'),
         # whole step against the tensor roofline: 6.62 GFLOP per AV-SI utterance
         'step_frac_of_tensor_roofline': value / world * 6.62e9 * (T / 250.0) / (pk['bf16_tflops_sustained'] * 1e12),
         'kernels': kernels,

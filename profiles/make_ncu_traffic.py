@@ -51,13 +51,15 @@ def main():
     if os.path.exists(g('gemm_f16_2sm_kernel')):
         ls = launches(g('gemm_f16_2sm_kernel'))
         if len(ls) == 13:
-            dw = [0, 2, 3, 4, 6, 7, 8, 10, 11, 12]
-            dx = [1, 5, 9]
-            out['gemm_dw'] = int(sum(ls[i]['dram_bytes'] for i in dw) / len(dw))
-            out['gemm_dx'] = int(sum(ls[i]['dram_bytes'] for i in dx) / len(dx))
-            out['gemm_backward_launches'] = [{'i': i, 'span': 'gemm_dw' if i in dw else 'gemm_dx', 'dram_bytes': int(l['dram_bytes']),
-                                              'duration': l['duration']} for i, l in enumerate(ls)]
-            out['source_digests']['gemm_dw'] = out['source_digests']['gemm_dx'] = bench.kernel_source_digest('gemm_dw')
+            spans = {'gemm_dw_head': [0], 'gemm_dw_ih': [2, 6, 10], 'gemm_dw_hh': [3, 4, 7, 8, 11, 12], 'gemm_dx': [1, 5, 9]}
+            which = {}
+            for name, idx in spans.items():
+                out[name] = int(sum(ls[i]['dram_bytes'] for i in idx) / len(idx))
+                out['source_digests'][name] = bench.kernel_source_digest('gemm_dx')
+                for i in idx:
+                    which[i] = name
+            out['gemm_backward_launches'] = [{'i': i, 'span': which[i], 'dram_bytes': int(l['dram_bytes']), 'duration': l['duration']}
+                                             for i, l in enumerate(ls)]
     json.dump(out, open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json'), 'w'), indent=1)
     print(json.dumps({k: v for k, v in out.items() if k not in ('comment', 'gemm_backward_launches')}, indent=1))
 
