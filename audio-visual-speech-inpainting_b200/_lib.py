@@ -74,6 +74,7 @@ SIGNATURES = {
     'avsi_mfcc': (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p]),
     'avsi_resample_workspace_bytes': (c_int64, [c_int, c_int64, c_int64]),
     'avsi_resample_fft': (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
+    'avsi_select_c64': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     'avsi_delta_features': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'avsi_dropout_f16': (c_int, [c_void_p, c_int, c_void_p, c_int, c_int64, c_int, c_float, c_uint64, c_uint64, c_void_p,
                                  c_int, c_void_p]),

@@ -146,3 +146,24 @@ extern "C" int avsi_log_mel(const float* spec, const float* mel_w, int64_t rows,
   AVSI_LAUNCH_CHECK();
   return AVSI_OK;
 }
+
+// out[i] = keep[i] != 0 ? a[i] : b[i] over n complex64 values (b == NULL: zero): the phase source of one consistency
+// iteration of phase_reconstruction.refine_phase -- the known spectrum in the reliable bins, the re-analysed one in the holes
+namespace avsi {
+__global__ void __launch_bounds__(256)
+select_c64_kernel(const float2* __restrict__ a, const float2* __restrict__ b, const float* __restrict__ keep, long long n,
+                  float2* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = (keep[i] != 0.f) ? a[i] : (b ? b[i] : make_float2(0.f, 0.f));
+}
+}  // namespace avsi
+
+extern "C" int avsi_select_c64(const float* a_c64, const float* b_c64, const float* keep, int64_t n, float* out_c64, void* stream) {
+  using namespace avsi;
+  AVSI_REQUIRE(a_c64 && keep && out_c64 && n > 0, "args");
+  int blocks = (int)min((long long)(n + 255) / 256, (long long)num_sms() * 16);
+  select_c64_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2*>(a_c64), reinterpret_cast<const float2*>(b_c64),
+                                                             keep, (long long)n, reinterpret_cast<float2*>(out_c64));
+  AVSI_LAUNCH_CHECK();
+  return AVSI_OK;
+}

@@ -1,9 +1,10 @@
 """infer(...): the reference's inference job (inference.py:20, working twin inference_siasr_ctc.py:22) on the B200
 hot path: restore `netmodel/sinet`, run the model over the test TFRecords, reconstruct the waveform with the masked
 (or oracle) phase through the fused iSTFT kernel and write `<audio_path>/<sample>/enhanced/<prefix>.wav` as int16
-(first seq_len * hop samples, inference_siasr_ctc.py:241-243).  The host-side LWS phase refinement of
-inference.py:143-154 needs the `lws` C extension and is outside the hot path: the written waveform is
-the `enhanced_sources` / `enhanced_sources_oracle_phase` tensor of the model."""
+(first seq_len * hop samples, inference_siasr_ctc.py:241-243).  Without the oracle phase the reference refines the
+phase of the inpainted frames with the `lws` C extension (inference.py:143-154); that package is not available here, so
+the same bookkeeping runs around the exact consistency projection on the GPU (phase_reconstruction.refine_phase,
+`phase_iterations` of them; 0 writes the model's masked-phase `enhanced_sources` tensor as it is)."""
 import os
 from glob import glob
 
@@ -15,7 +16,8 @@ from .dataset_reader import DataManager
 from .training import build_model, feed_batch
 
 
-def infer(model_path, data_path_test, audio_path, out_file_prefix, norm=True, oracle_phase=False, batch_size=1):
+def infer(model_path, data_path_test, audio_path, out_file_prefix, norm=True, oracle_phase=False, batch_size=1,
+          phase_iterations=100):
     from scipy.io import wavfile
     config = load_configfile(os.path.join(model_path, 'config.txt'))
     for key, val in (('audio_feat_dim', 257), ('video_feat_dim', 136), ('num_asr_labels', 33), ('ctc_loss', 1),
@@ -46,7 +48,11 @@ def infer(model_path, data_path_test, audio_path, out_file_prefix, norm=True, or
                 raise SystemExit(2)
             hop = model.hop
         feed_batch(model, batch)
-        enhanced = (model.enhanced_sources_oracle_phase if oracle_phase else model.enhanced_sources).cpu().numpy()
+        enhanced = model.enhanced_sources_oracle_phase if oracle_phase else model.enhanced_sources
+        if not oracle_phase and phase_iterations > 0:
+            from .phase_reconstruction import refine_phase
+            enhanced = refine_phase(enhanced, model._fed['masks'], n_iter=phase_iterations)
+        enhanced = enhanced.cpu().numpy()
         loss_sum += float(model.loss_hole) * len(batch[0])
         for b, name in enumerate(batch[3]):
             name = name.decode() if isinstance(name, bytes) else str(name)

@@ -119,6 +119,10 @@ int64_t avsi_resample_workspace_bytes(int batch, int64_t n_in, int64_t n_out);
 int avsi_resample_fft(const double* x, int batch, int64_t n_in, double* y, int64_t n_out, void* workspace,
                       int64_t workspace_bytes, void* stream);
 int avsi_delta_features(const float* src, int ld_src, float* dst, int ld_dst, int B, int T, int F, int N, void* stream);
+/* out = keep != 0 ? a : b over n complex64 values (b NULL = 0): the phase source of one consistency iteration of the phase
+ * refinement that stands in for lws.run_lws in inference.py:143-154 (known spectrum in the reliable bins, re-analysed one
+ * in the holes); the iteration itself is avsi_istft_fwd + avsi_frontend_fwd (phase_reconstruction.py). */
+int avsi_select_c64(const float* a_c64, const float* b_c64, const float* keep, int64_t n, float* out_c64, void* stream);
 
 /* Waveform reconstruction (next row 8f.1): get_sources / reconstruct_sources
  * audio_processing.py:145-164, enhanced_sources models.py:181-197.

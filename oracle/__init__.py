@@ -20,7 +20,8 @@ relative to ``av_speech_inpainting/``):
   ``ctc.ctc_beam_search`` (tf.nn.ctc_beam_search_decoder, models.py:1627) pinned to exhaustive enumeration,
   ``stft.preemphasis / get_mfcc / delta / add_delta_features`` (audio_processing.py:19-22, 74-103),
   ``feat_stats.py`` (audio_feat_preprocessing.py:76-115), ``cpu_port.py`` (the timed torch-CPU port),
-  ``resample.py`` (downsampling, audio_processing.py:9-16 = scipy.signal.resample; pinned to scipy itself)
+  ``resample.py`` (downsampling, audio_processing.py:9-16 = scipy.signal.resample; pinned to scipy itself),
+  ``phase.py`` (the consistency-projection stand-in for lws.run_lws, inference.py:143-154; unpinned against lws)
 
 The arithmetic of the reference lives in TensorFlow 1.13-1.15 (un-vendored,
 ``requirements.txt:5-6`` gives only a lower bound) which is absent from this

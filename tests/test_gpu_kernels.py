@@ -891,6 +891,37 @@ def test_downsampling_fft_resample_matches_scipy():
         ap.resample(x.astype(np.complex128), 10)
 
 
+def test_phase_refinement_matches_oracle_and_converges():
+    """phase_reconstruction.refine_phase (the stand-in for lws.run_lws in inference.py:143-154: exact consistency projection,
+    phases of the reliable frames fixed) against its float64 restatement, and the property that makes it a phase
+    reconstruction: the spectrogram of the result approaches the wanted magnitudes monotonically; without holes the
+    waveform comes back unchanged."""
+    from avsi_b200 import phase_reconstruction as pr
+    from oracle import phase as oph
+    from oracle import stft as ostft
+    rng = np.random.default_rng(31)
+    d = dev()
+    B, N = 2, 19200
+    t = np.arange(N) / 16000.0
+    x = np.stack([sum(np.sin(2 * np.pi * np.cumsum((110 + 30 * b + 15 * np.sin(2 * np.pi * 3 * t)) * k) / 16000.0) / k
+                      for k in range(1, 10)) * 2000.0 + rng.standard_normal(N) * 40.0 for b in range(B)]).astype(np.float32)
+    T = -(-N // 192)
+    mask = np.ones((B, T, 257), np.float32)
+    mask[0, 30:55] = 0
+    mask[1, 60:80] = 0
+    mag = np.abs(ostft.get_stft(x.astype(np.float64), window_size=24, step_size=12))
+    xd, md = torch.from_numpy(x).to(d), torch.from_numpy(mask).to(d)
+    got = pr.refine_phase(xd, md, n_iter=8).cpu().numpy()
+    ref = oph.refine_phase(x, mask, n_iter=8)
+    assert got.shape == ref.shape == (B, N) and rel_l2(got, ref) < 1e-3
+    inc = [oph.inconsistency(pr.refine_phase(xd, md, n_iter=n).cpu().numpy(), mag) for n in (0, 4, 16, 64)]
+    assert all(a > b for a, b in zip(inc, inc[1:])) and inc[-1] < 0.35 * inc[0], inc
+    # frames far from the holes keep the recording (their phases are never touched)
+    assert rel_l2(got[0, 60 * 192:], x[0, 60 * 192:].astype(np.float64)) < 1e-2
+    same = pr.refine_phase(xd, torch.ones_like(md), n_iter=3).cpu().numpy()
+    assert rel_l2(same[:, 384:-384], x[:, 384:-384].astype(np.float64)) < 1e-5
+
+
 def test_mean_std_features_mfcc_with_deltas(tmp_path):
     """compute_mean_std_features(type='mfcc', preemph, delta) and save_features: the statistics of the composed features
     equal the float64 restatement's (audio_feat_preprocessing.py:23-115, 130-196)."""
