@@ -9,9 +9,10 @@ the B200 hot path: per batch of test TFRecords
   3. `<audio_path>/<sample>/enhanced/<prefix>.wav` (int16, first seq_len * 192 samples, :240-243) and
      `<audio_path>/<sample>/transcriptions/<prefix>.lbl` (comma-separated phonemes, :251-259) are written.
 
-The host-side LWS phase refinement of :222-235 needs the `lws` C extension (not in the image, not vendored by the
-reference): without oracle phase the written waveform is the model's `enhanced_sources` tensor, i.e. the masked-phase
-reconstruction that the reference hands to LWS (SURVEY.md 2.1 lists LWS as out of scope)."""
+The LWS phase refinement of :222-235 (applied to the WRITTEN waveform only; the recogniser hears the un-refined one, as in
+the reference) needs the `lws` C extension, which is neither in the image nor vendored by the reference: its place is taken by
+phase_reconstruction.refine_phase (exact consistency projection, `phase_iterations` of them; 0 = write the model's
+masked-phase `enhanced_sources` tensor as it is)."""
 import os
 from glob import glob
 
@@ -36,7 +37,7 @@ def _restore(model, folder, names):
 
 
 def infer(model_path, model_path_asr, data_path_test, audio_path, out_file_prefix, dictionary_file, norm=True,
-          oracle_phase=False, batch_size=1):
+          oracle_phase=False, batch_size=1, phase_iterations=100):
     from scipy.io import wavfile
     config = check_trainconfiguration(load_configfile(os.path.join(model_path, 'config.txt')))
     config_asr = check_trainconfiguration(load_configfile(os.path.join(model_path_asr, 'config.txt')))
@@ -79,6 +80,9 @@ def infer(model_path, model_path_asr, data_path_test, audio_path, out_file_prefi
         model_asr.feed(sequence_lengths=seq, labels_lengths=lab_len, target_sources=enhanced, masks=mask, labels=labels,
                        video_features=video if model_asr.input_type == 'av' else None, dropout_rate=0.0)
         decoded, loss_asr, per = model_asr.decoding, float(model_asr.loss), model_asr.per
+        if not oracle_phase and phase_iterations > 0:
+            from .phase_reconstruction import refine_phase
+            enhanced = refine_phase(enhanced, mask, n_iter=phase_iterations)
         enhanced = enhanced.cpu().numpy()
         for b, name in enumerate(paths):
             sample_dir = name.decode() if isinstance(name, bytes) else str(name)
