@@ -83,6 +83,9 @@ SIGNATURES = {
                               c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     'avsi_lstm_fwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     'avsi_lstm_bwd_scratch_bytes': (c_int64, [c_int]),
+    'avsi_set_reduce_scratch': (c_int, [c_void_p, c_int64, c_void_p]),
+    'avsi_reduce_scratch_min_bytes': (c_int64, []),
+    'avsi_gemm_f16_scratch_bytes': (c_int64, [c_int, c_int, c_int, c_int, c_int, c_int]),
     'avsi_lstm_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     'avsi_masked_l1': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),

@@ -39,9 +39,59 @@ def ctypes_ptr(addr):
 A_IL, C_IL, B_IL = 1, 2, 4     # avsi_gemm_f16 layout bits: A operand / f16 output / B operand stored interleaved (include/avsi_b200.h)
 
 
+# ---- bit-reproducible reductions (include/avsi_b200.h, avsi_set_reduce_scratch) ---------------------------------------
+# One scratch buffer per device, registered with the library: the split-K weight-gradient GEMMs, the bias-gradient column
+# sums and the loss sums then add their partial results in a fixed order instead of through floating-point atomics, and a
+# training step repeated on the same inputs gives the same bits.  AVSI_DETERMINISTIC=0 keeps the atomics (A/B runs).
+_REDUCE = {}          # device index -> {'buf': uint8 tensor registered with the library, 'keep': outgrown buffers, 'need': cache}
+
+
+def deterministic():
+    return os.environ.get('AVSI_DETERMINISTIC', '1') != '0'
+
+
+def ensure_reduce_scratch(nbytes=0):
+    """Register (or grow) this device's reduction scratch so that it holds at least nbytes.  Outgrown buffers are kept
+    alive: kernels in flight, or a captured CUDA graph, may still address them."""
+    if not deterministic():
+        return
+    lib = _lib.load()
+    dev = torch.cuda.current_device()
+    st = _REDUCE.setdefault(dev, {'buf': None, 'keep': [], 'need': {}})
+    need = max(int(nbytes), int(lib.avsi_reduce_scratch_min_bytes()))
+    if st['buf'] is not None and st['buf'].numel() >= need:
+        return
+    if torch.cuda.is_current_stream_capturing():
+        raise RuntimeError('the reduction scratch cannot grow inside a CUDA-graph capture: run one eager step first')
+    need = -(-need // (8 << 20)) * (8 << 20)
+    buf = torch.empty(need, dtype=torch.uint8, device='cuda:%d' % dev)
+    _lib.check(lib.avsi_set_reduce_scratch(_p(buf), need, _lib.stream_ptr()), 'avsi_set_reduce_scratch')
+    if st['buf'] is not None:
+        st['keep'].append(st['buf'])
+    st['buf'] = buf
+
+
+def release_reduce_scratch():
+    """Unregister this device's scratch (the library falls back to atomics); tests of the atomic path use it."""
+    lib = _lib.load()
+    dev = torch.cuda.current_device()
+    _lib.check(lib.avsi_set_reduce_scratch(None, 0, _lib.stream_ptr()), 'avsi_set_reduce_scratch')
+    st = _REDUCE.pop(dev, None)
+    if st is not None:
+        torch.cuda.synchronize()
+
+
 def gemm(A, lda, B, ldb, C, ldc, bias, M, N, K, trans, out_mode, split_k=1, tag='gemm', layout=0, nbytes=0):
     """nbytes: algorithmic operand bytes, given for the shapes that sit on the HBM roofline rather than the tensor one."""
     lib = _lib.load()
+    if out_mode == 2 and deterministic():
+        st = _REDUCE.get(torch.cuda.current_device())
+        key = (M, N, K, trans, split_k)
+        need = st['need'].get(key) if st is not None else None
+        if need is None:
+            need = int(lib.avsi_gemm_f16_scratch_bytes(M, N, K, trans, out_mode, split_k))
+            ensure_reduce_scratch(need)
+            _REDUCE[torch.cuda.current_device()]['need'][key] = need
     with _lib.span(tag, nbytes=nbytes, flops=2 * M * N * K):
         _lib.check(lib.avsi_gemm_f16(A, lda, B, ldb, C, ldc, bias, M, N, K, trans, out_mode, split_k, layout,
                                      _lib.stream_ptr()), 'avsi_gemm_f16')
@@ -172,8 +222,10 @@ class BLSTMEngine(object):
             ws['dlogits'] = torch.zeros(M, L.nop, dtype=torch.float16, device=dev)
             # dL/dy of a layer: INTERLEAVED like G (written by the dX GEMMs with C_IL, read by the BPTT kernel)
             ws['dY'] = [torch.zeros(Mp, NY, dtype=torch.float16, device=dev) for _ in range(2)]
+            # per-tile bias-gradient sums of the BPTT kernels, reduced in tile order (None: atomics, AVSI_DETERMINISTIC=0)
             nbytes = int(_lib.load().avsi_lstm_bwd_scratch_bytes(B))
-            ws['scratch'] = torch.empty(max(nbytes, 16) // 4, dtype=torch.float32, device=dev)
+            ws['scratch'] = torch.empty(max(nbytes, 16) // 4, dtype=torch.float32, device=dev) if deterministic() else None
+            ensure_reduce_scratch()
         if len(self._ws) > 4:
             self._ws = {}
         self._ws[key] = ws

@@ -5,7 +5,38 @@ namespace avsi {
 thread_local char g_last_error[512] = {0};
 std::atomic<long long> g_launch_count{0};
 std::atomic<int> g_env_gen{0};
+
+// per-device scratch of the ordered (bit-reproducible) reductions, registered by avsi_set_reduce_scratch
+static ReduceScratch g_reduce_scratch[64];
+ReduceScratch reduce_scratch() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return ReduceScratch{nullptr, nullptr, 0};
+  return g_reduce_scratch[dev];
+}
 }  // namespace avsi
+
+extern "C" int avsi_set_reduce_scratch(void* scratch, int64_t bytes, void* stream) {
+  using namespace avsi;
+  int dev = 0;
+  AVSI_CUDA(cudaGetDevice(&dev));
+  AVSI_REQUIRE(dev >= 0 && dev < 64, "device index");
+  if (!scratch) {
+    g_reduce_scratch[dev] = ReduceScratch{nullptr, nullptr, 0};
+    return AVSI_OK;
+  }
+  AVSI_REQUIRE(((uintptr_t)scratch & 255) == 0, "scratch must be 256-byte aligned");
+  AVSI_REQUIRE(bytes >= avsi_reduce_scratch_min_bytes(), "scratch smaller than avsi_reduce_scratch_min_bytes()");
+  // the tickets of the last-block reductions start at zero and reset themselves
+  AVSI_CUDA(cudaMemsetAsync(scratch, 0, REDUCE_COUNTER_BYTES, (cudaStream_t)stream));
+  g_reduce_scratch[dev] = ReduceScratch{reinterpret_cast<unsigned*>(scratch),
+                                        reinterpret_cast<unsigned char*>(scratch) + REDUCE_COUNTER_BYTES,
+                                        (long long)bytes - REDUCE_COUNTER_BYTES};
+  return AVSI_OK;
+}
+
+// counters + the partial sums of avsi_masked_l1 / avsi_colsum_f16 at their largest grids (the split-K GEMMs ask for more:
+// avsi_gemm_f16_scratch_bytes)
+extern "C" int64_t avsi_reduce_scratch_min_bytes(void) { return avsi::REDUCE_COUNTER_BYTES + (4LL << 20); }
 
 extern "C" const char* avsi_last_error(void) { return avsi::g_last_error; }
 

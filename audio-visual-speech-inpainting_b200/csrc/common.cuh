@@ -58,6 +58,18 @@ inline int set_error(int code, const char* fmt, const char* a = "", const char* 
       return avsi::set_error(AVSI_ERR_CUDA, "%s: launch failed: %s", __func__, cudaGetErrorString(e_)); \
   } while (0)
 
+// Scratch of the ordered reductions (avsi_set_reduce_scratch): [0, REDUCE_COUNTER_BYTES) tickets of the last-block
+// reductions (zero between launches), the rest is the partial-sum area of whichever reduction is running -- all users
+// are ordered on ONE stream.  ptr == nullptr: nothing registered, the reductions use floating-point atomics.
+constexpr long long REDUCE_COUNTER_BYTES = 4096;
+constexpr int REDUCE_SLOT_L1 = 0, REDUCE_SLOT_COLSUM = 8;      // colsum: one ticket per column block (<= 64)
+struct ReduceScratch {
+  unsigned* counters;
+  unsigned char* area;
+  long long area_bytes;
+};
+ReduceScratch reduce_scratch();
+
 inline int num_sms() {
   static int n = 0;
   if (n == 0) {

@@ -41,7 +41,9 @@ ctc_kernel(const float* __restrict__ logits, int ldl, int col0, int C, const int
   __shared__ int ext[NS];
   __shared__ unsigned char skip[NS];
   __shared__ float st[2][NS];
-  __shared__ float post[CTC_MAX_C];
+  __shared__ float gam[NS];                         // posterior mass of every state at the current frame
+  __shared__ unsigned short cls_states[NS];         // states grouped by class, ascending inside a class ...
+  __shared__ int cls_start[CTC_MAX_C + 1];          // ... class c owns cls_states[cls_start[c] .. cls_start[c+1])
   __shared__ float ll_sh;
   __shared__ float red[CTC_THREADS / 32];
   __shared__ int bad_label;
@@ -71,9 +73,28 @@ ctc_kernel(const float* __restrict__ logits, int ldl, int col0, int C, const int
     }
     ext[s] = e;
   }
-  for (int c = tid; c < CTC_MAX_C; c += CTC_THREADS) post[c] = 0.f;
   __syncthreads();
   for (int s = tid; s < S; s += CTC_THREADS) skip[s] = (s >= 2 && ext[s] != blank && ext[s] != ext[s - 2]) ? 1 : 0;
+  // states of every class in ascending order (a counting sort, once per utterance): the per-frame posterior of a class is
+  // then summed by ONE thread in a fixed order -- bit-reproducible, unlike a scatter of the states through atomics
+  if (dlogits) {
+    for (int c = tid; c < C; c += CTC_THREADS) {
+      int n = 0;
+      for (int s = 0; s < S; ++s) n += (ext[s] == c);
+      cls_start[c + 1] = n;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      cls_start[0] = 0;
+      for (int c = 0; c < C; ++c) cls_start[c + 1] += cls_start[c];
+    }
+    __syncthreads();
+    for (int c = tid; c < C; c += CTC_THREADS) {
+      int k = cls_start[c];
+      for (int s = 0; s < S; ++s)
+        if (ext[s] == c) cls_states[k++] = (unsigned short)s;
+    }
+  }
 
   // ---- log-softmax, one warp per frame ---------------------------------------------------
   for (int t = warp; t < Tb; t += CTC_THREADS / 32) {
@@ -240,16 +261,26 @@ ctc_kernel(const float* __restrict__ logits, int ldl, int col0, int C, const int
       if (s >= S) break;
       cur[s] = breg[i];
       // posterior mass of state s: alpha * beta / (y_t(ext_s) * p(l|x)); alpha*beta counts y_t twice -> subtract lp once.
-      // It is a probability (<= 1): no max-shift needed; scattered into its class with a shared-memory atomic.
+      // It is a probability (<= 1): no max-shift needed.
       const float e = alreg[i] + breg[i] - lpreg[i] + shift;
-      if (feasible && alreg[i] > CTC_NEG && breg[i] > CTC_NEG) atomicAdd(&post[ext[s]], expf(fminf(e, 0.f)));
+      gam[s] = (feasible && alreg[i] > CTC_NEG && breg[i] > CTC_NEG) ? expf(fminf(e, 0.f)) : 0.f;
     }
     __syncthreads();
-    // gradient of the NLL wrt the logits: softmax - posterior
+    // gradient of the NLL wrt the logits: softmax - posterior; the posterior of class c = its states' masses, added in
+    // ascending state order on four interleaved partial sums (the blank owns L + 1 states)
     for (int c = tid; c < C; c += CTC_THREADS) {
       const float lp = (c == tid) ? lpc : logp[t * C + c];
-      const float grad = feasible ? (expf(lp) - post[c]) : 0.f;
-      post[c] = 0.f;
+      float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+      int k = cls_start[c];
+      const int kz = cls_start[c + 1];
+      for (; k + 4 <= kz; k += 4) {
+        p0 += gam[cls_states[k]];
+        p1 += gam[cls_states[k + 1]];
+        p2 += gam[cls_states[k + 2]];
+        p3 += gam[cls_states[k + 3]];
+      }
+      for (; k < kz; ++k) p0 += gam[cls_states[k]];
+      const float grad = feasible ? (expf(lp) - ((p0 + p1) + (p2 + p3))) : 0.f;
       dlogits[((long long)t * B + b) * ldd + dcol0 + c] = __half_as_ushort(__float2half_rn(scale * grad));
     }
     __syncthreads();

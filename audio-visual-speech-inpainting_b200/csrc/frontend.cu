@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(FE_THREADS) frontend_kernel(avsi_frontend_args
   }
   if (p.hole_count) {
     holes = warp_sum(holes);
-    if ((tid & 31) == 0 && holes != 0.f) atomicAdd(p.hole_count, holes);
+    if ((tid & 31) == 0 && holes != 0.f) atomicAdd(p.hole_count, (double)holes);   // integer counts in a double: exact in any order
   }
 }
 
@@ -586,7 +586,7 @@ __global__ void __launch_bounds__(FE_THREADS, 2) frontend_train_kernel(avsi_fron
   }
   if (HOLES) {
     holes = warp_sum(holes);
-    if ((tid & 31) == 0 && holes != 0.f) atomicAdd(p.hole_count, holes);
+    if ((tid & 31) == 0 && holes != 0.f) atomicAdd(p.hole_count, (double)holes);   // integer counts in a double: exact in any order
   }
 }
 

@@ -60,6 +60,8 @@ struct GemmParams {
   int a_il, c_il, b_il;
   int fuse_l1;
   L1Fuse l1;
+  float* part;                  // out_mode 2, ordered split-K: partial products [k split][M][part_ld] f32 (else nullptr: atomics)
+  int part_ld;
 };
 
 // one element of the masked-L1 loss (same arithmetic as masked_l1_kernel, loss.cu): x = logit, y = target, m = mask,
@@ -89,7 +91,8 @@ struct GemmSmem {
 };
 
 // one warp-lane's 32 consecutive accumulator columns [n0, n0+32) of output row `row`
-__device__ __forceinline__ void epilogue_store(const GemmParams& p, int row, int n0, bool full, const uint32_t (&r)[32]) {
+// (ks = index of the k split that produced them: selects the slice of the ordered split-K partials)
+__device__ __forceinline__ void epilogue_store(const GemmParams& p, int row, int n0, bool full, const uint32_t (&r)[32], int ks = 0) {
   if (p.out_mode == 0 && p.c_il) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -139,10 +142,59 @@ __device__ __forceinline__ void epilogue_store(const GemmParams& p, int row, int
       for (int j = 0; j < 32; ++j)
         if (n0 + j < p.N) dst[j] = __uint_as_float(r[j]) + (p.bias ? __ldg(p.bias + n0 + j) : 0.f);
     }
+  } else if (p.part) {
+    // ordered split-K: this split's product goes to its own slice with plain stores; splitk_reduce_kernel adds the slices
+    // to C in split order (bit-reproducible, unlike the atomics below)
+    float* dst = p.part + ((long long)ks * p.M + row) * p.part_ld + n0;
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        reinterpret_cast<float4*>(dst)[j] = make_float4(__uint_as_float(r[4 * j + 0]), __uint_as_float(r[4 * j + 1]),
+                                                        __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+    } else {
+      for (int j = 0; j < 32; ++j)
+        if (n0 + j < p.N) dst[j] = __uint_as_float(r[j]);
+    }
   } else {
     float* dst = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + n0;
     for (int j = 0; j < 32; ++j)
       if (n0 + j < p.N) atomicAdd(dst + j, __uint_as_float(r[j]));
+  }
+}
+
+// C[M, N] += sum over the k splits, in split order, of part[split][M][part_ld]
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ part, int splits, int M, int N, int part_ld, float* __restrict__ C, int ldc) {
+  const int vpr = part_ld >> 2;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)M * vpr) return;
+  const int row = (int)(idx / vpr), c = (int)(idx - (long long)row * vpr) * 4;
+  if (c >= N) return;
+  float* dst = C + (long long)row * ldc + c;
+  const bool vec = (c + 4 <= N) && ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (vec) {
+    acc = *reinterpret_cast<const float4*>(dst);
+  } else {
+    acc.x = dst[0];
+    if (c + 1 < N) acc.y = dst[1];
+    if (c + 2 < N) acc.z = dst[2];
+    if (c + 3 < N) acc.w = dst[3];
+  }
+  const float* src = part + (long long)row * part_ld + c;
+  const long long slice = (long long)M * part_ld;
+#pragma unroll 4
+  for (int s = 0; s < splits; ++s) {
+    const float4 v = __ldcg(reinterpret_cast<const float4*>(src + s * slice));
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  if (vec) {
+    *reinterpret_cast<float4*>(dst) = acc;
+  } else {
+    dst[0] = acc.x;
+    if (c + 1 < N) dst[1] = acc.y;
+    if (c + 2 < N) dst[2] = acc.z;
+    if (c + 3 < N) dst[3] = acc.w;
   }
 }
 
@@ -358,7 +410,7 @@ gemm_f16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         continue;
       }
-      epilogue_store(p, row, n0, full, r);
+      epilogue_store(p, row, n0, full, r, (int)blockIdx.y);
     }
     if (p.fuse_l1) {
       // five sums: warp reduction in double, one atomic per warp and sum into one of L1_PARTS partial rows
@@ -572,7 +624,7 @@ gemm_f16_2sm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tmem_ld_wait();
         const int n0 = n_blk * TN + c * 32;
         if (!row_ok || n0 >= p.N) continue;
-        epilogue_store(p, row, n0, n0 + 32 <= p.N, r);
+        epilogue_store(p, row, n0, n0 + 32 <= p.N, r, ks);
       }
       tc_fence_before();
       __syncwarp();
@@ -937,6 +989,76 @@ static int launch_gemm_2sm_astat(const CUtensorMap& ta, const CUtensorMap& tb, c
 
 }  // namespace avsi
 
+// Which kernel serves a problem, and with how many k splits: shared by avsi_gemm_f16 and avsi_gemm_f16_scratch_bytes.
+namespace avsi {
+struct GemmPlan {
+  int kind;      // 0 one-tile kernel (bn), 1 CTA pairs 256 x 256, 2 CTA pairs 256 x 512, 3 A-stationary CTA pairs
+  int bn, split_k;
+};
+static GemmPlan plan_gemm(int M, int N, int K, int trans, int out_mode, int split_k) {
+  GemmPlan g{0, 128, split_k};
+  // tile width: 128 (3 stages, 2 CTAs/SM) by default; 256 (4 stages, 1 CTA/SM) for long-K problems
+  // where the main loop dominates; 64 for narrow outputs.  AVSI_GEMM_BN overrides (tuning only).
+  AVSI_ENV_CACHE(bn_env, env_int("AVSI_GEMM_BN", 0));
+  // large problems: persistent CTA-pair kernel (256 x 256 tiles, cta_group::2).  AVSI_GEMM_2SM=0 disables it.
+  AVSI_ENV_CACHE(use_2sm, env_is("AVSI_GEMM_2SM", "0") ? 0 : (env_is("AVSI_GEMM_2SM", "2") ? 2 : 1));
+  if (use_2sm && N >= 256 && (use_2sm == 2 || ((N + 255) / 256) * 256 * 3 <= N * 4) && (long long)M * N * K >= (1LL << 29)) {
+    // 256 x 512 tiles (one accumulator, a quarter less operand traffic per flop) where the main loop is long enough to
+    // carry the un-overlapped epilogue and the output is at least 3/4 of a 512-wide tile: the split-K dW shapes, and
+    // fixed-K shapes with K >= 2048 (dX).  AVSI_GEMM_WIDE = 0 never, 2 whenever N allows (A/B runs).
+    AVSI_ENV_CACHE(wide_env, env_int("AVSI_GEMM_WIDE", 1));
+    const bool n_fits = (N % 512 == 0) || (N % 512 >= 384);
+    const bool wide = wide_env && N >= 384 && n_fits && (wide_env == 2 || out_mode == 2 || K >= 2048);
+    // split-K only as far as needed to give every SM pair a work item
+    const int tn = wide ? 512 : 256;
+    const int m_t = (M + 255) / 256, n_t = (N + tn - 1) / tn, kbt = (K + GEMM_BK - 1) / GEMM_BK;
+    if (out_mode == 2) {
+      // split K so that the work items fill whole waves of SM pairs (80 items on 74 pairs would take two waves)
+      const int pairs = num_sms() / 2, tiles = m_t * n_t;
+      int best = 1;
+      double best_eff = 0.0;
+      for (int sk = 1; sk <= kbt && sk * tiles <= 4 * pairs; ++sk) {
+        const int work = sk * tiles, waves = (work + pairs - 1) / pairs;
+        const double eff = (double)work / ((double)waves * pairs);
+        if (eff > best_eff + 1e-9) {
+          best_eff = eff;
+          best = sk;
+        }
+      }
+      g.split_k = best;
+    }
+    // A-stationary sweep for the projection shape: trans = 0, the whole K in 8 k-slices, several n tiles to share A,
+    // enough row blocks to fill the chip.  AVSI_GEMM_ASTAT=0 disables it (A/B runs).
+    AVSI_ENV_CACHE(astat_env, env_int("AVSI_GEMM_ASTAT", 1));
+    if (astat_env && trans == 0 && out_mode != 2 && K <= GemmAStatSmem::KS_MAX * GEMM_BK && n_t >= 4 && m_t >= num_sms()) g.kind = 3;
+    else g.kind = wide ? 2 : 1;
+    g.bn = 256;
+    return g;
+  }
+  int bn = 128;
+  if (N > 128 && K >= 4096) bn = 256;
+  if (N <= 64) bn = 64;
+  if (bn_env == 64 || bn_env == 128 || bn_env == 256) bn = bn_env;
+  g.bn = bn;
+  return g;
+}
+// k splits that get at least one k block (the others leave their slice of the ordered partials unwritten)
+static int live_splits(int K, int split_k) {
+  const int kbt = (K + GEMM_BK - 1) / GEMM_BK, chunk = (kbt + split_k - 1) / split_k;
+  return (kbt + chunk - 1) / chunk;
+}
+}  // namespace avsi
+
+// Bytes of reduction scratch (avsi_set_reduce_scratch) with which this out_mode-2 problem runs its split-K sum in a fixed
+// order; 0 when it does not split K.
+extern "C" int64_t avsi_gemm_f16_scratch_bytes(int M, int N, int K, int trans, int out_mode, int split_k) {
+  using namespace avsi;
+  if (M <= 0 || N <= 0 || K <= 0 || out_mode != 2 || split_k < 1) return 0;
+  const GemmPlan g = plan_gemm(M, N, K, trans, out_mode, split_k);
+  if (g.split_k <= 1) return 0;
+  return REDUCE_COUNTER_BYTES + (int64_t)live_splits(K, g.split_k) * M * ((N + 3) & ~3) * (int64_t)sizeof(float);
+}
+
 extern "C" int avsi_gemm_f16(const uint16_t* A, int lda, const uint16_t* B, int ldb, void* C, int ldc,
                              const float* bias, int M, int N, int K, int trans, int out_mode, int split_k,
                              int layout, void* stream) {
@@ -967,37 +1089,31 @@ extern "C" int avsi_gemm_f16(const uint16_t* A, int lda, const uint16_t* B, int 
   }
 #endif
 
-  // tile width: wide tiles for wide outputs, narrow ones so that small-N problems still fill the chip
-  // tile width: 128 (3 stages, 2 CTAs/SM) by default; 256 (4 stages, 1 CTA/SM) for long-K problems
-  // where the main loop dominates; 64 for narrow outputs.  AVSI_GEMM_BN overrides (tuning only).
-  AVSI_ENV_CACHE(bn_env, env_int("AVSI_GEMM_BN", 0));
-  // large problems: persistent CTA-pair kernel (256 x 256 tiles, cta_group::2).  AVSI_GEMM_2SM=0 disables it.
-  AVSI_ENV_CACHE(use_2sm, env_is("AVSI_GEMM_2SM", "0") ? 0 : (env_is("AVSI_GEMM_2SM", "2") ? 2 : 1));
-  if (use_2sm && N >= 256 && (use_2sm == 2 || ((N + 255) / 256) * 256 * 3 <= N * 4) && (long long)M * N * K >= (1LL << 29)) {
-    // 256 x 512 tiles (one accumulator, a quarter less operand traffic per flop) where the main loop is long enough to
-    // carry the un-overlapped epilogue and the output is at least 3/4 of a 512-wide tile: the split-K dW shapes, and
-    // fixed-K shapes with K >= 2048 (dX).  AVSI_GEMM_WIDE = 0 never, 2 whenever N allows (A/B runs).
-    AVSI_ENV_CACHE(wide_env, env_int("AVSI_GEMM_WIDE", 1));
-    const bool n_fits = (N % 512 == 0) || (N % 512 >= 384);
-    const bool wide = wide_env && N >= 384 && n_fits && (wide_env == 2 || out_mode == 2 || K >= 2048);
-    // split-K only as far as needed to give every SM pair a work item
-    const int tn = wide ? 512 : 256;
-    const int m_t = (M + 255) / 256, n_t = (N + tn - 1) / tn, kbt = (K + GEMM_BK - 1) / GEMM_BK;
-    if (out_mode == 2) {
-      // split K so that the work items fill whole waves of SM pairs (80 items on 74 pairs would take two waves)
-      const int pairs = num_sms() / 2, tiles = m_t * n_t;
-      int best = 1;
-      double best_eff = 0.0;
-      for (int sk = 1; sk <= kbt && sk * tiles <= 4 * pairs; ++sk) {
-        const int work = sk * tiles, waves = (work + pairs - 1) / pairs;
-        const double eff = (double)work / ((double)waves * pairs);
-        if (eff > best_eff + 1e-9) {
-          best_eff = eff;
-          best = sk;
-        }
-      }
-      p.split_k = best;
+  const GemmPlan g = plan_gemm(M, N, K, trans, out_mode, split_k);
+  p.split_k = g.split_k;
+  // split-K sums in a fixed order when the reduction scratch is registered (avsi_set_reduce_scratch): every split
+  // writes its product to its own slice, splitk_reduce_kernel adds the slices to C.  Without scratch: fp32 atomics.
+  int splits_live = 0;
+  if (out_mode == 2 && p.split_k > 1) {
+    const ReduceScratch rs = reduce_scratch();
+    if (rs.counters) {
+      splits_live = live_splits(K, p.split_k);
+      p.part_ld = (N + 3) & ~3;
+      AVSI_REQUIRE((long long)splits_live * M * p.part_ld * (long long)sizeof(float) <= rs.area_bytes,
+                   "reduce scratch too small (avsi_gemm_f16_scratch_bytes)");
+      p.part = reinterpret_cast<float*>(rs.area);
     }
+  }
+  auto finish = [&](int rc) -> int {
+    if (rc != AVSI_OK || !p.part) return rc;
+    const long long vecs = (long long)M * (p.part_ld >> 2);
+    splitk_reduce_kernel<<<(unsigned)((vecs + 255) / 256), 256, 0, st>>>(p.part, splits_live, M, N, p.part_ld,
+                                                                        reinterpret_cast<float*>(C), ldc);
+    AVSI_LAUNCH_CHECK();
+    return AVSI_OK;
+  };
+
+  if (g.kind != 0) {
     CUtensorMap ta2, tb2;
     int rc2;
     if (trans == 0) {
@@ -1014,18 +1130,11 @@ extern "C" int avsi_gemm_f16(const uint16_t* A, int lda, const uint16_t* B, int 
                          : get_tmap(B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, GEMM_BK, &tb2);
       if (rc2) return rc2;
     }
-    // A-stationary sweep for the projection shape: trans = 0, the whole K in 8 k-slices, several n tiles to share A,
-    // enough row blocks to fill the chip.  AVSI_GEMM_ASTAT=0 disables it (A/B runs).
-    AVSI_ENV_CACHE(astat_env, env_int("AVSI_GEMM_ASTAT", 1));
-    if (astat_env && trans == 0 && out_mode != 2 && K <= GemmAStatSmem::KS_MAX * GEMM_BK && n_t >= 4 && m_t >= num_sms())
-      return launch_gemm_2sm_astat(ta2, tb2, p, st);
-    if (wide) return launch_gemm_2sm<256, true>(ta2, tb2, p, st);
-    return launch_gemm_2sm<256, false>(ta2, tb2, p, st);
+    if (g.kind == 3) return launch_gemm_2sm_astat(ta2, tb2, p, st);
+    if (g.kind == 2) return finish(launch_gemm_2sm<256, true>(ta2, tb2, p, st));
+    return finish(launch_gemm_2sm<256, false>(ta2, tb2, p, st));
   }
-  int bn = 128;
-  if (N > 128 && K >= 4096) bn = 256;
-  if (N <= 64) bn = 64;
-  if (bn_env == 64 || bn_env == 128 || bn_env == 256) bn = bn_env;
+  const int bn = g.bn;
   CUtensorMap ta, tb;
   int rc;
   if (trans == 0) {
@@ -1042,9 +1151,9 @@ extern "C" int avsi_gemm_f16(const uint16_t* A, int lda, const uint16_t* B, int 
                       : get_tmap(B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, GEMM_BK, &tb);
     if (rc) return rc;
   }
-  if (bn == 256) return launch_gemm<256, 4>(ta, tb, p, st);
-  if (bn == 128) return launch_gemm<128, 3>(ta, tb, p, st);
-  return launch_gemm<64, 4>(ta, tb, p, st);
+  if (bn == 256) return finish(launch_gemm<256, 4>(ta, tb, p, st));
+  if (bn == 128) return finish(launch_gemm<128, 3>(ta, tb, p, st));
+  return finish(launch_gemm<64, 4>(ta, tb, p, st));
 }
 
 // Head GEMM with the masked-L1 loss and its gradient in the epilogue (training step): logits = A[M,K] . W[N,K]^T + bias are

@@ -14,7 +14,7 @@ __global__ void __launch_bounds__(L1_THREADS)
 masked_l1_kernel(const float* __restrict__ logits, int ldl, const float* __restrict__ target,
                  const float* __restrict__ mask, const int32_t* __restrict__ seq_len, int B, int T, int F,
                  int mode, float grad_scale_h, const float* __restrict__ grad_scale_dev, double* __restrict__ sums, float* __restrict__ prediction,
-                 uint16_t* __restrict__ dlogits, int ldd) {
+                 uint16_t* __restrict__ dlogits, int ldd, double* __restrict__ partials, unsigned* __restrict__ ticket) {
   // one warp per (b,t) row, grid-stride
   const int lane = threadIdx.x & 31;
   const int warps_per_block = L1_THREADS / 32;
@@ -76,9 +76,38 @@ masked_l1_kernel(const float* __restrict__ logits, int ldl, const float* __restr
   if (threadIdx.x < 5) {
     double v = 0.0;
     for (int w = 0; w < warps_per_block; ++w) v += red[threadIdx.x][w];
-    atomicAdd(sums + threadIdx.x, v);
+    if (partials) partials[(long long)blockIdx.x * 5 + threadIdx.x] = v;
+    else atomicAdd(sums + threadIdx.x, v);
   }
-  if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(sums + 5, (double)rows * F);
+  if (!partials) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(sums + 5, (double)rows * F);
+    return;
+  }
+  // ordered tail (bit-reproducible sums): the block that draws the last ticket adds all blocks' partials in a fixed order
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    double v = 0.0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += L1_THREADS) v += __ldcg(partials + (long long)b * 5 + i);
+    v = warp_sum_d(v);
+    if (lane == 0) red[i][threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 5) {
+    double v = 0.0;
+    for (int w = 0; w < warps_per_block; ++w) v += red[threadIdx.x][w];
+    sums[threadIdx.x] += v;
+  }
+  if (threadIdx.x == 0) {
+    sums[5] += (double)rows * F;
+    *ticket = 0u;
+  }
 }
 
 // Column sums of an f16 matrix (bias gradients): a thread owns 8 consecutive columns (one 16-byte load per row) and every
@@ -89,7 +118,7 @@ constexpr int CS_ROWS = 4;                        // row lanes per block (256 th
 
 __global__ void __launch_bounds__(CS_VECS * CS_ROWS)
 colsum_f16_kernel(const uint16_t* __restrict__ X, int ldx, int rows, int col0, int ncols,
-                  float* __restrict__ out) {
+                  float* __restrict__ out, float* __restrict__ partials, unsigned* __restrict__ tickets) {
   const int v = threadIdx.x % CS_VECS, rl = threadIdx.x / CS_VECS;
   const int c = (blockIdx.x * CS_VECS + v) * 8;                     // first of this thread's 8 columns (relative to col0)
   float acc[8];
@@ -115,17 +144,62 @@ colsum_f16_kernel(const uint16_t* __restrict__ X, int ldx, int rows, int col0, i
 #pragma unroll
   for (int i = 0; i < 8; ++i) red[rl][v][i] = acc[i];
   __syncthreads();
-  if (rl == 0 && c < ncols && r1 > r0) {
+  if (!partials) {
+    if (rl == 0 && c < ncols && r1 > r0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (c + i < ncols) {
+          float t = 0.f;
+#pragma unroll
+          for (int k = 0; k < CS_ROWS; ++k) t += red[k][v][i];
+          atomicAdd(out + c + i, t);
+        }
+      }
+    }
+    return;
+  }
+  // ordered tail (bit-reproducible): row slab blockIdx.y's sums go to row blockIdx.y of the partial matrix; the block of
+  // this column block that draws the last ticket adds the slabs in slab order
+  const int pcols = gridDim.x * CS_VECS * 8;
+  if (rl == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < CS_ROWS; ++k) t += red[k][v][i];
+      partials[(long long)blockIdx.y * pcols + blockIdx.x * CS_VECS * 8 + v * 8 + i] = t;
+    }
+  }
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(tickets + blockIdx.x, 1u) == gridDim.y - 1);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int y = rl; y < (int)gridDim.y; y += CS_ROWS) {
+    const float4* src = reinterpret_cast<const float4*>(partials + (long long)y * pcols + blockIdx.x * CS_VECS * 8 + v * 8);
+    const float4 a = __ldcg(src), b = __ldcg(src + 1);
+    acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+    acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[rl][v][i] = acc[i];
+  __syncthreads();
+  if (rl == 0 && c < ncols) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       if (c + i < ncols) {
         float t = 0.f;
 #pragma unroll
         for (int k = 0; k < CS_ROWS; ++k) t += red[k][v][i];
-        atomicAdd(out + c + i, t);
+        out[c + i] += t;
       }
     }
   }
+  if (threadIdx.x == 0) tickets[blockIdx.x] = 0u;
 }
 
 }  // namespace avsi
@@ -141,8 +215,18 @@ extern "C" int avsi_masked_l1(const float* logits, int ldl, const float* target,
   AVSI_REQUIRE(!dlogits || ldd >= F, "ldd");
   long long rows = (long long)B * T;
   int blocks = (int)min((rows + 7) / 8, (long long)num_sms() * 8);
+  // ordered sums when the reduction scratch is registered (avsi_set_reduce_scratch), atomics otherwise
+  const ReduceScratch rs = reduce_scratch();
+  double* partials = nullptr;
+  unsigned* ticket = nullptr;
+  if (rs.counters) {
+    AVSI_REQUIRE((long long)blocks * 5 * (long long)sizeof(double) <= rs.area_bytes, "reduce scratch too small");
+    partials = reinterpret_cast<double*>(rs.area);
+    ticket = rs.counters + REDUCE_SLOT_L1;
+  }
   masked_l1_kernel<<<blocks, L1_THREADS, 0, (cudaStream_t)stream>>>(logits, ldl, target, mask, seq_len, B, T, F,
-                                                                   mode, grad_scale, grad_scale_dev, sums, prediction, dlogits, ldd);
+                                                                   mode, grad_scale, grad_scale_dev, sums, prediction, dlogits, ldd,
+                                                                   partials, ticket);
   AVSI_LAUNCH_CHECK();
   return AVSI_OK;
 }
@@ -157,7 +241,15 @@ extern "C" int avsi_colsum_f16(const uint16_t* X, int ldx, int rows, int col0, i
   if (gy > (rows + 63) / 64) gy = (rows + 63) / 64;
   if (gy < 1) gy = 1;
   dim3 grid(gx, (unsigned)gy);
-  colsum_f16_kernel<<<grid, CS_VECS * CS_ROWS, 0, (cudaStream_t)stream>>>(X, ldx, rows, col0, ncols, out);
+  const ReduceScratch rs = reduce_scratch();
+  float* partials = nullptr;
+  unsigned* tickets = nullptr;
+  if (rs.counters && gx <= 64) {
+    AVSI_REQUIRE((long long)gy * gx * CS_VECS * 8 * (long long)sizeof(float) <= rs.area_bytes, "reduce scratch too small");
+    partials = reinterpret_cast<float*>(rs.area);
+    tickets = rs.counters + REDUCE_SLOT_COLSUM;
+  }
+  colsum_f16_kernel<<<grid, CS_VECS * CS_ROWS, 0, (cudaStream_t)stream>>>(X, ldx, rows, col0, ncols, out, partials, tickets);
   AVSI_LAUNCH_CHECK();
   return AVSI_OK;
 }

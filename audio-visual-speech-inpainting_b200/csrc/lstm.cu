@@ -204,7 +204,7 @@ struct LstmBwdSmem {
 template <int BT>
 __global__ void __cluster_dims__(LS_CL, 1, 1) __launch_bounds__(LS_THREADS, 1)
 lstm_bwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whhT, const float* __restrict__ cst,
-                const uint16_t* __restrict__ dy, float* __restrict__ dbias, int T, int B) {
+                const uint16_t* __restrict__ dy, float* __restrict__ dbias, int dbias_tile_stride, int T, int B) {
   constexpr int MT = BT / 16;
   constexpr uint32_t PHASE_BYTES = LS_CL * BT * 32 * 2;
   extern __shared__ __align__(16) unsigned char ls_smem[];
@@ -368,7 +368,12 @@ lstm_bwd_kernel(uint16_t* __restrict__ gates, const uint16_t* __restrict__ whhT,
     v += __shfl_xor_sync(0xffffffffu, v, 4);
     v += __shfl_xor_sync(0xffffffffu, v, 8);
     v += __shfl_xor_sync(0xffffffffu, v, 16);
-    if (g == 0) atomicAdd(dbias + dir * LS_G + u * 4 + q, v);
+    // dbias_tile_stride > 0: this row tile's sums go to their own row of a scratch matrix (plain stores; reduced in
+    // tile order by dbias_reduce_kernel: run-to-run identical bits), else straight into dbias with atomics
+    if (g == 0) {
+      if (dbias_tile_stride > 0) dbias[(long long)(cid >> 1) * dbias_tile_stride + dir * LS_G + u * 4 + q] = v;
+      else atomicAdd(dbias + dir * LS_G + u * 4 + q, v);
+    }
   }
   cluster_sync_all();
 }
@@ -423,8 +428,8 @@ static int launch_fwd(uint16_t* gates, const uint16_t* whh, const float* bias, u
 }
 
 template <int BT>
-static int launch_bwd(uint16_t* gates, const uint16_t* whhT, const float* cst, const uint16_t* dy, float* dbias, int T,
-                      int B, cudaStream_t st) {
+static int launch_bwd(uint16_t* gates, const uint16_t* whhT, const float* cst, const uint16_t* dy, float* dbias,
+                      int dbias_tile_stride, int T, int B, cudaStream_t st) {
   static bool attr_done = false;
   const int smem = (int)sizeof(LstmBwdSmem<BT>);
   if (!attr_done) {
@@ -432,13 +437,22 @@ static int launch_bwd(uint16_t* gates, const uint16_t* whhT, const float* cst, c
     attr_done = true;
   }
   const int grid = 2 * ((B + BT - 1) / BT) * LS_CL;
-  lstm_bwd_kernel<BT><<<grid, LS_THREADS, smem, st>>>(gates, whhT, cst, dy, dbias, T, B);
+  lstm_bwd_kernel<BT><<<grid, LS_THREADS, smem, st>>>(gates, whhT, cst, dy, dbias, dbias_tile_stride, T, B);
   AVSI_LAUNCH_CHECK();
   return AVSI_OK;
 }
 
-int launch_lstm4_bwd(uint16_t* gates, const uint16_t* whhT, const float* cst, const uint16_t* dy, float* dbias, int T,
-                     int B, cudaStream_t st);   // lstm4_bwd.cu
+int launch_lstm4_bwd(uint16_t* gates, const uint16_t* whhT, const float* cst, const uint16_t* dy, float* dbias,
+                     int dbias_tile_stride, int T, int B, cudaStream_t st);   // lstm4_bwd.cu
+
+// dbias[c] += sum over row tiles (in tile order) of part[tile][c]: the deterministic tail of the bias gradient
+__global__ void dbias_reduce_kernel(const float* __restrict__ part, int tiles, int n, float* __restrict__ dbias) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n) return;
+  float acc = dbias[c];
+  for (int t = 0; t < tiles; ++t) acc += __ldcg(part + (long long)t * n + c);
+  dbias[c] = acc;
+}
 int launch_lstm4_fwd(uint16_t* gates, const uint16_t* whh, const float* bias, uint16_t* y, float* cst, int T, int B,
                      int y_il, cudaStream_t st);     // lstm4.cu
 
@@ -470,22 +484,38 @@ extern "C" int avsi_lstm_fwd(uint16_t* gates, const uint16_t* whh, const float* 
 }
 
 extern "C" int64_t avsi_lstm_bwd_scratch_bytes(int B) {
-  (void)B;
-  return 0;   // the reduce-scatter of partial dh lives in distributed shared memory
+  // one row of 2 x 1024 bias-gradient sums per row tile (at most ceil(B / 16) tiles, whichever kernel runs); the
+  // reduce-scatter of partial dh lives in distributed shared memory
+  if (B <= 0) return 0;
+  return (int64_t)((B + 15) / 16) * 2 * avsi::LS_G * (int64_t)sizeof(float);
 }
 
 extern "C" int avsi_lstm_bwd(uint16_t* gates, const uint16_t* whhT, const float* cst, const uint16_t* dy,
                              float* dbias, void* scratch, int T, int B, void* stream) {
   using namespace avsi;
-  (void)scratch;
   AVSI_REQUIRE(gates && whhT && cst && dy && dbias, "null pointer");
   AVSI_REQUIRE(T > 0 && B > 0, "T,B > 0");
+  AVSI_REQUIRE(((uintptr_t)scratch & 15) == 0, "scratch must be 16-byte aligned");
   const int bt = pick_bt(B);
   cudaStream_t st = (cudaStream_t)stream;
   // AVSI_LSTM_BWD=mma|l4 overrides (A/B measurements and the parity tests of the tcgen05 path at small batches)
   AVSI_ENV_CACHE(bmode, env_is("AVSI_LSTM_BWD", "mma") ? 1 : (env_is("AVSI_LSTM_BWD", "l4") ? 2 : 0));
-  if (bmode == 2 || (bmode == 0 && bt > 32)) return launch_lstm4_bwd(gates, whhT, cst, dy, dbias, T, B, st);
-  if (bt == 16) return launch_bwd<16>(gates, whhT, cst, dy, dbias, T, B, st);
-  if (bt == 32) return launch_bwd<32>(gates, whhT, cst, dy, dbias, T, B, st);
-  return launch_bwd<64>(gates, whhT, cst, dy, dbias, T, B, st);
+  // with scratch: per-tile bias-gradient sums + an ordered reduction (bit-reproducible); without: fp32 atomics into dbias
+  float* part = reinterpret_cast<float*>(scratch);
+  const int stride = part ? 2 * LS_G : 0;
+  float* dst = part ? part : dbias;
+  int rc, tiles;
+  if (bmode == 2 || (bmode == 0 && bt > 32)) {
+    tiles = (B + 127) / 128;
+    rc = launch_lstm4_bwd(gates, whhT, cst, dy, dst, stride, T, B, st);
+  } else {
+    tiles = (B + bt - 1) / bt;
+    if (bt == 16) rc = launch_bwd<16>(gates, whhT, cst, dy, dst, stride, T, B, st);
+    else if (bt == 32) rc = launch_bwd<32>(gates, whhT, cst, dy, dst, stride, T, B, st);
+    else rc = launch_bwd<64>(gates, whhT, cst, dy, dst, stride, T, B, st);
+  }
+  if (rc != AVSI_OK || !part) return rc;
+  dbias_reduce_kernel<<<(2 * LS_G + 255) / 256, 256, 0, st>>>(part, tiles, 2 * LS_G, dbias);
+  AVSI_LAUNCH_CHECK();
+  return AVSI_OK;
 }

@@ -104,7 +104,7 @@ __device__ unsigned long long g_b4_timing[24];
 template <bool TIMING, bool CFENCE, bool BPF, bool STMA>
 __global__ void __cluster_dims__(B4_CL, 1, 1) __launch_bounds__(B4_THREADS, 1)
 lstm4_bwd_kernel(const __grid_constant__ CUtensorMap tmG, uint16_t* __restrict__ gates, const uint16_t* __restrict__ whhT, const float* __restrict__ cst,
-                 const uint16_t* __restrict__ dy, float* __restrict__ dbias, int T, int B, int PFD) {
+                 const uint16_t* __restrict__ dy, float* __restrict__ dbias, int dbias_tile_stride, int T, int B, int PFD) {
   extern __shared__ unsigned char b4_smem_raw[];
   const uint32_t raw_s = smem_u32(b4_smem_raw);
   const uint32_t base_s = (raw_s + 127u) & ~127u;
@@ -458,7 +458,9 @@ lstm4_bwd_kernel(const __grid_constant__ CUtensorMap tmG, uint16_t* __restrict__
         const int m = q * 32 + lane, kc = m >> 3, e = m & 7;
         const int cgk = kc >> 2, i = kc & 3;
         const int col = (64 * j + 16 * cgk + 8 * h) * 4 + 8 * i + e;
-        atomicAdd(dbias + dir * B4_G + col, __uint_as_float(v[0]));
+        // per-tile row of the scratch matrix (ordered reduction afterwards) or atomics straight into dbias
+        if (dbias_tile_stride > 0) dbias[(long long)(cid >> 1) * dbias_tile_stride + dir * B4_G + col] = __uint_as_float(v[0]);
+        else atomicAdd(dbias + dir * B4_G + col, __uint_as_float(v[0]));
       }
     }
   }
@@ -472,8 +474,8 @@ lstm4_bwd_kernel(const __grid_constant__ CUtensorMap tmG, uint16_t* __restrict__
 
 int get_tmap_il(const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t brb, uint32_t bcc, CUtensorMap* out);
 
-int launch_lstm4_bwd(uint16_t* gates, const uint16_t* whhT, const float* cst, const uint16_t* dy, float* dbias, int T,
-                     int B, cudaStream_t st) {
+int launch_lstm4_bwd(uint16_t* gates, const uint16_t* whhT, const float* cst, const uint16_t* dy, float* dbias,
+                     int dbias_tile_stride, int T, int B, cudaStream_t st) {
   AVSI_ENV_CACHE(timing, env_is("AVSI_B4_TIMING", "1"));   // in-kernel phase timers (profiles/bench_lstm.py)
   const int smem = (int)sizeof(Lstm4BwdSmem) + 128;
   AVSI_ENV_CACHE(cfence, env_int("AVSI_B4_CFENCE", 1));    // 0: proxy fence in the 512 writers (round-1 form, A/B runs)
@@ -498,7 +500,7 @@ int launch_lstm4_bwd(uint16_t* gates, const uint16_t* whhT, const float* cst, co
       AVSI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       if (n_prepared < 8) prepared[n_prepared++] = (const void*)kern;
     }
-    kern<<<grid, B4_THREADS, smem, st>>>(tmG, gates, whhT, cst, dy, dbias, T, B, pfd);
+    kern<<<grid, B4_THREADS, smem, st>>>(tmG, gates, whhT, cst, dy, dbias, dbias_tile_stride, T, B, pfd);
     return AVSI_OK;
   };
   int rc;

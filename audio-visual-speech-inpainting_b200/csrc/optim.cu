@@ -131,11 +131,11 @@ __global__ void gate_bias_prescale_kernel(const float* __restrict__ b, int n, fl
   if (i < n) out[i] = b[i] * (((i & 3) != 1) ? 0.5f : 1.f);
 }
 
-__global__ void mtl_scales_kernel(const float* __restrict__ hole_count, int B, float ctc_w, float* __restrict__ out,
+__global__ void mtl_scales_kernel(const double* __restrict__ hole_count, int B, float ctc_w, float* __restrict__ out,
                                   const int32_t* __restrict__ guard) {
   // out[0] = S  (scale of the L1 dlogits), out[1] = S * (w/B) * holes (scale of the CTC dlogits),
   // out[2] = 1 / (S * holes)  (optimiser unscale), out[3] = holes
-  float holes = fmaxf(*hole_count, 1.f);
+  float holes = fmaxf((float)*hole_count, 1.f);
   float rel = ctc_w / (float)B * holes;         // CTC gradient relative to the +-1 L1 gradient
   float S = 1.f;
   while (rel * S > 64.f) S *= 0.5f;             // keep fp16 dlogits far from 65504
@@ -236,7 +236,7 @@ extern "C" int avsi_grad_guard_update(int32_t* guard, int growth_interval, void*
   return AVSI_OK;
 }
 
-extern "C" int avsi_mtl_scales(const float* hole_count, int B, float ctc_weight, float* out, const int32_t* guard,
+extern "C" int avsi_mtl_scales(const double* hole_count, int B, float ctc_weight, float* out, const int32_t* guard,
                                void* stream) {
   using namespace avsi;
   AVSI_REQUIRE(hole_count && out && B > 0, "args");

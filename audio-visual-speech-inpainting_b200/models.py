@@ -221,7 +221,7 @@ class StackedBLSTMModel(object):
         ws = self.engine.workspace(T, B, self.is_training)
         hole = None
         if self.MTL:
-            hole = self._cache.setdefault('hole', torch.zeros(1, dtype=torch.float32, device=self.device))
+            hole = self._cache.setdefault('hole', torch.zeros(1, dtype=torch.float64, device=self.device))
             hole.zero_()
         L = self.engine.layout
         ext = self._fed.get('audio_features') if self.external_audio_features else None

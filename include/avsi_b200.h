@@ -83,7 +83,8 @@ typedef struct {
   float* stft_out; float* spec_out; float* feat_out;
   uint16_t* xh_out; int ldx;
   float* logmel_out; const float* mel_w; int n_mel; float mel_eps;
-  float* hole_count;   /* optional [1] f32 device accumulator: += sum(1 - mask) (caller zeroes) */
+  double* hole_count;  /* optional [1] f64 device accumulator: += sum(1 - mask) (caller zeroes); a double so that the
+                        * count of a {0,1} mask is exact -- and the same bits -- in whatever order the warps arrive */
   int xh_video_only;   /* input='v' (models.py:42-43): xh_out holds only the video columns, from column 0 */
   int mel_masked;      /* != 0: the power spectrum is multiplied by the mask before the mel projection
                           (models_asr.py:33-36, apply_mask) */
@@ -204,6 +205,23 @@ int avsi_gemm_f16(const uint16_t* A, int lda, const uint16_t* B, int ldb, void* 
                   int layout, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Bit-reproducible reductions.  TensorFlow's gradient kernels behind models.py:161-196 (compute_gradients: cuDNN /
+ * cuBLAS weight gradients, BiasAddGrad, the reduce_sum of the losses) are not run-to-run deterministic, and neither
+ * is this library by default: split-K weight-gradient GEMMs, bias-gradient column sums and the loss sums meet in
+ * floating-point atomics.  Once a device scratch buffer is registered here, avsi_gemm_f16 (out_mode 2 with k splits),
+ * avsi_colsum_f16 and avsi_masked_l1 write per-split / per-block partial sums into it and add them in a FIXED order
+ * (a second tiny kernel, or the block that draws the last ticket), and avsi_lstm_bwd does the same with its own
+ * `scratch` argument: two runs of a training step on the same inputs then produce the same bits.
+ *   scratch: device memory, 256-byte aligned, >= avsi_reduce_scratch_min_bytes() and >= avsi_gemm_f16_scratch_bytes(...)
+ *   of every split-K problem that will run (a too small buffer is an error, never a silent fallback); NULL unregisters.
+ *   One registration per device; all users must be ordered on ONE stream (they share the buffer).  The first 4 KB hold
+ *   tickets that are zero between launches (zeroed here on `stream`).  Not covered: avsi_ctc_loss (posterior
+ *   scatter in shared-memory atomics), the fp32 hole counter of the front end, avsi_istft_fwd's overlap-add. */
+int avsi_set_reduce_scratch(void* scratch, int64_t bytes, void* stream);
+int64_t avsi_reduce_scratch_min_bytes(void);
+int64_t avsi_gemm_f16_scratch_bytes(int M, int N, int K, int trans, int out_mode, int split_k);
+
+/* ------------------------------------------------------------------------------------
  * Persistent bidirectional LSTM recurrence.  Replaces cudnnRNNForwardTraining /
  * BackwardData of tf.contrib.cudnn_rnn.CudnnLSTM (models.py:95-104) and the
  * CudnnCompatibleLSTMCell while-loop (models.py:106-115).  Both directions of one
@@ -222,7 +240,8 @@ int avsi_gemm_f16(const uint16_t* A, int lda, const uint16_t* B, int ldb, void* 
  *   cst   [T*B, 512] f32    out: c_t (stash for BPTT), INTERLEAVED with 4-float chunks ([rows/32][512/4][32][4])
  * Backward: dy [T*B,512] f16 (scaled dL/dy), INTERLEAVED like the gates ([rows/32][512/8][32][8]: a warp's 32 rows x
  * 8 units are 512 contiguous bytes; avsi_gemm_f16 writes it with layout bit 1), whhT [256,2048] f16 (whh^T) -> gates becomes dgates
- * (in place), dbias[2048] f32 += column sums, scratch >= avsi_lstm_bwd_scratch_bytes(B). */
+ * (in place), dbias[2048] f32 += column sums.  scratch (16-byte aligned, >= avsi_lstm_bwd_scratch_bytes(B)) receives one
+ * row of column sums per batch tile, added to dbias in tile order (bit-reproducible); scratch == NULL: fp32 atomics. */
 int avsi_lstm_fwd(uint16_t* gates, const uint16_t* whh, const float* bias, uint16_t* y, float* cst,
                   int T, int B, int y_il, void* stream);
 int64_t avsi_lstm_bwd_scratch_bytes(int B);
@@ -259,7 +278,7 @@ int avsi_head_l1_workspace_bytes(void);
  * out[1] = S*(ctc_weight/B)*holes (CTC dlogits scale), out[2] = 1/(S*holes) (optimiser unscale),
  * out[3] = holes.  loss = loss_hole + ctc_weight * mean_b(nll_b)  (models.py:1955). */
 /* guard (optional): the overflow-guard state below; its dynamic scale multiplies out[0] and out[1]. */
-int avsi_mtl_scales(const float* hole_count, int B, float ctc_weight, float* out, const int32_t* guard,
+int avsi_mtl_scales(const double* hole_count, int B, float ctc_weight, float* out, const int32_t* guard,
                     void* stream);
 
 /* Inverted dropout of the BLSTM outputs ahead of the head(s): tf.nn.dropout(rnn_outputs, rate=dropout_rate) at

@@ -190,7 +190,7 @@ def _frontend_case(B, N, T=None, F=257, with_video=True, frame_ms=24, hop_ms=12,
     video = rng.standard_normal((B, T, V)).astype(np.float32) if with_video else None
     ldx = (F + (V if with_video else 0) + 63) // 64 * 64
     xh = torch.full((T * B, ldx), 9.0, dtype=torch.float16, device=d)
-    hole = torch.zeros(1, dtype=torch.float32, device=d)
+    hole = torch.zeros(1, dtype=torch.float64, device=d)
     res = ap.fused_features(torch.from_numpy(wav).to(d), frame_len, hop, T=T, F=F, mean=mean, std=std, mask=mask,
                             video=video, want_stft=True, want_spec=True, want_feat=True, xh_out=xh, ldx=ldx,
                             hole_count=hole)
@@ -730,7 +730,7 @@ def test_tcgen05_recurrence_data_paths_are_bit_identical(T, B):
     for o in outs[1:]:
         for a, b in zip(outs[0][:4], o[:4]):
             assert torch.equal(a, b)
-        assert torch.allclose(outs[0][4], o[4], rtol=1e-3, atol=1e-2)      # bias gradient: fp32 atomics across clusters
+        assert torch.equal(outs[0][4], o[4])      # bias gradient: per-tile sums reduced in tile order (scratch given)
 
 
 # ------------------------------------------------------------------------------------------ feature statistics (a15)
