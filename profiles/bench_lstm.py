@@ -24,7 +24,7 @@ for B in BS:
     cst = torch.empty(-(-T * B // 32) * 32, 512, device=d)
     dy = torch.randn(-(-T * B // 32) * 32, 512, device=d).half()          # interleaved dL/dy (values are random anyway)
     dbias = torch.zeros(2048, device=d)
-    scratch = torch.empty(16, device=d)
+    scratch = torch.empty(int(lib.avsi_lstm_bwd_scratch_bytes(B)) // 4 + 4, device=d)
 
     def fwd():
         _lib.check(lib.avsi_lstm_fwd(_lib.ptr(gates), _lib.ptr(whh), _lib.ptr(bias), _lib.ptr(y), _lib.ptr(cst), T, B,

@@ -24,7 +24,7 @@ for B in BS:
     whhT = whh.t().contiguous()
     bias = torch.zeros(2048, device=d)
     dy = torch.randn(Mp, 512, device=d).half()
-    scratch = torch.empty(16, device=d)
+    scratch = torch.empty(int(lib.avsi_lstm_bwd_scratch_bytes(B)) // 4 + 4, device=d)
     ref = {}
     if os.environ.get('AVSI_VARIANT_SET', '') == 'r02a':
         variants = [('stg', dict(AVSI_L4_BULK=0, AVSI_B4_LATE=0)), ('stg+late', dict(AVSI_L4_BULK=0, AVSI_B4_LATE=1)),
@@ -48,6 +48,9 @@ for B in BS:
         # BPTT reduce-scatter by st.async straight out of TMEM (no staging / control-thread hop); second chain as two N = 128
         # halves (AVSI_B4_NSPLIT, gone from the code: 1.382 vs 1.323 ms) -- logs r02n_*
         variants = [('default', dict())]
+    # (r02y: forward activations as tanh.approx.f16x2 -- SASS shows two MUFU.TANH.F16 per instruction, no packed MUFU: 1.161 vs
+    # 1.142 ms; with every MUFU compiled out of the cell update (wrong values) the launch still takes 1.121 ms: the XU pipe is
+    # not on the step's critical path.  Log r02y_*, code not kept)
     # (r02u: the forward TMA store again with the first pass's store AHEAD of its pushes and the second BEHIND them: +7 %, log kept)
     else:   # current defaults against the round-1 forms that are still selectable
         on = dict(AVSI_L4_CFENCE=1, AVSI_B4_CFENCE=1, AVSI_L4_BPF=1, AVSI_B4_BPF=1, AVSI_B4_STMA=1)
@@ -89,4 +92,5 @@ for B in BS:
         out.append(row)
         print(json.dumps(row), flush=True)
 _lib.set_env(AVSI_LSTM_FWD=None, AVSI_LSTM_BWD=None, AVSI_L4_BULK=None, AVSI_B4_LATE=None, AVSI_L4_CFENCE=None,
-             AVSI_B4_CFENCE=None, AVSI_L4_BPF=None, AVSI_B4_BPF=None, AVSI_L4_PREFETCH=None, AVSI_B4_PFD=None, AVSI_B4_STMA=None)
+             AVSI_B4_CFENCE=None, AVSI_L4_BPF=None, AVSI_B4_BPF=None, AVSI_L4_PREFETCH=None, AVSI_B4_PFD=None, AVSI_B4_STMA=None,
+             AVSI_LSTM_ACT=None)
