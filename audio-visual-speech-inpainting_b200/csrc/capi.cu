@@ -26,8 +26,13 @@ extern "C" int avsi_set_reduce_scratch(void* scratch, int64_t bytes, void* strea
   }
   AVSI_REQUIRE(((uintptr_t)scratch & 255) == 0, "scratch must be 256-byte aligned");
   AVSI_REQUIRE(bytes >= avsi_reduce_scratch_min_bytes(), "scratch smaller than avsi_reduce_scratch_min_bytes()");
-  // the tickets of the last-block reductions start at zero and reset themselves
+  // the tickets of the last-block reductions start at zero and reset themselves; the zeroing is complete when this call
+  // returns, whichever stream the reductions then run on (not callable inside a stream capture)
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  AVSI_CUDA(cudaStreamIsCapturing((cudaStream_t)stream, &cap));
+  AVSI_REQUIRE(cap == cudaStreamCaptureStatusNone, "not inside a CUDA-graph capture");
   AVSI_CUDA(cudaMemsetAsync(scratch, 0, REDUCE_COUNTER_BYTES, (cudaStream_t)stream));
+  AVSI_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   g_reduce_scratch[dev] = ReduceScratch{reinterpret_cast<unsigned*>(scratch),
                                         reinterpret_cast<unsigned char*>(scratch) + REDUCE_COUNTER_BYTES,
                                         (long long)bytes - REDUCE_COUNTER_BYTES};
