@@ -51,6 +51,7 @@ for B in BS:
     # (r02y: forward activations as tanh.approx.f16x2 -- SASS shows two MUFU.TANH.F16 per instruction, no packed MUFU: 1.161 vs
     # 1.142 ms; with every MUFU compiled out of the cell update (wrong values) the launch still takes 1.121 ms: the XU pipe is
     # not on the step's critical path.  Log r02y_*, code not kept)
+    # (r02y: forward pre-activations through TMA tensor loads + shared memory instead of LDG.128: +4 / +6 %, log kept, code not)
     # (r02u: the forward TMA store again with the first pass's store AHEAD of its pushes and the second BEHIND them: +7 %, log kept)
     else:   # current defaults against the round-1 forms that are still selectable
         on = dict(AVSI_L4_CFENCE=1, AVSI_B4_CFENCE=1, AVSI_L4_BPF=1, AVSI_B4_BPF=1, AVSI_B4_STMA=1)
