@@ -202,11 +202,33 @@ class _NullSpan(object):
 _NULL = _NullSpan()
 
 
+class _NvtxSpan(object):
+    """AVSI_NVTX=1: every span is an NVTX range (`ncu --nvtx --nvtx-include "lstm_bwd/"` then selects a stage of the step by
+    name instead of by kernel regex and launch index)."""
+    __slots__ = ('name',)
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        import torch
+        torch.cuda.nvtx.range_push(self.name)
+        return self
+
+    def __exit__(self, *exc):
+        import torch
+        torch.cuda.nvtx.range_pop()
+        return False
+
+
+_NVTX = os.environ.get('AVSI_NVTX', '0') == '1'
+
+
 def span(name, nbytes=0, flops=0):
     """``with span('lstm_fwd'):`` brackets kernel launches with CUDA events on the current stream
     while profiling is enabled (profile_start / profile_stop)."""
     if _prof is None:
-        return _NULL
+        return _NvtxSpan(name) if _NVTX else _NULL
     return _Span(name, nbytes, flops)
 
 
