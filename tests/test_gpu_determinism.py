@@ -28,7 +28,8 @@ def scratch_state():
 @pytest.mark.parametrize('M,N,K,split', [(2048, 512, 64000, 1),      # CTA-pair kernel, 256 x 512 tiles, library-chosen split
                                          (1024, 256, 40000, 1),      # CTA-pair kernel, 256 x 256 tiles
                                          (291, 500, 3200, 6),        # one-tile kernel, caller's split, ragged M and N
-                                         (64, 40, 640, 32)])         # more splits asked for than k blocks (10): empty splits
+                                         (64, 40, 640, 32),          # more splits asked for than k blocks (10): empty splits
+                                         (130, 37, 2048, 4)])        # odd row length of C: the scalar tail of the reduction
 def test_split_k_gemm_ordered_sum(M, N, K, split, scratch_state):
     blstm = scratch_state
     from avsi_b200 import _lib
