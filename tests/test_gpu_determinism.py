@@ -199,3 +199,21 @@ def test_training_runs_repeat_bit_for_bit(model_name, B, audio_len):
     assert torch.equal(runs[0][0], runs[1][0]), float((runs[0][0] - runs[1][0]).abs().max())
     assert torch.equal(runs[0][1], runs[1][1]) and torch.equal(runs[0][2], runs[1][2])
     assert runs[0][3] == runs[1][3] and all(np.isfinite(runs[0][3]))
+
+
+def test_atomic_mode_of_the_host_still_trains(monkeypatch, scratch_state):
+    """AVSI_DETERMINISTIC=0: nothing is registered, the BPTT kernels get no scratch, the step runs on the atomics of
+    round 1 -- same gradient to summation-order noise."""
+    blstm = scratch_state
+    from test_gpu_model import _build
+    model, _, _, _ = _build('av-blstm', 6, 4800, seed=8)
+    g_ordered = {k: np.array(v) for k, v in model.canonical_gradients().items()}
+    monkeypatch.setenv('AVSI_DETERMINISTIC', '0')
+    blstm.release_reduce_scratch()
+    other, _, _, _ = _build('av-blstm', 6, 4800, seed=8)
+    assert other.engine.workspace(other._fed['masks'].shape[1], 6)['scratch'] is None
+    g_atomic = other.canonical_gradients()
+    assert torch.cuda.current_device() not in blstm._REDUCE
+    a = np.concatenate([g_ordered[k].ravel() for k in sorted(g_ordered)])
+    b = np.concatenate([g_atomic[k].ravel() for k in sorted(g_ordered)])
+    assert np.linalg.norm(a) > 0 and rel_l2(b, a) < 1e-5
