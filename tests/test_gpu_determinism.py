@@ -217,3 +217,25 @@ def test_atomic_mode_of_the_host_still_trains(monkeypatch, scratch_state):
     a = np.concatenate([g_ordered[k].ravel() for k in sorted(g_ordered)])
     b = np.concatenate([g_atomic[k].ravel() for k in sorted(g_ordered)])
     assert np.linalg.norm(a) > 0 and rel_l2(b, a) < 1e-5
+
+
+def test_bench_shape_steps_repeat_bit_for_bit():
+    """The exact bench launch (B = 2048, T = 250: 32 recurrence clusters, 9- and 37-way split-K dW GEMMs, 16 bias-gradient
+    tiles): two steps from the same weights, twice -- identical weights and losses."""
+    from test_gpu_model import _build
+    from avsi_b200 import blstm
+    assert blstm.deterministic()
+    runs = []
+    for _ in range(2):
+        model, _, _, _ = _build('av-blstm', 2048, 48000, seed=12)
+        losses = []
+        for _s in range(2):
+            model.feed()
+            model.train_op()
+            losses.append(float(model.loss))
+        torch.cuda.synchronize()
+        runs.append((model.engine.theta.clone(), losses))
+        del model
+        torch.cuda.empty_cache()
+    assert torch.equal(runs[0][0], runs[1][0]), float((runs[0][0] - runs[1][0]).abs().max())
+    assert runs[0][1] == runs[1][1] and all(np.isfinite(runs[0][1]))
