@@ -41,7 +41,8 @@ def _cudnn_stack(canon, in_dim, hidden, n_layers, device):
 @pytest.mark.parametrize('model_name,B,audio_len', [('av-blstm', 6, 9600),        # mma.sync recurrence kernels, T = 50
                                                     ('a-blstm', 230, 3840),      # tcgen05 kernels, ragged second batch tile
                                                     ('av-blstm', 256, 48000),    # tcgen05 kernels at the GRID length, T = 250
-                                                    ('av-blstm', 2048, 48000)])  # the launch bench.py times: 2048 DISTINCT utterances
+                                                    ('av-blstm', 2048, 48000),   # the launch bench.py times: 2048 DISTINCT utterances
+                                                    ('av-blstm', 256, 320000)])  # 20 s utterances (configs[4]): 1667-step chains
 def test_blstm_stack_matches_cudnn_forward_and_gradients(model_name, B, audio_len):
     from oracle import blstm as oblstm
     assert torch.backends.cudnn.is_available() and torch.backends.cudnn.enabled
