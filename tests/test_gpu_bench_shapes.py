@@ -277,3 +277,37 @@ def test_frontend_bench_launch_2048_distinct_utterances_vs_cufft():
         vid = ovideo.video_features(batch['landmarks'][b].astype(np.float64), T, batch['vmean'][b].astype(np.float64),
                                     batch['vstd'][b].astype(np.float64))
         assert rel_l2(x[b, :, F:].cpu().numpy(), vid) < 1e-3                  # fp16 copy of the z-normed motion vectors
+
+
+def test_ctc_bench_launch_2048_utterances_vs_torch_ctc():
+    """The CTC launch of the AV-MTL-SI bench step (B = 2048 utterances, T = 250 frames, 34 classes, labels padded to 50,
+    blank = last class, unnormalised logits: models.py:1950-1953) against torch.nn.functional.ctc_loss in float64 on the
+    same GPU (the implementation the float64 oracle itself is pinned to on small problems): every utterance's NLL and the
+    whole gradient with respect to the logits."""
+    from avsi_b200 import _lib
+    lib = _lib.load()
+    d = torch.device('cuda:0')
+    T, B, C, Lmax, ldl, col0 = 250, 2048, 34, 50, 320, 257
+    gen = torch.Generator(device='cpu').manual_seed(5)
+    logits = (torch.randn(T * B, ldl, generator=gen) * 2).to(d)
+    lab_len = torch.randint(12, 25, (B,), generator=gen, dtype=torch.int32)
+    labels = torch.randint(0, C - 1, (B, Lmax), generator=gen, dtype=torch.int32)
+    labels[0, 1] = labels[0, 0]                                      # a repeated label: the blank between them is mandatory
+    seq = torch.full((B,), T, dtype=torch.int32)
+    seq[1::7] = T - 9
+    nll = torch.empty(B, device=d)
+    dl = torch.zeros(T * B, ldl, dtype=torch.float16, device=d)
+    ws = torch.empty(int(lib.avsi_ctc_workspace_bytes(B, T, Lmax)) // 4 + 4, device=d)
+    tlab, tll, tsl = labels.to(d), lab_len.to(d), seq.to(d)
+    _lib.check(lib.avsi_ctc_loss(_lib.ptr(logits), ldl, col0, C, _lib.ptr(tlab), Lmax, _lib.ptr(tll), _lib.ptr(tsl), B, T,
+                                 8.0, None, _lib.ptr(nll), _lib.ptr(dl), ldl, col0, _lib.ptr(ws), _lib.stream_ptr()), 'ctc')
+    torch.cuda.synchronize()
+    lg = logits.view(T, B, ldl)[:, :, col0:col0 + C].double().clone().requires_grad_(True)
+    ref = torch.nn.functional.ctc_loss(torch.log_softmax(lg, dim=2), tlab.long(), tsl.long(), tll.long(), blank=C - 1,
+                                       reduction='none', zero_infinity=False)
+    ref.sum().backward()
+    assert torch.allclose(nll.double(), ref.detach(), rtol=2e-5, atol=1e-4)
+    g = dl.view(T, B, ldl)[:, :, col0:col0 + C].double() / 8.0
+    assert float((g - lg.grad).abs().max()) < 2e-3                   # fp16 storage of values in [-1, 1]
+    assert rel_l2(g.cpu().numpy(), lg.grad.cpu().numpy()) < 1e-3
+    assert bool((dl.view(T, B, ldl)[:, :, :col0] == 0).all())
